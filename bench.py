@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json: `MulticlassConfusionMatrix(num_classes=1000)` updated with
+[65536, 1000] bf16 logits (configs[1]); one "step" = one `update()` over one batch = 65,536,000 metric-updates.
+
+    python bench.py --gpus N --steps K --warmup W            # ours (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU op chain on the host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §measurement for how each field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_ROWS, N_CLASSES = 65536, 1000
+UNITS_PER_STEP = N_ROWS * N_CLASSES
+# algorithmic bytes of ONE update launch: logits N*C*2 + target N*8 + one 8-byte counter RMW per row
+ALGO_BYTES_PER_LAUNCH = N_ROWS * N_CLASSES * 2 + N_ROWS * 8 + N_ROWS * 8
+METRIC = "metric-updates/sec (batch x classes)"
+UNIT = "updates/s"
+N_ROT = 4  # distinct device batches rotated through, so no step re-reads what L2 (126 MB) could still hold
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int) -> None:
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self) -> None:
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, v in names.items():
+                    if bits & v:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.004)
+
+    def start(self) -> None:
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self) -> dict:
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+        return {
+            "sm_mhz": statistics.median(self.samples) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+def make_batch(seed: int):
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(N_ROWS, N_CLASSES, generator=g).bfloat16()
+    target = torch.randint(0, N_CLASSES, (N_ROWS,), generator=g)
+    return logits, target
+
+
+# --------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's CPU op chain (oracle port) on the host cores
+# --------------------------------------------------------------------------------------------------------------
+def time_cpu_chain(logits, target, rows: int, steps: int, warmup: int):
+    from oracle.torch_cpu_chain import multiclass_confmat_update_cpu
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    lg, tg = logits[:rows], target[:rows]
+    confmat = torch.zeros(N_CLASSES, N_CLASSES, dtype=torch.long)
+    for _ in range(warmup):
+        multiclass_confmat_update_cpu(confmat, lg, tg, N_CLASSES)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        multiclass_confmat_update_cpu(confmat, lg, tg, N_CLASSES)
+    dt = time.perf_counter() - t0
+    return dt, rows * N_CLASSES * steps / dt, torch.get_num_threads()
+
+
+def run_reference(args) -> dict:
+    logits, target = make_batch(0)
+    # bound the whole run to roughly a minute: full batches cost ~50 ms each on 8 cores
+    budget_s, est_full = 60.0, 0.06
+    rows = N_ROWS
+    while rows > 1024 and args.steps * est_full * rows / N_ROWS > budget_s:
+        rows //= 2
+    dt, ups, threads = time_cpu_chain(logits, target, rows, args.steps, args.warmup)
+    sample = f"{args.steps} update() calls on the first {rows} rows of the seed-0 [65536,1000] bf16 batch"
+    return {
+        "impl": "reference",
+        "metric": METRIC, "value": ups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "MulticlassConfusionMatrix(num_classes=1000).update, [65536,1000] bf16 logits + int64 target",
+                   "rows_per_step": rows, "device": "cpu",
+                   "what": "reference CPU op chain argmax->t*C+p->bincount->+= restated in oracle/torch_cpu_chain.py"},
+        "cpu_baseline": {"value": ups, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": ups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+# --------------------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------------------
+def run_ours(args) -> dict:
+    from metrics_b200 import _native
+    from metrics_b200.classification import MulticlassConfusionMatrix
+
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    distributed = world > 1
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if distributed:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+
+    host = [make_batch(1000 * rank + i) for i in range(N_ROT)]  # rank-distinct synthetic shards
+    dev_batches = [(lg.to(dev), tg.to(dev)) for lg, tg in host]
+    metric = MulticlassConfusionMatrix(num_classes=N_CLASSES, validate_args=False).to(dev)
+
+    def barrier():
+        if distributed:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput (`value`) -------------------------------------------------------------
+    pre = max(args.warmup, 3)
+    for i in range(pre):
+        metric.update(*dev_batches[i % N_ROT])
+    torch.cuda.synchronize(dev)
+    t_spin = time.perf_counter()  # extra untimed spin-up so clocks are at their loaded state
+    while time.perf_counter() - t_spin < 0.25:
+        for i in range(64):
+            metric.update(*dev_batches[i % N_ROT])
+        torch.cuda.synchronize(dev)
+    metric.reset()
+
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    launches0 = _native.launch_count()
+    ev0.record()
+    for i in range(args.steps):
+        metric.update(*dev_batches[i % N_ROT])
+    ev_upd = torch.cuda.Event(enable_timing=True)
+    ev_upd.record()
+    result = metric.compute()  # cross-rank sync of the [C, C] state (one all-reduce) happens here when N > 1
+    ev1.record()
+    barrier()
+    launches = _native.launch_count() - launches0
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    ms_updates = ev0.elapsed_time(ev_upd)
+    assert int(result.sum()) == N_ROWS * args.steps * world, "confusion matrix lost samples"
+
+    times = torch.tensor([ms_total, ms_updates], dtype=torch.float64, device=dev)
+    if distributed:
+        torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
+    ms_total, ms_updates = float(times[0]), float(times[1])
+    value = UNITS_PER_STEP * args.steps * world / (ms_total * 1e-3)
+
+    kernel_ms = ms_updates / args.steps  # one kernel launch per step, back to back on one stream
+    peak, peak_src = measured_peak_gbs()
+    achieved = ALGO_BYTES_PER_LAUNCH / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_confmat_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- end to end through the public API: pinned host -> device -> update -> flag read-back, compute at the end
+    e2e_steps = max(1, min(args.steps, 64))
+    pinned = [(lg.pin_memory(), tg.pin_memory()) for lg, tg in host[:2]]
+    m2 = MulticlassConfusionMatrix(num_classes=N_CLASSES, validate_args=True).to(dev)
+    stage = [(torch.empty_like(dev_batches[0][0]), torch.empty_like(dev_batches[0][1])) for _ in range(2)]
+    for i in range(2):
+        stage[i][0].copy_(pinned[i][0], non_blocking=True)
+        stage[i][1].copy_(pinned[i][1], non_blocking=True)
+        m2.update(*stage[i])
+    m2.reset()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(e2e_steps):
+        s = i % 2
+        stage[s][0].copy_(pinned[s][0], non_blocking=True)
+        stage[s][1].copy_(pinned[s][1], non_blocking=True)
+        m2.update(*stage[s])  # validate_args=True: reads the kernel's 4-byte validation word back every step
+    out_host = m2.compute().cpu()  # the metric result leaves the device
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if distributed:
+        torch.distributed.all_reduce(e2e_ms, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = UNITS_PER_STEP * e2e_steps * world / (float(e2e_ms[0]) * 1e-3)
+    assert int(out_host.sum()) == N_ROWS * e2e_steps * world
+    h2d = N_ROWS * N_CLASSES * 2 + N_ROWS * 8
+    d2h = 4 + (N_CLASSES * N_CLASSES * 8) / e2e_steps
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {
+            "workload": "MulticlassConfusionMatrix(num_classes=1000).update, [65536,1000] bf16 logits + int64 target"
+                        " per GPU per step (BASELINE.json configs[1]); K updates then one compute()",
+            "units_per_step_per_gpu": UNITS_PER_STEP, "validate_args": False,
+            "l2": f"inputs larger than L2: rotating {N_ROT} distinct 131 MB device batches (524 MB > 126 MB L2)",
+            "parallelism": f"dp{world} (independent shards; one int64 all-reduce of the [C,C] state at compute())",
+            "pre_warm": "0.25 s untimed spin-up after the W warm-up steps",
+        },
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "rows_vec_kernel<bf16, ConfmatSink>",
+                     "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_LAUNCH},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "validate_args": True},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        logits0, target0 = make_batch(0)
+        n_cpu = 60
+        dt, ups, threads = time_cpu_chain(logits0, target0, N_ROWS, n_cpu, 3)
+        line["cpu_baseline"] = {
+            "value": ups, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_cpu} update() calls of the full seed-0 [65536,1000] bf16 batch through the reference's CPU "
+                      f"op chain (oracle/torch_cpu_chain.py), {dt:.1f} s",
+        }
+    if distributed:
+        torch.distributed.destroy_process_group()
+    return line if rank == 0 else {}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", 0)) != 0:
+            return
+        print(json.dumps(run_reference(args)), flush=True)
+        return
+    line = run_ours(args)
+    if line:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

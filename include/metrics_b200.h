@@ -1,0 +1,116 @@
+/*
+ * metrics_b200 — C-ABI of the B200 (sm_100a) metric hot path.
+ *
+ * Drop-in boundary for the per-batch update()/compute() arithmetic of TorchMetrics
+ * (reference = PyTorchLightning/metrics @ 1.7.0dev, paths below relative to src/torchmetrics/).
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a CUDA stream handle
+ * (void* == cudaStream_t / CUstream, NULL = legacy default stream) and returns 0 on success or a
+ * negative MB200_ERR_* code; `mb200_last_error()` returns a thread-local message for the last failure.
+ *
+ * All pointers are DEVICE pointers unless a parameter is documented as host memory.
+ * Kernels are enqueued asynchronously on `stream`; no entry point synchronises the host unless stated.
+ * State tensors (`confmat`, `tp` ...) are updated IN PLACE, mirroring `self.confmat += ...` in the
+ * reference classes.  There is no CPU implementation behind this ABI: calling it without a CUDA device
+ * fails with MB200_ERR_CUDA.
+ */
+#ifndef METRICS_B200_H_
+#define METRICS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MB200_API __attribute__((visibility("default")))
+#else
+#define MB200_API
+#endif
+
+/* element types accepted for preds / target buffers */
+enum mb200_dtype {
+    MB200_F32 = 0,
+    MB200_F16 = 1,
+    MB200_BF16 = 2,
+    MB200_F64 = 3,
+    MB200_I64 = 4,
+    MB200_I32 = 5,
+    MB200_I16 = 6,
+    MB200_I8 = 7,
+    MB200_U8 = 8,
+    MB200_BOOL = 9
+};
+
+enum mb200_status {
+    MB200_OK = 0,
+    MB200_ERR_INVALID = -1, /* bad argument (shape, dtype, null pointer) */
+    MB200_ERR_CUDA = -2,    /* CUDA runtime error, message in mb200_last_error() */
+    MB200_ERR_UNSUPPORTED = -3
+};
+
+/* bits OR-ed into the optional device-side `err_flag` word by the update kernels */
+#define MB200_FLAG_TARGET_RANGE 1u /* a non-ignored target label was outside [0, num_classes) */
+#define MB200_FLAG_PREDS_RANGE 2u  /* an integer preds label was outside [0, num_classes)      */
+#define MB200_FLAG_SPIN_TIMEOUT 4u /* internal look-back wait exceeded its bound (results invalid) */
+
+MB200_API int mb200_abi_version(void);
+MB200_API const char* mb200_last_error(void);
+/* number of kernels this library has launched since load (all streams); used by bench.py `gpu_launches` */
+MB200_API uint64_t mb200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1 — multiclass confusion matrix update.
+ * Replaces: functional/classification/confusion_matrix.py:297-328
+ *           (_multiclass_confusion_matrix_format: argmax(dim=1) + flatten + ignore_index drop, then
+ *            _multiclass_confusion_matrix_update: bincount(target*C + preds, C*C).reshape(C, C))
+ *           + utilities/data.py:178-206 (_bincount) + classification/confusion_matrix.py:286
+ *           (`self.confmat += confmat`), fused into ONE pass over the logits.
+ *
+ *  preds        : if preds_has_class_dim != 0: scores laid out [n_outer, num_classes, inner] contiguous
+ *                 (inner = product of trailing dims, 1 for plain [N, C]); floating dtype.
+ *                 else: integer (or floating holding integers is NOT accepted) labels [n_outer*inner].
+ *  target       : integer labels [n_outer * inner]
+ *  confmat      : int64 [num_classes, num_classes], row = target, col = prediction, updated in place
+ *  ignore_index : rows whose target equals it are skipped when has_ignore_index != 0
+ *  err_flag     : optional uint32 device word (may be NULL); MB200_FLAG_* bits are OR-ed in.  Rows with an
+ *                 out-of-range label are skipped (the reference raises from bincount/reshape instead).
+ * argmax semantics == torch.argmax: first index of the maximum, NaN is maximal (first NaN wins), -0 == +0.
+ * ------------------------------------------------------------------------------------------------ */
+MB200_API int mb200_multiclass_confmat_update(const void* preds, int preds_dtype, int preds_has_class_dim,
+                                    const void* target, int target_dtype, int64_t n_outer,
+                                    int64_t num_classes, int64_t inner, int has_ignore_index,
+                                    int64_t ignore_index, int64_t* confmat, uint32_t* err_flag,
+                                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1b — multiclass stat scores update (tp / fp / tn / fn), top_k == 1, multidim_average == "global".
+ * Replaces: functional/classification/stat_scores.py:328-344 (_multiclass_stat_scores_format) and
+ *           :424-448 (_multiclass_stat_scores_update micro + bincount paths) + the in-place state adds of
+ *           classification/stat_scores.py:69-80.  The C*C bincount is never materialised.
+ *
+ *  micro != 0 : tp/fp/tn/fn are int64[1]  (tp = #(p==t), fp = fn = #(p!=t), tn = C*n_valid - tp - fp - fn)
+ *  micro == 0 : tp/fp/tn/fn are int64[num_classes]
+ *  workspace  : int64[3*num_classes + 2] device scratch that MUST be zero on entry; the kernel leaves it
+ *               zeroed again on exit (self-cleaning), so one zero-initialised buffer per metric instance
+ *               can be reused forever.  It must not be shared by calls running concurrently on
+ *               different streams.
+ * ------------------------------------------------------------------------------------------------ */
+MB200_API int mb200_multiclass_stat_scores_update(const void* preds, int preds_dtype, int preds_has_class_dim,
+                                        const void* target, int target_dtype, int64_t n_outer,
+                                        int64_t num_classes, int64_t inner, int has_ignore_index,
+                                        int64_t ignore_index, int micro, int64_t* tp, int64_t* fp,
+                                        int64_t* tn, int64_t* fn, int64_t* workspace,
+                                        uint32_t* err_flag, void* stream);
+
+/* Row argmax only (the `preds.argmax(dim=1)` of the format step) — used by the samplewise / top-k host
+ * paths and by tests to pin tie/NaN semantics.  out: int64 [n_outer * inner]. */
+MB200_API int mb200_argmax_rows(const void* preds, int preds_dtype, int64_t n_outer, int64_t num_classes,
+                      int64_t inner, int64_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METRICS_B200_H_ */

@@ -1,0 +1,208 @@
+"""ctypes binding of the C-ABI in ``include/metrics_b200.h`` (``_lib/libmetrics_b200.so``).
+
+This is the only place where Python crosses into the hand-written sm_100a kernels.  There is deliberately NO
+CPU or PyTorch fallback: if the shared library is missing, or a tensor handed to a kernel wrapper does not
+live on a CUDA device, we raise immediately.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libmetrics_b200.so")
+_lib: Optional[ctypes.CDLL] = None
+
+# enum mb200_dtype
+F32, F16, BF16, F64, I64, I32, I16, I8, U8, BOOL = range(10)
+_DTYPE_TAG = {
+    torch.float32: F32,
+    torch.float16: F16,
+    torch.bfloat16: BF16,
+    torch.float64: F64,
+    torch.int64: I64,
+    torch.int32: I32,
+    torch.int16: I16,
+    torch.int8: I8,
+    torch.uint8: U8,
+    torch.bool: BOOL,
+}
+
+FLAG_TARGET_RANGE = 1
+FLAG_PREDS_RANGE = 2
+FLAG_SPIN_TIMEOUT = 4
+
+
+class NativeLibraryError(RuntimeError):
+    """The CUDA extension is missing or a kernel call failed."""
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the shared library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise NativeLibraryError(
+                f"metrics_b200: CUDA extension not built: {_LIB_PATH} is missing. Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C metrics_b200/csrc`). "
+                "There is no CPU fallback."
+            )
+        handle = ctypes.CDLL(_LIB_PATH)
+        handle.mb200_last_error.restype = ctypes.c_char_p
+        handle.mb200_launch_count.restype = ctypes.c_uint64
+        handle.mb200_abi_version.restype = ctypes.c_int
+        _lib = handle
+    return _lib
+
+
+def launch_count() -> int:
+    return int(lib().mb200_launch_count())
+
+
+def tag(t: Tensor) -> int:
+    try:
+        return _DTYPE_TAG[t.dtype]
+    except KeyError:
+        raise TypeError(f"metrics_b200: unsupported tensor dtype {t.dtype}") from None
+
+
+def require_cuda(*tensors: Tensor) -> torch.device:
+    """All tensors must live on the same CUDA device (the kernels have no host implementation)."""
+    dev = None
+    for t in tensors:
+        if not t.is_cuda:
+            raise NativeLibraryError(
+                "metrics_b200 kernels only run on CUDA tensors (sm_100a); got a tensor on "
+                f"'{t.device}'. Move the metric and its inputs to the GPU: there is no CPU fallback."
+            )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(
+                f"Expected all tensors to be on the same device, but found at least two devices, {dev} and {t.device}!"
+            )
+    return dev
+
+
+class _NoOp:
+    def __enter__(self) -> None:
+        return None
+
+    def __exit__(self, *exc: object) -> None:
+        return None
+
+
+_NOOP = _NoOp()
+
+
+def on_device(device: torch.device):
+    """Context that makes ``device`` current for the launch; free when it already is (the common case)."""
+    if torch.cuda.current_device() == device.index:
+        return _NOOP
+    return torch.cuda.device(device)
+
+
+def ptr(t: Optional[Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream_handle(device: torch.device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def i64(v: int) -> ctypes.c_int64:
+    return ctypes.c_int64(int(v))
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().mb200_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(f"metrics_b200.{what}: {msg}")
+        raise NativeLibraryError(f"metrics_b200.{what} failed (code {rc}): {msg}")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K1 wrappers
+# ----------------------------------------------------------------------------------------------------------
+def _class_dim_geometry(preds: Tensor, has_class_dim: bool) -> tuple[int, int]:
+    """(n_outer, inner) of a contiguous [N, C, ...] (or label [N, ...]) tensor."""
+    if has_class_dim:
+        n_outer = preds.shape[0]
+        inner = 1
+        for s in preds.shape[2:]:
+            inner *= s
+        return n_outer, inner
+    return preds.numel(), 1
+
+
+def multiclass_confmat_update_(
+    confmat: Tensor,
+    preds: Tensor,
+    target: Tensor,
+    num_classes: int,
+    ignore_index: Optional[int],
+    err_flag: Optional[Tensor] = None,
+) -> None:
+    """In-place ``confmat[t, argmax(preds)] += 1`` (``mb200_multiclass_confmat_update``)."""
+    dev = require_cuda(confmat, preds, target)
+    has_class_dim = preds.ndim == target.ndim + 1
+    preds = preds.contiguous()
+    target = target.contiguous()
+    n_outer, inner = _class_dim_geometry(preds, has_class_dim)
+    with on_device(dev):
+        rc = lib().mb200_multiclass_confmat_update(
+            ptr(preds), tag(preds), int(has_class_dim), ptr(target), tag(target), i64(n_outer), i64(num_classes),
+            i64(inner), int(ignore_index is not None), i64(ignore_index or 0), ptr(confmat), ptr(err_flag),
+            stream_handle(dev),
+        )
+    check(rc, "multiclass_confmat_update")
+
+
+def multiclass_stat_scores_update_(
+    tp: Tensor,
+    fp: Tensor,
+    tn: Tensor,
+    fn: Tensor,
+    workspace: Tensor,
+    preds: Tensor,
+    target: Tensor,
+    num_classes: int,
+    ignore_index: Optional[int],
+    micro: bool,
+    err_flag: Optional[Tensor] = None,
+) -> None:
+    """In-place tp/fp/tn/fn accumulation (``mb200_multiclass_stat_scores_update``)."""
+    dev = require_cuda(tp, fp, tn, fn, workspace, preds, target)
+    has_class_dim = preds.ndim == target.ndim + 1
+    preds = preds.contiguous()
+    target = target.contiguous()
+    n_outer, inner = _class_dim_geometry(preds, has_class_dim)
+    with on_device(dev):
+        rc = lib().mb200_multiclass_stat_scores_update(
+            ptr(preds), tag(preds), int(has_class_dim), ptr(target), tag(target), i64(n_outer), i64(num_classes),
+            i64(inner), int(ignore_index is not None), i64(ignore_index or 0), int(micro), ptr(tp), ptr(fp),
+            ptr(tn), ptr(fn), ptr(workspace), ptr(err_flag), stream_handle(dev),
+        )
+    check(rc, "multiclass_stat_scores_update")
+
+
+def argmax_rows(preds: Tensor) -> Tensor:
+    """``preds.argmax(dim=1)`` for a floating [N, C, ...] tensor, torch tie/NaN semantics."""
+    dev = require_cuda(preds)
+    preds = preds.contiguous()
+    n_outer, inner = _class_dim_geometry(preds, True)
+    out = torch.empty((preds.shape[0], *preds.shape[2:]), dtype=torch.int64, device=dev)
+    with on_device(dev):
+        rc = lib().mb200_argmax_rows(
+            ptr(preds), tag(preds), i64(n_outer), i64(preds.shape[1]), i64(inner), ptr(out), stream_handle(dev)
+        )
+    check(rc, "argmax_rows")
+    return out

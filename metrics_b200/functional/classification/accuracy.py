@@ -1,0 +1,67 @@
+"""Accuracy reducers and functionals (reference: functional/classification/accuracy.py)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+from typing_extensions import Literal
+
+from metrics_b200.functional.classification.stat_scores import (
+    _multiclass_stat_scores_arg_validation,
+    _multiclass_stat_scores_tensor_validation,
+    _multiclass_stat_scores_update_,
+    _require_kernel_mode,
+    stat_scores_workspace,
+)
+from metrics_b200.utilities.compute import _adjust_weights_safe_divide, _safe_divide
+
+
+def _accuracy_reduce(
+    tp: Tensor,
+    fp: Tensor,
+    tn: Tensor,
+    fn: Tensor,
+    average: Optional[str],
+    multidim_average: str = "global",
+    multilabel: bool = False,
+    top_k: int = 1,
+) -> Tensor:
+    """tp/fp/tn/fn -> accuracy (reference :37-88).  Counts are widened to f32 and divided once."""
+    axis = 0 if multidim_average == "global" else 1
+    if average == "binary":
+        return _safe_divide(tp + tn, tp + tn + fp + fn)
+    if average == "micro":
+        tp, fn = tp.sum(dim=axis), fn.sum(dim=axis)
+        if not multilabel:
+            return _safe_divide(tp, tp + fn)
+        fp, tn = fp.sum(dim=axis), tn.sum(dim=axis)
+        return _safe_divide(tp + tn, tp + tn + fp + fn)
+    per_class = _safe_divide(tp + tn, tp + tn + fp + fn) if multilabel else _safe_divide(tp, tp + fn)
+    return _adjust_weights_safe_divide(per_class, average, multilabel, tp, fp, fn, top_k)
+
+
+def multiclass_accuracy(
+    preds: Tensor,
+    target: Tensor,
+    num_classes: int,
+    average: Optional[Literal["micro", "macro", "weighted", "none"]] = "macro",
+    top_k: int = 1,
+    multidim_average: Literal["global", "samplewise"] = "global",
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+) -> Tensor:
+    """Multiclass accuracy (reference :263-369)."""
+    if validate_args:
+        _multiclass_stat_scores_arg_validation(num_classes, top_k, average, multidim_average, ignore_index)
+        _multiclass_stat_scores_tensor_validation(preds, target, num_classes, multidim_average, ignore_index)
+    _require_kernel_mode(top_k, multidim_average)
+    micro = average == "micro"
+    states = [torch.zeros(1 if micro else num_classes, dtype=torch.int64, device=preds.device) for _ in range(4)]
+    ws = stat_scores_workspace(num_classes, preds.device)
+    _multiclass_stat_scores_update_(
+        *states, ws, preds, target, num_classes, top_k, average, multidim_average, ignore_index, validate_args
+    )
+    if micro:
+        states = [s.reshape(()) for s in states]
+    return _accuracy_reduce(*states, average=average, multidim_average=multidim_average, top_k=top_k)

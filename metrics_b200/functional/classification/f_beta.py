@@ -1,0 +1,90 @@
+"""F-beta / F1 reducers and functionals (reference: functional/classification/f_beta.py)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+from typing_extensions import Literal
+
+from metrics_b200.functional.classification.stat_scores import (
+    _multiclass_stat_scores_arg_validation,
+    _multiclass_stat_scores_tensor_validation,
+    _multiclass_stat_scores_update_,
+    _require_kernel_mode,
+    stat_scores_workspace,
+)
+from metrics_b200.utilities.compute import _adjust_weights_safe_divide, _safe_divide
+
+
+def _fbeta_reduce(
+    tp: Tensor,
+    fp: Tensor,
+    tn: Tensor,
+    fn: Tensor,
+    beta: float,
+    average: Optional[str],
+    multidim_average: str = "global",
+    multilabel: bool = False,
+    zero_division: float = 0,
+) -> Tensor:
+    """tp/fp/fn -> F-beta (reference :37-58): ``(1+b^2) tp / ((1+b^2) tp + b^2 fn + fp)``."""
+    b2 = beta**2
+    if average == "micro":
+        axis = 0 if multidim_average == "global" else 1
+        tp, fn, fp = tp.sum(dim=axis), fn.sum(dim=axis), fp.sum(dim=axis)
+    score = _safe_divide((1 + b2) * tp, (1 + b2) * tp + b2 * fn + fp, zero_division)
+    if average in ("binary", "micro"):
+        return score
+    return _adjust_weights_safe_divide(score, average, multilabel, tp, fp, fn)
+
+
+def _fbeta_arg_validation(beta: float) -> None:
+    if not (isinstance(beta, float) and beta > 0):
+        raise ValueError(f"Expected argument `beta` to be a float larger than 0, but got {beta}.")
+
+
+def multiclass_fbeta_score(
+    preds: Tensor,
+    target: Tensor,
+    beta: float,
+    num_classes: int,
+    average: Optional[Literal["micro", "macro", "weighted", "none"]] = "macro",
+    top_k: int = 1,
+    multidim_average: Literal["global", "samplewise"] = "global",
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+    zero_division: float = 0,
+) -> Tensor:
+    """Multiclass F-beta (reference :356-470)."""
+    if validate_args:
+        _fbeta_arg_validation(beta)
+        _multiclass_stat_scores_arg_validation(num_classes, top_k, average, multidim_average, ignore_index, zero_division)
+        _multiclass_stat_scores_tensor_validation(preds, target, num_classes, multidim_average, ignore_index)
+    _require_kernel_mode(top_k, multidim_average)
+    micro = average == "micro"
+    states = [torch.zeros(1 if micro else num_classes, dtype=torch.int64, device=preds.device) for _ in range(4)]
+    ws = stat_scores_workspace(num_classes, preds.device)
+    _multiclass_stat_scores_update_(
+        *states, ws, preds, target, num_classes, top_k, average, multidim_average, ignore_index, validate_args
+    )
+    if micro:
+        states = [s.reshape(()) for s in states]
+    return _fbeta_reduce(*states, beta, average=average, multidim_average=multidim_average, zero_division=zero_division)
+
+
+def multiclass_f1_score(
+    preds: Tensor,
+    target: Tensor,
+    num_classes: int,
+    average: Optional[Literal["micro", "macro", "weighted", "none"]] = "macro",
+    top_k: int = 1,
+    multidim_average: Literal["global", "samplewise"] = "global",
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+    zero_division: float = 0,
+) -> Tensor:
+    """Multiclass F1 = F-beta with beta 1 (reference :745-860)."""
+    return multiclass_fbeta_score(
+        preds, target, 1.0, num_classes, average, top_k, multidim_average, ignore_index, validate_args, zero_division
+    )

@@ -1,0 +1,182 @@
+"""Stat-scores (tp / fp / tn / fn) functionals (reference: functional/classification/stat_scores.py).
+
+Multiclass, ``top_k == 1``, ``multidim_average == "global"`` runs in ONE kernel
+(`mb200_multiclass_stat_scores_update`, csrc/confmat.cu): row argmax + per-class counters, never materialising
+the ``C*C`` bincount the reference derives tp/fp/fn/tn from (stat_scores.py:435-448).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+from typing_extensions import Literal
+
+from metrics_b200 import _native
+from metrics_b200.functional.classification._validation import check_multiclass_shapes, new_flag, raise_if_flagged
+
+_AVERAGES = ("micro", "macro", "weighted", "none", None)
+_MULTIDIM = ("global", "samplewise")
+
+
+def _multiclass_stat_scores_arg_validation(
+    num_classes: Optional[int],
+    top_k: int = 1,
+    average: Optional[str] = "macro",
+    multidim_average: str = "global",
+    ignore_index: Optional[int] = None,
+    zero_division: float = 0,
+) -> None:
+    """Non-tensor argument rules (reference :218-262)."""
+    if num_classes is None and average != "micro":
+        raise ValueError(
+            f"Argument `num_classes` can only be `None` for `average='micro'`, but got `average={average}`."
+        )
+    if num_classes is not None and (not isinstance(num_classes, int) or num_classes < 2):
+        raise ValueError(f"Expected argument `num_classes` to be an integer larger than 1, but got {num_classes}")
+    if not isinstance(top_k, int) or top_k < 1:
+        raise ValueError(f"Expected argument `top_k` to be an integer larger than or equal to 1, but got {top_k}")
+    if top_k > (num_classes if num_classes is not None else 1):
+        raise ValueError(
+            f"Expected argument `top_k` to be smaller or equal to `num_classes` but got {top_k} and {num_classes}"
+        )
+    if average not in _AVERAGES:
+        raise ValueError(f"Expected argument `average` to be one of {_AVERAGES}, but got {average}")
+    if multidim_average not in _MULTIDIM:
+        raise ValueError(
+            f"Expected argument `multidim_average` to be one of {_MULTIDIM}, but got {multidim_average}"
+        )
+    if ignore_index is not None and not isinstance(ignore_index, int):
+        raise ValueError(f"Expected argument `ignore_index` to either be `None` or an integer, but got {ignore_index}")
+    if zero_division not in [0, 1]:
+        raise ValueError(f"Expected argument `zero_division` to be 0 or 1, but got {zero_division}.")
+
+
+def _multiclass_stat_scores_tensor_validation(
+    preds: Tensor,
+    target: Tensor,
+    num_classes: Optional[int],
+    multidim_average: str = "global",
+    ignore_index: Optional[int] = None,
+) -> None:
+    """Host-side shape rules (reference :264-314); label values are range-checked inside the kernel."""
+    check_multiclass_shapes(preds, target, num_classes)
+    if multidim_average != "global":
+        if preds.ndim == target.ndim + 1 and preds.ndim < 3:
+            raise ValueError(
+                "If `preds` have one dimension more than `target`, the shape of `preds` should be"
+                " at least 3D when multidim_average is set to `samplewise`"
+            )
+        if preds.ndim == target.ndim and preds.ndim < 2:
+            raise ValueError(
+                "When `preds` and `target` have the same shape, the shape of `preds` should be"
+                " at least 2D when multidim_average is set to `samplewise`"
+            )
+
+
+def _require_kernel_mode(top_k: int, multidim_average: str) -> None:
+    if top_k != 1 or multidim_average != "global":
+        raise NotImplementedError(
+            "metrics_b200: multiclass stat scores currently run on the GPU kernel for `top_k=1` and "
+            f"`multidim_average='global'` only (got top_k={top_k}, multidim_average={multidim_average!r})."
+        )
+
+
+def _multiclass_stat_scores_update_(
+    tp: Tensor,
+    fp: Tensor,
+    tn: Tensor,
+    fn: Tensor,
+    workspace: Tensor,
+    preds: Tensor,
+    target: Tensor,
+    num_classes: int,
+    top_k: int = 1,
+    average: Optional[str] = "macro",
+    multidim_average: str = "global",
+    ignore_index: Optional[int] = None,
+    validate_args: bool = False,
+) -> None:
+    """FUSED format+update: add this batch's tp/fp/tn/fn to the four int64 state tensors in place."""
+    _require_kernel_mode(top_k, multidim_average)
+    flag = new_flag(tp.device) if validate_args else None
+    _native.multiclass_stat_scores_update_(
+        tp, fp, tn, fn, workspace, preds, target, num_classes, ignore_index, average == "micro", flag
+    )
+    if flag is not None:
+        raise_if_flagged(flag, num_classes, ignore_index)
+
+
+def stat_scores_workspace(num_classes: int, device: torch.device) -> Tensor:
+    """Zeroed, self-cleaning scratch required by the stat-scores kernel (see include/metrics_b200.h)."""
+    return torch.zeros(3 * num_classes + 2, dtype=torch.int64, device=device)
+
+
+def _multiclass_stat_scores_update(
+    preds: Tensor,
+    target: Tensor,
+    num_classes: int,
+    top_k: int = 1,
+    average: Optional[str] = "macro",
+    multidim_average: str = "global",
+    ignore_index: Optional[int] = None,
+) -> tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Functional seam (reference :371-449): fresh tp, fp, tn, fn for one batch."""
+    size = () if average == "micro" else (num_classes,)
+    states = [torch.zeros(size if size else (1,), dtype=torch.int64, device=preds.device) for _ in range(4)]
+    ws = stat_scores_workspace(num_classes, preds.device)
+    _multiclass_stat_scores_update_(*states, ws, preds, target, num_classes, top_k, average, multidim_average, ignore_index)
+    if average == "micro":
+        states = [s.reshape(()) for s in states]
+    return states[0], states[1], states[2], states[3]
+
+
+def _multiclass_stat_scores_compute(
+    tp: Tensor,
+    fp: Tensor,
+    tn: Tensor,
+    fn: Tensor,
+    average: Optional[str] = "macro",
+    multidim_average: str = "global",
+) -> Tensor:
+    """Stack ``[tp, fp, tn, fn, support]`` and apply the averaging strategy (reference :452-478)."""
+    res = torch.stack([tp, fp, tn, fn, tp + fn], dim=-1)
+    sum_dim = 0 if multidim_average == "global" else 1
+    if average == "micro":
+        return res.sum(sum_dim) if res.ndim > 1 else res
+    if average == "macro":
+        return res.float().mean(sum_dim)
+    if average == "weighted":
+        weight = tp + fn
+        if multidim_average == "global":
+            return (res * (weight / weight.sum()).reshape(*weight.shape, 1)).sum(sum_dim)
+        return (res * (weight / weight.sum(-1, keepdim=True)).reshape(*weight.shape, 1)).sum(sum_dim)
+    if average is None or average == "none":
+        return res
+    return None
+
+
+def multiclass_stat_scores(
+    preds: Tensor,
+    target: Tensor,
+    num_classes: int,
+    average: Optional[Literal["micro", "macro", "weighted", "none"]] = "macro",
+    top_k: int = 1,
+    multidim_average: Literal["global", "samplewise"] = "global",
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+) -> Tensor:
+    """tp / fp / tn / fn / support for multiclass inputs (reference :481-600)."""
+    if validate_args:
+        _multiclass_stat_scores_arg_validation(num_classes, top_k, average, multidim_average, ignore_index)
+        _multiclass_stat_scores_tensor_validation(preds, target, num_classes, multidim_average, ignore_index)
+    _require_kernel_mode(top_k, multidim_average)
+    micro = average == "micro"
+    states = [torch.zeros(1 if micro else num_classes, dtype=torch.int64, device=preds.device) for _ in range(4)]
+    ws = stat_scores_workspace(num_classes, preds.device)
+    _multiclass_stat_scores_update_(
+        *states, ws, preds, target, num_classes, top_k, average, multidim_average, ignore_index, validate_args
+    )
+    if micro:
+        states = [s.reshape(()) for s in states]
+    return _multiclass_stat_scores_compute(*states, average, multidim_average)

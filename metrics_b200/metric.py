@@ -1,0 +1,853 @@
+"""The metric runtime: state registration, update/compute wrapping, forward, cross-rank sync, checkpointing.
+
+API-compatible with the reference base class (src/torchmetrics/metric.py:52-1311) — same constructor kwargs,
+same public methods, same observable state names — but written for this package:
+
+* states are plain attributes tracked in three dicts (defaults / reduction / persistence);
+* ``sync()`` keeps *references* to the local states instead of cloning them (the reference clones every state,
+  metric.py:611 / :958-971): every reduction here builds new tensors, so ``unsync()`` is free;
+* when no custom ``dist_sync_fn`` is given, ``sync()`` uses the bucketed exchange of
+  ``metrics_b200.parallel_sync`` (one all-reduce for all integer "sum"/"max"/"min" states, one size exchange +
+  one all-gather per "cat" state, no barriers) instead of barrier + shape-gather + data-gather per state
+  (utilities/distributed.py:100-153).  A user ``dist_sync_fn`` is still called once per state tensor.
+"""
+from __future__ import annotations
+
+import builtins
+import functools
+import inspect
+import operator as _op
+from abc import ABC, abstractmethod
+from collections.abc import Generator, Sequence
+from contextlib import contextmanager
+from copy import deepcopy
+from typing import Any, Callable, ClassVar, Dict, List, Optional, Union
+
+import torch
+from torch import Tensor
+from torch.nn import Module
+
+from metrics_b200.utilities.data import (
+    _flatten,
+    _squeeze_if_scalar,
+    apply_to_collection,
+    dim_zero_cat,
+    dim_zero_max,
+    dim_zero_mean,
+    dim_zero_min,
+    dim_zero_sum,
+)
+from metrics_b200.utilities.distributed import gather_all_tensors
+from metrics_b200.utilities.exceptions import TorchMetricsUserError
+from metrics_b200.utilities.prints import rank_zero_warn
+
+_NAMED_REDUCTIONS: Dict[str, Callable] = {
+    "sum": dim_zero_sum,
+    "mean": dim_zero_mean,
+    "max": dim_zero_max,
+    "min": dim_zero_min,
+    "cat": dim_zero_cat,
+}
+_CONST_ATTRS = (
+    "higher_is_better",
+    "is_differentiable",
+    "full_state_update",
+    "plot_lower_bound",
+    "plot_upper_bound",
+    "plot_legend_name",
+)
+_BOOL_KWARGS = (
+    ("compute_on_cpu", False, "an `bool`"),
+    ("dist_sync_on_step", False, "an `bool`"),
+    ("sync_on_compute", True, "a `bool`"),
+    ("compute_with_cache", True, "a `bool`"),
+)
+
+
+def jit_distributed_available() -> bool:
+    """Default ``distributed_available_fn``: is a default process group up?"""
+    return torch.distributed.is_available() and torch.distributed.is_initialized()
+
+
+def _detached_copy(value: Any) -> Any:
+    if isinstance(value, Tensor):
+        return value.detach().clone()
+    return deepcopy(value)
+
+
+class Metric(Module, ABC):
+    """Base class of every metric.  Subclasses implement ``update`` and ``compute`` and register their states with
+    ``add_state``; everything else (device moves, caching, ``forward``, distributed sync, checkpointing, arithmetic
+    composition) is provided here.
+
+    Keyword arguments (reference: metric.py:119-154): ``compute_on_cpu``, ``dist_sync_on_step``, ``process_group``,
+    ``dist_sync_fn``, ``distributed_available_fn``, ``sync_on_compute``, ``compute_with_cache``.
+    """
+
+    __jit_ignored_attributes__: ClassVar[List[str]] = ["device"]
+    __jit_unused_properties__: ClassVar[List[str]] = [
+        "is_differentiable",
+        "higher_is_better",
+        "plot_lower_bound",
+        "plot_upper_bound",
+        "plot_legend_name",
+        "metric_state",
+        "_update_called",
+    ]
+    is_differentiable: Optional[bool] = None
+    higher_is_better: Optional[bool] = None
+    full_state_update: Optional[bool] = None
+    plot_lower_bound: Optional[float] = None
+    plot_upper_bound: Optional[float] = None
+    plot_legend_name: Optional[str] = None
+
+    def __init__(self, **kwargs: Any) -> None:
+        super().__init__()
+        self._device = torch.device("cpu")
+        self._dtype = torch.get_default_dtype()
+
+        for name, default, article in _BOOL_KWARGS:
+            value = kwargs.pop(name, default)
+            if not isinstance(value, bool):
+                raise ValueError(f"Expected keyword argument `{name}` to be {article} but got {value}")
+            setattr(self, name, value)
+        self.process_group = kwargs.pop("process_group", None)
+        self.dist_sync_fn = kwargs.pop("dist_sync_fn", None)
+        if self.dist_sync_fn is not None and not callable(self.dist_sync_fn):
+            raise ValueError(
+                f"Expected keyword argument `dist_sync_fn` to be an callable function but got {self.dist_sync_fn}"
+            )
+        self.distributed_available_fn = kwargs.pop("distributed_available_fn", None) or jit_distributed_available
+        if kwargs:
+            unknown = ", ".join(f"`{k}`" for k in sorted(kwargs))
+            raise ValueError(f"Unexpected keyword arguments: {unknown}")
+
+        self._install_wrappers()
+        self._computed: Any = None
+        self._forward_cache: Any = None
+        self._update_count = 0
+        self._to_sync = self.sync_on_compute
+        self._should_unsync = True
+        self._enable_grad = False
+        self._dtype_convert = False
+
+        self._defaults: Dict[str, Union[list, Tensor]] = {}
+        self._persistent: Dict[str, bool] = {}
+        self._reductions: Dict[str, Union[Callable, None]] = {}
+
+        self._is_synced = False
+        self._cache: Optional[Dict[str, Union[List[Tensor], Tensor]]] = None
+
+    # ------------------------------------------------------------------------------------------------
+    # wrappers around the user-defined update / compute
+    # ------------------------------------------------------------------------------------------------
+    def _install_wrappers(self) -> None:
+        self._update_signature = inspect.signature(self.update)
+        self.update: Callable = self._wrap_update(self.update)  # type: ignore[method-assign]
+        self.compute: Callable = self._wrap_compute(self.compute)  # type: ignore[method-assign]
+
+    def _wrap_update(self, update: Callable) -> Callable:
+        @functools.wraps(update)
+        def wrapped_func(*args: Any, **kwargs: Any) -> None:
+            self._computed = None
+            self._update_count += 1
+            with torch.set_grad_enabled(self._enable_grad):
+                try:
+                    update(*args, **kwargs)
+                except RuntimeError as err:
+                    if "Expected all tensors to be on" in str(err):
+                        name = self.__class__.__name__
+                        raise RuntimeError(
+                            "Encountered different devices in metric calculation (see stacktrace for details)."
+                            " This could be due to the metric class not being on the same device as input."
+                            f" Instead of `metric={name}(...)` try to do"
+                            f" `metric={name}(...).to(device)` where"
+                            " device corresponds to the device of the input."
+                        ) from err
+                    raise err
+            if self.compute_on_cpu:
+                self._move_list_states_to_cpu()
+
+        return wrapped_func
+
+    def _wrap_compute(self, compute: Callable) -> Callable:
+        @functools.wraps(compute)
+        def wrapped_func(*args: Any, **kwargs: Any) -> Any:
+            if not self.update_called:
+                rank_zero_warn(
+                    f"The ``compute`` method of metric {self.__class__.__name__}"
+                    " was called before the ``update`` method which may lead to errors,"
+                    " as metric states have not yet been updated.",
+                    UserWarning,
+                )
+            if self._computed is not None:
+                return self._computed
+            with self.sync_context(
+                dist_sync_fn=self.dist_sync_fn,
+                should_sync=self._to_sync,
+                should_unsync=self._should_unsync,
+            ):
+                value = _squeeze_if_scalar(compute(*args, **kwargs))
+                # results must not alias the states: later in-place updates would silently change them
+                value = apply_to_collection(value, Tensor, lambda t: t.clone())
+            if self.compute_with_cache:
+                self._computed = value
+            return value
+
+        return wrapped_func
+
+    @abstractmethod
+    def update(self, *_: Any, **__: Any) -> None:
+        """Fold one batch into the metric states."""
+
+    @abstractmethod
+    def compute(self) -> Any:
+        """Produce the metric value from the (possibly synchronised) states."""
+
+    # ------------------------------------------------------------------------------------------------
+    # bookkeeping properties
+    # ------------------------------------------------------------------------------------------------
+    @property
+    def _update_called(self) -> bool:
+        rank_zero_warn(
+            "This property will be removed in 2.0.0. Use `Metric.updated_called` instead.",
+            DeprecationWarning,
+            stacklevel=2,
+        )
+        return self.update_called
+
+    @property
+    def update_called(self) -> bool:
+        return self._update_count > 0
+
+    @property
+    def update_count(self) -> int:
+        return self._update_count
+
+    @property
+    def metric_state(self) -> Dict[str, Union[List[Tensor], Tensor]]:
+        return {name: getattr(self, name) for name in self._defaults}
+
+    @property
+    def device(self) -> "torch.device":
+        return self._device
+
+    @property
+    def dtype(self) -> "torch.dtype":
+        return self._dtype
+
+    # ------------------------------------------------------------------------------------------------
+    # state registration / reset
+    # ------------------------------------------------------------------------------------------------
+    def add_state(
+        self,
+        name: str,
+        default: Union[list, Tensor],
+        dist_reduce_fx: Optional[Union[str, Callable]] = None,
+        persistent: bool = False,
+    ) -> None:
+        """Register a state: a tensor (reset to ``default``) or an initially empty list (reset to empty).
+
+        ``dist_reduce_fx`` is one of "sum" | "mean" | "max" | "min" | "cat" | callable | None and decides how the
+        per-rank copies are merged in ``sync`` (and how ``forward``/``merge_state`` fold two states together).
+        Reference: metric.py:201-284.
+        """
+        if isinstance(default, list):
+            if default:
+                raise ValueError("state variable must be a tensor or any empty list (where you can append tensors)")
+        elif not isinstance(default, Tensor):
+            raise ValueError("state variable must be a tensor or any empty list (where you can append tensors)")
+
+        if isinstance(dist_reduce_fx, str):
+            if dist_reduce_fx not in _NAMED_REDUCTIONS:
+                raise ValueError(
+                    "`dist_reduce_fx` must be callable or one of ['mean', 'sum', 'cat', 'min', 'max', None]"
+                )
+            reduction: Optional[Callable] = _NAMED_REDUCTIONS[dist_reduce_fx]
+        elif dist_reduce_fx is None or callable(dist_reduce_fx):
+            reduction = dist_reduce_fx
+        else:
+            raise ValueError("`dist_reduce_fx` must be callable or one of ['mean', 'sum', 'cat', 'min', 'max', None]")
+
+        if isinstance(default, Tensor):
+            default = default.contiguous()
+        setattr(self, name, default)
+        self._defaults[name] = deepcopy(default)
+        self._persistent[name] = persistent
+        self._reductions[name] = reduction
+
+    def reset(self) -> None:
+        """Back to the registered defaults (tensor states re-created on their current device, lists emptied)."""
+        self._update_count = 0
+        self._forward_cache = None
+        self._computed = None
+        for name, default in self._defaults.items():
+            current = getattr(self, name)
+            if isinstance(default, Tensor):
+                setattr(self, name, default.detach().clone().to(current.device))
+            else:
+                current.clear()
+        self._cache = None
+        self._is_synced = False
+
+    def _snapshot_states(self) -> Dict[str, Union[Tensor, List[Any]]]:
+        """Deep, autograd-detached copy of all states (used by ``forward``)."""
+        snap: Dict[str, Union[Tensor, List[Any]]] = {}
+        for name in self._defaults:
+            value = getattr(self, name)
+            snap[name] = _detached_copy(value) if isinstance(value, Tensor) else [_detached_copy(v) for v in value]
+        return snap
+
+    # kept under the reference's private name as well: wrappers/tests reach for it
+    _copy_state_dict = _snapshot_states
+
+    def _move_list_states_to_cpu(self) -> None:
+        for name in self._defaults:
+            value = getattr(self, name)
+            if isinstance(value, Sequence):
+                setattr(self, name, [v.to("cpu") for v in value])
+
+    # ------------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------------
+    @torch.jit.unused
+    def forward(self, *args: Any, **kwargs: Any) -> Any:
+        """Accumulate the batch into the global state AND return the metric of this batch alone.
+
+        Reference: metric.py:286-402.  ``full_state_update`` (or ``dist_sync_on_step``) selects the two-update
+        strategy, otherwise the batch state is computed once and merged into the global state.
+        """
+        if self._is_synced:
+            raise TorchMetricsUserError(
+                "The Metric shouldn't be synced when performing ``forward``. HINT: Did you forget to call ``unsync`` ?."
+            )
+        if self.full_state_update or self.full_state_update is None or self.dist_sync_on_step:
+            self._forward_cache = self._forward_full_state_update(*args, **kwargs)
+        else:
+            self._forward_cache = self._forward_reduce_state_update(*args, **kwargs)
+        return self._forward_cache
+
+    def _enter_batch_mode(self) -> bool:
+        self._to_sync = self.dist_sync_on_step
+        self._should_unsync = False
+        saved_cpu_flag = self.compute_on_cpu
+        self.compute_on_cpu = False
+        self._enable_grad = True
+        return saved_cpu_flag
+
+    def _leave_batch_mode(self, saved_cpu_flag: bool) -> None:
+        self._is_synced = False
+        self._should_unsync = True
+        self._to_sync = self.sync_on_compute
+        self._computed = None
+        self._enable_grad = False
+        self.compute_on_cpu = saved_cpu_flag
+        if self.compute_on_cpu:
+            self._move_list_states_to_cpu()
+
+    def _forward_full_state_update(self, *args: Any, **kwargs: Any) -> Any:
+        """update(global) ; save ; reset ; update(batch) ; compute ; restore."""
+        self.update(*args, **kwargs)
+        count = self._update_count
+        saved_cpu_flag = self._enter_batch_mode()
+        saved = self._snapshot_states()
+
+        self.reset()
+        self.update(*args, **kwargs)
+        batch_val = self.compute()
+
+        for name, value in saved.items():
+            setattr(self, name, value)
+        self._update_count = count
+        self._leave_batch_mode(saved_cpu_flag)
+        return batch_val
+
+    def _forward_reduce_state_update(self, *args: Any, **kwargs: Any) -> Any:
+        """save ; reset ; update(batch) ; compute ; merge saved global state back in."""
+        global_state = self._snapshot_states()
+        count = self._update_count
+        self.reset()
+        saved_cpu_flag = self._enter_batch_mode()
+
+        self.update(*args, **kwargs)
+        batch_val = self.compute()
+
+        self._update_count = count + 1
+        with torch.no_grad():
+            self._reduce_states(global_state)
+        self._leave_batch_mode(saved_cpu_flag)
+        return batch_val
+
+    # ------------------------------------------------------------------------------------------------
+    # merging states
+    # ------------------------------------------------------------------------------------------------
+    def merge_state(self, incoming_state: Union[Dict[str, Any], "Metric"]) -> None:
+        """Fold another metric's state (instance of the same class, or a state dict) into this one."""
+        if not isinstance(incoming_state, (dict, Metric)):
+            raise ValueError(
+                f"Expected incoming state to be a dict or an instance of Metric but got {type(incoming_state)}"
+            )
+        if self.full_state_update or self.full_state_update is None or self.dist_sync_on_step:
+            raise RuntimeError(
+                "``merge_state`` is not supported for metrics with ``full_state_update=True`` or "
+                "``dist_sync_on_step=True``. Please overwrite the merge_state method in the metric class."
+            )
+        if isinstance(incoming_state, Metric):
+            if not isinstance(incoming_state, self.__class__):
+                raise ValueError(
+                    f"Expected incoming state to be an instance of {self.__class__.__name__} but got"
+                    f" {type(incoming_state)}"
+                )
+            incoming_state = incoming_state.metric_state
+        self._reduce_states(incoming_state)
+
+    def _reduce_states(self, incoming_state: Dict[str, Any]) -> None:
+        """state := reduce(incoming ("global"), current ("local")) per registered reduction (metric.py:465-499)."""
+        for name in self._defaults:
+            if name not in incoming_state:
+                raise ValueError(f"Expected state variable {name} to be present in incoming state {incoming_state}")
+            local, glob = getattr(self, name), incoming_state[name]
+            fn = self._reductions[name]
+            if fn is dim_zero_sum:
+                merged = glob + local
+            elif fn is dim_zero_mean:
+                merged = ((self._update_count - 1) * glob + local).float() / self._update_count
+            elif fn is dim_zero_max:
+                merged = torch.max(glob, local)
+            elif fn is dim_zero_min:
+                merged = torch.min(glob, local)
+            elif fn is dim_zero_cat:
+                merged = torch.cat([glob, local]) if isinstance(glob, Tensor) else glob + local
+            elif fn is None and isinstance(glob, Tensor):
+                merged = torch.stack([glob, local])
+            elif fn is None and isinstance(glob, list):
+                merged = _flatten([glob, local])
+            elif callable(fn):
+                merged = fn(torch.stack([glob, local]))
+            else:
+                raise TypeError(f"Unsupported reduce_fn: {fn}")
+            setattr(self, name, merged)
+
+    # ------------------------------------------------------------------------------------------------
+    # distributed sync
+    # ------------------------------------------------------------------------------------------------
+    def _sync_dist(self, dist_sync_fn: Callable = gather_all_tensors, process_group: Optional[Any] = None) -> None:
+        """Gather every state from every rank with ``dist_sync_fn`` (once per state tensor) and reduce locally.
+
+        Contract of the hook (reference metric.py:501-540, utilities/distributed.py:100-153):
+        ``dist_sync_fn(tensor, group=...) -> list[Tensor]`` with one entry per rank.
+        """
+        group = process_group or self.process_group
+        staged: Dict[str, Any] = {}
+        for name, fn in self._reductions.items():
+            value = getattr(self, name)
+            if fn is dim_zero_cat and isinstance(value, list):
+                if len(value) > 1:
+                    value = [dim_zero_cat(value)]  # one collective per state, not per list element
+                elif len(value) == 0:
+                    # this rank saw no data: contribute an empty tensor so the collective still matches up
+                    value = [torch.tensor([], device=self.device, dtype=self.dtype)]
+            staged[name] = value
+
+        gathered = apply_to_collection(staged, Tensor, dist_sync_fn, group=group)
+
+        for name, fn in self._reductions.items():
+            out = gathered[name]
+            if isinstance(out, list) and len(out) == 0:
+                setattr(self, name, [])
+                continue
+            if isinstance(out[0], Tensor):
+                out = torch.stack(out)
+            elif isinstance(out[0], list):
+                out = _flatten(out)
+            if not (callable(fn) or fn is None):
+                raise TypeError("reduction_fn must be callable or None")
+            setattr(self, name, fn(out) if fn is not None else out)
+
+    def sync(
+        self,
+        dist_sync_fn: Optional[Callable] = None,
+        process_group: Optional[Any] = None,
+        should_sync: bool = True,
+        distributed_available: Optional[Callable] = None,
+    ) -> None:
+        """Replace the local states by their cross-rank reduction until ``unsync`` (metric.py:573-615)."""
+        if self._is_synced and should_sync:
+            raise TorchMetricsUserError("The Metric has already been synced.")
+        if distributed_available is None and self.distributed_available_fn is not None:
+            distributed_available = self.distributed_available_fn
+        is_distributed = distributed_available() if callable(distributed_available) else None
+        if not should_sync or not is_distributed:
+            return
+
+        # Local states are kept by reference: every reduction below allocates new tensors.
+        self._cache = {name: getattr(self, name) for name in self._defaults}
+        self._cache = {k: (list(v) if isinstance(v, list) else v) for k, v in self._cache.items()}
+
+        if dist_sync_fn is None:
+            from metrics_b200.parallel_sync import sync_states_bucketed
+
+            if not sync_states_bucketed(self, process_group or self.process_group):
+                self._sync_dist(gather_all_tensors, process_group=process_group)
+        else:
+            self._sync_dist(dist_sync_fn, process_group=process_group)
+        self._is_synced = True
+
+    def unsync(self, should_unsync: bool = True) -> None:
+        """Restore the local (pre-sync) states (metric.py:617-637)."""
+        if not should_unsync:
+            return
+        if not self._is_synced:
+            raise TorchMetricsUserError("The Metric has already been un-synced.")
+        if self._cache is None:
+            raise TorchMetricsUserError("The internal cache should exist to unsync the Metric.")
+        for name, value in self._cache.items():
+            setattr(self, name, value)
+        self._is_synced = False
+        self._cache = None
+
+    @contextmanager
+    def sync_context(
+        self,
+        dist_sync_fn: Optional[Callable] = None,
+        process_group: Optional[Any] = None,
+        should_sync: bool = True,
+        should_unsync: bool = True,
+        distributed_available: Optional[Callable] = None,
+    ) -> Generator:
+        """``sync`` on entry, ``unsync`` on exit (if a sync actually happened)."""
+        self.sync(
+            dist_sync_fn=dist_sync_fn,
+            process_group=process_group,
+            should_sync=should_sync,
+            distributed_available=distributed_available,
+        )
+        yield
+        self.unsync(should_unsync=self._is_synced and should_unsync)
+
+    # ------------------------------------------------------------------------------------------------
+    # copying / pickling / constants
+    # ------------------------------------------------------------------------------------------------
+    def clone(self) -> "Metric":
+        return deepcopy(self)
+
+    def __getstate__(self) -> Dict[str, Any]:
+        skip = ("update", "compute", "_update_signature")
+        return {k: v for k, v in self.__dict__.items() if k not in skip}
+
+    def __setstate__(self, state: Dict[str, Any]) -> None:
+        self.__dict__.update(state)
+        self._install_wrappers()
+
+    def __setattr__(self, name: str, value: Any) -> None:
+        if name in _CONST_ATTRS:
+            raise RuntimeError(f"Can't change const `{name}`.")
+        super().__setattr__(name, value)
+
+    def plot(self, *_: Any, **__: Any) -> Any:
+        raise NotImplementedError("plotting is outside the scope of metrics_b200 (matplotlib front-end not ported)")
+
+    # ------------------------------------------------------------------------------------------------
+    # dtype / device handling
+    # ------------------------------------------------------------------------------------------------
+    def type(self, dst_type: Union[str, torch.dtype]) -> "Metric":  # noqa: A003
+        """No-op by design: use ``set_dtype`` (reference metric.py:823-853)."""
+        return self
+
+    def float(self) -> "Metric":
+        return self
+
+    def double(self) -> "Metric":
+        return self
+
+    def half(self) -> "Metric":
+        return self
+
+    def set_dtype(self, dst_type: Union[str, torch.dtype]) -> "Metric":
+        """The one sanctioned way to change the dtype of floating states."""
+        self._dtype_convert = True
+        out = super().type(dst_type)
+        out._dtype_convert = False
+        return out
+
+    def _apply(self, fn: Callable, exclude_state: Sequence[str] = "") -> Module:
+        """Extend ``nn.Module._apply`` (``.to()``, ``.cuda()`` ...) to states, defaults and cached results."""
+        this = super()._apply(fn)
+        is_dtype_move = any(
+            tok in str(fn) for tok in ("Module.type", "Module.half", "Module.float", "Module.double", "Module.bfloat16")
+        )
+        if is_dtype_move and not self._dtype_convert:
+            return this
+
+        for name, default in this._defaults.items():
+            if name in exclude_state:
+                continue
+            if isinstance(default, Tensor):
+                this._defaults[name] = fn(default)
+            elif isinstance(default, Sequence):
+                this._defaults[name] = [fn(v) for v in default]
+            current = getattr(this, name)
+            if isinstance(current, Tensor):
+                setattr(this, name, fn(current))
+            elif isinstance(current, Sequence):
+                setattr(this, name, [fn(v) for v in current])
+            else:
+                raise TypeError(
+                    f"Expected metric state to be either a Tensor or a list of Tensor, but encountered {current}"
+                )
+
+        probe = fn(torch.zeros(1, device=self.device))
+        self._device = probe.device
+        self._dtype = probe.dtype
+
+        if this._computed is not None:
+            this._computed = apply_to_collection(this._computed, Tensor, fn)
+        if this._forward_cache is not None:
+            this._forward_cache = apply_to_collection(this._forward_cache, Tensor, fn)
+        return this
+
+    # ------------------------------------------------------------------------------------------------
+    # checkpointing
+    # ------------------------------------------------------------------------------------------------
+    def persistent(self, mode: bool = False) -> None:
+        for name in self._persistent:
+            self._persistent[name] = mode
+
+    def state_dict(  # type: ignore[override]
+        self,
+        destination: Optional[Dict[str, Any]] = None,
+        prefix: str = "",
+        keep_vars: bool = False,
+    ) -> Dict[str, Any]:
+        destination = super().state_dict(destination=destination, prefix=prefix, keep_vars=keep_vars)  # type: ignore[arg-type]
+        for name in self._defaults:
+            if not self._persistent[name]:
+                continue
+            value = getattr(self, name)
+            if not keep_vars:
+                if isinstance(value, Tensor):
+                    value = value.detach()
+                elif isinstance(value, list):
+                    value = [v.detach() if isinstance(v, Tensor) else v for v in value]
+            destination[prefix + name] = deepcopy(value)
+        return destination
+
+    def _load_from_state_dict(
+        self,
+        state_dict: dict,
+        prefix: str,
+        local_metadata: dict,
+        strict: bool,
+        missing_keys: List[str],
+        unexpected_keys: List[str],
+        error_msgs: List[str],
+    ) -> None:
+        for name in self._defaults:
+            key = prefix + name
+            if key in state_dict:
+                setattr(self, name, state_dict.pop(key))
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, True, missing_keys, unexpected_keys, error_msgs)
+
+    def _filter_kwargs(self, **kwargs: Any) -> Dict[str, Any]:
+        """Keep only the kwargs that ``update`` can take (used by ``MetricCollection``)."""
+        params = self._update_signature.parameters
+        variadic = (inspect.Parameter.VAR_POSITIONAL, inspect.Parameter.VAR_KEYWORD)
+        if any(p.kind == inspect.Parameter.VAR_KEYWORD for p in params.values()):
+            return kwargs
+        return {k: v for k, v in kwargs.items() if k in params and params[k].kind not in variadic}
+
+    def __hash__(self) -> int:
+        parts: List[Any] = [self.__class__.__name__, id(self)]
+        for name in self._defaults:
+            value = getattr(self, name)
+            if hasattr(value, "__iter__") and not isinstance(value, Tensor):
+                parts.extend(value)
+            else:
+                parts.append(value)
+        return hash(tuple(parts))
+
+    # ------------------------------------------------------------------------------------------------
+    # arithmetic composition
+    # ------------------------------------------------------------------------------------------------
+    def _binary(self, fn: Callable, other: Any, reflected: bool = False) -> "CompositionalMetric":
+        return CompositionalMetric(fn, other, self) if reflected else CompositionalMetric(fn, self, other)
+
+    def __add__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.add, other)
+
+    def __radd__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.add, other, True)
+
+    def __sub__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.sub, other)
+
+    def __rsub__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.sub, other, True)
+
+    def __mul__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.mul, other)
+
+    def __rmul__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.mul, other, True)
+
+    def __truediv__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.true_divide, other)
+
+    def __rtruediv__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.true_divide, other, True)
+
+    def __floordiv__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.floor_divide, other)
+
+    def __rfloordiv__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.floor_divide, other, True)
+
+    def __mod__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.fmod, other)
+
+    def __rmod__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.fmod, other, True)
+
+    def __pow__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.pow, other)
+
+    def __rpow__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.pow, other, True)
+
+    def __matmul__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.matmul, other)
+
+    def __rmatmul__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.matmul, other, True)
+
+    def __and__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.bitwise_and, other)
+
+    def __rand__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.bitwise_and, other, True)
+
+    def __or__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.bitwise_or, other)
+
+    def __ror__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.bitwise_or, other, True)
+
+    def __xor__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.bitwise_xor, other)
+
+    def __rxor__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.bitwise_xor, other, True)
+
+    def __eq__(self, other: Any) -> "CompositionalMetric":  # type: ignore[override]
+        return self._binary(torch.eq, other)
+
+    def __ne__(self, other: Any) -> "CompositionalMetric":  # type: ignore[override]
+        return self._binary(torch.ne, other)
+
+    def __ge__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.ge, other)
+
+    def __gt__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.gt, other)
+
+    def __le__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.le, other)
+
+    def __lt__(self, other: Any) -> "CompositionalMetric":
+        return self._binary(torch.lt, other)
+
+    def __abs__(self) -> "CompositionalMetric":
+        return CompositionalMetric(torch.abs, self, None)
+
+    def __neg__(self) -> "CompositionalMetric":
+        return CompositionalMetric(lambda x: -torch.abs(x), self, None)
+
+    def __pos__(self) -> "CompositionalMetric":
+        return CompositionalMetric(torch.abs, self, None)
+
+    def __invert__(self) -> "CompositionalMetric":
+        return CompositionalMetric(torch.bitwise_not, self, None)
+
+    def __inv__(self) -> "CompositionalMetric":
+        return self.__invert__()
+
+    def __getitem__(self, idx: Any) -> "CompositionalMetric":
+        return CompositionalMetric(lambda x: x[idx], self, None)
+
+    def __getnewargs__(self) -> tuple:
+        return tuple(Metric.__str__(self))
+
+    __iter__ = None
+
+
+def _as_operand(value: Any) -> Any:
+    if isinstance(value, (builtins.int, builtins.float)):
+        return torch.tensor(value)
+    return value
+
+
+class CompositionalMetric(Metric):
+    """Lazy ``operator(metric_a, metric_b)`` (reference: metric.py:1188-1311).
+
+    Update/reset/persistent fan out to the operand metrics, ``compute`` applies the operator to their results.
+    It owns no state and never syncs by itself (the operands sync themselves).
+    """
+
+    def __init__(self, operator: Callable, metric_a: Any, metric_b: Any) -> None:
+        super().__init__()
+        self.op = operator
+        for slot, operand in (("metric_a", _as_operand(metric_a)), ("metric_b", _as_operand(metric_b))):
+            if isinstance(operand, Tensor):
+                self.register_buffer(slot, operand, persistent=False)
+            else:
+                setattr(self, slot, operand)
+
+    def _sync_dist(self, dist_sync_fn: Optional[Callable] = None, process_group: Optional[Any] = None) -> None:
+        return None
+
+    def sync(self, *args: Any, **kwargs: Any) -> None:  # operands sync themselves inside their own compute()
+        return None
+
+    def unsync(self, should_unsync: bool = True) -> None:
+        return None
+
+    def update(self, *args: Any, **kwargs: Any) -> None:
+        for operand in (self.metric_a, self.metric_b):
+            if isinstance(operand, Metric):
+                operand.update(*args, **operand._filter_kwargs(**kwargs))
+
+    def compute(self) -> Any:
+        a = self.metric_a.compute() if isinstance(self.metric_a, Metric) else self.metric_a
+        b = self.metric_b.compute() if isinstance(self.metric_b, Metric) else self.metric_b
+        if b is None:
+            return self.op(a)
+        return self.op(a, b)
+
+    @torch.jit.unused
+    def forward(self, *args: Any, **kwargs: Any) -> Any:
+        a = self.metric_a(*args, **self.metric_a._filter_kwargs(**kwargs)) if isinstance(self.metric_a, Metric) else self.metric_a
+        b = self.metric_b(*args, **self.metric_b._filter_kwargs(**kwargs)) if isinstance(self.metric_b, Metric) else self.metric_b
+        if a is None:
+            self._forward_cache = None
+        elif b is None:
+            self._forward_cache = None if isinstance(self.metric_b, Metric) else self.op(a)
+        else:
+            self._forward_cache = self.op(a, b)
+        return self._forward_cache
+
+    def reset(self) -> None:
+        for operand in (self.metric_a, self.metric_b):
+            if isinstance(operand, Metric):
+                operand.reset()
+
+    def persistent(self, mode: bool = False) -> None:
+        for operand in (self.metric_a, self.metric_b):
+            if isinstance(operand, Metric):
+                operand.persistent(mode=mode)
+
+    def __repr__(self) -> str:
+        name = getattr(self.op, "__name__", repr(self.op))
+        return f"{self.__class__.__name__}(\n  {name}(\n    {self.metric_a!r},\n    {self.metric_b!r}\n  )\n)"
+
+    def _wrap_compute(self, compute: Callable) -> Callable:
+        return compute

@@ -1,0 +1,201 @@
+"""Generate golden vectors from the UNMODIFIED reference (TorchMetrics under /root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+The reference is imported from /root/reference/src through the documented stand-in for its missing
+`lightning_utilities` dependency (tests/golden/_standins/).  No reference source is copied
+or modified.  Inputs that are too large to commit are regenerated from their seed by the tests and pinned by a
+sha256 of their bytes stored here.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "_standins"))
+sys.path.insert(0, "/root/reference/src")
+
+import torchmetrics  # noqa: E402
+from torchmetrics.classification import (  # noqa: E402
+    MulticlassAccuracy,
+    MulticlassConfusionMatrix,
+    MulticlassF1Score,
+    MulticlassStatScores,
+)
+from torchmetrics.functional.classification import (  # noqa: E402
+    multiclass_accuracy,
+    multiclass_confusion_matrix,
+    multiclass_f1_score,
+    multiclass_fbeta_score,
+    multiclass_stat_scores,
+)
+
+
+def sha(t: torch.Tensor) -> str:
+    t = t.contiguous()
+    if t.dtype == torch.bfloat16:
+        t = t.view(torch.int16)
+    return hashlib.sha256(t.numpy().tobytes()).hexdigest()
+
+
+def np_of(t: torch.Tensor) -> np.ndarray:
+    if t.dtype in (torch.bfloat16, torch.float16):
+        return t.float().numpy()
+    return t.numpy()
+
+
+def edge_rows(C: int) -> torch.Tensor:
+    """Adversarial rows for argmax: ties, NaN, +-inf, signed zeros, max in the last / first column."""
+    g = torch.Generator().manual_seed(100 + C)
+    rows = [torch.randn(C, generator=g) for _ in range(24)]
+    nan, inf = float("nan"), float("inf")
+    r = rows
+    r[0][:] = 1.0  # all equal -> 0
+    r[1][C // 2] = 50.0
+    r[1][C - 1] = 50.0  # tie -> first
+    r[2][C - 1] = 99.0  # max in last column
+    r[3][0] = 99.0
+    r[4][C // 3] = nan  # NaN is max
+    r[5][C // 3] = nan
+    r[5][C - 1] = nan  # first NaN wins
+    r[6][1] = inf
+    r[6][C - 2] = inf
+    r[7][:] = -inf  # all -inf -> 0
+    r[8][:] = -1.0
+    r[8][2] = -0.0
+    r[8][C - 1] = 0.0  # -0.0 == 0.0, first wins
+    r[9][:] = -1.0
+    r[9][C - 1] = -0.0
+    r[10][2] = inf
+    r[10][1] = nan  # NaN beats inf
+    r[11][:] = nan
+    r[12][C - 1] = nan
+    r[13][:] = -inf
+    r[13][C - 1] = -1e30
+    r[14][:] = 0.0
+    r[14][C // 2] = 1e-30  # f32 denormal-ish / underflows to 0 in f16
+    return torch.stack(rows)
+
+
+def classification_golden() -> dict:
+    out: dict = {}
+
+    # ---- A. argmax edge semantics per dtype and row width -------------------------------------------------------
+    for C in (4, 37, 64, 1000, 1024, 2500):
+        base = edge_rows(C)
+        for name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16), ("f16", torch.float16), ("f64", torch.float64)):
+            x = base.to(dt)
+            out[f"argmax/{name}/C{C}/x"] = np_of(x) if dt != torch.float64 else x.numpy()
+            out[f"argmax/{name}/C{C}/y"] = x.argmax(dim=1).numpy()
+
+    # ---- B. confusion matrix cases ----------------------------------------------------------------------------------
+    g = torch.Generator().manual_seed(7)
+    for C, N in ((5, 128), (37, 512), (130, 2048)):
+        logits = torch.randn(N, C, generator=g)
+        target = torch.randint(0, C, (N,), generator=g)
+        labels = torch.randint(0, C, (N,), generator=g)
+        out[f"confmat/C{C}/logits"] = logits.numpy()
+        out[f"confmat/C{C}/target"] = target.numpy()
+        out[f"confmat/C{C}/labels"] = labels.numpy()
+        for ign in (None, -1, 0):
+            t = target.clone()
+            if ign == -1:
+                t[::7] = -1
+            tag = "none" if ign is None else str(ign)
+            out[f"confmat/C{C}/ign{tag}/target"] = t.numpy()
+            out[f"confmat/C{C}/ign{tag}/from_logits"] = multiclass_confusion_matrix(logits, t, C, ignore_index=ign).numpy()
+            out[f"confmat/C{C}/ign{tag}/from_labels"] = multiclass_confusion_matrix(labels, t, C, ignore_index=ign).numpy()
+        for norm in ("true", "pred", "all"):
+            out[f"confmat/C{C}/norm_{norm}"] = multiclass_confusion_matrix(logits, target, C, normalize=norm).numpy()
+    # multidim (N, C, d1, d2) and small integer dtypes
+    md_logits = torch.randn(16, 6, 5, 3, generator=g)
+    md_target = torch.randint(0, 6, (16, 5, 3), generator=g)
+    out["confmat/multidim/logits"] = md_logits.numpy()
+    out["confmat/multidim/target"] = md_target.numpy()
+    out["confmat/multidim/confmat"] = multiclass_confusion_matrix(md_logits, md_target, 6).numpy()
+    u8p = torch.randint(0, 200, (300,), generator=g).to(torch.uint8)
+    u8t = torch.randint(0, 200, (300,), generator=g).to(torch.uint8)
+    out["confmat/uint8/preds"] = u8p.numpy()
+    out["confmat/uint8/target"] = u8t.numpy()
+    out["confmat/uint8/confmat"] = multiclass_confusion_matrix(u8p, u8t, 200).numpy()
+
+    # ---- C. cfg1: MulticlassAccuracy(5), 100 updates of [1024, 5] -------------------------------------------------
+    g = torch.Generator().manual_seed(0)
+    preds = torch.randn(100, 1024, 5, generator=g)
+    target = torch.randint(0, 5, (100, 1024), generator=g)
+    m = MulticlassAccuracy(num_classes=5)
+    for i in range(100):
+        m.update(preds[i], target[i])
+    out["cfg1/value"] = m.compute().numpy()
+    for s in ("tp", "fp", "tn", "fn"):
+        out[f"cfg1/{s}"] = getattr(m, s).numpy()
+    out["cfg1/preds_sha256"] = np.array(sha(preds))
+    out["cfg1/target_sha256"] = np.array(sha(target))
+
+    # ---- D. cfg2: MulticlassConfusionMatrix(1000), [65536, 1000] bf16 -----------------------------------------------
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(65536, 1000, generator=g).bfloat16()
+    target = torch.randint(0, 1000, (65536,), generator=g)
+    cm = MulticlassConfusionMatrix(num_classes=1000)
+    cm.update(logits, target)
+    confmat = cm.compute()
+    out["cfg2/argmax_i16"] = logits.argmax(dim=1).to(torch.int16).numpy()
+    out["cfg2/confmat_sha256"] = np.array(sha(confmat))
+    out["cfg2/confmat_rowsum"] = confmat.sum(1).numpy()
+    out["cfg2/confmat_colsum"] = confmat.sum(0).numpy()
+    out["cfg2/confmat_diag"] = confmat.diag().numpy()
+    out["cfg2/logits_sha256"] = np.array(sha(logits))
+    out["cfg2/target_sha256"] = np.array(sha(target))
+    out["cfg2/tied_rows"] = np.array(int((logits == logits.max(dim=1, keepdim=True).values).sum(1).gt(1).sum()))
+
+    # ---- E. stat scores / accuracy / f-beta ----------------------------------------------------------------------
+    g = torch.Generator().manual_seed(11)
+    for C, N in ((5, 300), (1000, 4096)):
+        logits = torch.randn(N, C, generator=g)
+        target = torch.randint(0, C, (N,), generator=g)
+        if C == 5:
+            target[target == 3] = 1  # class 3 never occurs in target
+            out[f"stats/C{C}/logits"] = logits.numpy()
+            out[f"stats/C{C}/target"] = target.numpy()
+        else:
+            out[f"stats/C{C}/logits_sha256"] = np.array(sha(logits))
+            out[f"stats/C{C}/target_sha256"] = np.array(sha(target))
+        for avg in ("micro", "macro", "weighted", "none"):
+            for ign in (None, -1, 1):
+                t = target.clone()
+                if ign == -1:
+                    t[::5] = -1
+                tag = f"stats/C{C}/{avg}/ign{'none' if ign is None else ign}"
+                out[f"{tag}/stat_scores"] = multiclass_stat_scores(logits, t, C, average=avg, ignore_index=ign).numpy()
+                out[f"{tag}/accuracy"] = multiclass_accuracy(logits, t, C, average=avg, ignore_index=ign).numpy()
+                out[f"{tag}/f1"] = multiclass_f1_score(logits, t, C, average=avg, ignore_index=ign).numpy()
+                out[f"{tag}/fbeta2"] = multiclass_fbeta_score(logits, t, 2.0, C, average=avg, ignore_index=ign).numpy()
+        # modular class over 4 batches (states)
+        for avg in ("micro", "macro"):
+            mm = MulticlassStatScores(num_classes=C, average=avg)
+            f1 = MulticlassF1Score(num_classes=C, average=avg)
+            for chunk_l, chunk_t in zip(logits.chunk(4), target.chunk(4)):
+                mm.update(chunk_l, chunk_t)
+                f1.update(chunk_l, chunk_t)
+            for s in ("tp", "fp", "tn", "fn"):
+                out[f"stats/C{C}/{avg}/class_state_{s}"] = getattr(mm, s).numpy()
+            out[f"stats/C{C}/{avg}/class_f1"] = f1.compute().numpy()
+    out["meta/torchmetrics_version"] = np.array(torchmetrics.__version__)
+    out["meta/torch_version"] = np.array(torch.__version__)
+    return out
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["classification"]
+    if "classification" in which:
+        data = classification_golden()
+        path = os.path.join(HERE, "classification.npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
