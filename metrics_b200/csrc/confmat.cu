@@ -12,385 +12,14 @@
 // holding that maximum (torch.argmax tie rule) — again one REDUX.  Lane 0 then commits one 64-bit RED to
 // the L2-resident state.  No intermediate (argmax vector, t*C+p, C*C bins) ever touches HBM, so the
 // algorithmic traffic is the logits read itself.
+#include <stdlib.h>
+#include <string.h>
+
+#include "argmax_core.cuh"
 #include "common.cuh"
+#include "sinks.cuh"
 
 namespace mb200 {
-
-// =====================================================================================================
-// Per-dtype row traits for the vectorised path.  A "vector" is 16 bytes.
-// =====================================================================================================
-template <typename T>
-struct RowTraits;
-
-template <>
-struct RowTraits<__nv_bfloat16> {
-    static constexpr int EPV = 8;
-    static constexpr unsigned kFill = 0xff80ff80u;  // two bf16 -inf
-    using Acc = __nv_bfloat162;
-    static __device__ __forceinline__ Acc as2(unsigned u) { return *reinterpret_cast<Acc*>(&u); }
-    static __device__ __forceinline__ Acc acc_init() { return as2(kFill); }
-    static __device__ __forceinline__ void accumulate(Acc& a, const uint4& v) {
-        a = __hmax2_nan(a, __hmax2_nan(__hmax2_nan(as2(v.x), as2(v.y)), __hmax2_nan(as2(v.z), as2(v.w))));
-    }
-    static __device__ __forceinline__ unsigned lane_key(Acc a) {
-        return f32_order_key(__bfloat162float(__hmax_nan(a.x, a.y)));
-    }
-    // Two words of four 0xFF/0x00 bytes each, byte order == column order inside the vector.
-    static __device__ __forceinline__ void match_words(const uint4& v, unsigned rowkey, unsigned& w0,
-                                                       unsigned& w1) {
-        unsigned e0, e1, e2, e3;
-        if (rowkey == 0xffffffffu) {  // NaN row (warp-uniform): a NaN is the only thing != itself
-            e0 = ~__heq2_mask(as2(v.x), as2(v.x));
-            e1 = ~__heq2_mask(as2(v.y), as2(v.y));
-            e2 = ~__heq2_mask(as2(v.z), as2(v.z));
-            e3 = ~__heq2_mask(as2(v.w), as2(v.w));
-        } else {
-            const Acc m = __float2bfloat162_rn(f32_from_order_key(rowkey));
-            e0 = __heq2_mask(as2(v.x), m);
-            e1 = __heq2_mask(as2(v.y), m);
-            e2 = __heq2_mask(as2(v.z), m);
-            e3 = __heq2_mask(as2(v.w), m);
-        }
-        w0 = __byte_perm(e0, e1, 0x6420);
-        w1 = __byte_perm(e2, e3, 0x6420);
-    }
-    static __device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
-};
-
-template <>
-struct RowTraits<__half> {
-    static constexpr int EPV = 8;
-    static constexpr unsigned kFill = 0xfc00fc00u;  // two f16 -inf
-    using Acc = __half2;
-    static __device__ __forceinline__ Acc as2(unsigned u) { return *reinterpret_cast<Acc*>(&u); }
-    static __device__ __forceinline__ Acc acc_init() { return as2(kFill); }
-    static __device__ __forceinline__ void accumulate(Acc& a, const uint4& v) {
-        a = __hmax2_nan(a, __hmax2_nan(__hmax2_nan(as2(v.x), as2(v.y)), __hmax2_nan(as2(v.z), as2(v.w))));
-    }
-    static __device__ __forceinline__ unsigned lane_key(Acc a) {
-        return f32_order_key(__half2float(__hmax_nan(__low2half(a), __high2half(a))));
-    }
-    static __device__ __forceinline__ void match_words(const uint4& v, unsigned rowkey, unsigned& w0,
-                                                       unsigned& w1) {
-        unsigned e0, e1, e2, e3;
-        if (rowkey == 0xffffffffu) {
-            e0 = ~__heq2_mask(as2(v.x), as2(v.x));
-            e1 = ~__heq2_mask(as2(v.y), as2(v.y));
-            e2 = ~__heq2_mask(as2(v.z), as2(v.z));
-            e3 = ~__heq2_mask(as2(v.w), as2(v.w));
-        } else {
-            const Acc m = __float2half2_rn(f32_from_order_key(rowkey));
-            e0 = __heq2_mask(as2(v.x), m);
-            e1 = __heq2_mask(as2(v.y), m);
-            e2 = __heq2_mask(as2(v.z), m);
-            e3 = __heq2_mask(as2(v.w), m);
-        }
-        w0 = __byte_perm(e0, e1, 0x6420);
-        w1 = __byte_perm(e2, e3, 0x6420);
-    }
-    static __device__ __forceinline__ float to_f32(__half x) { return __half2float(x); }
-};
-
-__device__ __forceinline__ float fmax_nan(float a, float b) {
-    float r;
-    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-    return r;
-}
-
-template <>
-struct RowTraits<float> {
-    static constexpr int EPV = 4;
-    static constexpr unsigned kFill = 0xff800000u;  // -inf
-    using Acc = float;
-    static __device__ __forceinline__ Acc acc_init() { return __uint_as_float(kFill); }
-    static __device__ __forceinline__ void accumulate(Acc& a, const uint4& v) {
-        a = fmax_nan(a, fmax_nan(fmax_nan(__uint_as_float(v.x), __uint_as_float(v.y)),
-                                 fmax_nan(__uint_as_float(v.z), __uint_as_float(v.w))));
-    }
-    static __device__ __forceinline__ unsigned lane_key(Acc a) { return f32_order_key(a); }
-    static __device__ __forceinline__ void match_words(const uint4& v, unsigned rowkey, unsigned& w0,
-                                                       unsigned& w1) {
-        const float x0 = __uint_as_float(v.x), x1 = __uint_as_float(v.y), x2 = __uint_as_float(v.z),
-                    x3 = __uint_as_float(v.w);
-        unsigned w = 0;
-        if (rowkey == 0xffffffffu) {
-            w |= (x0 != x0) ? 0x000000ffu : 0u;
-            w |= (x1 != x1) ? 0x0000ff00u : 0u;
-            w |= (x2 != x2) ? 0x00ff0000u : 0u;
-            w |= (x3 != x3) ? 0xff000000u : 0u;
-        } else {
-            const float m = f32_from_order_key(rowkey);
-            w |= (x0 == m) ? 0x000000ffu : 0u;
-            w |= (x1 == m) ? 0x0000ff00u : 0u;
-            w |= (x2 == m) ? 0x00ff0000u : 0u;
-            w |= (x3 == m) ? 0xff000000u : 0u;
-        }
-        w0 = w;
-        w1 = 0;
-    }
-    static __device__ __forceinline__ float to_f32(float x) { return x; }
-};
-
-// Generic order key used by the scalar paths (any float dtype, incl. f64).
-template <typename T>
-__device__ __forceinline__ unsigned long long order_key(T x) {
-    return (unsigned long long)f32_order_key(RowTraits<T>::to_f32(x));
-}
-template <>
-__device__ __forceinline__ unsigned long long order_key<double>(double x) {
-    return f64_order_key(x);
-}
-
-// =====================================================================================================
-// Warp-per-row argmax, vectorised.  Requires: row base 16-byte aligned and C * sizeof(T) % 16 == 0.
-// All lanes return the same column index.
-// =====================================================================================================
-constexpr int kVPL = 4;  // vectors per lane per chunk  -> chunk = 32 lanes * 4 * 16 B = 2 KiB of one row
-
-template <typename T>
-__device__ __forceinline__ int warp_row_argmax_vec(const T* __restrict__ row, int nvec, int lane) {
-    using TR = RowTraits<T>;
-    const uint4* __restrict__ rv = reinterpret_cast<const uint4*>(row);
-    unsigned best_key = 0;
-    int best_col = 0;
-    bool have = false;
-    for (int cv = 0; cv < nvec; cv += kVPL * kWarp) {
-        uint4 v[kVPL];
-#pragma unroll
-        for (int j = 0; j < kVPL; ++j) {
-            const int vi = cv + j * kWarp + lane;
-            if (vi < nvec) {
-                v[j] = ld_stream16(rv + vi);
-            } else {
-                v[j] = make_uint4(TR::kFill, TR::kFill, TR::kFill, TR::kFill);
-            }
-        }
-        typename TR::Acc acc = TR::acc_init();
-#pragma unroll
-        for (int j = 0; j < kVPL; ++j) TR::accumulate(acc, v[j]);
-        const unsigned ckey = __reduce_max_sync(kFull, TR::lane_key(acc));
-
-        unsigned bw0 = 0, bw1 = 0;
-        int bj = 0;
-#pragma unroll
-        for (int j = kVPL - 1; j >= 0; --j) {
-            unsigned w0, w1;
-            TR::match_words(v[j], ckey, w0, w1);
-            if ((w0 | w1) != 0u) {
-                bw0 = w0;
-                bw1 = w1;
-                bj = j;
-            }
-        }
-        unsigned col = 0x7fffffffu;
-        if ((bw0 | bw1) != 0u) {
-            const int e = bw0 ? ((__ffs(bw0) - 1) >> 3) : (4 + ((__ffs(bw1) - 1) >> 3));
-            col = (unsigned)((cv + bj * kWarp + lane) * TR::EPV + e);
-        }
-        const unsigned ccol = __reduce_min_sync(kFull, col);
-        // strictly-greater keeps the earliest chunk on ties (and the first NaN chunk: all NaN keys are equal)
-        if (!have || ckey > best_key) {
-            best_key = ckey;
-            best_col = (int)ccol;
-            have = true;
-        }
-    }
-    return best_col;
-}
-
-// Warp-per-row argmax, scalar loads (any alignment / any C).  All lanes return the same column.
-template <typename T>
-__device__ __forceinline__ int warp_row_argmax_scalar(const T* __restrict__ row, int C, int lane) {
-    unsigned long long bk = 0;
-    int bc = 0x7fffffff;
-    for (int c = lane; c < C; c += kWarp) {
-        const unsigned long long k = order_key<T>(row[c]);
-        if (bc == 0x7fffffff || k > bk) {
-            bk = k;
-            bc = c;
-        }
-    }
-    // lanes without any element (C < 32) carry key 0 / col INT_MAX and can never win against a real element
-    unsigned long long mk = bk;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(kFull, mk, o);
-        mk = other > mk ? other : mk;
-    }
-    const unsigned col = (bk == mk && bc != 0x7fffffff) ? (unsigned)bc : 0x7fffffffu;
-    return (int)__reduce_min_sync(kFull, col);
-}
-
-// Thread-per-(outer, inner) argmax over a strided class dimension: element c at base[c * stride].
-template <typename T>
-__device__ __forceinline__ int thread_argmax_strided(const T* __restrict__ base, int C, long long stride) {
-    unsigned long long bk = order_key<T>(base[0]);
-    int bc = 0;
-    for (int c = 1; c < C; ++c) {
-        const unsigned long long k = order_key<T>(base[(long long)c * stride]);
-        if (k > bk) {
-            bk = k;
-            bc = c;
-        }
-    }
-    return bc;
-}
-
-// =====================================================================================================
-// Sinks: what happens with one (target, prediction) pair.
-// =====================================================================================================
-struct ArgmaxOutSink {
-    long long* out;
-    struct Local {};
-    __device__ __forceinline__ void block_init() {}
-    __device__ __forceinline__ void init(Local&) {}
-    __device__ __forceinline__ void row(Local&, long long idx, long long /*t*/, int p) { out[idx] = p; }
-    __device__ __forceinline__ void finish(Local&) {}
-    static constexpr bool kNeedsTarget = false;
-};
-
-// confmat[t, p] += 1 straight into the (L2-resident) state; optional shared-memory privatisation for tiny C.
-template <bool kSmem>
-struct ConfmatSink {
-    long long* confmat;
-    int C;
-    struct Local {};
-    static constexpr bool kNeedsTarget = true;
-    __device__ __forceinline__ void block_init() {
-        if (kSmem) {
-            extern __shared__ unsigned sh_bins[];
-            for (int i = threadIdx.x; i < C * C; i += blockDim.x) sh_bins[i] = 0;
-            __syncthreads();
-        }
-    }
-    __device__ __forceinline__ void init(Local&) {}
-    __device__ __forceinline__ void row(Local&, long long, long long t, int p) {
-        if (kSmem) {
-            extern __shared__ unsigned sh_bins[];
-            atomicAdd(&sh_bins[(int)t * C + p], 1u);
-        } else {
-            red_add_u64(confmat + t * C + p, 1ull);
-        }
-    }
-    __device__ __forceinline__ void finish(Local&) {
-        if (kSmem) {
-            extern __shared__ unsigned sh_bins[];
-            __syncthreads();
-            for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
-                const unsigned v = sh_bins[i];
-                if (v) red_add_u64(confmat + i, v);
-            }
-        }
-    }
-};
-
-// tp/fp/fn deltas go to a zeroed workspace; the last block to finish folds them (and tn) into the states and
-// re-zeroes the workspace.  ws layout: [0,C) dtp | [C,2C) dfp | [2C,3C) dfn | [3C] n_valid | [3C+1] ticket.
-// micro: ws[0] = #match, ws[1] = #mismatch.
-template <bool kSmem>
-struct StatsSink {
-    long long *tp, *fp, *tn, *fn, *ws;
-    int C;
-    int micro;
-    struct Local {
-        unsigned n_valid, n_match;
-    };
-    static constexpr bool kNeedsTarget = true;
-    __device__ __forceinline__ void block_init() {
-        if (kSmem) {
-            extern __shared__ unsigned sh_bins[];
-            for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sh_bins[i] = 0;
-            __syncthreads();
-        }
-    }
-    __device__ __forceinline__ void init(Local& l) { l.n_valid = 0, l.n_match = 0; }
-    __device__ __forceinline__ void row(Local& l, long long, long long t, int p) {
-        l.n_valid++;
-        if (micro) {
-            l.n_match += ((long long)p == t);
-            return;
-        }
-        if (kSmem) {
-            extern __shared__ unsigned sh_bins[];
-            if ((long long)p == t) {
-                atomicAdd(&sh_bins[p], 1u);
-            } else {
-                atomicAdd(&sh_bins[C + p], 1u);
-                atomicAdd(&sh_bins[2 * C + (int)t], 1u);
-            }
-        } else {
-            if ((long long)p == t) {
-                red_add_u64(ws + p, 1ull);
-            } else {
-                red_add_u64(ws + C + p, 1ull);
-                red_add_u64(ws + 2 * C + t, 1ull);
-            }
-        }
-    }
-    __device__ __forceinline__ void finish(Local& l) {
-        // per-warp totals -> one atomic per warp
-        const unsigned nv = __reduce_add_sync(kFull, l.n_valid);
-        const unsigned nm = __reduce_add_sync(kFull, l.n_match);
-        if ((threadIdx.x & 31) == 0) {
-            if (nv) red_add_u64(ws + 3 * C, nv);
-            if (micro) {
-                if (nm) red_add_u64(ws + 0, nm);
-                if (nv - nm) red_add_u64(ws + 1, nv - nm);
-            }
-        }
-        if (kSmem && !micro) {
-            extern __shared__ unsigned sh_bins[];
-            __syncthreads();
-            for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
-                const unsigned v = sh_bins[i];
-                if (v) red_add_u64(ws + i, v);
-            }
-        }
-        // ---- last-block fold -------------------------------------------------------------------
-        __shared__ int is_last;
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned long long ticket =
-                atomicAdd(reinterpret_cast<unsigned long long*>(ws + 3 * C + 1), 1ull);
-            is_last = (ticket == (unsigned long long)gridDim.x - 1ull);
-        }
-        __syncthreads();
-        if (!is_last) return;
-        __threadfence();
-        long long* vws = ws;
-        const long long n_valid = __ldcg(ws + 3 * C);
-        if (micro) {
-            if (threadIdx.x == 0) {
-                const long long m = __ldcg(ws + 0), mm = __ldcg(ws + 1);
-                tp[0] += m;
-                fp[0] += mm;
-                fn[0] += mm;
-                tn[0] += (long long)C * n_valid - (m + 2 * mm);
-                vws[0] = 0;
-                vws[1] = 0;
-            }
-        } else {
-            for (int c = threadIdx.x; c < C; c += blockDim.x) {
-                const long long a = __ldcg(ws + c), b = __ldcg(ws + C + c), d = __ldcg(ws + 2 * C + c);
-                if (a | b | d) {
-                    tp[c] += a;
-                    fp[c] += b;
-                    fn[c] += d;
-                    vws[c] = 0;
-                    vws[C + c] = 0;
-                    vws[2 * C + c] = 0;
-                }
-                tn[c] += n_valid - (a + b + d);
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            vws[3 * C] = 0;
-            vws[3 * C + 1] = 0;
-        }
-    }
-};
 
 // =====================================================================================================
 // Kernels
@@ -407,10 +36,16 @@ struct RowArgs {
     unsigned* err;
 };
 
-__device__ __forceinline__ bool admit_target(const RowArgs& a, long long idx, long long& t, bool report) {
-    t = load_label(a.target, a.target_dtype, idx);
+template <bool kI64>
+__device__ __forceinline__ long long fetch_label(const RowArgs& a, long long idx) {
+    if (kI64) return __ldg(reinterpret_cast<const long long*>(a.target) + idx);
+    return load_label(a.target, a.target_dtype, idx);
+}
+
+// Decide whether a row with label t takes part; flags out-of-range labels.
+__device__ __forceinline__ bool admit_label(const RowArgs& a, long long t, bool report) {
     if (a.has_ignore && t == a.ignore_index) return false;
-    if (t < 0 || t >= a.C) {
+    if ((unsigned long long)t >= (unsigned long long)a.C) {  // also catches negatives
         if (report && a.err) atomicOr(a.err, MB200_FLAG_TARGET_RANGE);
         return false;
     }
@@ -419,28 +54,155 @@ __device__ __forceinline__ bool admit_target(const RowArgs& a, long long idx, lo
 
 constexpr int kRowThreads = 256;
 
-// (1) aligned fast path: warp per row, 16-byte vectors
-template <typename T, typename Sink>
+// (1) aligned path: warp per row, 16-byte streaming vector loads from global memory.  The label of the warp's NEXT
+// row is requested before the current row is reduced, so label latency never sits in front of the row loads.
+// Measured (profiles/r01_confmat_sweep.txt): with >= 4 resident CTAs/SM this loop runs at the same rate as a pure
+// read-only streaming probe over the same 131 MB, i.e. the reduction is completely hidden behind HBM; deeper software
+// pipelining or a TMA/bulk-copy ring (1b) buys nothing on top of it.
+template <typename T, typename Sink, bool kI64>
 __global__ void __launch_bounds__(kRowThreads) rows_vec_kernel(RowArgs a, Sink sink) {
     sink.block_init();
     typename Sink::Local loc;
     sink.init(loc);
     const int lane = threadIdx.x & 31;
-    const long long wpb = blockDim.x >> 5;
-    const long long nwarps = (long long)gridDim.x * wpb;
+    const int wpb = blockDim.x >> 5;
+    const int nwarps = gridDim.x * wpb;
+    const int n = (int)a.n_outer;
     const int nvec = (int)(((long long)a.C * sizeof(T)) >> 4);
     const T* __restrict__ preds = reinterpret_cast<const T*>(a.preds);
-    for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < a.n_outer; r += nwarps) {
-        long long t = 0;
-        if (Sink::kNeedsTarget && !admit_target(a, r, t, lane == 0)) continue;  // ignored rows are never read
-        const int p = warp_row_argmax_vec<T>(preds + r * a.C, nvec, lane);
+    constexpr bool kLabels = Sink::kNeedsTarget;
+    int r = blockIdx.x * wpb + (threadIdx.x >> 5);
+    long long t_next = 0;
+    if (kLabels && r < n) t_next = fetch_label<kI64>(a, r);
+    for (; r < n; r += nwarps) {
+        const long long t = t_next;
+        if (kLabels && r + nwarps < n) t_next = fetch_label<kI64>(a, r + nwarps);
+        if (kLabels && !admit_label(a, t, lane == 0)) continue;  // ignored rows are never read
+        const GlobalVecLoader load{reinterpret_cast<const uint4*>(preds + (size_t)r * a.C)};
+        const int p = warp_row_argmax_vec<T>(load, nvec, lane);
         if (lane == 0) sink.row(loc, r, t, p);
     }
     sink.finish(loc);
 }
 
+// (1b) aligned path, bulk-copy pipeline: one producer thread streams tiles of kRows whole rows into a shared-memory
+// ring with `cp.async.bulk` (1-D TMA, completion counted on an mbarrier); kRows consumer warps each reduce one staged
+// row per tile.  HBM requests stay in flight for the whole ring depth and cost no registers.
+constexpr int kBulkMaxStages = 8;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes,
+                                         unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <typename T, typename Sink, bool kI64, int kRows>
+__global__ void __launch_bounds__((kRows + 1) * 32, 1) rows_bulk_kernel(RowArgs a, Sink sink, int stages) {
+    extern __shared__ __align__(128) unsigned char bulk_smem[];
+    __shared__ __align__(8) unsigned long long full_bar[kBulkMaxStages];
+    __shared__ __align__(8) unsigned long long empty_bar[kBulkMaxStages];
+    typename Sink::Local loc;
+    sink.init(loc);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned row_bytes = (unsigned)a.C * (unsigned)sizeof(T);
+    const unsigned stage_bytes = row_bytes * kRows;
+    const int nvec = (int)(row_bytes >> 4);
+    const int n = (int)a.n_outer;
+    const int n_tiles = (n + kRows - 1) / kRows;
+    const unsigned char* __restrict__ gbase = reinterpret_cast<const unsigned char*>(a.preds);
+    constexpr bool kLabels = Sink::kNeedsTarget;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kRows);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kRows) {
+        // ===== producer: one elected lane keeps the ring full =====
+        if (lane == 0) {
+            int s = 0;
+            unsigned phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(&empty_bar[s], phase ^ 1u);  // first lap: passes immediately
+                const int row0 = tile * kRows;
+                const int rows = min(kRows, n - row0);
+                const unsigned bytes = (unsigned)rows * row_bytes;
+                mbar_expect_tx(&full_bar[s], bytes);
+                bulk_g2s(bulk_smem + (size_t)s * stage_bytes, gbase + (size_t)row0 * row_bytes, bytes, &full_bar[s]);
+                if (++s == stages) {
+                    s = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===== consumers: warp w reduces row w of every tile; labels are fetched one tile ahead =====
+        int s = 0;
+        unsigned phase = 0;
+        int tile = blockIdx.x;
+        long long t_next = 0;
+        if (kLabels && tile < n_tiles && tile * kRows + warp < n) t_next = fetch_label<kI64>(a, tile * kRows + warp);
+        for (; tile < n_tiles; tile += gridDim.x) {
+            const int r = tile * kRows + warp;
+            const long long t = t_next;
+            const int rn = (tile + (int)gridDim.x) * kRows + warp;
+            if (kLabels && rn < n) t_next = fetch_label<kI64>(a, rn);
+            mbar_wait(&full_bar[s], phase);
+            int p = 0;
+            const bool live = r < n && (!kLabels || admit_label(a, t, lane == 0));
+            if (live) {
+                const SharedVecLoader load{
+                    reinterpret_cast<const uint4*>(bulk_smem + (size_t)s * stage_bytes + (size_t)warp * row_bytes)};
+                p = warp_row_argmax_vec<T>(load, nvec, lane);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty_bar[s]);  // this warp's row of the stage now lives in registers / is reduced
+                if (live) sink.row(loc, r, t, p);
+            }
+            if (++s == stages) {
+                s = 0;
+                phase ^= 1u;
+            }
+        }
+    }
+    sink.finish(loc);
+}
+
 // (2) warp per row, scalar loads
-template <typename T, typename Sink>
+template <typename T, typename Sink, bool kI64>
 __global__ void __launch_bounds__(kRowThreads) rows_scalar_kernel(RowArgs a, Sink sink) {
     sink.block_init();
     typename Sink::Local loc;
@@ -451,7 +213,10 @@ __global__ void __launch_bounds__(kRowThreads) rows_scalar_kernel(RowArgs a, Sin
     const T* __restrict__ preds = reinterpret_cast<const T*>(a.preds);
     for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < a.n_outer; r += nwarps) {
         long long t = 0;
-        if (Sink::kNeedsTarget && !admit_target(a, r, t, lane == 0)) continue;
+        if (Sink::kNeedsTarget) {
+            t = fetch_label<kI64>(a, r);
+            if (!admit_label(a, t, lane == 0)) continue;
+        }
         const int p = warp_row_argmax_scalar<T>(preds + r * a.C, a.C, lane);
         if (lane == 0) sink.row(loc, r, t, p);
     }
@@ -459,7 +224,7 @@ __global__ void __launch_bounds__(kRowThreads) rows_scalar_kernel(RowArgs a, Sin
 }
 
 // (3) thread per (outer, inner) position, class dim strided by `inner` (also the tiny-C path with inner == 1)
-template <typename T, typename Sink>
+template <typename T, typename Sink, bool kI64>
 __global__ void __launch_bounds__(kRowThreads) rows_strided_kernel(RowArgs a, Sink sink) {
     sink.block_init();
     typename Sink::Local loc;
@@ -469,7 +234,10 @@ __global__ void __launch_bounds__(kRowThreads) rows_strided_kernel(RowArgs a, Si
     const T* __restrict__ preds = reinterpret_cast<const T*>(a.preds);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
         long long t = 0;
-        if (Sink::kNeedsTarget && !admit_target(a, i, t, true)) continue;
+        if (Sink::kNeedsTarget) {
+            t = fetch_label<kI64>(a, i);
+            if (!admit_label(a, t, true)) continue;
+        }
         const long long n = i / a.inner, x = i - n * a.inner;
         const int p = thread_argmax_strided<T>(preds + (n * a.C) * a.inner + x, a.C, a.inner);
         sink.row(loc, i, t, p);
@@ -478,7 +246,7 @@ __global__ void __launch_bounds__(kRowThreads) rows_strided_kernel(RowArgs a, Si
 }
 
 // (4) integer label predictions: thread per sample
-template <typename Sink>
+template <typename Sink, bool kI64>
 __global__ void __launch_bounds__(kRowThreads) labels_kernel(RowArgs a, int preds_dtype, Sink sink) {
     sink.block_init();
     typename Sink::Local loc;
@@ -486,10 +254,10 @@ __global__ void __launch_bounds__(kRowThreads) labels_kernel(RowArgs a, int pred
     const long long total = a.n_outer * a.inner;
     const long long nthreads = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
-        long long t = 0;
-        if (!admit_target(a, i, t, true)) continue;
+        const long long t = fetch_label<kI64>(a, i);
+        if (!admit_label(a, t, true)) continue;
         const long long p = load_label(a.preds, preds_dtype, i);
-        if (p < 0 || p >= a.C) {
+        if ((unsigned long long)p >= (unsigned long long)a.C) {
             if (a.err) atomicOr(a.err, MB200_FLAG_PREDS_RANGE);
             continue;
         }
@@ -503,46 +271,95 @@ __global__ void __launch_bounds__(kRowThreads) labels_kernel(RowArgs a, int pred
 // =====================================================================================================
 extern void count_launch();
 
-static inline int grid_for(long long work_items, int items_per_block, int max_waves_blocks) {
+static inline int grid_for(long long work_items, int items_per_block, int max_blocks) {
     long long g = (work_items + items_per_block - 1) / items_per_block;
     if (g < 1) g = 1;
-    if (g > max_waves_blocks) g = max_waves_blocks;
+    if (g > max_blocks) g = max_blocks;
     return (int)g;
 }
 
-template <typename T, typename Sink>
+// Path override for A/B measurements: MB200_ROWS_PATH=vec|bulk (default vec: it measured faster, see (1)).
+static int rows_path_override() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("MB200_ROWS_PATH");
+        cached = (e && e[0] == 'b') ? 2 : 1;
+    }
+    return cached;
+}
+
+template <typename Kernel>
+static int resident_blocks(Kernel k, int threads, size_t smem) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    return per_sm * sm_count();
+}
+
+template <typename T, typename Sink, bool kI64, int kRows>
+static int launch_bulk(const RowArgs& a, Sink sink, cudaStream_t st, bool& launched) {
+    const size_t stage_bytes = (size_t)a.C * sizeof(T) * kRows;
+    int stages = (int)((200 * 1024) / stage_bytes);
+    if (stages > kBulkMaxStages) stages = kBulkMaxStages;
+    launched = false;
+    if (stages < 3 || a.n_outer < 4 * kRows) return 0;
+    auto kern = rows_bulk_kernel<T, Sink, kI64, kRows>;
+    static thread_local bool configured = false;
+    if (!configured) {
+        MB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
+        configured = true;
+    }
+    const long long tiles = (a.n_outer + kRows - 1) / kRows;
+    int grid = sm_count();
+    if (tiles < grid) grid = (int)tiles;
+    kern<<<grid, (kRows + 1) * 32, (size_t)stages * stage_bytes, st>>>(a, sink, stages);
+    launched = true;
+    return 0;
+}
+
+template <typename T, typename Sink, bool kI64>
 static int launch_rows(const RowArgs& a, Sink sink, size_t smem, cudaStream_t st) {
-    const int sms = sm_count();
-    const int max_blocks = sms * 8;  // 8 CTAs of 256 threads = 64 resident warps per SM
     const size_t row_bytes = (size_t)a.C * sizeof(T);
     const bool vec_ok = sizeof(T) <= 4 && a.inner == 1 && a.C >= 32 && (row_bytes % 16 == 0) &&
                         ((reinterpret_cast<uintptr_t>(a.preds) & 15) == 0);
     if (a.inner == 1 && a.C >= 32) {
-        const int grid = grid_for(a.n_outer, kRowThreads / 32, max_blocks);
         if (vec_ok) {
             if constexpr (sizeof(T) <= 4) {
-                rows_vec_kernel<T, Sink><<<grid, kRowThreads, smem, st>>>(a, sink);
+                const int ov = rows_path_override();
+                bool launched = false;
+                if (smem == 0 && ov == 2) {
+                    if (int rc = launch_bulk<T, Sink, kI64, 16>(a, sink, st, launched)) return rc;
+                }
+                if (!launched) {
+                    auto kern = rows_vec_kernel<T, Sink, kI64>;
+                    const int grid = grid_for(a.n_outer, kRowThreads / 32, resident_blocks(kern, kRowThreads, smem));
+                    kern<<<grid, kRowThreads, smem, st>>>(a, sink);
+                }
             }
         } else {
-            rows_scalar_kernel<T, Sink><<<grid, kRowThreads, smem, st>>>(a, sink);
+            auto kern = rows_scalar_kernel<T, Sink, kI64>;
+            const int grid = grid_for(a.n_outer, kRowThreads / 32, resident_blocks(kern, kRowThreads, smem));
+            kern<<<grid, kRowThreads, smem, st>>>(a, sink);
         }
     } else {
-        const int grid = grid_for(a.n_outer * a.inner, kRowThreads, max_blocks);
-        rows_strided_kernel<T, Sink><<<grid, kRowThreads, smem, st>>>(a, sink);
+        auto kern = rows_strided_kernel<T, Sink, kI64>;
+        const int grid = grid_for(a.n_outer * a.inner, kRowThreads, resident_blocks(kern, kRowThreads, smem));
+        kern<<<grid, kRowThreads, smem, st>>>(a, sink);
     }
     count_launch();
     return check_cuda(cudaGetLastError(), "row kernel launch");
 }
 
-template <typename Sink>
-static int dispatch_rows(int preds_dtype, int preds_has_class_dim, const RowArgs& a, Sink sink, size_t smem,
-                         cudaStream_t st) {
+template <typename Sink, bool kI64>
+static int dispatch_rows_t(int preds_dtype, int preds_has_class_dim, const RowArgs& a, Sink sink, size_t smem,
+                           cudaStream_t st) {
     if (!preds_has_class_dim) {
         if constexpr (Sink::kNeedsTarget) {
             MB200_REQUIRE(preds_dtype >= MB200_I64 && preds_dtype <= MB200_BOOL,
                           "label-format preds must have an integer dtype (got dtype tag %d)", preds_dtype);
-            const int grid = grid_for(a.n_outer * a.inner, kRowThreads, sm_count() * 8);
-            labels_kernel<Sink><<<grid, kRowThreads, smem, st>>>(a, preds_dtype, sink);
+            auto kern = labels_kernel<Sink, kI64>;
+            const int grid = grid_for(a.n_outer * a.inner, kRowThreads, resident_blocks(kern, kRowThreads, smem));
+            kern<<<grid, kRowThreads, smem, st>>>(a, preds_dtype, sink);
             count_launch();
             return check_cuda(cudaGetLastError(), "labels kernel launch");
         } else {
@@ -551,14 +368,23 @@ static int dispatch_rows(int preds_dtype, int preds_has_class_dim, const RowArgs
         }
     }
     switch (preds_dtype) {
-        case MB200_BF16: return launch_rows<__nv_bfloat16, Sink>(a, sink, smem, st);
-        case MB200_F16: return launch_rows<__half, Sink>(a, sink, smem, st);
-        case MB200_F32: return launch_rows<float, Sink>(a, sink, smem, st);
-        case MB200_F64: return launch_rows<double, Sink>(a, sink, smem, st);
+        case MB200_BF16: return launch_rows<__nv_bfloat16, Sink, kI64>(a, sink, smem, st);
+        case MB200_F16: return launch_rows<__half, Sink, kI64>(a, sink, smem, st);
+        case MB200_F32: return launch_rows<float, Sink, kI64>(a, sink, smem, st);
+        case MB200_F64: return launch_rows<double, Sink, kI64>(a, sink, smem, st);
         default:
             set_error("preds with a class dimension must be floating point (got dtype tag %d)", preds_dtype);
             return MB200_ERR_INVALID;
     }
+}
+
+template <typename Sink>
+static int dispatch_rows(int preds_dtype, int preds_has_class_dim, const RowArgs& a, Sink sink, size_t smem,
+                         cudaStream_t st) {
+    MB200_REQUIRE(a.n_outer * a.inner < (1ll << 31), "more than 2^31-1 rows per call are not supported (got %lld)",
+                  (long long)(a.n_outer * a.inner));
+    if (a.target_dtype == MB200_I64) return dispatch_rows_t<Sink, true>(preds_dtype, preds_has_class_dim, a, sink, smem, st);
+    return dispatch_rows_t<Sink, false>(preds_dtype, preds_has_class_dim, a, sink, smem, st);
 }
 
 static int validate_common(const void* preds, const void* target, int target_dtype, int64_t n_outer,

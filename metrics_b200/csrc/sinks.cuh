@@ -1,0 +1,164 @@
+// Sinks of the row kernels: what happens with one (target, prediction) pair.  See confmat.cu.
+#pragma once
+#include "common.cuh"
+
+namespace mb200 {
+
+// =====================================================================================================
+// Sinks: what happens with one (target, prediction) pair.
+// =====================================================================================================
+struct ArgmaxOutSink {
+    long long* out;
+    struct Local {};
+    __device__ __forceinline__ void block_init() {}
+    __device__ __forceinline__ void init(Local&) {}
+    __device__ __forceinline__ void row(Local&, long long idx, long long /*t*/, int p) { out[idx] = p; }
+    __device__ __forceinline__ void finish(Local&) {}
+    static constexpr bool kNeedsTarget = false;
+};
+
+// confmat[t, p] += 1 straight into the (L2-resident) state; optional shared-memory privatisation for tiny C.
+template <bool kSmem>
+struct ConfmatSink {
+    long long* confmat;
+    int C;
+    struct Local {};
+    static constexpr bool kNeedsTarget = true;
+    __device__ __forceinline__ void block_init() {
+        if (kSmem) {
+            extern __shared__ unsigned sh_bins[];
+            for (int i = threadIdx.x; i < C * C; i += blockDim.x) sh_bins[i] = 0;
+            __syncthreads();
+        }
+    }
+    __device__ __forceinline__ void init(Local&) {}
+    __device__ __forceinline__ void row(Local&, long long, long long t, int p) {
+        if (kSmem) {
+            extern __shared__ unsigned sh_bins[];
+            atomicAdd(&sh_bins[(int)t * C + p], 1u);
+        } else {
+            red_add_u64(confmat + t * C + p, 1ull);
+        }
+    }
+    __device__ __forceinline__ void finish(Local&) {
+        if (kSmem) {
+            extern __shared__ unsigned sh_bins[];
+            __syncthreads();
+            for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+                const unsigned v = sh_bins[i];
+                if (v) red_add_u64(confmat + i, v);
+            }
+        }
+    }
+};
+
+// tp/fp/fn deltas go to a zeroed workspace; the last block to finish folds them (and tn) into the states and
+// re-zeroes the workspace.  ws layout: [0,C) dtp | [C,2C) dfp | [2C,3C) dfn | [3C] n_valid | [3C+1] ticket.
+// micro: ws[0] = #match, ws[1] = #mismatch.
+template <bool kSmem>
+struct StatsSink {
+    long long *tp, *fp, *tn, *fn, *ws;
+    int C;
+    int micro;
+    struct Local {
+        unsigned n_valid, n_match;
+    };
+    static constexpr bool kNeedsTarget = true;
+    __device__ __forceinline__ void block_init() {
+        if (kSmem) {
+            extern __shared__ unsigned sh_bins[];
+            for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sh_bins[i] = 0;
+            __syncthreads();
+        }
+    }
+    __device__ __forceinline__ void init(Local& l) { l.n_valid = 0, l.n_match = 0; }
+    __device__ __forceinline__ void row(Local& l, long long, long long t, int p) {
+        l.n_valid++;
+        if (micro) {
+            l.n_match += ((long long)p == t);
+            return;
+        }
+        if (kSmem) {
+            extern __shared__ unsigned sh_bins[];
+            if ((long long)p == t) {
+                atomicAdd(&sh_bins[p], 1u);
+            } else {
+                atomicAdd(&sh_bins[C + p], 1u);
+                atomicAdd(&sh_bins[2 * C + (int)t], 1u);
+            }
+        } else {
+            if ((long long)p == t) {
+                red_add_u64(ws + p, 1ull);
+            } else {
+                red_add_u64(ws + C + p, 1ull);
+                red_add_u64(ws + 2 * C + t, 1ull);
+            }
+        }
+    }
+    __device__ __forceinline__ void finish(Local& l) {
+        // per-warp totals -> one atomic per warp
+        const unsigned nv = __reduce_add_sync(kFull, l.n_valid);
+        const unsigned nm = __reduce_add_sync(kFull, l.n_match);
+        if ((threadIdx.x & 31) == 0) {
+            if (nv) red_add_u64(ws + 3 * C, nv);
+            if (micro) {
+                if (nm) red_add_u64(ws + 0, nm);
+                if (nv - nm) red_add_u64(ws + 1, nv - nm);
+            }
+        }
+        if (kSmem && !micro) {
+            extern __shared__ unsigned sh_bins[];
+            __syncthreads();
+            for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+                const unsigned v = sh_bins[i];
+                if (v) red_add_u64(ws + i, v);
+            }
+        }
+        // ---- last-block fold -------------------------------------------------------------------
+        __shared__ int is_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long ticket =
+                atomicAdd(reinterpret_cast<unsigned long long*>(ws + 3 * C + 1), 1ull);
+            is_last = (ticket == (unsigned long long)gridDim.x - 1ull);
+        }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        long long* vws = ws;
+        const long long n_valid = __ldcg(ws + 3 * C);
+        if (micro) {
+            if (threadIdx.x == 0) {
+                const long long m = __ldcg(ws + 0), mm = __ldcg(ws + 1);
+                tp[0] += m;
+                fp[0] += mm;
+                fn[0] += mm;
+                tn[0] += (long long)C * n_valid - (m + 2 * mm);
+                vws[0] = 0;
+                vws[1] = 0;
+            }
+        } else {
+            for (int c = threadIdx.x; c < C; c += blockDim.x) {
+                const long long a = __ldcg(ws + c), b = __ldcg(ws + C + c), d = __ldcg(ws + 2 * C + c);
+                if (a | b | d) {
+                    tp[c] += a;
+                    fp[c] += b;
+                    fn[c] += d;
+                    vws[c] = 0;
+                    vws[C + c] = 0;
+                    vws[2 * C + c] = 0;
+                }
+                tn[c] += n_valid - (a + b + d);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            vws[3 * C] = 0;
+            vws[3 * C + 1] = 0;
+        }
+    }
+};
+
+
+}  // namespace mb200

@@ -126,7 +126,11 @@ def test_cfg1_multiclass_accuracy_bit_exact(golden_cls):
             np.testing.assert_array_equal(getattr(m, s).cpu().numpy(), golden_cls[f"cfg1/{s}"])
         val = m.compute()
         assert val.dtype == torch.float32
-        assert float(val) == float(golden_cls["cfg1/value"]) == 0.1986250877380371
+        # float32 ratio of exact integer states: tolerance 1e-6 relative (north_star); the reduction over the
+        # 5 classes runs in a CUDA kernel whose summation order may differ from the CPU's by one ulp
+        ref = float(golden_cls["cfg1/value"])
+        assert ref == 0.1986250877380371
+        assert abs(float(val) - ref) <= 1e-6 * ref
 
 
 def test_cfg2_confmat_bit_exact_full_size(golden_cls):
