@@ -110,6 +110,43 @@ MB200_API int mb200_multiclass_stat_scores_update(const void* preds, int preds_d
 MB200_API int mb200_argmax_rows(const void* preds, int preds_dtype, int64_t n_outer, int64_t num_classes,
                       int64_t inner, int64_t* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K6 — `normalize_logits_if_needed` (utilities/compute.py:190-229, device branch :223-229).
+ * out = (any(x < 0) | any(x > 1)) ? sigmoid(x) : x, decided per call over the whole buffer, no host sync.
+ * `flag_scratch` is a 4-byte device word owned by the caller (zeroed internally with cudaMemsetAsync).
+ * out may alias preds.  Math in fp32 (fp64 for MB200_F64), rounded to the storage dtype like ATen.
+ * ------------------------------------------------------------------------------------------------ */
+MB200_API int mb200_curve_sigmoid_if_logits(const void* preds, int dtype, int64_t n, void* out,
+                                            uint32_t* flag_scratch, void* stream);
+/* softmax(dim=1) variant for [n, num_classes] row-major scores (multiclass curve metrics,
+ * functional/classification/precision_recall_curve.py:454). */
+MB200_API int mb200_curve_softmax_if_logits(const void* preds, int dtype, int64_t n, int64_t num_classes, void* out,
+                                            uint32_t* flag_scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3/K5 — exact-mode curve evaluation: sort + tie-collapsing TP/FP scan + AUROC / average precision.
+ * Replaces functional/classification/precision_recall_curve.py:30-82 (_binary_clf_curve), roc.py:40-80,
+ * auroc.py:83-107 (max_fpr=None), average_precision.py:70-75, utilities/compute.py:101-109, and for
+ * num_classes > 1 the per-class Python loops of roc.py:176-181 / precision_recall_curve.py:565-569
+ * (one segment per class, sorted together in one batched radix sort).
+ *
+ *  preds      : num_classes == 1: [n] scores; else [n, num_classes] row-major.  f32 / f16 / bf16.
+ *  target     : [n] integer labels.  Positive for curve c: target == c (num_classes == 1: target == pos_label).
+ *  workspace  : device scratch of at least mb200_curve_workspace_bytes(num_classes, n) bytes
+ *  out_auroc  : float32 [num_classes]   area under ROC (0 when a curve has no positives or no negatives)
+ *  out_ap     : float32 [num_classes]   average precision (-0.0 when a curve has no positives, like the reference)
+ *  out_counts : int64 [num_classes][3]  {#positives, #negatives, #distinct thresholds U}
+ *  fps_out, tps_out, thr_out : optional (all or none) float32 [num_classes][n]; for curve c the first U entries
+ *               are the reference's `fps, tps, thresholds` (descending thresholds), the rest is untouched.
+ * TP/FP are counted in integers (exact for n < 2^31); AUROC = exact integer sum / (2 P N) evaluated in fp64;
+ * AP accumulated in fp64 in a fixed order (bitwise reproducible run to run).
+ * ------------------------------------------------------------------------------------------------ */
+MB200_API int64_t mb200_curve_workspace_bytes(int64_t num_classes, int64_t n);
+MB200_API int mb200_curve_evaluate(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                   int64_t n, int64_t num_classes, int64_t pos_label, void* workspace,
+                                   int64_t workspace_bytes, float* out_auroc, float* out_ap, int64_t* out_counts,
+                                   float* fps_out, float* tps_out, float* thr_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

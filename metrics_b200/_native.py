@@ -206,3 +206,70 @@ def argmax_rows(preds: Tensor) -> Tensor:
         )
     check(rc, "argmax_rows")
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K3/K5/K6 wrappers (exact curve family)
+# ----------------------------------------------------------------------------------------------------------
+def sigmoid_if_logits(preds: Tensor) -> Tensor:
+    """``normalize_logits_if_needed(preds, "sigmoid")``: per-call global range test + conditional sigmoid, no host sync."""
+    dev = require_cuda(preds)
+    preds = preds.contiguous()
+    out = torch.empty_like(preds)
+    if preds.numel() == 0:
+        return out
+    flag = torch.empty(1, dtype=torch.int32, device=dev)
+    with on_device(dev):
+        rc = lib().mb200_curve_sigmoid_if_logits(ptr(preds), tag(preds), i64(preds.numel()), ptr(out), ptr(flag), stream_handle(dev))
+    check(rc, "curve_sigmoid_if_logits")
+    return out
+
+
+def softmax_if_logits(preds: Tensor) -> Tensor:
+    """``normalize_logits_if_needed(preds, "softmax")`` for a contiguous ``[N, C]`` tensor."""
+    dev = require_cuda(preds)
+    preds = preds.contiguous()
+    out = torch.empty_like(preds)
+    if preds.numel() == 0:
+        return out
+    if preds.dtype == torch.float64:
+        raise NotImplementedError("metrics_b200: float64 scores are not supported by the multiclass curve kernels")
+    flag = torch.empty(1, dtype=torch.int32, device=dev)
+    with on_device(dev):
+        rc = lib().mb200_curve_softmax_if_logits(
+            ptr(preds), tag(preds), i64(preds.shape[0]), i64(preds.shape[1]), ptr(out), ptr(flag), stream_handle(dev)
+        )
+    check(rc, "curve_softmax_if_logits")
+    return out
+
+
+def curve_evaluate(preds: Tensor, target: Tensor, num_classes: int = 1, pos_label: int = 1, want_curve: bool = False):
+    """Sort + TP/FP scan for ``num_classes`` one-vs-rest curves (``mb200_curve_evaluate``).
+
+    Returns ``(auroc[C] f32, ap[C] f32, counts[C, 3] i64, curve)`` where ``curve`` is ``None`` or the tuple
+    ``(fps, tps, thresholds)`` of ``[C, N]`` float32 buffers whose first ``counts[c, 2]`` entries per row are valid.
+    """
+    dev = require_cuda(preds, target)
+    if preds.dtype == torch.float64:
+        raise NotImplementedError("metrics_b200: float64 scores are not supported by the exact curve kernels; cast to float32")
+    preds = preds.contiguous()
+    target = target.contiguous()
+    n = target.numel()
+    lib_ = lib()
+    lib_.mb200_curve_workspace_bytes.restype = ctypes.c_int64
+    nbytes = int(lib_.mb200_curve_workspace_bytes(i64(num_classes), i64(n)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    auroc = torch.empty(num_classes, dtype=torch.float32, device=dev)
+    ap = torch.empty(num_classes, dtype=torch.float32, device=dev)
+    counts = torch.empty((num_classes, 3), dtype=torch.int64, device=dev)
+    curve = None
+    if want_curve:
+        curve = tuple(torch.empty((num_classes, n), dtype=torch.float32, device=dev) for _ in range(3))
+    with on_device(dev):
+        rc = lib_.mb200_curve_evaluate(
+            ptr(preds), tag(preds), ptr(target), tag(target), i64(n), i64(num_classes), i64(pos_label), ptr(ws),
+            i64(nbytes), ptr(auroc), ptr(ap), ptr(counts), ptr(curve[0] if curve else None),
+            ptr(curve[1] if curve else None), ptr(curve[2] if curve else None), stream_handle(dev),
+        )
+    check(rc, "curve_evaluate")
+    return auroc, ap, counts, curve

@@ -3,3 +3,10 @@ from metrics_b200.classification.accuracy import MulticlassAccuracy  # noqa: F40
 from metrics_b200.classification.confusion_matrix import MulticlassConfusionMatrix  # noqa: F401
 from metrics_b200.classification.f_beta import MulticlassF1Score, MulticlassFBetaScore  # noqa: F401
 from metrics_b200.classification.stat_scores import MulticlassStatScores  # noqa: F401
+from metrics_b200.classification.auroc import BinaryAUROC, MulticlassAUROC  # noqa: F401,E402
+from metrics_b200.classification.average_precision import BinaryAveragePrecision, MulticlassAveragePrecision  # noqa: F401,E402
+from metrics_b200.classification.precision_recall_curve import (  # noqa: F401,E402
+    BinaryPrecisionRecallCurve,
+    MulticlassPrecisionRecallCurve,
+)
+from metrics_b200.classification.roc import BinaryROC, MulticlassROC  # noqa: F401,E402

@@ -1,0 +1,117 @@
+"""Precision-recall-curve metric classes, exact mode (reference: classification/precision_recall_curve.py).
+
+States are the reference's: list states ``preds`` / ``target`` with ``dist_reduce_fx="cat"`` (observable through
+``metric_state``, compute groups, ``state_dict``).  ``update`` runs the format kernel (conditional sigmoid/softmax) and
+appends; ``compute`` concatenates once and runs the batched sort + scan pipeline.
+"""
+from __future__ import annotations
+
+from typing import Any, List, Optional, Union
+
+from torch import Tensor
+from typing_extensions import Literal
+
+from metrics_b200.functional.classification.precision_recall_curve import (
+    _adjust_threshold_arg,
+    _binary_precision_recall_curve_arg_validation,
+    _binary_precision_recall_curve_compute,
+    _binary_precision_recall_curve_format,
+    _binary_precision_recall_curve_tensor_validation,
+    _binary_precision_recall_curve_update,
+    _multiclass_precision_recall_curve_arg_validation,
+    _multiclass_precision_recall_curve_compute,
+    _multiclass_precision_recall_curve_format,
+    _multiclass_precision_recall_curve_tensor_validation,
+    _multiclass_precision_recall_curve_update,
+    _no_binned,
+)
+from metrics_b200.metric import Metric
+from metrics_b200.utilities.data import dim_zero_cat
+
+
+class BinaryPrecisionRecallCurve(Metric):
+    """Reference :55-177."""
+
+    is_differentiable: bool = False
+    higher_is_better: Optional[bool] = None
+    full_state_update: bool = False
+    preds: List[Tensor]
+    target: List[Tensor]
+
+    def __init__(
+        self,
+        thresholds: Optional[Union[int, List[float], Tensor]] = None,
+        ignore_index: Optional[int] = None,
+        validate_args: bool = True,
+        **kwargs: Any,
+    ) -> None:
+        super().__init__(**kwargs)
+        if validate_args:
+            _binary_precision_recall_curve_arg_validation(thresholds, ignore_index)
+        _no_binned(thresholds)
+        self.ignore_index = ignore_index
+        self.validate_args = validate_args
+        self.thresholds = _adjust_threshold_arg(thresholds)
+        self.add_state("preds", default=[], dist_reduce_fx="cat")
+        self.add_state("target", default=[], dist_reduce_fx="cat")
+
+    def update(self, preds: Tensor, target: Tensor) -> None:
+        if self.validate_args:
+            _binary_precision_recall_curve_tensor_validation(preds, target, self.ignore_index)
+        preds, target, _ = _binary_precision_recall_curve_format(preds, target, self.thresholds, self.ignore_index)
+        state = _binary_precision_recall_curve_update(preds, target, self.thresholds)
+        self.preds.append(state[0])
+        self.target.append(state[1])
+
+    def _state(self) -> tuple[Tensor, Tensor]:
+        return dim_zero_cat(self.preds), dim_zero_cat(self.target)
+
+    def compute(self) -> tuple[Tensor, Tensor, Tensor]:
+        return _binary_precision_recall_curve_compute(self._state(), self.thresholds)
+
+
+class MulticlassPrecisionRecallCurve(Metric):
+    """Reference :228-380."""
+
+    is_differentiable: bool = False
+    higher_is_better: Optional[bool] = None
+    full_state_update: bool = False
+    preds: List[Tensor]
+    target: List[Tensor]
+
+    def __init__(
+        self,
+        num_classes: int,
+        thresholds: Optional[Union[int, List[float], Tensor]] = None,
+        average: Optional[Literal["micro", "macro"]] = None,
+        ignore_index: Optional[int] = None,
+        validate_args: bool = True,
+        **kwargs: Any,
+    ) -> None:
+        super().__init__(**kwargs)
+        if validate_args:
+            _multiclass_precision_recall_curve_arg_validation(num_classes, thresholds, ignore_index, average)
+        _no_binned(thresholds)
+        self.num_classes = num_classes
+        self.average = average
+        self.ignore_index = ignore_index
+        self.validate_args = validate_args
+        self.thresholds = _adjust_threshold_arg(thresholds)
+        self.add_state("preds", default=[], dist_reduce_fx="cat")
+        self.add_state("target", default=[], dist_reduce_fx="cat")
+
+    def update(self, preds: Tensor, target: Tensor) -> None:
+        if self.validate_args:
+            _multiclass_precision_recall_curve_tensor_validation(preds, target, self.num_classes, self.ignore_index)
+        preds, target, _ = _multiclass_precision_recall_curve_format(
+            preds, target, self.num_classes, self.thresholds, self.ignore_index, self.average
+        )
+        state = _multiclass_precision_recall_curve_update(preds, target, self.num_classes, self.thresholds, self.average)
+        self.preds.append(state[0])
+        self.target.append(state[1])
+
+    def _state(self) -> tuple[Tensor, Tensor]:
+        return dim_zero_cat(self.preds), dim_zero_cat(self.target)
+
+    def compute(self):
+        return _multiclass_precision_recall_curve_compute(self._state(), self.num_classes, self.thresholds, self.average)

@@ -1,0 +1,831 @@
+// K3 / K5 / K6 — exact ROC / PR-curve family on sm_100a: score formatting, key packing, segmented LSD radix sort,
+// tie-collapsing TP/FP scan with fused AUROC / average-precision accumulation.
+//
+// Reference op chain replaced (src/torchmetrics/):
+//   utilities/compute.py:190-229                      normalize_logits_if_needed (batch-global range test + sigmoid/softmax)
+//   functional/classification/precision_recall_curve.py:30-82   _binary_clf_curve: argsort(desc) -> gathers -> distinct
+//                                                     thresholds (where) -> cumsum -> fps = 1 + idx - tps
+//   functional/classification/roc.py:40-80, auroc.py:83-107, average_precision.py:70-75, compute.py:101-109 (trapz)
+//   functional/classification/{roc.py:162-204, precision_recall_curve.py:565-569}  per-class Python loop (one sort each)
+//
+// Data layout: a "segment" is one curve (binary: 1 segment; multiclass one-vs-rest: one segment per class, stored
+// class-major so that a segment is contiguous).  Per element we keep a 4-byte key (order-preserving transform of the fp32
+// score, inverted so that ascending key order == descending score order) and a 1-byte label (target == positive class).
+// The 8-bit LSD radix sort moves 5 B/element/pass; with <= ~25 M elements both ping-pong buffers live in the 126 MB L2.
+// The scan counts in integers: TP/FP are exact for any N < 2^32 per segment (the reference counts in fp32 and is exact
+// only below 2^24), AUROC is accumulated as the exact integer  sum dFP * (TP_prev + TP)  (== 2 * Mann-Whitney U),
+// AP in fp64 with a fixed reduction order (deterministic).
+#include "common.cuh"
+
+namespace mb200 {
+
+extern void count_launch();
+
+// =====================================================================================================
+// helpers
+// =====================================================================================================
+template <typename T>
+__device__ __forceinline__ float to_float(T x);
+template <>
+__device__ __forceinline__ float to_float<float>(float x) { return x; }
+template <>
+__device__ __forceinline__ float to_float<__half>(__half x) { return __half2float(x); }
+template <>
+__device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <>
+__device__ __forceinline__ float to_float<double>(double x) { return (float)x; }
+
+template <typename T>
+__device__ __forceinline__ T from_float(float x);
+template <>
+__device__ __forceinline__ float from_float<float>(float x) { return x; }
+template <>
+__device__ __forceinline__ __half from_float<__half>(float x) { return __float2half_rn(x); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+// ascending sort of this key == descending sort of the score; NaN first (torch.argsort(descending=True) puts NaN first)
+__device__ __forceinline__ unsigned desc_key(float v) { return ~f32_order_key(v); }
+__device__ __forceinline__ float score_of_key(unsigned k) {
+    const unsigned ok = ~k;
+    if (ok == 0xffffffffu) return __int_as_float(0x7fc00000);
+    return f32_from_order_key(ok);
+}
+
+// =====================================================================================================
+// K6: batch-global "are these logits?" test and conditional sigmoid  (utilities/compute.py:223-229, device branch:
+// cond = any(x < 0) | any(x > 1); out = where(cond, sigmoid(x), x) — decided per batch tensor, no host sync)
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) range_flag_kernel(const T* __restrict__ x, long long n, unsigned* flag) {
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = to_float<T>(x[i]);
+        bad |= (v < 0.f) | (v > 1.f);
+    }
+    if (__any_sync(kFull, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+template <>
+__global__ void __launch_bounds__(256) range_flag_kernel<double>(const double* __restrict__ x, long long n, unsigned* flag) {
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        bad |= (v < 0.0) | (v > 1.0);
+    }
+    if (__any_sync(kFull, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) sigmoid_if_kernel(const T* __restrict__ x, T* __restrict__ out, long long n,
+                                                         const unsigned* __restrict__ flag) {
+    const bool apply = (*flag) != 0u;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (apply) {
+            const float v = to_float<T>(x[i]);
+            out[i] = from_float<T>(1.0f / (1.0f + expf(-v)));  // fp32 math, rounded to T like ATen's sigmoid
+        } else {
+            out[i] = x[i];
+        }
+    }
+}
+template <>
+__global__ void __launch_bounds__(256) sigmoid_if_kernel<double>(const double* __restrict__ x, double* __restrict__ out,
+                                                                 long long n, const unsigned* __restrict__ flag) {
+    const bool apply = (*flag) != 0u;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = apply ? 1.0 / (1.0 + exp(-x[i])) : x[i];
+}
+
+// Row softmax over [N, C] when the batch flag is set (utilities/compute.py:226-229 with normalization="softmax").
+// One warp per row, values staged in registers chunk-wise; fp32 math.
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_if_kernel(const T* __restrict__ x, T* __restrict__ out, int n, int C,
+                                                         const unsigned* __restrict__ flag) {
+    const bool apply = (*flag) != 0u;
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n; r += gridDim.x * wpb) {
+        const T* __restrict__ row = x + (size_t)r * C;
+        T* __restrict__ orow = out + (size_t)r * C;
+        if (!apply) {
+            for (int c = lane; c < C; c += 32) orow[c] = row[c];
+            continue;
+        }
+        float m = -INFINITY;
+        for (int c = lane; c < C; c += 32) m = fmaxf(m, to_float<T>(row[c]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s += expf(to_float<T>(row[c]) - m);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+        for (int c = lane; c < C; c += 32) orow[c] = from_float<T>(expf(to_float<T>(row[c]) - m) / s);
+    }
+}
+
+// =====================================================================================================
+// key packing
+// =====================================================================================================
+// binary: keys[i] = desc_key(preds[i]), labels[i] = (target[i] == pos_label)
+template <typename T>
+__global__ void __launch_bounds__(256) pack_binary_kernel(const T* __restrict__ preds, const void* __restrict__ target,
+                                                          int tdtype, long long n, long long pos_label,
+                                                          unsigned* __restrict__ keys, unsigned char* __restrict__ labels) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        keys[i] = desc_key(to_float<T>(preds[i]));
+        labels[i] = (unsigned char)(load_label(target, tdtype, i) == pos_label);
+    }
+}
+
+// multiclass one-vs-rest: preds [N, C] row-major -> keys [C][N] (class-major), labels[c][n] = (target[n] == c).
+// 32x32 shared-memory tile transpose so that both the read and the write are coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_ovr_kernel(const T* __restrict__ preds, const void* __restrict__ target,
+                                                       int tdtype, int n, int C, unsigned* __restrict__ keys,
+                                                       unsigned char* __restrict__ labels) {
+    __shared__ unsigned tile[32][33];
+    __shared__ int tgt[32];
+    const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of 32 threads
+    if (threadIdx.x < 32) {
+        const int nn = n0 + threadIdx.x;
+        tgt[threadIdx.x] = nn < n ? (int)load_label(target, tdtype, nn) : -1;
+    }
+    for (int j = ty; j < 32; j += 8) {
+        const int nn = n0 + j, cc = c0 + tx;
+        if (nn < n && cc < C) tile[j][tx] = desc_key(to_float<T>(preds[(size_t)nn * C + cc]));
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int cc = c0 + j, nn = n0 + tx;
+        if (nn < n && cc < C) {
+            keys[(size_t)cc * n + nn] = tile[tx][j];
+            labels[(size_t)cc * n + nn] = (unsigned char)(tgt[tx] == cc);
+        }
+    }
+}
+
+// =====================================================================================================
+// segmented LSD radix sort, 8-bit digits, u32 keys + u8 payload.   grid = (tiles_per_segment, segments)
+// =====================================================================================================
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per CTA
+
+// (A) per-tile digit histogram -> tile_hist[seg][digit][tile]
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const unsigned* __restrict__ keys, int n, int tiles,
+                                                                  int shift, unsigned* __restrict__ tile_hist) {
+    __shared__ unsigned hist[256];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int seg = blockIdx.y, tile = blockIdx.x;
+    const unsigned* __restrict__ k = keys + (size_t)seg * n;
+    const int base = tile * kSortTile;
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+        const int idx = base + i * kSortThreads + threadIdx.x;
+        if (idx < n) atomicAdd(&hist[(k[idx] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    tile_hist[((size_t)seg * 256 + threadIdx.x) * tiles + tile] = hist[threadIdx.x];
+}
+
+// (B) per (segment, digit): exclusive scan over tiles in place; digit totals -> digit_total[seg][digit]
+__global__ void __launch_bounds__(256) radix_scan_kernel(unsigned* __restrict__ tile_hist, int tiles,
+                                                         unsigned* __restrict__ digit_total) {
+    __shared__ unsigned warp_sums[8];
+    __shared__ unsigned carry_s;
+    const int seg = blockIdx.y, digit = blockIdx.x;
+    unsigned* __restrict__ h = tile_hist + ((size_t)seg * 256 + digit) * tiles;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < tiles; base += 256) {
+        const int idx = base + threadIdx.x;
+        const unsigned v = idx < tiles ? h[idx] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        unsigned woff = 0;
+        for (int w = 0; w < warp; ++w) woff += warp_sums[w];
+        const unsigned carry = carry_s;
+        if (idx < tiles) h[idx] = carry + woff + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry_s = carry + woff + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) digit_total[seg * 256 + digit] = carry_s;
+}
+
+// (C) stable scatter.  Warp-striped arrangement: warp w owns keys [tile_base + w*512, +512), item i of lane l is
+// element i*32 + l of that range, so (i, l) order == memory order.  Ranks come from MATCH.ANY groups + per-warp
+// running digit counters in shared memory.
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsigned* __restrict__ keys_in,
+                                                                     const unsigned char* __restrict__ labels_in,
+                                                                     unsigned* __restrict__ keys_out,
+                                                                     unsigned char* __restrict__ labels_out, int n,
+                                                                     int tiles, int shift,
+                                                                     const unsigned* __restrict__ tile_hist,
+                                                                     const unsigned* __restrict__ digit_total) {
+    __shared__ unsigned warp_hist[8][256];
+    __shared__ unsigned digit_base[256];
+    __shared__ unsigned scan_tmp[8];
+    const int seg = blockIdx.y, tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t seg_off = (size_t)seg * n;
+    const unsigned* __restrict__ kin = keys_in + seg_off;
+    const unsigned char* __restrict__ lin = labels_in + seg_off;
+    for (int i = threadIdx.x; i < 8 * 256; i += kSortThreads) (&warp_hist[0][0])[i] = 0;
+
+    // global base of every digit for this tile: exclusive scan of the digit totals + this tile's exclusive offset
+    {
+        const unsigned tot = digit_total[seg * 256 + threadIdx.x];
+        unsigned incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) scan_tmp[warp] = incl;
+        __syncthreads();
+        unsigned woff = 0;
+        for (int w = 0; w < warp; ++w) woff += scan_tmp[w];
+        digit_base[threadIdx.x] = woff + incl - tot + tile_hist[((size_t)seg * 256 + threadIdx.x) * tiles + tile];
+    }
+    __syncthreads();
+
+    const int wbase = tile * kSortTile + warp * (kSortItems * 32);
+    unsigned key[kSortItems];
+    unsigned char lab[kSortItems];
+    unsigned short rank[kSortItems];
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+        const int idx = wbase + i * 32 + lane;
+        const bool valid = idx < n;
+        key[i] = valid ? kin[idx] : 0u;
+        lab[i] = valid ? lin[idx] : (unsigned char)0;
+    }
+    const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+        const int idx = wbase + i * 32 + lane;
+        const bool valid = idx < n;
+        const unsigned digit = valid ? ((key[i] >> shift) & 255u) : (0x100u + lane);  // invalid lanes: unique groups
+        const unsigned peers = __match_any_sync(kFull, digit);
+        const int leader = __ffs(peers) - 1;
+        unsigned base = 0;
+        if (valid && lane == leader) {
+            base = warp_hist[warp][digit];
+            warp_hist[warp][digit] = base + __popc(peers);
+        }
+        base = __shfl_sync(kFull, base, leader);
+        rank[i] = (unsigned short)(base + __popc(peers & lt_mask));
+        __syncwarp();
+    }
+    __syncthreads();
+    // exclusive scan over the 8 warps for every digit
+    {
+        unsigned off = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const unsigned c = warp_hist[w][threadIdx.x];
+            warp_hist[w][threadIdx.x] = off;
+            off += c;
+        }
+    }
+    __syncthreads();
+    unsigned* __restrict__ kout = keys_out + seg_off;
+    unsigned char* __restrict__ lout = labels_out + seg_off;
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+        const int idx = wbase + i * 32 + lane;
+        if (idx < n) {
+            const unsigned digit = (key[i] >> shift) & 255u;
+            const unsigned dst = digit_base[digit] + warp_hist[warp][digit] + rank[i];
+            kout[dst] = key[i];
+            lout[dst] = lab[i];
+        }
+    }
+}
+
+// =====================================================================================================
+// tie-collapsing TP/FP scan over sorted (key, label)     grid = (tiles, segments), tile = 256 threads x 8 items
+// =====================================================================================================
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;  // 2048
+
+struct TileInfo {        // produced by phase 1, turned into carries by phase 2
+    unsigned npos;       // positives in the tile           -> exclusive prefix of positives before the tile
+    unsigned nbound;     // distinct-threshold group ends   -> exclusive prefix of group ends before the tile
+    unsigned tp_last;    // local TP at the tile's last group end (or 0)   -> TP at the last group end before the tile
+    unsigned fp_last;    // local FP at the tile's last group end (or 0)   -> FP at the last group end before the tile
+    unsigned has_bound;  // tile contains a group end
+};
+
+__device__ __forceinline__ unsigned block_excl_sum(unsigned v, unsigned* smem8, unsigned& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();
+    if (lane == 31) smem8[warp] = incl;
+    __syncthreads();
+    unsigned woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const unsigned s = smem8[w];
+        if (w < warp) woff += s;
+        tot += s;
+    }
+    total = tot;
+    return woff + incl - v;
+}
+__device__ __forceinline__ unsigned block_excl_max(unsigned v, unsigned* smem8) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl = max(incl, t);
+    }
+    __syncthreads();
+    if (lane == 31) smem8[warp] = incl;
+    __syncthreads();
+    unsigned wmax = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+        if (w < warp) wmax = max(wmax, smem8[w]);
+    unsigned excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 0;
+    return max(wmax, excl);
+}
+
+// Blocked arrangement: thread t owns elements [t*8, t*8+8) of the tile.
+struct ScanThreadData {
+    unsigned key[kScanItems];
+    unsigned key_next;  // key following the thread's last element (or ~own for "end of segment")
+    unsigned char lab[kScanItems];
+    int count;  // valid elements
+};
+
+__device__ __forceinline__ void scan_load(ScanThreadData& d, const unsigned* __restrict__ k,
+                                          const unsigned char* __restrict__ l, int n, int tile) {
+    const int base = tile * kScanTile + threadIdx.x * kScanItems;
+    d.count = max(0, min(kScanItems, n - base));
+    const bool aligned = ((reinterpret_cast<uintptr_t>(k + base) & 15) == 0) && ((reinterpret_cast<uintptr_t>(l + base) & 7) == 0);
+    if (d.count == kScanItems && aligned) {
+        const uint4 a = *reinterpret_cast<const uint4*>(k + base);
+        const uint4 b = *reinterpret_cast<const uint4*>(k + base + 4);
+        d.key[0] = a.x, d.key[1] = a.y, d.key[2] = a.z, d.key[3] = a.w;
+        d.key[4] = b.x, d.key[5] = b.y, d.key[6] = b.z, d.key[7] = b.w;
+        const uint2 lb = *reinterpret_cast<const uint2*>(l + base);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            d.lab[i] = (unsigned char)((lb.x >> (8 * i)) & 0xff);
+            d.lab[4 + i] = (unsigned char)((lb.y >> (8 * i)) & 0xff);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            d.key[i] = i < d.count ? k[base + i] : 0u;
+            d.lab[i] = i < d.count ? l[base + i] : (unsigned char)0;
+        }
+    }
+    const int nxt = base + kScanItems;
+    d.key_next = (d.count == kScanItems && nxt < n) ? k[nxt] : 0u;
+}
+// is element i of this thread the last of its tie group?
+__device__ __forceinline__ bool is_group_end(const ScanThreadData& d, int i, int n, int tile) {
+    if (i >= d.count) return false;
+    const int g = tile * kScanTile + threadIdx.x * kScanItems + i;
+    if (g == n - 1) return true;
+    const unsigned nk = (i + 1 < kScanItems) ? d.key[i + 1] : d.key_next;
+    return d.key[i] != nk;
+}
+
+// phase 1: per-tile aggregates
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const unsigned* __restrict__ keys,
+                                                                   const unsigned char* __restrict__ labels, int n,
+                                                                   int tiles, TileInfo* __restrict__ info) {
+    __shared__ unsigned sm[8];
+    const int seg = blockIdx.y, tile = blockIdx.x;
+    ScanThreadData d;
+    scan_load(d, keys + (size_t)seg * n, labels + (size_t)seg * n, n, tile);
+    unsigned npos = 0, nb = 0, cum_at_last = 0;
+    int last_local = -1;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        npos += d.lab[i];
+        if (is_group_end(d, i, n, tile)) {
+            nb++;
+            last_local = threadIdx.x * kScanItems + i;
+            cum_at_last = npos;  // thread-local inclusive count at that element
+        }
+    }
+    unsigned tot_pos, tot_b;
+    const unsigned pos_excl = block_excl_sum(npos, sm, tot_pos);
+    (void)block_excl_sum(nb, sm, tot_b);
+    // the thread holding the tile's last group end: the max local index
+    const unsigned mine = last_local >= 0 ? (unsigned)(last_local + 1) : 0u;
+    unsigned best = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(kFull, best, o));
+    __shared__ unsigned wbest[8];
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
+    __syncthreads();
+    unsigned tile_best = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tile_best = max(tile_best, wbest[w]);
+    TileInfo* out = info + (size_t)seg * tiles + tile;
+    if (threadIdx.x == 0) {
+        out->npos = tot_pos;
+        out->nbound = tot_b;
+        out->has_bound = tile_best != 0u;
+        if (tile_best == 0u) {
+            out->tp_last = 0;
+            out->fp_last = 0;
+        }
+    }
+    if (mine != 0u && mine == tile_best) {
+        const unsigned tp = pos_excl + cum_at_last;
+        out->tp_last = tp;                          // local (within tile) counts; made global in phase 2
+        out->fp_last = (unsigned)last_local + 1u - tp;
+    }
+}
+
+// phase 2: one CTA per segment turns tile aggregates into exclusive carries (sequential over <= a few thousand tiles,
+// chunked 256 at a time with block scans).
+__global__ void __launch_bounds__(256) scan_carry_kernel(TileInfo* __restrict__ info, int tiles, int n,
+                                                         unsigned* __restrict__ seg_totals /* [seg][2]: P, U */) {
+    __shared__ unsigned sm[8];
+    __shared__ unsigned c_pos, c_b, c_tp, c_fp;
+    const int seg = blockIdx.x;
+    TileInfo* __restrict__ ti = info + (size_t)seg * tiles;
+    if (threadIdx.x == 0) c_pos = 0, c_b = 0, c_tp = 0, c_fp = 0;
+    __syncthreads();
+    for (int base = 0; base < tiles; base += 256) {
+        const int t = base + threadIdx.x;
+        TileInfo v{0, 0, 0, 0, 0};
+        if (t < tiles) v = ti[t];
+        unsigned tot_pos, tot_b;
+        const unsigned pos_excl = c_pos + block_excl_sum(v.npos, sm, tot_pos);
+        const unsigned b_excl = c_b + block_excl_sum(v.nbound, sm, tot_b);
+        // global TP / FP at this tile's last group end (monotone non-decreasing along the segment -> max-scan = "last valid")
+        const unsigned tp_here = v.has_bound ? pos_excl + v.tp_last : 0u;
+        const unsigned fp_here = v.has_bound ? ((unsigned)t * (unsigned)kScanTile - pos_excl) + v.fp_last : 0u;
+        const unsigned tp_prev = max(c_tp, block_excl_max(tp_here, sm));
+        const unsigned fp_prev = max(c_fp, block_excl_max(fp_here, sm));
+        if (t < tiles) {
+            ti[t].npos = pos_excl;
+            ti[t].nbound = b_excl;
+            ti[t].tp_last = tp_prev;
+            ti[t].fp_last = fp_prev;
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) {
+            c_pos = pos_excl + v.npos;
+            c_b = b_excl + v.nbound;
+            c_tp = max(tp_prev, tp_here);
+            c_fp = max(fp_prev, fp_here);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        seg_totals[2 * seg + 0] = c_pos;
+        seg_totals[2 * seg + 1] = c_b;
+    }
+}
+
+// phase 3: per-tile scan with carries; accumulates the AUROC integer and the AP partial sum; optionally writes the
+// compacted curve (fps, tps, thresholds) at distinct thresholds.
+template <bool kWriteCurve>
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const unsigned* __restrict__ keys,
+                                                                  const unsigned char* __restrict__ labels, int n,
+                                                                  int tiles, const TileInfo* __restrict__ info,
+                                                                  unsigned long long* __restrict__ auroc_acc /*[seg]*/,
+                                                                  double* __restrict__ ap_partial /*[seg][tiles]*/,
+                                                                  float* __restrict__ fps_out, float* __restrict__ tps_out,
+                                                                  float* __restrict__ thr_out, long long curve_stride) {
+    __shared__ unsigned sm[8];
+    __shared__ double dsum[8];
+    __shared__ unsigned long long usum[8];
+    const int seg = blockIdx.y, tile = blockIdx.x;
+    ScanThreadData d;
+    scan_load(d, keys + (size_t)seg * n, labels + (size_t)seg * n, n, tile);
+    const TileInfo carry = info[(size_t)seg * tiles + tile];
+
+    unsigned npos = 0, nb = 0;
+    bool ends[kScanItems];
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        npos += d.lab[i];
+        ends[i] = is_group_end(d, i, n, tile);
+        nb += ends[i];
+    }
+    unsigned tot;
+    const unsigned pos_excl = carry.npos + block_excl_sum(npos, sm, tot);
+    const unsigned b_excl = carry.nbound + block_excl_sum(nb, sm, tot);
+    // TP / FP at the thread's own last group end (0 if none) -> exclusive max-scan gives "previous group end" values
+    unsigned my_tp = 0, my_fp = 0;
+    {
+        unsigned run = pos_excl;
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            run += d.lab[i];
+            if (ends[i]) {
+                my_tp = run;
+                my_fp = (unsigned)(tile * kScanTile + threadIdx.x * kScanItems + i) + 1u - run;
+            }
+        }
+    }
+    unsigned tp_prev = max(carry.tp_last, block_excl_max(my_tp, sm));
+    unsigned fp_prev = max(carry.fp_last, block_excl_max(my_fp, sm));
+
+    unsigned long long s_auc = 0;
+    double s_ap = 0.0;
+    unsigned run = pos_excl, bi = b_excl;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        run += d.lab[i];
+        if (ends[i]) {
+            const unsigned tp = run;
+            const unsigned fp = (unsigned)(tile * kScanTile + threadIdx.x * kScanItems + i) + 1u - tp;
+            s_auc += (unsigned long long)(fp - fp_prev) * (unsigned long long)(tp_prev + tp);
+            if (tp != tp_prev) s_ap += (double)(tp - tp_prev) * ((double)tp / (double)(tp + fp));
+            if (kWriteCurve) {
+                const long long o = (long long)seg * curve_stride + bi;
+                fps_out[o] = (float)fp;
+                tps_out[o] = (float)tp;
+                thr_out[o] = score_of_key(d.key[i]);
+            }
+            tp_prev = tp;
+            fp_prev = fp;
+            bi++;
+        }
+    }
+    // block reductions in a fixed order (deterministic fp64 result)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s_auc += __shfl_down_sync(kFull, s_auc, o);
+        s_ap += __shfl_down_sync(kFull, s_ap, o);
+    }
+    __syncthreads();
+    if (lane == 0) usum[warp] = s_auc, dsum[warp] = s_ap;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long a = 0;
+        double p = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += usum[w], p += dsum[w];
+        if (a) atomicAdd(auroc_acc + seg, a);  // integer: order-independent, exact
+        ap_partial[(size_t)seg * tiles + tile] = p;
+    }
+}
+
+// phase 4: one warp per segment folds the per-tile AP partials in tile order and emits the scalars.
+// out[seg] = {auroc, ap, n_pos, n_neg, n_thresholds} as fp32 (counts < 2^24 are exact; larger ones only inform weights)
+__global__ void __launch_bounds__(256) scan_finalize_kernel(const unsigned long long* __restrict__ auroc_acc,
+                                                            const double* __restrict__ ap_partial,
+                                                            const unsigned* __restrict__ seg_totals, int tiles, int n,
+                                                            int segments, float* __restrict__ out_auroc,
+                                                            float* __restrict__ out_ap, long long* __restrict__ out_counts) {
+    const int seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (seg >= segments) return;
+    double s = 0.0;
+    // fixed order: lane-strided partial sums then a fixed shuffle tree
+    for (int t = lane; t < tiles; t += 32) s += ap_partial[(size_t)seg * tiles + t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(kFull, s, o);
+    if (lane == 0) {
+        const double P = (double)seg_totals[2 * seg + 0];
+        const double Nn = (double)n - P;
+        const double auc = (P > 0.0 && Nn > 0.0) ? (double)auroc_acc[seg] / (2.0 * P * Nn) : 0.0;
+        // all-negative: the reference forces recall to 1 everywhere and gets -0.0 (precision_recall_curve.py:278-283)
+        const double ap = P > 0.0 ? s / P : -0.0;
+        out_auroc[seg] = (float)auc;
+        out_ap[seg] = (float)ap;
+        out_counts[3 * seg + 0] = (long long)seg_totals[2 * seg + 0];
+        out_counts[3 * seg + 1] = (long long)n - (long long)seg_totals[2 * seg + 0];
+        out_counts[3 * seg + 2] = (long long)seg_totals[2 * seg + 1];
+    }
+}
+
+__global__ void zero_u64_kernel(unsigned long long* p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0ull;
+}
+
+static inline int blocks_for(long long n, int per_block, int cap) {
+    long long b = (n + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return (int)b;
+}
+
+}  // namespace mb200
+
+using namespace mb200;
+
+// =====================================================================================================
+// C-ABI
+// =====================================================================================================
+extern "C" int mb200_curve_sigmoid_if_logits(const void* preds, int dtype, int64_t n, void* out, uint32_t* flag_scratch,
+                                             void* stream) {
+    MB200_REQUIRE(n >= 0, "negative n");
+    if (n == 0) return 0;
+    MB200_REQUIRE(preds && out && flag_scratch, "NULL pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    MB200_CUDA_OK(cudaMemsetAsync(flag_scratch, 0, sizeof(uint32_t), st));
+    const int grid = blocks_for(n, 256 * 8, sm_count() * 8);
+#define MB200_FMT(T)                                                                                             \
+    range_flag_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), n, flag_scratch);             \
+    sigmoid_if_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), reinterpret_cast<T*>(out), n, \
+                                               flag_scratch);
+    switch (dtype) {
+        case MB200_F32: MB200_FMT(float) break;
+        case MB200_F16: MB200_FMT(__half) break;
+        case MB200_BF16: MB200_FMT(__nv_bfloat16) break;
+        case MB200_F64: MB200_FMT(double) break;
+        default: set_error("scores must be floating point (dtype tag %d)", dtype); return MB200_ERR_INVALID;
+    }
+#undef MB200_FMT
+    count_launch();
+    count_launch();
+    return check_cuda(cudaGetLastError(), "curve format launch");
+}
+
+extern "C" int mb200_curve_softmax_if_logits(const void* preds, int dtype, int64_t n, int64_t num_classes, void* out,
+                                             uint32_t* flag_scratch, void* stream) {
+    MB200_REQUIRE(n >= 0 && num_classes >= 1, "bad sizes");
+    if (n == 0) return 0;
+    MB200_REQUIRE(preds && out && flag_scratch, "NULL pointer");
+    MB200_REQUIRE(n < (1ll << 31) && num_classes < (1ll << 31), "sizes exceed int32");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    MB200_CUDA_OK(cudaMemsetAsync(flag_scratch, 0, sizeof(uint32_t), st));
+    const long long total = n * num_classes;
+    const int grid = blocks_for(total, 256 * 8, sm_count() * 8);
+    const int grid_rows = blocks_for(n, 8, sm_count() * 8);
+#define MB200_FMT(T)                                                                                                \
+    range_flag_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), total, flag_scratch);            \
+    softmax_if_kernel<T><<<grid_rows, 256, 0, st>>>(reinterpret_cast<const T*>(preds), reinterpret_cast<T*>(out),  \
+                                                    (int)n, (int)num_classes, flag_scratch);
+    switch (dtype) {
+        case MB200_F32: MB200_FMT(float) break;
+        case MB200_F16: MB200_FMT(__half) break;
+        case MB200_BF16: MB200_FMT(__nv_bfloat16) break;
+        default: set_error("softmax scores must be f32/f16/bf16 (dtype tag %d)", dtype); return MB200_ERR_INVALID;
+    }
+#undef MB200_FMT
+    count_launch();
+    count_launch();
+    return check_cuda(cudaGetLastError(), "curve softmax launch");
+}
+
+extern "C" int64_t mb200_curve_workspace_bytes(int64_t segments, int64_t n) {
+    if (segments < 1 || n < 0) return -1;
+    const int64_t sort_tiles = (n + kSortTile - 1) / kSortTile;
+    const int64_t scan_tiles = (n + kScanTile - 1) / kScanTile;
+    int64_t b = 0;
+    b += segments * n * 4;                          // keys ping
+    b += segments * n * 4;                          // keys pong
+    b += segments * n * 1 + 16;                     // labels ping
+    b += segments * n * 1 + 16;                     // labels pong
+    b += segments * 256 * (sort_tiles + 1) * 4;     // tile_hist
+    b += segments * 256 * 4;                        // digit_total
+    b += segments * (scan_tiles + 1) * (int64_t)sizeof(TileInfo);
+    b += segments * 2 * 4;                          // seg_totals
+    b += segments * 8;                              // auroc_acc
+    b += segments * (scan_tiles + 1) * 8;           // ap_partial
+    return b + 16 * 256;                            // alignment slack
+}
+
+namespace {
+struct CurveWs {
+    unsigned *keys_a, *keys_b;
+    unsigned char *lab_a, *lab_b;
+    unsigned *tile_hist, *digit_total, *seg_totals;
+    TileInfo* info;
+    unsigned long long* auroc_acc;
+    double* ap_partial;
+};
+inline unsigned char* bump(unsigned char*& p, int64_t bytes) {
+    unsigned char* r = p;
+    p += (bytes + 255) / 256 * 256;
+    return r;
+}
+CurveWs carve(void* workspace, int64_t segments, int64_t n) {
+    const int64_t sort_tiles = (n + kSortTile - 1) / kSortTile;
+    const int64_t scan_tiles = (n + kScanTile - 1) / kScanTile;
+    unsigned char* p = reinterpret_cast<unsigned char*>(workspace);
+    CurveWs w;
+    w.keys_a = (unsigned*)bump(p, segments * n * 4);
+    w.keys_b = (unsigned*)bump(p, segments * n * 4);
+    w.lab_a = bump(p, segments * n + 16);
+    w.lab_b = bump(p, segments * n + 16);
+    w.tile_hist = (unsigned*)bump(p, segments * 256 * (sort_tiles + 1) * 4);
+    w.digit_total = (unsigned*)bump(p, segments * 256 * 4);
+    w.info = (TileInfo*)bump(p, segments * (scan_tiles + 1) * (int64_t)sizeof(TileInfo));
+    w.seg_totals = (unsigned*)bump(p, segments * 2 * 4);
+    w.auroc_acc = (unsigned long long*)bump(p, segments * 8);
+    w.ap_partial = (double*)bump(p, segments * (scan_tiles + 1) * 8);
+    return w;
+}
+}  // namespace
+
+// Exact-mode curve evaluation for `segments` one-vs-rest curves over `n` samples each.
+//   preds  : binary (num_classes == 1): [n] scores.  multiclass: [n, num_classes] row-major scores.
+//   target : [n] integer labels; positive for segment c is (target == c) (binary: target == pos_label).
+//   out_auroc / out_ap : float32 [segments];  out_counts : int64 [segments][3] = {n_pos, n_neg, n_distinct_thresholds}
+//   curve outputs (optional, all three or none): float32 [segments][n] each, valid prefix = n_distinct_thresholds.
+extern "C" int mb200_curve_evaluate(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                    int64_t n, int64_t num_classes, int64_t pos_label, void* workspace,
+                                    int64_t workspace_bytes, float* out_auroc, float* out_ap, int64_t* out_counts,
+                                    float* fps_out, float* tps_out, float* thr_out, void* stream) {
+    MB200_REQUIRE(n >= 1, "curve evaluation needs at least one sample (got %lld)", (long long)n);
+    MB200_REQUIRE(num_classes >= 1, "bad num_classes");
+    MB200_REQUIRE(n < (1ll << 31), "more than 2^31-1 samples per curve are not supported");
+    MB200_REQUIRE(preds && target && workspace && out_auroc && out_ap && out_counts, "NULL pointer");
+    const int64_t segments = num_classes;
+    MB200_REQUIRE(workspace_bytes >= mb200_curve_workspace_bytes(segments, n), "workspace too small");
+    MB200_REQUIRE((fps_out == nullptr) == (tps_out == nullptr) && (fps_out == nullptr) == (thr_out == nullptr),
+                  "curve outputs must be given all together or not at all");
+    MB200_REQUIRE(segments <= 65535, "at most 65535 curves per call");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CurveWs w = carve(workspace, segments, n);
+    const int ni = (int)n;
+    const int sort_tiles = (ni + kSortTile - 1) / kSortTile;
+    const int scan_tiles = (ni + kScanTile - 1) / kScanTile;
+
+    // ---- pack ----
+    if (segments == 1) {
+        const int grid = blocks_for(n, 256 * 4, sm_count() * 8);
+#define MB200_PACK(T) \
+    pack_binary_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, n, pos_label, w.keys_a, w.lab_a);
+        switch (preds_dtype) {
+            case MB200_F32: MB200_PACK(float) break;
+            case MB200_F16: MB200_PACK(__half) break;
+            case MB200_BF16: MB200_PACK(__nv_bfloat16) break;
+            default: set_error("scores must be f32/f16/bf16 (dtype tag %d)", preds_dtype); return MB200_ERR_UNSUPPORTED;
+        }
+#undef MB200_PACK
+    } else {
+        const dim3 grid((unsigned)((ni + 31) / 32), (unsigned)((segments + 31) / 32));
+#define MB200_PACK(T) \
+    pack_ovr_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, ni, (int)segments, w.keys_a, w.lab_a);
+        switch (preds_dtype) {
+            case MB200_F32: MB200_PACK(float) break;
+            case MB200_F16: MB200_PACK(__half) break;
+            case MB200_BF16: MB200_PACK(__nv_bfloat16) break;
+            default: set_error("scores must be f32/f16/bf16 (dtype tag %d)", preds_dtype); return MB200_ERR_UNSUPPORTED;
+        }
+#undef MB200_PACK
+    }
+    count_launch();
+
+    // ---- 4 x 8-bit LSD passes (ping-pong; an even number of passes leaves the result in the *_a buffers) ----
+    unsigned *kin = w.keys_a, *kout = w.keys_b;
+    unsigned char *lin = w.lab_a, *lout = w.lab_b;
+    const dim3 tgrid((unsigned)sort_tiles, (unsigned)segments);
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 8 * pass;
+        radix_hist_kernel<<<tgrid, kSortThreads, 0, st>>>(kin, ni, sort_tiles, shift, w.tile_hist);
+        radix_scan_kernel<<<dim3(256, (unsigned)segments), 256, 0, st>>>(w.tile_hist, sort_tiles, w.digit_total);
+        radix_scatter_kernel<<<tgrid, kSortThreads, 0, st>>>(kin, lin, kout, lout, ni, sort_tiles, shift, w.tile_hist,
+                                                            w.digit_total);
+        count_launch(), count_launch(), count_launch();
+        unsigned* tk = kin;
+        kin = kout;
+        kout = tk;
+        unsigned char* tl = lin;
+        lin = lout;
+        lout = tl;
+    }
+
+    // ---- scan ----
+    const dim3 sgrid((unsigned)scan_tiles, (unsigned)segments);
+    zero_u64_kernel<<<(int)((segments + 255) / 256), 256, 0, st>>>(w.auroc_acc, (int)segments);
+    scan_reduce_kernel<<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, scan_tiles, w.info);
+    scan_carry_kernel<<<(unsigned)segments, 256, 0, st>>>(w.info, scan_tiles, ni, w.seg_totals);
+    if (fps_out)
+        scan_apply_kernel<true><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, scan_tiles, w.info, w.auroc_acc,
+                                                                w.ap_partial, fps_out, tps_out, thr_out, n);
+    else
+        scan_apply_kernel<false><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, scan_tiles, w.info, w.auroc_acc,
+                                                                 w.ap_partial, nullptr, nullptr, nullptr, n);
+    scan_finalize_kernel<<<(int)((segments + 7) / 8), 256, 0, st>>>(w.auroc_acc, w.ap_partial, w.seg_totals, scan_tiles,
+                                                                    ni, (int)segments, out_auroc, out_ap, reinterpret_cast<long long*>(out_counts));
+    for (int i = 0; i < 5; ++i) count_launch();
+    return check_cuda(cudaGetLastError(), "curve evaluate launch");
+}

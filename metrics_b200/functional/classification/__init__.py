@@ -3,3 +3,13 @@ from metrics_b200.functional.classification.accuracy import multiclass_accuracy 
 from metrics_b200.functional.classification.confusion_matrix import multiclass_confusion_matrix  # noqa: F401
 from metrics_b200.functional.classification.f_beta import multiclass_f1_score, multiclass_fbeta_score  # noqa: F401
 from metrics_b200.functional.classification.stat_scores import multiclass_stat_scores  # noqa: F401
+from metrics_b200.functional.classification.auroc import binary_auroc, multiclass_auroc  # noqa: F401,E402
+from metrics_b200.functional.classification.average_precision import (  # noqa: F401,E402
+    binary_average_precision,
+    multiclass_average_precision,
+)
+from metrics_b200.functional.classification.precision_recall_curve import (  # noqa: F401,E402
+    binary_precision_recall_curve,
+    multiclass_precision_recall_curve,
+)
+from metrics_b200.functional.classification.roc import binary_roc, multiclass_roc  # noqa: F401,E402

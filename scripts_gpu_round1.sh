@@ -1,16 +1,33 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log
-for P in bulk16 bulk32; do
-MB200_ROWS_PATH=$P timeout 900 python -m pytest tests/test_confmat_gpu.py -m gpu -x -q > gpurun_out/pytest_gpu_$P.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_$P.log
-tail -3 gpurun_out/pytest_gpu_$P.log
-done
-timeout 600 python bench.py --steps 2000 --warmup 20 > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-for P in bulk16 bulk32; do
-MB200_ROWS_PATH=$P timeout 600 python bench.py --steps 2000 --warmup 20 --no-cpu-baseline > gpurun_out/bench_$P.json 2> gpurun_out/bench_$P.err; python -c "
-import json; d=json.load(open('gpurun_out/bench_$P.json')); print('$P', d['ms_per_step'], d['roofline']['frac'])"; tail -3 gpurun_out/bench_$P.err
-done
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:rows_vec_kernel -s 30 -c 2 -o gpurun_out/prof_confmat_vec python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_vec.log 2>&1
-MB200_ROWS_PATH=bulk32 timeout 900 ncu --set full --clock-control none --import-source on -k regex:rows_bulk_kernel -s 30 -c 2 -o gpurun_out/prof_confmat_bulk32 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_bulk.log 2>&1
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -40 gpurun_out/pytest_gpu.log
+timeout 600 python - > gpurun_out/cfg3_timing.log 2>&1 <<'PY'
+import time, torch, sys
+sys.path.insert(0, '.')
+from tests.helpers import cfg3_inputs
+from metrics_b200 import MetricCollection, _native
+from metrics_b200.classification import BinaryAUROC, BinaryAveragePrecision
+preds, target = cfg3_inputs()
+preds, target = preds.cuda(), target.cuda()
+mc = MetricCollection([BinaryAUROC(validate_args=False), BinaryAveragePrecision(validate_args=False)]).cuda()
+for rep in range(3):
+    mc.reset()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for i in range(1000): mc.update(preds[i], target[i])
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    res = mc.compute()
+    torch.cuda.synchronize(); t2 = time.perf_counter()
+    print(f"rep{rep}: update phase {1e3*(t1-t0):.2f} ms ({1e3*(t1-t0):.1f} us/update), compute {1e3*(t2-t1):.3f} ms", {k: float(v) for k, v in res.items()})
+# kernel-only: one curve_evaluate on 1e7 samples
+p, t = preds.reshape(-1), target.reshape(-1)
+for _ in range(3): _native.curve_evaluate(p, t)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10): _native.curve_evaluate(p, t)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 10
+print(f"curve_evaluate(1e7): {ms:.3f} ms -> {150e6/ms/1e6:.1f} GB/s on the 150 MB algorithmic figure, {450e6/ms/1e6:.1f} GB/s on the 4-pass model")
+PY
+cat gpurun_out/cfg3_timing.log

@@ -30,3 +30,10 @@ def golden_cls():
     import numpy as np
 
     return np.load(os.path.join(GOLDEN_DIR, "classification.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_curves():
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN_DIR, "curves.npz"), allow_pickle=False)

@@ -192,10 +192,131 @@ def classification_golden() -> dict:
     return out
 
 
+def curves_golden() -> dict:
+    from torchmetrics import MetricCollection
+    from torchmetrics.classification import (
+        BinaryAUROC,
+        BinaryAveragePrecision,
+        MulticlassAUROC,
+        MulticlassAveragePrecision,
+    )
+    from torchmetrics.functional.classification import (
+        binary_auroc,
+        binary_average_precision,
+        binary_precision_recall_curve,
+        binary_roc,
+        multiclass_auroc,
+        multiclass_average_precision,
+        multiclass_precision_recall_curve,
+        multiclass_roc,
+    )
+    from torchmetrics.functional.classification.precision_recall_curve import _binary_clf_curve
+
+    import warnings
+
+    warnings.simplefilter("ignore")
+    out: dict = {}
+    # ---- binary cases --------------------------------------------------------------------------------------------
+    g = torch.Generator().manual_seed(21)
+    cases = {}
+    cases["doc"] = (torch.tensor([0.1, 0.4, 0.35, 0.8]), torch.tensor([0, 0, 1, 1]))
+    cases["rand"] = (torch.rand(3000, generator=g), torch.randint(0, 2, (3000,), generator=g))
+    cases["ties"] = ((torch.rand(5000, generator=g) * 50).floor() / 50, torch.randint(0, 2, (5000,), generator=g))
+    cases["logits"] = (torch.randn(2000, generator=g) * 3, torch.randint(0, 2, (2000,), generator=g))
+    cases["allpos"] = (torch.rand(257, generator=g), torch.ones(257, dtype=torch.long))
+    cases["allneg"] = (torch.rand(257, generator=g), torch.zeros(257, dtype=torch.long))
+    cases["alltied"] = (torch.full((100,), 0.5), torch.randint(0, 2, (100,), generator=g))
+    cases["one"] = (torch.tensor([0.3]), torch.tensor([1]))
+    cases["odd"] = (torch.rand(4097, generator=g), torch.randint(0, 2, (4097,), generator=g))
+    cases["skew"] = (torch.rand(20000, generator=g), (torch.rand(20000, generator=g) < 0.01).long())
+    for name, (p, t) in cases.items():
+        out[f"bin/{name}/preds"] = p.numpy()
+        out[f"bin/{name}/target"] = t.numpy()
+        out[f"bin/{name}/auroc"] = binary_auroc(p, t).numpy()
+        out[f"bin/{name}/ap"] = binary_average_precision(p, t).numpy()
+        pf = torch.sigmoid(p) if name == "logits" else p
+        fps, tps, thr = _binary_clf_curve(pf, t)
+        out[f"bin/{name}/clf_fps"], out[f"bin/{name}/clf_tps"], out[f"bin/{name}/clf_thr"] = fps.numpy(), tps.numpy(), thr.numpy()
+        fpr, tpr, th = binary_roc(p, t)
+        out[f"bin/{name}/roc_fpr"], out[f"bin/{name}/roc_tpr"], out[f"bin/{name}/roc_thr"] = fpr.numpy(), tpr.numpy(), th.numpy()
+        pr, rc, th = binary_precision_recall_curve(p, t)
+        out[f"bin/{name}/prc_p"], out[f"bin/{name}/prc_r"], out[f"bin/{name}/prc_thr"] = pr.numpy(), rc.numpy(), th.numpy()
+        for mf in (0.5, 0.8):
+            out[f"bin/{name}/auroc_maxfpr{mf}"] = binary_auroc(p, t, max_fpr=mf).numpy()
+    p, t = cases["rand"]
+    t2 = t.clone()
+    t2[::9] = -1
+    out["bin/ignore/target"] = t2.numpy()
+    out["bin/ignore/auroc"] = binary_auroc(p, t2, ignore_index=-1).numpy()
+    out["bin/ignore/ap"] = binary_average_precision(p, t2, ignore_index=-1).numpy()
+    pb = cases["logits"][0].bfloat16()
+    out["bin/bf16/auroc"] = binary_auroc(pb, cases["logits"][1]).numpy()
+    out["bin/bf16/ap"] = binary_average_precision(pb, cases["logits"][1]).numpy()
+    out["bin/bf16/roc_thr"] = binary_roc(pb, cases["logits"][1])[2].float().numpy()
+
+    # ---- cfg3: 1000 x 10000 samples through a MetricCollection ----------------------------------------------------------
+    g = torch.Generator().manual_seed(0)
+    preds = torch.rand(1000, 10000, generator=g)
+    target = torch.randint(0, 2, (1000, 10000), generator=g)
+    mc = MetricCollection([BinaryAUROC(), BinaryAveragePrecision()])
+    for i in range(1000):
+        mc.update(preds[i], target[i])
+    res = mc.compute()
+    out["cfg3/auroc"] = res["BinaryAUROC"].numpy()
+    out["cfg3/ap"] = res["BinaryAveragePrecision"].numpy()
+    out["cfg3/preds_sha256"] = np.array(sha(preds))
+    out["cfg3/target_sha256"] = np.array(sha(target))
+    out["cfg3/compute_groups"] = np.array(str(mc.compute_groups))
+
+    # ---- multiclass ------------------------------------------------------------------------------------------------------
+    g = torch.Generator().manual_seed(33)
+    for C, N, kind in ((5, 400, "probs"), (5, 400, "logits"), (37, 1500, "logits"), (1000, 2048, "logits")):
+        logits = torch.randn(N, C, generator=g)
+        tgt = torch.randint(0, C, (N,), generator=g)
+        if C == 5:
+            tgt[tgt == 4] = 2  # class 4 has no positive sample
+        p = torch.softmax(logits, 1) if kind == "probs" else logits
+        key = f"mc/C{C}_{kind}"
+        if C <= 37:
+            out[f"{key}/preds"], out[f"{key}/target"] = p.numpy(), tgt.numpy()
+        else:
+            out[f"{key}/preds_sha256"], out[f"{key}/target_sha256"] = np.array(sha(p)), np.array(sha(tgt))
+        for avg in ("macro", "weighted", "none"):
+            out[f"{key}/auroc_{avg}"] = multiclass_auroc(p, tgt, C, average=avg).numpy()
+            out[f"{key}/ap_{avg}"] = multiclass_average_precision(p, tgt, C, average=avg).numpy()
+        if C == 5:
+            fpr, tpr, thr = multiclass_roc(p, tgt, C)
+            pr, rc, th2 = multiclass_precision_recall_curve(p, tgt, C)
+            for c in range(C):
+                out[f"{key}/roc_fpr{c}"], out[f"{key}/roc_tpr{c}"], out[f"{key}/roc_thr{c}"] = fpr[c].numpy(), tpr[c].numpy(), thr[c].numpy()
+                out[f"{key}/prc_p{c}"], out[f"{key}/prc_r{c}"], out[f"{key}/prc_thr{c}"] = pr[c].numpy(), rc[c].numpy(), th2[c].numpy()
+            t3 = tgt.clone()
+            t3[::6] = -1
+            out[f"{key}/ignore_target"] = t3.numpy()
+            out[f"{key}/ignore_auroc"] = multiclass_auroc(p, t3, C, average="none", ignore_index=-1).numpy()
+    # modular: cfg5-like single rank, 4 batches of [4096, 1000] fp32 logits (rank 0 stream: torch.manual_seed(0))
+    torch.manual_seed(0)
+    m_auc = MulticlassAUROC(num_classes=1000)
+    m_ap = MulticlassAveragePrecision(num_classes=1000)
+    for _ in range(2):
+        lg = torch.randn(4096, 1000)
+        tg = torch.randint(0, 1000, (4096,))
+        m_auc.update(lg, tg)
+        m_ap.update(lg, tg)
+    out["mc/cfg5_rank0_2batches/auroc"] = m_auc.compute().numpy()
+    out["mc/cfg5_rank0_2batches/ap"] = m_ap.compute().numpy()
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["classification"]
     if "classification" in which:
         data = classification_golden()
         path = os.path.join(HERE, "classification.npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
+    if "curves" in which:
+        data = curves_golden()
+        path = os.path.join(HERE, "curves.npz")
         np.savez_compressed(path, **data)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")

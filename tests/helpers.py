@@ -47,3 +47,37 @@ def stats_inputs(C: int, N: int):
 
 
 TORCH_DTYPES = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16, "f64": torch.float64}
+
+
+def cfg3_inputs():
+    g = torch.Generator().manual_seed(0)
+    preds = torch.rand(1000, 10000, generator=g)
+    target = torch.randint(0, 2, (1000, 10000), generator=g)
+    return preds, target
+
+
+MC_CASES = ((5, 400, "probs"), (5, 400, "logits"), (37, 1500, "logits"), (1000, 2048, "logits"))
+
+
+def mc_inputs(C: int, N: int, kind: str):
+    """Replays the generator stream of make_golden.py (curves, multiclass section)."""
+    g = torch.Generator().manual_seed(33)
+    for c, n, k in MC_CASES:
+        logits = torch.randn(n, c, generator=g)
+        tgt = torch.randint(0, c, (n,), generator=g)
+        if c == 5:
+            tgt[tgt == 4] = 2
+        p = torch.softmax(logits, 1) if k == "probs" else logits
+        if (c, n, k) == (C, N, kind):
+            return p, tgt
+    raise KeyError((C, N, kind))
+
+
+def cfg5_rank_batches(rank: int, n_batches: int):
+    torch.manual_seed(rank)
+    out = []
+    for _ in range(n_batches):
+        lg = torch.randn(4096, 1000)
+        tg = torch.randint(0, 1000, (4096,))
+        out.append((lg, tg))
+    return out
