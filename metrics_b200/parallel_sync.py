@@ -22,6 +22,8 @@ from metrics_b200.utilities.data import _flatten, dim_zero_cat, dim_zero_max, di
 from metrics_b200.utilities.distributed import gather_all_tensors
 
 _MAX_DIMS = 8
+_DTYPE_CODES = [torch.float32, torch.float64, torch.float16, torch.bfloat16, torch.int64, torch.int32, torch.int16,
+                torch.int8, torch.uint8, torch.bool]
 _INT_DTYPES = (torch.int64, torch.int32, torch.int16, torch.int8, torch.uint8)
 
 
@@ -38,9 +40,12 @@ def _reduce_op(fn: Any) -> Optional[Any]:
 
 def _gather_equal(t: Tensor, group: Any, world: int) -> Tensor:
     """Stack of the same-shaped tensor from every rank: [world, *t.shape]."""
-    out = torch.empty((world, *t.shape), dtype=t.dtype, device=t.device)
-    torch.distributed.all_gather_into_tensor(out, t.contiguous(), group=group)
-    return out
+    flat = t.contiguous().reshape(-1)
+    if flat.numel() == 0:
+        return torch.empty((world, *t.shape), dtype=t.dtype, device=t.device)
+    out = torch.empty(world * flat.numel(), dtype=t.dtype, device=t.device)
+    torch.distributed.all_gather_into_tensor(out, flat, group=group)
+    return out.reshape(world, *t.shape)
 
 
 def sync_states_bucketed(metric: Any, group: Optional[Any]) -> bool:
@@ -95,24 +100,28 @@ def sync_states_bucketed(metric: Any, group: Optional[Any]) -> bool:
             else:
                 locals_.append(dim_zero_cat(value).contiguous())
         dev = locals_[0].device
-        desc = torch.zeros((len(cat_states), 1 + _MAX_DIMS), dtype=torch.int64)
+        desc = torch.zeros((len(cat_states), 2 + _MAX_DIMS), dtype=torch.int64)
         for i, t in enumerate(locals_):
-            if t.ndim > _MAX_DIMS:
+            if t.ndim > _MAX_DIMS or t.dtype not in _DTYPE_CODES:
                 return False
             desc[i, 0] = t.ndim
+            desc[i, 1] = _DTYPE_CODES.index(t.dtype)
             for d, s in enumerate(t.shape):
-                desc[i, 1 + d] = s
+                desc[i, 2 + d] = s
         desc = desc.to(dev)
-        all_desc = _gather_equal(desc, group, world).cpu()  # [world, n_states, 1 + MAX_DIMS]; the one host sync
+        all_desc = _gather_equal(desc, group, world).cpu()  # [world, n_states, 2 + MAX_DIMS]; the one host sync
         for i, n in enumerate(cat_states):
             t = locals_[i]
-            shapes = [tuple(int(x) for x in all_desc[r, i, 1: 1 + int(all_desc[r, i, 0])]) for r in range(world)]
+            shapes = [tuple(int(x) for x in all_desc[r, i, 2: 2 + int(all_desc[r, i, 0])]) for r in range(world)]
             numels = [int(torch.Size(s).numel()) for s in shapes]
             nonempty = [r for r in range(world) if numels[r] > 0]
             if not nonempty:
                 setattr(metric, n, dim_zero_cat([t]) if t.numel() == 0 else t)
                 continue
-            dtype = t.dtype
+            # a rank that saw no data contributes an empty placeholder: it adopts the dtype the data-holding ranks use
+            dtype = _DTYPE_CODES[int(all_desc[nonempty[0], i, 1])]
+            if t.numel() == 0 and t.dtype != dtype:
+                t = t.to(dtype)
             trailing = shapes[nonempty[0]][1:]
             if all(s == shapes[0] for s in shapes):
                 gathered = _gather_equal(t, group, world)  # [world, n, *trailing]
