@@ -55,6 +55,7 @@ enum mb200_status {
 #define MB200_FLAG_TARGET_RANGE 1u /* a non-ignored target label was outside [0, num_classes) */
 #define MB200_FLAG_PREDS_RANGE 2u  /* an integer preds label was outside [0, num_classes)      */
 #define MB200_FLAG_SPIN_TIMEOUT 4u /* internal look-back wait exceeded its bound (results invalid) */
+#define MB200_FLAG_CAPACITY 8u     /* a per-image / per-class capacity of a kernel was exceeded (results invalid) */
 
 MB200_API int mb200_abi_version(void);
 MB200_API const char* mb200_last_error(void);
@@ -146,6 +147,34 @@ MB200_API int mb200_curve_evaluate(const void* preds, int preds_dtype, const voi
                                    int64_t n, int64_t num_classes, int64_t pos_label, void* workspace,
                                    int64_t workspace_bytes, float* out_auroc, float* out_ap, int64_t* out_counts,
                                    float* fps_out, float* tps_out, float* thr_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K8 — COCO-style bounding-box mAP / mAR evaluation on the device.
+ * Replaces detection/mean_ap.py:521-598 (MeanAveragePrecision.compute): the per-element host marshalling of
+ * :867-958 and the third-party pycocotools calls at :538-546 (COCOeval.evaluate / accumulate and maskApi.c:bbIou;
+ * algorithm restated with citations in oracle/coco_map.py).  `summarize` (means over the precision / recall tensors)
+ * is left to the caller.
+ *
+ * Inputs are the concatenation of all images (list position = image id):
+ *  det_box_xywh [n_det,4] f32, det_score [n_det] f32, det_label [n_det] i64, det_off [n_img+1] i32 (prefix counts)
+ *  gt_box_xywh  [n_gt,4]  f32, gt_label [n_gt] i64, gt_crowd [n_gt] u8, gt_area [n_gt] f64 (<= 0: use w*h),
+ *  gt_off [n_img+1] i32;  max_det_per_img / max_gt_per_img: largest per-image counts (sizes the shared-memory stage)
+ *  classes [num_classes] i64 sorted unique labels over detections and ground truths; micro != 0: one class for all.
+ *  iou_thr_host [n_iou_thr <= 16] f64 (HOST), rec_thr_dev [n_rec_thr] f64 (DEVICE), max_dets_host [n_max_dets <= 8]
+ *  i64 ascending (HOST).
+ * Outputs (device, f64), K = micro ? 1 : num_classes, A = 4 area ranges (all, small, medium, large):
+ *  precision [T, R, K, A, M], recall [T, K, A, M], scores [T, R, K, A, M]; -1 where COCOeval leaves -1.
+ * err_flag: optional device word; MB200_FLAG_CAPACITY is set when one image holds more than 256 ground truths of one
+ * class.  Returns MB200_ERR_UNSUPPORTED when an image is too large for the shared-memory stage.
+ * ------------------------------------------------------------------------------------------------ */
+MB200_API int64_t mb200_coco_map_workspace_bytes(int64_t n_det, int64_t num_classes, int64_t num_max_dets);
+MB200_API int mb200_coco_map_evaluate(
+    const float* det_box_xywh, const float* det_score, const int64_t* det_label, const int32_t* det_off,
+    const float* gt_box_xywh, const int64_t* gt_label, const uint8_t* gt_crowd, const double* gt_area,
+    const int32_t* gt_off, int64_t n_img, int64_t n_det, int64_t n_gt, int64_t max_det_per_img, int64_t max_gt_per_img,
+    const int64_t* classes, int64_t num_classes, int micro, const double* iou_thr_host, int64_t n_iou_thr,
+    const double* rec_thr_dev, int64_t n_rec_thr, const int64_t* max_dets_host, int64_t n_max_dets, void* workspace,
+    int64_t workspace_bytes, double* precision, double* recall, double* scores, uint32_t* err_flag, void* stream);
 
 #ifdef __cplusplus
 }

@@ -273,3 +273,54 @@ def curve_evaluate(preds: Tensor, target: Tensor, num_classes: int = 1, pos_labe
         )
     check(rc, "curve_evaluate")
     return auroc, ap, counts, curve
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K8 wrapper (COCO mAP)
+# ----------------------------------------------------------------------------------------------------------
+def coco_map_evaluate(
+    det_box: Tensor, det_score: Tensor, det_label: Tensor, det_counts: list,
+    gt_box: Tensor, gt_label: Tensor, gt_crowd: Tensor, gt_area: Tensor, gt_counts: list,
+    classes: Tensor, micro: bool, iou_thresholds: list, rec_thresholds: list, max_dets: list,
+):
+    """``mb200_coco_map_evaluate``: returns ``precision [T,R,K,A,M]``, ``recall [T,K,A,M]``, ``scores`` (float64)."""
+    import numpy as np
+
+    dev = require_cuda(det_box, det_score, det_label, gt_box, gt_label, gt_crowd, gt_area, classes)
+    n_img = len(det_counts)
+    det_off = torch.from_numpy(np.concatenate([[0], np.cumsum(det_counts)]).astype(np.int32)).to(dev, non_blocking=True)
+    gt_off = torch.from_numpy(np.concatenate([[0], np.cumsum(gt_counts)]).astype(np.int32)).to(dev, non_blocking=True)
+    n_det, n_gt = int(sum(det_counts)), int(sum(gt_counts))
+    K = 1 if micro else int(classes.numel())
+    T, R, M = len(iou_thresholds), len(rec_thresholds), len(max_dets)
+    det_box = det_box.to(torch.float32).contiguous()
+    det_score = det_score.to(torch.float32).contiguous()
+    det_label = det_label.to(torch.int64).contiguous()
+    gt_box = gt_box.to(torch.float32).contiguous()
+    gt_label = gt_label.to(torch.int64).contiguous()
+    gt_crowd = gt_crowd.to(torch.uint8).contiguous()
+    gt_area = gt_area.to(torch.float64).contiguous()
+    classes = classes.to(torch.int64).contiguous()
+    rec_dev = torch.tensor(rec_thresholds, dtype=torch.float64).to(dev, non_blocking=True)
+    lib_ = lib()
+    lib_.mb200_coco_map_workspace_bytes.restype = ctypes.c_int64
+    nbytes = int(lib_.mb200_coco_map_workspace_bytes(i64(n_det), i64(max(1, classes.numel())), i64(M)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    precision = torch.empty((T, R, K, 4, M), dtype=torch.float64, device=dev)
+    recall = torch.empty((T, K, 4, M), dtype=torch.float64, device=dev)
+    scores = torch.empty((T, R, K, 4, M), dtype=torch.float64, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    iou_host = (ctypes.c_double * T)(*[float(x) for x in iou_thresholds])
+    md_host = (ctypes.c_int64 * M)(*[int(x) for x in max_dets])
+    with on_device(dev):
+        rc = lib_.mb200_coco_map_evaluate(
+            ptr(det_box), ptr(det_score), ptr(det_label), ptr(det_off), ptr(gt_box), ptr(gt_label), ptr(gt_crowd),
+            ptr(gt_area), ptr(gt_off), i64(n_img), i64(n_det), i64(n_gt), i64(max(det_counts) if det_counts else 0),
+            i64(max(gt_counts) if gt_counts else 0), ptr(classes), i64(max(1, classes.numel())), int(micro), iou_host,
+            i64(T), ptr(rec_dev), i64(R), md_host, i64(M), ptr(ws), i64(nbytes), ptr(precision), ptr(recall),
+            ptr(scores), ptr(err), stream_handle(dev),
+        )
+    if rc == -3:
+        raise NotImplementedError("metrics_b200: " + lib_.mb200_last_error().decode("utf-8", "replace"))
+    check(rc, "coco_map_evaluate")
+    return precision, recall, scores, err

@@ -1,0 +1,256 @@
+"""COCO-style mean average precision / recall for object detection (reference: detection/mean_ap.py).
+
+The reference stores per-image tensors, then at ``compute`` copies every number to host Python objects and lets
+``pycocotools`` do all the arithmetic on the CPU.  Here the nine list states and their per-image layout are kept (same
+names, ``dist_reduce_fx=None``), but ``compute`` concatenates them once on the device and runs three kernels
+(`mb200_coco_map_evaluate`, csrc/cocomap.cu): per-image matching, a stable radix sort by (class, score), per-(class,
+area, maxDet) accumulation.  Only ``iou_type="bbox"`` is in scope.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import torch
+from torch import Tensor
+from typing_extensions import Literal
+
+from metrics_b200 import _native
+from metrics_b200.detection.helpers import _fix_empty_tensors, _input_validator
+from metrics_b200.metric import Metric
+from metrics_b200.utilities.prints import rank_zero_warn
+
+
+def _box_convert_to_xywh(boxes: Tensor, in_fmt: str) -> Tensor:
+    """torchvision.ops.box_convert(boxes, in_fmt, "xywh") restated op for op (fp32 rounding matters for parity):
+    cxcywh goes through xyxy first (reference detection/mean_ap.py:846)."""
+    if in_fmt == "xywh":
+        return boxes
+    if in_fmt == "cxcywh":
+        cx, cy, w, h = boxes.unbind(-1)
+        boxes = torch.stack((cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h), dim=-1)
+    x1, y1, x2, y2 = boxes.unbind(-1)
+    return torch.stack((x1, y1, x2 - x1, y2 - y1), dim=-1)
+
+
+class MeanAveragePrecision(Metric):
+    """mAP / mAR for bounding-box detection (reference :77-1063).
+
+    ``update(preds, target)``: lists (one entry per image) of dicts with ``boxes [n,4]``, ``scores [n]``, ``labels [n]``
+    (preds) and ``boxes``, ``labels`` and optional ``iscrowd``, ``area`` (target).  ``compute()`` returns the
+    reference's dict: ``map, map_50, map_75, map_small/medium/large, mar_{d1,d2,d3}, mar_small/medium/large,
+    map_per_class, mar_{d3}_per_class, classes`` (+ ``precision / recall / scores`` with ``extended_summary``).
+    """
+
+    is_differentiable: bool = False
+    higher_is_better: Optional[bool] = True
+    full_state_update: bool = True
+    plot_lower_bound: float = 0.0
+    plot_upper_bound: float = 1.0
+
+    detection_box: List[Tensor]
+    detection_scores: List[Tensor]
+    detection_labels: List[Tensor]
+    groundtruth_box: List[Tensor]
+    groundtruth_labels: List[Tensor]
+    groundtruth_crowds: List[Tensor]
+    groundtruth_area: List[Tensor]
+    warn_on_many_detections: bool = True
+
+    def __init__(
+        self,
+        box_format: Literal["xyxy", "xywh", "cxcywh"] = "xyxy",
+        iou_type: Union[Literal["bbox", "segm"], Tuple[str]] = "bbox",
+        iou_thresholds: Optional[List[float]] = None,
+        rec_thresholds: Optional[List[float]] = None,
+        max_detection_thresholds: Optional[List[int]] = None,
+        class_metrics: bool = False,
+        extended_summary: bool = False,
+        average: Literal["macro", "micro"] = "macro",
+        backend: Literal["pycocotools", "faster_coco_eval"] = "pycocotools",
+        **kwargs: Any,
+    ) -> None:
+        super().__init__(**kwargs)
+        allowed_box_formats = ("xyxy", "xywh", "cxcywh")
+        if box_format not in allowed_box_formats:
+            raise ValueError(f"Expected argument `box_format` to be one of {allowed_box_formats} but got {box_format}")
+        self.box_format = box_format
+        if isinstance(iou_type, str):
+            iou_type = (iou_type,)
+        if any(tp not in ("bbox", "segm") for tp in iou_type):
+            raise ValueError(f"Expected argument `iou_type` to be one of ('bbox', 'segm') or a tuple of, but got {iou_type}")
+        if tuple(iou_type) != ("bbox",):
+            raise NotImplementedError("metrics_b200: only `iou_type='bbox'` is implemented (mask IoU is out of scope)")
+        self.iou_type = tuple(iou_type)
+
+        if iou_thresholds is not None and not isinstance(iou_thresholds, list):
+            raise ValueError(
+                f"Expected argument `iou_thresholds` to either be `None` or a list of floats but got {iou_thresholds}"
+            )
+        self.iou_thresholds = iou_thresholds or torch.linspace(0.5, 0.95, round((0.95 - 0.5) / 0.05) + 1).tolist()
+        if rec_thresholds is not None and not isinstance(rec_thresholds, list):
+            raise ValueError(
+                f"Expected argument `rec_thresholds` to either be `None` or a list of floats but got {rec_thresholds}"
+            )
+        self.rec_thresholds = rec_thresholds or torch.linspace(0.0, 1.00, round(1.00 / 0.01) + 1).tolist()
+        if max_detection_thresholds is not None and not isinstance(max_detection_thresholds, list):
+            raise ValueError(
+                f"Expected argument `max_detection_thresholds` to either be `None` or a list of ints"
+                f" but got {max_detection_thresholds}"
+            )
+        if max_detection_thresholds is not None and len(max_detection_thresholds) != 3:
+            raise ValueError(
+                "When providing a list of max detection thresholds it should have length 3."
+                f" Got value {len(max_detection_thresholds)}"
+            )
+        self.max_detection_thresholds = sorted(int(x) for x in (max_detection_thresholds or [1, 10, 100]))
+        if not isinstance(class_metrics, bool):
+            raise ValueError("Expected argument `class_metrics` to be a boolean")
+        self.class_metrics = class_metrics
+        if not isinstance(extended_summary, bool):
+            raise ValueError("Expected argument `extended_summary` to be a boolean")
+        self.extended_summary = extended_summary
+        if average not in ("macro", "micro"):
+            raise ValueError(f"Expected argument `average` to be one of ('macro', 'micro') but got {average}")
+        self.average = average
+        if backend not in ("pycocotools", "faster_coco_eval"):
+            raise ValueError(
+                f"Expected argument `backend` to be one of ('pycocotools', 'faster_coco_eval') but got {backend}"
+            )
+        self.backend = backend  # accepted for API compatibility; the evaluation always runs on the device
+
+        for name in ("detection_box", "detection_mask", "detection_scores", "detection_labels", "groundtruth_box",
+                     "groundtruth_mask", "groundtruth_labels", "groundtruth_crowds", "groundtruth_area"):
+            self.add_state(name, default=[], dist_reduce_fx=None)
+
+    # ------------------------------------------------------------------------------------------------
+    def update(self, preds: List[Dict[str, Tensor]], target: List[Dict[str, Tensor]]) -> None:
+        """Append one entry per image to the list states (reference :478-519).  Box conversion to xywh runs as ONE
+        batched op per call; the per-image states are views into it."""
+        _input_validator(preds, target)
+        limit = self.max_detection_thresholds[-1]
+        if self.warn_on_many_detections and any(len(p["labels"]) > limit for p in preds):
+            rank_zero_warn(
+                f"Encountered more than {limit} detections in a single image. This means that certain detections with "
+                "the lowest scores will be ignored, that may have an undesirable impact on performance. Please consider"
+                " adjusting the `max_detection_threshold` to suit your use case. To disable this warning, set attribute "
+                "class `warn_on_many_detections=False`, after initializing the metric.",
+                UserWarning,
+            )
+        for boxes_list, store in (([_fix_empty_tensors(p["boxes"]) for p in preds], self.detection_box),
+                                  ([_fix_empty_tensors(t["boxes"]) for t in target], self.groundtruth_box)):
+            counts = [b.shape[0] if b.numel() > 0 else 0 for b in boxes_list]
+            nonempty = [b.reshape(-1, 4) for b in boxes_list if b.numel() > 0]
+            if nonempty:
+                converted = _box_convert_to_xywh(torch.cat(nonempty), self.box_format)
+                pieces = iter(converted.split([c for c in counts if c > 0]))
+            for b, c in zip(boxes_list, counts):
+                store.append(next(pieces) if c > 0 else b)
+        for item in preds:
+            self.detection_labels.append(item["labels"])
+            self.detection_scores.append(item["scores"])
+        for item in target:
+            self.groundtruth_labels.append(item["labels"])
+            self.groundtruth_crowds.append(item.get("iscrowd", torch.zeros_like(item["labels"])))
+            self.groundtruth_area.append(item.get("area", torch.zeros_like(item["labels"])))
+
+    def _get_classes(self) -> List[int]:
+        if len(self.detection_labels) > 0 or len(self.groundtruth_labels) > 0:
+            return torch.cat(self.detection_labels + self.groundtruth_labels).unique().cpu().tolist()
+        return []
+
+    @staticmethod
+    def _cat_or_empty(items: List[Tensor], shape: Tuple[int, ...], dtype: torch.dtype, device: torch.device) -> Tensor:
+        items = [t.reshape(-1, *shape[1:]) for t in items if t.numel() > 0]
+        if not items:
+            return torch.empty(shape, dtype=dtype, device=device)
+        return torch.cat(items).to(dtype)
+
+    def _stats_dict(self, stats: List[Tensor]) -> Dict[str, Tensor]:
+        mdt = self.max_detection_thresholds
+        names = ["map", "map_50", "map_75", "map_small", "map_medium", "map_large", f"mar_{mdt[0]}", f"mar_{mdt[1]}",
+                 f"mar_{mdt[2]}", "mar_small", "mar_medium", "mar_large"]
+        return {n: s.to(torch.float32).reshape(1) for n, s in zip(names, stats)}
+
+    def compute(self) -> Dict[str, Tensor]:
+        """Reference :521-598 (bbox)."""
+        dev = self.device
+        n_img = len(self.detection_labels)
+        minus_one = torch.tensor(-1.0, dtype=torch.float64, device=dev)
+        classes_list = self._get_classes()
+        result: Dict[str, Tensor] = {}
+        if n_img == 0:
+            result.update(self._stats_dict([minus_one] * 12))
+            result["map_per_class"] = torch.tensor([-1.0], dtype=torch.float32, device=dev)
+            result[f"mar_{self.max_detection_thresholds[-1]}_per_class"] = torch.tensor([-1.0], dtype=torch.float32, device=dev)
+            result["classes"] = torch.tensor(classes_list, dtype=torch.int32, device=dev)
+            return result
+
+        det_counts = [int(t.shape[0]) for t in self.detection_labels]
+        gt_counts = [int(t.shape[0]) for t in self.groundtruth_labels]
+        det_box = self._cat_or_empty(self.detection_box, (0, 4), torch.float32, dev)
+        det_score = self._cat_or_empty(self.detection_scores, (0,), torch.float32, dev)
+        det_label = self._cat_or_empty(self.detection_labels, (0,), torch.int64, dev)
+        gt_box = self._cat_or_empty(self.groundtruth_box, (0, 4), torch.float32, dev)
+        gt_label = self._cat_or_empty(self.groundtruth_labels, (0,), torch.int64, dev)
+        gt_crowd = self._cat_or_empty(self.groundtruth_crowds, (0,), torch.uint8, dev)
+        gt_area = self._cat_or_empty(self.groundtruth_area, (0,), torch.float64, dev)
+        classes = torch.tensor(classes_list, dtype=torch.int64, device=dev)
+        if classes.numel() == 0:  # images without any box at all
+            classes = torch.zeros(1, dtype=torch.int64, device=dev)
+
+        def run(micro: bool):
+            return _native.coco_map_evaluate(
+                det_box, det_score, det_label, det_counts, gt_box, gt_label, gt_crowd, gt_area, gt_counts, classes,
+                micro, self.iou_thresholds, self.rec_thresholds, self.max_detection_thresholds,
+            )
+
+        precision, recall, scores, err = run(self.average == "micro")
+        if int(err.item()) != 0:
+            raise NotImplementedError("metrics_b200: more than 256 ground truths of one class in a single image")
+        result.update(self._stats_dict(self._summarize(precision, recall)))
+        if self.extended_summary:
+            result["precision"] = precision
+            result["recall"] = recall
+            result["scores"] = scores
+        last = self.max_detection_thresholds[-1]
+        if self.class_metrics:
+            if self.average == "micro":  # the reference re-evaluates per class with the true labels (:566-569)
+                precision, recall, _, _ = run(False)
+            m_last = len(self.max_detection_thresholds) - 1
+            result["map_per_class"] = self._masked_mean(precision[:, :, :, 0, m_last], dims=(0, 1)).to(torch.float32)
+            result[f"mar_{last}_per_class"] = self._masked_mean(recall[:, :, 0, m_last], dims=(0,)).to(torch.float32)
+        else:
+            result["map_per_class"] = torch.tensor([-1.0], dtype=torch.float32, device=dev)
+            result[f"mar_{last}_per_class"] = torch.tensor([-1.0], dtype=torch.float32, device=dev)
+        result["classes"] = torch.tensor(classes_list, dtype=torch.int32, device=dev)
+        return result
+
+    @staticmethod
+    def _masked_mean(x: Tensor, dims: Optional[Tuple[int, ...]] = None) -> Tensor:
+        """Mean over the entries ``> -1`` (COCOeval._summarize), -1 if there is none."""
+        valid = x > -1
+        if dims is None:
+            cnt = valid.sum()
+            tot = torch.where(valid, x, torch.zeros_like(x)).sum()
+        else:
+            cnt = valid.sum(dim=dims)
+            tot = torch.where(valid, x, torch.zeros_like(x)).sum(dim=dims)
+        return torch.where(cnt > 0, tot / cnt.clamp(min=1), torch.full_like(tot, -1.0))
+
+    def _summarize(self, precision: Tensor, recall: Tensor) -> List[Tensor]:
+        """The 12 COCO statistics (COCOeval.summarize; stat order of reference :632-648)."""
+        m_last = len(self.max_detection_thresholds) - 1
+        thr = torch.tensor(self.iou_thresholds, dtype=torch.float64)
+
+        def ap(iou: Optional[float] = None, area: int = 0) -> Tensor:
+            s = precision[:, :, :, area, m_last]
+            if iou is not None:
+                sel = (thr == iou).nonzero().flatten().tolist()
+                s = s[sel]
+            return self._masked_mean(s)
+
+        def ar(area: int = 0, m: int = m_last) -> Tensor:
+            return self._masked_mean(recall[:, :, area, m])
+
+        return [ap(), ap(0.5), ap(0.75), ap(area=1), ap(area=2), ap(area=3), ar(m=0), ar(m=1), ar(m=m_last), ar(area=1),
+                ar(area=2), ar(area=3)]

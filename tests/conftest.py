@@ -37,3 +37,10 @@ def golden_curves():
     import numpy as np
 
     return np.load(os.path.join(GOLDEN_DIR, "curves.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_det():
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN_DIR, "detection.npz"), allow_pickle=False)

@@ -81,3 +81,59 @@ def cfg5_rank_batches(rank: int, n_batches: int):
         tg = torch.randint(0, 1000, (4096,))
         out.append((lg, tg))
     return out
+
+
+def synth_detection(seed: int, n_img: int, n_gt: int, n_det: int, n_cls: int, crowd_frac: float = 0.0, dup_scores: bool = False):
+    """Scaled-down BASELINE cfg4 recipe: 640x480 images, jittered-gt detections + random ones."""
+    g = torch.Generator().manual_seed(seed)
+    preds, target = [], []
+    for _ in range(n_img):
+        x1 = torch.rand(n_gt, generator=g) * 540
+        y1 = torch.rand(n_gt, generator=g) * 380
+        w = 8 + torch.rand(n_gt, generator=g) * 192
+        h = 8 + torch.rand(n_gt, generator=g) * 192
+        gt = torch.stack([x1, y1, (x1 + w).clamp(max=640), (y1 + h).clamp(max=480)], 1)
+        gl = torch.randint(0, n_cls, (n_gt,), generator=g)
+        crowd = (torch.rand(n_gt, generator=g) < crowd_frac).long()
+        n_jit = min(n_gt, n_det)
+        jit = gt[:n_jit] + torch.randn(n_jit, 4, generator=g) * 0.1 * torch.stack([w, h, w, h], 1)[:n_jit]
+        jl = torch.where(torch.rand(n_jit, generator=g) < 0.9, gl[:n_jit], torch.randint(0, n_cls, (n_jit,), generator=g))
+        n_rand = n_det - n_jit
+        rx = torch.rand(n_rand, generator=g) * 540
+        ry = torch.rand(n_rand, generator=g) * 380
+        rnd = torch.stack([rx, ry, rx + 8 + torch.rand(n_rand, generator=g) * 192, ry + 8 + torch.rand(n_rand, generator=g) * 192], 1)
+        boxes = torch.cat([jit, rnd])
+        boxes = torch.stack([boxes[:, 0].clamp(0, 639), boxes[:, 1].clamp(0, 479), boxes[:, 2], boxes[:, 3]], 1)
+        boxes[:, 2] = torch.maximum(boxes[:, 2], boxes[:, 0] + 1)
+        boxes[:, 3] = torch.maximum(boxes[:, 3], boxes[:, 1] + 1)
+        labels = torch.cat([jl, torch.randint(0, n_cls, (n_rand,), generator=g)])
+        scores = torch.rand(n_det, generator=g)
+        if dup_scores:
+            scores = (scores * 20).floor() / 20
+        preds.append({"boxes": boxes, "scores": scores, "labels": labels})
+        t = {"boxes": gt, "labels": gl}
+        if crowd_frac > 0:
+            t["iscrowd"] = crowd
+        target.append(t)
+    return preds, target
+
+
+LEGACY_MAP_CASES = {
+    "small": dict(seed=5, n_img=12, n_gt=6, n_det=20, n_cls=4),
+    "mid": dict(seed=6, n_img=60, n_gt=10, n_det=40, n_cls=8),
+    "dup": dict(seed=7, n_img=30, n_gt=8, n_det=30, n_cls=5, dup_scores=True),
+}
+
+
+def det_to_numpy(preds, target):
+    """list-of-dict torch inputs -> the per-image numpy lists oracle.coco_map.coco_evaluate takes"""
+    kw = dict(
+        det_boxes=[p["boxes"].numpy() for p in preds], det_scores=[p["scores"].numpy() for p in preds],
+        det_labels=[p["labels"].numpy() for p in preds], gt_boxes=[t["boxes"].numpy() for t in target],
+        gt_labels=[t["labels"].numpy() for t in target],
+    )
+    if any("iscrowd" in t for t in target):
+        kw["gt_crowds"] = [t.get("iscrowd", torch.zeros_like(t["labels"])).numpy() for t in target]
+    if any("area" in t for t in target):
+        kw["gt_areas"] = [t.get("area", torch.zeros_like(t["labels"])).numpy() for t in target]
+    return kw
