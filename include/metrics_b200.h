@@ -176,6 +176,23 @@ MB200_API int mb200_coco_map_evaluate(
     const double* rec_thr_dev, int64_t n_rec_thr, const int64_t* max_dets_host, int64_t n_max_dets, void* workspace,
     int64_t workspace_bytes, double* precision, double* recall, double* scores, uint32_t* err_flag, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K2 — binary / multilabel stat scores and confusion-matrix counts.
+ * Replaces functional/classification/stat_scores.py:95-134 (_binary_stat_scores_format/_update), :681-714
+ * (multilabel), confusion_matrix.py:119-152 and :477-516 (the 2x2 matrices are [[tn, fp], [fn, tp]]).
+ *
+ *  preds   : [n_outer, num_labels, inner] contiguous; floating scores (sigmoid applied when ANY value of the call
+ *            lies outside [0,1], then `> threshold`) or integer labels compared raw against the target.
+ *  target  : same layout, integer; elements equal to ignore_index are skipped; values outside {0,1} are skipped and
+ *            flagged (MB200_FLAG_TARGET_RANGE); integer preds outside {0,1} are flagged (MB200_FLAG_PREDS_RANGE).
+ *  counts  : int64 [G][4] += (tp, fp, tn, fn), G = num_labels, or n_outer * num_labels when samplewise != 0.
+ *  flag_scratch : 4-byte device word (required for floating preds).
+ * ------------------------------------------------------------------------------------------------ */
+MB200_API int mb200_binary_stat_counts(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                       int64_t n_outer, int64_t num_labels, int64_t inner, double threshold,
+                                       int has_ignore_index, int64_t ignore_index, int samplewise, int64_t* counts,
+                                       uint32_t* flag_scratch, uint32_t* err_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -324,3 +324,32 @@ def coco_map_evaluate(
         raise NotImplementedError("metrics_b200: " + lib_.mb200_last_error().decode("utf-8", "replace"))
     check(rc, "coco_map_evaluate")
     return precision, recall, scores, err
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K2 wrapper (binary / multilabel counts)
+# ----------------------------------------------------------------------------------------------------------
+def binary_stat_counts(
+    preds: Tensor, target: Tensor, num_labels: int, threshold: float, ignore_index: Optional[int], samplewise: bool,
+    counts: Optional[Tensor] = None, err_flag: Optional[Tensor] = None,
+) -> Tensor:
+    """(tp, fp, tn, fn) per group from ``[N, L, ...]`` (multilabel) or ``[N, ...]`` (binary, ``num_labels == 1`` with no
+    label dim) inputs; adds into ``counts [G, 4]`` (allocated zeroed when omitted)."""
+    dev = require_cuda(preds, target)
+    preds = preds.contiguous()
+    target = target.contiguous()
+    n_outer = preds.shape[0] if preds.ndim > 0 else 1
+    total = preds.numel()
+    inner = total // max(1, n_outer * num_labels) if total else 1
+    groups = n_outer * num_labels if samplewise else num_labels
+    if counts is None:
+        counts = torch.zeros((groups, 4), dtype=torch.int64, device=dev)
+    flag = torch.empty(1, dtype=torch.int32, device=dev) if preds.is_floating_point() else None
+    with on_device(dev):
+        rc = lib().mb200_binary_stat_counts(
+            ptr(preds), tag(preds), ptr(target), tag(target), i64(n_outer), i64(num_labels), i64(max(1, inner)),
+            ctypes.c_double(float(threshold)), int(ignore_index is not None), i64(ignore_index or 0), int(samplewise),
+            ptr(counts), ptr(flag), ptr(err_flag), stream_handle(dev),
+        )
+    check(rc, "binary_stat_counts")
+    return counts

@@ -10,3 +10,22 @@ from metrics_b200.classification.precision_recall_curve import (  # noqa: F401,E
     MulticlassPrecisionRecallCurve,
 )
 from metrics_b200.classification.roc import BinaryROC, MulticlassROC  # noqa: F401,E402
+from metrics_b200.classification.accuracy import Accuracy, BinaryAccuracy, MultilabelAccuracy  # noqa: F401,E402
+from metrics_b200.classification.confusion_matrix import (  # noqa: F401,E402
+    BinaryConfusionMatrix,
+    ConfusionMatrix,
+    MultilabelConfusionMatrix,
+)
+from metrics_b200.classification.f_beta import (  # noqa: F401,E402
+    BinaryF1Score,
+    BinaryFBetaScore,
+    F1Score,
+    FBetaScore,
+    MultilabelF1Score,
+    MultilabelFBetaScore,
+)
+from metrics_b200.classification.stat_scores import BinaryStatScores, MultilabelStatScores, StatScores  # noqa: F401,E402
+from metrics_b200.classification.auroc import AUROC  # noqa: F401,E402
+from metrics_b200.classification.average_precision import AveragePrecision  # noqa: F401,E402
+from metrics_b200.classification.precision_recall_curve import PrecisionRecallCurve  # noqa: F401,E402
+from metrics_b200.classification.roc import ROC  # noqa: F401,E402

@@ -71,3 +71,38 @@ class MulticlassAUROC(MulticlassPrecisionRecallCurve):
 
     def compute(self) -> Tensor:
         return _multiclass_auroc_compute(self._state(), self.num_classes, self.average, self.thresholds)
+
+
+from metrics_b200.classification.base import _ClassificationTaskWrapper  # noqa: E402
+from metrics_b200.metric import Metric  # noqa: E402
+from metrics_b200.utilities.enums import ClassificationTask  # noqa: E402
+
+
+def _no_multilabel(name: str) -> None:
+    raise NotImplementedError(f"metrics_b200: multilabel {name} is not implemented yet (binary and multiclass are)")
+
+
+class AUROC(_ClassificationTaskWrapper):
+    """Task wrapper (reference :432-547)."""
+
+    def __new__(  # type: ignore[misc]
+        cls,
+        task: Literal["binary", "multiclass", "multilabel"],
+        thresholds: Optional[Union[int, List[float], Tensor]] = None,
+        num_classes: Optional[int] = None,
+        num_labels: Optional[int] = None,
+        average: Optional[Literal["macro", "weighted", "none"]] = "macro",
+        max_fpr: Optional[float] = None,
+        ignore_index: Optional[int] = None,
+        validate_args: bool = True,
+        **kwargs: Any,
+    ) -> Metric:
+        task = ClassificationTask.from_str(task)
+        kwargs.update({"thresholds": thresholds, "ignore_index": ignore_index, "validate_args": validate_args})
+        if task == ClassificationTask.BINARY:
+            return BinaryAUROC(max_fpr, **kwargs)
+        if task == ClassificationTask.MULTICLASS:
+            if not isinstance(num_classes, int):
+                raise ValueError(f"`num_classes` is expected to be `int` but `{type(num_classes)} was passed.`")
+            return MulticlassAUROC(num_classes, average, **kwargs)
+        _no_multilabel("AUROC")

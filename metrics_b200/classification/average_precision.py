@@ -56,3 +56,33 @@ class MulticlassAveragePrecision(MulticlassPrecisionRecallCurve):
 
     def compute(self) -> Tensor:
         return _multiclass_average_precision_compute(self._state(), self.num_classes, self.average, self.thresholds)
+
+
+from metrics_b200.classification.base import _ClassificationTaskWrapper  # noqa: E402
+from metrics_b200.metric import Metric  # noqa: E402
+from metrics_b200.utilities.enums import ClassificationTask  # noqa: E402
+
+
+class AveragePrecision(_ClassificationTaskWrapper):
+    """Task wrapper (reference :430-544)."""
+
+    def __new__(  # type: ignore[misc]
+        cls,
+        task: Literal["binary", "multiclass", "multilabel"],
+        thresholds: Optional[Union[int, List[float], Tensor]] = None,
+        num_classes: Optional[int] = None,
+        num_labels: Optional[int] = None,
+        average: Optional[Literal["macro", "weighted", "none"]] = "macro",
+        ignore_index: Optional[int] = None,
+        validate_args: bool = True,
+        **kwargs: Any,
+    ) -> Metric:
+        task = ClassificationTask.from_str(task)
+        kwargs.update({"thresholds": thresholds, "ignore_index": ignore_index, "validate_args": validate_args})
+        if task == ClassificationTask.BINARY:
+            return BinaryAveragePrecision(**kwargs)
+        if task == ClassificationTask.MULTICLASS:
+            if not isinstance(num_classes, int):
+                raise ValueError(f"`num_classes` is expected to be `int` but `{type(num_classes)} was passed.`")
+            return MulticlassAveragePrecision(num_classes, average, **kwargs)
+        raise NotImplementedError("metrics_b200: multilabel AveragePrecision is not implemented yet")

@@ -115,3 +115,31 @@ class MulticlassPrecisionRecallCurve(Metric):
 
     def compute(self):
         return _multiclass_precision_recall_curve_compute(self._state(), self.num_classes, self.thresholds, self.average)
+
+
+from metrics_b200.classification.base import _ClassificationTaskWrapper  # noqa: E402
+from metrics_b200.utilities.enums import ClassificationTask  # noqa: E402
+
+
+class PrecisionRecallCurve(_ClassificationTaskWrapper):
+    """Task wrapper (reference :600-692)."""
+
+    def __new__(  # type: ignore[misc]
+        cls,
+        task: Literal["binary", "multiclass", "multilabel"],
+        thresholds: Optional[Union[int, List[float], Tensor]] = None,
+        num_classes: Optional[int] = None,
+        num_labels: Optional[int] = None,
+        ignore_index: Optional[int] = None,
+        validate_args: bool = True,
+        **kwargs: Any,
+    ) -> Metric:
+        task = ClassificationTask.from_str(task)
+        kwargs.update({"thresholds": thresholds, "ignore_index": ignore_index, "validate_args": validate_args})
+        if task == ClassificationTask.BINARY:
+            return BinaryPrecisionRecallCurve(**kwargs)
+        if task == ClassificationTask.MULTICLASS:
+            if not isinstance(num_classes, int):
+                raise ValueError(f"`num_classes` is expected to be `int` but `{type(num_classes)} was passed.`")
+            return MulticlassPrecisionRecallCurve(num_classes, **kwargs)
+        raise NotImplementedError("metrics_b200: multilabel PrecisionRecallCurve is not implemented yet")

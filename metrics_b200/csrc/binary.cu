@@ -1,0 +1,233 @@
+// K2 — binary / multilabel stat scores and confusion matrices: one pass over [n_outer, num_labels, inner] scores or
+// labels producing (tp, fp, tn, fn) per group (label, or sample x label when `samplewise`).
+//
+// Reference op chains replaced (src/torchmetrics/functional/classification/):
+//   stat_scores.py:95-134   _binary_stat_scores_format/_update      (sigmoid-if-logits, > threshold, 4 masked sums)
+//   stat_scores.py:681-714  _multilabel_stat_scores_format/_update
+//   confusion_matrix.py:119-152, :477-516  binary / multilabel confusion matrices ([[tn, fp], [fn, tp]] = same 4 counts)
+// The reference runs ~12 elementwise + reduction launches per update; here: a batch-global range-flag kernel (only for
+// floating scores) and ONE counting kernel.  Counters are privatised per thread (runs of equal group), then per CTA in
+// shared memory, then added to the int64 outputs with 64-bit REDs.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace mb200 {
+
+extern void count_launch();
+
+template <typename T>
+__device__ __forceinline__ float score_to_float(T x);
+template <>
+__device__ __forceinline__ float score_to_float<float>(float x) { return x; }
+template <>
+__device__ __forceinline__ float score_to_float<__half>(__half x) { return __half2float(x); }
+template <>
+__device__ __forceinline__ float score_to_float<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <>
+__device__ __forceinline__ float score_to_float<double>(double x) { return (float)x; }
+
+template <typename T>
+__device__ __forceinline__ float round_to(float x) { return x; }
+template <>
+__device__ __forceinline__ float round_to<__half>(float x) { return __half2float(__float2half_rn(x)); }
+template <>
+__device__ __forceinline__ float round_to<__nv_bfloat16>(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) bin_range_flag_kernel(const T* __restrict__ x, long long n, unsigned* flag) {
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = (double)x[i];
+        bad |= (v < 0.0) | (v > 1.0);
+    }
+    if (__any_sync(kFull, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+template <>
+__global__ void __launch_bounds__(256) bin_range_flag_kernel<__half>(const __half* __restrict__ x, long long n, unsigned* flag) {
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = __half2float(x[i]);
+        bad |= (v < 0.f) | (v > 1.f);
+    }
+    if (__any_sync(kFull, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+template <>
+__global__ void __launch_bounds__(256) bin_range_flag_kernel<__nv_bfloat16>(const __nv_bfloat16* __restrict__ x, long long n, unsigned* flag) {
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = __bfloat162float(x[i]);
+        bad |= (v < 0.f) | (v > 1.f);
+    }
+    if (__any_sync(kFull, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+
+struct BinArgs {
+    const void* preds;
+    const void* target;
+    int preds_dtype;
+    int target_dtype;
+    long long n_outer;
+    long long num_labels;
+    long long inner;
+    float threshold;
+    double threshold_d;
+    int has_ignore;
+    long long ignore_index;
+    int samplewise;
+    long long* counts;       // [G][4] tp, fp, tn, fn
+    const unsigned* logits;  // batch flag written by bin_range_flag_kernel (NULL for integer preds)
+    unsigned* err;
+    int smem_groups;  // > 0: groups privatised in shared memory
+};
+
+// prediction as the integer the reference compares with the target
+template <typename T>
+__device__ __forceinline__ long long pred_label(const BinArgs& a, long long i, bool logits) {
+    const T* __restrict__ p = reinterpret_cast<const T*>(a.preds);
+    float v = score_to_float<T>(p[i]);
+    if (logits) v = round_to<T>(1.0f / (1.0f + expf(-v)));  // ATen's sigmoid: fp32 math, result stored in T
+    return v > a.threshold ? 1 : 0;
+}
+template <>
+__device__ __forceinline__ long long pred_label<double>(const BinArgs& a, long long i, bool logits) {
+    double v = reinterpret_cast<const double*>(a.preds)[i];
+    if (logits) v = 1.0 / (1.0 + exp(-v));
+    return v > a.threshold_d ? 1 : 0;
+}
+struct IntPred {};
+template <>
+__device__ __forceinline__ long long pred_label<IntPred>(const BinArgs& a, long long i, bool) {
+    const long long p = load_label(a.preds, a.preds_dtype, i);
+    if ((unsigned long long)p > 1ull && a.err) atomicOr(a.err, MB200_FLAG_PREDS_RANGE);
+    return p;
+}
+
+__device__ __forceinline__ void flush_group(const BinArgs& a, long long group, unsigned (&c)[4], unsigned* sh) {
+    if (group < 0) return;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (c[k] == 0) continue;
+        if (sh) atomicAdd(&sh[group * 4 + k], c[k]);
+        else red_add_u64(a.counts + group * 4 + k, c[k]);
+        c[k] = 0;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bin_count_kernel(BinArgs a) {
+    extern __shared__ unsigned sh_counts[];
+    unsigned* sh = a.smem_groups > 0 ? sh_counts : nullptr;
+    if (sh) {
+        for (int i = threadIdx.x; i < a.smem_groups * 4; i += blockDim.x) sh[i] = 0;
+        __syncthreads();
+    }
+    const bool logits = a.logits != nullptr && (*a.logits) != 0u;
+    const long long per_outer = a.num_labels * a.inner;
+    const long long total = a.n_outer * per_outer;
+    // contiguous chunk per thread so that runs of equal group stay in registers
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const long long chunk = (total + nthreads - 1) / nthreads;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // warp-interleaved assignment keeps loads coalesced: thread handles i = base + k*32 + lane inside its warp's span
+    const long long warp_id = tid >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long span = chunk * 32;
+    const long long begin = warp_id * span;
+    const long long end = min(begin + span, total);
+    long long cur = -1;
+    unsigned c[4] = {0, 0, 0, 0};
+    for (long long i = begin + lane; i < end; i += 32) {
+        const long long t = load_label(a.target, a.target_dtype, i);
+        if (a.has_ignore && t == a.ignore_index) continue;
+        if ((unsigned long long)t > 1ull) {
+            if (a.err) atomicOr(a.err, MB200_FLAG_TARGET_RANGE);
+            continue;  // the reference counts such elements in none of the four masks
+        }
+        const long long p = pred_label<T>(a, i, logits);
+        const long long n = i / per_outer;
+        const long long l = (i - n * per_outer) / a.inner;
+        const long long group = a.samplewise ? n * a.num_labels + l : l;
+        if (group != cur) {
+            flush_group(a, cur, c, sh);
+            cur = group;
+        }
+        const bool eq = (p == t);
+        c[0] += (eq && t == 1);   // tp
+        c[1] += (!eq && t == 0);  // fp
+        c[2] += (eq && t == 0);   // tn
+        c[3] += (!eq && t == 1);  // fn
+    }
+    if (!a.samplewise && a.num_labels == 1) {
+        // single group: reduce across the warp before touching memory
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[k] = __reduce_add_sync(kFull, c[k]);
+        if (lane == 0) {
+            cur = 0;
+            flush_group(a, cur, c, sh);
+        }
+    } else {
+        flush_group(a, cur, c, sh);
+    }
+    if (sh) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < a.smem_groups * 4; i += blockDim.x) {
+            const unsigned v = sh[i];
+            if (v) red_add_u64(a.counts + i, v);
+        }
+    }
+}
+
+}  // namespace mb200
+
+using namespace mb200;
+
+extern "C" int mb200_binary_stat_counts(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                        int64_t n_outer, int64_t num_labels, int64_t inner, double threshold,
+                                        int has_ignore_index, int64_t ignore_index, int samplewise, int64_t* counts,
+                                        uint32_t* flag_scratch, uint32_t* err_flag, void* stream) {
+    MB200_REQUIRE(n_outer >= 0 && num_labels >= 1 && inner >= 1, "bad sizes");
+    const long long total = n_outer * num_labels * inner;
+    if (total == 0) return 0;
+    MB200_REQUIRE(preds && target && counts, "NULL pointer");
+    MB200_REQUIRE(target_dtype >= MB200_I64 && target_dtype <= MB200_BOOL, "target must be an integer tensor");
+    const bool float_preds = preds_dtype <= MB200_F64;
+    MB200_REQUIRE(!float_preds || flag_scratch, "flag_scratch is required for floating scores");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long groups = samplewise ? n_outer * num_labels : num_labels;
+    BinArgs a;
+    a.preds = preds, a.target = target, a.preds_dtype = preds_dtype, a.target_dtype = target_dtype;
+    a.n_outer = n_outer, a.num_labels = num_labels, a.inner = inner;
+    a.threshold = (float)threshold, a.threshold_d = threshold;
+    a.has_ignore = has_ignore_index, a.ignore_index = ignore_index, a.samplewise = samplewise;
+    a.counts = reinterpret_cast<long long*>(counts);
+    a.logits = float_preds ? flag_scratch : nullptr;
+    a.err = err_flag;
+    a.smem_groups = (groups <= 2048) ? (int)groups : 0;
+    const size_t smem = (size_t)a.smem_groups * 4 * sizeof(unsigned);
+    long long blocks = (total + 256 * 16 - 1) / (256 * 16);
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    const int grid = (int)blocks;
+    if (float_preds) {
+        MB200_CUDA_OK(cudaMemsetAsync(flag_scratch, 0, sizeof(uint32_t), st));
+        const int fgrid = (int)std::min<long long>(cap, (total + 2047) / 2048);
+        switch (preds_dtype) {
+            case MB200_F32: bin_range_flag_kernel<float><<<fgrid, 256, 0, st>>>((const float*)preds, total, flag_scratch); break;
+            case MB200_F16: bin_range_flag_kernel<__half><<<fgrid, 256, 0, st>>>((const __half*)preds, total, flag_scratch); break;
+            case MB200_BF16: bin_range_flag_kernel<__nv_bfloat16><<<fgrid, 256, 0, st>>>((const __nv_bfloat16*)preds, total, flag_scratch); break;
+            case MB200_F64: bin_range_flag_kernel<double><<<fgrid, 256, 0, st>>>((const double*)preds, total, flag_scratch); break;
+        }
+        count_launch();
+    }
+    switch (preds_dtype) {
+        case MB200_F32: bin_count_kernel<float><<<grid, 256, smem, st>>>(a); break;
+        case MB200_F16: bin_count_kernel<__half><<<grid, 256, smem, st>>>(a); break;
+        case MB200_BF16: bin_count_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(a); break;
+        case MB200_F64: bin_count_kernel<double><<<grid, 256, smem, st>>>(a); break;
+        default: bin_count_kernel<IntPred><<<grid, 256, smem, st>>>(a); break;
+    }
+    count_launch();
+    return check_cuda(cudaGetLastError(), "binary stat counts launch");
+}

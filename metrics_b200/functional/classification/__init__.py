@@ -13,3 +13,20 @@ from metrics_b200.functional.classification.precision_recall_curve import (  # n
     multiclass_precision_recall_curve,
 )
 from metrics_b200.functional.classification.roc import binary_roc, multiclass_roc  # noqa: F401,E402
+from metrics_b200.functional.classification.accuracy import binary_accuracy, multilabel_accuracy  # noqa: F401,E402
+from metrics_b200.functional.classification.confusion_matrix import (  # noqa: F401,E402
+    binary_confusion_matrix,
+    confusion_matrix,
+    multilabel_confusion_matrix,
+)
+from metrics_b200.functional.classification.f_beta import (  # noqa: F401,E402
+    binary_f1_score,
+    binary_fbeta_score,
+    multilabel_f1_score,
+    multilabel_fbeta_score,
+)
+from metrics_b200.functional.classification.stat_scores import (  # noqa: F401,E402
+    binary_stat_scores,
+    multilabel_stat_scores,
+    stat_scores,
+)

@@ -120,3 +120,125 @@ def multiclass_confusion_matrix(
     confmat = torch.zeros(num_classes, num_classes, dtype=torch.int64, device=preds.device)
     _multiclass_confusion_matrix_update_(confmat, preds, target, num_classes, ignore_index, validate_args)
     return _multiclass_confusion_matrix_compute(confmat, normalize)
+
+
+# =========================================================================================================
+# binary / multilabel (kernel K2): the 2x2 matrix is [[tn, fp], [fn, tp]]
+# =========================================================================================================
+from metrics_b200.functional.classification import _binary_counts as _bc  # noqa: E402
+
+
+def _counts_to_confmat(c: Tensor) -> Tensor:
+    tp, fp, tn, fn = c.unbind(-1)
+    return torch.stack([torch.stack([tn, fp], -1), torch.stack([fn, tp], -1)], -2)
+
+
+def _binary_confusion_matrix_arg_validation(
+    threshold: float = 0.5, ignore_index: Optional[int] = None, normalize: Optional[str] = None
+) -> None:
+    if not (isinstance(threshold, float) and (0 <= threshold <= 1)):
+        raise ValueError(f"Expected argument `threshold` to be a float in the [0,1] range, but got {threshold}.")
+    if ignore_index is not None and not isinstance(ignore_index, int):
+        raise ValueError(f"Expected argument `ignore_index` to either be `None` or an integer, but got {ignore_index}")
+    if normalize not in _NORMALIZE:
+        raise ValueError(f"Expected argument `normalize` to be one of {_NORMALIZE}, but got {normalize}.")
+
+
+def _binary_confusion_matrix_tensor_validation(preds: Tensor, target: Tensor, ignore_index: Optional[int] = None) -> None:
+    _bc.binary_shape_validation(preds, target, "global")
+
+
+def _binary_confusion_matrix_update(
+    preds: Tensor, target: Tensor, threshold: float = 0.5, ignore_index: Optional[int] = None, validate_args: bool = False
+) -> Tensor:
+    """FUSED format+update (reference :119-152): ``[2, 2]`` int64 counts of this batch."""
+    return _counts_to_confmat(_bc.counts(preds, target, 1, threshold, ignore_index, False, validate_args))[0]
+
+
+def _binary_confusion_matrix_compute(confmat: Tensor, normalize: Optional[str] = None) -> Tensor:
+    return _confusion_matrix_reduce(confmat, normalize)
+
+
+def binary_confusion_matrix(
+    preds: Tensor,
+    target: Tensor,
+    threshold: float = 0.5,
+    normalize: Optional[Literal["true", "pred", "all", "none"]] = None,
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+) -> Tensor:
+    """``[[tn, fp], [fn, tp]]`` (reference :164-228)."""
+    if validate_args:
+        _binary_confusion_matrix_arg_validation(threshold, ignore_index, normalize)
+        _binary_confusion_matrix_tensor_validation(preds, target, ignore_index)
+    confmat = _binary_confusion_matrix_update(preds, target, threshold, ignore_index, validate_args)
+    return _binary_confusion_matrix_compute(confmat, normalize)
+
+
+def _multilabel_confusion_matrix_arg_validation(
+    num_labels: int, threshold: float = 0.5, ignore_index: Optional[int] = None, normalize: Optional[str] = None
+) -> None:
+    if not isinstance(num_labels, int) or num_labels < 2:
+        raise ValueError(f"Expected argument `num_labels` to be an integer larger than 1, but got {num_labels}")
+    _binary_confusion_matrix_arg_validation(threshold, ignore_index, normalize)
+
+
+def _multilabel_confusion_matrix_tensor_validation(
+    preds: Tensor, target: Tensor, num_labels: int, ignore_index: Optional[int] = None
+) -> None:
+    _bc.multilabel_shape_validation(preds, target, num_labels, "global")
+
+
+def _multilabel_confusion_matrix_update(
+    preds: Tensor, target: Tensor, num_labels: int, threshold: float = 0.5, ignore_index: Optional[int] = None,
+    validate_args: bool = False,
+) -> Tensor:
+    """FUSED format+update (reference :477-516): ``[L, 2, 2]`` int64 counts of this batch."""
+    return _counts_to_confmat(_bc.counts(preds, target, num_labels, threshold, ignore_index, False, validate_args))
+
+
+def _multilabel_confusion_matrix_compute(confmat: Tensor, normalize: Optional[str] = None) -> Tensor:
+    return _confusion_matrix_reduce(confmat, normalize)
+
+
+def multilabel_confusion_matrix(
+    preds: Tensor,
+    target: Tensor,
+    num_labels: int,
+    threshold: float = 0.5,
+    normalize: Optional[Literal["true", "pred", "all", "none"]] = None,
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+) -> Tensor:
+    """Per-label ``[[tn, fp], [fn, tp]]`` (reference :527-600)."""
+    if validate_args:
+        _multilabel_confusion_matrix_arg_validation(num_labels, threshold, ignore_index, normalize)
+        _multilabel_confusion_matrix_tensor_validation(preds, target, num_labels, ignore_index)
+    confmat = _multilabel_confusion_matrix_update(preds, target, num_labels, threshold, ignore_index, validate_args)
+    return _multilabel_confusion_matrix_compute(confmat, normalize)
+
+
+def confusion_matrix(
+    preds: Tensor,
+    target: Tensor,
+    task: Literal["binary", "multiclass", "multilabel"],
+    threshold: float = 0.5,
+    num_classes: Optional[int] = None,
+    num_labels: Optional[int] = None,
+    normalize: Optional[str] = None,
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+) -> Tensor:
+    """Task dispatcher (reference :603-655)."""
+    from metrics_b200.utilities.enums import ClassificationTask
+
+    task = ClassificationTask.from_str(task)
+    if task == ClassificationTask.BINARY:
+        return binary_confusion_matrix(preds, target, threshold, normalize, ignore_index, validate_args)
+    if task == ClassificationTask.MULTICLASS:
+        if not isinstance(num_classes, int):
+            raise ValueError(f"`num_classes` is expected to be `int` but `{type(num_classes)} was passed.`")
+        return multiclass_confusion_matrix(preds, target, num_classes, normalize, ignore_index, validate_args)
+    if not isinstance(num_labels, int):
+        raise ValueError(f"`num_labels` is expected to be `int` but `{type(num_labels)} was passed.`")
+    return multilabel_confusion_matrix(preds, target, num_labels, threshold, normalize, ignore_index, validate_args)

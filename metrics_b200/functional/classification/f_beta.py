@@ -88,3 +88,86 @@ def multiclass_f1_score(
     return multiclass_fbeta_score(
         preds, target, 1.0, num_classes, average, top_k, multidim_average, ignore_index, validate_args, zero_division
     )
+
+
+# ---- binary / multilabel ---------------------------------------------------------------------------------
+from metrics_b200.functional.classification.stat_scores import (  # noqa: E402
+    _binary_stat_scores_arg_validation,
+    _binary_stat_scores_tensor_validation,
+    _binary_stat_scores_update,
+    _multilabel_stat_scores_arg_validation,
+    _multilabel_stat_scores_tensor_validation,
+    _multilabel_stat_scores_update,
+)
+
+
+def binary_fbeta_score(
+    preds: Tensor,
+    target: Tensor,
+    beta: float,
+    threshold: float = 0.5,
+    multidim_average: Literal["global", "samplewise"] = "global",
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+    zero_division: float = 0,
+) -> Tensor:
+    """Reference :80-160."""
+    if validate_args:
+        _fbeta_arg_validation(beta)
+        _binary_stat_scores_arg_validation(threshold, multidim_average, ignore_index, zero_division)
+        _binary_stat_scores_tensor_validation(preds, target, multidim_average, ignore_index)
+    tp, fp, tn, fn = _binary_stat_scores_update(preds, target, threshold, multidim_average, ignore_index, validate_args)
+    return _fbeta_reduce(tp, fp, tn, fn, beta, average="binary", multidim_average=multidim_average, zero_division=zero_division)
+
+
+def binary_f1_score(
+    preds: Tensor,
+    target: Tensor,
+    threshold: float = 0.5,
+    multidim_average: Literal["global", "samplewise"] = "global",
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+    zero_division: float = 0,
+) -> Tensor:
+    return binary_fbeta_score(preds, target, 1.0, threshold, multidim_average, ignore_index, validate_args, zero_division)
+
+
+def multilabel_fbeta_score(
+    preds: Tensor,
+    target: Tensor,
+    beta: float,
+    num_labels: int,
+    threshold: float = 0.5,
+    average: Optional[Literal["micro", "macro", "weighted", "none"]] = "macro",
+    multidim_average: Literal["global", "samplewise"] = "global",
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+    zero_division: float = 0,
+) -> Tensor:
+    """Reference :290-400."""
+    if validate_args:
+        _fbeta_arg_validation(beta)
+        _multilabel_stat_scores_arg_validation(num_labels, threshold, average, multidim_average, ignore_index, zero_division)
+        _multilabel_stat_scores_tensor_validation(preds, target, num_labels, multidim_average, ignore_index)
+    tp, fp, tn, fn = _multilabel_stat_scores_update(
+        preds, target, num_labels, threshold, multidim_average, ignore_index, validate_args
+    )
+    return _fbeta_reduce(
+        tp, fp, tn, fn, beta, average=average, multidim_average=multidim_average, multilabel=True, zero_division=zero_division
+    )
+
+
+def multilabel_f1_score(
+    preds: Tensor,
+    target: Tensor,
+    num_labels: int,
+    threshold: float = 0.5,
+    average: Optional[Literal["micro", "macro", "weighted", "none"]] = "macro",
+    multidim_average: Literal["global", "samplewise"] = "global",
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+    zero_division: float = 0,
+) -> Tensor:
+    return multilabel_fbeta_score(
+        preds, target, 1.0, num_labels, threshold, average, multidim_average, ignore_index, validate_args, zero_division
+    )

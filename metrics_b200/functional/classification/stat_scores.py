@@ -180,3 +180,169 @@ def multiclass_stat_scores(
     if micro:
         states = [s.reshape(()) for s in states]
     return _multiclass_stat_scores_compute(*states, average, multidim_average)
+
+
+# =========================================================================================================
+# binary / multilabel (kernel K2, csrc/binary.cu)
+# =========================================================================================================
+from metrics_b200.functional.classification import _binary_counts as _bc  # noqa: E402
+
+
+def _binary_stat_scores_arg_validation(
+    threshold: float = 0.5, multidim_average: str = "global", ignore_index: Optional[int] = None, zero_division: float = 0
+) -> None:
+    _bc.check_threshold(threshold)
+    _bc.check_common(multidim_average, ignore_index, zero_division)
+
+
+def _binary_stat_scores_tensor_validation(
+    preds: Tensor, target: Tensor, multidim_average: str = "global", ignore_index: Optional[int] = None
+) -> None:
+    """Shape rules (reference :49-88); values are range-checked inside the counting kernel."""
+    _bc.binary_shape_validation(preds, target, multidim_average)
+
+
+def _binary_stat_scores_update(
+    preds: Tensor,
+    target: Tensor,
+    threshold: float = 0.5,
+    multidim_average: str = "global",
+    ignore_index: Optional[int] = None,
+    validate_args: bool = False,
+) -> tuple[Tensor, Tensor, Tensor, Tensor]:
+    """FUSED format+update (reference :95-134): sigmoid-if-logits, threshold, ignore mask and the four masked sums in
+    one counting kernel.  Returns 0-d tensors (global) or ``[N]`` tensors (samplewise)."""
+    samplewise = multidim_average == "samplewise"
+    c = _bc.counts(preds, target, 1, threshold, ignore_index, samplewise, validate_args)
+    tp, fp, tn, fn = c.unbind(-1)
+    if not samplewise:
+        return tp.reshape(()), fp.reshape(()), tn.reshape(()), fn.reshape(())
+    return tp.squeeze(), fp.squeeze(), tn.squeeze(), fn.squeeze()
+
+
+def _binary_stat_scores_compute(tp: Tensor, fp: Tensor, tn: Tensor, fn: Tensor, multidim_average: str = "global") -> Tensor:
+    return torch.stack([tp, fp, tn, fn, tp + fn], dim=0 if multidim_average == "global" else 1).squeeze()
+
+
+def binary_stat_scores(
+    preds: Tensor,
+    target: Tensor,
+    threshold: float = 0.5,
+    multidim_average: Literal["global", "samplewise"] = "global",
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+) -> Tensor:
+    """tp, fp, tn, fn, support for binary inputs (reference :137-213)."""
+    if validate_args:
+        _binary_stat_scores_arg_validation(threshold, multidim_average, ignore_index)
+        _binary_stat_scores_tensor_validation(preds, target, multidim_average, ignore_index)
+    tp, fp, tn, fn = _binary_stat_scores_update(preds, target, threshold, multidim_average, ignore_index, validate_args)
+    return _binary_stat_scores_compute(tp, fp, tn, fn, multidim_average)
+
+
+def _multilabel_stat_scores_arg_validation(
+    num_labels: int,
+    threshold: float = 0.5,
+    average: Optional[str] = "macro",
+    multidim_average: str = "global",
+    ignore_index: Optional[int] = None,
+    zero_division: float = 0,
+) -> None:
+    if not isinstance(num_labels, int) or num_labels < 2:
+        raise ValueError(f"Expected argument `num_labels` to be an integer larger than 1, but got {num_labels}")
+    if not (isinstance(threshold, float) and (0 <= threshold <= 1)):
+        raise ValueError(f"Expected argument `threshold` to be a float, but got {threshold}.")
+    if average not in _AVERAGES:
+        raise ValueError(f"Expected argument `average` to be one of {_AVERAGES}, but got {average}")
+    _bc.check_common(multidim_average, ignore_index, zero_division)
+
+
+def _multilabel_stat_scores_tensor_validation(
+    preds: Tensor, target: Tensor, num_labels: int, multidim_average: str, ignore_index: Optional[int] = None
+) -> None:
+    _bc.multilabel_shape_validation(preds, target, num_labels, multidim_average)
+
+
+def _multilabel_stat_scores_update(
+    preds: Tensor,
+    target: Tensor,
+    num_labels: int,
+    threshold: float = 0.5,
+    multidim_average: str = "global",
+    ignore_index: Optional[int] = None,
+    validate_args: bool = False,
+) -> tuple[Tensor, Tensor, Tensor, Tensor]:
+    """FUSED format+update (reference :681-714): ``[L]`` (global) or ``[N, L]`` (samplewise) counters."""
+    samplewise = multidim_average == "samplewise"
+    c = _bc.counts(preds, target, num_labels, threshold, ignore_index, samplewise, validate_args)
+    if samplewise:
+        c = c.reshape(preds.shape[0], num_labels, 4)
+    tp, fp, tn, fn = c.unbind(-1)
+    return tp, fp, tn, fn
+
+
+def _multilabel_stat_scores_compute(
+    tp: Tensor, fp: Tensor, tn: Tensor, fn: Tensor, average: Optional[str] = "macro", multidim_average: str = "global"
+) -> Tensor:
+    res = torch.stack([tp, fp, tn, fn, tp + fn], dim=-1)
+    sum_dim = 0 if multidim_average == "global" else 1
+    if average == "micro":
+        return res.sum(sum_dim)
+    if average == "macro":
+        return res.float().mean(sum_dim)
+    if average == "weighted":
+        w = tp + fn
+        return (res * (w / w.sum()).reshape(*w.shape, 1)).sum(sum_dim)
+    if average is None or average == "none":
+        return res
+    return None
+
+
+def multilabel_stat_scores(
+    preds: Tensor,
+    target: Tensor,
+    num_labels: int,
+    threshold: float = 0.5,
+    average: Optional[Literal["micro", "macro", "weighted", "none"]] = "macro",
+    multidim_average: Literal["global", "samplewise"] = "global",
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+) -> Tensor:
+    """tp, fp, tn, fn, support per label (reference :748-860)."""
+    if validate_args:
+        _multilabel_stat_scores_arg_validation(num_labels, threshold, average, multidim_average, ignore_index)
+        _multilabel_stat_scores_tensor_validation(preds, target, num_labels, multidim_average, ignore_index)
+    tp, fp, tn, fn = _multilabel_stat_scores_update(
+        preds, target, num_labels, threshold, multidim_average, ignore_index, validate_args
+    )
+    return _multilabel_stat_scores_compute(tp, fp, tn, fn, average, multidim_average)
+
+
+def stat_scores(
+    preds: Tensor,
+    target: Tensor,
+    task: Literal["binary", "multiclass", "multilabel"],
+    threshold: float = 0.5,
+    num_classes: Optional[int] = None,
+    num_labels: Optional[int] = None,
+    average: Optional[str] = "micro",
+    multidim_average: Optional[str] = "global",
+    top_k: Optional[int] = 1,
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+) -> Tensor:
+    """Task dispatcher (reference :1100-1162)."""
+    from metrics_b200.utilities.enums import ClassificationTask
+
+    task = ClassificationTask.from_str(task)
+    if task == ClassificationTask.BINARY:
+        return binary_stat_scores(preds, target, threshold, multidim_average, ignore_index, validate_args)
+    if task == ClassificationTask.MULTICLASS:
+        if not isinstance(num_classes, int):
+            raise ValueError(f"`num_classes` is expected to be `int` but `{type(num_classes)} was passed.`")
+        if not isinstance(top_k, int):
+            raise ValueError(f"`top_k` is expected to be `int` but `{type(top_k)} was passed.`")
+        return multiclass_stat_scores(preds, target, num_classes, average, top_k, multidim_average, ignore_index, validate_args)
+    if not isinstance(num_labels, int):
+        raise ValueError(f"`num_labels` is expected to be `int` but `{type(num_labels)} was passed.`")
+    return multilabel_stat_scores(preds, target, num_labels, threshold, average, multidim_average, ignore_index, validate_args)

@@ -108,3 +108,54 @@ def fbeta_reduce(tp, fp, tn, fn, beta: float, average, zero_division: float = 0.
     if average == "micro":
         return score
     return _adjust_weights_safe_divide(score, average, False, tp, fp, fn)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# binary / multilabel stat scores and confusion matrices
+# ---------------------------------------------------------------------------------------------------------
+def _sigmoid_if_logits(preds: np.ndarray) -> np.ndarray:
+    """normalize_logits_if_needed(preds, "sigmoid") (utilities/compute.py:190-229), fp32 math."""
+    with np.errstate(invalid="ignore"):
+        cond = (preds < 0).any() or (preds > 1).any()
+    if not cond:
+        return preds
+    x = preds.astype(np.float32)
+    return (1.0 / (1.0 + np.exp(-x, dtype=np.float32))).astype(np.float32)
+
+
+def binary_stat_scores(preds, target, threshold: float = 0.5, ignore_index: Optional[int] = None, samplewise: bool = False):
+    """_binary_stat_scores_format + _update (stat_scores.py:95-134)."""
+    if np.issubdtype(preds.dtype, np.floating):
+        preds = _sigmoid_if_logits(preds) > threshold
+    p = preds.reshape(preds.shape[0], -1).astype(np.int64)
+    t = target.reshape(target.shape[0], -1).astype(np.int64).copy()
+    if ignore_index is not None:
+        t[t == ignore_index] = -1
+    axis = (1,) if samplewise else (0, 1)
+    tp = ((t == p) & (t == 1)).sum(axis)
+    fn = ((t != p) & (t == 1)).sum(axis)
+    fp = ((t != p) & (t == 0)).sum(axis)
+    tn = ((t == p) & (t == 0)).sum(axis)
+    return tp, fp, tn, fn
+
+
+def multilabel_stat_scores(preds, target, num_labels: int, threshold: float = 0.5, ignore_index: Optional[int] = None,
+                           samplewise: bool = False):
+    """_multilabel_stat_scores_format + _update (stat_scores.py:681-714)."""
+    if np.issubdtype(preds.dtype, np.floating):
+        preds = _sigmoid_if_logits(preds) > threshold
+    p = preds.reshape(preds.shape[0], preds.shape[1], -1).astype(np.int64)
+    t = target.reshape(target.shape[0], target.shape[1], -1).astype(np.int64).copy()
+    if ignore_index is not None:
+        t[t == ignore_index] = -1
+    axis = (2,) if samplewise else (0, 2)
+    tp = ((t == p) & (t == 1)).sum(axis)
+    fn = ((t != p) & (t == 1)).sum(axis)
+    fp = ((t != p) & (t == 0)).sum(axis)
+    tn = ((t == p) & (t == 0)).sum(axis)
+    return tp, fp, tn, fn
+
+
+def confmat_from_counts(tp, fp, tn, fn) -> np.ndarray:
+    """[[tn, fp], [fn, tp]] — what bincount(2*target + preds, 4).reshape(2, 2) yields (confusion_matrix.py:148-152, 511-516)."""
+    return np.stack([np.stack([tn, fp], -1), np.stack([fn, tp], -1)], -2).astype(np.int64)

@@ -187,6 +187,52 @@ def classification_golden() -> dict:
             for s in ("tp", "fp", "tn", "fn"):
                 out[f"stats/C{C}/{avg}/class_state_{s}"] = getattr(mm, s).numpy()
             out[f"stats/C{C}/{avg}/class_f1"] = f1.compute().numpy()
+    # ---- F. binary / multilabel stat scores, confusion matrices, accuracy, f1 -------------------------------------------
+    from torchmetrics.functional.classification import (
+        binary_accuracy,
+        binary_confusion_matrix,
+        binary_f1_score,
+        binary_stat_scores,
+        multilabel_accuracy,
+        multilabel_confusion_matrix,
+        multilabel_f1_score,
+        multilabel_stat_scores,
+    )
+
+    g = torch.Generator().manual_seed(17)
+    bp = {"probs": torch.rand(64, 7, generator=g), "logits": torch.randn(64, 7, generator=g) * 2,
+          "labels": torch.randint(0, 2, (64, 7), generator=g)}
+    bt = torch.randint(0, 2, (64, 7), generator=g)
+    bt_ign = bt.clone()
+    bt_ign[::5] = -1
+    out["bin2/target"], out["bin2/target_ign"] = bt.numpy(), bt_ign.numpy()
+    for kind, p in bp.items():
+        out[f"bin2/{kind}/preds"] = p.numpy()
+        for ign, t in ((None, bt), (-1, bt_ign)):
+            for mda in ("global", "samplewise"):
+                tag = f"bin2/{kind}/ign{'none' if ign is None else ign}/{mda}"
+                out[f"{tag}/stat_scores"] = binary_stat_scores(p, t, multidim_average=mda, ignore_index=ign).numpy()
+                out[f"{tag}/accuracy"] = binary_accuracy(p, t, multidim_average=mda, ignore_index=ign).numpy()
+                out[f"{tag}/f1"] = binary_f1_score(p, t, multidim_average=mda, ignore_index=ign).numpy()
+            out[f"bin2/{kind}/ign{'none' if ign is None else ign}/confmat"] = binary_confusion_matrix(p, t, ignore_index=ign).numpy()
+    out["bin2/probs/thr0.3/stat_scores"] = binary_stat_scores(bp["probs"], bt, threshold=0.3).numpy()
+    L = 6
+    mp = {"probs": torch.rand(40, L, 5, generator=g), "logits": torch.randn(40, L, 5, generator=g) * 2,
+          "labels": torch.randint(0, 2, (40, L, 5), generator=g)}
+    mt = torch.randint(0, 2, (40, L, 5), generator=g)
+    mt_ign = mt.clone()
+    mt_ign[::3] = -1
+    out["ml/target"], out["ml/target_ign"] = mt.numpy(), mt_ign.numpy()
+    for kind, p in mp.items():
+        out[f"ml/{kind}/preds"] = p.numpy()
+        for ign, t in ((None, mt), (-1, mt_ign)):
+            for mda in ("global", "samplewise"):
+                for avg in ("micro", "macro", "weighted", "none"):
+                    tag = f"ml/{kind}/ign{'none' if ign is None else ign}/{mda}/{avg}"
+                    out[f"{tag}/stat_scores"] = multilabel_stat_scores(p, t, L, average=avg, multidim_average=mda, ignore_index=ign).numpy()
+                    out[f"{tag}/accuracy"] = multilabel_accuracy(p, t, L, average=avg, multidim_average=mda, ignore_index=ign).numpy()
+                    out[f"{tag}/f1"] = multilabel_f1_score(p, t, L, average=avg, multidim_average=mda, ignore_index=ign).numpy()
+            out[f"ml/{kind}/ign{'none' if ign is None else ign}/confmat"] = multilabel_confusion_matrix(p, t, L, ignore_index=ign).numpy()
     out["meta/torchmetrics_version"] = np.array(torchmetrics.__version__)
     out["meta/torch_version"] = np.array(torch.__version__)
     return out
