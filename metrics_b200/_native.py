@@ -353,3 +353,35 @@ def binary_stat_counts(
         )
     check(rc, "binary_stat_counts")
     return counts
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K9 wrapper (regression running sums)
+# ----------------------------------------------------------------------------------------------------------
+REG_MSE, REG_MAE, REG_MAPE, REG_SMAPE, REG_WMAPE, REG_MSLE, REG_LOGCOSH, REG_MINKOWSKI, REG_R2, REG_EXPVAR = range(10)
+_REG_NUM_SUMS = {REG_WMAPE: 2, REG_R2: 3, REG_EXPVAR: 4}
+
+
+def regression_sums(preds: Tensor, target: Tensor, op: int, num_outputs: int = 1, param: float = 0.0, eps: float = 0.0) -> Tensor:
+    """``float64 [num_sums, num_outputs]`` sums of the per-element terms of regression op ``op`` (``mb200_regression_sums``)."""
+    dev = require_cuda(preds, target)
+    if not preds.is_floating_point():
+        preds = preds.float()
+    if target.dtype != preds.dtype:
+        target = target.to(preds.dtype)
+    preds = preds.contiguous()
+    target = target.contiguous()
+    d = int(num_outputs)
+    n = preds.numel() // d if d else 0
+    k = _REG_NUM_SUMS.get(op, 1)
+    out = torch.empty((k, d), dtype=torch.float64, device=dev)
+    lib_ = lib()
+    lib_.mb200_regression_scratch_doubles.restype = ctypes.c_int64
+    scratch = torch.empty(int(lib_.mb200_regression_scratch_doubles(i64(n), i64(d), int(op))), dtype=torch.float64, device=dev)
+    with on_device(dev):
+        rc = lib_.mb200_regression_sums(
+            ptr(preds), ptr(target), tag(preds), i64(n), i64(d), int(op), ctypes.c_double(float(param)),
+            ctypes.c_double(float(eps)), ptr(out), ptr(scratch), stream_handle(dev),
+        )
+    check(rc, "regression_sums")
+    return out

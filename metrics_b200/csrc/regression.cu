@@ -1,0 +1,163 @@
+// K9 — regression running sums: one fused map-reduce pass producing every sum a metric's `update` needs.
+//
+// Reference op chains replaced (src/torchmetrics/functional/regression/): mse.py:22-40, mae.py:22-42, mape.py:22-45,
+// symmetric_mape.py:22-46, wmape.py:22-38, log_mse.py:22-34, log_cosh.py:32-52, minkowski.py:21-38, r2.py:22-45 (also
+// used by rse.py), explained_variance.py:25-40 — each 2-5 elementwise + reduction launches per call.
+// Per-element terms are evaluated in fp32 with the reference's operation order (fp64 for fp64 inputs); the sums are
+// accumulated in fp64 with a fixed reduction order (per-thread strided rows -> fixed shared-memory tree -> ordered sum of
+// the per-CTA partials), so results are bitwise reproducible and at least as accurate as the reference's fp32 `torch.sum`.
+#include "common.cuh"
+
+namespace mb200 {
+
+extern void count_launch();
+
+enum RegOp { REG_MSE = 0, REG_MAE, REG_MAPE, REG_SMAPE, REG_WMAPE, REG_MSLE, REG_LOGCOSH, REG_MINKOWSKI, REG_R2, REG_EXPVAR };
+constexpr int kRegMaxK = 4;
+
+__host__ __device__ inline int reg_num_sums(int op) {
+    switch (op) {
+        case REG_WMAPE: return 2;
+        case REG_R2: return 3;
+        case REG_EXPVAR: return 4;
+        default: return 1;
+    }
+}
+
+template <typename F>
+__device__ __forceinline__ void reg_terms(int op, F p, F t, F param, F eps, F (&out)[kRegMaxK]) {
+    const F d = p - t;
+    switch (op) {
+        case REG_MSE: out[0] = d * d; break;
+        case REG_MAE: out[0] = fabs(d); break;
+        case REG_MAPE: out[0] = fabs(d) / fmax(fabs(t), eps); break;
+        case REG_SMAPE: out[0] = fabs(d) / fmax(fabs(t) + fabs(p), eps); break;  // the factor 2 is applied to the sum
+        case REG_WMAPE: out[0] = fabs(d), out[1] = fabs(t); break;
+        case REG_MSLE: {
+            const F l = log1p(p) - log1p(t);
+            out[0] = l * l;
+            break;
+        }
+        case REG_LOGCOSH: out[0] = log((exp(d) + exp(-d)) / (F)2); break;
+        case REG_MINKOWSKI: out[0] = pow(fabs(d), param); break;
+        case REG_R2: {
+            const F r = t - p;
+            out[0] = t * t, out[1] = t, out[2] = r * r;
+            break;
+        }
+        case REG_EXPVAR: {
+            const F r = t - p;
+            out[0] = r, out[1] = r * r, out[2] = t, out[3] = t * t;
+            break;
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ double load_as_double(const T* p, long long i);
+template <>
+__device__ __forceinline__ double load_as_double<float>(const float* p, long long i) { return p[i]; }
+template <>
+__device__ __forceinline__ double load_as_double<double>(const double* p, long long i) { return p[i]; }
+template <>
+__device__ __forceinline__ double load_as_double<__half>(const __half* p, long long i) { return __half2float(p[i]); }
+template <>
+__device__ __forceinline__ double load_as_double<__nv_bfloat16>(const __nv_bfloat16* p, long long i) { return __bfloat162float(p[i]); }
+
+// grid.x CTAs of 256 threads laid out as rows x cols_per_block; grid.y tiles the columns.
+template <typename T, bool kDouble>
+__global__ void __launch_bounds__(256) reg_partial_kernel(const T* __restrict__ preds, const T* __restrict__ target,
+                                                          long long n, int d, int op, double param, double eps,
+                                                          int cols_per_block, double* __restrict__ partial) {
+    __shared__ double sm[256];
+    const int K = reg_num_sums(op);
+    const int rows_per_block = 256 / cols_per_block;
+    const int c_local = threadIdx.x % cols_per_block;
+    const int r_local = threadIdx.x / cols_per_block;
+    const int c = blockIdx.y * cols_per_block + c_local;
+    double acc[kRegMaxK] = {0.0, 0.0, 0.0, 0.0};
+    if (r_local < rows_per_block && c < d) {
+        for (long long r = (long long)blockIdx.x * rows_per_block + r_local; r < n; r += (long long)gridDim.x * rows_per_block) {
+            const long long i = r * d + c;
+            if (kDouble) {
+                double out[kRegMaxK];
+                reg_terms<double>(op, load_as_double<T>(preds, i), load_as_double<T>(target, i), param, eps, out);
+                for (int k = 0; k < K; ++k) acc[k] += out[k];
+            } else {
+                float out[kRegMaxK];
+                reg_terms<float>(op, (float)load_as_double<T>(preds, i), (float)load_as_double<T>(target, i), (float)param,
+                                 (float)eps, out);
+                for (int k = 0; k < K; ++k) acc[k] += (double)out[k];
+            }
+        }
+    }
+    // fixed-order reduction over the rows of the CTA, one sum at a time
+    for (int k = 0; k < K; ++k) {
+        __syncthreads();
+        sm[threadIdx.x] = acc[k];
+        __syncthreads();
+        if (r_local == 0 && c < d) {
+            double s = 0.0;
+            for (int r = 0; r < rows_per_block; ++r) s += sm[r * cols_per_block + c_local];
+            partial[((size_t)blockIdx.x * K + k) * d + c] = s;
+        }
+    }
+}
+
+// out[k][c] = sum over CTAs (in order) of partial[cta][k][c]
+__global__ void reg_final_kernel(const double* __restrict__ partial, int n_cta, int K, int d, double* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K * d) return;
+    double s = 0.0;
+    for (int b = 0; b < n_cta; ++b) s += partial[(size_t)b * K * d + idx];
+    out[idx] = s;
+}
+
+}  // namespace mb200
+
+using namespace mb200;
+
+extern "C" int mb200_regression_num_sums(int op) { return (op >= 0 && op <= REG_EXPVAR) ? reg_num_sums(op) : -1; }
+
+extern "C" int64_t mb200_regression_scratch_doubles(int64_t n, int64_t d, int op) {
+    if (n < 0 || d < 1 || op < 0 || op > REG_EXPVAR) return -1;
+    return (int64_t)296 * reg_num_sums(op) * d + 8;
+}
+
+extern "C" int mb200_regression_sums(const void* preds, const void* target, int dtype, int64_t n, int64_t d, int op,
+                                     double param, double epsilon, double* out_sums, double* scratch, void* stream) {
+    MB200_REQUIRE(n >= 0 && d >= 1 && d < (1 << 30), "bad sizes");
+    MB200_REQUIRE(op >= 0 && op <= REG_EXPVAR, "unknown regression op %d", op);
+    MB200_REQUIRE(out_sums && scratch, "NULL pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int K = reg_num_sums(op);
+    const int cols_per_block = d >= 256 ? 256 : (int)d;
+    const int rows_per_block = 256 / cols_per_block;
+    long long want = (n + (long long)rows_per_block * 8 - 1) / ((long long)rows_per_block * 8);
+    const int col_tiles = (int)((d + cols_per_block - 1) / cols_per_block);
+    long long cap = 296 / col_tiles;
+    if (cap < 1) cap = 1;
+    int gx = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    if ((int64_t)gx * K * d + 8 > mb200_regression_scratch_doubles(n, d, op)) gx = 1;
+    if (n > 0) MB200_REQUIRE(preds && target, "NULL pointer");
+    const dim3 grid((unsigned)gx, (unsigned)col_tiles);
+    switch (dtype) {
+        case MB200_F32:
+            reg_partial_kernel<float, false><<<grid, 256, 0, st>>>((const float*)preds, (const float*)target, n, (int)d, op, param, epsilon, cols_per_block, scratch);
+            break;
+        case MB200_F64:
+            reg_partial_kernel<double, true><<<grid, 256, 0, st>>>((const double*)preds, (const double*)target, n, (int)d, op, param, epsilon, cols_per_block, scratch);
+            break;
+        case MB200_F16:
+            reg_partial_kernel<__half, false><<<grid, 256, 0, st>>>((const __half*)preds, (const __half*)target, n, (int)d, op, param, epsilon, cols_per_block, scratch);
+            break;
+        case MB200_BF16:
+            reg_partial_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)preds, (const __nv_bfloat16*)target, n, (int)d, op, param, epsilon, cols_per_block, scratch);
+            break;
+        default: set_error("regression inputs must be floating point (dtype tag %d)", dtype); return MB200_ERR_INVALID;
+    }
+    reg_final_kernel<<<(int)((K * d + 255) / 256), 256, 0, st>>>(scratch, gx, K, (int)d, out_sums);
+    count_launch();
+    count_launch();
+    return check_cuda(cudaGetLastError(), "regression sums launch");
+}

@@ -1,0 +1,14 @@
+"""Modular regression metrics (reference: src/torchmetrics/regression/)."""
+from metrics_b200.regression.metrics import (  # noqa: F401
+    ExplainedVariance,
+    LogCoshError,
+    MeanAbsoluteError,
+    MeanAbsolutePercentageError,
+    MeanSquaredError,
+    MeanSquaredLogError,
+    MinkowskiDistance,
+    R2Score,
+    RelativeSquaredError,
+    SymmetricMeanAbsolutePercentageError,
+    WeightedMeanAbsolutePercentageError,
+)

@@ -44,3 +44,10 @@ def golden_det():
     import numpy as np
 
     return np.load(os.path.join(GOLDEN_DIR, "detection.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_reg():
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN_DIR, "regression.npz"), allow_pickle=False)

@@ -418,11 +418,60 @@ def map_golden() -> dict:
     return out
 
 
+def regression_golden() -> dict:
+    import torchmetrics.functional as TF
+    import torchmetrics.regression as TR
+
+    out: dict = {}
+    g = torch.Generator().manual_seed(41)
+    p1 = torch.rand(1000, generator=g) * 4 + 0.1
+    t1 = torch.rand(1000, generator=g) * 4 + 0.1
+    p2 = torch.randn(600, 5, generator=g) * 2 + 1
+    t2 = torch.randn(600, 5, generator=g) * 2 + 1
+    for k, v in (("p1", p1), ("t1", t1), ("p2", p2), ("t2", t2)):
+        out[f"reg/{k}"] = v.numpy()
+    out["reg/mse"] = TF.mean_squared_error(p1, t1).numpy()
+    out["reg/rmse"] = TF.mean_squared_error(p1, t1, squared=False).numpy()
+    out["reg/mse_multi"] = TF.mean_squared_error(p2, t2, num_outputs=5).numpy()
+    out["reg/mae"] = TF.mean_absolute_error(p1, t1).numpy()
+    out["reg/mape"] = TF.mean_absolute_percentage_error(p1, t1).numpy()
+    out["reg/smape"] = TF.symmetric_mean_absolute_percentage_error(p1, t1).numpy()
+    out["reg/wmape"] = TF.weighted_mean_absolute_percentage_error(p1, t1).numpy()
+    out["reg/msle"] = TF.mean_squared_log_error(p1, t1).numpy()
+    out["reg/logcosh"] = TF.log_cosh_error(p1, t1).numpy()
+    out["reg/logcosh_multi"] = TF.log_cosh_error(p2, t2).numpy()
+    out["reg/minkowski3"] = TF.minkowski_distance(p1, t1, 3).numpy()
+    out["reg/minkowski1.5"] = TF.minkowski_distance(p2, t2, 1.5).numpy()
+    for mo in ("raw_values", "uniform_average", "variance_weighted"):
+        out[f"reg/r2_{mo}"] = TF.r2_score(p2, t2, multioutput=mo).numpy()
+        out[f"reg/ev_{mo}"] = TF.explained_variance(p2, t2, multioutput=mo).numpy()
+    out["reg/r2_1d"] = TF.r2_score(p1, t1).numpy()
+    out["reg/r2_adj"] = TF.r2_score(p2, t2, adjusted=3).numpy()
+    out["reg/rse"] = TF.relative_squared_error(p2, t2).numpy()
+    out["reg/rrse"] = TF.relative_squared_error(p2, t2, squared=False).numpy()
+    out["reg/ev_1d"] = TF.explained_variance(p1, t1).numpy()
+    # modular, 4 updates
+    for name, m, (pp, tt) in (("MeanSquaredError", TR.MeanSquaredError(), (p1, t1)),
+                              ("MeanAbsoluteError", TR.MeanAbsoluteError(), (p1, t1)),
+                              ("R2Score", TR.R2Score(), (p1, t1)),
+                              ("ExplainedVariance", TR.ExplainedVariance(multioutput="raw_values"), (p2, t2)),
+                              ("MeanSquaredErrorMulti", TR.MeanSquaredError(num_outputs=5), (p2, t2))):
+        for a, b in zip(pp.chunk(4), tt.chunk(4)):
+            m.update(a, b)
+        out[f"reg/class/{name}"] = m.compute().numpy()
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["classification"]
     if "classification" in which:
         data = classification_golden()
         path = os.path.join(HERE, "classification.npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
+    if "regression" in which:
+        data = regression_golden()
+        path = os.path.join(HERE, "regression.npz")
         np.savez_compressed(path, **data)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
     if "map" in which:
