@@ -30,3 +30,33 @@ def multiclass_confmat_update_cpu(confmat: Tensor, preds: Tensor, target: Tensor
     unique_mapping = target.to(torch.long) * num_classes + preds.to(torch.long)  # :326
     bins = torch.bincount(unique_mapping, minlength=num_classes**2)  # utilities/data.py:206
     confmat += bins.reshape(num_classes, num_classes)  # :328 and classification/confusion_matrix.py:286
+
+
+def binary_auroc_ap_compute_cpu(preds: Tensor, target: Tensor):
+    """BinaryAUROC.compute + BinaryAveragePrecision.compute on CPU tensors, op for op: each metric runs its own
+    `_binary_clf_curve` (functional/classification/precision_recall_curve.py:30-82) — two full sorts per collection
+    compute (roc.py:53 and precision_recall_curve.py:275)."""
+    import torch.nn.functional as F
+
+    def clf_curve(p: Tensor, t: Tensor):
+        idx = torch.argsort(p, descending=True)  # :60
+        p, t = p[idx], t[idx]  # :62-63
+        distinct = torch.where(p[1:] - p[:-1])[0]  # :70
+        thr_idx = F.pad(distinct, [0, 1], value=t.size(0) - 1)  # :71
+        t = (t == 1).to(torch.long)  # :72
+        tps = torch.cumsum(t * 1.0, dim=0)[thr_idx]  # :73
+        fps = 1 + thr_idx - tps  # :80
+        return fps, tps, p[thr_idx]
+
+    fps, tps, _ = clf_curve(preds, target)  # roc.py:53-78
+    tps = torch.cat([torch.zeros(1, dtype=tps.dtype), tps])
+    fps = torch.cat([torch.zeros(1, dtype=fps.dtype), fps])
+    fpr, tpr = fps / fps[-1], tps / tps[-1]
+    auroc = torch.trapz(tpr, fpr)  # utilities/compute.py:101-109
+    fps, tps, _ = clf_curve(preds, target)  # precision_recall_curve.py:275-290
+    precision = tps / (tps + fps)
+    recall = tps / tps[-1]
+    precision = torch.cat([precision.flip(0), torch.ones(1)])
+    recall = torch.cat([recall.flip(0), torch.zeros(1)])
+    ap = -torch.sum((recall[1:] - recall[:-1]) * precision[:-1])  # average_precision.py:74-75
+    return auroc, ap
