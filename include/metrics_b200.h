@@ -106,6 +106,24 @@ MB200_API int mb200_multiclass_stat_scores_update(const void* preds, int preds_d
                                         int64_t* tn, int64_t* fn, int64_t* workspace,
                                         uint32_t* err_flag, void* stream);
 
+/* K1b variants.
+ * top-k (functional/classification/stat_scores.py:347-368, 390-423 with top_k > 1): the effective prediction of a row is
+ * its target when the target is among the k best scores, else the argmax; per-class tp/fp/tn/fn as above (micro == 0
+ * layout, workspace contract identical).  preds: [n, num_classes] floating scores.
+ * samplewise (multidim_average="samplewise", :390-423): per (sample, class) counts over the trailing dims;
+ * counts: int64 [3][n_outer][num_classes] = tp | fp | fn planes, n_valid: int64 [n_outer]; both zero on entry;
+ * tn = n_valid - tp - fp - fn is left to the caller. */
+MB200_API int mb200_multiclass_stat_scores_topk_update(const void* preds, int preds_dtype, const void* target,
+                                                       int target_dtype, int64_t n, int64_t num_classes, int64_t top_k,
+                                                       int has_ignore_index, int64_t ignore_index, int64_t* tp,
+                                                       int64_t* fp, int64_t* tn, int64_t* fn, int64_t* workspace,
+                                                       uint32_t* err_flag, void* stream);
+MB200_API int mb200_multiclass_stat_scores_samplewise(const void* preds, int preds_dtype, int preds_has_class_dim,
+                                                      const void* target, int target_dtype, int64_t n_outer,
+                                                      int64_t num_classes, int64_t inner, int has_ignore_index,
+                                                      int64_t ignore_index, int64_t* counts, int64_t* n_valid,
+                                                      uint32_t* err_flag, void* stream);
+
 /* Row argmax only (the `preds.argmax(dim=1)` of the format step) — used by the samplewise / top-k host
  * paths and by tests to pin tie/NaN semantics.  out: int64 [n_outer * inner]. */
 MB200_API int mb200_argmax_rows(const void* preds, int preds_dtype, int64_t n_outer, int64_t num_classes,
@@ -139,14 +157,15 @@ MB200_API int mb200_curve_softmax_if_logits(const void* preds, int dtype, int64_
  *  out_counts : int64 [num_classes][3]  {#positives, #negatives, #distinct thresholds U}
  *  fps_out, tps_out, thr_out : optional (all or none) float32 [num_classes][n]; for curve c the first U entries
  *               are the reference's `fps, tps, thresholds` (descending thresholds), the rest is untouched.
- * TP/FP are counted in integers (exact for n < 2^31); AUROC = exact integer sum / (2 P N) evaluated in fp64;
+ *  err_flag   : optional device word; MB200_FLAG_SPIN_TIMEOUT is raised if the sort's bounded look-back wait expires
+ * TP/FP are counted in integers (n < 2^30 samples per curve); AUROC = exact integer sum / (2 P N) evaluated in fp64;
  * AP accumulated in fp64 in a fixed order (bitwise reproducible run to run).
  * ------------------------------------------------------------------------------------------------ */
 MB200_API int64_t mb200_curve_workspace_bytes(int64_t num_classes, int64_t n);
 MB200_API int mb200_curve_evaluate(const void* preds, int preds_dtype, const void* target, int target_dtype,
                                    int64_t n, int64_t num_classes, int64_t pos_label, void* workspace,
                                    int64_t workspace_bytes, float* out_auroc, float* out_ap, int64_t* out_counts,
-                                   float* fps_out, float* tps_out, float* thr_out, void* stream);
+                                   float* fps_out, float* tps_out, float* thr_out, uint32_t* err_flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K8 — COCO-style bounding-box mAP / mAR evaluation on the device.
@@ -210,6 +229,21 @@ MB200_API int mb200_regression_num_sums(int op);
 MB200_API int64_t mb200_regression_scratch_doubles(int64_t n, int64_t d, int op);
 MB200_API int mb200_regression_sums(const void* preds, const void* target, int dtype, int64_t n, int64_t d, int op,
                                     double param, double epsilon, double* out_sums, double* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4 — binned (fixed-threshold) curve state update.
+ * Replaces functional/classification/precision_recall_curve.py:191-251 (binary) and :464-533 (multiclass):
+ * the multi-threshold confusion matrix confmat[i, (c,) target, score >= thr[i]].
+ *  preds      : [n] (num_classes == 1) or [n, num_classes] row-major scores, already sigmoid/softmax-normalised
+ *  target     : [n] integer labels; binary: 1 = positive, 0 = negative, anything else skipped
+ *  thresholds_sorted : float32 [num_thresholds], ASCENDING (device)
+ *  confmat    : int64 [num_thresholds, num_classes, 2, 2] (binary callers view it as [T, 2, 2]), updated in place
+ *  scratch    : uint64 [mb200_binned_curve_scratch_words(...)], zero on entry, left zeroed (self-cleaning)
+ * ------------------------------------------------------------------------------------------------ */
+MB200_API int64_t mb200_binned_curve_scratch_words(int64_t num_classes, int64_t num_thresholds);
+MB200_API int mb200_binned_curve_update(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                        int64_t n, int64_t num_classes, const float* thresholds_sorted,
+                                        int64_t num_thresholds, int64_t* confmat, uint64_t* scratch, void* stream);
 
 #ifdef __cplusplus
 }

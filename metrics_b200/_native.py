@@ -269,7 +269,7 @@ def curve_evaluate(preds: Tensor, target: Tensor, num_classes: int = 1, pos_labe
         rc = lib_.mb200_curve_evaluate(
             ptr(preds), tag(preds), ptr(target), tag(target), i64(n), i64(num_classes), i64(pos_label), ptr(ws),
             i64(nbytes), ptr(auroc), ptr(ap), ptr(counts), ptr(curve[0] if curve else None),
-            ptr(curve[1] if curve else None), ptr(curve[2] if curve else None), stream_handle(dev),
+            ptr(curve[1] if curve else None), ptr(curve[2] if curve else None), ptr(None), stream_handle(dev),
         )
     check(rc, "curve_evaluate")
     return auroc, ap, counts, curve
@@ -385,3 +385,79 @@ def regression_sums(preds: Tensor, target: Tensor, op: int, num_outputs: int = 1
         )
     check(rc, "regression_sums")
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K4 wrapper (binned curve update)
+# ----------------------------------------------------------------------------------------------------------
+def binned_curve_update(preds: Tensor, target: Tensor, thresholds: Tensor, num_classes: int = 1) -> Tensor:
+    """Multi-threshold confusion matrix of one batch: int64 ``[T, 2, 2]`` (``num_classes == 1``) or ``[T, C, 2, 2]``.
+    ``thresholds`` may be in any order (rows of the result follow it); the kernel works on a sorted copy."""
+    dev = require_cuda(preds, target, thresholds)
+    preds = preds.contiguous()
+    target = target.contiguous()
+    thr = thresholds.to(torch.float32)
+    order = None
+    if thr.numel() > 1 and not bool((thr[1:] >= thr[:-1]).all()):
+        thr, order = torch.sort(thr)
+    thr = thr.contiguous()
+    n = target.numel()
+    t_count = thr.numel()
+    confmat = torch.zeros((t_count, num_classes, 2, 2), dtype=torch.int64, device=dev)
+    lib_ = lib()
+    lib_.mb200_binned_curve_scratch_words.restype = ctypes.c_int64
+    scratch = torch.zeros(int(lib_.mb200_binned_curve_scratch_words(i64(num_classes), i64(t_count))), dtype=torch.int64, device=dev)
+    with on_device(dev):
+        rc = lib_.mb200_binned_curve_update(
+            ptr(preds), tag(preds), ptr(target), tag(target), i64(n), i64(num_classes), ptr(thr), i64(t_count),
+            ptr(confmat), ptr(scratch), stream_handle(dev),
+        )
+    check(rc, "binned_curve_update")
+    if order is not None:
+        inv = torch.empty_like(order)
+        inv[order] = torch.arange(t_count, device=dev)
+        confmat = confmat[inv]
+    return confmat[:, 0] if num_classes == 1 else confmat
+
+
+def multiclass_stat_scores_topk_update_(
+    tp: Tensor, fp: Tensor, tn: Tensor, fn: Tensor, workspace: Tensor, preds: Tensor, target: Tensor, num_classes: int,
+    top_k: int, ignore_index: Optional[int], err_flag: Optional[Tensor] = None,
+) -> None:
+    """In-place per-class tp/fp/tn/fn with the top-k refined prediction (``mb200_multiclass_stat_scores_topk_update``)."""
+    dev = require_cuda(tp, fp, tn, fn, workspace, preds, target)
+    if preds.ndim != 2 or target.ndim != 1:
+        raise NotImplementedError("metrics_b200: top_k > 1 supports `preds` of shape (N, C) with `target` of shape (N,)")
+    preds = preds.contiguous()
+    target = target.contiguous()
+    with on_device(dev):
+        rc = lib().mb200_multiclass_stat_scores_topk_update(
+            ptr(preds), tag(preds), ptr(target), tag(target), i64(preds.shape[0]), i64(num_classes), i64(top_k),
+            int(ignore_index is not None), i64(ignore_index or 0), ptr(tp), ptr(fp), ptr(tn), ptr(fn), ptr(workspace),
+            ptr(err_flag), stream_handle(dev),
+        )
+    check(rc, "multiclass_stat_scores_topk_update")
+
+
+def multiclass_stat_scores_samplewise(
+    preds: Tensor, target: Tensor, num_classes: int, ignore_index: Optional[int], err_flag: Optional[Tensor] = None
+):
+    """Per-sample ``tp, fp, tn, fn`` of shape ``[N, C]`` over the trailing dims (``mb200_multiclass_stat_scores_samplewise``)."""
+    dev = require_cuda(preds, target)
+    has_class_dim = preds.ndim == target.ndim + 1
+    preds = preds.contiguous()
+    target = target.contiguous()
+    n_outer = target.shape[0]
+    inner = target.numel() // max(1, n_outer)
+    counts = torch.zeros((3, n_outer, num_classes), dtype=torch.int64, device=dev)
+    n_valid = torch.zeros(n_outer, dtype=torch.int64, device=dev)
+    with on_device(dev):
+        rc = lib().mb200_multiclass_stat_scores_samplewise(
+            ptr(preds), tag(preds), int(has_class_dim), ptr(target), tag(target), i64(n_outer), i64(num_classes),
+            i64(max(1, inner)), int(ignore_index is not None), i64(ignore_index or 0), ptr(counts), ptr(n_valid),
+            ptr(err_flag), stream_handle(dev),
+        )
+    check(rc, "multiclass_stat_scores_samplewise")
+    tp, fp, fn = counts[0], counts[1], counts[2]
+    tn = n_valid[:, None] - tp - fp - fn
+    return tp, fp, tn, fn

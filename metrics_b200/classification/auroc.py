@@ -39,6 +39,8 @@ class BinaryAUROC(BinaryPrecisionRecallCurve):
         self.max_fpr = max_fpr
 
     def compute(self) -> Tensor:
+        if self.thresholds is None and (self.max_fpr is None or self.max_fpr == 1):
+            return _binary_auroc_compute(None, self.thresholds, self.max_fpr, scalars=self._curve_scalars())
         return _binary_auroc_compute(self._state(), self.thresholds, self.max_fpr)
 
 
@@ -70,7 +72,10 @@ class MulticlassAUROC(MulticlassPrecisionRecallCurve):
         self.validate_args = validate_args
 
     def compute(self) -> Tensor:
-        return _multiclass_auroc_compute(self._state(), self.num_classes, self.average, self.thresholds)
+        if self.thresholds is not None:
+            return _multiclass_auroc_compute(self._state(), self.num_classes, self.average, self.thresholds)
+        return _multiclass_auroc_compute(None, self.num_classes, self.average, self.thresholds,
+                                         scalars=self._curve_scalars(self.num_classes))
 
 
 from metrics_b200.classification.base import _ClassificationTaskWrapper  # noqa: E402

@@ -24,7 +24,7 @@ class BinaryAveragePrecision(BinaryPrecisionRecallCurve):
     plot_upper_bound: float = 1.0
 
     def compute(self) -> Tensor:
-        return _binary_average_precision_compute(self._state(), self.thresholds)
+        return _binary_average_precision_compute(self._state(), self.thresholds, scalars=self._curve_scalars())
 
 
 class MulticlassAveragePrecision(MulticlassPrecisionRecallCurve):
@@ -55,7 +55,8 @@ class MulticlassAveragePrecision(MulticlassPrecisionRecallCurve):
         self.validate_args = validate_args
 
     def compute(self) -> Tensor:
-        return _multiclass_average_precision_compute(self._state(), self.num_classes, self.average, self.thresholds)
+        return _multiclass_average_precision_compute(self._state(), self.num_classes, self.average, self.thresholds,
+                                                     scalars=self._curve_scalars(self.num_classes))
 
 
 from metrics_b200.classification.base import _ClassificationTaskWrapper  # noqa: E402

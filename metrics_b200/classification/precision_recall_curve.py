@@ -8,6 +8,7 @@ from __future__ import annotations
 
 from typing import Any, List, Optional, Union
 
+import torch
 from torch import Tensor
 from typing_extensions import Literal
 
@@ -23,7 +24,6 @@ from metrics_b200.functional.classification.precision_recall_curve import (
     _multiclass_precision_recall_curve_format,
     _multiclass_precision_recall_curve_tensor_validation,
     _multiclass_precision_recall_curve_update,
-    _no_binned,
 )
 from metrics_b200.metric import Metric
 from metrics_b200.utilities.data import dim_zero_cat
@@ -48,22 +48,57 @@ class BinaryPrecisionRecallCurve(Metric):
         super().__init__(**kwargs)
         if validate_args:
             _binary_precision_recall_curve_arg_validation(thresholds, ignore_index)
-        _no_binned(thresholds)
         self.ignore_index = ignore_index
         self.validate_args = validate_args
-        self.thresholds = _adjust_threshold_arg(thresholds)
-        self.add_state("preds", default=[], dist_reduce_fx="cat")
-        self.add_state("target", default=[], dist_reduce_fx="cat")
+        thresholds = _adjust_threshold_arg(thresholds)
+        if thresholds is None:
+            self.thresholds = thresholds
+            self.add_state("preds", default=[], dist_reduce_fx="cat")
+            self.add_state("target", default=[], dist_reduce_fx="cat")
+        else:  # binned mode: constant-size state (reference :156-160)
+            self.register_buffer("thresholds", thresholds, persistent=False)
+            self.add_state("confmat", default=torch.zeros(len(thresholds), 2, 2, dtype=torch.long), dist_reduce_fx="sum")
+        # One sort + scan yields AUROC *and* AP: members of a MetricCollection compute group share this dict by reference
+        # (collections.py links it like a state), so the second metric of the group reuses the first one's evaluation.
+        self._group_cache: dict = {}
+
+    def reset(self) -> None:
+        self._group_cache.clear()
+        Metric.reset(self)
+
+    def _curve_scalars(self, num_classes: int = 1, pos_label: int = 1):
+        """``(auroc, ap, counts)`` of the current state from ONE `mb200_curve_evaluate` call, memoised until the next
+        update / reset.  Keyed by the identity of the state object, so synced states never hit a local entry."""
+        from metrics_b200 import _native
+
+        if self.thresholds is not None:
+            return None  # binned mode: the compute functions work on the confmat state
+        key = (id(self.preds), id(self.target), num_classes, pos_label)
+        hit = self._group_cache.get(key)
+        if hit is None:
+            preds, target = self._state()
+            if preds.numel() == 0:
+                raise IndexError("metrics_b200: cannot evaluate a curve metric without samples")
+            auroc, ap, counts, _ = _native.curve_evaluate(preds, target, num_classes, pos_label, want_curve=False)
+            hit = (auroc, ap, counts)
+            self._group_cache[key] = hit
+        return hit
 
     def update(self, preds: Tensor, target: Tensor) -> None:
+        self._group_cache.clear()
         if self.validate_args:
             _binary_precision_recall_curve_tensor_validation(preds, target, self.ignore_index)
         preds, target, _ = _binary_precision_recall_curve_format(preds, target, self.thresholds, self.ignore_index)
         state = _binary_precision_recall_curve_update(preds, target, self.thresholds)
-        self.preds.append(state[0])
-        self.target.append(state[1])
+        if isinstance(state, Tensor):
+            self.confmat += state
+        else:
+            self.preds.append(state[0])
+            self.target.append(state[1])
 
-    def _state(self) -> tuple[Tensor, Tensor]:
+    def _state(self):
+        if self.thresholds is not None:
+            return self.confmat
         return dim_zero_cat(self.preds), dim_zero_cat(self.target)
 
     def compute(self) -> tuple[Tensor, Tensor, Tensor]:
@@ -91,27 +126,39 @@ class MulticlassPrecisionRecallCurve(Metric):
         super().__init__(**kwargs)
         if validate_args:
             _multiclass_precision_recall_curve_arg_validation(num_classes, thresholds, ignore_index, average)
-        _no_binned(thresholds)
         self.num_classes = num_classes
         self.average = average
         self.ignore_index = ignore_index
         self.validate_args = validate_args
-        self.thresholds = _adjust_threshold_arg(thresholds)
-        self.add_state("preds", default=[], dist_reduce_fx="cat")
-        self.add_state("target", default=[], dist_reduce_fx="cat")
+        thresholds = _adjust_threshold_arg(thresholds)
+        if thresholds is None:
+            self.thresholds = thresholds
+            self.add_state("preds", default=[], dist_reduce_fx="cat")
+            self.add_state("target", default=[], dist_reduce_fx="cat")
+        else:  # binned mode (reference :353-359); micro average keeps the binary [T, 2, 2] layout
+            self.register_buffer("thresholds", thresholds, persistent=False)
+            shape = (len(thresholds), 2, 2) if average == "micro" else (len(thresholds), num_classes, 2, 2)
+            self.add_state("confmat", default=torch.zeros(*shape, dtype=torch.long), dist_reduce_fx="sum")
+        self._group_cache: dict = {}  # see BinaryPrecisionRecallCurve
+
+    reset = BinaryPrecisionRecallCurve.reset
+    _curve_scalars = BinaryPrecisionRecallCurve._curve_scalars
 
     def update(self, preds: Tensor, target: Tensor) -> None:
+        self._group_cache.clear()
         if self.validate_args:
             _multiclass_precision_recall_curve_tensor_validation(preds, target, self.num_classes, self.ignore_index)
         preds, target, _ = _multiclass_precision_recall_curve_format(
             preds, target, self.num_classes, self.thresholds, self.ignore_index, self.average
         )
         state = _multiclass_precision_recall_curve_update(preds, target, self.num_classes, self.thresholds, self.average)
-        self.preds.append(state[0])
-        self.target.append(state[1])
+        if isinstance(state, Tensor):
+            self.confmat += state
+        else:
+            self.preds.append(state[0])
+            self.target.append(state[1])
 
-    def _state(self) -> tuple[Tensor, Tensor]:
-        return dim_zero_cat(self.preds), dim_zero_cat(self.target)
+    _state = BinaryPrecisionRecallCurve._state
 
     def compute(self):
         return _multiclass_precision_recall_curve_compute(self._state(), self.num_classes, self.thresholds, self.average)

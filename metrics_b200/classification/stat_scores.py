@@ -99,6 +99,12 @@ class MulticlassStatScores(_AbstractStatScores):
                 preds, target, self.num_classes, self.multidim_average, self.ignore_index
             )
         num_classes = self.num_classes if self.num_classes is not None else 1
+        if self.multidim_average == "samplewise":
+            from metrics_b200.functional.classification.stat_scores import _multiclass_stat_scores_states
+
+            self._update_state(*_multiclass_stat_scores_states(
+                preds, target, num_classes, self.top_k, self.average, "samplewise", self.ignore_index, self.validate_args))
+            return
         _multiclass_stat_scores_update_(
             self.tp, self.fp, self.tn, self.fn, self._workspace(num_classes, self.tp.device), preds, target,
             num_classes, self.top_k, self.average, self.multidim_average, self.ignore_index, self.validate_args,

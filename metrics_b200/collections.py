@@ -142,6 +142,8 @@ class MetricCollection(ModuleDict):
                         value = getattr(leader, state)
                         setattr(follower, state, deepcopy(value) if copy else value)
                     follower._update_count = leader._update_count
+                    if hasattr(leader, "_group_cache"):  # memoised evaluations shared by the group (curve metrics)
+                        follower._group_cache = {} if copy else leader._group_cache
         self._state_is_copy = copy
 
     def compute(self) -> Dict[str, Any]:

@@ -1,0 +1,143 @@
+// K4 — binned (fixed-threshold) curve state update: multi-threshold confusion matrix `[T, (C,) 2, 2]` in one pass.
+//
+// Reference op chains replaced (functional/classification/precision_recall_curve.py): binary :191-251
+// (`_binary_precision_recall_curve_update_vectorized` = N*T int64 temporaries + bincount, or `_loop` = T passes over
+// the data above 50 000 samples) and multiclass :464-533 (N*C*T temporaries, or T passes above 10^6 elements).
+// Here every score does ONE binary search over the (ascending) thresholds — k = #{thr <= score} — and bumps a
+// shared-memory counter (class, target == class, k); the suffix sums over k that turn bucket counts into
+// "predicted positive at threshold i" counts cost O(C * T) at the end of the kernel that finishes last.
+#include "common.cuh"
+
+namespace mb200 {
+
+extern void count_launch();
+
+template <typename T>
+__device__ __forceinline__ float binned_to_float(T x);
+template <>
+__device__ __forceinline__ float binned_to_float<float>(float x) { return x; }
+template <>
+__device__ __forceinline__ float binned_to_float<__half>(__half x) { return __half2float(x); }
+template <>
+__device__ __forceinline__ float binned_to_float<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <>
+__device__ __forceinline__ float binned_to_float<double>(double x) { return (float)x; }
+template <typename T>
+struct CmpType { using type = float; };
+template <>
+struct CmpType<double> { using type = double; };  // fp64 scores are compared against the fp32 thresholds in fp64
+template <typename T>
+__device__ __forceinline__ typename CmpType<T>::type binned_load(const T* p, long long i) { return binned_to_float<T>(p[i]); }
+template <>
+__device__ __forceinline__ double binned_load<double>(const double* p, long long i) { return p[i]; }
+
+// bucket counts: scratch[(c * 2 + y) * (T + 1) + k], zero on entry, self-cleaning (the folding CTA re-zeroes it)
+template <typename T>
+__global__ void __launch_bounds__(256) binned_bucket_kernel(const T* __restrict__ preds, const void* __restrict__ target,
+                                                            int tdtype, long long n, int C, const float* __restrict__ thr,
+                                                            int nthr, unsigned long long* __restrict__ scratch,
+                                                            long long* __restrict__ confmat, int use_smem) {
+    extern __shared__ unsigned sh_cnt[];  // C * 2 * (nthr + 1) when use_smem
+    const int stride = nthr + 1;
+    const int ncnt = C * 2 * stride;
+    if (use_smem) {
+        for (int i = threadIdx.x; i < ncnt; i += blockDim.x) sh_cnt[i] = 0;
+        __syncthreads();
+    }
+    const long long total = n * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i / C;
+        const int c = (int)(i - s * C);
+        const long long t = load_label(target, tdtype, s);
+        const int y = (C == 1) ? (t == 1) : (t == c);
+        if (C == 1 && (unsigned long long)t > 1ull) continue;  // binary: only {0,1} targets take part
+        const typename CmpType<T>::type p = binned_load<T>(preds, i);
+        // k = number of thresholds <= p  (p >= thr[j]  <=>  j < k);  NaN compares false everywhere -> k = 0
+        int lo = 0, hi = nthr;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((typename CmpType<T>::type)thr[mid] <= p) lo = mid + 1;
+            else hi = mid;
+        }
+        const int slot = (c * 2 + y) * stride + lo;
+        if (use_smem) atomicAdd(&sh_cnt[slot], 1u);
+        else atomicAdd(&scratch[slot], 1ull);
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < ncnt; i += blockDim.x) {
+            const unsigned v = sh_cnt[i];
+            if (v) atomicAdd(&scratch[i], (unsigned long long)v);
+        }
+    }
+    // ---- last CTA folds the bucket counts into the [T, C, 2, 2] state and cleans the scratch ----
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long ticket = atomicAdd(&scratch[ncnt], 1ull);
+        is_last = ticket == (unsigned long long)gridDim.x - 1ull;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // one thread per (class, y): serial suffix sum over k (T is small), confmat[i, c, y, pred] layout [T][C][2][2]
+    for (int cy = threadIdx.x; cy < C * 2; cy += blockDim.x) {
+        const int c = cy >> 1, y = cy & 1;
+        unsigned long long* row = scratch + (size_t)cy * stride;
+        unsigned long long tot = 0;
+        for (int k = 0; k <= nthr; ++k) tot += __ldcg(row + k);
+        unsigned long long ge = tot;  // samples with k > i, starting at i = -1
+        for (int i = 0; i < nthr; ++i) {
+            ge -= __ldcg(row + i);  // now: samples with k > i  <=>  score >= thr[i]
+            long long* cell = confmat + (((size_t)i * C + c) * 2 + y) * 2;
+            cell[1] += (long long)ge;
+            cell[0] += (long long)(tot - ge);
+        }
+        for (int k = 0; k <= nthr; ++k) row[k] = 0ull;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) scratch[ncnt] = 0ull;
+}
+
+}  // namespace mb200
+
+using namespace mb200;
+
+extern "C" int64_t mb200_binned_curve_scratch_words(int64_t num_classes, int64_t num_thresholds) {
+    if (num_classes < 1 || num_thresholds < 1) return -1;
+    return num_classes * 2 * (num_thresholds + 1) + 8;
+}
+
+extern "C" int mb200_binned_curve_update(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                         int64_t n, int64_t num_classes, const float* thresholds_sorted,
+                                         int64_t num_thresholds, int64_t* confmat, uint64_t* scratch, void* stream) {
+    MB200_REQUIRE(n >= 0 && num_classes >= 1 && num_thresholds >= 1, "bad sizes");
+    MB200_REQUIRE(num_thresholds < (1 << 24) && num_classes < (1 << 24), "sizes too large");
+    if (n == 0) return 0;
+    MB200_REQUIRE(preds && target && thresholds_sorted && confmat && scratch, "NULL pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long total = n * num_classes;
+    const size_t smem_need = (size_t)num_classes * 2 * (num_thresholds + 1) * sizeof(unsigned);
+    const int use_smem = smem_need <= 40 * 1024;
+    long long blocks = (total + 256 * 8 - 1) / (256 * 8);
+    const long long cap = (long long)sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    unsigned long long* sc = reinterpret_cast<unsigned long long*>(scratch);
+    long long* cm = reinterpret_cast<long long*>(confmat);
+#define MB200_BINNED(T)                                                                                              \
+    binned_bucket_kernel<T><<<(int)blocks, 256, use_smem ? smem_need : 0, st>>>(                                     \
+        reinterpret_cast<const T*>(preds), target, target_dtype, n, (int)num_classes, thresholds_sorted,            \
+        (int)num_thresholds, sc, cm, use_smem);
+    switch (preds_dtype) {
+        case MB200_F32: MB200_BINNED(float) break;
+        case MB200_F16: MB200_BINNED(__half) break;
+        case MB200_BF16: MB200_BINNED(__nv_bfloat16) break;
+        case MB200_F64: MB200_BINNED(double) break;
+        default: set_error("scores must be floating point (dtype tag %d)", preds_dtype); return MB200_ERR_INVALID;
+    }
+#undef MB200_BINNED
+    count_launch();
+    return check_cuda(cudaGetLastError(), "binned curve launch");
+}

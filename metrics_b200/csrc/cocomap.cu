@@ -442,7 +442,7 @@ namespace {
 struct MapWs {
     int *det_cat, *det_rank, *npig, *range_start;
     unsigned long long *det_match, *det_ignore, *keys_a, *keys_b;
-    unsigned *vals_a, *vals_b, *tile_hist, *digit_total, *tp_cum, *cidx;
+    unsigned *vals_a, *vals_b, *sort_scratch, *tp_cum, *cidx;
     double* prec;
 };
 inline unsigned char* bump(unsigned char*& p, int64_t bytes) {
@@ -469,8 +469,8 @@ MapWs carve(void* ws, int64_t nd, int64_t K, int64_t M, int64_t* total) {
     w.cidx = (unsigned*)bump(p, kMapAreas * M * n1 * 4);
     w.npig = (int*)bump(p, (K + 1) * kMapAreas * 4);
     w.range_start = (int*)bump(p, (K + 2) * 4);
-    w.tile_hist = (unsigned*)bump(p, 256 * (tiles + 1) * 4);
-    w.digit_total = (unsigned*)bump(p, 256 * 4);
+    w.sort_scratch = (unsigned*)bump(p, (int64_t)radix_sort_scratch_words(n1, 1, 8) * 4);
+    (void)tiles;
     if (total) *total = (int64_t)(p - p0) + 256;
     return w;
 }
@@ -564,8 +564,9 @@ extern "C" int mb200_coco_map_evaluate(
         int key_bytes = 4;  // score
         for (long long kk = K - 1; kk > 0; kk >>= 8) key_bytes++;
         const int where = radix_sort_passes<unsigned long long, unsigned>(w.keys_a, w.vals_a, w.keys_b, w.vals_b, nd,
-                                                                           1, key_bytes, w.tile_hist, w.digit_total,
-                                                                           st, &count_launch);
+                                                                           1, key_bytes, w.sort_scratch, err_flag, st,
+                                                                           &count_launch);
+        if (where < 0) return check_cuda(cudaGetLastError(), "radix sort");
         skeys = where ? w.keys_b : w.keys_a;
         sidx = where ? w.vals_b : w.vals_a;
     }

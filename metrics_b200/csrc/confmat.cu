@@ -223,6 +223,37 @@ __global__ void __launch_bounds__(kRowThreads) rows_scalar_kernel(RowArgs a, Sin
     sink.finish(loc);
 }
 
+// (2b) top-k "refined" prediction (functional/classification/stat_scores.py:347-368 `_refine_preds_oh`): the effective
+// label is the target when it is among the k best scores of the row, else the argmax.  Warp per row, scalar loads;
+// "among the k best" = fewer than k columns beat the target's score (greater key, or equal key and lower index —
+// the order a stable descending sort gives).
+template <typename T, typename Sink, bool kI64>
+__global__ void __launch_bounds__(kRowThreads) rows_topk_kernel(RowArgs a, Sink sink, int top_k) {
+    sink.block_init();
+    typename Sink::Local loc;
+    sink.init(loc);
+    const int lane = threadIdx.x & 31;
+    const long long wpb = blockDim.x >> 5;
+    const long long nwarps = (long long)gridDim.x * wpb;
+    const T* __restrict__ preds = reinterpret_cast<const T*>(a.preds);
+    for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < a.n_outer; r += nwarps) {
+        const long long t = fetch_label<kI64>(a, r);
+        if (!admit_label(a, t, lane == 0)) continue;
+        const T* __restrict__ row = preds + r * a.C;
+        const unsigned long long kt = order_key<T>(row[t]);
+        int beats = 0;
+        for (int c = lane; c < a.C; c += kWarp) {
+            const unsigned long long k = order_key<T>(row[c]);
+            beats += (k > kt) || (k == kt && c < (int)t);
+        }
+        beats = __reduce_add_sync(kFull, beats);
+        int p = (int)t;
+        if (beats >= top_k) p = warp_row_argmax_scalar<T>(row, a.C, lane);
+        if (lane == 0) sink.row(loc, r, t, p);
+    }
+    sink.finish(loc);
+}
+
 // (3) thread per (outer, inner) position, class dim strided by `inner` (also the tiny-C path with inner == 1)
 template <typename T, typename Sink, bool kI64>
 __global__ void __launch_bounds__(kRowThreads) rows_strided_kernel(RowArgs a, Sink sink) {
@@ -452,6 +483,56 @@ extern "C" int mb200_multiclass_stat_scores_update(const void* preds, int preds_
     StatsSink<false> s{(long long*)tp, (long long*)fp, (long long*)tn, (long long*)fn, (long long*)workspace,
                        (int)num_classes, micro};
     return dispatch_rows(preds_dtype, preds_has_class_dim, a, s, 0, st);
+}
+
+template <typename Sink, bool kI64>
+static int launch_topk_t(int preds_dtype, const RowArgs& a, Sink sink, size_t smem, int top_k, cudaStream_t st) {
+#define MB200_TOPK(T)                                                                                        \
+    {                                                                                                        \
+        auto kern = rows_topk_kernel<T, Sink, kI64>;                                                         \
+        const int grid = grid_for(a.n_outer, kRowThreads / 32, resident_blocks(kern, kRowThreads, smem));   \
+        kern<<<grid, kRowThreads, smem, st>>>(a, sink, top_k);                                               \
+    }
+    switch (preds_dtype) {
+        case MB200_BF16: MB200_TOPK(__nv_bfloat16) break;
+        case MB200_F16: MB200_TOPK(__half) break;
+        case MB200_F32: MB200_TOPK(float) break;
+        case MB200_F64: MB200_TOPK(double) break;
+        default: set_error("top-k needs floating scores (dtype tag %d)", preds_dtype); return MB200_ERR_INVALID;
+    }
+#undef MB200_TOPK
+    count_launch();
+    return check_cuda(cudaGetLastError(), "top-k kernel launch");
+}
+
+extern "C" int mb200_multiclass_stat_scores_topk_update(const void* preds, int preds_dtype, const void* target,
+                                                        int target_dtype, int64_t n, int64_t num_classes, int64_t top_k,
+                                                        int has_ignore_index, int64_t ignore_index, int64_t* tp,
+                                                        int64_t* fp, int64_t* tn, int64_t* fn, int64_t* workspace,
+                                                        uint32_t* err_flag, void* stream) {
+    if (int rc = validate_common(preds, target, target_dtype, n, num_classes, 1, true)) return rc;
+    MB200_REQUIRE(tp && fp && tn && fn && workspace, "state / workspace pointer is NULL");
+    MB200_REQUIRE(top_k >= 1 && top_k <= num_classes, "top_k must be in [1, num_classes]");
+    if (n == 0) return 0;
+    RowArgs a{preds, target, target_dtype, n, (int)num_classes, 1, has_ignore_index, ignore_index, err_flag};
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    StatsSink<false> s{(long long*)tp, (long long*)fp, (long long*)tn, (long long*)fn, (long long*)workspace,
+                       (int)num_classes, 0};
+    if (target_dtype == MB200_I64) return launch_topk_t<StatsSink<false>, true>(preds_dtype, a, s, 0, (int)top_k, st);
+    return launch_topk_t<StatsSink<false>, false>(preds_dtype, a, s, 0, (int)top_k, st);
+}
+
+extern "C" int mb200_multiclass_stat_scores_samplewise(const void* preds, int preds_dtype, int preds_has_class_dim,
+                                                       const void* target, int target_dtype, int64_t n_outer,
+                                                       int64_t num_classes, int64_t inner, int has_ignore_index,
+                                                       int64_t ignore_index, int64_t* counts, int64_t* n_valid,
+                                                       uint32_t* err_flag, void* stream) {
+    if (int rc = validate_common(preds, target, target_dtype, n_outer, num_classes, inner, true)) return rc;
+    MB200_REQUIRE(counts && n_valid, "NULL pointer");
+    if (n_outer * inner == 0) return 0;
+    RowArgs a{preds, target, target_dtype, n_outer, (int)num_classes, inner, has_ignore_index, ignore_index, err_flag};
+    SamplewiseSink s{(long long*)counts, (long long*)n_valid, n_outer, inner, (int)num_classes};
+    return dispatch_rows(preds_dtype, preds_has_class_dim, a, s, 0, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mb200_argmax_rows(const void* preds, int preds_dtype, int64_t n_outer, int64_t num_classes,

@@ -555,8 +555,8 @@ extern "C" int64_t mb200_curve_workspace_bytes(int64_t segments, int64_t n) {
     b += segments * n * 4;                          // keys pong
     b += segments * n * 1 + 16;                     // labels ping
     b += segments * n * 1 + 16;                     // labels pong
-    b += segments * 256 * (sort_tiles + 1) * 4;     // tile_hist
-    b += segments * 256 * 4;                        // digit_total
+    b += (int64_t)radix_sort_scratch_words(n, segments, 4) * 4 + 256;  // digit histograms, look-back status, tickets
+    (void)sort_tiles;
     b += segments * (scan_tiles + 1) * (int64_t)sizeof(TileInfo);
     b += segments * 2 * 4;                          // seg_totals
     b += segments * 8;                              // auroc_acc
@@ -568,7 +568,7 @@ namespace {
 struct CurveWs {
     unsigned *keys_a, *keys_b;
     unsigned char *lab_a, *lab_b;
-    unsigned *tile_hist, *digit_total, *seg_totals;
+    unsigned *sort_scratch, *seg_totals;
     TileInfo* info;
     unsigned long long* auroc_acc;
     double* ap_partial;
@@ -587,8 +587,8 @@ CurveWs carve(void* workspace, int64_t segments, int64_t n) {
     w.keys_b = (unsigned*)bump(p, segments * n * 4);
     w.lab_a = bump(p, segments * n + 16);
     w.lab_b = bump(p, segments * n + 16);
-    w.tile_hist = (unsigned*)bump(p, segments * 256 * (sort_tiles + 1) * 4);
-    w.digit_total = (unsigned*)bump(p, segments * 256 * 4);
+    w.sort_scratch = (unsigned*)bump(p, (int64_t)radix_sort_scratch_words(n, segments, 4) * 4);
+    (void)sort_tiles;
     w.info = (TileInfo*)bump(p, segments * (scan_tiles + 1) * (int64_t)sizeof(TileInfo));
     w.seg_totals = (unsigned*)bump(p, segments * 2 * 4);
     w.auroc_acc = (unsigned long long*)bump(p, segments * 8);
@@ -605,8 +605,9 @@ CurveWs carve(void* workspace, int64_t segments, int64_t n) {
 extern "C" int mb200_curve_evaluate(const void* preds, int preds_dtype, const void* target, int target_dtype,
                                     int64_t n, int64_t num_classes, int64_t pos_label, void* workspace,
                                     int64_t workspace_bytes, float* out_auroc, float* out_ap, int64_t* out_counts,
-                                    float* fps_out, float* tps_out, float* thr_out, void* stream) {
+                                    float* fps_out, float* tps_out, float* thr_out, uint32_t* err_flag, void* stream) {
     MB200_REQUIRE(n >= 1, "curve evaluation needs at least one sample (got %lld)", (long long)n);
+    MB200_REQUIRE(n < (1ll << 30), "more than 2^30-1 samples per curve are not supported");
     MB200_REQUIRE(num_classes >= 1, "bad num_classes");
     MB200_REQUIRE(n < (1ll << 31), "more than 2^31-1 samples per curve are not supported");
     MB200_REQUIRE(preds && target && workspace && out_auroc && out_ap && out_counts, "NULL pointer");
@@ -647,9 +648,13 @@ extern "C" int mb200_curve_evaluate(const void* preds, int preds_dtype, const vo
     }
     count_launch();
 
-    // ---- 4 x 8-bit LSD passes (ping-pong; an even number of passes leaves the result in the *_a buffers) ----
-    radix_sort_passes<unsigned, unsigned char>(w.keys_a, w.lab_a, w.keys_b, w.lab_b, ni, (int)segments, 4, w.tile_hist,
-                                               w.digit_total, st, &count_launch);
+    // ---- 4 one-sweep radix passes (ping-pong; an even number of passes leaves the result in the *_a buffers) ----
+    {
+        const int where = radix_sort_passes<unsigned, unsigned char>(w.keys_a, w.lab_a, w.keys_b, w.lab_b, ni,
+                                                                     (int)segments, 4, w.sort_scratch, err_flag, st,
+                                                                     &count_launch);
+        if (where < 0) return check_cuda(cudaGetLastError(), "radix sort");
+    }
     unsigned* kin = w.keys_a;
     unsigned char* lin = w.lab_a;
 

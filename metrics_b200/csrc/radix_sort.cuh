@@ -1,175 +1,259 @@
-// Segmented LSD radix sort building blocks (8-bit digits), shared by the curve and detection kernels.
-// KeyT in {u32, u64}, ValT any trivially copyable payload.  grid = (tiles_per_segment, segments).
+// Segmented LSD radix sort (8-bit digits) for sm_100a — "one sweep" per digit.
+//
+//   digit histograms   ONE pass over the keys counts every digit of every radix pass (order-independent), a tiny scan
+//                      turns them into per-(segment, pass) exclusive digit offsets;
+//   per radix pass     ONE kernel: CTAs take tiles in ticket order, rank their 8192 keys (warp-striped layout,
+//                      MATCH.ANY groups + per-warp digit counters in shared memory), publish the tile's digit counts,
+//                      obtain the counts of all earlier tiles of the segment by decoupled look-back on a status word
+//                      per (tile, digit) [flag:2 | count:30], reorder keys+payload by digit in shared memory and write
+//                      digit runs to their final positions with coalesced stores.
+// A pass therefore reads and writes every record exactly once (5 B/record for the curve keys); no per-pass histogram or
+// scan kernels.  The look-back spin is bounded: if it ever expires the kernel raises MB200_FLAG_SPIN_TIMEOUT and exits
+// instead of hanging the GPU.
+// KeyT in {u32, u64}, ValT any trivially copyable payload.  Segments have equal length n (< 2^30).
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mb200 {
 
-// =====================================================================================================
-constexpr int kSortThreads = 256;
+constexpr int kSortThreads = 512;
+constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortItems = 16;
-constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per CTA
+constexpr int kSortTile = kSortThreads * kSortItems;  // 8192 keys per CTA
+constexpr unsigned kStatAgg = 1u << 30;               // tile aggregate published
+constexpr unsigned kStatPrefix = 2u << 30;            // inclusive prefix published
+constexpr unsigned kStatMask = (1u << 30) - 1u;
 
-// (A) per-tile digit histogram -> tile_hist[seg][digit][tile]
+// ---- digit histograms of all passes in one read ----------------------------------------------------------------------
+// hist layout: [segment][pass][256]
 template <typename KeyT>
-__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const KeyT* __restrict__ keys, int n, int tiles,
-                                                                  int shift, unsigned* __restrict__ tile_hist) {
-    __shared__ unsigned hist[256];
-    hist[threadIdx.x] = 0;
+__global__ void __launch_bounds__(256) radix_digit_hist_kernel(const KeyT* __restrict__ keys, int n, int key_bytes,
+                                                               unsigned* __restrict__ hist) {
+    extern __shared__ unsigned sh_hist[];  // key_bytes * 256
+    for (int i = threadIdx.x; i < key_bytes * 256; i += blockDim.x) sh_hist[i] = 0;
     __syncthreads();
-    const int seg = blockIdx.y, tile = blockIdx.x;
+    const int seg = blockIdx.y;
     const KeyT* __restrict__ k = keys + (size_t)seg * n;
-    const int base = tile * kSortTile;
-#pragma unroll
-    for (int i = 0; i < kSortItems; ++i) {
-        const int idx = base + i * kSortThreads + threadIdx.x;
-        if (idx < n) atomicAdd(&hist[(unsigned)(k[idx] >> shift) & 255u], 1u);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const KeyT key = k[i];
+        for (int p = 0; p < key_bytes; ++p) atomicAdd(&sh_hist[p * 256 + ((unsigned)(key >> (8 * p)) & 255u)], 1u);
     }
     __syncthreads();
-    tile_hist[((size_t)seg * 256 + threadIdx.x) * tiles + tile] = hist[threadIdx.x];
+    for (int i = threadIdx.x; i < key_bytes * 256; i += blockDim.x) {
+        const unsigned v = sh_hist[i];
+        if (v) atomicAdd(&hist[(size_t)seg * key_bytes * 256 + i], v);
+    }
 }
 
-// (B) per (segment, digit): exclusive scan over tiles in place; digit totals -> digit_total[seg][digit]
-static __global__ void __launch_bounds__(256) radix_scan_kernel(unsigned* __restrict__ tile_hist, int tiles,
-                                                         unsigned* __restrict__ digit_total) {
-    __shared__ unsigned warp_sums[8];
-    __shared__ unsigned carry_s;
-    const int seg = blockIdx.y, digit = blockIdx.x;
-    unsigned* __restrict__ h = tile_hist + ((size_t)seg * 256 + digit) * tiles;
+// in-place exclusive scan of each 256-bin histogram: grid = segments * passes, block = 256
+static __global__ void __launch_bounds__(256) radix_digit_scan_kernel(unsigned* __restrict__ hist) {
+    __shared__ unsigned ws[8];
+    unsigned* h = hist + (size_t)blockIdx.x * 256;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int base = 0; base < tiles; base += 256) {
-        const int idx = base + threadIdx.x;
-        const unsigned v = idx < tiles ? h[idx] : 0u;
-        unsigned incl = v;
+    const unsigned v = h[threadIdx.x];
+    unsigned incl = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t = __shfl_up_sync(kFull, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) warp_sums[warp] = incl;
-        __syncthreads();
-        unsigned woff = 0;
-        for (int w = 0; w < warp; ++w) woff += warp_sums[w];
-        const unsigned carry = carry_s;
-        if (idx < tiles) h[idx] = carry + woff + incl - v;
-        __syncthreads();
-        if (threadIdx.x == 255) carry_s = carry + woff + incl;
-        __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
     }
-    if (threadIdx.x == 0) digit_total[seg * 256 + digit] = carry_s;
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    unsigned woff = 0;
+    for (int w = 0; w < warp; ++w) woff += ws[w];
+    h[threadIdx.x] = woff + incl - v;
 }
 
-// (C) stable scatter.  Warp-striped arrangement: warp w owns keys [tile_base + w*512, +512), item i of lane l is
-// element i*32 + l of that range, so (i, l) order == memory order.  Ranks come from MATCH.ANY groups + per-warp
-// running digit counters in shared memory.
+// ---- one radix pass ------------------------------------------------------------------------------------------------------
 template <typename KeyT, typename ValT>
-__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const KeyT* __restrict__ keys_in,
-                                                                     const ValT* __restrict__ labels_in,
-                                                                     KeyT* __restrict__ keys_out,
-                                                                     ValT* __restrict__ labels_out, int n,
-                                                                     int tiles, int shift,
-                                                                     const unsigned* __restrict__ tile_hist,
-                                                                     const unsigned* __restrict__ digit_total) {
-    __shared__ unsigned warp_hist[8][256];
-    __shared__ unsigned digit_base[256];
-    __shared__ unsigned scan_tmp[8];
-    const int seg = blockIdx.y, tile = blockIdx.x;
+struct SortSmem {
+    KeyT keys[kSortTile];
+    ValT vals[kSortTile];
+    unsigned warp_hist[kSortWarps][256];
+    unsigned digit_base[256];  // global position of the tile's first key of each digit
+    unsigned tile_off[256];    // position of the digit's run inside the tile
+    unsigned scan_tmp[8];
+    unsigned tile_index;
+};
+
+template <typename KeyT, typename ValT>
+__global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 2 : 1) radix_onesweep_kernel(
+    const KeyT* __restrict__ keys_in, const ValT* __restrict__ vals_in, KeyT* __restrict__ keys_out,
+    ValT* __restrict__ vals_out, int n, int tiles_per_seg, int shift, int pass, int key_bytes,
+    const unsigned* __restrict__ digit_offsets /*[seg][pass][256] exclusive*/, unsigned* __restrict__ status /*[tiles][256]*/,
+    unsigned* __restrict__ ticket, unsigned* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char sort_smem_raw[];
+    SortSmem<KeyT, ValT>& sm = *reinterpret_cast<SortSmem<KeyT, ValT>*>(sort_smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) sm.tile_index = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&sm.warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned tile_global = sm.tile_index;
+    const int seg = (int)(tile_global / (unsigned)tiles_per_seg);
+    const int tile = (int)(tile_global % (unsigned)tiles_per_seg);
     const size_t seg_off = (size_t)seg * n;
     const KeyT* __restrict__ kin = keys_in + seg_off;
-    const ValT* __restrict__ lin = labels_in + seg_off;
-    for (int i = threadIdx.x; i < 8 * 256; i += kSortThreads) (&warp_hist[0][0])[i] = 0;
+    const ValT* __restrict__ vin = vals_in + seg_off;
+    const int tile_base = tile * kSortTile;
+    const int tile_count = min(kSortTile, n - tile_base);
 
-    // global base of every digit for this tile: exclusive scan of the digit totals + this tile's exclusive offset
-    {
-        const unsigned tot = digit_total[seg * 256 + threadIdx.x];
-        unsigned incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t = __shfl_up_sync(kFull, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) scan_tmp[warp] = incl;
-        __syncthreads();
-        unsigned woff = 0;
-        for (int w = 0; w < warp; ++w) woff += scan_tmp[w];
-        digit_base[threadIdx.x] = woff + incl - tot + tile_hist[((size_t)seg * 256 + threadIdx.x) * tiles + tile];
-    }
-    __syncthreads();
-
-    const int wbase = tile * kSortTile + warp * (kSortItems * 32);
+    // ---- load (warp-striped: item i of lane l is element i*32 + l of the warp's 512-key span) and rank ----
+    const int wbase = tile_base + warp * (kSortItems * 32);
     KeyT key[kSortItems];
-    ValT lab[kSortItems];
+    ValT val[kSortItems];
     unsigned short rank[kSortItems];
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
         const int idx = wbase + i * 32 + lane;
         const bool valid = idx < n;
         key[i] = valid ? kin[idx] : (KeyT)0;
-        lab[i] = valid ? lin[idx] : (ValT)0;
+        val[i] = valid ? vin[idx] : (ValT)0;
     }
     const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
         const int idx = wbase + i * 32 + lane;
         const bool valid = idx < n;
-        const unsigned digit = valid ? ((unsigned)(key[i] >> shift) & 255u) : (0x100u + lane);  // invalid lanes: unique groups
+        const unsigned digit = valid ? ((unsigned)(key[i] >> shift) & 255u) : (0x100u + lane);  // invalid: unique groups
         const unsigned peers = __match_any_sync(kFull, digit);
         const int leader = __ffs(peers) - 1;
         unsigned base = 0;
         if (valid && lane == leader) {
-            base = warp_hist[warp][digit];
-            warp_hist[warp][digit] = base + __popc(peers);
+            base = sm.warp_hist[warp][digit];
+            sm.warp_hist[warp][digit] = base + __popc(peers);
         }
         base = __shfl_sync(kFull, base, leader);
         rank[i] = (unsigned short)(base + __popc(peers & lt_mask));
         __syncwarp();
     }
     __syncthreads();
-    // exclusive scan over the 8 warps for every digit
-    {
+
+    // ---- per digit: exclusive scan over warps, publish, look back ----
+    unsigned my_count = 0;
+    if (threadIdx.x < 256) {
+        const int d = threadIdx.x;
         unsigned off = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const unsigned c = warp_hist[w][threadIdx.x];
-            warp_hist[w][threadIdx.x] = off;
+        for (int w = 0; w < kSortWarps; ++w) {
+            const unsigned c = sm.warp_hist[w][d];
+            sm.warp_hist[w][d] = off;
             off += c;
         }
+        my_count = off;
+        volatile unsigned* st = status + (size_t)tile_global * 256 + d;
+        unsigned excl = 0;
+        if (tile == 0) {
+            *st = kStatPrefix | my_count;
+        } else {
+            *st = kStatAgg | my_count;
+            long long j = (long long)tile_global - 1;
+            unsigned spins = 0;
+            while (true) {
+                const unsigned s = *(volatile unsigned*)(status + (size_t)j * 256 + d);
+                const unsigned flag = s & ~kStatMask;
+                if (flag == 0u) {
+                    if (++spins > (1u << 24)) {  // never hang the GPU: report and produce garbage instead
+                        if (err) atomicOr(err, MB200_FLAG_SPIN_TIMEOUT);
+                        break;
+                    }
+                    __nanosleep(20);
+                    continue;
+                }
+                excl += s & kStatMask;
+                if (flag == kStatPrefix) break;
+                --j;  // the segment's first tile always publishes a prefix, so j never leaves the segment
+            }
+            *st = kStatPrefix | ((excl + my_count) & kStatMask);
+        }
+        sm.digit_base[d] = digit_offsets[((size_t)seg * key_bytes + pass) * 256 + d] + excl;
+        // exclusive scan of the tile's digit counts over the digits
+        unsigned incl = my_count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) sm.scan_tmp[warp] = incl;
+        sm.tile_off[d] = incl - my_count;  // warp-local for now
     }
     __syncthreads();
-    KeyT* __restrict__ kout = keys_out + seg_off;
-    ValT* __restrict__ lout = labels_out + seg_off;
+    if (threadIdx.x < 256) {
+        unsigned woff = 0;
+        for (int w = 0; w < warp; ++w) woff += sm.scan_tmp[w];
+        sm.tile_off[threadIdx.x] += woff;
+    }
+    __syncthreads();
+
+    // ---- reorder by digit in shared memory ----
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
         const int idx = wbase + i * 32 + lane;
         if (idx < n) {
             const unsigned digit = (unsigned)(key[i] >> shift) & 255u;
-            const unsigned dst = digit_base[digit] + warp_hist[warp][digit] + rank[i];
-            kout[dst] = key[i];
-            lout[dst] = lab[i];
+            const unsigned pos = sm.tile_off[digit] + sm.warp_hist[warp][digit] + rank[i];
+            sm.keys[pos] = key[i];
+            sm.vals[pos] = val[i];
         }
+    }
+    __syncthreads();
+    // ---- coalesced stores of the digit runs ----
+    KeyT* __restrict__ kout = keys_out + seg_off;
+    ValT* __restrict__ vout = vals_out + seg_off;
+    for (int i = threadIdx.x; i < tile_count; i += kSortThreads) {
+        const KeyT k = sm.keys[i];
+        const unsigned digit = (unsigned)(k >> shift) & 255u;
+        const unsigned dst = sm.digit_base[digit] + ((unsigned)i - sm.tile_off[digit]);
+        kout[dst] = k;
+        vout[dst] = sm.vals[i];
     }
 }
 
+// ---- host driver -----------------------------------------------------------------------------------------------------------
+// scratch (unsigned words): hist [segments*key_bytes*256] | status [key_bytes][segments*tiles][256] | tickets [key_bytes]
+static inline size_t radix_sort_scratch_words(long long n, long long segments, int key_bytes) {
+    const long long tiles = (n + kSortTile - 1) / kSortTile;
+    return (size_t)(segments * key_bytes * 256 + (long long)key_bytes * segments * tiles * 256 + key_bytes + 64);
+}
 
-// Host helper: `key_bytes` passes over ping-pong buffers; returns 0/1 = which buffer pair holds the result.
+// Sorts every segment by the low `key_bytes` bytes of the key.  Returns 0/1 = which buffer pair holds the result
+// (a = 0, b = 1), or a negative MB200_ERR_* code.
 template <typename KeyT, typename ValT>
 static inline int radix_sort_passes(KeyT* keys_a, ValT* vals_a, KeyT* keys_b, ValT* vals_b, int n, int segments,
-                                    int key_bytes, unsigned* tile_hist, unsigned* digit_total, cudaStream_t st,
+                                    int key_bytes, unsigned* scratch, unsigned* err_flag, cudaStream_t st,
                                     void (*on_launch)()) {
     const int tiles = (n + kSortTile - 1) / kSortTile;
-    const dim3 tgrid((unsigned)tiles, (unsigned)segments);
+    const size_t words = radix_sort_scratch_words(n, segments, key_bytes);
+    if (cudaMemsetAsync(scratch, 0, words * sizeof(unsigned), st) != cudaSuccess) return MB200_ERR_CUDA;
+    unsigned* hist = scratch;
+    unsigned* status = hist + (size_t)segments * key_bytes * 256;
+    unsigned* tickets = status + (size_t)key_bytes * segments * tiles * 256;
+
+    int hgrid = (n + 256 * 16 - 1) / (256 * 16);
+    const int hcap = std::max(1, (sm_count() * 8) / std::max(1, segments));
+    if (hgrid > hcap) hgrid = hcap;
+    if (hgrid < 1) hgrid = 1;
+    radix_digit_hist_kernel<KeyT><<<dim3((unsigned)hgrid, (unsigned)segments), 256, (size_t)key_bytes * 256 * 4, st>>>(
+        keys_a, n, key_bytes, hist);
+    radix_digit_scan_kernel<<<(unsigned)(segments * key_bytes), 256, 0, st>>>(hist);
+    if (on_launch) on_launch(), on_launch();
+
+    auto kern = radix_onesweep_kernel<KeyT, ValT>;
+    const size_t smem = sizeof(SortSmem<KeyT, ValT>);
+    static thread_local bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return MB200_ERR_CUDA;
+        configured = true;
+    }
     KeyT *kin = keys_a, *kout = keys_b;
     ValT *vin = vals_a, *vout = vals_b;
     for (int pass = 0; pass < key_bytes; ++pass) {
-        const int shift = 8 * pass;
-        radix_hist_kernel<KeyT><<<tgrid, kSortThreads, 0, st>>>(kin, n, tiles, shift, tile_hist);
-        radix_scan_kernel<<<dim3(256, (unsigned)segments), 256, 0, st>>>(tile_hist, tiles, digit_total);
-        radix_scatter_kernel<KeyT, ValT><<<tgrid, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, tiles, shift,
-                                                                          tile_hist, digit_total);
-        if (on_launch) on_launch(), on_launch(), on_launch();
+        kern<<<(unsigned)(segments * tiles), kSortThreads, smem, st>>>(
+            kin, vin, kout, vout, n, tiles, 8 * pass, pass, key_bytes, hist,
+            status + (size_t)pass * segments * tiles * 256, tickets + pass, err_flag);
+        if (on_launch) on_launch();
         KeyT* tk = kin;
         kin = kout;
         kout = tk;

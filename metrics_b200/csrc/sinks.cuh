@@ -161,4 +161,30 @@ struct StatsSink {
 };
 
 
+// Samplewise stat scores: per (sample, class) tp / fp / fn deltas in a zeroed [3][n_samples][C] int64 scratch plus the
+// number of admitted positions per sample; `idx / inner` is the sample.  tn is derived by the caller.
+struct SamplewiseSink {
+    long long* counts;   // [3][n_samples][C]
+    long long* n_valid;  // [n_samples]
+    long long n_samples;
+    long long inner;
+    int C;
+    struct Local {};
+    static constexpr bool kNeedsTarget = true;
+    __device__ __forceinline__ void block_init() {}
+    __device__ __forceinline__ void init(Local&) {}
+    __device__ __forceinline__ void row(Local&, long long idx, long long t, int p) {
+        const long long s = idx / inner;
+        const long long plane = n_samples * C;
+        red_add_u64(n_valid + s, 1ull);
+        if ((long long)p == t) {
+            red_add_u64(counts + s * C + p, 1ull);
+        } else {
+            red_add_u64(counts + plane + s * C + p, 1ull);
+            red_add_u64(counts + 2 * plane + s * C + t, 1ull);
+        }
+    }
+    __device__ __forceinline__ void finish(Local&) {}
+};
+
 }  // namespace mb200

@@ -10,9 +10,7 @@ from typing_extensions import Literal
 from metrics_b200.functional.classification.stat_scores import (
     _multiclass_stat_scores_arg_validation,
     _multiclass_stat_scores_tensor_validation,
-    _multiclass_stat_scores_update_,
-    _require_kernel_mode,
-    stat_scores_workspace,
+    _multiclass_stat_scores_states,
 )
 from metrics_b200.utilities.compute import _adjust_weights_safe_divide, _safe_divide
 
@@ -55,15 +53,7 @@ def multiclass_accuracy(
     if validate_args:
         _multiclass_stat_scores_arg_validation(num_classes, top_k, average, multidim_average, ignore_index)
         _multiclass_stat_scores_tensor_validation(preds, target, num_classes, multidim_average, ignore_index)
-    _require_kernel_mode(top_k, multidim_average)
-    micro = average == "micro"
-    states = [torch.zeros(1 if micro else num_classes, dtype=torch.int64, device=preds.device) for _ in range(4)]
-    ws = stat_scores_workspace(num_classes, preds.device)
-    _multiclass_stat_scores_update_(
-        *states, ws, preds, target, num_classes, top_k, average, multidim_average, ignore_index, validate_args
-    )
-    if micro:
-        states = [s.reshape(()) for s in states]
+    states = _multiclass_stat_scores_states(preds, target, num_classes, top_k, average, multidim_average, ignore_index, validate_args)
     return _accuracy_reduce(*states, average=average, multidim_average=multidim_average, top_k=top_k)
 
 

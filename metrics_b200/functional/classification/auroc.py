@@ -22,9 +22,8 @@ from metrics_b200.functional.classification.precision_recall_curve import (
     _multiclass_precision_recall_curve_format,
     _multiclass_precision_recall_curve_tensor_validation,
     _multiclass_precision_recall_curve_update,
-    _no_binned,
 )
-from metrics_b200.functional.classification.roc import _binary_roc_compute
+from metrics_b200.functional.classification.roc import _binary_roc_compute, _multiclass_roc_compute
 from metrics_b200.utilities.compute import _auc_compute_without_check, _safe_divide
 from metrics_b200.utilities.prints import rank_zero_warn
 
@@ -79,19 +78,23 @@ def _binary_auroc_compute(
     thresholds: Optional[Tensor],
     max_fpr: Optional[float] = None,
     pos_label: int = 1,
+    scalars: Optional[tuple] = None,
 ) -> Tensor:
-    """Area under the ROC curve (reference :83-107)."""
-    _no_binned(thresholds)
-    if max_fpr is None or max_fpr == 1:
-        preds, target = state
-        if preds.numel() == 0:
-            raise IndexError("metrics_b200: cannot compute AUROC from zero samples")
-        auroc, _, counts, _ = _native.curve_evaluate(preds, target, 1, pos_label, want_curve=False)
+    """Area under the ROC curve (reference :83-107).  ``scalars``: an already available ``(auroc, ap, counts)``
+    evaluation of the same state (metric classes share one per compute group)."""
+    if thresholds is None and (max_fpr is None or max_fpr == 1):
+        if scalars is not None:
+            auroc, _, counts = scalars
+        else:
+            preds, target = state
+            if preds.numel() == 0:
+                raise IndexError("metrics_b200: cannot compute AUROC from zero samples")
+            auroc, _, counts, _ = _native.curve_evaluate(preds, target, 1, pos_label, want_curve=False)
         _warn_degenerate(counts[0].cpu())  # the reference branches on `fps[-1] <= 0` / `tps[-1] <= 0` (host sync) too
         return auroc[0]
 
     fpr, tpr, _ = _binary_roc_compute(state, thresholds, pos_label)
-    if fpr.sum() == 0 or tpr.sum() == 0:
+    if max_fpr is None or max_fpr == 1 or fpr.sum() == 0 or tpr.sum() == 0:
         return _auc_compute_without_check(fpr, tpr, 1.0)
     max_area: Tensor = tensor(max_fpr, device=fpr.device)
     # add one point at max_fpr by linear interpolation, then McClish-standardise the partial area
@@ -139,12 +142,19 @@ def _multiclass_auroc_compute(
     num_classes: int,
     average: Optional[str] = "macro",
     thresholds: Optional[Tensor] = None,
+    scalars: Optional[tuple] = None,
 ) -> Tensor:
     """Per-class one-vs-rest AUROC from ONE batched sort + scan, then the class reduction (reference :193-205).
     Classes without positives (or without negatives) score 0 and ARE part of the macro mean, like the reference."""
-    _no_binned(thresholds)
-    preds, target = state
-    auroc, _, counts, _ = _native.curve_evaluate(preds, target, num_classes, want_curve=False)
+    if isinstance(state, Tensor) and thresholds is not None:  # binned
+        fpr, tpr, _ = _multiclass_roc_compute(state, num_classes, thresholds)
+        res = _auc_compute_without_check(fpr, tpr, 1.0, axis=1)
+        return _reduce_per_class(res, average, state[0][:, 1, :].sum(-1).float(), "Average precision")
+    if scalars is not None:
+        auroc, _, counts = scalars
+    else:
+        preds, target = state
+        auroc, _, counts, _ = _native.curve_evaluate(preds, target, num_classes, want_curve=False)
     return _reduce_per_class(auroc, average, counts[:, 0].float(), "Average precision")
 
 

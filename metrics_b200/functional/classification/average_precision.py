@@ -22,7 +22,10 @@ from metrics_b200.functional.classification.precision_recall_curve import (
     _multiclass_precision_recall_curve_format,
     _multiclass_precision_recall_curve_tensor_validation,
     _multiclass_precision_recall_curve_update,
-    _no_binned,
+)
+from metrics_b200.functional.classification.precision_recall_curve import (  # noqa: E402
+    _binary_precision_recall_curve_compute,
+    _multiclass_precision_recall_curve_compute,
 )
 from metrics_b200.utilities.prints import rank_zero_warn
 
@@ -32,15 +35,21 @@ def _reduce_average_precision(res: Tensor, average: Optional[str] = "macro", wei
 
 
 def _binary_average_precision_compute(
-    state: Union[Tensor, tuple[Tensor, Tensor]], thresholds: Optional[Tensor], pos_label: int = 1
+    state: Union[Tensor, tuple[Tensor, Tensor]], thresholds: Optional[Tensor], pos_label: int = 1,
+    scalars: Optional[tuple] = None,
 ) -> Tensor:
     """Reference :70-75.  With no positive sample the reference warns, forces recall to 1 and returns -0.0."""
-    _no_binned(thresholds)
+    if isinstance(state, Tensor) and thresholds is not None:  # binned
+        precision, recall, _ = _binary_precision_recall_curve_compute(state, thresholds)
+        return -torch.sum((recall[1:] - recall[:-1]) * precision[:-1])
     preds, target = state
-    if preds.numel() == 0:
-        raise IndexError("metrics_b200: cannot compute average precision from zero samples")
-    _, ap, counts, _ = _native.curve_evaluate(preds, target, 1, pos_label, want_curve=False)
-    if bool((target == 0).all()):
+    if scalars is not None:
+        _, ap, counts = scalars
+    else:
+        if preds.numel() == 0:
+            raise IndexError("metrics_b200: cannot compute average precision from zero samples")
+        _, ap, counts, _ = _native.curve_evaluate(preds, target, 1, pos_label, want_curve=False)
+    if int(counts[0, 0]) == 0 and bool((target == 0).all()):
         rank_zero_warn(
             "No positive samples found in target, recall is undefined. Setting recall to one for all thresholds.",
             UserWarning,
@@ -81,6 +90,7 @@ def _multiclass_average_precision_compute(
     num_classes: int,
     average: Optional[str] = "macro",
     thresholds: Optional[Tensor] = None,
+    scalars: Optional[tuple] = None,
 ) -> Tensor:
     """Per-class one-vs-rest AP from ONE batched sort + scan (reference :164-176).
 
@@ -89,9 +99,15 @@ def _multiclass_average_precision_compute(
     and it is dropped from macro/weighted means with a warning — unless every target is class 0, in which case the
     guard fires for every class and absent classes score -0.0.
     """
-    _no_binned(thresholds)
+    if isinstance(state, Tensor) and thresholds is not None:  # binned
+        precision, recall, _ = _multiclass_precision_recall_curve_compute(state, num_classes, thresholds)
+        res = -torch.sum((recall[:, 1:] - recall[:, :-1]) * precision[:, :-1], 1)
+        return _reduce_average_precision(res, average, weights=state[0][:, 1, :].sum(-1).float())
     preds, target = state
-    _, ap, counts, _ = _native.curve_evaluate(preds, target, num_classes, want_curve=False)
+    if scalars is not None:
+        _, ap, counts = scalars
+    else:
+        _, ap, counts, _ = _native.curve_evaluate(preds, target, num_classes, want_curve=False)
     n_pos = counts[:, 0]
     if not bool((target == 0).all()):
         ap = torch.where(n_pos == 0, torch.full_like(ap, float("nan")), ap)

@@ -5,7 +5,9 @@ pipeline here (`mb200_curve_evaluate`, csrc/curve.cu): key packing, 4-pass 8-bit
 byte), tie-collapsing integer scan.  The multiclass one-vs-rest loop of the reference (one full sort per class in
 Python, :565-569) is a single call with one contiguous segment per class.
 
-Binned mode (``thresholds`` given) is not part of this round and raises NotImplementedError.
+Binned mode (``thresholds`` given): the `[T, (C,) 2, 2]` multi-threshold confusion matrix of a batch comes from ONE
+pass (`mb200_binned_curve_update`, csrc/binned.cu: bucket search + histogram + suffix sums) instead of the reference's
+N*T(*C) temporaries or T passes (:191-251, :464-533).
 """
 from __future__ import annotations
 
@@ -22,10 +24,15 @@ from metrics_b200.utilities.prints import rank_zero_warn
 
 
 def _no_binned(thresholds: Optional[Union[int, List[float], Tensor]]) -> None:
+    """Kept for callers that only make sense in exact mode."""
     if thresholds is not None:
-        raise NotImplementedError(
-            "metrics_b200: binned curve metrics (`thresholds` given) are not implemented yet; use `thresholds=None`."
-        )
+        raise ValueError("this code path expects exact mode (`thresholds=None`)")
+
+
+def _safe_div(num: Tensor, denom: Tensor) -> Tensor:
+    from metrics_b200.utilities.compute import _safe_divide
+
+    return _safe_divide(num, denom)
 
 
 def _binary_clf_curve(
@@ -131,8 +138,10 @@ def _binary_precision_recall_curve_format(
 def _binary_precision_recall_curve_update(
     preds: Tensor, target: Tensor, thresholds: Optional[Tensor]
 ) -> Union[Tensor, tuple[Tensor, Tensor]]:
-    _no_binned(thresholds)
-    return preds, target
+    """Exact mode: the formatted batch itself.  Binned mode: its ``[T, 2, 2]`` multi-threshold confusion matrix."""
+    if thresholds is None:
+        return preds, target
+    return _native.binned_curve_update(preds, target, thresholds.to(preds.device), 1)
 
 
 def _pr_from_counts(fps: Tensor, tps: Tensor, thr: Tensor, all_negative: bool) -> tuple[Tensor, Tensor, Tensor]:
@@ -153,7 +162,13 @@ def _pr_from_counts(fps: Tensor, tps: Tensor, thr: Tensor, all_negative: bool) -
 def _binary_precision_recall_curve_compute(
     state: Union[Tensor, tuple[Tensor, Tensor]], thresholds: Optional[Tensor], pos_label: int = 1
 ) -> tuple[Tensor, Tensor, Tensor]:
-    _no_binned(thresholds)
+    if isinstance(state, Tensor) and thresholds is not None:  # binned (reference :265-273)
+        tps, fps, fns = state[:, 1, 1], state[:, 0, 1], state[:, 1, 0]
+        precision = _safe_div(tps, tps + fps)
+        recall = _safe_div(tps, tps + fns)
+        precision = torch.cat([precision, torch.ones(1, dtype=precision.dtype, device=precision.device)])
+        recall = torch.cat([recall, torch.zeros(1, dtype=recall.dtype, device=recall.device)])
+        return precision, recall, thresholds
     fps, tps, thr = _binary_clf_curve(state[0], state[1], pos_label=pos_label)
     # the reference tests `(target == 0).all()` on the raw target, whatever pos_label is (:278)
     return _pr_from_counts(fps, tps, thr, bool((state[1] == 0).all()))
@@ -249,8 +264,11 @@ def _multiclass_precision_recall_curve_format(
 def _multiclass_precision_recall_curve_update(
     preds: Tensor, target: Tensor, num_classes: int, thresholds: Optional[Tensor], average: Optional[str] = None
 ) -> Union[Tensor, tuple[Tensor, Tensor]]:
-    _no_binned(thresholds)
-    return preds, target
+    if thresholds is None:
+        return preds, target
+    if average == "micro":
+        return _binary_precision_recall_curve_update(preds, target, thresholds)
+    return _native.binned_curve_update(preds, target, thresholds.to(preds.device), num_classes)
 
 
 def _ovr_curves(preds: Tensor, target: Tensor, num_classes: int):
@@ -268,10 +286,25 @@ def _multiclass_precision_recall_curve_compute(
     thresholds: Optional[Tensor],
     average: Optional[str] = None,
 ):
-    """Per-class PR curves (lists, exact mode) or their macro/micro aggregation — reference :536-589."""
-    _no_binned(thresholds)
+    """Per-class PR curves (lists in exact mode, ``[C, T+1]`` tensors in binned mode) or their macro/micro aggregation
+    — reference :536-589."""
     if average == "micro":
         return _binary_precision_recall_curve_compute(state, thresholds)
+    if isinstance(state, Tensor) and thresholds is not None:
+        tps, fps, fns = state[:, :, 1, 1], state[:, :, 0, 1], state[:, :, 1, 0]
+        precision = _safe_div(tps, tps + fps)
+        recall = _safe_div(tps, tps + fns)
+        precision = torch.cat([precision, torch.ones(1, num_classes, dtype=precision.dtype, device=precision.device)]).T
+        recall = torch.cat([recall, torch.zeros(1, num_classes, dtype=recall.dtype, device=recall.device)]).T
+        if average == "macro":
+            thres = thresholds.repeat(num_classes).sort().values
+            mean_precision = precision.flatten().sort().values
+            mean_recall = torch.zeros_like(mean_precision)
+            for c in range(num_classes):
+                mean_recall += interp(mean_precision, precision[c], recall[c])
+            mean_recall /= num_classes
+            return mean_precision, mean_recall, thres
+        return precision, recall, thresholds
     fps, tps, thr, lengths = _ovr_curves(state[0], state[1], num_classes)
     all_zero = bool((state[1] == 0).all())
     precision_list, recall_list, thres_list = [], [], []

@@ -17,8 +17,8 @@ from metrics_b200.functional.classification.precision_recall_curve import (
     _multiclass_precision_recall_curve_format,
     _multiclass_precision_recall_curve_tensor_validation,
     _multiclass_precision_recall_curve_update,
-    _no_binned,
     _ovr_curves,
+    _safe_div,
 )
 from metrics_b200.utilities.compute import interp
 from metrics_b200.utilities.prints import rank_zero_warn
@@ -55,7 +55,9 @@ def _roc_from_counts(fps: Tensor, tps: Tensor, thres: Tensor) -> tuple[Tensor, T
 def _binary_roc_compute(
     state: Union[Tensor, tuple[Tensor, Tensor]], thresholds: Optional[Tensor], pos_label: int = 1
 ) -> tuple[Tensor, Tensor, Tensor]:
-    _no_binned(thresholds)
+    if isinstance(state, Tensor) and thresholds is not None:  # binned (reference :45-52)
+        tps, fps, fns, tns = state[:, 1, 1], state[:, 0, 1], state[:, 1, 0], state[:, 0, 0]
+        return _safe_div(fps, fps + tns).flip(0), _safe_div(tps, tps + fns).flip(0), thresholds.flip(0)
     fps, tps, thres = _binary_clf_curve(preds=state[0], target=state[1], pos_label=pos_label)
     return _roc_from_counts(fps, tps, thres)
 
@@ -83,9 +85,22 @@ def _multiclass_roc_compute(
     average: Optional[str] = None,
 ):
     """Per-class ROC curves from ONE batched sort (reference loops over classes, :176-181)."""
-    _no_binned(thresholds)
     if average == "micro":
         return _binary_roc_compute(state, thresholds, pos_label=1)
+    if isinstance(state, Tensor) and thresholds is not None:  # binned (reference :171-179)
+        tps, fps, fns, tns = state[:, :, 1, 1], state[:, :, 0, 1], state[:, :, 1, 0], state[:, :, 0, 0]
+        tpr = _safe_div(tps, tps + fns).flip(0).T
+        fpr = _safe_div(fps, fps + tns).flip(0).T
+        thres = thresholds.flip(0)
+        if average == "macro":
+            thres = thres.repeat(num_classes).sort(descending=True).values
+            mean_fpr = fpr.flatten().sort().values
+            mean_tpr = torch.zeros_like(mean_fpr)
+            for c in range(num_classes):
+                mean_tpr += interp(mean_fpr, fpr[c], tpr[c])
+            mean_tpr /= num_classes
+            return mean_fpr, mean_tpr, thres
+        return fpr, tpr, thres
     fps, tps, thr, lengths = _ovr_curves(state[0], state[1], num_classes)
     fpr_list, tpr_list, thres_list = [], [], []
     for c in range(num_classes):

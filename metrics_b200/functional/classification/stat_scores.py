@@ -75,10 +75,10 @@ def _multiclass_stat_scores_tensor_validation(
 
 
 def _require_kernel_mode(top_k: int, multidim_average: str) -> None:
-    if top_k != 1 or multidim_average != "global":
+    if top_k != 1 and multidim_average != "global":
         raise NotImplementedError(
-            "metrics_b200: multiclass stat scores currently run on the GPU kernel for `top_k=1` and "
-            f"`multidim_average='global'` only (got top_k={top_k}, multidim_average={multidim_average!r})."
+            "metrics_b200: multiclass stat scores with `top_k > 1` are implemented for `multidim_average='global'` "
+            f"only (got top_k={top_k}, multidim_average={multidim_average!r})."
         )
 
 
@@ -97,12 +97,18 @@ def _multiclass_stat_scores_update_(
     ignore_index: Optional[int] = None,
     validate_args: bool = False,
 ) -> None:
-    """FUSED format+update: add this batch's tp/fp/tn/fn to the four int64 state tensors in place."""
+    """FUSED format+update: add this batch's tp/fp/tn/fn to the four int64 state tensors in place
+    (``multidim_average="global"``; ``top_k > 1`` uses the top-k refined prediction kernel, per-class states)."""
     _require_kernel_mode(top_k, multidim_average)
+    if multidim_average != "global":
+        raise ValueError("use `_multiclass_stat_scores_update` for samplewise statistics")
     flag = new_flag(tp.device) if validate_args else None
-    _native.multiclass_stat_scores_update_(
-        tp, fp, tn, fn, workspace, preds, target, num_classes, ignore_index, average == "micro", flag
-    )
+    if top_k > 1:
+        _native.multiclass_stat_scores_topk_update_(tp, fp, tn, fn, workspace, preds, target, num_classes, top_k, ignore_index, flag)
+    else:
+        _native.multiclass_stat_scores_update_(
+            tp, fp, tn, fn, workspace, preds, target, num_classes, ignore_index, average == "micro", flag
+        )
     if flag is not None:
         raise_if_flagged(flag, num_classes, ignore_index)
 
@@ -121,7 +127,12 @@ def _multiclass_stat_scores_update(
     multidim_average: str = "global",
     ignore_index: Optional[int] = None,
 ) -> tuple[Tensor, Tensor, Tensor, Tensor]:
-    """Functional seam (reference :371-449): fresh tp, fp, tn, fn for one batch."""
+    """Functional seam (reference :371-449): fresh tp, fp, tn, fn for one batch (``[N, C]`` when samplewise)."""
+    _require_kernel_mode(top_k, multidim_average)
+    if multidim_average == "samplewise":
+        return _native.multiclass_stat_scores_samplewise(preds, target, num_classes, ignore_index)
+    if top_k > 1:
+        average = "macro"  # per-class counters: the reference keeps [C]-sized states for top-k, also for micro
     size = () if average == "micro" else (num_classes,)
     states = [torch.zeros(size if size else (1,), dtype=torch.int64, device=preds.device) for _ in range(4)]
     ws = stat_scores_workspace(num_classes, preds.device)
@@ -156,6 +167,30 @@ def _multiclass_stat_scores_compute(
     return None
 
 
+def _multiclass_stat_scores_states(
+    preds: Tensor, target: Tensor, num_classes: int, top_k: int, average: Optional[str], multidim_average: str,
+    ignore_index: Optional[int], validate_args: bool,
+) -> tuple[Tensor, Tensor, Tensor, Tensor]:
+    """tp, fp, tn, fn of one call in the layout the reference's functional path produces: 0-d (micro, top-1, global),
+    ``[C]`` (global) or ``[N, C]`` (samplewise)."""
+    _require_kernel_mode(top_k, multidim_average)
+    if multidim_average == "samplewise":
+        flag = new_flag(preds.device) if validate_args else None
+        out = _native.multiclass_stat_scores_samplewise(preds, target, num_classes, ignore_index, flag)
+        if flag is not None:
+            raise_if_flagged(flag, num_classes, ignore_index)
+        return out
+    micro = average == "micro" and top_k == 1
+    states = [torch.zeros(1 if micro else num_classes, dtype=torch.int64, device=preds.device) for _ in range(4)]
+    ws = stat_scores_workspace(num_classes, preds.device)
+    _multiclass_stat_scores_update_(
+        *states, ws, preds, target, num_classes, top_k, average, multidim_average, ignore_index, validate_args
+    )
+    if micro:
+        states = [s.reshape(()) for s in states]
+    return states[0], states[1], states[2], states[3]
+
+
 def multiclass_stat_scores(
     preds: Tensor,
     target: Tensor,
@@ -170,15 +205,7 @@ def multiclass_stat_scores(
     if validate_args:
         _multiclass_stat_scores_arg_validation(num_classes, top_k, average, multidim_average, ignore_index)
         _multiclass_stat_scores_tensor_validation(preds, target, num_classes, multidim_average, ignore_index)
-    _require_kernel_mode(top_k, multidim_average)
-    micro = average == "micro"
-    states = [torch.zeros(1 if micro else num_classes, dtype=torch.int64, device=preds.device) for _ in range(4)]
-    ws = stat_scores_workspace(num_classes, preds.device)
-    _multiclass_stat_scores_update_(
-        *states, ws, preds, target, num_classes, top_k, average, multidim_average, ignore_index, validate_args
-    )
-    if micro:
-        states = [s.reshape(()) for s in states]
+    states = _multiclass_stat_scores_states(preds, target, num_classes, top_k, average, multidim_average, ignore_index, validate_args)
     return _multiclass_stat_scores_compute(*states, average, multidim_average)
 
 

@@ -150,3 +150,25 @@ def reduce_per_class(res: np.ndarray, average: Optional[str], weights: np.ndarra
         return res[keep].mean()
     w = weights[keep] / weights[keep].sum()
     return (res[keep] * w).sum()
+
+
+def binned_confmat(preds: np.ndarray, target: np.ndarray, thresholds: np.ndarray, num_classes: int = 1) -> np.ndarray:
+    """Multi-threshold confusion matrix (precision_recall_curve.py:211-226 binary, :488-507 multiclass):
+    confmat[i, (c,) y, pred >= thr_i].  preds already normalised; binary targets outside {0,1} are not expected."""
+    thr = np.asarray(thresholds, dtype=np.float32)
+    if num_classes == 1:
+        ge = preds.astype(np.float32)[:, None] >= thr[None, :]  # [N, T]
+        out = np.zeros((thr.size, 2, 2), np.int64)
+        for y in (0, 1):
+            sel = target == y
+            out[:, y, 1] = ge[sel].sum(0)
+            out[:, y, 0] = sel.sum() - out[:, y, 1]
+        return out
+    out = np.zeros((thr.size, num_classes, 2, 2), np.int64)
+    for c in range(num_classes):
+        ge = preds[:, c].astype(np.float32)[:, None] >= thr[None, :]
+        for y in (0, 1):
+            sel = (target == c) == bool(y)
+            out[:, c, y, 1] = ge[sel].sum(0)
+            out[:, c, y, 0] = sel.sum() - out[:, c, y, 1]
+    return out

@@ -51,3 +51,10 @@ def golden_reg():
     import numpy as np
 
     return np.load(os.path.join(GOLDEN_DIR, "regression.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_binned():
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN_DIR, "binned.npz"), allow_pickle=False)

@@ -233,6 +233,41 @@ def classification_golden() -> dict:
                     out[f"{tag}/accuracy"] = multilabel_accuracy(p, t, L, average=avg, multidim_average=mda, ignore_index=ign).numpy()
                     out[f"{tag}/f1"] = multilabel_f1_score(p, t, L, average=avg, multidim_average=mda, ignore_index=ign).numpy()
             out[f"ml/{kind}/ign{'none' if ign is None else ign}/confmat"] = multilabel_confusion_matrix(p, t, L, ignore_index=ign).numpy()
+    # ---- G. multiclass top-k and samplewise stat scores --------------------------------------------------------------
+    g = torch.Generator().manual_seed(23)
+    tk_logits = torch.randn(300, 7, generator=g)
+    tk_target = torch.randint(0, 7, (300,), generator=g)
+    tk_ign = tk_target.clone()
+    tk_ign[::6] = -1
+    out["topk/logits"], out["topk/target"], out["topk/target_ign"] = tk_logits.numpy(), tk_target.numpy(), tk_ign.numpy()
+    for k in (2, 3):
+        for avg in ("micro", "macro", "none"):
+            for ign, t in ((None, tk_target), (-1, tk_ign)):
+                tag = f"topk/k{k}/{avg}/ign{'none' if ign is None else ign}"
+                out[f"{tag}/stat_scores"] = multiclass_stat_scores(tk_logits, t, 7, average=avg, top_k=k, ignore_index=ign).numpy()
+                out[f"{tag}/accuracy"] = multiclass_accuracy(tk_logits, t, 7, average=avg, top_k=k, ignore_index=ign).numpy()
+                out[f"{tag}/f1"] = multiclass_f1_score(tk_logits, t, 7, average=avg, top_k=k, ignore_index=ign).numpy()
+    mk = MulticlassAccuracy(num_classes=7, top_k=2, average="micro")
+    for a, b in zip(tk_logits.chunk(3), tk_target.chunk(3)):
+        mk.update(a, b)
+    out["topk/class_acc_k2_micro"] = mk.compute().numpy()
+    sw_logits = torch.randn(20, 5, 11, generator=g)
+    sw_labels = torch.randint(0, 5, (20, 11), generator=g)
+    sw_target = torch.randint(0, 5, (20, 11), generator=g)
+    out["sw/logits"], out["sw/labels"], out["sw/target"] = sw_logits.numpy(), sw_labels.numpy(), sw_target.numpy()
+    for kind, p in (("logits", sw_logits), ("labels", sw_labels)):
+        for avg in ("micro", "macro", "none"):
+            for ign in (None, -1, 1):
+                t = sw_target.clone()
+                if ign == -1:
+                    t[:, ::4] = -1
+                tag = f"sw/{kind}/{avg}/ign{'none' if ign is None else ign}"
+                out[f"{tag}/stat_scores"] = multiclass_stat_scores(p, t, 5, average=avg, multidim_average="samplewise", ignore_index=ign).numpy()
+                out[f"{tag}/accuracy"] = multiclass_accuracy(p, t, 5, average=avg, multidim_average="samplewise", ignore_index=ign).numpy()
+    msw = MulticlassStatScores(num_classes=5, average="none", multidim_average="samplewise")
+    msw.update(sw_logits[:8], sw_target[:8])
+    msw.update(sw_logits[8:], sw_target[8:])
+    out["sw/class_none"] = msw.compute().numpy()
     out["meta/torchmetrics_version"] = np.array(torchmetrics.__version__)
     out["meta/torch_version"] = np.array(torch.__version__)
     return out
@@ -418,6 +453,79 @@ def map_golden() -> dict:
     return out
 
 
+def binned_golden() -> dict:
+    import warnings
+
+    from torchmetrics.classification import BinaryAUROC, MulticlassAveragePrecision, MulticlassPrecisionRecallCurve
+    from torchmetrics.functional.classification import (
+        binary_auroc,
+        binary_average_precision,
+        binary_precision_recall_curve,
+        binary_roc,
+        multiclass_auroc,
+        multiclass_average_precision,
+        multiclass_precision_recall_curve,
+        multiclass_roc,
+    )
+    from torchmetrics.functional.classification.precision_recall_curve import (
+        _binary_precision_recall_curve_format,
+        _binary_precision_recall_curve_update,
+        _multiclass_precision_recall_curve_format,
+        _multiclass_precision_recall_curve_update,
+    )
+
+    warnings.simplefilter("ignore")
+    out: dict = {}
+    g = torch.Generator().manual_seed(55)
+    bp = torch.rand(5000, generator=g)
+    bp[::13] = (bp[::13] * 10).round() / 10  # scores sitting exactly on thresholds
+    bl = torch.randn(3000, generator=g) * 2
+    bt = torch.randint(0, 2, (5000,), generator=g)
+    out["b/preds"], out["b/logits"], out["b/target"] = bp.numpy(), bl.numpy(), bt.numpy()
+    thr_sets = {"int11": 11, "int200": 200, "list": [0.9, 0.1, 0.5, 0.3], "tensor": torch.tensor([0.0, 0.2, 0.7, 1.0])}
+    for name, thr in thr_sets.items():
+        for kind, (p, t) in (("probs", (bp, bt)), ("logits", (bl, bt[:3000]))):
+            tag = f"b/{name}/{kind}"
+            pf, tf, th = _binary_precision_recall_curve_format(p, t, thr)
+            out[f"{tag}/confmat"] = _binary_precision_recall_curve_update(pf, tf, th).numpy()
+            out[f"{tag}/auroc"] = binary_auroc(p, t, thresholds=thr).numpy()
+            out[f"{tag}/auroc_maxfpr"] = binary_auroc(p, t, thresholds=thr, max_fpr=0.6).numpy()
+            out[f"{tag}/ap"] = binary_average_precision(p, t, thresholds=thr).numpy()
+            f, tp_, h = binary_roc(p, t, thresholds=thr)
+            out[f"{tag}/roc_fpr"], out[f"{tag}/roc_tpr"], out[f"{tag}/roc_thr"] = f.numpy(), tp_.numpy(), h.numpy()
+            pr, rc, h = binary_precision_recall_curve(p, t, thresholds=thr)
+            out[f"{tag}/prc_p"], out[f"{tag}/prc_r"], out[f"{tag}/prc_thr"] = pr.numpy(), rc.numpy(), h.numpy()
+    C = 6
+    ml = torch.randn(1200, C, generator=g)
+    mt = torch.randint(0, C, (1200,), generator=g)
+    mt[mt == 5] = 2
+    out["m/logits"], out["m/target"] = ml.numpy(), mt.numpy()
+    for name, thr in (("int7", 7), ("list", [0.05, 0.2, 0.6])):
+        pf, tf, th = _multiclass_precision_recall_curve_format(ml, mt, C, thr)
+        out[f"m/{name}/confmat"] = _multiclass_precision_recall_curve_update(pf, tf, C, th).numpy()
+        for avg in ("macro", "weighted", "none"):
+            out[f"m/{name}/auroc_{avg}"] = multiclass_auroc(ml, mt, C, average=avg, thresholds=thr).numpy()
+            out[f"m/{name}/ap_{avg}"] = multiclass_average_precision(ml, mt, C, average=avg, thresholds=thr).numpy()
+        f, tp_, h = multiclass_roc(ml, mt, C, thresholds=thr)
+        out[f"m/{name}/roc_fpr"], out[f"m/{name}/roc_tpr"], out[f"m/{name}/roc_thr"] = f.numpy(), tp_.numpy(), h.numpy()
+        pr, rc, h = multiclass_precision_recall_curve(ml, mt, C, thresholds=thr)
+        out[f"m/{name}/prc_p"], out[f"m/{name}/prc_r"] = pr.numpy(), rc.numpy()
+        for avg in ("micro", "macro"):
+            pr, rc, h = multiclass_precision_recall_curve(ml, mt, C, thresholds=thr, average=avg)
+            out[f"m/{name}/prc_{avg}_p"], out[f"m/{name}/prc_{avg}_r"], out[f"m/{name}/prc_{avg}_thr"] = pr.numpy(), rc.numpy(), h.numpy()
+    # modular, several updates
+    m = BinaryAUROC(thresholds=50)
+    for a, b in zip(bp.chunk(5), bt.chunk(5)):
+        m.update(a, b)
+    out["class/binary_auroc_50"] = m.compute().numpy()
+    out["class/binary_auroc_50_confmat"] = m.confmat.numpy()
+    m2 = MulticlassAveragePrecision(num_classes=C, thresholds=20)
+    for a, b in zip(ml.chunk(3), mt.chunk(3)):
+        m2.update(a, b)
+    out["class/mc_ap_20"] = m2.compute().numpy()
+    return out
+
+
 def regression_golden() -> dict:
     import torchmetrics.functional as TF
     import torchmetrics.regression as TR
@@ -467,6 +575,11 @@ if __name__ == "__main__":
     if "classification" in which:
         data = classification_golden()
         path = os.path.join(HERE, "classification.npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
+    if "binned" in which:
+        data = binned_golden()
+        path = os.path.join(HERE, "binned.npz")
         np.savez_compressed(path, **data)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
     if "regression" in which:
