@@ -152,9 +152,16 @@ def cfg5(dev, rank, world):
     def compute():
         for m in mc.values(copy_state=False):
             m._computed = None
+            if hasattr(m, "_group_cache"):
+                m._group_cache.clear()
         return mc.compute()
 
     comp_min, comp_med = ev_time(compute, reps=5, warm=2)
+    comp_gather_min = None
+    if world > 1:  # A/B: the reference's gather-everything sync followed by an all-class evaluation on every rank
+        os.environ["MB200_SHARDED_CURVES"] = "0"
+        comp_gather_min, _ = ev_time(compute, reps=5, warm=2)
+        os.environ["MB200_SHARDED_CURVES"] = "1"
     # sync only
     def sync_only():
         for m in mc.values(copy_state=False):
@@ -165,11 +172,13 @@ def cfg5(dev, rank, world):
     if world > 1:
         sync_min, _ = ev_time(sync_only, reps=5, warm=2)
     res = compute()
-    t = torch.tensor([upd_min, comp_min, sync_min or 0.0], device=dev, dtype=torch.float64)
+    t = torch.tensor([upd_min, comp_min, sync_min or 0.0, comp_gather_min or 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     return {"world": world, "update_ms_4_batches": float(t[0]), "update_units_per_s_per_gpu": 4 * 4096 * 1000 / (float(t[0]) * 1e-3),
             "compute_ms": float(t[1]), "sync_only_ms": float(t[2]) if world > 1 else None,
+            "compute_ms_gather_everything": float(t[3]) if world > 1 else None,
+            "compute_path": "class-sharded all_to_all (metrics_b200/parallel_curves.py)" if world > 1 else "local",
             "f1": float(res["MulticlassF1Score"]), "auroc": float(res["MulticlassAUROC"]),
             "sync_bytes_per_rank": 16384 * 1000 * 4 + 16384 * 8 + 4 * 1000 * 8}
 

@@ -161,7 +161,18 @@ MB200_API int mb200_curve_softmax_if_logits(const void* preds, int dtype, int64_
  * TP/FP are counted in integers (n < 2^30 samples per curve); AUROC = exact integer sum / (2 P N) evaluated in fp64;
  * AP accumulated in fp64 in a fixed order (bitwise reproducible run to run).
  * ------------------------------------------------------------------------------------------------ */
+#define MB200_CURVE_MULTILABEL (-2) /* pass as `pos_label` with num_classes = num_labels: target is [n, num_labels],
+                                       positives of curve l are target[:, l] == 1 (multilabel one-curve-per-label) */
 MB200_API int64_t mb200_curve_workspace_bytes(int64_t num_classes, int64_t n);
+/* the packing step alone: class-major keys [num_classes][n] of [n, num_classes] scores, and sort+scan on packed keys
+ * (positives of curve s: target == first_class + s; `keys` is sorted in place).  Used by the class-sharded multi-GPU
+ * evaluation, which exchanges key rows between ranks (all-to-all) between the two calls. */
+MB200_API int mb200_curve_pack_keys(const void* preds, int preds_dtype, int64_t n, int64_t num_classes,
+                                    uint32_t* keys_out, void* stream);
+MB200_API int mb200_curve_evaluate_keys(uint32_t* keys, const void* target, int target_dtype, int64_t n,
+                                        int64_t segments, int64_t first_class, void* workspace, int64_t workspace_bytes,
+                                        float* out_auroc, float* out_ap, int64_t* out_counts, uint32_t* err_flag,
+                                        void* stream);
 MB200_API int mb200_curve_evaluate(const void* preds, int preds_dtype, const void* target, int target_dtype,
                                    int64_t n, int64_t num_classes, int64_t pos_label, void* workspace,
                                    int64_t workspace_bytes, float* out_auroc, float* out_ap, int64_t* out_counts,

@@ -461,3 +461,41 @@ def multiclass_stat_scores_samplewise(
     tp, fp, fn = counts[0], counts[1], counts[2]
     tn = n_valid[:, None] - tp - fp - fn
     return tp, fp, tn, fn
+
+
+# ----------------------------------------------------------------------------------------------------------
+# class-sharded multi-GPU curve evaluation: packing and sort+scan as separate steps
+# ----------------------------------------------------------------------------------------------------------
+def curve_pack_keys(preds: Tensor, rows_out: Optional[int] = None) -> Tensor:
+    """Class-major sort keys of ``[n, C]`` scores: int32 ``[rows_out >= C, n]`` (rows beyond ``C`` are zero padding)."""
+    dev = require_cuda(preds)
+    preds = preds.contiguous()
+    n, c = preds.shape
+    rows = c if rows_out is None else rows_out
+    keys = torch.zeros((rows, n), dtype=torch.int32, device=dev) if rows > c else torch.empty((rows, n), dtype=torch.int32, device=dev)
+    with on_device(dev):
+        rc = lib().mb200_curve_pack_keys(ptr(preds), tag(preds), i64(n), i64(c), ptr(keys), stream_handle(dev))
+    check(rc, "curve_pack_keys")
+    return keys
+
+
+def curve_evaluate_keys(keys: Tensor, target: Tensor, first_class: int):
+    """Sort + scan of packed keys ``[S, n]`` (sorted in place); positives of row ``s`` are ``target == first_class + s``."""
+    dev = require_cuda(keys, target)
+    assert keys.is_contiguous() and keys.dtype == torch.int32
+    target = target.contiguous()
+    s, n = keys.shape
+    lib_ = lib()
+    lib_.mb200_curve_workspace_bytes.restype = ctypes.c_int64
+    nbytes = int(lib_.mb200_curve_workspace_bytes(i64(s), i64(n)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    auroc = torch.empty(s, dtype=torch.float32, device=dev)
+    ap = torch.empty(s, dtype=torch.float32, device=dev)
+    counts = torch.empty((s, 3), dtype=torch.int64, device=dev)
+    with on_device(dev):
+        rc = lib_.mb200_curve_evaluate_keys(
+            ptr(keys), ptr(target), tag(target), i64(n), i64(s), i64(first_class), ptr(ws), i64(nbytes), ptr(auroc), ptr(ap),
+            ptr(counts), ptr(None), stream_handle(dev),
+        )
+    check(rc, "curve_evaluate_keys")
+    return auroc, ap, counts

@@ -54,6 +54,19 @@ class MulticlassAUROC(MulticlassPrecisionRecallCurve):
     plot_upper_bound: float = 1.0
     plot_legend_name: str = "Class"
 
+    def _compute_distributed(self):
+        """Class-sharded multi-GPU evaluation (metrics_b200/parallel_curves.py) instead of all-gathering the score lists;
+        returns ``NotImplemented`` when the generic sync has to be used."""
+        from metrics_b200.parallel_curves import sharded_applicable
+
+        if not sharded_applicable(self):
+            return NotImplemented
+        self._sharded_now = True
+        try:
+            return self._compute_local()
+        finally:
+            self._sharded_now = False
+
     def __init__(
         self,
         num_classes: int,
@@ -71,11 +84,14 @@ class MulticlassAUROC(MulticlassPrecisionRecallCurve):
         self.average = average  # the parent stored its own (curve) `average=None`; this one drives the class reduction
         self.validate_args = validate_args
 
-    def compute(self) -> Tensor:
+    def _compute_local(self) -> Tensor:
         if self.thresholds is not None:
             return _multiclass_auroc_compute(self._state(), self.num_classes, self.average, self.thresholds)
         return _multiclass_auroc_compute(None, self.num_classes, self.average, self.thresholds,
                                          scalars=self._curve_scalars(self.num_classes))
+
+    def compute(self) -> Tensor:
+        return self._compute_local()
 
 
 from metrics_b200.classification.base import _ClassificationTaskWrapper  # noqa: E402

@@ -3,6 +3,7 @@ from __future__ import annotations
 
 from typing import Any, List, Optional, Union
 
+import torch
 from torch import Tensor
 from typing_extensions import Literal
 
@@ -37,6 +38,19 @@ class MulticlassAveragePrecision(MulticlassPrecisionRecallCurve):
     plot_upper_bound: float = 1.0
     plot_legend_name: str = "Class"
 
+    def _compute_distributed(self):
+        """Class-sharded multi-GPU evaluation (metrics_b200/parallel_curves.py) instead of all-gathering the score lists;
+        returns ``NotImplemented`` when the generic sync has to be used."""
+        from metrics_b200.parallel_curves import sharded_applicable
+
+        if not sharded_applicable(self):
+            return NotImplemented
+        self._sharded_now = True
+        try:
+            return self._compute_local()
+        finally:
+            self._sharded_now = False
+
     def __init__(
         self,
         num_classes: int,
@@ -54,9 +68,19 @@ class MulticlassAveragePrecision(MulticlassPrecisionRecallCurve):
         self.average = average
         self.validate_args = validate_args
 
+    def _compute_local(self) -> Tensor:
+        scalars = self._curve_scalars(self.num_classes)
+        if getattr(self, "_sharded_now", False):
+            # stand-in `target` for the reference's `(target == 0).all()` guard: the class-0 counts say it
+            counts = scalars[2]
+            all_zero = bool(counts[0, 1] == 0)  # no sample is a negative for class 0
+            state = (None, torch.zeros(1, dtype=torch.int64) if all_zero else torch.ones(1, dtype=torch.int64))
+        else:
+            state = self._state()
+        return _multiclass_average_precision_compute(state, self.num_classes, self.average, self.thresholds, scalars=scalars)
+
     def compute(self) -> Tensor:
-        return _multiclass_average_precision_compute(self._state(), self.num_classes, self.average, self.thresholds,
-                                                     scalars=self._curve_scalars(self.num_classes))
+        return self._compute_local()
 
 
 from metrics_b200.classification.base import _ClassificationTaskWrapper  # noqa: E402

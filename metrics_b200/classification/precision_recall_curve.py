@@ -66,6 +66,11 @@ class BinaryPrecisionRecallCurve(Metric):
         self._group_cache.clear()
         Metric.reset(self)
 
+    def _cache_put(self, key, value) -> None:
+        if len(self._group_cache) >= 4:  # synced states get a fresh identity per sync(): do not accumulate stale entries
+            self._group_cache.clear()
+        self._group_cache[key] = value
+
     def _curve_scalars(self, num_classes: int = 1, pos_label: int = 1):
         """``(auroc, ap, counts)`` of the current state from ONE `mb200_curve_evaluate` call, memoised until the next
         update / reset.  Keyed by the identity of the state object, so synced states never hit a local entry."""
@@ -73,15 +78,23 @@ class BinaryPrecisionRecallCurve(Metric):
 
         if self.thresholds is not None:
             return None  # binned mode: the compute functions work on the confmat state
-        key = (id(self.preds), id(self.target), num_classes, pos_label)
+        key = (id(self.preds), id(self.target), num_classes, pos_label, bool(getattr(self, "_sharded_now", False)))
         hit = self._group_cache.get(key)
+        if getattr(self, "_sharded_now", False):
+            from metrics_b200.parallel_curves import ovr_curve_scalars_sharded
+
+            has = len(self.preds) > 0 if isinstance(self.preds, list) else self.preds.numel() > 0
+            preds, target = self._state() if has else (None, None)
+            hit = ovr_curve_scalars_sharded(preds, target, num_classes, self.process_group, self.device, cached=hit)
+            self._cache_put(key, hit)
+            return hit
         if hit is None:
             preds, target = self._state()
             if preds.numel() == 0:
                 raise IndexError("metrics_b200: cannot evaluate a curve metric without samples")
             auroc, ap, counts, _ = _native.curve_evaluate(preds, target, num_classes, pos_label, want_curve=False)
             hit = (auroc, ap, counts)
-            self._group_cache[key] = hit
+            self._cache_put(key, hit)
         return hit
 
     def update(self, preds: Tensor, target: Tensor) -> None:
@@ -143,6 +156,7 @@ class MulticlassPrecisionRecallCurve(Metric):
 
     reset = BinaryPrecisionRecallCurve.reset
     _curve_scalars = BinaryPrecisionRecallCurve._curve_scalars
+    _cache_put = BinaryPrecisionRecallCurve._cache_put
 
     def update(self, preds: Tensor, target: Tensor) -> None:
         self._group_cache.clear()

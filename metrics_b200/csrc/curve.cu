@@ -166,6 +166,62 @@ __global__ void __launch_bounds__(256) pack_ovr_kernel(const T* __restrict__ pre
     }
 }
 
+// multilabel: preds [N, L] and target [N, L] row-major -> keys / labels [L][N]; label = (target == 1)
+template <typename T>
+__global__ void __launch_bounds__(256) pack_multilabel_kernel(const T* __restrict__ preds, const void* __restrict__ target,
+                                                              int tdtype, int n, int L, unsigned* __restrict__ keys,
+                                                              unsigned char* __restrict__ labels) {
+    __shared__ unsigned tile[32][33];
+    __shared__ unsigned char ltile[32][33];
+    const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const int nn = n0 + j, cc = c0 + tx;
+        if (nn < n && cc < L) {
+            tile[j][tx] = desc_key(to_float<T>(preds[(size_t)nn * L + cc]));
+            ltile[j][tx] = (unsigned char)(load_label(target, tdtype, (long long)nn * L + cc) == 1);
+        }
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int cc = c0 + j, nn = n0 + tx;
+        if (nn < n && cc < L) {
+            keys[(size_t)cc * n + nn] = tile[tx][j];
+            labels[(size_t)cc * n + nn] = ltile[tx][j];
+        }
+    }
+}
+
+// keys only, class-major, rows >= C (padding up to rows_out) left untouched: used by the class-sharded multi-GPU path
+template <typename T>
+__global__ void __launch_bounds__(256) pack_keys_kernel(const T* __restrict__ preds, int n, int C,
+                                                        unsigned* __restrict__ keys) {
+    __shared__ unsigned tile[32][33];
+    const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const int nn = n0 + j, cc = c0 + tx;
+        if (nn < n && cc < C) tile[j][tx] = desc_key(to_float<T>(preds[(size_t)nn * C + cc]));
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int cc = c0 + j, nn = n0 + tx;
+        if (nn < n && cc < C) keys[(size_t)cc * n + nn] = tile[tx][j];
+    }
+}
+
+// labels[s][i] = (target[i] == first_class + s)
+__global__ void __launch_bounds__(256) labels_from_target_kernel(const void* __restrict__ target, int tdtype, int n,
+                                                                 int segments, long long first_class,
+                                                                 unsigned char* __restrict__ labels) {
+    const long long total = (long long)n * segments;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(i / n);
+        const int k = (int)(i - (long long)s * n);
+        labels[i] = (unsigned char)(load_label(target, tdtype, k) == first_class + s);
+    }
+}
+
 // =====================================================================================================
 // tie-collapsing TP/FP scan over sorted (key, label)     grid = (tiles, segments), tile = 256 threads x 8 items
 // =====================================================================================================
@@ -597,6 +653,40 @@ CurveWs carve(void* workspace, int64_t segments, int64_t n) {
 }
 }  // namespace
 
+namespace {
+// sort (keys_a/lab_a are clobbered; the sorted result lands back in them) + tie-collapsing scan + finalize
+int sort_and_scan(unsigned* keys_a, unsigned char* lab_a, const CurveWs& w, int ni, int64_t segments, int64_t n,
+                  float* out_auroc, float* out_ap, int64_t* out_counts, float* fps_out, float* tps_out, float* thr_out,
+                  uint32_t* err_flag, cudaStream_t st) {
+    const int scan_tiles = (ni + kScanTile - 1) / kScanTile;
+    // ---- 4 one-sweep radix passes (ping-pong; an even number of passes leaves the result in the *_a buffers) ----
+    {
+        const int where = radix_sort_passes<unsigned, unsigned char>(keys_a, lab_a, w.keys_b, w.lab_b, ni,
+                                                                     (int)segments, 4, w.sort_scratch, err_flag, st,
+                                                                     &count_launch);
+        if (where < 0) return check_cuda(cudaGetLastError(), "radix sort");
+    }
+    unsigned* kin = keys_a;
+    unsigned char* lin = lab_a;
+
+    // ---- scan ----
+    const dim3 sgrid((unsigned)scan_tiles, (unsigned)segments);
+    zero_u64_kernel<<<(int)((segments + 255) / 256), 256, 0, st>>>(w.auroc_acc, (int)segments);
+    scan_reduce_kernel<<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, scan_tiles, w.info);
+    scan_carry_kernel<<<(unsigned)segments, 256, 0, st>>>(w.info, scan_tiles, ni, w.seg_totals);
+    if (fps_out)
+        scan_apply_kernel<true><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, scan_tiles, w.info, w.auroc_acc,
+                                                                w.ap_partial, fps_out, tps_out, thr_out, n);
+    else
+        scan_apply_kernel<false><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, scan_tiles, w.info, w.auroc_acc,
+                                                                 w.ap_partial, nullptr, nullptr, nullptr, n);
+    scan_finalize_kernel<<<(int)((segments + 7) / 8), 256, 0, st>>>(w.auroc_acc, w.ap_partial, w.seg_totals, scan_tiles,
+                                                                    ni, (int)segments, out_auroc, out_ap, reinterpret_cast<long long*>(out_counts));
+    for (int i = 0; i < 5; ++i) count_launch();
+    return check_cuda(cudaGetLastError(), "curve evaluate launch");
+}
+}  // namespace
+
 // Exact-mode curve evaluation for `segments` one-vs-rest curves over `n` samples each.
 //   preds  : binary (num_classes == 1): [n] scores.  multiclass: [n, num_classes] row-major scores.
 //   target : [n] integer labels; positive for segment c is (target == c) (binary: target == pos_label).
@@ -620,8 +710,6 @@ extern "C" int mb200_curve_evaluate(const void* preds, int preds_dtype, const vo
     CurveWs w = carve(workspace, segments, n);
     const int ni = (int)n;
     const int sort_tiles = (ni + kSortTile - 1) / kSortTile;
-    const int scan_tiles = (ni + kScanTile - 1) / kScanTile;
-
     // ---- pack ----
     if (segments == 1) {
         const int grid = blocks_for(n, 256 * 4, sm_count() * 8);
@@ -636,8 +724,12 @@ extern "C" int mb200_curve_evaluate(const void* preds, int preds_dtype, const vo
 #undef MB200_PACK
     } else {
         const dim3 grid((unsigned)((ni + 31) / 32), (unsigned)((segments + 31) / 32));
-#define MB200_PACK(T) \
-    pack_ovr_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, ni, (int)segments, w.keys_a, w.lab_a);
+#define MB200_PACK(T)                                                                                                 \
+    if (pos_label == MB200_CURVE_MULTILABEL)                                                                          \
+        pack_multilabel_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, ni,  \
+                                                        (int)segments, w.keys_a, w.lab_a);                            \
+    else                                                                                                              \
+        pack_ovr_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, ni, (int)segments, w.keys_a, w.lab_a);
         switch (preds_dtype) {
             case MB200_F32: MB200_PACK(float) break;
             case MB200_F16: MB200_PACK(__half) break;
@@ -648,29 +740,44 @@ extern "C" int mb200_curve_evaluate(const void* preds, int preds_dtype, const vo
     }
     count_launch();
 
-    // ---- 4 one-sweep radix passes (ping-pong; an even number of passes leaves the result in the *_a buffers) ----
-    {
-        const int where = radix_sort_passes<unsigned, unsigned char>(w.keys_a, w.lab_a, w.keys_b, w.lab_b, ni,
-                                                                     (int)segments, 4, w.sort_scratch, err_flag, st,
-                                                                     &count_launch);
-        if (where < 0) return check_cuda(cudaGetLastError(), "radix sort");
-    }
-    unsigned* kin = w.keys_a;
-    unsigned char* lin = w.lab_a;
+    return sort_and_scan(w.keys_a, w.lab_a, w, ni, segments, n, out_auroc, out_ap, out_counts, fps_out, tps_out, thr_out,
+                         err_flag, st);
+}
 
-    // ---- scan ----
-    const dim3 sgrid((unsigned)scan_tiles, (unsigned)segments);
-    zero_u64_kernel<<<(int)((segments + 255) / 256), 256, 0, st>>>(w.auroc_acc, (int)segments);
-    scan_reduce_kernel<<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, scan_tiles, w.info);
-    scan_carry_kernel<<<(unsigned)segments, 256, 0, st>>>(w.info, scan_tiles, ni, w.seg_totals);
-    if (fps_out)
-        scan_apply_kernel<true><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, scan_tiles, w.info, w.auroc_acc,
-                                                                w.ap_partial, fps_out, tps_out, thr_out, n);
-    else
-        scan_apply_kernel<false><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, scan_tiles, w.info, w.auroc_acc,
-                                                                 w.ap_partial, nullptr, nullptr, nullptr, n);
-    scan_finalize_kernel<<<(int)((segments + 7) / 8), 256, 0, st>>>(w.auroc_acc, w.ap_partial, w.seg_totals, scan_tiles,
-                                                                    ni, (int)segments, out_auroc, out_ap, reinterpret_cast<long long*>(out_counts));
-    for (int i = 0; i < 5; ++i) count_launch();
-    return check_cuda(cudaGetLastError(), "curve evaluate launch");
+// Class-major keys of [n, num_classes] scores: keys_out [num_classes][n] (the packing step of mb200_curve_evaluate on
+// its own; used by the class-sharded multi-GPU path, which exchanges key rows between ranks before sorting).
+extern "C" int mb200_curve_pack_keys(const void* preds, int preds_dtype, int64_t n, int64_t num_classes,
+                                     uint32_t* keys_out, void* stream) {
+    MB200_REQUIRE(n >= 0 && num_classes >= 1 && n < (1ll << 30), "bad sizes");
+    if (n == 0) return 0;
+    MB200_REQUIRE(preds && keys_out, "NULL pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const dim3 grid((unsigned)((n + 31) / 32), (unsigned)((num_classes + 31) / 32));
+    switch (preds_dtype) {
+        case MB200_F32: pack_keys_kernel<float><<<grid, 256, 0, st>>>((const float*)preds, (int)n, (int)num_classes, keys_out); break;
+        case MB200_F16: pack_keys_kernel<__half><<<grid, 256, 0, st>>>((const __half*)preds, (int)n, (int)num_classes, keys_out); break;
+        case MB200_BF16: pack_keys_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)preds, (int)n, (int)num_classes, keys_out); break;
+        default: set_error("scores must be f32/f16/bf16 (dtype tag %d)", preds_dtype); return MB200_ERR_UNSUPPORTED;
+    }
+    count_launch();
+    return check_cuda(cudaGetLastError(), "curve pack keys launch");
+}
+
+// Sort + scan for `segments` curves whose keys are already packed: keys [segments][n] (clobbered: sorted in place),
+// positives of curve s are the samples with target == first_class + s.  Outputs as in mb200_curve_evaluate.
+extern "C" int mb200_curve_evaluate_keys(uint32_t* keys, const void* target, int target_dtype, int64_t n,
+                                         int64_t segments, int64_t first_class, void* workspace, int64_t workspace_bytes,
+                                         float* out_auroc, float* out_ap, int64_t* out_counts, uint32_t* err_flag,
+                                         void* stream) {
+    MB200_REQUIRE(n >= 1 && n < (1ll << 30) && segments >= 1 && segments <= 65535, "bad sizes");
+    MB200_REQUIRE(keys && target && workspace && out_auroc && out_ap && out_counts, "NULL pointer");
+    MB200_REQUIRE(workspace_bytes >= mb200_curve_workspace_bytes(segments, n), "workspace too small");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CurveWs w = carve(workspace, segments, n);
+    const long long total = n * segments;
+    labels_from_target_kernel<<<blocks_for(total, 256 * 8, sm_count() * 8), 256, 0, st>>>(target, target_dtype, (int)n,
+                                                                                          (int)segments, first_class, w.lab_a);
+    count_launch();
+    return sort_and_scan(keys, w.lab_a, w, (int)n, segments, n, out_auroc, out_ap, out_counts, nullptr, nullptr, nullptr,
+                         err_flag, st);
 }

@@ -182,6 +182,16 @@ class Metric(Module, ABC):
                 )
             if self._computed is not None:
                 return self._computed
+            # metrics whose consumer shards naturally (one-vs-rest curves: by class) may replace "gather everything,
+            # then compute" by their own exchange; explicit sync()/unsync() keep the full-gather semantics
+            sharded = getattr(self, "_compute_distributed", None)
+            if sharded is not None and self._to_sync and not self._is_synced:
+                value = sharded()
+                if value is not NotImplemented:
+                    value = apply_to_collection(_squeeze_if_scalar(value), Tensor, lambda t: t.clone())
+                    if self.compute_with_cache:
+                        self._computed = value
+                    return value
             with self.sync_context(
                 dist_sync_fn=self.dist_sync_fn,
                 should_sync=self._to_sync,
