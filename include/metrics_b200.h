@@ -161,8 +161,6 @@ MB200_API int mb200_curve_softmax_if_logits(const void* preds, int dtype, int64_
  * TP/FP are counted in integers (n < 2^30 samples per curve); AUROC = exact integer sum / (2 P N) evaluated in fp64;
  * AP accumulated in fp64 in a fixed order (bitwise reproducible run to run).
  * ------------------------------------------------------------------------------------------------ */
-#define MB200_CURVE_MULTILABEL (-2) /* pass as `pos_label` with num_classes = num_labels: target is [n, num_labels],
-                                       positives of curve l are target[:, l] == 1 (multilabel one-curve-per-label) */
 MB200_API int64_t mb200_curve_workspace_bytes(int64_t num_classes, int64_t n);
 /* the packing step alone: class-major keys [num_classes][n] of [n, num_classes] scores, and sort+scan on packed keys
  * (positives of curve s: target == first_class + s; `keys` is sorted in place).  Used by the class-sharded multi-GPU
@@ -177,6 +175,17 @@ MB200_API int mb200_curve_evaluate(const void* preds, int preds_dtype, const voi
                                    int64_t n, int64_t num_classes, int64_t pos_label, void* workspace,
                                    int64_t workspace_bytes, float* out_auroc, float* out_ap, int64_t* out_counts,
                                    float* fps_out, float* tps_out, float* thr_out, uint32_t* err_flag, void* stream);
+/* Multilabel task: `num_labels` independent binary curves in one batched sort + scan.  preds / target are
+ * [n, num_labels] row-major, positives are target == 1.  With has_ignore, entries with target == ignore_index are
+ * removed from their own label's curve only (they are given the largest sort key and the scan stops before them).
+ * Replaces the per-label Python loop of functional/classification/precision_recall_curve.py:822-834
+ * (_multilabel_precision_recall_curve_compute), roc.py:_multilabel_roc_compute, auroc.py:308-333 and
+ * average_precision.py:_multilabel_average_precision_compute.  Outputs as in mb200_curve_evaluate. */
+MB200_API int mb200_curve_evaluate_multilabel(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                              int64_t n, int64_t num_labels, int has_ignore, int64_t ignore_index,
+                                              void* workspace, int64_t workspace_bytes, float* out_auroc, float* out_ap,
+                                              int64_t* out_counts, float* fps_out, float* tps_out, float* thr_out,
+                                              uint32_t* err_flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K8 — COCO-style bounding-box mAP / mAR evaluation on the device.
@@ -255,6 +264,13 @@ MB200_API int64_t mb200_binned_curve_scratch_words(int64_t num_classes, int64_t 
 MB200_API int mb200_binned_curve_update(const void* preds, int preds_dtype, const void* target, int target_dtype,
                                         int64_t n, int64_t num_classes, const float* thresholds_sorted,
                                         int64_t num_thresholds, int64_t* confmat, uint64_t* scratch, void* stream);
+/* Multilabel variant (replaces precision_recall_curve.py:777-799 _multilabel_precision_recall_curve_update): target is
+ * [n, num_labels] like preds; entries whose target is neither 0 nor 1 (ignore_index) are skipped.
+ * confmat: int64 [num_thresholds, num_labels, 2, 2]. */
+MB200_API int mb200_binned_curve_update_multilabel(const void* preds, int preds_dtype, const void* target,
+                                                   int target_dtype, int64_t n, int64_t num_labels,
+                                                   const float* thresholds_sorted, int64_t num_thresholds,
+                                                   int64_t* confmat, uint64_t* scratch, void* stream);
 
 #ifdef __cplusplus
 }

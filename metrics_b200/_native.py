@@ -390,9 +390,11 @@ def regression_sums(preds: Tensor, target: Tensor, op: int, num_outputs: int = 1
 # ----------------------------------------------------------------------------------------------------------
 # K4 wrapper (binned curve update)
 # ----------------------------------------------------------------------------------------------------------
-def binned_curve_update(preds: Tensor, target: Tensor, thresholds: Tensor, num_classes: int = 1) -> Tensor:
+def binned_curve_update(preds: Tensor, target: Tensor, thresholds: Tensor, num_classes: int = 1,
+                        multilabel: bool = False) -> Tensor:
     """Multi-threshold confusion matrix of one batch: int64 ``[T, 2, 2]`` (``num_classes == 1``) or ``[T, C, 2, 2]``.
-    ``thresholds`` may be in any order (rows of the result follow it); the kernel works on a sorted copy."""
+    ``thresholds`` may be in any order (rows of the result follow it); the kernel works on a sorted copy.
+    ``multilabel``: ``target`` is ``[N, C]`` like ``preds``; entries that are neither 0 nor 1 are skipped."""
     dev = require_cuda(preds, target, thresholds)
     preds = preds.contiguous()
     target = target.contiguous()
@@ -401,14 +403,15 @@ def binned_curve_update(preds: Tensor, target: Tensor, thresholds: Tensor, num_c
     if thr.numel() > 1 and not bool((thr[1:] >= thr[:-1]).all()):
         thr, order = torch.sort(thr)
     thr = thr.contiguous()
-    n = target.numel()
+    n = preds.shape[0] if multilabel else target.numel()
     t_count = thr.numel()
     confmat = torch.zeros((t_count, num_classes, 2, 2), dtype=torch.int64, device=dev)
     lib_ = lib()
     lib_.mb200_binned_curve_scratch_words.restype = ctypes.c_int64
     scratch = torch.zeros(int(lib_.mb200_binned_curve_scratch_words(i64(num_classes), i64(t_count))), dtype=torch.int64, device=dev)
     with on_device(dev):
-        rc = lib_.mb200_binned_curve_update(
+        fn = lib_.mb200_binned_curve_update_multilabel if multilabel else lib_.mb200_binned_curve_update
+        rc = fn(
             ptr(preds), tag(preds), ptr(target), tag(target), i64(n), i64(num_classes), ptr(thr), i64(t_count),
             ptr(confmat), ptr(scratch), stream_handle(dev),
         )
@@ -417,7 +420,7 @@ def binned_curve_update(preds: Tensor, target: Tensor, thresholds: Tensor, num_c
         inv = torch.empty_like(order)
         inv[order] = torch.arange(t_count, device=dev)
         confmat = confmat[inv]
-    return confmat[:, 0] if num_classes == 1 else confmat
+    return confmat[:, 0] if num_classes == 1 and not multilabel else confmat
 
 
 def multiclass_stat_scores_topk_update_(
@@ -499,3 +502,34 @@ def curve_evaluate_keys(keys: Tensor, target: Tensor, first_class: int):
         )
     check(rc, "curve_evaluate_keys")
     return auroc, ap, counts
+
+
+def curve_evaluate_multilabel(preds: Tensor, target: Tensor, num_labels: int, ignore_index: Optional[int] = None,
+                              want_curve: bool = False):
+    """``num_labels`` independent binary curves from ``[N, L]`` scores / targets in one batched sort + scan
+    (``mb200_curve_evaluate_multilabel``).  Same return layout as :func:`curve_evaluate`."""
+    dev = require_cuda(preds, target)
+    if preds.dtype == torch.float64:
+        raise NotImplementedError("metrics_b200: float64 scores are not supported by the exact curve kernels; cast to float32")
+    preds = preds.contiguous()
+    target = target.contiguous()
+    n = preds.shape[0]
+    lib_ = lib()
+    lib_.mb200_curve_workspace_bytes.restype = ctypes.c_int64
+    nbytes = int(lib_.mb200_curve_workspace_bytes(i64(num_labels), i64(n)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    auroc = torch.empty(num_labels, dtype=torch.float32, device=dev)
+    ap = torch.empty(num_labels, dtype=torch.float32, device=dev)
+    counts = torch.empty((num_labels, 3), dtype=torch.int64, device=dev)
+    curve = None
+    if want_curve:
+        curve = tuple(torch.empty((num_labels, n), dtype=torch.float32, device=dev) for _ in range(3))
+    with on_device(dev):
+        rc = lib_.mb200_curve_evaluate_multilabel(
+            ptr(preds), tag(preds), ptr(target), tag(target), i64(n), i64(num_labels),
+            ctypes.c_int(0 if ignore_index is None else 1), i64(0 if ignore_index is None else ignore_index), ptr(ws),
+            i64(nbytes), ptr(auroc), ptr(ap), ptr(counts), ptr(curve[0] if curve else None),
+            ptr(curve[1] if curve else None), ptr(curve[2] if curve else None), ptr(None), stream_handle(dev),
+        )
+    check(rc, "curve_evaluate_multilabel")
+    return auroc, ap, counts, curve

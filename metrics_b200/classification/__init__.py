@@ -29,3 +29,7 @@ from metrics_b200.classification.auroc import AUROC  # noqa: F401,E402
 from metrics_b200.classification.average_precision import AveragePrecision  # noqa: F401,E402
 from metrics_b200.classification.precision_recall_curve import PrecisionRecallCurve  # noqa: F401,E402
 from metrics_b200.classification.roc import ROC  # noqa: F401,E402
+from metrics_b200.classification.auroc import MultilabelAUROC  # noqa: F401,E402
+from metrics_b200.classification.average_precision import MultilabelAveragePrecision  # noqa: F401,E402
+from metrics_b200.classification.precision_recall_curve import MultilabelPrecisionRecallCurve  # noqa: F401,E402
+from metrics_b200.classification.roc import MultilabelROC  # noqa: F401,E402

@@ -6,12 +6,18 @@ from typing import Any, List, Optional, Union
 from torch import Tensor
 from typing_extensions import Literal
 
-from metrics_b200.classification.precision_recall_curve import BinaryPrecisionRecallCurve, MulticlassPrecisionRecallCurve
+from metrics_b200.classification.precision_recall_curve import (
+    BinaryPrecisionRecallCurve,
+    MulticlassPrecisionRecallCurve,
+    MultilabelPrecisionRecallCurve,
+)
 from metrics_b200.functional.classification.auroc import (
     _binary_auroc_arg_validation,
     _binary_auroc_compute,
     _multiclass_auroc_arg_validation,
     _multiclass_auroc_compute,
+    _multilabel_auroc_arg_validation,
+    _multilabel_auroc_compute,
 )
 
 
@@ -99,8 +105,35 @@ from metrics_b200.metric import Metric  # noqa: E402
 from metrics_b200.utilities.enums import ClassificationTask  # noqa: E402
 
 
-def _no_multilabel(name: str) -> None:
-    raise NotImplementedError(f"metrics_b200: multilabel {name} is not implemented yet (binary and multiclass are)")
+class MultilabelAUROC(MultilabelPrecisionRecallCurve):
+    """Reference :281-429."""
+
+    is_differentiable: bool = False
+    higher_is_better: Optional[bool] = True
+    full_state_update: bool = False
+    plot_lower_bound: float = 0.0
+    plot_upper_bound: float = 1.0
+    plot_legend_name: str = "Label"
+
+    def __init__(
+        self,
+        num_labels: int,
+        average: Optional[Literal["micro", "macro", "weighted", "none"]] = "macro",
+        thresholds: Optional[Union[int, List[float], Tensor]] = None,
+        ignore_index: Optional[int] = None,
+        validate_args: bool = True,
+        **kwargs: Any,
+    ) -> None:
+        super().__init__(num_labels=num_labels, thresholds=thresholds, ignore_index=ignore_index, validate_args=False, **kwargs)
+        if validate_args:
+            _multilabel_auroc_arg_validation(num_labels, average, thresholds, ignore_index)
+        self.average = average
+        self.validate_args = validate_args
+
+    def compute(self) -> Tensor:
+        scalars = None if self.average == "micro" else self._curve_scalars()
+        return _multilabel_auroc_compute(self._state(), self.num_labels, self.average, self.thresholds, self.ignore_index,
+                                         scalars=scalars)
 
 
 class AUROC(_ClassificationTaskWrapper):
@@ -126,4 +159,6 @@ class AUROC(_ClassificationTaskWrapper):
             if not isinstance(num_classes, int):
                 raise ValueError(f"`num_classes` is expected to be `int` but `{type(num_classes)} was passed.`")
             return MulticlassAUROC(num_classes, average, **kwargs)
-        _no_multilabel("AUROC")
+        if not isinstance(num_labels, int):
+            raise ValueError(f"`num_labels` is expected to be `int` but `{type(num_labels)} was passed.`")
+        return MultilabelAUROC(num_labels, average, **kwargs)

@@ -7,11 +7,17 @@ import torch
 from torch import Tensor
 from typing_extensions import Literal
 
-from metrics_b200.classification.precision_recall_curve import BinaryPrecisionRecallCurve, MulticlassPrecisionRecallCurve
+from metrics_b200.classification.precision_recall_curve import (
+    BinaryPrecisionRecallCurve,
+    MulticlassPrecisionRecallCurve,
+    MultilabelPrecisionRecallCurve,
+)
 from metrics_b200.functional.classification.average_precision import (
     _binary_average_precision_compute,
     _multiclass_average_precision_arg_validation,
     _multiclass_average_precision_compute,
+    _multilabel_average_precision_arg_validation,
+    _multilabel_average_precision_compute,
 )
 
 
@@ -83,6 +89,37 @@ class MulticlassAveragePrecision(MulticlassPrecisionRecallCurve):
         return self._compute_local()
 
 
+class MultilabelAveragePrecision(MultilabelPrecisionRecallCurve):
+    """Reference :293-441."""
+
+    is_differentiable: bool = False
+    higher_is_better: Optional[bool] = True
+    full_state_update: bool = False
+    plot_lower_bound: float = 0.0
+    plot_upper_bound: float = 1.0
+    plot_legend_name: str = "Label"
+
+    def __init__(
+        self,
+        num_labels: int,
+        average: Optional[Literal["micro", "macro", "weighted", "none"]] = "macro",
+        thresholds: Optional[Union[int, List[float], Tensor]] = None,
+        ignore_index: Optional[int] = None,
+        validate_args: bool = True,
+        **kwargs: Any,
+    ) -> None:
+        super().__init__(num_labels=num_labels, thresholds=thresholds, ignore_index=ignore_index, validate_args=False, **kwargs)
+        if validate_args:
+            _multilabel_average_precision_arg_validation(num_labels, average, thresholds, ignore_index)
+        self.average = average
+        self.validate_args = validate_args
+
+    def compute(self) -> Tensor:
+        scalars = None if self.average == "micro" else self._curve_scalars()
+        return _multilabel_average_precision_compute(self._state(), self.num_labels, self.average, self.thresholds,
+                                                     self.ignore_index, scalars=scalars)
+
+
 from metrics_b200.classification.base import _ClassificationTaskWrapper  # noqa: E402
 from metrics_b200.metric import Metric  # noqa: E402
 from metrics_b200.utilities.enums import ClassificationTask  # noqa: E402
@@ -110,4 +147,6 @@ class AveragePrecision(_ClassificationTaskWrapper):
             if not isinstance(num_classes, int):
                 raise ValueError(f"`num_classes` is expected to be `int` but `{type(num_classes)} was passed.`")
             return MulticlassAveragePrecision(num_classes, average, **kwargs)
-        raise NotImplementedError("metrics_b200: multilabel AveragePrecision is not implemented yet")
+        if not isinstance(num_labels, int):
+            raise ValueError(f"`num_labels` is expected to be `int` but `{type(num_labels)} was passed.`")
+        return MultilabelAveragePrecision(num_labels, average, **kwargs)

@@ -24,6 +24,11 @@ from metrics_b200.functional.classification.precision_recall_curve import (
     _multiclass_precision_recall_curve_format,
     _multiclass_precision_recall_curve_tensor_validation,
     _multiclass_precision_recall_curve_update,
+    _multilabel_precision_recall_curve_arg_validation,
+    _multilabel_precision_recall_curve_compute,
+    _multilabel_precision_recall_curve_format,
+    _multilabel_precision_recall_curve_tensor_validation,
+    _multilabel_precision_recall_curve_update,
 )
 from metrics_b200.metric import Metric
 from metrics_b200.utilities.data import dim_zero_cat
@@ -178,6 +183,80 @@ class MulticlassPrecisionRecallCurve(Metric):
         return _multiclass_precision_recall_curve_compute(self._state(), self.num_classes, self.thresholds, self.average)
 
 
+class MultilabelPrecisionRecallCurve(Metric):
+    """Reference :383-597.  States: ``preds`` / ``target`` lists of ``[N, L]`` batches (exact) or the ``[T, L, 2, 2]``
+    multi-threshold confusion matrix (binned)."""
+
+    is_differentiable: bool = False
+    higher_is_better: Optional[bool] = None
+    full_state_update: bool = False
+    preds: List[Tensor]
+    target: List[Tensor]
+
+    def __init__(
+        self,
+        num_labels: int,
+        thresholds: Optional[Union[int, List[float], Tensor]] = None,
+        ignore_index: Optional[int] = None,
+        validate_args: bool = True,
+        **kwargs: Any,
+    ) -> None:
+        super().__init__(**kwargs)
+        if validate_args:
+            _multilabel_precision_recall_curve_arg_validation(num_labels, thresholds, ignore_index)
+        self.num_labels = num_labels
+        self.ignore_index = ignore_index
+        self.validate_args = validate_args
+        thresholds = _adjust_threshold_arg(thresholds)
+        if thresholds is None:
+            self.thresholds = thresholds
+            self.add_state("preds", default=[], dist_reduce_fx="cat")
+            self.add_state("target", default=[], dist_reduce_fx="cat")
+        else:
+            self.register_buffer("thresholds", thresholds, persistent=False)
+            self.add_state("confmat", default=torch.zeros(len(thresholds), num_labels, 2, 2, dtype=torch.long), dist_reduce_fx="sum")
+        self._group_cache: dict = {}  # see BinaryPrecisionRecallCurve
+
+    reset = BinaryPrecisionRecallCurve.reset
+    _cache_put = BinaryPrecisionRecallCurve._cache_put
+    _state = BinaryPrecisionRecallCurve._state
+
+    def _curve_scalars(self):
+        """Per-label ``(auroc, ap, counts)`` from ONE `mb200_curve_evaluate_multilabel` call, shared by the members of a
+        compute group (see BinaryPrecisionRecallCurve._curve_scalars)."""
+        from metrics_b200 import _native
+
+        if self.thresholds is not None:
+            return None
+        key = (id(self.preds), id(self.target), "multilabel", self.num_labels, self.ignore_index)
+        hit = self._group_cache.get(key)
+        if hit is None:
+            preds, target = self._state()
+            if preds.numel() == 0:
+                raise IndexError("metrics_b200: cannot evaluate a curve metric without samples")
+            auroc, ap, counts, _ = _native.curve_evaluate_multilabel(preds, target, self.num_labels, self.ignore_index)
+            hit = (auroc, ap, counts)
+            self._cache_put(key, hit)
+        return hit
+
+    def update(self, preds: Tensor, target: Tensor) -> None:
+        self._group_cache.clear()
+        if self.validate_args:
+            _multilabel_precision_recall_curve_tensor_validation(preds, target, self.num_labels, self.ignore_index)
+        preds, target, _ = _multilabel_precision_recall_curve_format(
+            preds, target, self.num_labels, self.thresholds, self.ignore_index
+        )
+        state = _multilabel_precision_recall_curve_update(preds, target, self.num_labels, self.thresholds)
+        if isinstance(state, Tensor):
+            self.confmat += state
+        else:
+            self.preds.append(state[0])
+            self.target.append(state[1])
+
+    def compute(self):
+        return _multilabel_precision_recall_curve_compute(self._state(), self.num_labels, self.thresholds, self.ignore_index)
+
+
 from metrics_b200.classification.base import _ClassificationTaskWrapper  # noqa: E402
 from metrics_b200.utilities.enums import ClassificationTask  # noqa: E402
 
@@ -203,4 +282,6 @@ class PrecisionRecallCurve(_ClassificationTaskWrapper):
             if not isinstance(num_classes, int):
                 raise ValueError(f"`num_classes` is expected to be `int` but `{type(num_classes)} was passed.`")
             return MulticlassPrecisionRecallCurve(num_classes, **kwargs)
-        raise NotImplementedError("metrics_b200: multilabel PrecisionRecallCurve is not implemented yet")
+        if not isinstance(num_labels, int):
+            raise ValueError(f"`num_labels` is expected to be `int` but `{type(num_labels)} was passed.`")
+        return MultilabelPrecisionRecallCurve(num_labels, **kwargs)

@@ -3,8 +3,12 @@ from __future__ import annotations
 
 from torch import Tensor
 
-from metrics_b200.classification.precision_recall_curve import BinaryPrecisionRecallCurve, MulticlassPrecisionRecallCurve
-from metrics_b200.functional.classification.roc import _binary_roc_compute, _multiclass_roc_compute
+from metrics_b200.classification.precision_recall_curve import (
+    BinaryPrecisionRecallCurve,
+    MulticlassPrecisionRecallCurve,
+    MultilabelPrecisionRecallCurve,
+)
+from metrics_b200.functional.classification.roc import _binary_roc_compute, _multiclass_roc_compute, _multilabel_roc_compute
 
 
 class BinaryROC(BinaryPrecisionRecallCurve):
@@ -19,6 +23,13 @@ class MulticlassROC(MulticlassPrecisionRecallCurve):
 
     def compute(self):
         return _multiclass_roc_compute(self._state(), self.num_classes, self.thresholds, self.average)
+
+
+class MultilabelROC(MultilabelPrecisionRecallCurve):
+    """Reference :333-497."""
+
+    def compute(self):
+        return _multilabel_roc_compute(self._state(), self.num_labels, self.thresholds, self.ignore_index)
 
 
 from typing import Any, List, Optional, Union  # noqa: E402
@@ -51,4 +62,6 @@ class ROC(_ClassificationTaskWrapper):
             if not isinstance(num_classes, int):
                 raise ValueError(f"`num_classes` is expected to be `int` but `{type(num_classes)} was passed.`")
             return MulticlassROC(num_classes, **kwargs)
-        raise NotImplementedError("metrics_b200: multilabel ROC is not implemented yet")
+        if not isinstance(num_labels, int):
+            raise ValueError(f"`num_labels` is expected to be `int` but `{type(num_labels)} was passed.`")
+        return MultilabelROC(num_labels, **kwargs)

@@ -36,7 +36,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) binned_bucket_kernel(const T* __restrict__ preds, const void* __restrict__ target,
                                                             int tdtype, long long n, int C, const float* __restrict__ thr,
                                                             int nthr, unsigned long long* __restrict__ scratch,
-                                                            long long* __restrict__ confmat, int use_smem) {
+                                                            long long* __restrict__ confmat, int use_smem, int multilabel) {
     extern __shared__ unsigned sh_cnt[];  // C * 2 * (nthr + 1) when use_smem
     const int stride = nthr + 1;
     const int ncnt = C * 2 * stride;
@@ -48,9 +48,10 @@ __global__ void __launch_bounds__(256) binned_bucket_kernel(const T* __restrict_
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long s = i / C;
         const int c = (int)(i - s * C);
-        const long long t = load_label(target, tdtype, s);
-        const int y = (C == 1) ? (t == 1) : (t == c);
-        if (C == 1 && (unsigned long long)t > 1ull) continue;  // binary: only {0,1} targets take part
+        // multilabel: target is [n, C] like preds, every label is its own binary problem
+        const long long t = load_label(target, tdtype, multilabel ? i : s);
+        const int y = (C == 1 || multilabel) ? (t == 1) : (t == c);
+        if ((C == 1 || multilabel) && (unsigned long long)t > 1ull) continue;  // binary: only {0,1} targets take part
         const typename CmpType<T>::type p = binned_load<T>(preds, i);
         // k = number of thresholds <= p  (p >= thr[j]  <=>  j < k);  NaN compares false everywhere -> k = 0
         int lo = 0, hi = nthr;
@@ -109,7 +110,7 @@ extern "C" int64_t mb200_binned_curve_scratch_words(int64_t num_classes, int64_t
     return num_classes * 2 * (num_thresholds + 1) + 8;
 }
 
-extern "C" int mb200_binned_curve_update(const void* preds, int preds_dtype, const void* target, int target_dtype,
+static int binned_update_impl(int multilabel, const void* preds, int preds_dtype, const void* target, int target_dtype,
                                          int64_t n, int64_t num_classes, const float* thresholds_sorted,
                                          int64_t num_thresholds, int64_t* confmat, uint64_t* scratch, void* stream) {
     MB200_REQUIRE(n >= 0 && num_classes >= 1 && num_thresholds >= 1, "bad sizes");
@@ -129,7 +130,7 @@ extern "C" int mb200_binned_curve_update(const void* preds, int preds_dtype, con
 #define MB200_BINNED(T)                                                                                              \
     binned_bucket_kernel<T><<<(int)blocks, 256, use_smem ? smem_need : 0, st>>>(                                     \
         reinterpret_cast<const T*>(preds), target, target_dtype, n, (int)num_classes, thresholds_sorted,            \
-        (int)num_thresholds, sc, cm, use_smem);
+        (int)num_thresholds, sc, cm, use_smem, multilabel);
     switch (preds_dtype) {
         case MB200_F32: MB200_BINNED(float) break;
         case MB200_F16: MB200_BINNED(__half) break;
@@ -140,4 +141,20 @@ extern "C" int mb200_binned_curve_update(const void* preds, int preds_dtype, con
 #undef MB200_BINNED
     count_launch();
     return check_cuda(cudaGetLastError(), "binned curve launch");
+}
+
+extern "C" int mb200_binned_curve_update(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                         int64_t n, int64_t num_classes, const float* thresholds_sorted,
+                                         int64_t num_thresholds, int64_t* confmat, uint64_t* scratch, void* stream) {
+    return binned_update_impl(0, preds, preds_dtype, target, target_dtype, n, num_classes, thresholds_sorted, num_thresholds,
+                              confmat, scratch, stream);
+}
+
+// multilabel: target is [n, num_labels] like preds; entries whose target is not 0 / 1 (e.g. ignore_index) are skipped
+extern "C" int mb200_binned_curve_update_multilabel(const void* preds, int preds_dtype, const void* target,
+                                                    int target_dtype, int64_t n, int64_t num_labels,
+                                                    const float* thresholds_sorted, int64_t num_thresholds,
+                                                    int64_t* confmat, uint64_t* scratch, void* stream) {
+    return binned_update_impl(1, preds, preds_dtype, target, target_dtype, n, num_labels, thresholds_sorted, num_thresholds,
+                              confmat, scratch, stream);
 }

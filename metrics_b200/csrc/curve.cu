@@ -166,11 +166,16 @@ __global__ void __launch_bounds__(256) pack_ovr_kernel(const T* __restrict__ pre
     }
 }
 
-// multilabel: preds [N, L] and target [N, L] row-major -> keys / labels [L][N]; label = (target == 1)
+// multilabel: preds [N, L] and target [N, L] row-major -> keys / labels [L][N]; label = (target == 1).
+// Entries whose target equals `ignore` get the largest key (they sort behind every real score) and are counted per
+// label in seg_ignored[L]: the scan then works on the first n - seg_ignored[l] elements of segment l only — the
+// reference filters them per label before its sort (functional/classification/precision_recall_curve.py:826-830).
+constexpr unsigned kIgnoredKey = 0xFFFFFFFFu;
 template <typename T>
 __global__ void __launch_bounds__(256) pack_multilabel_kernel(const T* __restrict__ preds, const void* __restrict__ target,
-                                                              int tdtype, int n, int L, unsigned* __restrict__ keys,
-                                                              unsigned char* __restrict__ labels) {
+                                                              int tdtype, int n, int L, int has_ignore, long long ignore,
+                                                              unsigned* __restrict__ keys, unsigned char* __restrict__ labels,
+                                                              int* __restrict__ seg_ignored) {
     __shared__ unsigned tile[32][33];
     __shared__ unsigned char ltile[32][33];
     const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -178,16 +183,24 @@ __global__ void __launch_bounds__(256) pack_multilabel_kernel(const T* __restric
     for (int j = ty; j < 32; j += 8) {
         const int nn = n0 + j, cc = c0 + tx;
         if (nn < n && cc < L) {
-            tile[j][tx] = desc_key(to_float<T>(preds[(size_t)nn * L + cc]));
-            ltile[j][tx] = (unsigned char)(load_label(target, tdtype, (long long)nn * L + cc) == 1);
+            const long long t = load_label(target, tdtype, (long long)nn * L + cc);
+            const bool ign = has_ignore && t == ignore;
+            tile[j][tx] = ign ? kIgnoredKey : desc_key(to_float<T>(preds[(size_t)nn * L + cc]));
+            ltile[j][tx] = (unsigned char)(t == 1 && !ign);
         }
     }
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
         const int cc = c0 + j, nn = n0 + tx;
-        if (nn < n && cc < L) {
-            keys[(size_t)cc * n + nn] = tile[tx][j];
+        const bool ok = nn < n && cc < L;
+        const unsigned k = ok ? tile[tx][j] : 0u;
+        if (ok) {
+            keys[(size_t)cc * n + nn] = k;
             labels[(size_t)cc * n + nn] = ltile[tx][j];
+        }
+        if (has_ignore) {  // warp-uniform; one warp = 32 samples of label cc
+            const unsigned m = __ballot_sync(kFull, ok && k == kIgnoredKey);
+            if (tx == 0 && m) atomicAdd(seg_ignored + cc, __popc(m));
         }
     }
 }
@@ -323,12 +336,14 @@ __device__ __forceinline__ bool is_group_end(const ScanThreadData& d, int i, int
 
 // phase 1: per-tile aggregates
 __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const unsigned* __restrict__ keys,
-                                                                   const unsigned char* __restrict__ labels, int n,
+                                                                   const unsigned char* __restrict__ labels, int n_stride,
+                                                                   const int* __restrict__ seg_ignored,
                                                                    int tiles, TileInfo* __restrict__ info) {
     __shared__ unsigned sm[8];
     const int seg = blockIdx.y, tile = blockIdx.x;
+    const int n = seg_ignored ? n_stride - seg_ignored[seg] : n_stride;  // ignored entries sit behind the valid ones
     ScanThreadData d;
-    scan_load(d, keys + (size_t)seg * n, labels + (size_t)seg * n, n, tile);
+    scan_load(d, keys + (size_t)seg * n_stride, labels + (size_t)seg * n_stride, n, tile);
     unsigned npos = 0, nb = 0, cum_at_last = 0;
     int last_local = -1;
 #pragma unroll
@@ -419,7 +434,8 @@ __global__ void __launch_bounds__(256) scan_carry_kernel(TileInfo* __restrict__ 
 // compacted curve (fps, tps, thresholds) at distinct thresholds.
 template <bool kWriteCurve>
 __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const unsigned* __restrict__ keys,
-                                                                  const unsigned char* __restrict__ labels, int n,
+                                                                  const unsigned char* __restrict__ labels, int n_stride,
+                                                                  const int* __restrict__ seg_ignored,
                                                                   int tiles, const TileInfo* __restrict__ info,
                                                                   unsigned long long* __restrict__ auroc_acc /*[seg]*/,
                                                                   double* __restrict__ ap_partial /*[seg][tiles]*/,
@@ -429,8 +445,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const unsigned
     __shared__ double dsum[8];
     __shared__ unsigned long long usum[8];
     const int seg = blockIdx.y, tile = blockIdx.x;
+    const int n = seg_ignored ? n_stride - seg_ignored[seg] : n_stride;
     ScanThreadData d;
-    scan_load(d, keys + (size_t)seg * n, labels + (size_t)seg * n, n, tile);
+    scan_load(d, keys + (size_t)seg * n_stride, labels + (size_t)seg * n_stride, n, tile);
     const TileInfo carry = info[(size_t)seg * tiles + tile];
 
     unsigned npos = 0, nb = 0;
@@ -506,12 +523,14 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const unsigned
 // out[seg] = {auroc, ap, n_pos, n_neg, n_thresholds} as fp32 (counts < 2^24 are exact; larger ones only inform weights)
 __global__ void __launch_bounds__(256) scan_finalize_kernel(const unsigned long long* __restrict__ auroc_acc,
                                                             const double* __restrict__ ap_partial,
-                                                            const unsigned* __restrict__ seg_totals, int tiles, int n,
+                                                            const unsigned* __restrict__ seg_totals, int tiles, int n_stride,
+                                                            const int* __restrict__ seg_ignored,
                                                             int segments, float* __restrict__ out_auroc,
                                                             float* __restrict__ out_ap, long long* __restrict__ out_counts) {
     const int seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (seg >= segments) return;
+    const int n = seg_ignored ? n_stride - seg_ignored[seg] : n_stride;
     double s = 0.0;
     // fixed order: lane-strided partial sums then a fixed shuffle tree
     for (int t = lane; t < tiles; t += 32) s += ap_partial[(size_t)seg * tiles + t];
@@ -615,6 +634,7 @@ extern "C" int64_t mb200_curve_workspace_bytes(int64_t segments, int64_t n) {
     (void)sort_tiles;
     b += segments * (scan_tiles + 1) * (int64_t)sizeof(TileInfo);
     b += segments * 2 * 4;                          // seg_totals
+    b += segments * 4 + 256;                        // seg_ignored (multilabel + ignore_index)
     b += segments * 8;                              // auroc_acc
     b += segments * (scan_tiles + 1) * 8;           // ap_partial
     return b + 16 * 256;                            // alignment slack
@@ -625,6 +645,7 @@ struct CurveWs {
     unsigned *keys_a, *keys_b;
     unsigned char *lab_a, *lab_b;
     unsigned *sort_scratch, *seg_totals;
+    int* seg_ignored;
     TileInfo* info;
     unsigned long long* auroc_acc;
     double* ap_partial;
@@ -647,6 +668,7 @@ CurveWs carve(void* workspace, int64_t segments, int64_t n) {
     (void)sort_tiles;
     w.info = (TileInfo*)bump(p, segments * (scan_tiles + 1) * (int64_t)sizeof(TileInfo));
     w.seg_totals = (unsigned*)bump(p, segments * 2 * 4);
+    w.seg_ignored = (int*)bump(p, segments * 4);
     w.auroc_acc = (unsigned long long*)bump(p, segments * 8);
     w.ap_partial = (double*)bump(p, segments * (scan_tiles + 1) * 8);
     return w;
@@ -656,7 +678,7 @@ CurveWs carve(void* workspace, int64_t segments, int64_t n) {
 namespace {
 // sort (keys_a/lab_a are clobbered; the sorted result lands back in them) + tie-collapsing scan + finalize
 int sort_and_scan(unsigned* keys_a, unsigned char* lab_a, const CurveWs& w, int ni, int64_t segments, int64_t n,
-                  float* out_auroc, float* out_ap, int64_t* out_counts, float* fps_out, float* tps_out, float* thr_out,
+                  const int* seg_ignored, float* out_auroc, float* out_ap, int64_t* out_counts, float* fps_out, float* tps_out, float* thr_out,
                   uint32_t* err_flag, cudaStream_t st) {
     const int scan_tiles = (ni + kScanTile - 1) / kScanTile;
     // ---- 4 one-sweep radix passes (ping-pong; an even number of passes leaves the result in the *_a buffers) ----
@@ -672,16 +694,16 @@ int sort_and_scan(unsigned* keys_a, unsigned char* lab_a, const CurveWs& w, int 
     // ---- scan ----
     const dim3 sgrid((unsigned)scan_tiles, (unsigned)segments);
     zero_u64_kernel<<<(int)((segments + 255) / 256), 256, 0, st>>>(w.auroc_acc, (int)segments);
-    scan_reduce_kernel<<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, scan_tiles, w.info);
+    scan_reduce_kernel<<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, seg_ignored, scan_tiles, w.info);
     scan_carry_kernel<<<(unsigned)segments, 256, 0, st>>>(w.info, scan_tiles, ni, w.seg_totals);
     if (fps_out)
-        scan_apply_kernel<true><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, scan_tiles, w.info, w.auroc_acc,
+        scan_apply_kernel<true><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, seg_ignored, scan_tiles, w.info, w.auroc_acc,
                                                                 w.ap_partial, fps_out, tps_out, thr_out, n);
     else
-        scan_apply_kernel<false><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, scan_tiles, w.info, w.auroc_acc,
+        scan_apply_kernel<false><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, seg_ignored, scan_tiles, w.info, w.auroc_acc,
                                                                  w.ap_partial, nullptr, nullptr, nullptr, n);
     scan_finalize_kernel<<<(int)((segments + 7) / 8), 256, 0, st>>>(w.auroc_acc, w.ap_partial, w.seg_totals, scan_tiles,
-                                                                    ni, (int)segments, out_auroc, out_ap, reinterpret_cast<long long*>(out_counts));
+                                                                    ni, seg_ignored, (int)segments, out_auroc, out_ap, reinterpret_cast<long long*>(out_counts));
     for (int i = 0; i < 5; ++i) count_launch();
     return check_cuda(cudaGetLastError(), "curve evaluate launch");
 }
@@ -724,12 +746,8 @@ extern "C" int mb200_curve_evaluate(const void* preds, int preds_dtype, const vo
 #undef MB200_PACK
     } else {
         const dim3 grid((unsigned)((ni + 31) / 32), (unsigned)((segments + 31) / 32));
-#define MB200_PACK(T)                                                                                                 \
-    if (pos_label == MB200_CURVE_MULTILABEL)                                                                          \
-        pack_multilabel_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, ni,  \
-                                                        (int)segments, w.keys_a, w.lab_a);                            \
-    else                                                                                                              \
-        pack_ovr_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, ni, (int)segments, w.keys_a, w.lab_a);
+#define MB200_PACK(T) \
+    pack_ovr_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, ni, (int)segments, w.keys_a, w.lab_a);
         switch (preds_dtype) {
             case MB200_F32: MB200_PACK(float) break;
             case MB200_F16: MB200_PACK(__half) break;
@@ -740,8 +758,44 @@ extern "C" int mb200_curve_evaluate(const void* preds, int preds_dtype, const vo
     }
     count_launch();
 
-    return sort_and_scan(w.keys_a, w.lab_a, w, ni, segments, n, out_auroc, out_ap, out_counts, fps_out, tps_out, thr_out,
+    return sort_and_scan(w.keys_a, w.lab_a, w, ni, segments, n, nullptr, out_auroc, out_ap, out_counts, fps_out, tps_out, thr_out,
                          err_flag, st);
+}
+
+// Exact-mode evaluation of `num_labels` independent binary curves (multilabel task).
+//   preds / target : [n, num_labels] row-major; positives are target == 1; with has_ignore, entries whose target equals
+//   ignore_index are dropped from THEIR label's curve only (reference: precision_recall_curve.py:822-834).
+//   Outputs as in mb200_curve_evaluate; out_counts[l] = {n_pos, n_neg, n_distinct_thresholds} over the kept entries.
+extern "C" int mb200_curve_evaluate_multilabel(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                               int64_t n, int64_t num_labels, int has_ignore, int64_t ignore_index,
+                                               void* workspace, int64_t workspace_bytes, float* out_auroc, float* out_ap,
+                                               int64_t* out_counts, float* fps_out, float* tps_out, float* thr_out,
+                                               uint32_t* err_flag, void* stream) {
+    MB200_REQUIRE(n >= 1 && n < (1ll << 30), "curve evaluation needs 1 <= n < 2^30 samples (got %lld)", (long long)n);
+    MB200_REQUIRE(num_labels >= 1 && num_labels <= 65535, "bad num_labels");
+    MB200_REQUIRE(preds && target && workspace && out_auroc && out_ap && out_counts, "NULL pointer");
+    MB200_REQUIRE(workspace_bytes >= mb200_curve_workspace_bytes(num_labels, n), "workspace too small");
+    MB200_REQUIRE((fps_out == nullptr) == (tps_out == nullptr) && (fps_out == nullptr) == (thr_out == nullptr),
+                  "curve outputs must be given all together or not at all");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CurveWs w = carve(workspace, num_labels, n);
+    const int ni = (int)n;
+    if (has_ignore) MB200_CUDA_OK(cudaMemsetAsync(w.seg_ignored, 0, (size_t)num_labels * sizeof(int), st));
+    const dim3 grid((unsigned)((ni + 31) / 32), (unsigned)((num_labels + 31) / 32));
+#define MB200_PACK(T)                                                                                              \
+    pack_multilabel_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, ni,   \
+                                                    (int)num_labels, has_ignore, (long long)ignore_index, w.keys_a, \
+                                                    w.lab_a, w.seg_ignored);
+    switch (preds_dtype) {
+        case MB200_F32: MB200_PACK(float) break;
+        case MB200_F16: MB200_PACK(__half) break;
+        case MB200_BF16: MB200_PACK(__nv_bfloat16) break;
+        default: set_error("scores must be f32/f16/bf16 (dtype tag %d)", preds_dtype); return MB200_ERR_UNSUPPORTED;
+    }
+#undef MB200_PACK
+    count_launch();
+    return sort_and_scan(w.keys_a, w.lab_a, w, ni, num_labels, n, has_ignore ? w.seg_ignored : nullptr, out_auroc, out_ap,
+                         out_counts, fps_out, tps_out, thr_out, err_flag, st);
 }
 
 // Class-major keys of [n, num_classes] scores: keys_out [num_classes][n] (the packing step of mb200_curve_evaluate on
@@ -778,6 +832,6 @@ extern "C" int mb200_curve_evaluate_keys(uint32_t* keys, const void* target, int
     labels_from_target_kernel<<<blocks_for(total, 256 * 8, sm_count() * 8), 256, 0, st>>>(target, target_dtype, (int)n,
                                                                                           (int)segments, first_class, w.lab_a);
     count_launch();
-    return sort_and_scan(keys, w.lab_a, w, (int)n, segments, n, out_auroc, out_ap, out_counts, nullptr, nullptr, nullptr,
+    return sort_and_scan(keys, w.lab_a, w, (int)n, segments, n, nullptr, out_auroc, out_ap, out_counts, nullptr, nullptr, nullptr,
                          err_flag, st);
 }

@@ -30,3 +30,7 @@ from metrics_b200.functional.classification.stat_scores import (  # noqa: F401,E
     multilabel_stat_scores,
     stat_scores,
 )
+from metrics_b200.functional.classification.auroc import multilabel_auroc  # noqa: F401,E402
+from metrics_b200.functional.classification.average_precision import multilabel_average_precision  # noqa: F401,E402
+from metrics_b200.functional.classification.precision_recall_curve import multilabel_precision_recall_curve  # noqa: F401,E402
+from metrics_b200.functional.classification.roc import multilabel_roc  # noqa: F401,E402

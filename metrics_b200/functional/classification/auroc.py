@@ -176,3 +176,78 @@ def multiclass_auroc(
     )
     state = _multiclass_precision_recall_curve_update(preds, target, num_classes, thresholds)
     return _multiclass_auroc_compute(state, num_classes, average, thresholds)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# multilabel (reference auroc.py:292-425)
+# ----------------------------------------------------------------------------------------------------------------------
+def _multilabel_auroc_arg_validation(
+    num_labels: int,
+    average: Optional[str],
+    thresholds: Optional[Union[int, List[float], Tensor]] = None,
+    ignore_index: Optional[int] = None,
+) -> None:
+    from metrics_b200.functional.classification.precision_recall_curve import _multilabel_precision_recall_curve_arg_validation
+
+    _multilabel_precision_recall_curve_arg_validation(num_labels, thresholds, ignore_index)
+    allowed_average = ("micro", "macro", "weighted", "none", None)
+    if average not in allowed_average:
+        raise ValueError(f"Expected argument `average` to be one of {allowed_average} but got {average}")
+
+
+def _multilabel_micro_state(state, ignore_index: Optional[int]):
+    preds, target = state[0].flatten(), state[1].flatten()
+    if ignore_index is not None:
+        keep = target != ignore_index
+        preds, target = preds[keep], target[keep]
+    return preds, target
+
+
+def _multilabel_auroc_compute(
+    state: Union[Tensor, tuple[Tensor, Tensor]],
+    num_labels: int,
+    average: Optional[str],
+    thresholds: Optional[Tensor],
+    ignore_index: Optional[int] = None,
+    scalars: Optional[tuple] = None,
+) -> Tensor:
+    """Per-label AUROC from ONE batched sort + scan (reference :308-333 sorts once per label)."""
+    from metrics_b200.functional.classification.roc import _multilabel_roc_compute
+
+    if average == "micro":
+        if isinstance(state, Tensor) and thresholds is not None:
+            return _binary_auroc_compute(state.sum(1), thresholds, max_fpr=None)
+        return _binary_auroc_compute(_multilabel_micro_state(state, ignore_index), thresholds, max_fpr=None)
+    if isinstance(state, Tensor) and thresholds is not None:  # binned
+        fpr, tpr, _ = _multilabel_roc_compute(state, num_labels, thresholds, ignore_index)
+        res = _auc_compute_without_check(fpr, tpr, 1.0, axis=1)
+        return _reduce_per_class(res, average, state[0][:, 1, :].sum(-1).float(), "Average precision")
+    if scalars is not None:
+        auroc, _, counts = scalars
+    else:
+        auroc, _, counts, _ = _native.curve_evaluate_multilabel(state[0], state[1], num_labels, ignore_index)
+    return _reduce_per_class(auroc, average, counts[:, 0].float(), "Average precision")
+
+
+def multilabel_auroc(
+    preds: Tensor,
+    target: Tensor,
+    num_labels: int,
+    average: Optional[Literal["micro", "macro", "weighted", "none"]] = "macro",
+    thresholds: Optional[Union[int, List[float], Tensor]] = None,
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+) -> Tensor:
+    """Multilabel AUROC — reference :336-425."""
+    from metrics_b200.functional.classification.precision_recall_curve import (
+        _multilabel_precision_recall_curve_format,
+        _multilabel_precision_recall_curve_tensor_validation,
+        _multilabel_precision_recall_curve_update,
+    )
+
+    if validate_args:
+        _multilabel_auroc_arg_validation(num_labels, average, thresholds, ignore_index)
+        _multilabel_precision_recall_curve_tensor_validation(preds, target, num_labels, ignore_index)
+    preds, target, thresholds = _multilabel_precision_recall_curve_format(preds, target, num_labels, thresholds, ignore_index)
+    state = _multilabel_precision_recall_curve_update(preds, target, num_labels, thresholds)
+    return _multilabel_auroc_compute(state, num_labels, average, thresholds, ignore_index)

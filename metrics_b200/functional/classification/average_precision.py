@@ -132,3 +132,77 @@ def multiclass_average_precision(
     )
     state = _multiclass_precision_recall_curve_update(preds, target, num_classes, thresholds)
     return _multiclass_average_precision_compute(state, num_classes, average, thresholds)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# multilabel (reference average_precision.py:272-420)
+# ----------------------------------------------------------------------------------------------------------------------
+def _multilabel_average_precision_arg_validation(
+    num_labels: int,
+    average: Optional[str],
+    thresholds: Optional[Union[int, List[float], Tensor]] = None,
+    ignore_index: Optional[int] = None,
+) -> None:
+    from metrics_b200.functional.classification.precision_recall_curve import _multilabel_precision_recall_curve_arg_validation
+
+    _multilabel_precision_recall_curve_arg_validation(num_labels, thresholds, ignore_index)
+    allowed_average = ("micro", "macro", "weighted", "none", None)
+    if average not in allowed_average:
+        raise ValueError(f"Expected argument `average` to be one of {allowed_average} but got {average}")
+
+
+def _multilabel_average_precision_compute(
+    state: Union[Tensor, tuple[Tensor, Tensor]],
+    num_labels: int,
+    average: Optional[str],
+    thresholds: Optional[Tensor],
+    ignore_index: Optional[int] = None,
+    scalars: Optional[tuple] = None,
+) -> Tensor:
+    """Per-label AP from ONE batched sort + scan (reference :284-309).  A label without positives scores -0.0 (the
+    per-label binary all-negative guard), never NaN."""
+    from metrics_b200.functional.classification.auroc import _multilabel_micro_state
+    from metrics_b200.functional.classification.precision_recall_curve import _multilabel_precision_recall_curve_compute
+
+    if average == "micro":
+        if isinstance(state, Tensor) and thresholds is not None:
+            return _binary_average_precision_compute(state.sum(1), thresholds)
+        return _binary_average_precision_compute(_multilabel_micro_state(state, ignore_index), thresholds)
+    if isinstance(state, Tensor) and thresholds is not None:  # binned
+        precision, recall, _ = _multilabel_precision_recall_curve_compute(state, num_labels, thresholds, ignore_index)
+        res = -torch.sum((recall[:, 1:] - recall[:, :-1]) * precision[:, :-1], 1)
+        return _reduce_average_precision(res, average, weights=state[0][:, 1, :].sum(-1).float())
+    if scalars is not None:
+        _, ap, counts = scalars
+    else:
+        _, ap, counts, _ = _native.curve_evaluate_multilabel(state[0], state[1], num_labels, ignore_index)
+    if bool((counts[:, 0] == 0).any()):
+        rank_zero_warn(
+            "No positive samples found in target, recall is undefined. Setting recall to one for all thresholds.",
+            UserWarning,
+        )
+    return _reduce_average_precision(ap, average, weights=counts[:, 0].float())
+
+
+def multilabel_average_precision(
+    preds: Tensor,
+    target: Tensor,
+    num_labels: int,
+    average: Optional[Literal["micro", "macro", "weighted", "none"]] = "macro",
+    thresholds: Optional[Union[int, List[float], Tensor]] = None,
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+) -> Tensor:
+    """Multilabel average precision — reference :312-420."""
+    from metrics_b200.functional.classification.precision_recall_curve import (
+        _multilabel_precision_recall_curve_format,
+        _multilabel_precision_recall_curve_tensor_validation,
+        _multilabel_precision_recall_curve_update,
+    )
+
+    if validate_args:
+        _multilabel_average_precision_arg_validation(num_labels, average, thresholds, ignore_index)
+        _multilabel_precision_recall_curve_tensor_validation(preds, target, num_labels, ignore_index)
+    preds, target, thresholds = _multilabel_precision_recall_curve_format(preds, target, num_labels, thresholds, ignore_index)
+    state = _multilabel_precision_recall_curve_update(preds, target, num_labels, thresholds)
+    return _multilabel_average_precision_compute(state, num_labels, average, thresholds, ignore_index)

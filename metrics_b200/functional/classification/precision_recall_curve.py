@@ -343,3 +343,101 @@ def multiclass_precision_recall_curve(
     )
     state = _multiclass_precision_recall_curve_update(preds, target, num_classes, thresholds, average)
     return _multiclass_precision_recall_curve_compute(state, num_classes, thresholds, average)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# multilabel (reference :711-941): one binary curve per label, all labels in ONE batched sort + scan
+# ----------------------------------------------------------------------------------------------------------------------
+def _multilabel_precision_recall_curve_arg_validation(
+    num_labels: int,
+    thresholds: Optional[Union[int, List[float], Tensor]] = None,
+    ignore_index: Optional[int] = None,
+) -> None:
+    _multiclass_precision_recall_curve_arg_validation(num_labels, thresholds, ignore_index)
+
+
+def _multilabel_precision_recall_curve_tensor_validation(
+    preds: Tensor, target: Tensor, num_labels: int, ignore_index: Optional[int] = None
+) -> None:
+    _binary_precision_recall_curve_tensor_validation(preds, target, ignore_index)
+    if preds.shape[1] != num_labels:
+        raise ValueError(
+            "Expected both `target.shape[1]` and `preds.shape[1]` to be equal to the number of labels"
+            f" but got {preds.shape[1]} and expected {num_labels}"
+        )
+
+
+def _multilabel_precision_recall_curve_format(
+    preds: Tensor,
+    target: Tensor,
+    num_labels: int,
+    thresholds: Optional[Union[int, List[float], Tensor]] = None,
+    ignore_index: Optional[int] = None,
+) -> tuple[Tensor, Tensor, Optional[Tensor]]:
+    """``[N, L, ...] -> [N', L]``, sigmoid if the batch holds logits — reference :745-774.  Ignored entries stay in the
+    state (they are dropped per label by the kernels: exact mode gives them the largest sort key, the binned kernel skips
+    every target that is neither 0 nor 1), so no masked copy of the batch is made."""
+    preds = preds.transpose(0, 1).reshape(num_labels, -1).T
+    target = target.transpose(0, 1).reshape(num_labels, -1).T
+    preds = _native.sigmoid_if_logits(preds.contiguous())
+    return preds, target.contiguous(), _adjust_threshold_arg(thresholds, preds.device)
+
+
+def _multilabel_precision_recall_curve_update(
+    preds: Tensor, target: Tensor, num_labels: int, thresholds: Optional[Tensor]
+) -> Union[Tensor, tuple[Tensor, Tensor]]:
+    """Exact mode keeps the batch; binned mode returns the ``[T, L, 2, 2]`` multi-threshold confusion matrix
+    (reference :777-799) from the K4 kernel."""
+    if thresholds is None:
+        return preds, target
+    return _native.binned_curve_update(preds, target, thresholds.to(preds.device), num_labels, multilabel=True)
+
+
+def _multilabel_curves(preds: Tensor, target: Tensor, num_labels: int, ignore_index: Optional[int]):
+    _, _, counts, (fps, tps, thr) = _native.curve_evaluate_multilabel(preds, target, num_labels, ignore_index, want_curve=True)
+    host = counts.tolist()  # one host sync for all labels
+    if preds.dtype != torch.float32:
+        thr = thr.to(preds.dtype)
+    return fps, tps, thr, host
+
+
+def _multilabel_precision_recall_curve_compute(
+    state: Union[Tensor, tuple[Tensor, Tensor]],
+    num_labels: int,
+    thresholds: Optional[Tensor],
+    ignore_index: Optional[int] = None,
+):
+    """Reference :802-836 (a Python loop over labels with a sort each)."""
+    if isinstance(state, Tensor) and thresholds is not None:
+        tps, fps, fns = state[:, :, 1, 1], state[:, :, 0, 1], state[:, :, 1, 0]
+        precision = _safe_div(tps, tps + fps)
+        recall = _safe_div(tps, tps + fns)
+        precision = torch.cat([precision, torch.ones(1, num_labels, dtype=precision.dtype, device=precision.device)])
+        recall = torch.cat([recall, torch.zeros(1, num_labels, dtype=recall.dtype, device=recall.device)])
+        return precision.T, recall.T, thresholds
+    fps, tps, thr, host = _multilabel_curves(state[0], state[1], num_labels, ignore_index)
+    precision_list, recall_list, thres_list = [], [], []
+    for l in range(num_labels):
+        n_pos, _, u = host[l]
+        p, r, t = _pr_from_counts(fps[l, :u], tps[l, :u], thr[l, :u], n_pos == 0)
+        precision_list.append(p)
+        recall_list.append(r)
+        thres_list.append(t)
+    return precision_list, recall_list, thres_list
+
+
+def multilabel_precision_recall_curve(
+    preds: Tensor,
+    target: Tensor,
+    num_labels: int,
+    thresholds: Optional[Union[int, List[float], Tensor]] = None,
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+):
+    """Per-label PR curves — reference :839-941."""
+    if validate_args:
+        _multilabel_precision_recall_curve_arg_validation(num_labels, thresholds, ignore_index)
+        _multilabel_precision_recall_curve_tensor_validation(preds, target, num_labels, ignore_index)
+    preds, target, thresholds = _multilabel_precision_recall_curve_format(preds, target, num_labels, thresholds, ignore_index)
+    state = _multilabel_precision_recall_curve_update(preds, target, num_labels, thresholds)
+    return _multilabel_precision_recall_curve_compute(state, num_labels, thresholds, ignore_index)

@@ -138,3 +138,53 @@ def multiclass_roc(
     )
     state = _multiclass_precision_recall_curve_update(preds, target, num_classes, thresholds, average)
     return _multiclass_roc_compute(state, num_classes, thresholds, average)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# multilabel (reference roc.py:323-458)
+# ----------------------------------------------------------------------------------------------------------------------
+def _multilabel_roc_compute(
+    state: Union[Tensor, tuple[Tensor, Tensor]],
+    num_labels: int,
+    thresholds: Optional[Tensor],
+    ignore_index: Optional[int] = None,
+):
+    """Per-label ROC curves from ONE batched sort (reference loops over labels, :344-355)."""
+    from metrics_b200.functional.classification.precision_recall_curve import _multilabel_curves
+
+    if isinstance(state, Tensor) and thresholds is not None:
+        tps, fps, fns, tns = state[:, :, 1, 1], state[:, :, 0, 1], state[:, :, 1, 0], state[:, :, 0, 0]
+        return _safe_div(fps, fps + tns).flip(0).T, _safe_div(tps, tps + fns).flip(0).T, thresholds.flip(0)
+    fps, tps, thr, host = _multilabel_curves(state[0], state[1], num_labels, ignore_index)
+    fpr_list, tpr_list, thres_list = [], [], []
+    for l in range(num_labels):
+        u = host[l][2]
+        f, t, th = _roc_from_counts(fps[l, :u], tps[l, :u], thr[l, :u])
+        fpr_list.append(f)
+        tpr_list.append(t)
+        thres_list.append(th)
+    return fpr_list, tpr_list, thres_list
+
+
+def multilabel_roc(
+    preds: Tensor,
+    target: Tensor,
+    num_labels: int,
+    thresholds: Optional[Union[int, List[float], Tensor]] = None,
+    ignore_index: Optional[int] = None,
+    validate_args: bool = True,
+):
+    """Per-label ROC curves — reference :359-458."""
+    from metrics_b200.functional.classification.precision_recall_curve import (
+        _multilabel_precision_recall_curve_arg_validation,
+        _multilabel_precision_recall_curve_format,
+        _multilabel_precision_recall_curve_tensor_validation,
+        _multilabel_precision_recall_curve_update,
+    )
+
+    if validate_args:
+        _multilabel_precision_recall_curve_arg_validation(num_labels, thresholds, ignore_index)
+        _multilabel_precision_recall_curve_tensor_validation(preds, target, num_labels, ignore_index)
+    preds, target, thresholds = _multilabel_precision_recall_curve_format(preds, target, num_labels, thresholds, ignore_index)
+    state = _multilabel_precision_recall_curve_update(preds, target, num_labels, thresholds)
+    return _multilabel_roc_compute(state, num_labels, thresholds, ignore_index)

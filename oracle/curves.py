@@ -172,3 +172,66 @@ def binned_confmat(preds: np.ndarray, target: np.ndarray, thresholds: np.ndarray
             out[:, c, y, 1] = ge[sel].sum(0)
             out[:, c, y, 0] = sel.sum() - out[:, c, y, 1]
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# multilabel: one binary problem per label (precision_recall_curve.py:745-836, roc.py:329-356, auroc.py:308-333,
+# average_precision.py:284-309).  preds [N, L] already sigmoid-normalised, target [N, L].
+# ----------------------------------------------------------------------------------------------------------------------
+def multilabel_flatten(preds: np.ndarray, target: np.ndarray):
+    """[N, L, ...] -> [N', L]  (precision_recall_curve.py:765-766: transpose(0,1).reshape(L,-1).T)."""
+    L = preds.shape[1]
+    return np.moveaxis(preds, 1, 0).reshape(L, -1).T, np.moveaxis(target, 1, 0).reshape(L, -1).T
+
+
+def _label_column(preds: np.ndarray, target: np.ndarray, l: int, ignore_index: Optional[int]):
+    p, t = preds[:, l], target[:, l]
+    if ignore_index is not None:  # :826-830
+        keep = t != ignore_index
+        p, t = p[keep], t[keep]
+    return p, t
+
+
+def multilabel_auroc_exact(preds, target, ignore_index: Optional[int] = None) -> np.ndarray:
+    return np.array([binary_auroc_exact(*_label_column(preds, target, l, ignore_index)) for l in range(preds.shape[1])])
+
+
+def multilabel_average_precision_exact(preds, target, ignore_index: Optional[int] = None) -> np.ndarray:
+    return np.array([binary_average_precision_exact(*_label_column(preds, target, l, ignore_index)) for l in range(preds.shape[1])])
+
+
+def multilabel_roc_ref32(preds, target, ignore_index: Optional[int] = None):
+    return [binary_roc_ref32(*_label_column(preds, target, l, ignore_index)) for l in range(preds.shape[1])]
+
+
+def multilabel_prc_ref32(preds, target, ignore_index: Optional[int] = None):
+    return [binary_prc_ref32(*_label_column(preds, target, l, ignore_index)) for l in range(preds.shape[1])]
+
+
+def multilabel_positive_counts(target: np.ndarray) -> np.ndarray:
+    """Weights of the `weighted` average: (target == 1).sum(0) (auroc.py:332)."""
+    return (target == 1).sum(0).astype(np.float64)
+
+
+def multilabel_micro(preds, target, ignore_index: Optional[int] = None):
+    """`average="micro"`: flatten everything into one binary problem (auroc.py:319-325)."""
+    p, t = preds.reshape(-1), target.reshape(-1)
+    if ignore_index is not None:
+        keep = t != ignore_index
+        p, t = p[keep], t[keep]
+    return p, t
+
+
+def multilabel_binned_confmat(preds: np.ndarray, target: np.ndarray, thresholds: np.ndarray) -> np.ndarray:
+    """[T, L, 2, 2] multi-threshold confusion matrix (precision_recall_curve.py:777-799); entries whose target is not
+    0 / 1 (ignore_index, mapped to a negative bin by :768-774 and filtered at :797) do not count."""
+    thr = np.asarray(thresholds, dtype=np.float32)
+    L = preds.shape[1]
+    out = np.zeros((thr.size, L, 2, 2), np.int64)
+    for l in range(L):
+        ge = preds[:, l].astype(np.float32)[:, None] >= thr[None, :]
+        for y in (0, 1):
+            sel = target[:, l] == y
+            out[:, l, y, 1] = ge[sel].sum(0)
+            out[:, l, y, 0] = sel.sum() - out[:, l, y, 1]
+    return out

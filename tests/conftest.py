@@ -58,3 +58,10 @@ def golden_binned():
     import numpy as np
 
     return np.load(os.path.join(GOLDEN_DIR, "binned.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_multilabel():
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN_DIR, "multilabel.npz"), allow_pickle=False)

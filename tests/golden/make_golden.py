@@ -526,6 +526,69 @@ def binned_golden() -> dict:
     return out
 
 
+def multilabel_golden() -> dict:
+    """Multilabel curve family (exact + binned) from the unmodified reference."""
+    import warnings
+
+    from torchmetrics.classification import MultilabelAUROC, MultilabelAveragePrecision
+    from torchmetrics.functional.classification import (
+        multilabel_auroc,
+        multilabel_average_precision,
+        multilabel_precision_recall_curve,
+        multilabel_roc,
+    )
+    from torchmetrics.functional.classification.precision_recall_curve import (
+        _multilabel_precision_recall_curve_format,
+        _multilabel_precision_recall_curve_update,
+    )
+
+    warnings.simplefilter("ignore")
+    out: dict = {}
+    g = torch.Generator().manual_seed(77)
+    cases = {}
+    cases["L4_probs"] = (torch.rand(500, 4, generator=g), torch.randint(0, 2, (500, 4), generator=g))
+    lg = torch.randn(1300, 6, generator=g) * 2
+    tg = torch.randint(0, 2, (1300, 6), generator=g)
+    tg[:, 5] = 0  # label 5 has no positive
+    tg[:, 4] = 1  # label 4 has no negative
+    cases["L6_logits"] = (lg, tg)
+    cases["L3_ties"] = ((torch.rand(2100, 3, generator=g) * 20).floor() / 20, torch.randint(0, 2, (2100, 3), generator=g))
+    cases["L5_extra"] = (torch.rand(40, 5, 7, generator=g), torch.randint(0, 2, (40, 5, 7), generator=g))  # extra dim
+    for name, (p, t) in cases.items():
+        L = p.shape[1]
+        out[f"{name}/preds"], out[f"{name}/target"] = p.numpy(), t.numpy()
+        ti = t.clone()
+        ti.view(-1)[::7] = -1
+        out[f"{name}/target_ignore"] = ti.numpy()
+        for tag, tt, ig in (("", t, None), ("ign_", ti, -1)):
+            for avg in ("micro", "macro", "weighted", "none"):
+                out[f"{name}/{tag}auroc_{avg}"] = multilabel_auroc(p, tt, L, average=avg, ignore_index=ig).numpy()
+                out[f"{name}/{tag}ap_{avg}"] = multilabel_average_precision(p, tt, L, average=avg, ignore_index=ig).numpy()
+            fpr, tpr, thr = multilabel_roc(p, tt, L, ignore_index=ig)
+            pr, rc, th2 = multilabel_precision_recall_curve(p, tt, L, ignore_index=ig)
+            for l in range(L):
+                out[f"{name}/{tag}roc_fpr{l}"], out[f"{name}/{tag}roc_tpr{l}"], out[f"{name}/{tag}roc_thr{l}"] = fpr[l].numpy(), tpr[l].numpy(), thr[l].numpy()
+                out[f"{name}/{tag}prc_p{l}"], out[f"{name}/{tag}prc_r{l}"], out[f"{name}/{tag}prc_thr{l}"] = pr[l].numpy(), rc[l].numpy(), th2[l].numpy()
+            for tname, thrs in (("int9", 9), ("list", [0.8, 0.15, 0.5])):
+                pf, tf, th = _multilabel_precision_recall_curve_format(p, tt, L, thrs, ig)
+                out[f"{name}/{tag}{tname}/confmat"] = _multilabel_precision_recall_curve_update(pf, tf, L, th).numpy()
+                for avg in ("micro", "macro", "weighted", "none"):
+                    out[f"{name}/{tag}{tname}/auroc_{avg}"] = multilabel_auroc(p, tt, L, average=avg, thresholds=thrs, ignore_index=ig).numpy()
+                    out[f"{name}/{tag}{tname}/ap_{avg}"] = multilabel_average_precision(p, tt, L, average=avg, thresholds=thrs, ignore_index=ig).numpy()
+                f, tp_, h = multilabel_roc(p, tt, L, thresholds=thrs, ignore_index=ig)
+                out[f"{name}/{tag}{tname}/roc_fpr"], out[f"{name}/{tag}{tname}/roc_tpr"], out[f"{name}/{tag}{tname}/roc_thr"] = f.numpy(), tp_.numpy(), h.numpy()
+                pr, rc, h = multilabel_precision_recall_curve(p, tt, L, thresholds=thrs, ignore_index=ig)
+                out[f"{name}/{tag}{tname}/prc_p"], out[f"{name}/{tag}{tname}/prc_r"] = pr.numpy(), rc.numpy()
+    # modular, 3 updates
+    p, t = cases["L6_logits"]
+    for avg in ("macro", "micro"):
+        m1, m2, m3 = MultilabelAUROC(num_labels=6, average=avg), MultilabelAveragePrecision(num_labels=6, average=avg), MultilabelAUROC(num_labels=6, average=avg, thresholds=25)
+        for a, b in zip(p.chunk(3), t.chunk(3)):
+            m1.update(a, b), m2.update(a, b), m3.update(a, b)
+        out[f"class/auroc_{avg}"], out[f"class/ap_{avg}"], out[f"class/auroc_binned25_{avg}"] = m1.compute().numpy(), m2.compute().numpy(), m3.compute().numpy()
+    return out
+
+
 def regression_golden() -> dict:
     import torchmetrics.functional as TF
     import torchmetrics.regression as TR
@@ -590,6 +653,11 @@ if __name__ == "__main__":
     if "map" in which:
         data = map_golden()
         path = os.path.join(HERE, "detection.npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
+    if "multilabel" in which:
+        data = multilabel_golden()
+        path = os.path.join(HERE, "multilabel.npz")
         np.savez_compressed(path, **data)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
     if "curves" in which:
