@@ -33,3 +33,38 @@ from metrics_b200.classification.auroc import MultilabelAUROC  # noqa: F401,E402
 from metrics_b200.classification.average_precision import MultilabelAveragePrecision  # noqa: F401,E402
 from metrics_b200.classification.precision_recall_curve import MultilabelPrecisionRecallCurve  # noqa: F401,E402
 from metrics_b200.classification.roc import MultilabelROC  # noqa: F401,E402
+from metrics_b200.classification.ratio_metrics import (  # noqa: F401,E402
+    BinaryHammingDistance,
+    BinaryNegativePredictiveValue,
+    BinaryPrecision,
+    BinaryRecall,
+    BinarySpecificity,
+    HammingDistance,
+    MulticlassHammingDistance,
+    MulticlassNegativePredictiveValue,
+    MulticlassPrecision,
+    MulticlassRecall,
+    MulticlassSpecificity,
+    MultilabelHammingDistance,
+    MultilabelNegativePredictiveValue,
+    MultilabelPrecision,
+    MultilabelRecall,
+    MultilabelSpecificity,
+    NegativePredictiveValue,
+    Precision,
+    Recall,
+    Specificity,
+)
+from metrics_b200.classification.confmat_metrics import (  # noqa: F401,E402
+    BinaryCohenKappa,
+    BinaryJaccardIndex,
+    BinaryMatthewsCorrCoef,
+    CohenKappa,
+    JaccardIndex,
+    MatthewsCorrCoef,
+    MulticlassCohenKappa,
+    MulticlassJaccardIndex,
+    MulticlassMatthewsCorrCoef,
+    MultilabelJaccardIndex,
+    MultilabelMatthewsCorrCoef,
+)

@@ -34,3 +34,35 @@ from metrics_b200.functional.classification.auroc import multilabel_auroc  # noq
 from metrics_b200.functional.classification.average_precision import multilabel_average_precision  # noqa: F401,E402
 from metrics_b200.functional.classification.precision_recall_curve import multilabel_precision_recall_curve  # noqa: F401,E402
 from metrics_b200.functional.classification.roc import multilabel_roc  # noqa: F401,E402
+from metrics_b200.functional.classification.ratio_metrics import (  # noqa: F401,E402
+    binary_hamming_distance,
+    binary_negative_predictive_value,
+    binary_precision,
+    binary_recall,
+    binary_specificity,
+    hamming_distance,
+    multiclass_hamming_distance,
+    multiclass_negative_predictive_value,
+    multiclass_precision,
+    multiclass_recall,
+    multiclass_specificity,
+    multilabel_hamming_distance,
+    multilabel_negative_predictive_value,
+    multilabel_precision,
+    multilabel_recall,
+    multilabel_specificity,
+    negative_predictive_value,
+    precision,
+    recall,
+    specificity,
+)
+from metrics_b200.functional.classification.confmat_metrics import (  # noqa: F401,E402
+    binary_cohen_kappa,
+    binary_jaccard_index,
+    binary_matthews_corrcoef,
+    multiclass_cohen_kappa,
+    multiclass_jaccard_index,
+    multiclass_matthews_corrcoef,
+    multilabel_jaccard_index,
+    multilabel_matthews_corrcoef,
+)

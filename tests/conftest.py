@@ -65,3 +65,10 @@ def golden_multilabel():
     import numpy as np
 
     return np.load(os.path.join(GOLDEN_DIR, "multilabel.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_consumers():
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN_DIR, "consumers.npz"), allow_pickle=False)

@@ -589,6 +589,129 @@ def multilabel_golden() -> dict:
     return out
 
 
+def consumers_golden() -> dict:
+    """Stat-score / confusion-matrix consumer metrics (Precision, Recall, Specificity, NPV, Hamming, Jaccard, CohenKappa,
+    MatthewsCorrCoef) from the unmodified reference, on inputs shared with the product tests."""
+    import warnings
+
+    import torchmetrics.classification as TC
+    import torchmetrics.functional.classification as F
+
+    warnings.simplefilter("ignore")
+    out: dict = {}
+    g = torch.Generator().manual_seed(91)
+    # binary
+    bp = torch.rand(700, generator=g)
+    bt = torch.randint(0, 2, (700,), generator=g)
+    bt_good = ((bp + 0.35 * torch.randn(700, generator=g)) > 0.5).long()  # correlated with preds
+    bti = bt_good.clone()
+    bti[::11] = -1
+    bp_multi = torch.rand(30, 4, 5, generator=g)
+    bt_multi = torch.randint(0, 2, (30, 4, 5), generator=g)
+    out["b/preds"], out["b/target"], out["b/target_good"], out["b/target_ign"] = bp.numpy(), bt.numpy(), bt_good.numpy(), bti.numpy()
+    out["b/preds_multi"], out["b/target_multi"] = bp_multi.numpy(), bt_multi.numpy()
+    # multiclass
+    C = 7
+    ml = torch.randn(900, C, generator=g)
+    mt = torch.randint(0, C, (900,), generator=g)
+    mt[mt == 6] = 1  # class 6 never a target
+    ml[torch.arange(900), mt] += 1.2  # informative
+    ml[:, 5] -= 50  # class 5 never predicted
+    mti = mt.clone()
+    mti[::9] = -1
+    ml_multi = torch.randn(20, C, 6, generator=g)
+    mt_multi = torch.randint(0, C, (20, 6), generator=g)
+    out["mc/logits"], out["mc/target"], out["mc/target_ign"] = ml.numpy(), mt.numpy(), mti.numpy()
+    out["mc/logits_multi"], out["mc/target_multi"] = ml_multi.numpy(), mt_multi.numpy()
+    # multilabel
+    L = 5
+    lp = torch.rand(600, L, generator=g)
+    lt = ((lp + 0.4 * torch.randn(600, L, generator=g)) > 0.5).long()
+    lt[:, 4] = 0  # label 4 never positive
+    lti = lt.clone()
+    lti.view(-1)[::13] = -1
+    lp_multi = torch.rand(25, L, 4, generator=g)
+    lt_multi = torch.randint(0, 2, (25, L, 4), generator=g)
+    out["ml/preds"], out["ml/target"], out["ml/target_ign"] = lp.numpy(), lt.numpy(), lti.numpy()
+    out["ml/preds_multi"], out["ml/target_multi"] = lp_multi.numpy(), lt_multi.numpy()
+
+    ratio = ("precision", "recall", "specificity", "negative_predictive_value", "hamming_distance")
+    zd_kinds = ("precision", "recall", "negative_predictive_value")
+    for kind in ratio:
+        fb, fm, fl = getattr(F, f"binary_{kind}"), getattr(F, f"multiclass_{kind}"), getattr(F, f"multilabel_{kind}")
+        out[f"b/{kind}"] = fb(bp, bt_good).numpy()
+        out[f"b/{kind}_ign"] = fb(bp, bti, ignore_index=-1).numpy()
+        out[f"b/{kind}_thr0.8"] = fb(bp, bt_good, threshold=0.8).numpy()
+        out[f"b/{kind}_samplewise"] = fb(bp_multi, bt_multi, multidim_average="samplewise").numpy()
+        for avg in ("micro", "macro", "weighted", "none"):
+            out[f"mc/{kind}_{avg}"] = fm(ml, mt, C, average=avg).numpy()
+            out[f"mc/{kind}_{avg}_ign"] = fm(ml, mti, C, average=avg, ignore_index=-1).numpy()
+            out[f"mc/{kind}_{avg}_top2"] = fm(ml, mt, C, average=avg, top_k=2).numpy()
+            out[f"mc/{kind}_{avg}_samplewise"] = fm(ml_multi, mt_multi, C, average=avg, multidim_average="samplewise").numpy()
+            out[f"ml/{kind}_{avg}"] = fl(lp, lt, L, average=avg).numpy()
+            out[f"ml/{kind}_{avg}_ign"] = fl(lp, lti, L, average=avg, ignore_index=-1).numpy()
+            out[f"ml/{kind}_{avg}_samplewise"] = fl(lp_multi, lt_multi, L, average=avg, multidim_average="samplewise").numpy()
+            if kind in zd_kinds:
+                out[f"mc/{kind}_{avg}_zd1"] = fm(ml, mt, C, average=avg, zero_division=1).numpy()
+                out[f"ml/{kind}_{avg}_zd1"] = fl(lp, lt, L, average=avg, zero_division=1).numpy()
+    for avg in ("micro", "macro", "weighted", "none"):
+        out[f"mc/jaccard_{avg}"] = F.multiclass_jaccard_index(ml, mt, C, average=avg).numpy()
+        out[f"mc/jaccard_{avg}_ign"] = F.multiclass_jaccard_index(ml, mti, C, average=avg, ignore_index=-1).numpy()
+        out[f"mc/jaccard_{avg}_ign2"] = F.multiclass_jaccard_index(ml, mt, C, average=avg, ignore_index=2).numpy()
+        out[f"mc/jaccard_{avg}_zd1"] = F.multiclass_jaccard_index(ml, mt, C, average=avg, zero_division=1.0).numpy()
+        out[f"ml/jaccard_{avg}"] = F.multilabel_jaccard_index(lp, lt, L, average=avg).numpy()
+        out[f"ml/jaccard_{avg}_ign"] = F.multilabel_jaccard_index(lp, lti, L, average=avg, ignore_index=-1).numpy()
+    out["b/jaccard"] = F.binary_jaccard_index(bp, bt_good).numpy()
+    out["b/jaccard_ign"] = F.binary_jaccard_index(bp, bti, ignore_index=-1).numpy()
+    for w in ("none", "linear", "quadratic"):
+        out[f"b/kappa_{w}"] = F.binary_cohen_kappa(bp, bt_good, weights=w).numpy()
+        out[f"mc/kappa_{w}"] = F.multiclass_cohen_kappa(ml, mt, C, weights=w).numpy()
+        out[f"mc/kappa_{w}_ign"] = F.multiclass_cohen_kappa(ml, mti, C, weights=w, ignore_index=-1).numpy()
+    out["b/mcc"] = F.binary_matthews_corrcoef(bp, bt_good).numpy()
+    out["b/mcc_rand"] = F.binary_matthews_corrcoef(bp, bt).numpy()
+    out["b/mcc_ign"] = F.binary_matthews_corrcoef(bp, bti, ignore_index=-1).numpy()
+    out["b/mcc_perfect"] = F.binary_matthews_corrcoef((bt > 0).float(), bt).numpy()
+    out["b/mcc_inverse"] = F.binary_matthews_corrcoef((bt == 0).float(), bt).numpy()
+    out["b/mcc_allpos_pred"] = F.binary_matthews_corrcoef(torch.ones(700), bt).numpy()
+    out["b/mcc_allneg_target"] = F.binary_matthews_corrcoef(bp, torch.zeros(700, dtype=torch.long)).numpy()
+    out["mc/mcc"] = F.multiclass_matthews_corrcoef(ml, mt, C).numpy()
+    out["mc/mcc_ign"] = F.multiclass_matthews_corrcoef(ml, mti, C, ignore_index=-1).numpy()
+    out["mc/mcc_const"] = F.multiclass_matthews_corrcoef(torch.zeros(50, dtype=torch.long), torch.zeros(50, dtype=torch.long), C).numpy()
+    out["ml/mcc"] = F.multilabel_matthews_corrcoef(lp, lt, L).numpy()
+    out["ml/mcc_ign"] = F.multilabel_matthews_corrcoef(lp, lti, L, ignore_index=-1).numpy()
+    # modular: 3 updates each
+    mods = {
+        "MulticlassPrecision": TC.MulticlassPrecision(num_classes=C, average="macro"),
+        "MulticlassRecall_top2": TC.MulticlassRecall(num_classes=C, average="weighted", top_k=2),
+        "MulticlassSpecificity": TC.MulticlassSpecificity(num_classes=C, average="none"),
+        "MulticlassHammingDistance": TC.MulticlassHammingDistance(num_classes=C, average="micro"),
+        "MulticlassJaccardIndex": TC.MulticlassJaccardIndex(num_classes=C),
+        "MulticlassCohenKappa": TC.MulticlassCohenKappa(num_classes=C, weights="linear"),
+        "MulticlassMatthewsCorrCoef": TC.MulticlassMatthewsCorrCoef(num_classes=C),
+    }
+    for name, m in mods.items():
+        for a, b in zip(ml.chunk(3), mt.chunk(3)):
+            m.update(a, b)
+        out[f"class/{name}"] = m.compute().numpy()
+    mods = {
+        "MultilabelPrecision": TC.MultilabelPrecision(num_labels=L, average="macro"),
+        "MultilabelNegativePredictiveValue": TC.MultilabelNegativePredictiveValue(num_labels=L, average="none"),
+        "MultilabelJaccardIndex": TC.MultilabelJaccardIndex(num_labels=L, average="weighted"),
+        "MultilabelMatthewsCorrCoef": TC.MultilabelMatthewsCorrCoef(num_labels=L),
+    }
+    for name, m in mods.items():
+        for a, b in zip(lp.chunk(3), lt.chunk(3)):
+            m.update(a, b)
+        out[f"class/{name}"] = m.compute().numpy()
+    mods = {"BinaryRecall": TC.BinaryRecall(), "BinaryCohenKappa": TC.BinaryCohenKappa(), "BinaryJaccardIndex": TC.BinaryJaccardIndex(),
+            "BinaryMatthewsCorrCoef": TC.BinaryMatthewsCorrCoef(), "BinaryHammingDistance": TC.BinaryHammingDistance()}
+    for name, m in mods.items():
+        for a, b in zip(bp.chunk(3), bt_good.chunk(3)):
+            m.update(a, b)
+        out[f"class/{name}"] = m.compute().numpy()
+    return out
+
+
 def regression_golden() -> dict:
     import torchmetrics.functional as TF
     import torchmetrics.regression as TR
@@ -658,6 +781,11 @@ if __name__ == "__main__":
     if "multilabel" in which:
         data = multilabel_golden()
         path = os.path.join(HERE, "multilabel.npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
+    if "consumers" in which:
+        data = consumers_golden()
+        path = os.path.join(HERE, "consumers.npz")
         np.savez_compressed(path, **data)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
     if "curves" in which:
