@@ -153,6 +153,76 @@ class MeanAveragePrecision(Metric):
             self.groundtruth_crowds.append(item.get("iscrowd", torch.zeros_like(item["labels"])))
             self.groundtruth_area.append(item.get("area", torch.zeros_like(item["labels"])))
 
+    # ------------------------------------------------------------------------------------------------
+    # cross-rank sync of the per-image list states
+    # ------------------------------------------------------------------------------------------------
+    def _sync_states_fast(self, group: Optional[Any]) -> bool:
+        """Default-sync fast path (called by ``Metric.sync`` when no ``dist_sync_fn`` was given).
+
+        The reference gathers the ``dist_reduce_fx=None`` list states one per-image tensor at a time — 7 collectives
+        (+ barrier + shape gather each) per image, and it dead-locks unless every rank holds the same number of images
+        (metric.py:501-540 as reached from detection/mean_ap.py:1031-1043).  Here every rank packs its seven flat arrays
+        and the per-image counts into ONE byte buffer: two collectives in total (sizes, payload), ragged image counts
+        allowed.  Afterwards the states are per-image lists again, images interleaved rank by rank exactly like the
+        reference's ``_flatten`` of per-image gathers (image i of rank 0, image i of rank 1, ...).
+        """
+        from metrics_b200.parallel_sync import _gather_equal
+
+        dist = torch.distributed
+        group = group or dist.group.WORLD
+        world = dist.get_world_size(group)
+        dev = self.device
+        n_img = len(self.detection_labels)
+        det_counts = [int(t.shape[0]) for t in self.detection_labels]
+        gt_counts = [int(t.shape[0]) for t in self.groundtruth_labels]
+        n_det, n_gt = sum(det_counts), sum(gt_counts)
+        # 8-byte fields first so that every field starts 8-byte aligned inside the row
+        fields = [
+            self._cat_or_empty(self.detection_labels, (0,), torch.int64, dev),
+            self._cat_or_empty(self.groundtruth_labels, (0,), torch.int64, dev),
+            self._cat_or_empty(self.groundtruth_crowds, (0,), torch.int64, dev),
+            self._cat_or_empty(self.groundtruth_area, (0,), torch.float64, dev),
+            torch.tensor(det_counts + gt_counts, dtype=torch.int64, device=dev),
+            self._cat_or_empty(self.detection_box, (0, 4), torch.float32, dev),
+            self._cat_or_empty(self.groundtruth_box, (0, 4), torch.float32, dev),
+            self._cat_or_empty(self.detection_scores, (0,), torch.float32, dev),
+        ]
+        payload = torch.cat([f.contiguous().reshape(-1).view(torch.uint8) for f in fields])
+        sizes = _gather_equal(torch.tensor([n_img, n_det, n_gt], dtype=torch.int64, device=dev), group, world).tolist()
+        row_bytes = max(8 * (nd + 3 * ng + 2 * ni) + 16 * (nd + ng) + 4 * nd for ni, nd, ng in sizes)
+        row_bytes = (row_bytes + 15) // 16 * 16
+        if row_bytes == 0:
+            return True
+        row = torch.zeros(row_bytes, dtype=torch.uint8, device=dev)
+        row[: payload.numel()] = payload
+        rows = _gather_equal(row, group, world)
+
+        per_rank = []
+        for r, (ni, nd, ng) in enumerate(sizes):
+            buf, off = rows[r], 0
+
+            def take(count: int, dtype: torch.dtype, width: int = 1) -> Tensor:
+                nonlocal off
+                nbytes = count * width * torch.empty((), dtype=dtype).element_size()
+                out = buf[off:off + nbytes].view(dtype)
+                off += nbytes
+                return out.reshape(count, width) if width > 1 else out
+
+            det_label, gt_label, gt_crowd, gt_area = take(nd, torch.int64), take(ng, torch.int64), take(ng, torch.int64), take(ng, torch.float64)
+            counts = take(2 * ni, torch.int64).tolist()
+            det_box, gt_box, det_score = take(nd, torch.float32, 4), take(ng, torch.float32, 4), take(nd, torch.float32)
+            dc, gc = counts[:ni], counts[ni:]
+            per_rank.append({
+                "detection_box": det_box.split(dc), "detection_scores": det_score.split(dc), "detection_labels": det_label.split(dc),
+                "groundtruth_box": gt_box.split(gc), "groundtruth_labels": gt_label.split(gc),
+                "groundtruth_crowds": gt_crowd.split(gc), "groundtruth_area": gt_area.split(gc),
+            })
+        max_img = max(ni for ni, _, _ in sizes)
+        for name in ("detection_box", "detection_scores", "detection_labels", "groundtruth_box", "groundtruth_labels",
+                     "groundtruth_crowds", "groundtruth_area"):
+            setattr(self, name, [per_rank[r][name][i] for i in range(max_img) for r in range(world) if i < sizes[r][0]])
+        return True
+
     def _get_classes(self) -> List[int]:
         if len(self.detection_labels) > 0 or len(self.groundtruth_labels) > 0:
             return torch.cat(self.detection_labels + self.groundtruth_labels).unique().cpu().tolist()

@@ -494,7 +494,10 @@ class Metric(Module, ABC):
         self._cache = {name: getattr(self, name) for name in self._defaults}
         self._cache = {k: (list(v) if isinstance(v, list) else v) for k, v in self._cache.items()}
 
-        if dist_sync_fn is None:
+        fast = getattr(self, "_sync_states_fast", None)  # metric-specific exchange (e.g. mAP's per-image list states)
+        if dist_sync_fn is None and fast is not None and fast(process_group or self.process_group):
+            pass
+        elif dist_sync_fn is None:
             from metrics_b200.parallel_sync import sync_states_bucketed
 
             if not sync_states_bucketed(self, process_group or self.process_group):

@@ -61,6 +61,29 @@ def main():
             # same keys, same integer scan, same fp64 reduction order per class: bit-identical to both baselines
             assert torch.equal(a.nan_to_num(7.0), t.nan_to_num(7.0)), (k, seed, a, t)
             assert torch.equal(b.nan_to_num(7.0), t.nan_to_num(7.0)), (k, seed, b, t)
+    # ---- mAP under DDP: packed ragged exchange of the per-image list states, then the device evaluation ----------------------
+    from metrics_b200.detection import MeanAveragePrecision
+    from tests.helpers import synth_detection
+
+    n_imgs = [6 + 2 * r for r in range(world)]
+    shards = [synth_detection(seed=70 + r, n_img=n_imgs[r], n_gt=6, n_det=12, n_cls=5, crowd_frac=0.1, dup_scores=True)
+              for r in range(world)]
+
+    def to_dev(items):
+        return [{k: v.to(dev) for k, v in d.items()} for d in items]
+
+    m = MeanAveragePrecision(class_metrics=True).to(dev)
+    m.update(to_dev(shards[rank][0]), to_dev(shards[rank][1]))
+    got = m.compute()
+    one = MeanAveragePrecision(class_metrics=True, sync_on_compute=False).to(dev)
+    for i in range(max(n_imgs)):  # the interleaved image order of the synced state
+        for r in range(world):
+            if i < n_imgs[r]:
+                one.update(to_dev(shards[r][0][i:i + 1]), to_dev(shards[r][1][i:i + 1]))
+    truth = one.compute()
+    for k in truth:
+        assert torch.equal(got[k].cpu(), truth[k].cpu()), (k, got[k], truth[k])
+    assert len(m.detection_box) == n_imgs[rank]  # unsynced again
     torch.distributed.barrier()
     if rank == 0:
         print("SHARDED_OK")

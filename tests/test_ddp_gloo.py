@@ -128,6 +128,32 @@ def _scenarios(rank: int) -> None:
     mc.update(float(rank + 1))
     res = mc.compute()
     assert float(res["a"]) == 3.0 and float(res["b"]) == 1.5
+    # ---- mAP: per-image list states, ragged image counts per rank, one packed exchange ---------------------------------------
+    from metrics_b200.detection import MeanAveragePrecision
+    from tests.helpers import synth_detection
+
+    n_mine = 3 if rank == 0 else 2
+    shards = [synth_detection(seed=40 + r, n_img=3 if r == 0 else 2, n_gt=3, n_det=5, n_cls=4, crowd_frac=0.3) for r in range(WORLD)]
+    preds, target = shards[rank]
+    target[0]["area"] = torch.tensor([10.0, 20.0, 30.0])  # explicit area on one image, default elsewhere
+    mp_ = MeanAveragePrecision()
+    mp_.update(preds[:2], target[:2])
+    mp_.update(preds[2:], target[2:])
+    local_boxes = [b.clone() for b in mp_.detection_box]
+    mp_.sync()
+    assert len(mp_.detection_box) == 5 == len(mp_.groundtruth_area) == len(mp_.detection_scores)
+    order = [(0, 0), (1, 0), (0, 1), (1, 1), (0, 2)]  # (rank, image): interleaved like the reference's per-image gathers
+    for pos, (r, i) in enumerate(order):
+        exp_p, exp_t = shards[r]
+        assert torch.equal(mp_.detection_scores[pos], exp_p[i]["scores"])
+        assert torch.equal(mp_.detection_labels[pos], exp_p[i]["labels"])
+        assert torch.equal(mp_.groundtruth_labels[pos], exp_t[i]["labels"])
+        assert torch.equal(mp_.groundtruth_crowds[pos], exp_t[i]["iscrowd"].to(torch.int64))
+        assert tuple(mp_.detection_box[pos].shape) == (5, 4) and tuple(mp_.groundtruth_box[pos].shape) == (3, 4)
+    assert mp_.groundtruth_area[0].tolist() == [10.0, 20.0, 30.0] and mp_.groundtruth_area[1].tolist() == [10.0, 20.0, 30.0]
+    assert mp_.groundtruth_area[2].tolist() == [0.0, 0.0, 0.0]
+    mp_.unsync()
+    assert len(mp_.detection_box) == n_mine and all(torch.equal(a, b) for a, b in zip(mp_.detection_box, local_boxes))
     dist.barrier()
 
 
