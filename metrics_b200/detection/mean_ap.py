@@ -139,7 +139,7 @@ class MeanAveragePrecision(Metric):
         for boxes_list, store in (([_fix_empty_tensors(p["boxes"]) for p in preds], self.detection_box),
                                   ([_fix_empty_tensors(t["boxes"]) for t in target], self.groundtruth_box)):
             counts = [b.shape[0] if b.numel() > 0 else 0 for b in boxes_list]
-            nonempty = [b.reshape(-1, 4) for b in boxes_list if b.numel() > 0]
+            nonempty = [b if b.ndim == 2 else b.reshape(-1, 4) for b in boxes_list if b.numel() > 0]
             if nonempty:
                 converted = _box_convert_to_xywh(torch.cat(nonempty), self.box_format)
                 pieces = iter(converted.split([c for c in counts if c > 0]))
@@ -148,10 +148,21 @@ class MeanAveragePrecision(Metric):
         for item in preds:
             self.detection_labels.append(item["labels"])
             self.detection_scores.append(item["scores"])
-        for item in target:
-            self.groundtruth_labels.append(item["labels"])
-            self.groundtruth_crowds.append(item.get("iscrowd", torch.zeros_like(item["labels"])))
-            self.groundtruth_area.append(item.get("area", torch.zeros_like(item["labels"])))
+        # defaults for missing `iscrowd` / `area` (reference :518: zeros_like(labels) per image): ONE zero buffer per call,
+        # handed out as per-image views — a launch per image would dominate the whole update otherwise
+        zero_views = None
+        if target and any("iscrowd" not in t or "area" not in t for t in target):
+            first = target[0]["labels"]
+            zero_views = torch.zeros(sum(int(t["labels"].shape[0]) for t in target), dtype=first.dtype,
+                                     device=first.device).split([int(t["labels"].shape[0]) for t in target])
+        for i, item in enumerate(target):
+            labels = item["labels"]
+            self.groundtruth_labels.append(labels)
+            default = None
+            if zero_views is not None:
+                default = zero_views[i] if (labels.dtype == zero_views[i].dtype and labels.ndim == 1) else torch.zeros_like(labels)
+            self.groundtruth_crowds.append(item["iscrowd"] if "iscrowd" in item else default)
+            self.groundtruth_area.append(item["area"] if "area" in item else default)
 
     # ------------------------------------------------------------------------------------------------
     # cross-rank sync of the per-image list states
@@ -230,10 +241,19 @@ class MeanAveragePrecision(Metric):
 
     @staticmethod
     def _cat_or_empty(items: List[Tensor], shape: Tuple[int, ...], dtype: torch.dtype, device: torch.device) -> Tensor:
-        items = [t.reshape(-1, *shape[1:]) for t in items if t.numel() > 0]
+        """One flat ``[total, *shape[1:]]`` tensor from the per-image list (empty images contribute nothing)."""
         if not items:
             return torch.empty(shape, dtype=dtype, device=device)
-        return torch.cat(items).to(dtype)
+        try:  # common case: every entry already has the right trailing shape -> no per-image Python work
+            flat = torch.cat(items)
+            if flat.ndim != len(shape):
+                raise RuntimeError("rank mismatch")
+        except RuntimeError:
+            items = [t.reshape(-1, *shape[1:]) for t in items if t.numel() > 0]
+            if not items:
+                return torch.empty(shape, dtype=dtype, device=device)
+            flat = torch.cat(items)
+        return flat.to(dtype)
 
     def _stats_dict(self, stats: List[Tensor]) -> Dict[str, Tensor]:
         mdt = self.max_detection_thresholds
