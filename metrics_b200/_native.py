@@ -113,8 +113,28 @@ def ptr(t: Optional[Tensor]) -> ctypes.c_void_p:
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_handle(device: torch.device) -> ctypes.c_void_p:
+    """``cudaStream_t`` of torch's current stream on ``device`` (raw-pointer query: no Stream object per launch)."""
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(device.index if device.index is not None else torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+_flag_words: dict = {}
+
+
+def _flag_scratch(device: torch.device, stream: ctypes.c_void_p) -> Tensor:
+    """4-byte device word for the batch-global "are these logits?" vote, one per (device, stream): launches on one stream
+    are ordered, so consecutive format calls can share it; different streams never do."""
+    key = (device.index, stream.value)
+    t = _flag_words.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=device)
+        _flag_words[key] = t
+    return t
 
 
 def i64(v: int) -> ctypes.c_int64:
@@ -218,10 +238,12 @@ def sigmoid_if_logits(preds: Tensor) -> Tensor:
     out = torch.empty_like(preds)
     if preds.numel() == 0:
         return out
-    flag = torch.empty(1, dtype=torch.int32, device=dev)
+    st = stream_handle(dev)
     with on_device(dev):
-        rc = lib().mb200_curve_sigmoid_if_logits(ptr(preds), tag(preds), i64(preds.numel()), ptr(out), ptr(flag), stream_handle(dev))
-    check(rc, "curve_sigmoid_if_logits")
+        rc = lib().mb200_curve_sigmoid_if_logits(ptr(preds), tag(preds), i64(preds.numel()), ptr(out),
+                                                 ptr(_flag_scratch(dev, st)), st)
+    if rc != 0:
+        check(rc, "curve_sigmoid_if_logits")
     return out
 
 
@@ -234,10 +256,10 @@ def softmax_if_logits(preds: Tensor) -> Tensor:
         return out
     if preds.dtype == torch.float64:
         raise NotImplementedError("metrics_b200: float64 scores are not supported by the multiclass curve kernels")
-    flag = torch.empty(1, dtype=torch.int32, device=dev)
+    st = stream_handle(dev)
     with on_device(dev):
         rc = lib().mb200_curve_softmax_if_logits(
-            ptr(preds), tag(preds), i64(preds.shape[0]), i64(preds.shape[1]), ptr(out), ptr(flag), stream_handle(dev)
+            ptr(preds), tag(preds), i64(preds.shape[0]), i64(preds.shape[1]), ptr(out), ptr(_flag_scratch(dev, st)), st
         )
     check(rc, "curve_softmax_if_logits")
     return out

@@ -97,6 +97,46 @@ __global__ void __launch_bounds__(256) sigmoid_if_kernel<double>(const double* _
         out[i] = apply ? 1.0 / (1.0 + exp(-x[i])) : x[i];
 }
 
+// Small batches (n <= 1024 * kSmallItems): ONE CTA holds the whole batch in registers, votes with __syncthreads_or and
+// writes the result — one launch instead of memset + flag kernel + apply kernel (cfg3: 10 000 scores per update; the
+// launch sequence, not the 40 KB of traffic, is what an update costs).
+constexpr int kSmallItems = 32;
+constexpr int kSmallItemsF64 = 12;
+template <typename T, int kItems>
+__global__ void __launch_bounds__(1024) sigmoid_if_small_kernel(const T* __restrict__ x, T* __restrict__ out, int n) {
+    constexpr int kSmallItems = kItems;
+    T v[kSmallItems];
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < kSmallItems; ++k) {
+        const int i = k * 1024 + threadIdx.x;
+        if (i < n) {
+            v[k] = x[i];
+            if constexpr (sizeof(T) == 8) {
+                const double d = (double)v[k];
+                bad |= (d < 0.0) | (d > 1.0);
+            } else {
+                const float f = to_float<T>(v[k]);
+                bad |= (f < 0.f) | (f > 1.f);
+            }
+        }
+    }
+    const bool apply = __syncthreads_or(bad) != 0;
+#pragma unroll
+    for (int k = 0; k < kSmallItems; ++k) {
+        const int i = k * 1024 + threadIdx.x;
+        if (i < n) {
+            if (!apply) {
+                out[i] = v[k];
+            } else if constexpr (sizeof(T) == 8) {
+                out[i] = (T)(1.0 / (1.0 + exp(-(double)v[k])));
+            } else {
+                out[i] = from_float<T>(1.0f / (1.0f + expf(-to_float<T>(v[k]))));
+            }
+        }
+    }
+}
+
 // Row softmax over [N, C] when the batch flag is set (utilities/compute.py:226-229 with normalization="softmax").
 // One warp per row, values staged in registers chunk-wise; fp32 math.
 template <typename T>
@@ -575,6 +615,17 @@ extern "C" int mb200_curve_sigmoid_if_logits(const void* preds, int dtype, int64
     if (n == 0) return 0;
     MB200_REQUIRE(preds && out && flag_scratch, "NULL pointer");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (n <= 1024 * (dtype == MB200_F64 ? kSmallItemsF64 : kSmallItems)) {
+        switch (dtype) {
+            case MB200_F32: sigmoid_if_small_kernel<float, kSmallItems><<<1, 1024, 0, st>>>((const float*)preds, (float*)out, (int)n); break;
+            case MB200_F16: sigmoid_if_small_kernel<__half, kSmallItems><<<1, 1024, 0, st>>>((const __half*)preds, (__half*)out, (int)n); break;
+            case MB200_BF16: sigmoid_if_small_kernel<__nv_bfloat16, kSmallItems><<<1, 1024, 0, st>>>((const __nv_bfloat16*)preds, (__nv_bfloat16*)out, (int)n); break;
+            case MB200_F64: sigmoid_if_small_kernel<double, kSmallItemsF64><<<1, 1024, 0, st>>>((const double*)preds, (double*)out, (int)n); break;
+            default: set_error("scores must be floating point (dtype tag %d)", dtype); return MB200_ERR_INVALID;
+        }
+        count_launch();
+        return check_cuda(cudaGetLastError(), "curve format launch");
+    }
     MB200_CUDA_OK(cudaMemsetAsync(flag_scratch, 0, sizeof(uint32_t), st));
     const int grid = blocks_for(n, 256 * 8, sm_count() * 8);
 #define MB200_FMT(T)                                                                                             \

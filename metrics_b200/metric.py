@@ -56,6 +56,8 @@ _CONST_ATTRS = (
     "plot_upper_bound",
     "plot_legend_name",
 )
+_PLAIN_HOT_ATTRS = frozenset(("_computed", "_update_count", "_forward_cache", "_to_sync", "_should_unsync", "_enable_grad",
+                              "_is_synced", "_cache", "_sharded_now"))
 _BOOL_KWARGS = (
     ("compute_on_cpu", False, "an `bool`"),
     ("dist_sync_on_step", False, "an `bool`"),
@@ -553,6 +555,9 @@ class Metric(Module, ABC):
         self._install_wrappers()
 
     def __setattr__(self, name: str, value: Any) -> None:
+        if name in _PLAIN_HOT_ATTRS:  # per-call bookkeeping: skip nn.Module's parameter / buffer / module triage
+            object.__setattr__(self, name, value)
+            return
         if name in _CONST_ATTRS:
             raise RuntimeError(f"Can't change const `{name}`.")
         super().__setattr__(name, value)
@@ -663,6 +668,8 @@ class Metric(Module, ABC):
 
     def _filter_kwargs(self, **kwargs: Any) -> Dict[str, Any]:
         """Keep only the kwargs that ``update`` can take (used by ``MetricCollection``)."""
+        if not kwargs:
+            return kwargs
         params = self._update_signature.parameters
         variadic = (inspect.Parameter.VAR_POSITIONAL, inspect.Parameter.VAR_KEYWORD)
         if any(p.kind == inspect.Parameter.VAR_KEYWORD for p in params.values()):
