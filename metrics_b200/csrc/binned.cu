@@ -91,9 +91,10 @@ __global__ void __launch_bounds__(256) binned_bucket_kernel(const T* __restrict_
         unsigned long long ge = tot;  // samples with k > i, starting at i = -1
         for (int i = 0; i < nthr; ++i) {
             ge -= __ldcg(row + i);  // now: samples with k > i  <=>  score >= thr[i]
-            long long* cell = confmat + (((size_t)i * C + c) * 2 + y) * 2;
-            cell[1] += (long long)ge;
-            cell[0] += (long long)(tot - ge);
+            // fire-and-forget REDs: a load-add-store here would chain one L2 round trip per threshold
+            unsigned long long* cell = reinterpret_cast<unsigned long long*>(confmat + (((size_t)i * C + c) * 2 + y) * 2);
+            if (ge) atomicAdd(cell + 1, ge);
+            if (tot - ge) atomicAdd(cell + 0, tot - ge);
         }
         for (int k = 0; k <= nthr; ++k) row[k] = 0ull;
     }

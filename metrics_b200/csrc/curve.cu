@@ -60,8 +60,26 @@ __device__ __forceinline__ float score_of_key(unsigned k) {
 template <typename T>
 __global__ void __launch_bounds__(256) range_flag_kernel(const T* __restrict__ x, long long n, unsigned* flag) {
     bool bad = false;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float v = to_float<T>(x[i]);
+    constexpr int kVec = 16 / (int)sizeof(T);
+    // 16-byte streaming loads over the aligned body, scalar head / tail
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(x);
+    long long head = (long long)(((16 - (addr & 15)) & 15) / sizeof(T));
+    if (head > n) head = n;
+    const long long nvec = (n - head) / kVec;
+    const uint4* __restrict__ xv = reinterpret_cast<const uint4*>(x + head);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 q = ld_stream16(xv + i);
+        const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+        for (int k = 0; k < kVec; ++k) {
+            const float v = to_float<T>(e[k]);
+            bad |= (v < 0.f) | (v > 1.f);
+        }
+    }
+    const long long tail0 = head + nvec * kVec;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < head + (n - tail0); i += (long long)gridDim.x * blockDim.x) {
+        const long long j = i < head ? i : tail0 + (i - head);
+        const float v = to_float<T>(x[j]);
         bad |= (v < 0.f) | (v > 1.f);
     }
     if (__any_sync(kFull, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);

@@ -131,25 +131,23 @@ struct StatsSink {
         if (micro) {
             if (threadIdx.x == 0) {
                 const long long m = __ldcg(ws + 0), mm = __ldcg(ws + 1);
-                tp[0] += m;
-                fp[0] += mm;
-                fn[0] += mm;
-                tn[0] += (long long)C * n_valid - (m + 2 * mm);
+                red_add_u64(tp, (unsigned long long)m);
+                red_add_u64(fp, (unsigned long long)mm);
+                red_add_u64(fn, (unsigned long long)mm);
+                red_add_u64(tn, (unsigned long long)((long long)C * n_valid - (m + 2 * mm)));
                 vws[0] = 0;
                 vws[1] = 0;
             }
         } else {
+            // One CTA runs this while the rest of the GPU idles, so keep it to ONE memory round trip: read the deltas,
+            // then fire-and-forget 64-bit REDs into the states (a load-add-store per state would chain 3 more trips per
+            // class and made this tail 2/3 of a small update's duration).
             for (int c = threadIdx.x; c < C; c += blockDim.x) {
                 const long long a = __ldcg(ws + c), b = __ldcg(ws + C + c), d = __ldcg(ws + 2 * C + c);
-                if (a | b | d) {
-                    tp[c] += a;
-                    fp[c] += b;
-                    fn[c] += d;
-                    vws[c] = 0;
-                    vws[C + c] = 0;
-                    vws[2 * C + c] = 0;
-                }
-                tn[c] += n_valid - (a + b + d);
+                if (a) red_add_u64(tp + c, (unsigned long long)a), vws[c] = 0;
+                if (b) red_add_u64(fp + c, (unsigned long long)b), vws[C + c] = 0;
+                if (d) red_add_u64(fn + c, (unsigned long long)d), vws[2 * C + c] = 0;
+                red_add_u64(tn + c, (unsigned long long)(n_valid - (a + b + d)));
             }
         }
         __syncthreads();
