@@ -305,7 +305,8 @@ def _multilabel_stat_scores_update(
     if samplewise:
         c = c.reshape(preds.shape[0], num_labels, 4)
     tp, fp, tn, fn = c.unbind(-1)
-    return tp, fp, tn, fn
+    # the reference squeezes the counters (:709-712): a single sample in samplewise mode collapses to [L]
+    return tp.squeeze(), fp.squeeze(), tn.squeeze(), fn.squeeze()
 
 
 def _multilabel_stat_scores_compute(

@@ -72,3 +72,10 @@ def golden_consumers():
     import numpy as np
 
     return np.load(os.path.join(GOLDEN_DIR, "consumers.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_fuzz():
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN_DIR, "fuzz.npz"), allow_pickle=False)

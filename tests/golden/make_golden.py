@@ -712,6 +712,165 @@ def consumers_golden() -> dict:
     return out
 
 
+def fuzz_golden() -> dict:
+    """Randomised differential cases: random shapes / dtypes / ignore_index / averages through the reference's
+    functionals.  Each case k stores `k/spec` (JSON: functional name + kwargs), `k/preds`, `k/target` and `k/out*`."""
+    import json
+    import warnings
+
+    import torchmetrics.functional.classification as F
+
+    warnings.simplefilter("ignore")
+    out: dict = {}
+    rng = np.random.default_rng(2026)
+    g = torch.Generator().manual_seed(2026)
+    k = 0
+
+    def emit(name, kwargs, preds, target):
+        nonlocal k
+        try:
+            res = getattr(F, name)(preds, target, **kwargs)
+        except Exception as err:  # the reference itself cannot run this combination: not a parity case
+            print("skipped", name, kwargs, tuple(preds.shape), preds.dtype, type(err).__name__, str(err)[:60])
+            return
+        out[f"{k}/spec"] = np.array(json.dumps({"fn": name, "kwargs": kwargs, "preds_dtype": str(preds.dtype).replace("torch.", "")}))
+        out[f"{k}/preds"] = preds.float().numpy() if preds.dtype in (torch.bfloat16, torch.float16) else preds.numpy()
+        out[f"{k}/target"] = target.numpy()
+        if isinstance(res, (tuple, list)):
+            flat = []
+            for part in res:
+                flat.extend(part if isinstance(part, (tuple, list)) else [part])
+            out[f"{k}/n_out"] = np.array(len(flat))
+            for i, t in enumerate(flat):
+                out[f"{k}/out{i}"] = t.float().numpy() if t.dtype in (torch.bfloat16, torch.float16) else t.numpy()
+        else:
+            out[f"{k}/n_out"] = np.array(1)
+            out[f"{k}/out0"] = res.float().numpy() if res.dtype in (torch.bfloat16, torch.float16) else res.numpy()
+        k += 1
+
+    def pick(*xs):
+        return xs[int(rng.integers(len(xs)))]
+
+    # ---- multiclass: confusion matrix / stat scores / accuracy / f1 / precision / jaccard -------------------------------
+    for _ in range(36):
+        C = int(pick(2, 3, 5, 9, 17))
+        N = int(pick(1, 7, 64, 257))
+        extra = pick((), (), (3,), (2, 2))
+        kind = pick("logits", "logits", "probs", "labels")
+        dt = pick(torch.float32, torch.float32, torch.float16, torch.bfloat16, torch.float64)
+        ig = pick(None, None, -1, C - 1, 0)
+        # top_k > 1 cases get tie-free scores: which of two EQUAL maxima `torch.topk` lists first is implementation-defined
+        # (CPU and CUDA differ), so the reference has no single answer there; the kernels pick the lowest index like argmax
+        use_topk = kind != "labels" and C > 2 and not extra and rng.random() < 0.3
+        if kind == "labels":
+            preds = torch.randint(0, C, (N, *extra), generator=g)
+        else:
+            preds = torch.randn(N, C, *extra, generator=g)
+            if rng.random() < 0.4 and not use_topk:  # ties between classes
+                preds = (preds * 2).round() / 2
+            if kind == "probs":
+                preds = torch.softmax(preds, 1)
+            preds = preds.to(torch.float32 if use_topk else dt)
+        target = torch.randint(0, C, (N, *extra), generator=g)
+        if ig is not None:
+            mask = torch.rand(N, *extra, generator=g) < 0.2
+            target = torch.where(mask, torch.full_like(target, ig), target)
+        fn = pick("multiclass_confusion_matrix", "multiclass_stat_scores", "multiclass_accuracy", "multiclass_f1_score",
+                  "multiclass_precision", "multiclass_recall", "multiclass_jaccard_index", "multiclass_specificity")
+        kw = {"num_classes": C, "ignore_index": ig}
+        if fn == "multiclass_confusion_matrix":
+            kw["normalize"] = pick(None, None, "true", "pred", "all")
+        elif fn == "multiclass_jaccard_index":
+            kw["average"] = pick("micro", "macro", "weighted", "none")
+        else:
+            kw["average"] = pick("micro", "macro", "weighted", "none")
+            if use_topk:
+                kw["top_k"] = 2
+            if extra and rng.random() < 0.4:
+                kw["multidim_average"] = "samplewise"
+        emit(fn, kw, preds, target)
+    # ---- binary / multilabel counts ----------------------------------------------------------------------------------------
+    for _ in range(24):
+        ml = rng.random() < 0.5
+        L = int(pick(2, 3, 6))
+        N = int(pick(1, 9, 130))
+        extra = pick((), (), (4,))
+        shape = (N, L, *extra) if ml else (N, *extra)
+        kind = pick("probs", "logits", "labels")
+        ig = pick(None, None, -1)
+        if kind == "labels":
+            preds = torch.randint(0, 2, shape, generator=g)
+        elif kind == "probs":
+            preds = torch.rand(shape, generator=g).to(pick(torch.float32, torch.float16, torch.float64))
+        else:
+            preds = (torch.randn(shape, generator=g) * 3).to(pick(torch.float32, torch.bfloat16))
+        target = torch.randint(0, 2, shape, generator=g)
+        if ig is not None:
+            target = torch.where(torch.rand(shape, generator=g) < 0.2, torch.full_like(target, ig), target)
+        thr = float(pick(0.5, 0.5, 0.25, 0.8))
+        if ml:
+            fn = pick("multilabel_stat_scores", "multilabel_confusion_matrix", "multilabel_accuracy", "multilabel_f1_score",
+                      "multilabel_recall", "multilabel_hamming_distance", "multilabel_jaccard_index")
+            kw = {"num_labels": L, "threshold": thr, "ignore_index": ig}
+            if fn not in ("multilabel_confusion_matrix",):
+                kw["average"] = pick("micro", "macro", "weighted", "none")
+            if fn not in ("multilabel_confusion_matrix", "multilabel_jaccard_index") and extra and rng.random() < 0.5:
+                kw["multidim_average"] = "samplewise"
+        else:
+            fn = pick("binary_stat_scores", "binary_confusion_matrix", "binary_accuracy", "binary_f1_score", "binary_precision",
+                      "binary_specificity", "binary_matthews_corrcoef", "binary_cohen_kappa")
+            kw = {"threshold": thr, "ignore_index": ig}
+            if fn in ("binary_stat_scores", "binary_accuracy", "binary_f1_score", "binary_precision", "binary_specificity") \
+                    and extra and rng.random() < 0.5:
+                kw["multidim_average"] = "samplewise"
+        emit(fn, kw, preds, target)
+    # ---- curves ---------------------------------------------------------------------------------------------------------------
+    for _ in range(30):
+        task = pick("binary", "multiclass", "multilabel")
+        N = int(pick(2, 33, 400, 1500))
+        ig = pick(None, None, -1)
+        thresholds = pick(None, None, None, 7, [0.1, 0.5, 0.9])
+        ties = rng.random() < 0.4
+        logits = rng.random() < 0.4
+        dt = pick(torch.float32, torch.float32, torch.float16, torch.bfloat16)
+        if task == "binary":
+            preds = torch.randn(N, generator=g) * 2 if logits else torch.rand(N, generator=g)
+            target = torch.randint(0, 2, (N,), generator=g)
+            fn = pick("binary_auroc", "binary_average_precision", "binary_roc", "binary_precision_recall_curve")
+            kw = {}
+            if fn == "binary_auroc" and thresholds is None and rng.random() < 0.3:
+                kw["max_fpr"] = float(pick(0.3, 0.7))
+        elif task == "multiclass":
+            C = int(pick(3, 5, 11))
+            preds = torch.randn(N, C, generator=g)
+            if not logits:
+                preds = torch.softmax(preds, 1)
+            target = torch.randint(0, C, (N,), generator=g)
+            fn = pick("multiclass_auroc", "multiclass_average_precision", "multiclass_roc", "multiclass_precision_recall_curve")
+            kw = {"num_classes": C}
+            if fn in ("multiclass_auroc", "multiclass_average_precision"):
+                kw["average"] = pick("macro", "weighted", "none")
+        else:
+            L = int(pick(2, 4, 7))
+            preds = torch.randn(N, L, generator=g) * 2 if logits else torch.rand(N, L, generator=g)
+            target = torch.randint(0, 2, (N, L), generator=g)
+            fn = pick("multilabel_auroc", "multilabel_average_precision", "multilabel_roc", "multilabel_precision_recall_curve")
+            kw = {"num_labels": L}
+            if fn in ("multilabel_auroc", "multilabel_average_precision"):
+                kw["average"] = pick("micro", "macro", "weighted", "none")
+        if ties:
+            preds = (preds * 8).round() / 8
+            if not logits:
+                preds = preds.clamp(0, 1)
+        preds = preds.to(dt)
+        if ig is not None:
+            target = torch.where(torch.rand(target.shape, generator=g) < 0.15, torch.full_like(target, ig), target)
+        kw.update({"thresholds": thresholds, "ignore_index": ig})
+        emit(fn, kw, preds, target)
+    out["n_cases"] = np.array(k)
+    return out
+
+
 def regression_golden() -> dict:
     import torchmetrics.functional as TF
     import torchmetrics.regression as TR
@@ -786,6 +945,11 @@ if __name__ == "__main__":
     if "consumers" in which:
         data = consumers_golden()
         path = os.path.join(HERE, "consumers.npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
+    if "fuzz" in which:
+        data = fuzz_golden()
+        path = os.path.join(HERE, "fuzz.npz")
         np.savez_compressed(path, **data)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
     if "curves" in which:
