@@ -719,7 +719,9 @@ def fuzz_golden() -> dict:
     import warnings
 
     import torchmetrics.functional.classification as F
+    import torchmetrics.functional.regression as _FR
 
+    FR_holder = [_FR]
     warnings.simplefilter("ignore")
     out: dict = {}
     rng = np.random.default_rng(2026)
@@ -729,7 +731,7 @@ def fuzz_golden() -> dict:
     def emit(name, kwargs, preds, target):
         nonlocal k
         try:
-            res = getattr(F, name)(preds, target, **kwargs)
+            res = getattr(F if hasattr(F, name) else FR_holder[0], name)(preds, target, **kwargs)
         except Exception as err:  # the reference itself cannot run this combination: not a parity case
             print("skipped", name, kwargs, tuple(preds.shape), preds.dtype, type(err).__name__, str(err)[:60])
             return
@@ -867,6 +869,43 @@ def fuzz_golden() -> dict:
             target = torch.where(torch.rand(target.shape, generator=g) < 0.15, torch.full_like(target, ig), target)
         kw.update({"thresholds": thresholds, "ignore_index": ig})
         emit(fn, kw, preds, target)
+    # ---- regression ------------------------------------------------------------------------------------------------------------
+    import torchmetrics.functional.regression as FR
+
+    for _ in range(26):
+        fn = pick("mean_squared_error", "mean_absolute_error", "mean_absolute_percentage_error",
+                  "symmetric_mean_absolute_percentage_error", "weighted_mean_absolute_percentage_error",
+                  "mean_squared_log_error", "log_cosh_error", "minkowski_distance", "r2_score", "relative_squared_error",
+                  "explained_variance")
+        N = int(pick(2, 17, 300, 4097))
+        D = int(pick(1, 1, 3, 8))
+        dt = pick(torch.float32, torch.float32, torch.float64)
+        shape = (N,) if D == 1 else (N, D)
+        target = torch.randn(shape, generator=g).to(dt) * float(pick(1.0, 10.0))
+        preds = target + torch.randn(shape, generator=g).to(dt) * float(pick(0.1, 1.0))
+        kw = {}
+        if fn == "mean_squared_log_error":
+            preds, target = preds.abs(), target.abs()
+        if fn == "mean_squared_error":
+            kw = {"squared": bool(pick(True, False)), "num_outputs": D}
+        elif fn == "mean_absolute_error":
+            kw = {"num_outputs": D}
+        elif fn == "minkowski_distance":
+            kw = {"p": float(pick(1.0, 2.0, 3.5))}
+        elif fn == "r2_score":
+            kw = {"multioutput": pick("uniform_average", "raw_values", "variance_weighted")}
+            if N > 20 and rng.random() < 0.3:
+                kw["adjusted"] = 2
+        elif fn == "explained_variance":
+            kw = {"multioutput": pick("uniform_average", "raw_values", "variance_weighted")}
+        elif fn == "relative_squared_error":
+            kw = {"squared": bool(pick(True, False))}
+        kk = k
+        emit(fn, kw, preds, target)
+        if k > kk:
+            spec = json.loads(str(out[f"{kk}/spec"]))
+            spec["module"] = "regression"
+            out[f"{kk}/spec"] = np.array(json.dumps(spec))
     out["n_cases"] = np.array(k)
     return out
 
