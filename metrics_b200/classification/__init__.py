@@ -68,3 +68,21 @@ from metrics_b200.classification.confmat_metrics import (  # noqa: F401,E402
     MultilabelJaccardIndex,
     MultilabelMatthewsCorrCoef,
 )
+from metrics_b200.classification.at_fixed import (  # noqa: F401,E402
+    BinaryPrecisionAtFixedRecall,
+    BinaryRecallAtFixedPrecision,
+    BinarySensitivityAtSpecificity,
+    BinarySpecificityAtSensitivity,
+    MulticlassPrecisionAtFixedRecall,
+    MulticlassRecallAtFixedPrecision,
+    MulticlassSensitivityAtSpecificity,
+    MulticlassSpecificityAtSensitivity,
+    MultilabelPrecisionAtFixedRecall,
+    MultilabelRecallAtFixedPrecision,
+    MultilabelSensitivityAtSpecificity,
+    MultilabelSpecificityAtSensitivity,
+    PrecisionAtFixedRecall,
+    RecallAtFixedPrecision,
+    SensitivityAtSpecificity,
+    SpecificityAtSensitivity,
+)

@@ -66,3 +66,17 @@ from metrics_b200.functional.classification.confmat_metrics import (  # noqa: F4
     multilabel_jaccard_index,
     multilabel_matthews_corrcoef,
 )
+from metrics_b200.functional.classification.at_fixed import (  # noqa: F401,E402
+    binary_precision_at_fixed_recall,
+    binary_recall_at_fixed_precision,
+    binary_sensitivity_at_specificity,
+    binary_specificity_at_sensitivity,
+    multiclass_precision_at_fixed_recall,
+    multiclass_recall_at_fixed_precision,
+    multiclass_sensitivity_at_specificity,
+    multiclass_specificity_at_sensitivity,
+    multilabel_precision_at_fixed_recall,
+    multilabel_recall_at_fixed_precision,
+    multilabel_sensitivity_at_specificity,
+    multilabel_specificity_at_sensitivity,
+)

@@ -79,3 +79,10 @@ def golden_fuzz():
     import numpy as np
 
     return np.load(os.path.join(GOLDEN_DIR, "fuzz.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_atfixed():
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN_DIR, "atfixed.npz"), allow_pickle=False)

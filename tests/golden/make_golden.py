@@ -910,6 +910,61 @@ def fuzz_golden() -> dict:
     return out
 
 
+def atfixed_golden() -> dict:
+    """Operating-point metrics (recall@precision, precision@recall, sensitivity@specificity, specificity@sensitivity) from
+    the unmodified reference, exact and binned, on the multilabel / curves inputs regenerated here."""
+    import warnings
+
+    import torchmetrics.classification as TC
+    import torchmetrics.functional.classification as F
+
+    warnings.simplefilter("ignore")
+    out: dict = {}
+    g = torch.Generator().manual_seed(123)
+    bt = torch.randint(0, 2, (1500,), generator=g)
+    bp = (0.5 * torch.rand(1500, generator=g) + 0.35 * bt.float() + 0.1 * torch.rand(1500, generator=g)).clamp(0, 1)
+    bp = (bp * 64).round() / 64  # ties
+    bl = torch.randn(900, generator=g) * 2
+    C = 5
+    mt = torch.randint(0, C, (1200,), generator=g)
+    ml = torch.randn(1200, C, generator=g)
+    ml[torch.arange(1200), mt] += 1.0
+    L = 4
+    lt = torch.randint(0, 2, (800, L), generator=g)
+    lp = (torch.rand(800, L, generator=g) * 0.7 + 0.3 * lt.float() * torch.rand(800, L, generator=g)).clamp(0, 1)
+    lti = lt.clone()
+    lti.view(-1)[::9] = -1
+    for key, val in (("b/preds", bp), ("b/target", bt), ("b/logits", bl), ("mc/logits", ml), ("mc/target", mt),
+                     ("ml/preds", lp), ("ml/target", lt), ("ml/target_ign", lti)):
+        out[key] = val.numpy()
+    fams = (("recall_at_fixed_precision", "min_precision"), ("precision_at_fixed_recall", "min_recall"),
+            ("sensitivity_at_specificity", "min_specificity"), ("specificity_at_sensitivity", "min_sensitivity"))
+    for fam, arg in fams:
+        for floor in (0.0, 0.35, 0.6, 0.9, 1.0):
+            for tname, thr in (("exact", None), ("int21", 21), ("list", [0.2, 0.5, 0.8])):
+                tag = f"{fam}/{floor}/{tname}"
+                v, t = getattr(F, f"binary_{fam}")(bp, bt, **{arg: floor}, thresholds=thr)
+                out[f"b/{tag}/value"], out[f"b/{tag}/thr"] = v.numpy(), t.numpy()
+                v, t = getattr(F, f"binary_{fam}")(bl, bt[:900], **{arg: floor}, thresholds=thr)
+                out[f"bl/{tag}/value"], out[f"bl/{tag}/thr"] = v.numpy(), t.numpy()
+                v, t = getattr(F, f"multiclass_{fam}")(ml, mt, C, **{arg: floor}, thresholds=thr)
+                out[f"mc/{tag}/value"], out[f"mc/{tag}/thr"] = v.numpy(), t.numpy()
+                v, t = getattr(F, f"multilabel_{fam}")(lp, lt, L, **{arg: floor}, thresholds=thr)
+                out[f"ml/{tag}/value"], out[f"ml/{tag}/thr"] = v.numpy(), t.numpy()
+                v, t = getattr(F, f"multilabel_{fam}")(lp, lti, L, **{arg: floor}, thresholds=thr, ignore_index=-1)
+                out[f"mli/{tag}/value"], out[f"mli/{tag}/thr"] = v.numpy(), t.numpy()
+    # modular: three updates
+    m = TC.BinaryRecallAtFixedPrecision(min_precision=0.6)
+    m2 = TC.MulticlassSpecificityAtSensitivity(num_classes=C, min_sensitivity=0.5, thresholds=30)
+    for a, b in zip(bp.chunk(3), bt.chunk(3)):
+        m.update(a, b)
+    for a, b in zip(ml.chunk(3), mt.chunk(3)):
+        m2.update(a, b)
+    out["class/b_recall_at_p/value"], out["class/b_recall_at_p/thr"] = (x.numpy() for x in m.compute())
+    out["class/mc_spec_at_sens/value"], out["class/mc_spec_at_sens/thr"] = (x.numpy() for x in m2.compute())
+    return out
+
+
 def regression_golden() -> dict:
     import torchmetrics.functional as TF
     import torchmetrics.regression as TR
@@ -989,6 +1044,11 @@ if __name__ == "__main__":
     if "fuzz" in which:
         data = fuzz_golden()
         path = os.path.join(HERE, "fuzz.npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
+    if "atfixed" in which:
+        data = atfixed_golden()
+        path = os.path.join(HERE, "atfixed.npz")
         np.savez_compressed(path, **data)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
     if "curves" in which:
