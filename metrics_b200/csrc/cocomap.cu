@@ -546,11 +546,7 @@ extern "C" int mb200_coco_map_evaluate(
     ea.det_ignore = w.det_ignore;
     ea.npig = w.npig;
     ea.err = err_flag;
-    static thread_local bool configured = false;
-    if (!configured) {
-        MB200_CUDA_OK(cudaFuncSetAttribute(map_evaluate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
+    MB200_CUDA_OK(ensure_dynamic_smem(map_evaluate_kernel, 200 * 1024));
     map_evaluate_kernel<<<(unsigned)n_img, 256, smem, st>>>(ea, (int)max_det_per_img, (int)max_gt_per_img);
     count_launch();
 

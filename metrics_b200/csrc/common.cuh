@@ -8,6 +8,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <unordered_map>
+
 #include "../../include/metrics_b200.h"
 
 namespace mb200 {
@@ -79,6 +81,21 @@ __device__ __forceinline__ unsigned long long f64_order_key(double v) {
     if ((b & 0x7fffffffffffffffull) > 0x7ff0000000000000ull) return ~0ull;
     if (b == 0x8000000000000000ull) b = 0ull;
     return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// Opt a kernel into more than 48 KB of dynamic shared memory.  The attribute is per (function, device): remember which
+// devices were configured per function address, so a process that drives several GPUs configures each of them.
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kern, int bytes) {
+    static thread_local std::unordered_map<const void*, unsigned long long> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    unsigned long long& mask = done[reinterpret_cast<const void*>(kern)];
+    if (dev < 64 && ((mask >> dev) & 1ull)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev < 64) mask |= 1ull << dev;
+    return e;
 }
 
 }  // namespace mb200

@@ -335,11 +335,7 @@ static int launch_bulk(const RowArgs& a, Sink sink, cudaStream_t st, bool& launc
     launched = false;
     if (stages < 3 || a.n_outer < 4 * kRows) return 0;
     auto kern = rows_bulk_kernel<T, Sink, kI64, kRows>;
-    static thread_local bool configured = false;
-    if (!configured) {
-        MB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
-        configured = true;
-    }
+    MB200_CUDA_OK(ensure_dynamic_smem(kern, 227 * 1024 - 512));
     const long long tiles = (a.n_outer + kRows - 1) / kRows;
     int grid = sm_count();
     if (tiles < grid) grid = (int)tiles;

@@ -241,12 +241,7 @@ static inline int radix_sort_passes(KeyT* keys_a, ValT* vals_a, KeyT* keys_b, Va
 
     auto kern = radix_onesweep_kernel<KeyT, ValT>;
     const size_t smem = sizeof(SortSmem<KeyT, ValT>);
-    static thread_local bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return MB200_ERR_CUDA;
-        configured = true;
-    }
+    if (ensure_dynamic_smem(kern, (int)smem) != cudaSuccess) return MB200_ERR_CUDA;
     KeyT *kin = keys_a, *kout = keys_b;
     ValT *vin = vals_a, *vout = vals_b;
     for (int pass = 0; pass < key_bytes; ++pass) {
