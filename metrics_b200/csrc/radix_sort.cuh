@@ -3,7 +3,7 @@
 //   digit histograms   ONE pass over the keys counts every digit of every radix pass (order-independent), a tiny scan
 //                      turns them into per-(segment, pass) exclusive digit offsets;
 //   per radix pass     ONE kernel: CTAs take tiles in ticket order, rank their 8192 keys (warp-striped layout,
-//                      MATCH.ANY groups + per-warp digit counters in shared memory), publish the tile's digit counts,
+//                      ballot-built digit groups + per-warp digit counters in shared memory), publish the tile's digit counts,
 //                      obtain the counts of all earlier tiles of the segment by decoupled look-back on a status word
 //                      per (tile, digit) [flag:2 | count:30], reorder keys+payload by digit in shared memory and write
 //                      digit runs to their final positions with coalesced stores.
@@ -116,8 +116,18 @@ __global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 2 : 1) radix
     for (int i = 0; i < kSortItems; ++i) {
         const int idx = wbase + i * 32 + lane;
         const bool valid = idx < n;
-        const unsigned digit = valid ? ((unsigned)(key[i] >> shift) & 255u) : (0x100u + lane);  // invalid: unique groups
-        const unsigned peers = __match_any_sync(kFull, digit);
+        const unsigned digit = (unsigned)(key[i] >> shift) & 255u;
+        // lanes holding the same digit: 8 ballots (one per digit bit).  MATCH.ANY does this in one instruction but
+        // measures ~235 cycles per warp instruction per SM sub-partition on B200 vs ~100 for this sequence
+        // (tools/match_bench.cu) — it was half of the pass time.
+        unsigned peers = __ballot_sync(kFull, valid);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const bool bit = (digit >> b) & 1u;
+            const unsigned m = __ballot_sync(kFull, bit);
+            peers &= bit ? m : ~m;
+        }
+        if (!valid) peers = 1u << lane;  // tail lanes: singleton groups that never touch the counters
         const int leader = __ffs(peers) - 1;
         unsigned base = 0;
         if (valid && lane == leader) {
@@ -148,22 +158,39 @@ __global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 2 : 1) radix
             *st = kStatPrefix | my_count;
         } else {
             *st = kStatAgg | my_count;
+            // Decoupled look-back over the earlier tiles of the segment.  A window of kLookWindow predecessors is
+            // fetched with independent volatile loads (one L2 round trip for the whole window) and consumed in order:
+            // walking back one tile per round trip chains hundreds of L2 latencies across a wave of co-resident tiles.
+            constexpr int kLookWindow = 8;
+            const long long seg_first = (long long)tile_global - tile;  // the segment's tile 0 always holds a prefix
             long long j = (long long)tile_global - 1;
             unsigned spins = 0;
-            while (true) {
-                const unsigned s = *(volatile unsigned*)(status + (size_t)j * 256 + d);
-                const unsigned flag = s & ~kStatMask;
-                if (flag == 0u) {
-                    if (++spins > (1u << 24)) {  // never hang the GPU: report and produce garbage instead
+            bool done = false;
+            while (!done) {
+                unsigned w[kLookWindow];
+#pragma unroll
+                for (int k = 0; k < kLookWindow; ++k) {
+                    const long long jj = j - k;
+                    w[k] = jj >= seg_first ? *(volatile unsigned*)(status + (size_t)jj * 256 + d) : (2u << 30);  // == kStatPrefix | 0
+                }
+                int used = 0;
+#pragma unroll
+                for (int k = 0; k < kLookWindow; ++k) {
+                    if (done || used != k) continue;  // stop at the first entry that is not ready yet
+                    const unsigned flag = w[k] & ~kStatMask;
+                    if (flag == 0u) continue;
+                    excl += w[k] & kStatMask;
+                    used = k + 1;
+                    if (flag == kStatPrefix) done = true;
+                }
+                j -= used;
+                if (!done && used < kLookWindow) {  // ran into a tile that has not published anything yet
+                    if (++spins > (1u << 22)) {     // never hang the GPU: report and produce garbage instead
                         if (err) atomicOr(err, MB200_FLAG_SPIN_TIMEOUT);
                         break;
                     }
                     __nanosleep(20);
-                    continue;
                 }
-                excl += s & kStatMask;
-                if (flag == kStatPrefix) break;
-                --j;  // the segment's first tile always publishes a prefix, so j never leaves the segment
             }
             *st = kStatPrefix | ((excl + my_count) & kStatMask);
         }
