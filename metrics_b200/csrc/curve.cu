@@ -308,6 +308,7 @@ struct TileInfo {        // produced by phase 1, turned into carries by phase 2
     unsigned has_bound;  // tile contains a group end
 };
 
+template <int kWarps = 8>
 __device__ __forceinline__ unsigned block_excl_sum(unsigned v, unsigned* smem8, unsigned& total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned incl = v;
@@ -321,7 +322,7 @@ __device__ __forceinline__ unsigned block_excl_sum(unsigned v, unsigned* smem8, 
     __syncthreads();
     unsigned woff = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < kWarps; ++w) {
         const unsigned s = smem8[w];
         if (w < warp) woff += s;
         tot += s;
@@ -329,6 +330,7 @@ __device__ __forceinline__ unsigned block_excl_sum(unsigned v, unsigned* smem8, 
     total = tot;
     return woff + incl - v;
 }
+template <int kWarps = 8>
 __device__ __forceinline__ unsigned block_excl_max(unsigned v, unsigned* smem8) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned incl = v;
@@ -342,7 +344,7 @@ __device__ __forceinline__ unsigned block_excl_max(unsigned v, unsigned* smem8) 
     __syncthreads();
     unsigned wmax = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w)
+    for (int w = 0; w < kWarps; ++w)
         if (w < warp) wmax = max(wmax, smem8[w]);
     unsigned excl = __shfl_up_sync(kFull, incl, 1);
     if (lane == 0) excl = 0;
@@ -447,26 +449,27 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const unsigne
 
 // phase 2: one CTA per segment turns tile aggregates into exclusive carries (sequential over <= a few thousand tiles,
 // chunked 256 at a time with block scans).
-__global__ void __launch_bounds__(256) scan_carry_kernel(TileInfo* __restrict__ info, int tiles, int n,
+constexpr int kCarryThreads = 1024;
+__global__ void __launch_bounds__(kCarryThreads) scan_carry_kernel(TileInfo* __restrict__ info, int tiles, int n,
                                                          unsigned* __restrict__ seg_totals /* [seg][2]: P, U */) {
-    __shared__ unsigned sm[8];
+    __shared__ unsigned sm[kCarryThreads / 32];
     __shared__ unsigned c_pos, c_b, c_tp, c_fp;
     const int seg = blockIdx.x;
     TileInfo* __restrict__ ti = info + (size_t)seg * tiles;
     if (threadIdx.x == 0) c_pos = 0, c_b = 0, c_tp = 0, c_fp = 0;
     __syncthreads();
-    for (int base = 0; base < tiles; base += 256) {
+    for (int base = 0; base < tiles; base += kCarryThreads) {
         const int t = base + threadIdx.x;
         TileInfo v{0, 0, 0, 0, 0};
         if (t < tiles) v = ti[t];
         unsigned tot_pos, tot_b;
-        const unsigned pos_excl = c_pos + block_excl_sum(v.npos, sm, tot_pos);
-        const unsigned b_excl = c_b + block_excl_sum(v.nbound, sm, tot_b);
+        const unsigned pos_excl = c_pos + block_excl_sum<kCarryThreads / 32>(v.npos, sm, tot_pos);
+        const unsigned b_excl = c_b + block_excl_sum<kCarryThreads / 32>(v.nbound, sm, tot_b);
         // global TP / FP at this tile's last group end (monotone non-decreasing along the segment -> max-scan = "last valid")
         const unsigned tp_here = v.has_bound ? pos_excl + v.tp_last : 0u;
         const unsigned fp_here = v.has_bound ? ((unsigned)t * (unsigned)kScanTile - pos_excl) + v.fp_last : 0u;
-        const unsigned tp_prev = max(c_tp, block_excl_max(tp_here, sm));
-        const unsigned fp_prev = max(c_fp, block_excl_max(fp_here, sm));
+        const unsigned tp_prev = max(c_tp, block_excl_max<kCarryThreads / 32>(tp_here, sm));
+        const unsigned fp_prev = max(c_fp, block_excl_max<kCarryThreads / 32>(fp_here, sm));
         if (t < tiles) {
             ti[t].npos = pos_excl;
             ti[t].nbound = b_excl;
@@ -474,7 +477,7 @@ __global__ void __launch_bounds__(256) scan_carry_kernel(TileInfo* __restrict__ 
             ti[t].fp_last = fp_prev;
         }
         __syncthreads();
-        if (threadIdx.x == 255) {
+        if (threadIdx.x == kCarryThreads - 1) {
             c_pos = pos_excl + v.npos;
             c_b = b_excl + v.nbound;
             c_tp = max(tp_prev, tp_here);
@@ -600,6 +603,41 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(const unsigned long 
         const double auc = (P > 0.0 && Nn > 0.0) ? (double)auroc_acc[seg] / (2.0 * P * Nn) : 0.0;
         // all-negative: the reference forces recall to 1 everywhere and gets -0.0 (precision_recall_curve.py:278-283)
         const double ap = P > 0.0 ? s / P : -0.0;
+        out_auroc[seg] = (float)auc;
+        out_ap[seg] = (float)ap;
+        out_counts[3 * seg + 0] = (long long)seg_totals[2 * seg + 0];
+        out_counts[3 * seg + 1] = (long long)n - (long long)seg_totals[2 * seg + 0];
+        out_counts[3 * seg + 2] = (long long)seg_totals[2 * seg + 1];
+    }
+}
+
+// Same as scan_finalize_kernel for segments with many tiles (binary curves over millions of samples: one segment, thousands
+// of per-tile AP partials): a whole CTA folds one segment — thread-strided sums, then a fixed shuffle / shared-memory tree
+// (deterministic; a single warp walking 150 dependent L2 loads was 3 % of the whole evaluation).
+__global__ void __launch_bounds__(256) scan_finalize_wide_kernel(const unsigned long long* __restrict__ auroc_acc,
+                                                                 const double* __restrict__ ap_partial,
+                                                                 const unsigned* __restrict__ seg_totals, int tiles,
+                                                                 int n_stride, const int* __restrict__ seg_ignored,
+                                                                 float* __restrict__ out_auroc, float* __restrict__ out_ap,
+                                                                 long long* __restrict__ out_counts) {
+    __shared__ double part[8];
+    const int seg = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = seg_ignored ? n_stride - seg_ignored[seg] : n_stride;
+    double s = 0.0;
+    for (int t = threadIdx.x; t < tiles; t += 256) s += ap_partial[(size_t)seg * tiles + t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(kFull, s, o);
+    if (lane == 0) part[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += part[w];
+        const double P = (double)seg_totals[2 * seg + 0];
+        const double Nn = (double)n - P;
+        const double auc = (P > 0.0 && Nn > 0.0) ? (double)auroc_acc[seg] / (2.0 * P * Nn) : 0.0;
+        const double ap = P > 0.0 ? tot / P : -0.0;
         out_auroc[seg] = (float)auc;
         out_ap[seg] = (float)ap;
         out_counts[3 * seg + 0] = (long long)seg_totals[2 * seg + 0];
@@ -764,15 +802,20 @@ int sort_and_scan(unsigned* keys_a, unsigned char* lab_a, const CurveWs& w, int 
     const dim3 sgrid((unsigned)scan_tiles, (unsigned)segments);
     zero_u64_kernel<<<(int)((segments + 255) / 256), 256, 0, st>>>(w.auroc_acc, (int)segments);
     scan_reduce_kernel<<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, seg_ignored, scan_tiles, w.info);
-    scan_carry_kernel<<<(unsigned)segments, 256, 0, st>>>(w.info, scan_tiles, ni, w.seg_totals);
+    scan_carry_kernel<<<(unsigned)segments, kCarryThreads, 0, st>>>(w.info, scan_tiles, ni, w.seg_totals);
     if (fps_out)
         scan_apply_kernel<true><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, seg_ignored, scan_tiles, w.info, w.auroc_acc,
                                                                 w.ap_partial, fps_out, tps_out, thr_out, n);
     else
         scan_apply_kernel<false><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, seg_ignored, scan_tiles, w.info, w.auroc_acc,
                                                                  w.ap_partial, nullptr, nullptr, nullptr, n);
-    scan_finalize_kernel<<<(int)((segments + 7) / 8), 256, 0, st>>>(w.auroc_acc, w.ap_partial, w.seg_totals, scan_tiles,
-                                                                    ni, seg_ignored, (int)segments, out_auroc, out_ap, reinterpret_cast<long long*>(out_counts));
+    if (scan_tiles > 256)
+        scan_finalize_wide_kernel<<<(unsigned)segments, 256, 0, st>>>(w.auroc_acc, w.ap_partial, w.seg_totals, scan_tiles, ni,
+                                                                      seg_ignored, out_auroc, out_ap,
+                                                                      reinterpret_cast<long long*>(out_counts));
+    else
+        scan_finalize_kernel<<<(int)((segments + 7) / 8), 256, 0, st>>>(w.auroc_acc, w.ap_partial, w.seg_totals, scan_tiles,
+                                                                        ni, seg_ignored, (int)segments, out_auroc, out_ap, reinterpret_cast<long long*>(out_counts));
     for (int i = 0; i < 5; ++i) count_launch();
     return check_cuda(cudaGetLastError(), "curve evaluate launch");
 }

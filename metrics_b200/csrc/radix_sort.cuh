@@ -209,7 +209,9 @@ __global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 2 : 1) radix
     if (threadIdx.x < 256) {
         unsigned woff = 0;
         for (int w = 0; w < warp; ++w) woff += sm.scan_tmp[w];
-        sm.tile_off[threadIdx.x] += woff;
+        const unsigned off = sm.tile_off[threadIdx.x] + woff;
+        sm.tile_off[threadIdx.x] = off;
+        sm.digit_base[threadIdx.x] -= off;  // -> (global position of the digit's run) - (its position in the tile): dst = base + i
     }
     __syncthreads();
 
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 2 : 1) radix
     for (int i = threadIdx.x; i < tile_count; i += kSortThreads) {
         const KeyT k = sm.keys[i];
         const unsigned digit = (unsigned)(k >> shift) & 255u;
-        const unsigned dst = sm.digit_base[digit] + ((unsigned)i - sm.tile_off[digit]);
+        const unsigned dst = sm.digit_base[digit] + (unsigned)i;
         kout[dst] = k;
         vout[dst] = sm.vals[i];
     }
