@@ -60,6 +60,24 @@ def cfg1(dev):
         wall = time.perf_counter() - t0
         res[f"validate_{validate}"] = {"wall_us_per_update": wall / 100 * 1e6, "value": float(val),
                                        "units_per_s": 512000 / wall}
+    # the reference's CPU op chain on the same tensors, timed beside it (validate_args=False equivalent)
+    from oracle.torch_cpu_chain import macro_accuracy_cpu, multiclass_stat_scores_update_cpu
+
+    cp, ct = preds.cpu(), target.cpu()
+    torch.set_num_threads(min(os.cpu_count() or 1, 8))
+
+    def cpu_run():
+        st = [torch.zeros(5, dtype=torch.long) for _ in range(4)]
+        for i in range(100):
+            multiclass_stat_scores_update_cpu(*st, cp[i], ct[i], 5)
+        return macro_accuracy_cpu(*st)
+
+    cpu_run()
+    t0 = time.perf_counter()
+    cval = cpu_run()
+    wall = time.perf_counter() - t0
+    res["cpu_chain"] = {"wall_us_per_update": wall / 100 * 1e6, "value": float(cval), "threads": torch.get_num_threads(),
+                        "what": "reference op chain (argmax, bincount C^2, diag/row/col sums) without the Metric wrapper"}
     return res
 
 
@@ -172,6 +190,24 @@ def cfg5(dev, rank, world):
     if world > 1:
         sync_min, _ = ev_time(sync_only, reps=5, warm=2)
     res = compute()
+    cpu = None
+    if rank == 0 and world == 1:  # the reference's CPU chain for one rank's share, timed beside it
+        from oracle.torch_cpu_chain import multiclass_auroc_compute_cpu, multiclass_stat_scores_update_cpu
+
+        torch.set_num_threads(min(os.cpu_count() or 1, 32))
+        cb = [(lg.cpu(), tg.cpu()) for lg, tg in batches]
+        t0 = time.perf_counter()
+        st = [torch.zeros(1000, dtype=torch.long) for _ in range(4)]
+        probs = []
+        for lg, tg in cb:
+            multiclass_stat_scores_update_cpu(*st, lg, tg, 1000)
+            probs.append(torch.softmax(lg, 1))  # normalize_logits_if_needed on logits
+        t_upd = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        auc = multiclass_auroc_compute_cpu(torch.cat(probs), torch.cat([tg for _, tg in cb]), 1000)
+        t_cmp = time.perf_counter() - t0
+        cpu = {"update_ms_4_batches": t_upd * 1e3, "compute_ms": t_cmp * 1e3, "auroc": float(auc),
+               "threads": torch.get_num_threads()}
     t = torch.tensor([upd_min, comp_min, sync_min or 0.0, comp_gather_min or 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -179,7 +215,7 @@ def cfg5(dev, rank, world):
             "compute_ms": float(t[1]), "sync_only_ms": float(t[2]) if world > 1 else None,
             "compute_ms_gather_everything": float(t[3]) if world > 1 else None,
             "compute_path": "class-sharded all_to_all (metrics_b200/parallel_curves.py)" if world > 1 else "local",
-            "f1": float(res["MulticlassF1Score"]), "auroc": float(res["MulticlassAUROC"]),
+            "f1": float(res["MulticlassF1Score"]), "auroc": float(res["MulticlassAUROC"]), "cpu_chain_one_rank": cpu,
             "sync_bytes_per_rank": 16384 * 1000 * 4 + 16384 * 8 + 4 * 1000 * 8}
 
 

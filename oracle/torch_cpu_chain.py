@@ -60,3 +60,53 @@ def binary_auroc_ap_compute_cpu(preds: Tensor, target: Tensor):
     recall = torch.cat([recall.flip(0), torch.zeros(1)])
     ap = -torch.sum((recall[1:] - recall[:-1]) * precision[:-1])  # average_precision.py:74-75
     return auroc, ap
+
+
+def multiclass_stat_scores_update_cpu(tp: Tensor, fp: Tensor, tn: Tensor, fn: Tensor, preds: Tensor, target: Tensor,
+                                      num_classes: int) -> None:
+    """MulticlassStatScores.update on CPU tensors, top_k=1 / global / macro-style states (functional/classification/
+    stat_scores.py:328-344 format, :435-448 bincount path; classification/stat_scores.py:69-80 state add)."""
+    if preds.ndim == target.ndim + 1:  # :341
+        preds = preds.argmax(dim=1)
+    preds, target = preds.flatten(), target.flatten()  # :342-343
+    unique_mapping = target.to(torch.long) * num_classes + preds.to(torch.long)  # :441
+    confmat = torch.bincount(unique_mapping, minlength=num_classes**2).reshape(num_classes, num_classes)  # :442-443
+    d_tp = confmat.diag()  # :444
+    d_fp = confmat.sum(0) - d_tp  # :445
+    d_fn = confmat.sum(1) - d_tp  # :446
+    d_tn = confmat.sum() - (d_fp + d_fn + d_tp)  # :447
+    tp += d_tp
+    fp += d_fp
+    tn += d_tn
+    fn += d_fn
+
+
+def macro_accuracy_cpu(tp: Tensor, fp: Tensor, tn: Tensor, fn: Tensor) -> Tensor:
+    """_accuracy_reduce(average="macro") (functional/classification/accuracy.py:84-88 + utilities/compute.py:71-82)."""
+    score = torch.where(tp + fn != 0, tp.float() / (tp + fn).float(), torch.zeros(()))
+    weights = torch.ones_like(score)
+    weights[tp + fp + fn == 0] = 0.0
+    return (weights * score / weights.sum()).sum()
+
+
+def multiclass_auroc_compute_cpu(preds: Tensor, target: Tensor, num_classes: int) -> Tensor:
+    """MulticlassAUROC.compute(average="macro") on CPU tensors: the reference's Python loop over classes, one
+    `_binary_clf_curve` (argsort + cumsum) per class (roc.py:176-181, auroc.py:193-205)."""
+    import torch.nn.functional as F
+
+    aucs = []
+    for c in range(num_classes):
+        p, t = preds[:, c], target
+        idx = torch.argsort(p, descending=True)
+        p, t = p[idx], t[idx]
+        distinct = torch.where(p[1:] - p[:-1])[0]
+        thr_idx = F.pad(distinct, [0, 1], value=t.size(0) - 1)
+        t = (t == c).to(torch.long)
+        tps = torch.cumsum(t * 1.0, dim=0)[thr_idx]
+        fps = 1 + thr_idx - tps
+        tps = torch.cat([torch.zeros(1, dtype=tps.dtype), tps])
+        fps = torch.cat([torch.zeros(1, dtype=fps.dtype), fps])
+        fpr = fps / fps[-1] if fps[-1] > 0 else torch.zeros_like(fps)
+        tpr = tps / tps[-1] if tps[-1] > 0 else torch.zeros_like(tps)
+        aucs.append(torch.trapz(tpr, fpr))
+    return torch.stack(aucs).mean()
