@@ -86,3 +86,4 @@ from metrics_b200.classification.at_fixed import (  # noqa: F401,E402
     SensitivityAtSpecificity,
     SpecificityAtSensitivity,
 )
+from metrics_b200.classification.exact_match import ExactMatch, MulticlassExactMatch, MultilabelExactMatch  # noqa: F401,E402

@@ -80,3 +80,4 @@ from metrics_b200.functional.classification.at_fixed import (  # noqa: F401,E402
     multilabel_sensitivity_at_specificity,
     multilabel_specificity_at_sensitivity,
 )
+from metrics_b200.functional.classification.exact_match import exact_match, multiclass_exact_match, multilabel_exact_match  # noqa: F401,E402

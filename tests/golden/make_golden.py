@@ -869,6 +869,34 @@ def fuzz_golden() -> dict:
             target = torch.where(torch.rand(target.shape, generator=g) < 0.15, torch.full_like(target, ig), target)
         kw.update({"thresholds": thresholds, "ignore_index": ig})
         emit(fn, kw, preds, target)
+    # ---- exact match (multiclass / multilabel, extra dims, samplewise, ignore_index) ---------------------------------------------
+    for _ in range(16):
+        N, P = int(pick(1, 5, 40)), int(pick(1, 3, 6))
+        ig = pick(None, None, -1)
+        mda = pick("global", "samplewise")
+        if rng.random() < 0.5:
+            C = int(pick(2, 4, 9))
+            kind = pick("logits", "labels")
+            target = torch.randint(0, C, (N, P), generator=g)
+            if kind == "labels":
+                preds = torch.where(torch.rand(N, P, generator=g) < 0.8, target, torch.randint(0, C, (N, P), generator=g))
+            else:
+                preds = torch.randn(N, C, P, generator=g)
+                preds.scatter_(1, target.unsqueeze(1), 4.0 * (torch.rand(N, 1, P, generator=g) < 0.8).float(), reduce="add")
+            if ig is not None:
+                target = torch.where(torch.rand(N, P, generator=g) < 0.2, torch.full_like(target, ig), target)
+            emit("multiclass_exact_match", {"num_classes": C, "multidim_average": mda, "ignore_index": ig}, preds, target)
+        else:
+            L = int(pick(2, 3, 5))
+            target = torch.randint(0, 2, (N, L, P), generator=g)
+            noise = torch.rand(N, L, P, generator=g)
+            preds = torch.where(noise < 0.85, target.float() * 0.8 + 0.1, 1 - (target.float() * 0.8 + 0.1))
+            if rng.random() < 0.4:
+                preds = (preds - 0.5) * 6  # logits
+            if ig is not None:
+                target = torch.where(torch.rand(N, L, P, generator=g) < 0.1, torch.full_like(target, ig), target)
+            emit("multilabel_exact_match", {"num_labels": L, "threshold": float(pick(0.5, 0.3)), "multidim_average": mda,
+                                            "ignore_index": ig}, preds, target)
     # ---- regression ------------------------------------------------------------------------------------------------------------
     import torchmetrics.functional.regression as FR
 
