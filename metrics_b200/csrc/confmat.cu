@@ -61,6 +61,9 @@ constexpr int kRowThreads = 256;
 // pipelining or a TMA/bulk-copy ring (1b) buys nothing on top of it.
 template <typename T, typename Sink, bool kI64>
 __global__ void __launch_bounds__(kRowThreads) rows_vec_kernel(RowArgs a, Sink sink) {
+    // Let the next update's grid (launched with programmatic stream serialization, see launch_overlapped) start filling
+    // SMs as soon as this grid's CTAs retire, instead of after the whole grid has drained and a launch gap has passed.
+    if constexpr (Sink::kOverlapSafe) asm volatile("griddepcontrol.launch_dependents;");
     sink.block_init();
     typename Sink::Local loc;
     sink.init(loc);
@@ -319,6 +322,34 @@ static int rows_path_override() {
     return cached;
 }
 
+// MB200_ROWS_OVERLAP=0 disables programmatic dependent launch of back-to-back confusion-matrix updates (A/B switch).
+static bool rows_overlap_enabled() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("MB200_ROWS_OVERLAP");
+        cached = (e && e[0] == '0') ? 0 : 1;
+    }
+    return cached == 1;
+}
+
+// Launch with cudaLaunchAttributeProgrammaticStreamSerialization: the grid may begin while the previous kernel of the
+// stream is still draining (that kernel opts in with griddepcontrol.launch_dependents).  Only used for launches whose
+// sole shared data are commutative atomics on the state.
+template <typename Kernel, typename... Args>
+static cudaError_t launch_overlapped(Kernel kern, int grid, int threads, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <typename Kernel>
 static int resident_blocks(Kernel k, int threads, size_t smem) {
     int per_sm = 0;
@@ -360,7 +391,15 @@ static int launch_rows(const RowArgs& a, Sink sink, size_t smem, cudaStream_t st
                 if (!launched) {
                     auto kern = rows_vec_kernel<T, Sink, kI64>;
                     const int grid = grid_for(a.n_outer, kRowThreads / 32, resident_blocks(kern, kRowThreads, smem));
-                    kern<<<grid, kRowThreads, smem, st>>>(a, sink);
+                    if constexpr (Sink::kOverlapSafe) {
+                        if (rows_overlap_enabled()) {
+                            MB200_CUDA_OK(launch_overlapped(kern, grid, kRowThreads, smem, st, a, sink));
+                        } else {
+                            kern<<<grid, kRowThreads, smem, st>>>(a, sink);
+                        }
+                    } else {
+                        kern<<<grid, kRowThreads, smem, st>>>(a, sink);
+                    }
                 }
             }
         } else {

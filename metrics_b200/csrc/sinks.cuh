@@ -15,6 +15,7 @@ struct ArgmaxOutSink {
     __device__ __forceinline__ void row(Local&, long long idx, long long /*t*/, int p) { out[idx] = p; }
     __device__ __forceinline__ void finish(Local&) {}
     static constexpr bool kNeedsTarget = false;
+    static constexpr bool kOverlapSafe = false;
 };
 
 // confmat[t, p] += 1 straight into the (L2-resident) state; optional shared-memory privatisation for tiny C.
@@ -24,6 +25,9 @@ struct ConfmatSink {
     int C;
     struct Local {};
     static constexpr bool kNeedsTarget = true;
+    // Two consecutive launches may overlap (programmatic dependent launch): all they share is the state, and they only
+    // ever touch it with commutative 64-bit REDs.
+    static constexpr bool kOverlapSafe = true;
     __device__ __forceinline__ void block_init() {
         if (kSmem) {
             extern __shared__ unsigned sh_bins[];
@@ -64,6 +68,7 @@ struct StatsSink {
         unsigned n_valid, n_match;
     };
     static constexpr bool kNeedsTarget = true;
+    static constexpr bool kOverlapSafe = false;  // self-cleaning workspace + last-CTA ticket: launches must not overlap
     __device__ __forceinline__ void block_init() {
         if (kSmem) {
             extern __shared__ unsigned sh_bins[];
@@ -169,6 +174,7 @@ struct SamplewiseSink {
     int C;
     struct Local {};
     static constexpr bool kNeedsTarget = true;
+    static constexpr bool kOverlapSafe = false;
     __device__ __forceinline__ void block_init() {}
     __device__ __forceinline__ void init(Local&) {}
     __device__ __forceinline__ void row(Local&, long long idx, long long t, int p) {
