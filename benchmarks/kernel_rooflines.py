@@ -1,0 +1,90 @@
+"""Device-resident timing of every kernel family at a large size: achieved algorithmic GB/s vs the measured HBM peak.
+One JSON document (profiles/r01_kernel_rooflines.json).  Inputs are larger than L2 or rotated so nothing is re-read from it."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from metrics_b200 import _native  # noqa: E402
+from metrics_b200.functional.classification.stat_scores import stat_scores_workspace  # noqa: E402
+
+dev = torch.device("cuda", 0)
+peak = 6574.8
+try:
+    peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timed(fn, reps=20, warm=3, inner=1):
+    """Best-of-`reps` CUDA-event time of `inner` back-to-back calls, per call (inner > 1 for kernels shorter than a launch)."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(inner):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / inner)
+    return best
+
+
+out = {"peak_gbs_measured_copy": peak, "kernels": {}}
+
+
+def record(name, ms, algo_bytes, note):
+    gbs = algo_bytes / (ms * 1e-3) / 1e9
+    out["kernels"][name] = {"ms": ms, "algorithmic_bytes": algo_bytes, "achieved_gbs": gbs, "frac_of_measured_peak": gbs / peak,
+                            "note": note}
+
+
+g = torch.Generator(device=dev).manual_seed(0)
+# K1b: multiclass stat scores, cfg2 shape (65536 x 1000 bf16), eight rotating batches (1 GB >> L2)
+N, C = 65536, 1000
+lg = [torch.randn(N, C, generator=g, device=dev).bfloat16() for _ in range(8)]
+tg = [torch.randint(0, C, (N,), generator=g, device=dev) for _ in range(8)]
+st = [torch.zeros(C, dtype=torch.int64, device=dev) for _ in range(4)]
+ws = stat_scores_workspace(C, dev)
+k = [0]
+
+
+def k1b():
+    i = k[0] = (k[0] + 1) % 8
+    _native.multiclass_stat_scores_update_(*st, ws, lg[i], tg[i], C, None, False, None)
+
+
+record("K1b multiclass_stat_scores_update [65536,1000] bf16", timed(k1b, inner=64), N * C * 2 + N * 8,
+       "64 back-to-back launches over 8 distinct batches (1 GB); logits + labels read once; states in L2")
+del lg
+
+# K2: binary counts over 2^26 f32 probabilities + int64 targets (805 MB)
+n = 1 << 26
+p = torch.rand(n, generator=g, device=dev)
+t = torch.randint(0, 2, (n,), generator=g, device=dev)
+record("K2 binary_stat_counts 2^26 f32 + i64", timed(lambda: _native.binary_stat_counts(p, t, 1, 0.5, None, False)),
+       n * 12, "range-flag pass + counting pass: scores are read twice (8 B/elem) + 8 B labels once")
+# K6: sigmoid_if_logits (flag pass + apply pass): read 4 + read 4 + write 4
+record("K6 sigmoid_if_logits 2^26 f32", timed(lambda: _native.sigmoid_if_logits(p)), n * 8,
+       "algorithmic = read + write; the global logits vote costs a second read (12 B/elem of traffic)")
+# K4: binned curve update, T = 200 thresholds
+thr = torch.linspace(0, 1, 200, device=dev)
+record("K4 binned_curve_update 2^26 f32, T=200", timed(lambda: _native.binned_curve_update(p, t, thr, 1), reps=5), n * 12,
+       "one pass: 8-step binary search per element + shared-memory histogram")
+# K9: regression sums (MSE) over 2 x 2^26 f32
+q = torch.rand(n, generator=g, device=dev)
+record("K9 regression_sums (MSE) 2 x 2^26 f32", timed(lambda: _native.regression_sums(p, q, 0)), n * 8, "two inputs read once")
+del q
+# K3/K5: exact binary curve evaluation, 10^7 samples
+n7 = 10_000_000
+p7, t7 = p[:n7].contiguous(), t[:n7].contiguous()
+record("K3/K5 curve_evaluate 1e7 f32 (pack + 4-pass sort + scan)", timed(lambda: _native.curve_evaluate(p7, t7, 1), reps=10), 150e6,
+       "SURVEY 8(d) figure: each 5-byte record read once, written once, scanned once; the working set (50 MB) is L2-resident")
+print(json.dumps(out, indent=1))
+if len(sys.argv) > 1:
+    open(sys.argv[1], "w").write(json.dumps(out, indent=1))

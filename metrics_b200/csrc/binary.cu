@@ -35,30 +35,32 @@ template <>
 __device__ __forceinline__ float round_to<__nv_bfloat16>(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 template <typename T>
+__device__ __forceinline__ bool out_of_unit_range(T x) {
+    if constexpr (sizeof(T) == 8) {
+        return (x < 0.0) | (x > 1.0);
+    } else {
+        const float v = score_to_float<T>(x);
+        return (v < 0.f) | (v > 1.f);
+    }
+}
+// batch-global "are these logits?" vote: 16-byte streaming loads over the aligned body, scalar head / tail
+template <typename T>
 __global__ void __launch_bounds__(256) bin_range_flag_kernel(const T* __restrict__ x, long long n, unsigned* flag) {
     bool bad = false;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double v = (double)x[i];
-        bad |= (v < 0.0) | (v > 1.0);
+    constexpr int kVec = 16 / (int)sizeof(T);
+    long long head = (long long)(((16 - (reinterpret_cast<uintptr_t>(x) & 15)) & 15) / sizeof(T));
+    if (head > n) head = n;
+    const long long nvec = (n - head) / kVec;
+    const uint4* __restrict__ xv = reinterpret_cast<const uint4*>(x + head);
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = gtid; i < nvec; i += stride) {
+        const uint4 q = ld_stream16(xv + i);
+        const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+        for (int k = 0; k < kVec; ++k) bad |= out_of_unit_range<T>(e[k]);
     }
-    if (__any_sync(kFull, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
-}
-template <>
-__global__ void __launch_bounds__(256) bin_range_flag_kernel<__half>(const __half* __restrict__ x, long long n, unsigned* flag) {
-    bool bad = false;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float v = __half2float(x[i]);
-        bad |= (v < 0.f) | (v > 1.f);
-    }
-    if (__any_sync(kFull, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
-}
-template <>
-__global__ void __launch_bounds__(256) bin_range_flag_kernel<__nv_bfloat16>(const __nv_bfloat16* __restrict__ x, long long n, unsigned* flag) {
-    bool bad = false;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float v = __bfloat162float(x[i]);
-        bad |= (v < 0.f) | (v > 1.f);
-    }
+    const long long tail0 = head + nvec * kVec;
+    for (long long i = gtid; i < head + (n - tail0); i += stride) bad |= out_of_unit_range<T>(x[i < head ? i : tail0 + (i - head)]);
     if (__any_sync(kFull, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
@@ -178,6 +180,70 @@ __global__ void __launch_bounds__(256) bin_count_kernel(BinArgs a) {
     }
 }
 
+// prediction from a score VALUE (same arithmetic as pred_label)
+template <typename T>
+__device__ __forceinline__ int pred_from_value(const BinArgs& a, T x, bool logits) {
+    if constexpr (sizeof(T) == 8) {
+        double v = x;
+        if (logits) v = 1.0 / (1.0 + exp(-v));
+        return v > a.threshold_d ? 1 : 0;
+    } else {
+        float v = score_to_float<T>(x);
+        if (logits) v = round_to<T>(1.0f / (1.0f + expf(-v)));
+        return v > a.threshold ? 1 : 0;
+    }
+}
+
+// Single-group fast path (binary task, global counts, int64 targets, 16-byte aligned inputs): no per-element group
+// arithmetic (the generic kernel spends two 64-bit divisions per element on it), 16-byte streaming loads for scores and
+// labels, counters in registers, one warp reduction and four REDs per warp at the end.
+template <typename T>
+__global__ void __launch_bounds__(256) bin_count_flat_kernel(BinArgs a) {
+    const bool logits = a.logits != nullptr && (*a.logits) != 0u;
+    const long long total = a.n_outer * a.num_labels * a.inner;
+    constexpr int kVec = 16 / (int)sizeof(T);
+    const long long nvec = total / kVec;
+    const uint4* __restrict__ pv = reinterpret_cast<const uint4*>(a.preds);
+    const uint4* __restrict__ tv = reinterpret_cast<const uint4*>(a.target);  // two int64 labels per vector
+    const T* __restrict__ ps = reinterpret_cast<const T*>(a.preds);
+    const long long* __restrict__ ts = reinterpret_cast<const long long*>(a.target);
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    unsigned c[4] = {0, 0, 0, 0};
+    bool bad_target = false;
+    auto count = [&](T x, long long t) {
+        if (a.has_ignore && t == a.ignore_index) return;
+        if ((unsigned long long)t > 1ull) {
+            bad_target = true;
+            return;  // the reference counts such elements in none of the four masks
+        }
+        const int p = pred_from_value<T>(a, x, logits);
+        const bool eq = (p == (int)t);
+        c[0] += (eq && t == 1);
+        c[1] += (!eq && t == 0);
+        c[2] += (eq && t == 0);
+        c[3] += (!eq && t == 1);
+    };
+    for (long long v = gtid; v < nvec; v += stride) {
+        const uint4 q = ld_stream16(pv + v);
+        const T* e = reinterpret_cast<const T*>(&q);
+        uint4 lab[kVec / 2];
+#pragma unroll
+        for (int k = 0; k < kVec / 2; ++k) lab[k] = ld_stream16(tv + v * (kVec / 2) + k);
+        const long long* l = reinterpret_cast<const long long*>(lab);
+#pragma unroll
+        for (int k = 0; k < kVec; ++k) count(e[k], l[k]);
+    }
+    for (long long i = nvec * kVec + gtid; i < total; i += stride) count(ps[i], ts[i]);
+    if (__any_sync(kFull, bad_target) && (threadIdx.x & 31) == 0 && a.err) atomicOr(a.err, MB200_FLAG_TARGET_RANGE);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[k] = __reduce_add_sync(kFull, c[k]);
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c[k]) red_add_u64(a.counts + k, c[k]);
+    }
+}
+
 }  // namespace mb200
 
 using namespace mb200;
@@ -220,6 +286,18 @@ extern "C" int mb200_binary_stat_counts(const void* preds, int preds_dtype, cons
             case MB200_F64: bin_range_flag_kernel<double><<<fgrid, 256, 0, st>>>((const double*)preds, total, flag_scratch); break;
         }
         count_launch();
+    }
+    const bool flat = float_preds && !samplewise && num_labels == 1 && target_dtype == MB200_I64 &&
+                      ((reinterpret_cast<uintptr_t>(preds) | reinterpret_cast<uintptr_t>(target)) & 15) == 0;
+    if (flat) {
+        switch (preds_dtype) {
+            case MB200_F32: bin_count_flat_kernel<float><<<grid, 256, 0, st>>>(a); break;
+            case MB200_F16: bin_count_flat_kernel<__half><<<grid, 256, 0, st>>>(a); break;
+            case MB200_BF16: bin_count_flat_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a); break;
+            default: bin_count_flat_kernel<double><<<grid, 256, 0, st>>>(a); break;
+        }
+        count_launch();
+        return check_cuda(cudaGetLastError(), "binary stat counts launch");
     }
     switch (preds_dtype) {
         case MB200_F32: bin_count_kernel<float><<<grid, 256, smem, st>>>(a); break;

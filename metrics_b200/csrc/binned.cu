@@ -36,33 +36,85 @@ template <typename T>
 __global__ void __launch_bounds__(256) binned_bucket_kernel(const T* __restrict__ preds, const void* __restrict__ target,
                                                             int tdtype, long long n, int C, const float* __restrict__ thr,
                                                             int nthr, unsigned long long* __restrict__ scratch,
-                                                            long long* __restrict__ confmat, int use_smem, int multilabel) {
-    extern __shared__ unsigned sh_cnt[];  // C * 2 * (nthr + 1) when use_smem
+                                                            long long* __restrict__ confmat, int use_smem, int multilabel,
+                                                            int thr_in_smem) {
+    extern __shared__ unsigned sh_cnt[];  // [C * 2 * (nthr + 1) when use_smem] counters, then nthr thresholds
     const int stride = nthr + 1;
     const int ncnt = C * 2 * stride;
-    if (use_smem) {
+    typedef typename CmpType<T>::type Cmp;
+    float* sh_stage = reinterpret_cast<float*>(sh_cnt + (use_smem ? ncnt : 0));
+    if (thr_in_smem)
+        for (int i = threadIdx.x; i < nthr; i += blockDim.x) sh_stage[i] = thr[i];
+    const float* __restrict__ sh_thr = thr_in_smem ? sh_stage : thr;  // very long threshold lists stay in global memory
+    if (use_smem)
         for (int i = threadIdx.x; i < ncnt; i += blockDim.x) sh_cnt[i] = 0;
-        __syncthreads();
-    }
+    __syncthreads();
+    // bucket hint for (near-)uniform grids: k ~ (p - thr[0]) * (nthr - 1) / (thr[last] - thr[0]); the exact bucket is then
+    // found by stepping against the real thresholds, so the hint only affects speed, never the result
+    const float t_first = sh_thr[0], t_last = sh_thr[nthr - 1];
+    const float scale = (nthr > 1 && t_last > t_first) ? (float)(nthr - 1) / (t_last - t_first) : 0.f;
     const long long total = n * C;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long s = i / C;
-        const int c = (int)(i - s * C);
-        // multilabel: target is [n, C] like preds, every label is its own binary problem
-        const long long t = load_label(target, tdtype, multilabel ? i : s);
-        const int y = (C == 1 || multilabel) ? (t == 1) : (t == c);
-        if ((C == 1 || multilabel) && (unsigned long long)t > 1ull) continue;  // binary: only {0,1} targets take part
-        const typename CmpType<T>::type p = binned_load<T>(preds, i);
-        // k = number of thresholds <= p  (p >= thr[j]  <=>  j < k);  NaN compares false everywhere -> k = 0
-        int lo = 0, hi = nthr;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((typename CmpType<T>::type)thr[mid] <= p) lo = mid + 1;
-            else hi = mid;
+    const bool flat = (C == 1) || multilabel;  // label index == element index
+    // bucket of one score: k = number of thresholds <= p  (p >= thr[j]  <=>  j < k);  NaN compares false everywhere -> 0
+    auto bucket_of = [&](Cmp p) -> int {
+        int k = 0;
+        if (p == p) {
+            const float h = ((float)p - t_first) * scale;
+            k = h <= 0.f ? 0 : (h >= (float)nthr ? nthr : (int)h);
+            int steps = 0;
+            while (k < nthr && (Cmp)sh_thr[k] <= p && steps < 4) ++k, ++steps;
+            while (k > 0 && !((Cmp)sh_thr[k - 1] <= p) && steps < 8) --k, ++steps;
+            const bool settled = (k == nthr || !((Cmp)sh_thr[k] <= p)) && (k == 0 || (Cmp)sh_thr[k - 1] <= p);
+            if (!settled) {  // irregular thresholds: plain binary search
+                int lo = 0, hi = nthr;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if ((Cmp)sh_thr[mid] <= p) lo = mid + 1;
+                    else hi = mid;
+                }
+                k = lo;
+            }
         }
-        const int slot = (c * 2 + y) * stride + lo;
+        return k;
+    };
+    auto commit = [&](int c, long long t, Cmp p) {
+        // multilabel: target is [n, C] like preds, every label is its own binary problem
+        const int y = (C == 1 || multilabel) ? (t == 1) : (t == c);
+        if ((C == 1 || multilabel) && (unsigned long long)t > 1ull) return;  // binary: only {0,1} targets take part
+        const int slot = (c * 2 + y) * stride + bucket_of(p);
         if (use_smem) atomicAdd(&sh_cnt[slot], 1u);
         else atomicAdd(&scratch[slot], 1ull);
+    };
+    const long long gstride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int kUnroll = 4;  // independent elements in flight per thread: loads first, then the dependent bucket work
+    for (; i + (kUnroll - 1) * gstride < total; i += kUnroll * gstride) {
+        long long tt[kUnroll];
+        Cmp pp[kUnroll];
+        int cc[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long e = i + u * gstride;
+            long long srow = e;
+            cc[u] = 0;
+            if (C > 1) {
+                srow = e / C;
+                cc[u] = (int)(e - srow * C);
+            }
+            tt[u] = load_label(target, tdtype, flat ? e : srow);
+            pp[u] = binned_load<T>(preds, e);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) commit(cc[u], tt[u], pp[u]);
+    }
+    for (; i < total; i += gstride) {
+        long long srow = i;
+        int c = 0;
+        if (C > 1) {
+            srow = i / C;
+            c = (int)(i - srow * C);
+        }
+        commit(c, load_label(target, tdtype, flat ? i : srow), binned_load<T>(preds, i));
     }
     if (use_smem) {
         __syncthreads();
@@ -122,16 +174,18 @@ static int binned_update_impl(int multilabel, const void* preds, int preds_dtype
     const long long total = n * num_classes;
     const size_t smem_need = (size_t)num_classes * 2 * (num_thresholds + 1) * sizeof(unsigned);
     const int use_smem = smem_need <= 40 * 1024;
+    const int thr_in_smem = num_thresholds <= 2048;
+    const size_t smem_total = (use_smem ? smem_need : 0) + (thr_in_smem ? (size_t)num_thresholds * sizeof(float) : 0);
     long long blocks = (total + 256 * 8 - 1) / (256 * 8);
-    const long long cap = (long long)sm_count() * 4;
+    const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     unsigned long long* sc = reinterpret_cast<unsigned long long*>(scratch);
     long long* cm = reinterpret_cast<long long*>(confmat);
 #define MB200_BINNED(T)                                                                                              \
-    binned_bucket_kernel<T><<<(int)blocks, 256, use_smem ? smem_need : 0, st>>>(                                     \
+    binned_bucket_kernel<T><<<(int)blocks, 256, smem_total, st>>>(                                                  \
         reinterpret_cast<const T*>(preds), target, target_dtype, n, (int)num_classes, thresholds_sorted,            \
-        (int)num_thresholds, sc, cm, use_smem, multilabel);
+        (int)num_thresholds, sc, cm, use_smem, multilabel, thr_in_smem);
     switch (preds_dtype) {
         case MB200_F32: MB200_BINNED(float) break;
         case MB200_F16: MB200_BINNED(__half) break;

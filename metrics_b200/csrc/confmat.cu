@@ -522,9 +522,10 @@ extern "C" int mb200_multiclass_stat_scores_update(const void* preds, int preds_
     RowArgs a{preds, target, target_dtype, n_outer, (int)num_classes, inner, has_ignore_index,
               ignore_index, err_flag};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    // shared-memory privatisation pays once every CTA sees many rows per class bin; with few rows per launch (cfg5:
-    // 4096 rows, 1000 classes) zero-filling and flushing 3C counters per CTA costs more than ~3 L2 atomics per row
-    const bool priv = !micro && num_classes <= 2048 && n_outer * inner >= 4096 && n_outer * inner >= 16 * num_classes;
+    // Shared-memory privatisation pays when many rows hit few class bins (L2 atomics on a handful of addresses
+    // serialise).  With hundreds of classes the ~2 REDs per row spread over 3C L2-resident words cost nothing, while
+    // zero-filling and flushing 3C counters per CTA does (cfg2 shape: 37 us privatised vs the 22 us of the confmat kernel).
+    const bool priv = !micro && num_classes <= 256 && n_outer * inner >= 4096 && n_outer * inner >= 16 * num_classes;
     if (priv) {
         StatsSink<true> s{(long long*)tp, (long long*)fp, (long long*)tn, (long long*)fn,
                           (long long*)workspace, (int)num_classes, micro};

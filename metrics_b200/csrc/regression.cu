@@ -104,6 +104,74 @@ __global__ void __launch_bounds__(256) reg_partial_kernel(const T* __restrict__ 
     }
 }
 
+// d == 1 (one output: the common case): flat, vectorised map-reduce.  Every thread streams 16-byte vectors of both inputs
+// (two independent vector pairs in flight), accumulates its terms in fp64, then a fixed shuffle / shared-memory tree folds
+// the CTA (deterministic order).  The generic kernel above walks one element per thread per iteration with 16 warps per SM
+// and measured 0.94 TB/s; this one is bound by HBM.
+constexpr int kRegFlatThreads = 512;
+template <typename T, bool kDouble>
+__global__ void __launch_bounds__(kRegFlatThreads) reg_flat_kernel(const T* __restrict__ preds, const T* __restrict__ target,
+                                                                   long long n, int op, double param, double eps,
+                                                                   double* __restrict__ partial) {
+    __shared__ double sm[kRegFlatThreads / 32];
+    const int K = reg_num_sums(op);
+    constexpr int kVec = 16 / (int)sizeof(T);
+    double acc[kRegMaxK] = {0.0, 0.0, 0.0, 0.0};
+    const long long gtid = (long long)blockIdx.x * kRegFlatThreads + threadIdx.x;
+    const long long stride = (long long)gridDim.x * kRegFlatThreads;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(preds) | reinterpret_cast<uintptr_t>(target)) & 15) == 0;
+    const long long nvec = aligned ? n / kVec : 0;
+    auto consume = [&](const T& pv, const T& tv) {
+        if (kDouble) {
+            double out[kRegMaxK];
+            reg_terms<double>(op, (double)pv, (double)tv, param, eps, out);
+            for (int k = 0; k < K; ++k) acc[k] += out[k];
+        } else {
+            float out[kRegMaxK];
+            reg_terms<float>(op, (float)load_as_double<T>(&pv, 0), (float)load_as_double<T>(&tv, 0), (float)param, (float)eps, out);
+            for (int k = 0; k < K; ++k) acc[k] += (double)out[k];
+        }
+    };
+    const uint4* __restrict__ pv4 = reinterpret_cast<const uint4*>(preds);
+    const uint4* __restrict__ tv4 = reinterpret_cast<const uint4*>(target);
+    long long v = gtid;
+    for (; v + stride < nvec; v += 2 * stride) {  // two vector pairs in flight
+        const uint4 p0 = ld_stream16(pv4 + v), t0 = ld_stream16(tv4 + v);
+        const uint4 p1 = ld_stream16(pv4 + v + stride), t1 = ld_stream16(tv4 + v + stride);
+        const T* a0 = reinterpret_cast<const T*>(&p0);
+        const T* b0 = reinterpret_cast<const T*>(&t0);
+        const T* a1 = reinterpret_cast<const T*>(&p1);
+        const T* b1 = reinterpret_cast<const T*>(&t1);
+#pragma unroll
+        for (int e = 0; e < kVec; ++e) consume(a0[e], b0[e]);
+#pragma unroll
+        for (int e = 0; e < kVec; ++e) consume(a1[e], b1[e]);
+    }
+    for (; v < nvec; v += stride) {
+        const uint4 p0 = ld_stream16(pv4 + v), t0 = ld_stream16(tv4 + v);
+        const T* a0 = reinterpret_cast<const T*>(&p0);
+        const T* b0 = reinterpret_cast<const T*>(&t0);
+#pragma unroll
+        for (int e = 0; e < kVec; ++e) consume(a0[e], b0[e]);
+    }
+    for (long long i = nvec * kVec + gtid; i < n; i += stride) consume(preds[i], target[i]);  // tail / unaligned
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < K; ++k) {
+        double s = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(kFull, s, o);
+        __syncthreads();
+        if (lane == 0) sm[warp] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < kRegFlatThreads / 32; ++w) tot += sm[w];
+            partial[(size_t)blockIdx.x * K + k] = tot;
+        }
+    }
+}
+
 // out[k][c] = sum over CTAs (in order) of partial[cta][k][c]
 __global__ void reg_final_kernel(const double* __restrict__ partial, int n_cta, int K, int d, double* __restrict__ out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,6 +208,23 @@ extern "C" int mb200_regression_sums(const void* preds, const void* target, int 
     int gx = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     if ((int64_t)gx * K * d + 8 > mb200_regression_scratch_doubles(n, d, op)) gx = 1;
     if (n > 0) MB200_REQUIRE(preds && target, "NULL pointer");
+    if (d == 1 && n > 0) {  // flat vectorised path
+        constexpr int per_cta = kRegFlatThreads * 8;
+        long long fg = (n + per_cta - 1) / per_cta;
+        if (fg > 296) fg = 296;  // scratch holds 296 partial rows
+        const int g1 = (int)(fg < 1 ? 1 : fg);
+        switch (dtype) {
+            case MB200_F32: reg_flat_kernel<float, false><<<g1, kRegFlatThreads, 0, st>>>((const float*)preds, (const float*)target, n, op, param, epsilon, scratch); break;
+            case MB200_F64: reg_flat_kernel<double, true><<<g1, kRegFlatThreads, 0, st>>>((const double*)preds, (const double*)target, n, op, param, epsilon, scratch); break;
+            case MB200_F16: reg_flat_kernel<__half, false><<<g1, kRegFlatThreads, 0, st>>>((const __half*)preds, (const __half*)target, n, op, param, epsilon, scratch); break;
+            case MB200_BF16: reg_flat_kernel<__nv_bfloat16, false><<<g1, kRegFlatThreads, 0, st>>>((const __nv_bfloat16*)preds, (const __nv_bfloat16*)target, n, op, param, epsilon, scratch); break;
+            default: set_error("regression inputs must be floating point (dtype tag %d)", dtype); return MB200_ERR_INVALID;
+        }
+        reg_final_kernel<<<1, 256, 0, st>>>(scratch, g1, K, 1, out_sums);
+        count_launch();
+        count_launch();
+        return check_cuda(cudaGetLastError(), "regression sums launch");
+    }
     const dim3 grid((unsigned)gx, (unsigned)col_tiles);
     switch (dtype) {
         case MB200_F32:
