@@ -69,6 +69,11 @@ p = torch.rand(n, generator=g, device=dev)
 t = torch.randint(0, 2, (n,), generator=g, device=dev)
 record("K2 binary_stat_counts 2^26 f32 + i64", timed(lambda: _native.binary_stat_counts(p, t, 1, 0.5, None, False)),
        n * 12, "range-flag pass + counting pass: scores are read twice (8 B/elem) + 8 B labels once")
+# K2 multilabel: [2^20, 64] f32 probabilities + int64 targets, per-label counters
+pm = p[: (1 << 26)].view(1 << 20, 64)
+tm = t[: (1 << 26)].view(1 << 20, 64)
+record("K2 multilabel counts [2^20, 64] f32 + i64", timed(lambda: _native.binary_stat_counts(pm, tm, 64, 0.5, None, False)),
+       n * 12, "generic grouped kernel: group index per element, runs of equal group kept in registers")
 # K6: sigmoid_if_logits (flag pass + apply pass): read 4 + read 4 + write 4
 record("K6 sigmoid_if_logits 2^26 f32", timed(lambda: _native.sigmoid_if_logits(p)), n * 8,
        "algorithmic = read + write; the global logits vote costs a second read (12 B/elem of traffic)")

@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(256) bin_count_kernel(BinArgs a) {
     const long long end = min(begin + span, total);
     long long cur = -1;
     unsigned c[4] = {0, 0, 0, 0};
+    const bool small = total < (1ll << 31);
+    const unsigned per_outer_u = (unsigned)per_outer, inner_u = (unsigned)a.inner;
     for (long long i = begin + lane; i < end; i += 32) {
         const long long t = load_label(a.target, a.target_dtype, i);
         if (a.has_ignore && t == a.ignore_index) continue;
@@ -147,8 +149,17 @@ __global__ void __launch_bounds__(256) bin_count_kernel(BinArgs a) {
             continue;  // the reference counts such elements in none of the four masks
         }
         const long long p = pred_label<T>(a, i, logits);
-        const long long n = i / per_outer;
-        const long long l = (i - n * per_outer) / a.inner;
+        long long n, l;
+        if (small) {  // 32-bit index arithmetic: a 64-bit division is ~4x the instructions, and there are two per element
+            const unsigned iu = (unsigned)i;
+            const unsigned nu = iu / per_outer_u;
+            const unsigned rem = iu - nu * per_outer_u;
+            n = nu;
+            l = inner_u == 1u ? rem : rem / inner_u;
+        } else {
+            n = i / per_outer;
+            l = (i - n * per_outer) / a.inner;
+        }
         const long long group = a.samplewise ? n * a.num_labels + l : l;
         if (group != cur) {
             flush_group(a, cur, c, sh);
@@ -244,6 +255,62 @@ __global__ void __launch_bounds__(256) bin_count_flat_kernel(BinArgs a) {
     }
 }
 
+// Multilabel fast path (global counts, `[N, L]` layout with inner == 1, L <= 256): every thread OWNS one label column
+// (column = threadIdx % L, rows strided over the grid), so its four counters live in registers for the whole kernel and
+// consecutive threads still read consecutive addresses.  The generic kernel flushes its register counters to shared
+// memory whenever the group changes — with inner == 1 that is every element.
+template <typename T>
+__global__ void __launch_bounds__(256) bin_count_cols_kernel(BinArgs a) {
+    __shared__ unsigned sh[256 * 4];
+    const int L = (int)a.num_labels;
+    for (int i = threadIdx.x; i < L * 4; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const bool logits = a.logits != nullptr && (*a.logits) != 0u;
+    const int rows_per_block = 256 / L;
+    const int col = threadIdx.x % L;
+    const int rloc = threadIdx.x / L;
+    unsigned c[4] = {0, 0, 0, 0};
+    bool bad_target = false;
+    if (rloc < rows_per_block) {
+        const T* __restrict__ ps = reinterpret_cast<const T*>(a.preds);
+        const long long rstride = (long long)gridDim.x * rows_per_block;
+        long long r = (long long)blockIdx.x * rows_per_block + rloc;
+        auto count = [&](T x, long long t) {
+            if (a.has_ignore && t == a.ignore_index) return;
+            if ((unsigned long long)t > 1ull) {
+                bad_target = true;
+                return;
+            }
+            const int p = pred_from_value<T>(a, x, logits);
+            const bool eq = (p == (int)t);
+            c[0] += (eq && t == 1);
+            c[1] += (!eq && t == 0);
+            c[2] += (eq && t == 0);
+            c[3] += (!eq && t == 1);
+        };
+        for (; r + rstride < a.n_outer; r += 2 * rstride) {  // two independent elements in flight
+            const long long i0 = r * L + col, i1 = (r + rstride) * L + col;
+            const T x0 = ps[i0], x1 = ps[i1];
+            const long long t0 = load_label(a.target, a.target_dtype, i0), t1 = load_label(a.target, a.target_dtype, i1);
+            count(x0, t0);
+            count(x1, t1);
+        }
+        for (; r < a.n_outer; r += rstride) {
+            const long long i0 = r * L + col;
+            count(ps[i0], load_label(a.target, a.target_dtype, i0));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c[k]) atomicAdd(&sh[col * 4 + k], c[k]);
+    }
+    if (__any_sync(kFull, bad_target) && (threadIdx.x & 31) == 0 && a.err) atomicOr(a.err, MB200_FLAG_TARGET_RANGE);
+    __syncthreads();
+    for (int i = threadIdx.x; i < L * 4; i += blockDim.x) {
+        const unsigned v = sh[i];
+        if (v) red_add_u64(a.counts + i, v);
+    }
+}
+
 }  // namespace mb200
 
 using namespace mb200;
@@ -295,6 +362,16 @@ extern "C" int mb200_binary_stat_counts(const void* preds, int preds_dtype, cons
             case MB200_F16: bin_count_flat_kernel<__half><<<grid, 256, 0, st>>>(a); break;
             case MB200_BF16: bin_count_flat_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a); break;
             default: bin_count_flat_kernel<double><<<grid, 256, 0, st>>>(a); break;
+        }
+        count_launch();
+        return check_cuda(cudaGetLastError(), "binary stat counts launch");
+    }
+    if (float_preds && !samplewise && inner == 1 && num_labels >= 2 && num_labels <= 256) {
+        switch (preds_dtype) {
+            case MB200_F32: bin_count_cols_kernel<float><<<grid, 256, 0, st>>>(a); break;
+            case MB200_F16: bin_count_cols_kernel<__half><<<grid, 256, 0, st>>>(a); break;
+            case MB200_BF16: bin_count_cols_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a); break;
+            default: bin_count_cols_kernel<double><<<grid, 256, 0, st>>>(a); break;
         }
         count_launch();
         return check_cuda(cudaGetLastError(), "binary stat counts launch");
