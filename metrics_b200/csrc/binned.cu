@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(256) binned_bucket_kernel(const T* __restrict_
         else atomicAdd(&scratch[slot], 1ull);
     };
     const long long gstride = (long long)gridDim.x * blockDim.x;
+    const bool small = total < (1ll << 31);
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     constexpr int kUnroll = 4;  // independent elements in flight per thread: loads first, then the dependent bucket work
     for (; i + (kUnroll - 1) * gstride < total; i += kUnroll * gstride) {
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(256) binned_bucket_kernel(const T* __restrict_
             long long srow = e;
             cc[u] = 0;
             if (C > 1) {
-                srow = e / C;
+                srow = small ? (long long)((unsigned)e / (unsigned)C) : e / C;  // 32-bit division when it fits
                 cc[u] = (int)(e - srow * C);
             }
             tt[u] = load_label(target, tdtype, flat ? e : srow);
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256) binned_bucket_kernel(const T* __restrict_
         long long srow = i;
         int c = 0;
         if (C > 1) {
-            srow = i / C;
+            srow = small ? (long long)((unsigned)i / (unsigned)C) : i / C;
             c = (int)(i - srow * C);
         }
         commit(c, load_label(target, tdtype, flat ? i : srow), binned_load<T>(preds, i));

@@ -18,5 +18,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:rows
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/curve_launches_1e7.csv python benchmarks/curve_kernel_times.py 10000000 1 > $O/curve_ncu.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/curve_launches_mc.csv python benchmarks/curve_kernel_times.py 16384 1000 >> $O/curve_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:radix_onesweep_kernel -c 1 -o $O/prof_onesweep -f python benchmarks/curve_kernel_times.py 10000000 1 > $O/ncu_onesweep.log 2>&1
+timeout 300 python benchmarks/kernel_rooflines.py $O/kernel_rooflines.json > $O/kernel_rooflines.log 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.draw,temperature.gpu --format=csv > $O/smi.txt
 ls -la $O | tail -30
