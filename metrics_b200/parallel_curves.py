@@ -21,6 +21,7 @@ import torch
 from torch import Tensor
 
 from metrics_b200 import _native
+from metrics_b200.parallel_sync import _gather_equal
 
 
 def sharded_applicable(metric: Any) -> bool:
@@ -83,8 +84,7 @@ def ovr_curve_scalars_sharded(preds: Optional[Tensor], target: Optional[Tensor],
     else:
         padded = torch.zeros(n_max, dtype=torch.int64, device=device)
         padded[:n_local] = target
-        slab = torch.empty((world, n_max), dtype=torch.int64, device=device)
-        dist.all_gather_into_tensor(slab, padded, group=group)
+        slab = _gather_equal(padded, group, world)  # [world, n_max]
         tgt_all = torch.cat([slab[r, :n] for r, n in enumerate(n_all)])
 
     # class-major keys [c_pad, n_local]; rows [d*cpr, (d+1)*cpr) go to rank d
@@ -104,7 +104,5 @@ def ovr_curve_scalars_sharded(preds: Optional[Tensor], target: Optional[Tensor],
     auroc, ap, counts = _native.curve_evaluate_keys(keys_mine, tgt_all, first_class=rank * cpr)
     # per-class results of every rank
     packed = torch.cat([auroc.double().unsqueeze(1), ap.double().unsqueeze(1), counts.double()], dim=1).contiguous()  # [cpr, 5]
-    gathered = torch.empty((world * cpr, 5), dtype=torch.float64, device=device)
-    dist.all_gather_into_tensor(gathered, packed, group=group)
-    gathered = gathered[:num_classes]
+    gathered = _gather_equal(packed, group, world).reshape(world * cpr, 5)[:num_classes]
     return gathered[:, 0].float(), gathered[:, 1].float(), gathered[:, 2:].round().to(torch.int64)

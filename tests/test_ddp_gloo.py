@@ -155,6 +155,68 @@ def _scenarios(rank: int) -> None:
     mp_.unsync()
     assert len(mp_.detection_box) == n_mine and all(torch.equal(a, b) for a, b in zip(mp_.detection_box, local_boxes))
     dist.barrier()
+    _sharded_curve_choreography(rank)
+    dist.barrier()
+
+
+def _sharded_curve_choreography(rank: int) -> None:
+    """Class-sharded AUROC/AP exchange (metrics_b200/parallel_curves.py) over gloo: the collectives, the ragged / empty
+    rank handling and the collective cache decision run for real; the two kernels are replaced by numpy stand-ins built
+    on the oracle (the real kernels are covered on 2 GPUs by tests/test_sharded_curves_gpu.py)."""
+    import numpy as np
+
+    import metrics_b200._native as native
+    import metrics_b200.parallel_curves as pc
+    from oracle import curves as oc
+
+    def to_key(x: torch.Tensor) -> torch.Tensor:  # descending-order key of an f32 score, as the pack kernel emits it
+        b = x.contiguous().view(torch.int32).numpy().view(np.uint32)
+        ok = np.where(b >> 31, ~b, b | np.uint32(0x80000000))
+        return torch.from_numpy((~ok).view(np.int32).copy())
+
+    def from_key(k: np.ndarray) -> np.ndarray:
+        ok = ~k.view(np.uint32)
+        b = np.where(ok >> 31, ok & np.uint32(0x7FFFFFFF), ~ok)
+        return b.view(np.float32)
+
+    def pack_keys(preds, rows_out=None):
+        n, c = preds.shape
+        keys = torch.zeros((rows_out or c, n), dtype=torch.int32)
+        keys[:c] = to_key(preds.float().T.contiguous())
+        return keys
+
+    def evaluate_keys(keys, target, first_class):
+        s, n = keys.shape
+        au, ap, cnt = np.zeros(s, np.float32), np.zeros(s, np.float32), np.zeros((s, 3), np.int64)
+        for j in range(s):
+            score = from_key(keys[j].numpy())
+            lab = (target.numpy() == first_class + j).astype(np.int64)
+            au[j], ap[j] = oc.binary_auroc_exact(score, lab), oc.binary_average_precision_exact(score, lab)
+            cnt[j] = [lab.sum(), n - lab.sum(), np.unique(score).size]
+        return torch.from_numpy(au), torch.from_numpy(ap), torch.from_numpy(cnt)
+
+    native.curve_pack_keys, native.curve_evaluate_keys = pack_keys, evaluate_keys
+    group = torch.distributed.group.WORLD
+    C = 5
+    for case, ns in enumerate(([40, 27], [0, 33], [16, 16])):  # ragged, one empty rank, equal
+        g = torch.Generator().manual_seed(100 * case)
+        alld = []
+        for r in range(WORLD):
+            p = torch.softmax(torch.randn(ns[r], C, generator=g), 1)
+            alld.append((p, torch.randint(0, C, (ns[r],), generator=g)))
+        mine = alld[rank] if ns[rank] else (None, None)
+        auroc, ap, counts = pc.ovr_curve_scalars_sharded(mine[0], mine[1], C, group, torch.device("cpu"))
+        allp, allt = torch.cat([a[0] for a in alld]).numpy(), torch.cat([a[1] for a in alld]).numpy()
+        np.testing.assert_allclose(auroc.numpy(), oc.multiclass_auroc_exact(allp, allt, C), rtol=1e-6)
+        exp_ap = [oc.binary_average_precision_exact(allp[:, c], (allt == c).astype(np.int64)) for c in range(C)]
+        np.testing.assert_allclose(ap.numpy(), exp_ap, rtol=1e-6)
+        assert counts[:, 0].tolist() == [int((allt == c).sum()) for c in range(C)]
+        # collective cache decision: a hit on one rank only must NOT skip the exchange (the other rank would dead-lock)
+        again = pc.ovr_curve_scalars_sharded(mine[0], mine[1], C, group, torch.device("cpu"),
+                                             cached=(auroc, ap, counts) if rank == 0 else None)
+        assert torch.equal(again[0], auroc)
+        both = pc.ovr_curve_scalars_sharded(mine[0], mine[1], C, group, torch.device("cpu"), cached=("sentinel",) * 3)
+        assert both == ("sentinel",) * 3  # every rank had a hit: the memoised value is returned after one tiny all-reduce
 
 
 def _worker(rank: int, port: int, errq) -> None:
