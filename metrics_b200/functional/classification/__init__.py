@@ -81,3 +81,4 @@ from metrics_b200.functional.classification.at_fixed import (  # noqa: F401,E402
     multilabel_specificity_at_sensitivity,
 )
 from metrics_b200.functional.classification.exact_match import exact_match, multiclass_exact_match, multilabel_exact_match  # noqa: F401,E402
+from metrics_b200.functional.classification.logauc import binary_logauc, logauc, multiclass_logauc, multilabel_logauc  # noqa: F401,E402

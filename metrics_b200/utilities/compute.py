@@ -53,7 +53,7 @@ def _auc_compute_without_check(x: Tensor, y: Tensor, direction: float, axis: int
 
 def interp(x: Tensor, xp: Tensor, fp: Tensor) -> Tensor:
     """1-D piecewise-linear interpolation, numpy.interp-like (compute.py:157-187)."""
-    m = (fp[1:] - fp[:-1]) / (xp[1:] - xp[:-1])
+    m = _safe_divide(fp[1:] - fp[:-1], xp[1:] - xp[:-1])  # repeated sample points: slope 0, like the reference (:181)
     b = fp[:-1] - m * xp[:-1]
     idx = torch.sum(torch.ge(x[:, None], xp[None, :]), 1) - 1
     idx = torch.clamp(idx, 0, len(m) - 1)

@@ -71,3 +71,15 @@ def _squeeze_scalar_element_tensor(x: Tensor) -> Tensor:
 
 def _squeeze_if_scalar(data: Any) -> Any:
     return apply_to_collection(data, Tensor, _squeeze_scalar_element_tensor)
+
+
+def interp(x: Tensor, xp: Tensor, fp: Tensor) -> Tensor:
+    """numpy.interp-like evaluation used by the log-AUC window (reference utilities/data.py:249-272; NOT the variant of
+    utilities/compute.py that the macro-averaged curves use): sample points sorted by ``xp``, left-sided interval lookup,
+    plain slopes (a repeated ``xp`` gives an infinite slope there, like the reference).  The sort is stable so that curves
+    with repeated abscissae keep their original (monotone) ordinate order on every device."""
+    order = torch.argsort(xp, stable=True)
+    xp, fp = xp[order], fp[order]
+    slopes = (fp[1:] - fp[:-1]) / (xp[1:] - xp[:-1])
+    idx = torch.clamp(torch.searchsorted(xp, x) - 1, 0, slopes.numel() - 1)
+    return fp[idx] + slopes[idx] * (x - xp[idx])

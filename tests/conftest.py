@@ -86,3 +86,10 @@ def golden_atfixed():
     import numpy as np
 
     return np.load(os.path.join(GOLDEN_DIR, "atfixed.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_logauc():
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN_DIR, "logauc.npz"), allow_pickle=False)

@@ -993,6 +993,38 @@ def atfixed_golden() -> dict:
     return out
 
 
+def logauc_golden() -> dict:
+    """LogAUC: (i) the reference's window integration on synthetic strictly increasing ROC curves (pins the reducer; with
+    repeated fpr values the reference interpolates through an UNSTABLE argsort, utilities/data.py:259, so its output is
+    implementation-defined there), (ii) end-to-end cases whose ROC curves have no repeated fpr next to the window ends."""
+    import warnings
+
+    import torchmetrics  # noqa: F401
+    import torchmetrics.functional.classification as F
+
+    L = sys.modules["torchmetrics.functional.classification.logauc"]
+    warnings.simplefilter("ignore")
+    out: dict = {}
+    g = torch.Generator().manual_seed(321)
+    for k in range(12):
+        n = int(torch.randint(5, 400, (1,), generator=g))
+        fpr = torch.cat([torch.zeros(1), torch.cumsum(torch.rand(n, generator=g) + 1e-3, 0)])
+        fpr = fpr / fpr[-1]
+        tpr = torch.cat([torch.zeros(1), torch.cumsum(torch.rand(n, generator=g), 0)])
+        tpr = tpr / tpr[-1]
+        out[f"curve/{k}/fpr"], out[f"curve/{k}/tpr"] = fpr.numpy(), tpr.numpy()
+        for j, rng in enumerate(((0.001, 0.1), (0.01, 0.5), (0.0005, 1.0))):
+            out[f"curve/{k}/logauc{j}"] = L._binary_logauc_compute(fpr, tpr, rng).numpy()
+    # end to end, exact mode, continuous scores (distinct thresholds); negatives dominate so fpr moves at almost every step
+    n = 3000
+    t = (torch.rand(n, generator=g) < 0.05).long()
+    p = (torch.rand(n, generator=g) * 0.7 + 0.3 * t.float() * torch.rand(n, generator=g)).clamp(0, 1)
+    out["b/preds"], out["b/target"] = p.numpy(), t.numpy()
+    for j, rng in enumerate(((0.001, 0.1), (0.01, 0.5))):
+        out[f"b/logauc{j}"] = F.binary_logauc(p, t, fpr_range=rng).numpy()
+    return out
+
+
 def regression_golden() -> dict:
     import torchmetrics.functional as TF
     import torchmetrics.regression as TR
@@ -1077,6 +1109,11 @@ if __name__ == "__main__":
     if "atfixed" in which:
         data = atfixed_golden()
         path = os.path.join(HERE, "atfixed.npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
+    if "logauc" in which:
+        data = logauc_golden()
+        path = os.path.join(HERE, "logauc.npz")
         np.savez_compressed(path, **data)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
     if "curves" in which:
