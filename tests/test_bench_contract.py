@@ -1,0 +1,29 @@
+"""CPU: the reference arm of bench.py honours the output contract — exactly ONE JSON line on stdout with the keys the
+driver reads (the GPU arm shares the same printing code; it is exercised on the GPU box)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "updates/s"
+    assert d["metric"].startswith("metric-updates/sec") and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["config"]["workload"].startswith("MulticlassConfusionMatrix")
+
+
+def test_reference_arm_non_zero_rank_exits_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "0"], cwd=ROOT, capture_output=True, text=True, timeout=120, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
