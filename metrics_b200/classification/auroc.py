@@ -6,11 +6,8 @@ from typing import Any, List, Optional, Union
 from torch import Tensor
 from typing_extensions import Literal
 
-from metrics_b200.classification.precision_recall_curve import (
-    BinaryPrecisionRecallCurve,
-    MulticlassPrecisionRecallCurve,
-    MultilabelPrecisionRecallCurve,
-)
+from metrics_b200.classification import precision_recall_curve as _prc
+from metrics_b200.classification._curve_common import _RankingScore, build_for_task, finish_score_init
 from metrics_b200.functional.classification.auroc import (
     _binary_auroc_arg_validation,
     _binary_auroc_compute,
@@ -21,14 +18,8 @@ from metrics_b200.functional.classification.auroc import (
 )
 
 
-class BinaryAUROC(BinaryPrecisionRecallCurve):
+class BinaryAUROC(_RankingScore, _prc.BinaryPrecisionRecallCurve):
     """Reference :44-125."""
-
-    is_differentiable: bool = False
-    higher_is_better: Optional[bool] = True
-    full_state_update: bool = False
-    plot_lower_bound: float = 0.0
-    plot_upper_bound: float = 1.0
 
     def __init__(
         self,
@@ -50,14 +41,9 @@ class BinaryAUROC(BinaryPrecisionRecallCurve):
         return _binary_auroc_compute(self._state(), self.thresholds, self.max_fpr)
 
 
-class MulticlassAUROC(MulticlassPrecisionRecallCurve):
+class MulticlassAUROC(_RankingScore, _prc.MulticlassPrecisionRecallCurve):
     """Reference :170-282."""
 
-    is_differentiable: bool = False
-    higher_is_better: Optional[bool] = True
-    full_state_update: bool = False
-    plot_lower_bound: float = 0.0
-    plot_upper_bound: float = 1.0
     plot_legend_name: str = "Class"
 
     def _compute_distributed(self):
@@ -102,17 +88,11 @@ class MulticlassAUROC(MulticlassPrecisionRecallCurve):
 
 from metrics_b200.classification.base import _ClassificationTaskWrapper  # noqa: E402
 from metrics_b200.metric import Metric  # noqa: E402
-from metrics_b200.utilities.enums import ClassificationTask  # noqa: E402
 
 
-class MultilabelAUROC(MultilabelPrecisionRecallCurve):
+class MultilabelAUROC(_RankingScore, _prc.MultilabelPrecisionRecallCurve):
     """Reference :281-429."""
 
-    is_differentiable: bool = False
-    higher_is_better: Optional[bool] = True
-    full_state_update: bool = False
-    plot_lower_bound: float = 0.0
-    plot_upper_bound: float = 1.0
     plot_legend_name: str = "Label"
 
     def __init__(
@@ -125,10 +105,8 @@ class MultilabelAUROC(MultilabelPrecisionRecallCurve):
         **kwargs: Any,
     ) -> None:
         super().__init__(num_labels=num_labels, thresholds=thresholds, ignore_index=ignore_index, validate_args=False, **kwargs)
-        if validate_args:
-            _multilabel_auroc_arg_validation(num_labels, average, thresholds, ignore_index)
-        self.average = average
-        self.validate_args = validate_args
+        finish_score_init(self, average, validate_args,
+                          lambda: _multilabel_auroc_arg_validation(num_labels, average, thresholds, ignore_index))
 
     def compute(self) -> Tensor:
         scalars = None if self.average == "micro" else self._curve_scalars()
@@ -151,14 +129,8 @@ class AUROC(_ClassificationTaskWrapper):
         validate_args: bool = True,
         **kwargs: Any,
     ) -> Metric:
-        task = ClassificationTask.from_str(task)
-        kwargs.update({"thresholds": thresholds, "ignore_index": ignore_index, "validate_args": validate_args})
-        if task == ClassificationTask.BINARY:
-            return BinaryAUROC(max_fpr, **kwargs)
-        if task == ClassificationTask.MULTICLASS:
-            if not isinstance(num_classes, int):
-                raise ValueError(f"`num_classes` is expected to be `int` but `{type(num_classes)} was passed.`")
-            return MulticlassAUROC(num_classes, average, **kwargs)
-        if not isinstance(num_labels, int):
-            raise ValueError(f"`num_labels` is expected to be `int` but `{type(num_labels)} was passed.`")
-        return MultilabelAUROC(num_labels, average, **kwargs)
+        shared = dict(kwargs, thresholds=thresholds, ignore_index=ignore_index, validate_args=validate_args)
+        return build_for_task(task, num_classes, num_labels,
+                              lambda: BinaryAUROC(max_fpr, **shared),
+                              lambda c: MulticlassAUROC(c, average, **shared),
+                              lambda n: MultilabelAUROC(n, average, **shared))

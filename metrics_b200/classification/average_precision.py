@@ -7,11 +7,8 @@ import torch
 from torch import Tensor
 from typing_extensions import Literal
 
-from metrics_b200.classification.precision_recall_curve import (
-    BinaryPrecisionRecallCurve,
-    MulticlassPrecisionRecallCurve,
-    MultilabelPrecisionRecallCurve,
-)
+from metrics_b200.classification import precision_recall_curve as _prc
+from metrics_b200.classification._curve_common import _RankingScore, build_for_task, finish_score_init
 from metrics_b200.functional.classification.average_precision import (
     _binary_average_precision_compute,
     _multiclass_average_precision_arg_validation,
@@ -21,27 +18,17 @@ from metrics_b200.functional.classification.average_precision import (
 )
 
 
-class BinaryAveragePrecision(BinaryPrecisionRecallCurve):
+class BinaryAveragePrecision(_RankingScore, _prc.BinaryPrecisionRecallCurve):
     """Reference :47-119."""
 
-    is_differentiable: bool = False
-    higher_is_better: Optional[bool] = True
-    full_state_update: bool = False
-    plot_lower_bound: float = 0.0
-    plot_upper_bound: float = 1.0
 
     def compute(self) -> Tensor:
         return _binary_average_precision_compute(self._state(), self.thresholds, scalars=self._curve_scalars())
 
 
-class MulticlassAveragePrecision(MulticlassPrecisionRecallCurve):
+class MulticlassAveragePrecision(_RankingScore, _prc.MulticlassPrecisionRecallCurve):
     """Reference :170-290."""
 
-    is_differentiable: bool = False
-    higher_is_better: Optional[bool] = True
-    full_state_update: bool = False
-    plot_lower_bound: float = 0.0
-    plot_upper_bound: float = 1.0
     plot_legend_name: str = "Class"
 
     def _compute_distributed(self):
@@ -69,10 +56,8 @@ class MulticlassAveragePrecision(MulticlassPrecisionRecallCurve):
         super().__init__(
             num_classes=num_classes, thresholds=thresholds, ignore_index=ignore_index, validate_args=False, **kwargs
         )
-        if validate_args:
-            _multiclass_average_precision_arg_validation(num_classes, average, thresholds, ignore_index)
-        self.average = average
-        self.validate_args = validate_args
+        finish_score_init(self, average, validate_args,
+                          lambda: _multiclass_average_precision_arg_validation(num_classes, average, thresholds, ignore_index))
 
     def _compute_local(self) -> Tensor:
         scalars = self._curve_scalars(self.num_classes)
@@ -89,14 +74,9 @@ class MulticlassAveragePrecision(MulticlassPrecisionRecallCurve):
         return self._compute_local()
 
 
-class MultilabelAveragePrecision(MultilabelPrecisionRecallCurve):
+class MultilabelAveragePrecision(_RankingScore, _prc.MultilabelPrecisionRecallCurve):
     """Reference :293-441."""
 
-    is_differentiable: bool = False
-    higher_is_better: Optional[bool] = True
-    full_state_update: bool = False
-    plot_lower_bound: float = 0.0
-    plot_upper_bound: float = 1.0
     plot_legend_name: str = "Label"
 
     def __init__(
@@ -109,10 +89,8 @@ class MultilabelAveragePrecision(MultilabelPrecisionRecallCurve):
         **kwargs: Any,
     ) -> None:
         super().__init__(num_labels=num_labels, thresholds=thresholds, ignore_index=ignore_index, validate_args=False, **kwargs)
-        if validate_args:
-            _multilabel_average_precision_arg_validation(num_labels, average, thresholds, ignore_index)
-        self.average = average
-        self.validate_args = validate_args
+        finish_score_init(self, average, validate_args,
+                          lambda: _multilabel_average_precision_arg_validation(num_labels, average, thresholds, ignore_index))
 
     def compute(self) -> Tensor:
         scalars = None if self.average == "micro" else self._curve_scalars()
@@ -122,7 +100,6 @@ class MultilabelAveragePrecision(MultilabelPrecisionRecallCurve):
 
 from metrics_b200.classification.base import _ClassificationTaskWrapper  # noqa: E402
 from metrics_b200.metric import Metric  # noqa: E402
-from metrics_b200.utilities.enums import ClassificationTask  # noqa: E402
 
 
 class AveragePrecision(_ClassificationTaskWrapper):
@@ -139,14 +116,8 @@ class AveragePrecision(_ClassificationTaskWrapper):
         validate_args: bool = True,
         **kwargs: Any,
     ) -> Metric:
-        task = ClassificationTask.from_str(task)
-        kwargs.update({"thresholds": thresholds, "ignore_index": ignore_index, "validate_args": validate_args})
-        if task == ClassificationTask.BINARY:
-            return BinaryAveragePrecision(**kwargs)
-        if task == ClassificationTask.MULTICLASS:
-            if not isinstance(num_classes, int):
-                raise ValueError(f"`num_classes` is expected to be `int` but `{type(num_classes)} was passed.`")
-            return MulticlassAveragePrecision(num_classes, average, **kwargs)
-        if not isinstance(num_labels, int):
-            raise ValueError(f"`num_labels` is expected to be `int` but `{type(num_labels)} was passed.`")
-        return MultilabelAveragePrecision(num_labels, average, **kwargs)
+        shared = dict(kwargs, thresholds=thresholds, ignore_index=ignore_index, validate_args=validate_args)
+        return build_for_task(task, num_classes, num_labels,
+                              lambda: BinaryAveragePrecision(**shared),
+                              lambda c: MulticlassAveragePrecision(c, average, **shared),
+                              lambda n: MultilabelAveragePrecision(n, average, **shared))

@@ -55,17 +55,30 @@ class BinaryPrecisionRecallCurve(Metric):
             _binary_precision_recall_curve_arg_validation(thresholds, ignore_index)
         self.ignore_index = ignore_index
         self.validate_args = validate_args
-        thresholds = _adjust_threshold_arg(thresholds)
-        if thresholds is None:
-            self.thresholds = thresholds
-            self.add_state("preds", default=[], dist_reduce_fx="cat")
-            self.add_state("target", default=[], dist_reduce_fx="cat")
-        else:  # binned mode: constant-size state (reference :156-160)
-            self.register_buffer("thresholds", thresholds, persistent=False)
-            self.add_state("confmat", default=torch.zeros(len(thresholds), 2, 2, dtype=torch.long), dist_reduce_fx="sum")
+        self._install_curve_states(thresholds, lambda n_thr: (n_thr, 2, 2))
+
+    def _install_curve_states(self, thresholds, binned_shape) -> None:
+        """Exact mode (``thresholds=None``): list states ``preds`` / ``target`` (``cat``).  Binned mode: a non-persistent
+        ``thresholds`` buffer and ONE constant-size int64 ``confmat`` state of shape ``binned_shape(T)`` (``sum``)."""
+        grid = _adjust_threshold_arg(thresholds)
+        if grid is None:
+            self.thresholds = None
+            for name in ("preds", "target"):
+                self.add_state(name, default=[], dist_reduce_fx="cat")
+        else:
+            self.register_buffer("thresholds", grid, persistent=False)
+            self.add_state("confmat", default=torch.zeros(*binned_shape(len(grid)), dtype=torch.long), dist_reduce_fx="sum")
         # One sort + scan yields AUROC *and* AP: members of a MetricCollection compute group share this dict by reference
         # (collections.py links it like a state), so the second metric of the group reuses the first one's evaluation.
         self._group_cache: dict = {}
+
+    def _accumulate(self, state) -> None:
+        """Fold one batch's functional state into the metric: add the binned counts, or keep the formatted batch."""
+        if isinstance(state, Tensor):
+            self.confmat += state
+        else:
+            self.preds.append(state[0])
+            self.target.append(state[1])
 
     def reset(self) -> None:
         self._group_cache.clear()
@@ -108,11 +121,7 @@ class BinaryPrecisionRecallCurve(Metric):
             _binary_precision_recall_curve_tensor_validation(preds, target, self.ignore_index)
         preds, target, _ = _binary_precision_recall_curve_format(preds, target, self.thresholds, self.ignore_index)
         state = _binary_precision_recall_curve_update(preds, target, self.thresholds)
-        if isinstance(state, Tensor):
-            self.confmat += state
-        else:
-            self.preds.append(state[0])
-            self.target.append(state[1])
+        self._accumulate(state)
 
     def _state(self):
         if self.thresholds is not None:
@@ -148,20 +157,14 @@ class MulticlassPrecisionRecallCurve(Metric):
         self.average = average
         self.ignore_index = ignore_index
         self.validate_args = validate_args
-        thresholds = _adjust_threshold_arg(thresholds)
-        if thresholds is None:
-            self.thresholds = thresholds
-            self.add_state("preds", default=[], dist_reduce_fx="cat")
-            self.add_state("target", default=[], dist_reduce_fx="cat")
-        else:  # binned mode (reference :353-359); micro average keeps the binary [T, 2, 2] layout
-            self.register_buffer("thresholds", thresholds, persistent=False)
-            shape = (len(thresholds), 2, 2) if average == "micro" else (len(thresholds), num_classes, 2, 2)
-            self.add_state("confmat", default=torch.zeros(*shape, dtype=torch.long), dist_reduce_fx="sum")
-        self._group_cache: dict = {}  # see BinaryPrecisionRecallCurve
+        # binned mode (reference :353-359): micro average keeps the binary [T, 2, 2] layout
+        self._install_curve_states(thresholds, lambda n_thr: (n_thr, 2, 2) if average == "micro" else (n_thr, num_classes, 2, 2))
 
     reset = BinaryPrecisionRecallCurve.reset
     _curve_scalars = BinaryPrecisionRecallCurve._curve_scalars
     _cache_put = BinaryPrecisionRecallCurve._cache_put
+    _install_curve_states = BinaryPrecisionRecallCurve._install_curve_states
+    _accumulate = BinaryPrecisionRecallCurve._accumulate
 
     def update(self, preds: Tensor, target: Tensor) -> None:
         self._group_cache.clear()
@@ -171,11 +174,7 @@ class MulticlassPrecisionRecallCurve(Metric):
             preds, target, self.num_classes, self.thresholds, self.ignore_index, self.average
         )
         state = _multiclass_precision_recall_curve_update(preds, target, self.num_classes, self.thresholds, self.average)
-        if isinstance(state, Tensor):
-            self.confmat += state
-        else:
-            self.preds.append(state[0])
-            self.target.append(state[1])
+        self._accumulate(state)
 
     _state = BinaryPrecisionRecallCurve._state
 
@@ -207,19 +206,13 @@ class MultilabelPrecisionRecallCurve(Metric):
         self.num_labels = num_labels
         self.ignore_index = ignore_index
         self.validate_args = validate_args
-        thresholds = _adjust_threshold_arg(thresholds)
-        if thresholds is None:
-            self.thresholds = thresholds
-            self.add_state("preds", default=[], dist_reduce_fx="cat")
-            self.add_state("target", default=[], dist_reduce_fx="cat")
-        else:
-            self.register_buffer("thresholds", thresholds, persistent=False)
-            self.add_state("confmat", default=torch.zeros(len(thresholds), num_labels, 2, 2, dtype=torch.long), dist_reduce_fx="sum")
-        self._group_cache: dict = {}  # see BinaryPrecisionRecallCurve
+        self._install_curve_states(thresholds, lambda n_thr: (n_thr, num_labels, 2, 2))
 
     reset = BinaryPrecisionRecallCurve.reset
     _cache_put = BinaryPrecisionRecallCurve._cache_put
     _state = BinaryPrecisionRecallCurve._state
+    _install_curve_states = BinaryPrecisionRecallCurve._install_curve_states
+    _accumulate = BinaryPrecisionRecallCurve._accumulate
 
     def _curve_scalars(self):
         """Per-label ``(auroc, ap, counts)`` from ONE `mb200_curve_evaluate_multilabel` call, shared by the members of a
@@ -247,18 +240,14 @@ class MultilabelPrecisionRecallCurve(Metric):
             preds, target, self.num_labels, self.thresholds, self.ignore_index
         )
         state = _multilabel_precision_recall_curve_update(preds, target, self.num_labels, self.thresholds)
-        if isinstance(state, Tensor):
-            self.confmat += state
-        else:
-            self.preds.append(state[0])
-            self.target.append(state[1])
+        self._accumulate(state)
 
     def compute(self):
         return _multilabel_precision_recall_curve_compute(self._state(), self.num_labels, self.thresholds, self.ignore_index)
 
 
 from metrics_b200.classification.base import _ClassificationTaskWrapper  # noqa: E402
-from metrics_b200.utilities.enums import ClassificationTask  # noqa: E402
+from metrics_b200.classification._curve_common import build_for_task  # noqa: E402
 
 
 class PrecisionRecallCurve(_ClassificationTaskWrapper):
@@ -274,14 +263,7 @@ class PrecisionRecallCurve(_ClassificationTaskWrapper):
         validate_args: bool = True,
         **kwargs: Any,
     ) -> Metric:
-        task = ClassificationTask.from_str(task)
-        kwargs.update({"thresholds": thresholds, "ignore_index": ignore_index, "validate_args": validate_args})
-        if task == ClassificationTask.BINARY:
-            return BinaryPrecisionRecallCurve(**kwargs)
-        if task == ClassificationTask.MULTICLASS:
-            if not isinstance(num_classes, int):
-                raise ValueError(f"`num_classes` is expected to be `int` but `{type(num_classes)} was passed.`")
-            return MulticlassPrecisionRecallCurve(num_classes, **kwargs)
-        if not isinstance(num_labels, int):
-            raise ValueError(f"`num_labels` is expected to be `int` but `{type(num_labels)} was passed.`")
-        return MultilabelPrecisionRecallCurve(num_labels, **kwargs)
+        shared = dict(kwargs, thresholds=thresholds, ignore_index=ignore_index, validate_args=validate_args)
+        return build_for_task(task, num_classes, num_labels, lambda: BinaryPrecisionRecallCurve(**shared),
+                              lambda c: MulticlassPrecisionRecallCurve(c, **shared),
+                              lambda n: MultilabelPrecisionRecallCurve(n, **shared))

@@ -38,7 +38,7 @@ from typing_extensions import Literal  # noqa: E402
 
 from metrics_b200.classification.base import _ClassificationTaskWrapper  # noqa: E402
 from metrics_b200.metric import Metric  # noqa: E402
-from metrics_b200.utilities.enums import ClassificationTask  # noqa: E402
+from metrics_b200.classification._curve_common import build_for_task  # noqa: E402
 
 
 class ROC(_ClassificationTaskWrapper):
@@ -54,14 +54,6 @@ class ROC(_ClassificationTaskWrapper):
         validate_args: bool = True,
         **kwargs: Any,
     ) -> Metric:
-        task = ClassificationTask.from_str(task)
-        kwargs.update({"thresholds": thresholds, "ignore_index": ignore_index, "validate_args": validate_args})
-        if task == ClassificationTask.BINARY:
-            return BinaryROC(**kwargs)
-        if task == ClassificationTask.MULTICLASS:
-            if not isinstance(num_classes, int):
-                raise ValueError(f"`num_classes` is expected to be `int` but `{type(num_classes)} was passed.`")
-            return MulticlassROC(num_classes, **kwargs)
-        if not isinstance(num_labels, int):
-            raise ValueError(f"`num_labels` is expected to be `int` but `{type(num_labels)} was passed.`")
-        return MultilabelROC(num_labels, **kwargs)
+        shared = dict(kwargs, thresholds=thresholds, ignore_index=ignore_index, validate_args=validate_args)
+        return build_for_task(task, num_classes, num_labels, lambda: BinaryROC(**shared),
+                              lambda c: MulticlassROC(c, **shared), lambda n: MultilabelROC(n, **shared))
