@@ -64,7 +64,6 @@ class MetricCollection(ModuleDict):
     """A dict of metrics driven with a single call; see module docstring."""
 
     _modules: Dict[str, Metric]  # type: ignore[assignment]
-    _groups: Dict[int, List[str]]
     __jit_unused_properties__ = ["metric_state"]
 
     def __init__(

@@ -7,7 +7,7 @@
 HERE="$(cd "$(dirname "$0")" && pwd)"
 printf "[pytest]\naddopts =\n" > /tmp/mb200_ref_pytest.ini
 cd /tmp
-for f in test_metric test_composition test_hashing test_ddp; do
+for f in test_metric test_composition test_hashing test_ddp test_collections; do
     echo "=== bases/$f.py"
     USE_PYTEST_POOL=1 PYTHONPATH="$HERE:/root/reference/tests" python -m pytest -c /tmp/mb200_ref_pytest.ini --rootdir /tmp \
         /root/reference/tests/unittests/bases/$f.py -q --no-header -p no:cacheprovider 2>&1 | grep "passed\|failed" | tail -2

@@ -287,3 +287,17 @@ def test_collection_nested_and_dict_results():
     fwd = mc(1.0)
     assert float(fwd["a"]) == 1.0
     assert set(mc.metric_state) == {"D", "in_DummySum"}  # nested members are registered under their renamed key
+
+
+def test_collection_can_be_scripted():
+    """`torch.jit.script(MetricCollection(...))` works (reference tests/unittests/bases/test_collections.py:42-50): string
+    class-level annotations on the collection would make TorchScript's annotation resolution fail."""
+    import warnings
+
+    from metrics_b200 import MetricCollection
+    from tests.dummies import DummyMean, DummySum
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        scripted = torch.jit.script(MetricCollection({"a": DummySum(), "b": DummyMean()}))
+    assert scripted is not None
