@@ -26,7 +26,6 @@ class MulticlassConfusionMatrix(Metric):
     is_differentiable: bool = False
     higher_is_better: Optional[bool] = None
     full_state_update: bool = False
-    confmat: Tensor
 
     def __init__(
         self,
@@ -77,7 +76,6 @@ class BinaryConfusionMatrix(Metric):
     is_differentiable: bool = False
     higher_is_better: Optional[bool] = None
     full_state_update: bool = False
-    confmat: Tensor
 
     def __init__(
         self,
@@ -111,7 +109,6 @@ class MultilabelConfusionMatrix(Metric):
     is_differentiable: bool = False
     higher_is_better: Optional[bool] = None
     full_state_update: bool = False
-    confmat: Tensor
 
     def __init__(
         self,

@@ -40,8 +40,6 @@ class BinaryPrecisionRecallCurve(Metric):
     is_differentiable: bool = False
     higher_is_better: Optional[bool] = None
     full_state_update: bool = False
-    preds: List[Tensor]
-    target: List[Tensor]
 
     def __init__(
         self,
@@ -138,8 +136,6 @@ class MulticlassPrecisionRecallCurve(Metric):
     is_differentiable: bool = False
     higher_is_better: Optional[bool] = None
     full_state_update: bool = False
-    preds: List[Tensor]
-    target: List[Tensor]
 
     def __init__(
         self,
@@ -189,8 +185,6 @@ class MultilabelPrecisionRecallCurve(Metric):
     is_differentiable: bool = False
     higher_is_better: Optional[bool] = None
     full_state_update: bool = False
-    preds: List[Tensor]
-    target: List[Tensor]
 
     def __init__(
         self,

@@ -23,10 +23,6 @@ class _AbstractStatScores(Metric):
     """Holds the four counters ``tp, fp, tn, fn`` (reference :43-88): int64 tensors with ``sum`` reduction, or
     lists with ``cat`` reduction when ``multidim_average="samplewise"``."""
 
-    tp: Union[List[Tensor], Tensor]
-    fp: Union[List[Tensor], Tensor]
-    tn: Union[List[Tensor], Tensor]
-    fn: Union[List[Tensor], Tensor]
 
     def _create_state(self, size: int, multidim_average: str = "global") -> None:
         for name in ("tp", "fp", "tn", "fn"):

@@ -47,13 +47,6 @@ class MeanAveragePrecision(Metric):
     plot_lower_bound: float = 0.0
     plot_upper_bound: float = 1.0
 
-    detection_box: List[Tensor]
-    detection_scores: List[Tensor]
-    detection_labels: List[Tensor]
-    groundtruth_box: List[Tensor]
-    groundtruth_labels: List[Tensor]
-    groundtruth_crowds: List[Tensor]
-    groundtruth_area: List[Tensor]
     warn_on_many_detections: bool = True
 
     def __init__(

@@ -82,3 +82,16 @@ from metrics_b200.functional.classification.at_fixed import (  # noqa: F401,E402
 )
 from metrics_b200.functional.classification.exact_match import exact_match, multiclass_exact_match, multilabel_exact_match  # noqa: F401,E402
 from metrics_b200.functional.classification.logauc import binary_logauc, logauc, multiclass_logauc, multilabel_logauc  # noqa: F401,E402
+from metrics_b200.functional.classification.accuracy import accuracy  # noqa: F401,E402
+from metrics_b200.functional.classification.auroc import auroc  # noqa: F401,E402
+from metrics_b200.functional.classification.average_precision import average_precision  # noqa: F401,E402
+from metrics_b200.functional.classification.roc import roc  # noqa: F401,E402
+from metrics_b200.functional.classification.precision_recall_curve import precision_recall_curve  # noqa: F401,E402
+from metrics_b200.functional.classification.f_beta import f1_score, fbeta_score  # noqa: F401,E402
+from metrics_b200.functional.classification.confmat_metrics import cohen_kappa, jaccard_index, matthews_corrcoef  # noqa: F401,E402
+from metrics_b200.functional.classification.at_fixed import (  # noqa: F401,E402
+    precision_at_fixed_recall,
+    recall_at_fixed_precision,
+    sensitivity_at_specificity,
+    specificity_at_sensitivity,
+)

@@ -102,3 +102,22 @@ def multilabel_accuracy(
         preds, target, num_labels, threshold, multidim_average, ignore_index, validate_args
     )
     return _accuracy_reduce(tp, fp, tn, fn, average=average, multidim_average=multidim_average, multilabel=True)
+
+
+def accuracy(preds: Tensor, target: Tensor, task: Literal["binary", "multiclass", "multilabel"], threshold: float = 0.5,
+             num_classes: Optional[int] = None, num_labels: Optional[int] = None,
+             average: Optional[Literal["micro", "macro", "weighted", "none"]] = "micro",
+             multidim_average: Literal["global", "samplewise"] = "global", top_k: Optional[int] = 1,
+             ignore_index: Optional[int] = None, validate_args: bool = True) -> Tensor:
+    """Task wrapper (reference :473-548)."""
+    from metrics_b200.functional.classification._task import call_for_task
+
+    def mc(c: int) -> Tensor:
+        if not isinstance(top_k, int):
+            raise ValueError(f"`top_k` is expected to be `int` but `{type(top_k)} was passed.`")
+        return multiclass_accuracy(preds, target, c, average, top_k, multidim_average, ignore_index, validate_args)
+
+    return call_for_task(
+        task, num_classes, num_labels,
+        lambda: binary_accuracy(preds, target, threshold, multidim_average, ignore_index, validate_args), mc,
+        lambda n: multilabel_accuracy(preds, target, n, threshold, average, multidim_average, ignore_index, validate_args))

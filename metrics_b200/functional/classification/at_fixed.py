@@ -226,3 +226,33 @@ multilabel_sensitivity_at_specificity = _make_multilabel("sensitivity_at_specifi
 binary_specificity_at_sensitivity = _make_binary("specificity_at_sensitivity")
 multiclass_specificity_at_sensitivity = _make_multiclass("specificity_at_sensitivity")
 multilabel_specificity_at_sensitivity = _make_multilabel("specificity_at_sensitivity")
+
+
+def _make_task(kind: str, b: Callable, mc: Callable, ml: Callable) -> Callable:
+    fam = _FAMILIES[kind]
+
+    def fn_(preds: Tensor, target: Tensor, task: Literal["binary", "multiclass", "multilabel"], floor: Optional[float] = None,
+            thresholds: Optional[Union[int, List[float], Tensor]] = None, num_classes: Optional[int] = None,
+            num_labels: Optional[int] = None, ignore_index: Optional[int] = None, validate_args: bool = True,
+            **named: float):
+        from metrics_b200.functional.classification._task import call_for_task
+
+        floor = _named_floor(fam, floor, named)
+        return call_for_task(task, num_classes, num_labels,
+                             lambda: b(preds, target, floor, thresholds, ignore_index, validate_args),
+                             lambda c: mc(preds, target, c, floor, thresholds, ignore_index, validate_args),
+                             lambda n: ml(preds, target, n, floor, thresholds, ignore_index, validate_args))
+
+    fn_.__name__ = fn_.__qualname__ = kind
+    fn_.__doc__ = f"Task wrapper for {kind.replace('_', ' ')} (reference {fam.reference}); `floor` = `{fam.arg}`."
+    return fn_
+
+
+recall_at_fixed_precision = _make_task("recall_at_fixed_precision", binary_recall_at_fixed_precision,
+                                       multiclass_recall_at_fixed_precision, multilabel_recall_at_fixed_precision)
+precision_at_fixed_recall = _make_task("precision_at_fixed_recall", binary_precision_at_fixed_recall,
+                                       multiclass_precision_at_fixed_recall, multilabel_precision_at_fixed_recall)
+sensitivity_at_specificity = _make_task("sensitivity_at_specificity", binary_sensitivity_at_specificity,
+                                        multiclass_sensitivity_at_specificity, multilabel_sensitivity_at_specificity)
+specificity_at_sensitivity = _make_task("specificity_at_sensitivity", binary_specificity_at_sensitivity,
+                                        multiclass_specificity_at_sensitivity, multilabel_specificity_at_sensitivity)

@@ -251,3 +251,17 @@ def multilabel_auroc(
     preds, target, thresholds = _multilabel_precision_recall_curve_format(preds, target, num_labels, thresholds, ignore_index)
     state = _multilabel_precision_recall_curve_update(preds, target, num_labels, thresholds)
     return _multilabel_auroc_compute(state, num_labels, average, thresholds, ignore_index)
+
+
+def auroc(preds: Tensor, target: Tensor, task: Literal["binary", "multiclass", "multilabel"],
+          thresholds: Optional[Union[int, List[float], Tensor]] = None, num_classes: Optional[int] = None,
+          num_labels: Optional[int] = None, average: Optional[Literal["macro", "weighted", "none"]] = "macro",
+          max_fpr: Optional[float] = None, ignore_index: Optional[int] = None, validate_args: bool = True) -> Optional[Tensor]:
+    """Task wrapper (reference :428-491)."""
+    from metrics_b200.functional.classification._task import call_for_task
+
+    return call_for_task(
+        task, num_classes, num_labels,
+        lambda: binary_auroc(preds, target, max_fpr, thresholds, ignore_index, validate_args),
+        lambda c: multiclass_auroc(preds, target, c, average, thresholds, ignore_index, validate_args),
+        lambda n: multilabel_auroc(preds, target, n, average, thresholds, ignore_index, validate_args))

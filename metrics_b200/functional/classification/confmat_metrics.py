@@ -205,3 +205,42 @@ def multilabel_matthews_corrcoef(preds: Tensor, target: Tensor, num_labels: int,
     """Reference matthews_corrcoef.py:208-270."""
     return _matthews_corrcoef_reduce(
         multilabel_confusion_matrix(preds, target, num_labels, threshold, None, ignore_index, validate_args))
+
+
+def cohen_kappa(preds: Tensor, target: Tensor, task: Literal["binary", "multiclass"], threshold: float = 0.5,
+                num_classes: Optional[int] = None, weights: Optional[Literal["linear", "quadratic", "none"]] = None,
+                ignore_index: Optional[int] = None, validate_args: bool = True) -> Tensor:
+    """Task wrapper (reference cohen_kappa.py:228-278); binary and multiclass only."""
+    from metrics_b200.functional.classification._task import call_for_task
+
+    return call_for_task(
+        task, num_classes, None,
+        lambda: binary_cohen_kappa(preds, target, threshold, weights, ignore_index, validate_args),
+        lambda c: multiclass_cohen_kappa(preds, target, c, weights, ignore_index, validate_args), None)
+
+
+def jaccard_index(preds: Tensor, target: Tensor, task: Literal["binary", "multiclass", "multilabel"], threshold: float = 0.5,
+                  num_classes: Optional[int] = None, num_labels: Optional[int] = None,
+                  average: Optional[Literal["micro", "macro", "weighted", "none"]] = "macro",
+                  ignore_index: Optional[int] = None, validate_args: bool = True, zero_division: float = 0.0) -> Tensor:
+    """Task wrapper (reference jaccard.py:348-420)."""
+    from metrics_b200.functional.classification._task import call_for_task
+
+    return call_for_task(
+        task, num_classes, num_labels,
+        lambda: binary_jaccard_index(preds, target, threshold, ignore_index, validate_args, zero_division),
+        lambda c: multiclass_jaccard_index(preds, target, c, average, ignore_index, validate_args, zero_division),
+        lambda n: multilabel_jaccard_index(preds, target, n, threshold, average, ignore_index, validate_args, zero_division))
+
+
+def matthews_corrcoef(preds: Tensor, target: Tensor, task: Literal["binary", "multiclass", "multilabel"], threshold: float = 0.5,
+                      num_classes: Optional[int] = None, num_labels: Optional[int] = None,
+                      ignore_index: Optional[int] = None, validate_args: bool = True) -> Tensor:
+    """Task wrapper (reference matthews_corrcoef.py:273-330)."""
+    from metrics_b200.functional.classification._task import call_for_task
+
+    return call_for_task(
+        task, num_classes, num_labels,
+        lambda: binary_matthews_corrcoef(preds, target, threshold, ignore_index, validate_args),
+        lambda c: multiclass_matthews_corrcoef(preds, target, c, ignore_index, validate_args),
+        lambda n: multilabel_matthews_corrcoef(preds, target, n, threshold, ignore_index, validate_args))

@@ -161,3 +161,35 @@ def multilabel_f1_score(
     return multilabel_fbeta_score(
         preds, target, 1.0, num_labels, threshold, average, multidim_average, ignore_index, validate_args, zero_division
     )
+
+
+def fbeta_score(preds: Tensor, target: Tensor, task: Literal["binary", "multiclass", "multilabel"], beta: float = 1.0,
+                threshold: float = 0.5, num_classes: Optional[int] = None, num_labels: Optional[int] = None,
+                average: Optional[Literal["micro", "macro", "weighted", "none"]] = "micro",
+                multidim_average: Optional[Literal["global", "samplewise"]] = "global", top_k: Optional[int] = 1,
+                ignore_index: Optional[int] = None, validate_args: bool = True, zero_division: float = 0) -> Tensor:
+    """Task wrapper (reference :636-707)."""
+    from metrics_b200.functional.classification._task import call_for_task
+
+    def mc(c: int) -> Tensor:
+        if not isinstance(top_k, int):
+            raise ValueError(f"`top_k` is expected to be `int` but `{type(top_k)} was passed.`")
+        return multiclass_fbeta_score(preds, target, beta, c, average, top_k, multidim_average, ignore_index, validate_args,
+                                      zero_division)
+
+    return call_for_task(
+        task, num_classes, num_labels,
+        lambda: binary_fbeta_score(preds, target, beta, threshold, multidim_average, ignore_index, validate_args, zero_division),
+        mc,
+        lambda n: multilabel_fbeta_score(preds, target, beta, n, threshold, average, multidim_average, ignore_index,
+                                         validate_args, zero_division))
+
+
+def f1_score(preds: Tensor, target: Tensor, task: Literal["binary", "multiclass", "multilabel"], threshold: float = 0.5,
+             num_classes: Optional[int] = None, num_labels: Optional[int] = None,
+             average: Optional[Literal["micro", "macro", "weighted", "none"]] = "micro",
+             multidim_average: Optional[Literal["global", "samplewise"]] = "global", top_k: Optional[int] = 1,
+             ignore_index: Optional[int] = None, validate_args: bool = True, zero_division: float = 0) -> Tensor:
+    """Task wrapper (reference :710-780): F-beta with beta = 1."""
+    return fbeta_score(preds, target, task, 1.0, threshold, num_classes, num_labels, average, multidim_average, top_k,
+                       ignore_index, validate_args, zero_division)

@@ -188,3 +188,17 @@ def multilabel_roc(
     preds, target, thresholds = _multilabel_precision_recall_curve_format(preds, target, num_labels, thresholds, ignore_index)
     state = _multilabel_precision_recall_curve_update(preds, target, num_labels, thresholds)
     return _multilabel_roc_compute(state, num_labels, thresholds, ignore_index)
+
+
+def roc(preds: Tensor, target: Tensor, task: Literal["binary", "multiclass", "multilabel"],
+        thresholds: Optional[Union[int, List[float], Tensor]] = None, num_classes: Optional[int] = None,
+        num_labels: Optional[int] = None, average: Optional[Literal["micro", "macro"]] = None,
+        ignore_index: Optional[int] = None, validate_args: bool = True):
+    """Task wrapper (reference :461-565)."""
+    from metrics_b200.functional.classification._task import call_for_task
+
+    return call_for_task(
+        task, num_classes, num_labels,
+        lambda: binary_roc(preds, target, thresholds, ignore_index, validate_args),
+        lambda c: multiclass_roc(preds, target, c, thresholds, average, ignore_index, validate_args),
+        lambda n: multilabel_roc(preds, target, n, thresholds, ignore_index, validate_args))

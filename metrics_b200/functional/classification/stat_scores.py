@@ -374,3 +374,12 @@ def stat_scores(
     if not isinstance(num_labels, int):
         raise ValueError(f"`num_labels` is expected to be `int` but `{type(num_labels)} was passed.`")
     return multilabel_stat_scores(preds, target, num_labels, threshold, average, multidim_average, ignore_index, validate_args)
+
+
+def _refine_preds_oh(preds: Tensor, preds_oh: Tensor, target: Tensor, top_k: int) -> Tensor:
+    """Host-side statement of the top-k refinement the kernel fuses (operator seam of reference :347-368): the one-hot
+    prediction becomes the target's one-hot when the target is among the ``top_k`` best scores, else the best score's."""
+    scores, labels = preds.squeeze(), target.squeeze()
+    best = torch.topk(scores, k=top_k, dim=1).indices
+    chosen = torch.where((best == labels.unsqueeze(1)).any(dim=1), labels, best[:, 0])
+    return torch.zeros_like(preds_oh, dtype=torch.int32).scatter_(-1, chosen.unsqueeze(1).unsqueeze(1), 1)

@@ -1,0 +1,294 @@
+"""TEST INFRASTRUCTURE ONLY — torch-CPU stand-ins for the wrappers of `metrics_b200._native`.
+
+`sitecustomize.py` installs them (env `MB200_REF_CPU_KERNELS=1`) so that the REFERENCE's own unit tests, which feed CPU
+tensors, can exercise everything ABOVE the C-ABI — argument validation, input formatting, state handling, reducers, metric
+classes, collections — against scikit-learn, exactly as they test the reference.  The kernels themselves are verified on the
+GPU by tests/test_*_gpu.py; nothing here is importable from the product (`metrics_b200` never imports `tests`).
+
+Every function mirrors the contract of the wrapper of the same name in metrics_b200/_native.py.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+FLAG_TARGET_RANGE, FLAG_PREDS_RANGE = 1, 2
+
+
+def launch_count() -> int:
+    return 0
+
+
+def _labels_from(preds: Tensor, target: Tensor):
+    """(pred labels, target labels) flattened; class dim of float scores reduced with torch.argmax."""
+    if preds.ndim == target.ndim + 1:
+        preds = preds.argmax(dim=1)
+    return preds.reshape(-1).long(), target.reshape(-1).long()
+
+
+def _admit(p: Tensor, t: Tensor, num_classes: int, ignore_index: Optional[int], err_flag: Optional[Tensor], int_preds: bool):
+    keep = torch.ones_like(t, dtype=torch.bool)
+    if ignore_index is not None:
+        keep &= t != ignore_index
+    bad_t = keep & ((t < 0) | (t >= num_classes))
+    bad_p = keep & ((p < 0) | (p >= num_classes)) if int_preds else torch.zeros_like(keep)
+    if err_flag is not None:
+        if bool(bad_t.any()):
+            err_flag |= FLAG_TARGET_RANGE
+        if bool(bad_p.any()):
+            err_flag |= FLAG_PREDS_RANGE
+    keep &= ~bad_t & ~bad_p
+    return p[keep], t[keep]
+
+
+def multiclass_confmat_update_(confmat, preds, target, num_classes, ignore_index, err_flag=None) -> None:
+    int_preds = not preds.is_floating_point()
+    p, t = _labels_from(preds, target)
+    p, t = _admit(p, t, num_classes, ignore_index, err_flag, int_preds)
+    confmat += torch.bincount(t * num_classes + p, minlength=num_classes**2).reshape(num_classes, num_classes)
+
+
+def _per_class_counts(p: Tensor, t: Tensor, num_classes: int):
+    cm = torch.bincount(t * num_classes + p, minlength=num_classes**2).reshape(num_classes, num_classes)
+    tp = cm.diag()
+    fp = cm.sum(0) - tp
+    fn = cm.sum(1) - tp
+    tn = cm.sum() - (tp + fp + fn)
+    return tp, fp, tn, fn
+
+
+def multiclass_stat_scores_update_(tp, fp, tn, fn, workspace, preds, target, num_classes, ignore_index, micro, err_flag=None) -> None:
+    int_preds = not preds.is_floating_point()
+    p, t = _labels_from(preds, target)
+    p, t = _admit(p, t, num_classes, ignore_index, err_flag, int_preds)
+    if micro:
+        match = (p == t).sum()
+        miss = (p != t).sum()
+        tp += match
+        fp += miss
+        fn += miss
+        tn += num_classes * p.numel() - (match + 2 * miss)
+        return
+    a, b, c, d = _per_class_counts(p, t, num_classes)
+    tp += a
+    fp += b
+    tn += c
+    fn += d
+
+
+def multiclass_stat_scores_topk_update_(tp, fp, tn, fn, workspace, preds, target, num_classes, top_k, ignore_index, err_flag=None) -> None:
+    if preds.ndim != 2 or target.ndim != 1:
+        raise NotImplementedError("metrics_b200: top_k > 1 supports `preds` of shape (N, C) with `target` of shape (N,)")
+    t = target.long()
+    keep = torch.ones_like(t, dtype=torch.bool)
+    if ignore_index is not None:
+        keep &= t != ignore_index
+    bad = keep & ((t < 0) | (t >= num_classes))
+    if err_flag is not None and bool(bad.any()):
+        err_flag |= FLAG_TARGET_RANGE
+    keep &= ~bad
+    scores, t = preds[keep].float(), t[keep]
+    # k best indices with the lowest index first among equal scores (the kernel's rule)
+    order = torch.argsort(-scores, dim=1, stable=True)[:, :top_k]
+    in_topk = (order == t[:, None]).any(1)
+    p = torch.where(in_topk, t, order[:, 0])
+    a, b, c, d = _per_class_counts(p, t, num_classes)
+    tp += a
+    fp += b
+    tn += c
+    fn += d
+
+
+def multiclass_stat_scores_samplewise(preds, target, num_classes, ignore_index, err_flag=None):
+    n = target.shape[0]
+    p_all = preds.argmax(dim=1) if preds.ndim == target.ndim + 1 else preds
+    int_preds = not preds.is_floating_point()
+    outs = []
+    for i in range(n):
+        p, t = p_all[i].reshape(-1).long(), target[i].reshape(-1).long()
+        p, t = _admit(p, t, num_classes, ignore_index, err_flag, int_preds)
+        outs.append(torch.stack(_per_class_counts(p, t, num_classes)))
+    stacked = torch.stack(outs) if outs else torch.zeros((0, 4, num_classes), dtype=torch.long)
+    return stacked[:, 0], stacked[:, 1], stacked[:, 2], stacked[:, 3]
+
+
+def argmax_rows(preds: Tensor) -> Tensor:
+    return preds.argmax(dim=1)
+
+
+def _is_logits(x: Tensor) -> bool:
+    return bool(((x < 0) | (x > 1)).any())
+
+
+def sigmoid_if_logits(preds: Tensor) -> Tensor:
+    return preds.sigmoid() if preds.numel() and _is_logits(preds) else preds.clone()
+
+
+def softmax_if_logits(preds: Tensor) -> Tensor:
+    return preds.softmax(1) if preds.numel() and _is_logits(preds) else preds.clone()
+
+
+def _one_curve(scores: Tensor, positive: Tensor, n_pad: int):
+    """Tie-collapsed descending curve of one binary problem: auroc, ap, counts row, padded (fps, tps, thr)."""
+    n = scores.numel()
+    order = torch.argsort(scores.float(), descending=True, stable=True)
+    s, y = scores[order].float(), positive[order].long()
+    is_end = torch.ones(n, dtype=torch.bool)
+    if n > 1:
+        is_end[:-1] = s[1:] != s[:-1]
+    idx = torch.nonzero(is_end).flatten()
+    tps = torch.cumsum(y, 0)[idx]
+    fps = idx + 1 - tps
+    P, N = int(y.sum()), int(n - y.sum())
+    tp_prev = torch.cat([tps.new_zeros(1), tps[:-1]])
+    fp_prev = torch.cat([fps.new_zeros(1), fps[:-1]])
+    auroc = float(((fps - fp_prev) * (tps + tp_prev)).sum()) / (2.0 * P * N) if P and N else 0.0
+    if P:
+        ap = float(((tps - tp_prev).double() / P * (tps.double() / (tps + fps).double())).sum())
+    else:
+        ap = -0.0
+    pad = torch.zeros(n_pad)
+    f, t, h = pad.clone(), pad.clone(), pad.clone()
+    f[: idx.numel()], t[: idx.numel()], h[: idx.numel()] = fps.float(), tps.float(), s[idx]
+    return auroc, ap, [P, N, int(idx.numel())], f, t, h
+
+
+def curve_evaluate(preds: Tensor, target: Tensor, num_classes: int = 1, pos_label: int = 1, want_curve: bool = False):
+    if preds.dtype == torch.float64:
+        raise NotImplementedError("metrics_b200: float64 scores are not supported by the exact curve kernels; cast to float32")
+    n = target.numel()
+    rows = []
+    for c in range(num_classes):
+        if num_classes == 1:
+            rows.append(_one_curve(preds.reshape(-1), target.reshape(-1) == pos_label, n))
+        else:
+            rows.append(_one_curve(preds[:, c], target == c, n))
+    auroc = torch.tensor([r[0] for r in rows], dtype=torch.float32)
+    ap = torch.tensor([r[1] for r in rows], dtype=torch.float32)
+    counts = torch.tensor([r[2] for r in rows], dtype=torch.int64)
+    curve = tuple(torch.stack([r[k] for r in rows]) for k in (3, 4, 5)) if want_curve else None
+    return auroc, ap, counts, curve
+
+
+def curve_evaluate_multilabel(preds: Tensor, target: Tensor, num_labels: int, ignore_index: Optional[int] = None,
+                              want_curve: bool = False):
+    if preds.dtype == torch.float64:
+        raise NotImplementedError("metrics_b200: float64 scores are not supported by the exact curve kernels; cast to float32")
+    n = preds.shape[0]
+    rows = []
+    for l in range(num_labels):
+        p, t = preds[:, l], target[:, l]
+        if ignore_index is not None:
+            keep = t != ignore_index
+            p, t = p[keep], t[keep]
+        rows.append(_one_curve(p, t == 1, n))
+    auroc = torch.tensor([r[0] for r in rows], dtype=torch.float32)
+    ap = torch.tensor([r[1] for r in rows], dtype=torch.float32)
+    counts = torch.tensor([r[2] for r in rows], dtype=torch.int64)
+    curve = tuple(torch.stack([r[k] for r in rows]) for k in (3, 4, 5)) if want_curve else None
+    return auroc, ap, counts, curve
+
+
+def binary_stat_counts(preds, target, num_labels, threshold, ignore_index, samplewise, counts=None, err_flag=None) -> Tensor:
+    n_outer = preds.shape[0] if preds.ndim > 0 else 1
+    if preds.is_floating_point():
+        x = preds
+        if preds.numel() and _is_logits(preds):
+            x = preds.sigmoid()
+        p = (x > threshold).long()
+    else:
+        p = preds.long()
+        if err_flag is not None and bool(((p < 0) | (p > 1)).any()):
+            err_flag |= FLAG_PREDS_RANGE
+    t = target.long()
+    p = p.reshape(n_outer, num_labels, -1)
+    t = t.reshape(n_outer, num_labels, -1)
+    valid = (t == 0) | (t == 1)
+    if ignore_index is not None:
+        ignored = t == ignore_index
+    else:
+        ignored = torch.zeros_like(valid)
+    if err_flag is not None and bool((~valid & ~ignored).any()):
+        err_flag |= FLAG_TARGET_RANGE
+    valid = valid & ~ignored  # ignore_index may itself be 0 or 1
+    eq = p == t
+    dims = (2,) if samplewise else (0, 2)
+    tp = (valid & eq & (t == 1)).sum(dims)
+    fp = (valid & ~eq & (t == 0)).sum(dims)
+    tn = (valid & eq & (t == 0)).sum(dims)
+    fn = (valid & ~eq & (t == 1)).sum(dims)
+    out = torch.stack([tp, fp, tn, fn], -1).reshape(-1, 4)
+    if counts is None:
+        return out
+    counts += out
+    return counts
+
+
+_REG_NUM_SUMS = {4: 2, 8: 3, 9: 4}
+
+
+def regression_sums(preds, target, op, num_outputs=1, param=0.0, eps=0.0) -> Tensor:
+    if not preds.is_floating_point():
+        preds = preds.float()
+    target = target.to(preds.dtype)
+    d = int(num_outputs)
+    p, t = preds.reshape(-1, d), target.reshape(-1, d)
+    diff = p - t
+    if op == 0:
+        terms = [diff * diff]
+    elif op == 1:
+        terms = [diff.abs()]
+    elif op == 2:
+        terms = [diff.abs() / t.abs().clamp(min=eps)]
+    elif op == 3:
+        terms = [diff.abs() / (t.abs() + p.abs()).clamp(min=eps)]
+    elif op == 4:
+        terms = [diff.abs(), t.abs()]
+    elif op == 5:
+        terms = [(torch.log1p(p) - torch.log1p(t)) ** 2]
+    elif op == 6:
+        terms = [torch.log((torch.exp(diff) + torch.exp(-diff)) / 2)]
+    elif op == 7:
+        terms = [diff.abs() ** param]
+    elif op == 8:
+        r = t - p
+        terms = [t * t, t, r * r]
+    else:
+        r = t - p
+        terms = [r, r * r, t, t * t]
+    return torch.stack([x.double().sum(0) for x in terms])
+
+
+def binned_curve_update(preds, target, thresholds, num_classes=1, multilabel=False) -> Tensor:
+    thr = thresholds.to(torch.float32)
+    t_count = thr.numel()
+    cmp_dtype = torch.float64 if preds.dtype == torch.float64 else torch.float32
+    if num_classes == 1 and not multilabel:
+        p, t = preds.reshape(-1).to(cmp_dtype), target.reshape(-1)
+        out = torch.zeros((t_count, 2, 2), dtype=torch.int64)
+        ge = p[:, None] >= thr.to(cmp_dtype)[None, :]
+        for y in (0, 1):
+            sel = t == y
+            out[:, y, 1] = ge[sel].sum(0)
+            out[:, y, 0] = sel.sum() - out[:, y, 1]
+        return out
+    out = torch.zeros((t_count, num_classes, 2, 2), dtype=torch.int64)
+    for c in range(num_classes):
+        p = preds[:, c].to(cmp_dtype)
+        ge = p[:, None] >= thr.to(cmp_dtype)[None, :]
+        for y in (0, 1):
+            sel = (target[:, c] == y) if multilabel else ((target == c) == bool(y))
+            out[:, c, y, 1] = ge[sel].sum(0)
+            out[:, c, y, 0] = sel.sum() - out[:, c, y, 1]
+    return out
+
+
+def install(native_module) -> None:
+    """Replace the kernel wrappers of `metrics_b200._native` by the stand-ins above."""
+    for name in ("launch_count", "multiclass_confmat_update_", "multiclass_stat_scores_update_",
+                 "multiclass_stat_scores_topk_update_", "multiclass_stat_scores_samplewise", "argmax_rows",
+                 "sigmoid_if_logits", "softmax_if_logits", "curve_evaluate", "curve_evaluate_multilabel",
+                 "binary_stat_counts", "regression_sums", "binned_curve_update"):
+        setattr(native_module, name, globals()[name])

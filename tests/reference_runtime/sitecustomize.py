@@ -82,3 +82,10 @@ _mod("torchmetrics.utilities.imports", _TORCH_GREATER_EQUAL_2_1=True)
 # names some reference test modules import at module level but that are outside the scope (wrappers)
 if not hasattr(metrics_b200, "ClasswiseWrapper"):
     metrics_b200.ClasswiseWrapper = _Absent
+
+# optional: torch-CPU stand-ins for the kernel wrappers, so that the reference's CPU-tensor unit tests reach our host layer
+if os.environ.get("MB200_REF_CPU_KERNELS") == "1":
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_kernels  # noqa: E402
+
+    cpu_kernels.install(sys.modules["metrics_b200._native"])

@@ -301,3 +301,37 @@ def test_collection_can_be_scripted():
         warnings.simplefilter("ignore")
         scripted = torch.jit.script(MetricCollection({"a": DummySum(), "b": DummyMean()}))
     assert scripted is not None
+
+
+def test_every_metric_class_can_be_scripted():
+    """The reference's MetricTester scripts every metric it tests (tests/unittests/_helpers/testers.py:144); bare class-level
+    annotations turned into strings by `from __future__ import annotations` break TorchScript's type resolution."""
+    import warnings
+
+    import metrics_b200.classification as TC
+    import metrics_b200.regression as TR
+    from metrics_b200.detection import MeanAveragePrecision
+
+    floors = ("AtFixed", "SensitivityAt", "SpecificityAt")
+    made = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name in dir(TC):
+            cls = getattr(TC, name)
+            prefix = next((p for p in ("Binary", "Multiclass", "Multilabel") if name.startswith(p)), None)
+            if not isinstance(cls, type) or prefix is None:
+                continue
+            args = () if prefix == "Binary" else (3,)
+            if "FBeta" in name:
+                args = (2.0,) + args
+            if any(f in name for f in floors):
+                args = args + (0.5,)
+            torch.jit.script(cls(*args))
+            made += 1
+        for name in dir(TR):
+            cls = getattr(TR, name)
+            if isinstance(cls, type) and issubclass(cls, torch.nn.Module) and cls.__module__.startswith("metrics_b200.regression"):
+                torch.jit.script(cls(p=2.0) if name == "MinkowskiDistance" else cls())
+                made += 1
+        torch.jit.script(MeanAveragePrecision())
+    assert made >= 75  # 67 classification classes + 11 regression metrics at the time of writing
