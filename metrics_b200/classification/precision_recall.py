@@ -1,0 +1,12 @@
+"""Import-path alias: the reference keeps these in `torchmetrics/classification/precision_recall.py`; here they are rows of the
+table-driven `ratio_metrics` module."""
+from metrics_b200.classification.ratio_metrics import (  # noqa: F401
+    BinaryPrecision,
+    BinaryRecall,
+    MulticlassPrecision,
+    MulticlassRecall,
+    MultilabelPrecision,
+    MultilabelRecall,
+    Precision,
+    Recall,
+)

@@ -1,0 +1,8 @@
+"""Import-path alias: the reference keeps these in `torchmetrics/classification/specificity.py`; here they are rows of the
+table-driven `ratio_metrics` module."""
+from metrics_b200.classification.ratio_metrics import (  # noqa: F401
+    BinarySpecificity,
+    MulticlassSpecificity,
+    MultilabelSpecificity,
+    Specificity,
+)

@@ -1,0 +1,8 @@
+"""Import-path alias: the reference keeps these in `torchmetrics/classification/specificity_sensitivity.py`; here they are rows of the
+table-driven `at_fixed` module."""
+from metrics_b200.classification.at_fixed import (  # noqa: F401
+    BinarySpecificityAtSensitivity,
+    MulticlassSpecificityAtSensitivity,
+    MultilabelSpecificityAtSensitivity,
+    SpecificityAtSensitivity,
+)

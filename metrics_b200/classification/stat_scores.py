@@ -94,7 +94,10 @@ class MulticlassStatScores(_AbstractStatScores):
             _multiclass_stat_scores_tensor_validation(
                 preds, target, self.num_classes, self.multidim_average, self.ignore_index
             )
-        num_classes = self.num_classes if self.num_classes is not None else 1
+        if self.num_classes is None:
+            self._update_unknown_class_count(preds, target)
+            return
+        num_classes = self.num_classes
         if self.multidim_average == "samplewise":
             from metrics_b200.functional.classification.stat_scores import _multiclass_stat_scores_states
 
@@ -105,6 +108,23 @@ class MulticlassStatScores(_AbstractStatScores):
             self.tp, self.fp, self.tn, self.fn, self._workspace(num_classes, self.tp.device), preds, target,
             num_classes, self.top_k, self.average, self.multidim_average, self.ignore_index, self.validate_args,
         )
+
+    def _update_unknown_class_count(self, preds: Tensor, target: Tensor) -> None:
+        """``num_classes=None`` (only legal with ``average="micro"``, reference :238-241): the micro counters do not need
+        the class count except for ``tn``, for which the reference substitutes 1 (:343, :434), i.e. ``tn = -fp``.  The
+        kernel's range check needs a bound, so it is read from the batch — one device sync, on this corner only."""
+        if self.multidim_average == "samplewise" or self.top_k != 1:
+            raise NotImplementedError("`num_classes=None` is supported for global top-1 micro statistics only")
+        if preds.is_floating_point():
+            bound = preds.shape[1]
+        else:
+            bound = int(torch.maximum(preds.max(), target.max()).item()) + 1 if preds.numel() else 2
+        bound = max(bound, 2)
+        _multiclass_stat_scores_update_(
+            self.tp, self.fp, self.tn, self.fn, self._workspace(bound, self.tp.device), preds, target, bound, 1,
+            "micro", "global", self.ignore_index, False,
+        )
+        self.tn = -self.fp
 
     def compute(self) -> Tensor:
         tp, fp, tn, fn = self._final_state()

@@ -18,6 +18,16 @@ def counts(
     """``[G, 4]`` int64 ``(tp, fp, tn, fn)``; with ``validate_args`` the kernel's range flags are read back (one 4-byte
     D2H) and turned into the reference's RuntimeErrors."""
     flag = new_flag(preds.device) if validate_args else None
+    if target.is_floating_point():
+        # The reference has no dtype rule for binary / multilabel targets (stat_scores.py:49-88), only the value rule
+        # {0, 1, ignore_index}; the kernel reads integer targets, so a float 0./1. tensor is cast once on the device.
+        as_int = target.long()
+        if validate_args and bool((as_int != target).any()):
+            raise RuntimeError(
+                f"Detected the following values in `target`: {torch.unique(target)} but expected only"
+                f" the following values {[0, 1] if ignore_index is None else [ignore_index]}."
+            )
+        target = as_int
     out = _native.binary_stat_counts(preds, target, num_labels, threshold, ignore_index, samplewise, into, flag)
     if flag is not None:
         bits = int(flag.item())
@@ -51,8 +61,6 @@ def check_common(multidim_average: str, ignore_index: Optional[int], zero_divisi
 
 def binary_shape_validation(preds: Tensor, target: Tensor, multidim_average: str) -> None:
     _check_same_shape(preds, target)
-    if target.is_floating_point():
-        raise ValueError(f"Expected argument `target` to be an int or long tensor, but got tensor with dtype {target.dtype}")
     if multidim_average != "global" and preds.ndim < 2:
         raise ValueError("Expected input to be at least 2D when multidim_average is set to `samplewise`")
 
@@ -64,7 +72,5 @@ def multilabel_shape_validation(preds: Tensor, target: Tensor, num_labels: int, 
             "Expected both `target.shape[1]` and `preds.shape[1]` to be equal to the number of labels"
             f" but got {preds.shape[1]} and expected {num_labels}"
         )
-    if target.is_floating_point():
-        raise ValueError(f"Expected argument `target` to be an int or long tensor, but got tensor with dtype {target.dtype}")
     if multidim_average != "global" and preds.ndim < 3:
         raise ValueError("Expected input to be at least 3D when multidim_average is set to `samplewise`")

@@ -88,12 +88,17 @@ class _Family(NamedTuple):
     reference: str
 
 
+def _convert_fpr_to_specificity(fpr: Tensor) -> Tensor:
+    """Specificity is the complement of the false-positive rate (reference sensitivity_specificity.py:42-44)."""
+    return 1 - fpr
+
+
 def _pick_sens_at_spec(fpr: Tensor, tpr: Tensor, thresholds: Tensor, floor: float):
-    return _best_with_floor(tpr, 1 - fpr, thresholds, floor)
+    return _best_with_floor(tpr, _convert_fpr_to_specificity(fpr), thresholds, floor)
 
 
 def _pick_spec_at_sens(fpr: Tensor, tpr: Tensor, thresholds: Tensor, floor: float):
-    return _best_with_floor(1 - fpr, tpr, thresholds, floor)
+    return _best_with_floor(_convert_fpr_to_specificity(fpr), tpr, thresholds, floor)
 
 
 _FAMILIES: Dict[str, _Family] = {

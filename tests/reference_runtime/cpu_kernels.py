@@ -291,4 +291,5 @@ def install(native_module) -> None:
                  "multiclass_stat_scores_topk_update_", "multiclass_stat_scores_samplewise", "argmax_rows",
                  "sigmoid_if_logits", "softmax_if_logits", "curve_evaluate", "curve_evaluate_multilabel",
                  "binary_stat_counts", "regression_sums", "binned_curve_update"):
-        setattr(native_module, name, globals()[name])
+        # a kernel launch is invisible to autograd; the stand-ins are plain torch ops, so detach them the same way
+        setattr(native_module, name, torch.no_grad()(globals()[name]))

@@ -77,7 +77,6 @@ _mod("torchmetrics.aggregation", SumMetric=SumMetric, MeanMetric=MeanMetric)
 _mod("torchmetrics.clustering", AdjustedRandScore=_Absent)
 _mod("torchmetrics.image", StructuralSimilarityIndexMeasure=_Absent)
 sys.modules["torchmetrics.regression"].PearsonCorrCoef = _Absent
-_mod("torchmetrics.utilities.imports", _TORCH_GREATER_EQUAL_2_1=True)
 
 # names some reference test modules import at module level but that are outside the scope (wrappers)
 if not hasattr(metrics_b200, "ClasswiseWrapper"):
