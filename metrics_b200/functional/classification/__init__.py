@@ -95,3 +95,14 @@ from metrics_b200.functional.classification.at_fixed import (  # noqa: F401,E402
     sensitivity_at_specificity,
     specificity_at_sensitivity,
 )
+
+# The reference's import paths `<package>.{cohen_kappa, matthews_corrcoef, negative_predictive_value, specificity}` are alias submodules that share a name with a function exported
+# above.  Loading a submodule binds it as a package attribute, so load them now and re-bind the functions afterwards: a
+# later `import` of an already-loaded submodule does not touch the attribute again.
+import importlib as _importlib  # noqa: E402
+
+for _name in ("cohen_kappa", "matthews_corrcoef", "negative_predictive_value", "specificity"):
+    _fn = globals()[_name]
+    _importlib.import_module(f"{__name__}.{_name}")
+    globals()[_name] = _fn
+del _importlib, _name, _fn

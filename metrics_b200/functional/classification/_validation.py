@@ -63,8 +63,12 @@ def check_multiclass_shapes(preds: Tensor, target: Tensor, num_classes: Optional
             "Either `preds` and `target` both should have the (same) shape (N, ...), or `target` should be (N, ...)"
             " and `preds` should be (N, C, ...)."
         )
+
+
+def labels_as_int(preds: Tensor, target: Tensor) -> Tensor:
+    """Label-format predictions (same shape as ``target``) in a floating dtype: the reference has no dtype rule for them
+    and truncates with ``.long()`` when it builds the bincount index (functional/classification/stat_scores.py:442,
+    confusion_matrix.py:323); the kernels read integer labels, so do that cast once here."""
     if preds.ndim == target.ndim and preds.is_floating_point():
-        raise ValueError(
-            "metrics_b200: label-format `preds` (same shape as `target`) must be an integer tensor; "
-            f"got dtype {preds.dtype}."
-        )
+        return preds.long()
+    return preds

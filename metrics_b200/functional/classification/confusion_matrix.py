@@ -13,7 +13,7 @@ from torch import Tensor
 from typing_extensions import Literal
 
 from metrics_b200 import _native
-from metrics_b200.functional.classification._validation import check_multiclass_shapes, new_flag, raise_if_flagged
+from metrics_b200.functional.classification._validation import check_multiclass_shapes, labels_as_int, new_flag, raise_if_flagged
 from metrics_b200.utilities.prints import rank_zero_warn
 
 _NORMALIZE = ("true", "pred", "all", "none", None)
@@ -71,7 +71,7 @@ def _multiclass_confusion_matrix_update_(
 ) -> None:
     """FUSED format+update: ``confmat[target, argmax(preds)] += 1`` in place, one pass over ``preds``."""
     flag = new_flag(confmat.device) if validate_args else None
-    _native.multiclass_confmat_update_(confmat, preds, target, num_classes, ignore_index, flag)
+    _native.multiclass_confmat_update_(confmat, labels_as_int(preds, target), target, num_classes, ignore_index, flag)
     if flag is not None:
         raise_if_flagged(flag, num_classes, ignore_index)
 
@@ -93,7 +93,7 @@ def _multiclass_confusion_matrix_format(
 def _multiclass_confusion_matrix_update(preds: Tensor, target: Tensor, num_classes: int) -> Tensor:
     """Piecewise seam (reference :324-328): label preds + label target -> fresh ``[C, C]`` int64 counts."""
     confmat = torch.zeros(num_classes, num_classes, dtype=torch.int64, device=preds.device)
-    _native.multiclass_confmat_update_(confmat, preds, target, num_classes, None, None)
+    _native.multiclass_confmat_update_(confmat, labels_as_int(preds, target), target, num_classes, None, None)
     return confmat
 
 

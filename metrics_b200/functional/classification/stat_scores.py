@@ -13,7 +13,7 @@ from torch import Tensor
 from typing_extensions import Literal
 
 from metrics_b200 import _native
-from metrics_b200.functional.classification._validation import check_multiclass_shapes, new_flag, raise_if_flagged
+from metrics_b200.functional.classification._validation import check_multiclass_shapes, labels_as_int, new_flag, raise_if_flagged
 
 _AVERAGES = ("micro", "macro", "weighted", "none", None)
 _MULTIDIM = ("global", "samplewise")
@@ -107,7 +107,7 @@ def _multiclass_stat_scores_update_(
         _native.multiclass_stat_scores_topk_update_(tp, fp, tn, fn, workspace, preds, target, num_classes, top_k, ignore_index, flag)
     else:
         _native.multiclass_stat_scores_update_(
-            tp, fp, tn, fn, workspace, preds, target, num_classes, ignore_index, average == "micro", flag
+            tp, fp, tn, fn, workspace, labels_as_int(preds, target), target, num_classes, ignore_index, average == "micro", flag
         )
     if flag is not None:
         raise_if_flagged(flag, num_classes, ignore_index)
@@ -130,7 +130,7 @@ def _multiclass_stat_scores_update(
     """Functional seam (reference :371-449): fresh tp, fp, tn, fn for one batch (``[N, C]`` when samplewise)."""
     _require_kernel_mode(top_k, multidim_average)
     if multidim_average == "samplewise":
-        return _native.multiclass_stat_scores_samplewise(preds, target, num_classes, ignore_index)
+        return _native.multiclass_stat_scores_samplewise(labels_as_int(preds, target), target, num_classes, ignore_index)
     if top_k > 1:
         average = "macro"  # per-class counters: the reference keeps [C]-sized states for top-k, also for micro
     size = () if average == "micro" else (num_classes,)
@@ -176,7 +176,7 @@ def _multiclass_stat_scores_states(
     _require_kernel_mode(top_k, multidim_average)
     if multidim_average == "samplewise":
         flag = new_flag(preds.device) if validate_args else None
-        out = _native.multiclass_stat_scores_samplewise(preds, target, num_classes, ignore_index, flag)
+        out = _native.multiclass_stat_scores_samplewise(labels_as_int(preds, target), target, num_classes, ignore_index, flag)
         if flag is not None:
             raise_if_flagged(flag, num_classes, ignore_index)
         return out

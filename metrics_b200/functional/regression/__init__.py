@@ -12,3 +12,14 @@ from metrics_b200.functional.regression.metrics import (  # noqa: F401
     symmetric_mean_absolute_percentage_error,
     weighted_mean_absolute_percentage_error,
 )
+
+# The reference's import paths `<package>.{explained_variance}` are alias submodules that share a name with a function exported
+# above.  Loading a submodule binds it as a package attribute, so load them now and re-bind the functions afterwards: a
+# later `import` of an already-loaded submodule does not touch the attribute again.
+import importlib as _importlib  # noqa: E402
+
+for _name in ("explained_variance",):
+    _fn = globals()[_name]
+    _importlib.import_module(f"{__name__}.{_name}")
+    globals()[_name] = _fn
+del _importlib, _name, _fn

@@ -14,7 +14,7 @@ from metrics_b200.utilities.exceptions import TorchMetricsUserError
 
 
 class _SumOverN(Metric):
-    is_differentiable: bool = True
+    is_differentiable: bool = False  # kernel launches carry no autograd graph (reference: True)
     full_state_update: bool = False
     plot_lower_bound: float = 0.0
 
@@ -168,7 +168,7 @@ class LogCoshError(_SumOverN):
 class MinkowskiDistance(Metric):
     """Reference regression/minkowski.py:27-100."""
 
-    is_differentiable: Optional[bool] = True
+    is_differentiable: Optional[bool] = False  # kernel launches carry no autograd graph (reference: True)
     higher_is_better: Optional[bool] = False
     full_state_update: Optional[bool] = False
     plot_lower_bound: float = 0.0
@@ -190,7 +190,7 @@ class MinkowskiDistance(Metric):
 class R2Score(Metric):
     """Reference regression/r2.py:27-160."""
 
-    is_differentiable: bool = True
+    is_differentiable: bool = False  # kernel launches carry no autograd graph (reference: True)
     higher_is_better: bool = True
     full_state_update: bool = False
     plot_lower_bound: float = 0.0
@@ -224,7 +224,7 @@ class R2Score(Metric):
 class RelativeSquaredError(Metric):
     """Reference regression/rse.py:27-110."""
 
-    is_differentiable: bool = True
+    is_differentiable: bool = False  # kernel launches carry no autograd graph (reference: True)
     higher_is_better: bool = False
     full_state_update: bool = False
 
@@ -251,7 +251,7 @@ class RelativeSquaredError(Metric):
 class ExplainedVariance(Metric):
     """Reference regression/explained_variance.py:30-130."""
 
-    is_differentiable: bool = True
+    is_differentiable: bool = False  # kernel launches carry no autograd graph (reference: True)
     higher_is_better: bool = True
     full_state_update: bool = False
     plot_lower_bound: float = 0.0

@@ -74,13 +74,21 @@ def _mod(name, **attrs):
 
 
 _mod("torchmetrics.aggregation", SumMetric=SumMetric, MeanMetric=MeanMetric)
-_mod("torchmetrics.clustering", AdjustedRandScore=_Absent)
+_mod("torchmetrics.clustering", AdjustedRandScore=_Absent, CalinskiHarabaszScore=_Absent)
 _mod("torchmetrics.image", StructuralSimilarityIndexMeasure=_Absent)
 sys.modules["torchmetrics.regression"].PearsonCorrCoef = _Absent
 
-# names some reference test modules import at module level but that are outside the scope (wrappers)
-if not hasattr(metrics_b200, "ClasswiseWrapper"):
-    metrics_b200.ClasswiseWrapper = _Absent
+
+def _absent_fn(*a, **k):
+    raise NotImplementedError("not part of metrics_b200's scope")
+
+
+# tests/unittests/regression/test_mean_error.py imports these at module level (NRMSE is outside the scope; `permetrics` is a
+# test-only dependency missing from this image and only used as NRMSE's oracle)
+_mod("torchmetrics.regression.nrmse", NormalizedRootMeanSquaredError=_Absent)
+sys.modules["torchmetrics.functional"].normalized_root_mean_squared_error = _absent_fn
+_mod("permetrics")
+_mod("permetrics.regression", RegressionMetric=_absent_fn)
 
 # optional: torch-CPU stand-ins for the kernel wrappers, so that the reference's CPU-tensor unit tests reach our host layer
 if os.environ.get("MB200_REF_CPU_KERNELS") == "1":

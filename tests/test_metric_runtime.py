@@ -335,3 +335,42 @@ def test_every_metric_class_can_be_scripted():
                 made += 1
         torch.jit.script(MeanAveragePrecision())
     assert made >= 75  # 67 classification classes + 11 regression metrics at the time of writing
+
+
+def test_classwise_wrapper_names_results_and_is_transparent_to_compute_groups():
+    """Reference wrappers/classwise.py:32-237 and tests/unittests/bases/test_collections.py:574-604."""
+    from metrics_b200 import ClasswiseWrapper
+
+    class PerClass(DummyIntStates):
+        def compute(self):
+            return self.tp
+
+    class PerClassTwice(DummyIntStates):
+        def compute(self):
+            return 2 * self.tp
+
+    w = ClasswiseWrapper(PerClass(n=3))
+    assert list(w(torch.tensor([1, 2, 3]))) == ["perclass_0", "perclass_1", "perclass_2"]
+    w.update(torch.tensor([1, 1, 1]))
+    assert [int(v) for v in w.compute().values()] == [2, 3, 4]
+    assert w.tp is w.metric.tp  # states are the wrapped metric's
+    w.reset()
+    assert int(w.metric.tp.sum()) == 0
+    named = ClasswiseWrapper(PerClass(n=2), labels=["tree", "bush"], prefix="f_", postfix="_x")
+    assert list(named(torch.tensor([1, 2]))) == ["f_tree_x", "f_bush_x"]
+    for bad in ({"metric": 3}, {"metric": PerClass(), "labels": "ab"}, {"metric": PerClass(), "prefix": 1},
+                {"metric": PerClass(), "postfix": 1}):
+        with pytest.raises(ValueError, match="Expected argument"):
+            ClasswiseWrapper(**bad)
+
+    members = {"a": ClasswiseWrapper(PerClass(n=3), prefix="a"), "b": ClasswiseWrapper(PerClassTwice(n=3), prefix="b")}
+    mc = MetricCollection(members, compute_groups=[["a", "b"]], prefix="val/")
+    assert mc.compute_groups == {0: ["a", "b"]}
+    mc.update(torch.tensor([1, 2, 3]))
+    mc.update(torch.tensor([1, 2, 3]))
+    res = mc.compute()
+    assert {k: int(v) for k, v in res.items()} == {"val/a0": 2, "val/a1": 4, "val/a2": 6, "val/b0": 4, "val/b1": 8, "val/b2": 12}
+    auto = MetricCollection({"a": ClasswiseWrapper(PerClass(n=3), prefix="a"), "b": ClasswiseWrapper(PerClassTwice(n=3), prefix="b")})
+    auto.update(torch.tensor([1, 2, 3]))
+    assert auto.compute_groups == {0: ["a", "b"]}
+    assert int(auto(torch.tensor([1, 1, 1]))["b2"]) == 2
