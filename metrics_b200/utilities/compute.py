@@ -58,3 +58,46 @@ def interp(x: Tensor, xp: Tensor, fp: Tensor) -> Tensor:
     idx = torch.sum(torch.ge(x[:, None], xp[None, :]), 1) - 1
     idx = torch.clamp(idx, 0, len(m) - 1)
     return m[idx] * x + b[idx]
+
+
+def _auc_format_inputs(x: Tensor, y: Tensor) -> tuple[Tensor, Tensor]:
+    """Squeeze to 1-d and check the two lengths (reference compute.py:85-98)."""
+    x = x.squeeze() if x.ndim > 1 else x
+    y = y.squeeze() if y.ndim > 1 else y
+    if x.ndim > 1 or y.ndim > 1:
+        raise ValueError(f"Expected both `x` and `y` tensor to be 1d, but got tensors with dimension {x.ndim} and {y.ndim}")
+    if x.numel() != y.numel():
+        raise ValueError(f"Expected the same number of elements in `x` and `y` tensor but received {x.numel()} and {y.numel()}")
+    return x, y
+
+
+def _auc_compute(x: Tensor, y: Tensor, reorder: bool = False) -> Tensor:
+    """Trapezoidal area under ``y(x)`` for monotone ``x`` (either direction); ``reorder`` sorts first (reference :112-138)."""
+    with torch.no_grad():
+        if reorder:
+            x, order = torch.sort(x, stable=True)
+            y = y[order]
+        dx = x[1:] - x[:-1]
+        direction = 1.0
+        if bool((dx < 0).any()):
+            if not bool((dx <= 0).all()):
+                raise ValueError(
+                    "The `x` tensor is neither increasing or decreasing. Try setting the reorder argument to `True`."
+                )
+            direction = -1.0
+        return _auc_compute_without_check(x, y, direction)
+
+
+def auc(x: Tensor, y: Tensor, reorder: bool = False) -> Tensor:
+    """Area under the curve by the trapezoidal rule (reference :141-154)."""
+    return _auc_compute(*_auc_format_inputs(x, y), reorder=reorder)
+
+
+def normalize_logits_if_needed(tensor: Tensor, normalization: str) -> Tensor:
+    """Sigmoid / softmax (over dim 1) when any value lies outside [0, 1] — kernel K6 with its device-side vote, no host
+    sync (reference :190-230).  CUDA tensors only, like every kernel of this package."""
+    from metrics_b200 import _native
+
+    if normalization not in ("sigmoid", "softmax"):
+        raise ValueError(f"Expected `normalization` to be 'sigmoid' or 'softmax' but got {normalization}")
+    return _native.sigmoid_if_logits(tensor) if normalization == "sigmoid" else _native.softmax_if_logits(tensor)

@@ -60,3 +60,28 @@ def gather_all_tensors(result: Tensor, group: Optional[Any] = None) -> List[Tens
     out = [b[:n].reshape(s) for b, n, s in zip(buf, numels, shapes_host)]
     out[rank] = result
     return out
+
+
+def reduce(x: Tensor, reduction: Optional[str]) -> Tensor:
+    """``"elementwise_mean"`` | ``"sum"`` | ``"none"`` / ``None`` (reference :22-42)."""
+    if reduction == "elementwise_mean":
+        return torch.mean(x)
+    if reduction == "sum":
+        return torch.sum(x)
+    if reduction is None or reduction == "none":
+        return x
+    raise ValueError("Reduction parameter unknown.")
+
+
+def class_reduce(num: Tensor, denom: Tensor, weights: Tensor, class_reduction: Optional[str] = "none") -> Tensor:
+    """``num / denom`` per class with 0 where the quotient is NaN, then micro / macro / weighted / none (reference :45-88)."""
+    valid_reduction = ("micro", "macro", "weighted", "none", None)
+    if class_reduction not in valid_reduction:
+        raise ValueError(f"Reduction parameter {class_reduction} unknown. Choose between one of these: {valid_reduction}")
+    fraction = num.sum() / denom.sum() if class_reduction == "micro" else num / denom
+    fraction = torch.where(torch.isnan(fraction), torch.zeros_like(fraction), fraction)
+    if class_reduction == "macro":
+        return fraction.mean()
+    if class_reduction == "weighted":
+        return (fraction * (weights.float() / weights.sum())).sum()
+    return fraction
