@@ -8,6 +8,7 @@ area, maxDet) accumulation.  Only ``iou_type="bbox"`` is in scope.
 """
 from __future__ import annotations
 
+import json
 from typing import Any, Dict, List, Optional, Tuple, Union
 
 import torch
@@ -226,6 +227,111 @@ class MeanAveragePrecision(Metric):
                      "groundtruth_crowds", "groundtruth_area"):
             setattr(self, name, [per_rank[r][name][i] for i in range(max_img) for r in range(world) if i < sizes[r][0]])
         return True
+
+    # ------------------------------------------------------------------------------------------------
+    # COCO json on either side of the metric (reference :651-825, :867-958)
+    # ------------------------------------------------------------------------------------------------
+    @staticmethod
+    def coco_to_tm(
+        coco_preds: str,
+        coco_target: str,
+        iou_type: Union[Literal["bbox", "segm"], List[str]] = "bbox",
+        backend: Literal["pycocotools", "faster_coco_eval"] = "pycocotools",
+    ) -> Tuple[List[Dict[str, Tensor]], List[Dict[str, Tensor]]]:
+        """COCO ground-truth json (``{"annotations": [...], ...}``) + COCO results json (a list of detections) -> the
+        ``(preds, target)`` lists ``update`` takes (reference :651-760).  The files are read directly — the reference goes
+        through ``pycocotools.COCO(...).loadRes`` only to get the same annotation lists back.  One entry per image that
+        has at least one ground-truth annotation, in order of first appearance; boxes stay in the files' xywh format."""
+        kinds = (iou_type,) if isinstance(iou_type, str) else tuple(iou_type)
+        if any(k not in ("bbox", "segm") for k in kinds):
+            raise ValueError(f"Expected argument `iou_type` to be one of ('bbox', 'segm') or a tuple of, but got {iou_type}")
+        if kinds != ("bbox",):
+            raise NotImplementedError("metrics_b200: only `iou_type='bbox'` is implemented (mask IoU is out of scope)")
+        with open(coco_target) as fh:
+            gt_file = json.load(fh)
+        with open(coco_preds) as fh:
+            dt_file = json.load(fh)
+        if not isinstance(gt_file, dict):
+            raise ValueError(f"annotation file format {type(gt_file)} not supported")
+        if not isinstance(dt_file, list):
+            raise ValueError("results in not an array of objects")
+        known_images = {img["id"] for img in gt_file.get("images", [])} or {a["image_id"] for a in gt_file["annotations"]}
+        if any(d["image_id"] not in known_images for d in dt_file):
+            raise ValueError("Results do not correspond to current coco set")
+
+        per_image: Dict[Any, Dict[str, list]] = {}
+        for ann in gt_file["annotations"]:
+            slot = per_image.setdefault(ann["image_id"], {"g_boxes": [], "g_labels": [], "g_crowd": [], "g_area": [],
+                                                          "d_boxes": [], "d_labels": [], "d_scores": []})
+            slot["g_boxes"].append(ann["bbox"])
+            slot["g_labels"].append(ann["category_id"])
+            slot["g_crowd"].append(ann["iscrowd"])
+            slot["g_area"].append(ann["area"])
+        for det in dt_file:
+            slot = per_image.get(det["image_id"])
+            if slot is not None:  # detections on images without ground truth are not evaluated (reference :736)
+                slot["d_boxes"].append(det["bbox"])
+                slot["d_labels"].append(det["category_id"])
+                slot["d_scores"].append(det["score"])
+        preds = [{"scores": torch.tensor(s["d_scores"], dtype=torch.float32),
+                  "labels": torch.tensor(s["d_labels"], dtype=torch.int32),
+                  "boxes": torch.tensor(s["d_boxes"], dtype=torch.float32)} for s in per_image.values()]
+        target = [{"labels": torch.tensor(s["g_labels"], dtype=torch.int32),
+                   "iscrowd": torch.tensor(s["g_crowd"], dtype=torch.int32),
+                   "area": torch.tensor(s["g_area"], dtype=torch.float32),
+                   "boxes": torch.tensor(s["g_boxes"], dtype=torch.float32)} for s in per_image.values()]
+        return preds, target
+
+    def _coco_dataset(self, labels: List[Tensor], boxes: List[Tensor], scores: Optional[List[Tensor]] = None,
+                      crowds: Optional[List[Tensor]] = None, area: Optional[List[Tensor]] = None) -> Dict[str, list]:
+        """The cached per-image states as one COCO dataset dict (reference :867-958, bbox): annotation ids start at 1,
+        image ids are the positions in the state lists, ``area`` falls back to ``w * h`` when missing or not positive.
+        Every state kind is brought to the host with ONE copy (the reference does one per image and per annotation)."""
+        counts = [int(lab.numel()) for lab in labels]
+
+        def host(items: Optional[List[Tensor]], width: int = 1) -> Optional[list]:
+            if items is None:
+                return None
+            kept = [t.reshape(-1, width) if width > 1 else t.reshape(-1) for t in items if t.numel() > 0]
+            return torch.cat(kept).cpu().tolist() if kept else []
+
+        for image_id, (lab, box) in enumerate(zip(labels, boxes)):
+            if box.numel() != 4 * lab.numel():
+                raise ValueError(f"Invalid input box of sample {image_id}, element 0 (expected 4 values, got"
+                                 f" {box.numel() // max(1, lab.numel())})")
+        flat_labels, flat_boxes = host(labels), host(boxes, 4)
+        flat_scores, flat_crowds, flat_area = host(scores), host(crowds), host(area)
+        annotations = []
+        k = 0
+        for image_id, count in enumerate(counts):
+            for j in range(count):
+                label, box = flat_labels[k], flat_boxes[k]
+                if not isinstance(label, int):
+                    raise ValueError(f"Invalid input class of sample {image_id}, element {j}"
+                                     f" (expected value of type integer, got type {type(label)})")
+                given = flat_area[k] if flat_area is not None else 0
+                ann = {"id": k + 1, "image_id": image_id, "area": given if given > 0 else box[2] * box[3],
+                       "category_id": label, "iscrowd": flat_crowds[k] if flat_crowds is not None else 0, "bbox": box}
+                if flat_scores is not None:
+                    if not isinstance(flat_scores[k], float):
+                        raise ValueError(f"Invalid input score of sample {image_id}, element {j}"
+                                         f" (expected value of type float, got type {type(flat_scores[k])})")
+                    ann["score"] = flat_scores[k]
+                annotations.append(ann)
+                k += 1
+        return {"images": [{"id": i} for i in range(len(counts))], "annotations": annotations,
+                "categories": [{"id": c, "name": str(c)} for c in self._get_classes()]}
+
+    def tm_to_coco(self, name: str = "tm_map_input") -> None:
+        """Write everything ``update`` has cached as ``{name}_preds.json`` (the COCO results list) and
+        ``{name}_target.json`` (the COCO ground-truth dataset), reference :762-825."""
+        target = self._coco_dataset(self.groundtruth_labels, self.groundtruth_box, crowds=self.groundtruth_crowds,
+                                    area=self.groundtruth_area)
+        preds = self._coco_dataset(self.detection_labels, self.detection_box, scores=self.detection_scores)
+        with open(f"{name}_preds.json", "w") as fh:
+            fh.write(json.dumps(preds["annotations"], indent=4))
+        with open(f"{name}_target.json", "w") as fh:
+            fh.write(json.dumps(target, indent=4))
 
     def _get_classes(self) -> List[int]:
         if len(self.detection_labels) > 0 or len(self.groundtruth_labels) > 0:

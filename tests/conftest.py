@@ -93,3 +93,10 @@ def golden_logauc():
     import numpy as np
 
     return np.load(os.path.join(GOLDEN_DIR, "logauc.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_coco_format():
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN_DIR, "coco_format.npz"), allow_pickle=False)

@@ -1069,6 +1069,48 @@ def regression_golden() -> dict:
     return out
 
 
+def coco_format_golden() -> dict:
+    """The reference's COCO-json formatter (detection/mean_ap.py:867-958, bbox) applied to per-image states.  The
+    reference class cannot be instantiated here (no pycocotools), but `_get_coco_format` only needs `iou_type` and
+    `_get_classes` from `self`, so it is called unbound on a stand-in object.  Inputs are stored already converted to
+    xywh (what `update` caches); outputs are the two dataset dicts as json strings."""
+    import json
+    import types
+
+    from torchmetrics.detection.mean_ap import MeanAveragePrecision as Ref
+
+    g = torch.Generator().manual_seed(20240921)
+    images = []
+    for i in range(8):
+        nd, ng = int(torch.randint(0, 6, (1,), generator=g)), int(torch.randint(0, 5, (1,), generator=g))
+        img = {
+            "d_box": torch.cat([torch.rand(nd, 2, generator=g) * 100, torch.rand(nd, 2, generator=g) * 50 + 1], 1),
+            "d_score": torch.rand(nd, generator=g),
+            "d_label": torch.randint(0, 5, (nd,), generator=g),
+            "g_box": torch.cat([torch.rand(ng, 2, generator=g) * 100, torch.rand(ng, 2, generator=g) * 50 + 1], 1),
+            "g_label": torch.randint(0, 5, (ng,), generator=g),
+        }
+        if i % 2:
+            img["g_crowd"] = torch.randint(0, 2, (ng,), generator=g)
+            img["g_area"] = torch.rand(ng, generator=g) * 100 * (torch.rand(ng, generator=g) > 0.3)
+        else:  # what `update` stores when the user gives neither: zeros_like(labels)
+            img["g_crowd"] = torch.zeros_like(img["g_label"])
+            img["g_area"] = torch.zeros_like(img["g_label"])
+        images.append(img)
+    labels = torch.cat([im["d_label"] for im in images] + [im["g_label"] for im in images]).unique().tolist()
+    fake = types.SimpleNamespace(iou_type=("bbox",), _get_classes=lambda: labels)
+    target = Ref._get_coco_format(fake, labels=[im["g_label"] for im in images], boxes=[im["g_box"] for im in images],
+                                  masks=None, crowds=[im["g_crowd"] for im in images], area=[im["g_area"] for im in images])
+    preds = Ref._get_coco_format(fake, labels=[im["d_label"] for im in images], boxes=[im["d_box"] for im in images],
+                                 masks=None, scores=[im["d_score"] for im in images])
+    out = {"n_images": np.array(len(images)), "target_json": np.array(json.dumps(target)),
+           "preds_json": np.array(json.dumps(preds["annotations"]))}
+    for i, im in enumerate(images):
+        for k, v in im.items():
+            out[f"img{i}/{k}"] = np_of(v)
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["classification"]
     if "classification" in which:
@@ -1119,5 +1161,10 @@ if __name__ == "__main__":
     if "curves" in which:
         data = curves_golden()
         path = os.path.join(HERE, "curves.npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
+    if "coco_format" in which:
+        data = coco_format_golden()
+        path = os.path.join(HERE, "coco_format.npz")
         np.savez_compressed(path, **data)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
