@@ -82,6 +82,12 @@ from metrics_b200.functional.classification.at_fixed import (  # noqa: F401,E402
 )
 from metrics_b200.functional.classification.exact_match import exact_match, multiclass_exact_match, multilabel_exact_match  # noqa: F401,E402
 from metrics_b200.functional.classification.logauc import binary_logauc, logauc, multiclass_logauc, multilabel_logauc  # noqa: F401,E402
+from metrics_b200.functional.classification.group_fairness import (  # noqa: F401,E402
+    binary_fairness,
+    binary_groups_stat_rates,
+    demographic_parity,
+    equal_opportunity,
+)
 from metrics_b200.functional.classification.accuracy import accuracy  # noqa: F401,E402
 from metrics_b200.functional.classification.auroc import auroc  # noqa: F401,E402
 from metrics_b200.functional.classification.average_precision import average_precision  # noqa: F401,E402

@@ -100,3 +100,30 @@ def golden_coco_format():
     import numpy as np
 
     return np.load(os.path.join(GOLDEN_DIR, "coco_format.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_fairness():
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN_DIR, "fairness.npz"), allow_pickle=False)
+
+
+@pytest.fixture
+def cpu_kernel_standins(monkeypatch):
+    """HOST-LAYER tests only.  For the duration of one test the kernel wrappers of `metrics_b200._native` are replaced by
+    the torch-CPU stand-ins of tests/reference_runtime/cpu_kernels.py (same contracts), so that the Python above the C-ABI
+    — validation, format seams, state handling, reducers — can be checked against the reference's goldens without a GPU.
+    Like `oracle/`, the stand-ins are test infrastructure: nothing under `metrics_b200/` can reach them, and the product
+    raises `NativeLibraryError` on CPU tensors (tests/test_native_abi.py)."""
+    import importlib.util
+
+    from metrics_b200 import _native
+
+    spec = importlib.util.spec_from_file_location(
+        "mb200_cpu_kernels", os.path.join(os.path.dirname(__file__), "reference_runtime", "cpu_kernels.py"))
+    module = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(module)
+    for name, fn in module.standins().items():
+        monkeypatch.setattr(_native, name, fn)
+    return module

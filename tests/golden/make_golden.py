@@ -1111,6 +1111,63 @@ def coco_format_golden() -> dict:
     return out
 
 
+def fairness_golden() -> dict:
+    """Group fairness (reference functional/classification/group_fairness.py): per-group counters from
+    `_binary_groups_stat_scores`, the rates of `binary_groups_stat_rates`, and the DP / EO dictionaries of
+    `binary_fairness` — keys included, they carry the arg-min / arg-max group."""
+    import warnings
+
+    from torchmetrics.classification.group_fairness import BinaryFairness
+    from torchmetrics.functional.classification.group_fairness import (
+        _binary_groups_stat_scores,
+        binary_fairness,
+        binary_groups_stat_rates,
+    )
+
+    g = torch.Generator().manual_seed(777)
+    out = {}
+    case = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for kind in ("probs", "logits", "labels"):
+            for ign in (None, 0, -1):
+                for num_groups, shape in ((2, (256,)), (5, (193,)), (3, (64, 7))):
+                    n = shape[0]
+                    if kind == "probs":
+                        preds = torch.rand(shape, generator=g)
+                    elif kind == "logits":
+                        preds = torch.randn(shape, generator=g) * 3
+                    else:
+                        preds = torch.randint(0, 2, shape, generator=g)
+                    target = torch.randint(0, 2, shape, generator=g)
+                    if ign is not None:
+                        target[torch.rand(shape, generator=g) < 0.1] = ign
+                    groups = torch.randint(0, num_groups, (n,), generator=g)
+                    groups[:num_groups] = torch.arange(num_groups)  # every group occurs in both halves of the batch
+                    groups[n // 2: n // 2 + num_groups] = torch.arange(num_groups)
+                    stats = _binary_groups_stat_scores(preds, target, groups, num_groups, 0.5, ign, True)
+                    rates = binary_groups_stat_rates(preds, target, groups, num_groups, 0.5, ign)
+                    fair = binary_fairness(preds, target, groups, "all", 0.5, ign)
+                    metric = BinaryFairness(num_groups, ignore_index=ign)
+                    metric.update(preds[: n // 2], target[: n // 2], groups[: n // 2])
+                    metric.update(preds[n // 2:], target[n // 2:], groups[n // 2:])
+                    fair_two_updates = metric.compute()
+                    key = f"case{case}"
+                    out[f"{key}/preds"] = np_of(preds)
+                    out[f"{key}/target"] = np_of(target)
+                    out[f"{key}/groups"] = np_of(groups)
+                    out[f"{key}/meta"] = np.array([num_groups, -999 if ign is None else ign])
+                    out[f"{key}/counts"] = np.stack([np.array([int(v) for v in st]) for st in stats])
+                    out[f"{key}/rates"] = np.stack([np_of(rates[f"group_{i}"]) for i in range(num_groups)])
+                    out[f"{key}/fair_keys"] = np.array(",".join(fair.keys()))
+                    out[f"{key}/fair_values"] = np.array([float(v) for v in fair.values()], dtype=np.float32)
+                    out[f"{key}/fair2_keys"] = np.array(",".join(fair_two_updates.keys()))
+                    out[f"{key}/fair2_values"] = np.array([float(v) for v in fair_two_updates.values()], dtype=np.float32)
+                    case += 1
+    out["n_cases"] = np.array(case)
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["classification"]
     if "classification" in which:
@@ -1166,5 +1223,10 @@ if __name__ == "__main__":
     if "coco_format" in which:
         data = coco_format_golden()
         path = os.path.join(HERE, "coco_format.npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
+    if "fairness" in which:
+        data = fairness_golden()
+        path = os.path.join(HERE, "fairness.npz")
         np.savez_compressed(path, **data)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")

@@ -285,11 +285,18 @@ def binned_curve_update(preds, target, thresholds, num_classes=1, multilabel=Fal
     return out
 
 
+NAMES = ("launch_count", "multiclass_confmat_update_", "multiclass_stat_scores_update_",
+         "multiclass_stat_scores_topk_update_", "multiclass_stat_scores_samplewise", "argmax_rows",
+         "sigmoid_if_logits", "softmax_if_logits", "curve_evaluate", "curve_evaluate_multilabel",
+         "binary_stat_counts", "regression_sums", "binned_curve_update")
+
+
+def standins() -> dict:
+    """name -> stand-in; a kernel launch is invisible to autograd, so the plain-torch stand-ins are detached the same way."""
+    return {name: torch.no_grad()(globals()[name]) for name in NAMES}
+
+
 def install(native_module) -> None:
     """Replace the kernel wrappers of `metrics_b200._native` by the stand-ins above."""
-    for name in ("launch_count", "multiclass_confmat_update_", "multiclass_stat_scores_update_",
-                 "multiclass_stat_scores_topk_update_", "multiclass_stat_scores_samplewise", "argmax_rows",
-                 "sigmoid_if_logits", "softmax_if_logits", "curve_evaluate", "curve_evaluate_multilabel",
-                 "binary_stat_counts", "regression_sums", "binned_curve_update"):
-        # a kernel launch is invisible to autograd; the stand-ins are plain torch ops, so detach them the same way
-        setattr(native_module, name, torch.no_grad()(globals()[name]))
+    for name, fn in standins().items():
+        setattr(native_module, name, fn)
