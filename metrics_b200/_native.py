@@ -55,11 +55,51 @@ def lib() -> ctypes.CDLL:
                 "There is no CPU fallback."
             )
         handle = ctypes.CDLL(_LIB_PATH)
-        handle.mb200_last_error.restype = ctypes.c_char_p
-        handle.mb200_launch_count.restype = ctypes.c_uint64
-        handle.mb200_abi_version.restype = ctypes.c_int
+        declare_signatures(handle)
         _lib = handle
     return _lib
+
+
+# Return / argument types of every entry point of include/metrics_b200.h, one letter per C type (tests/test_native_abi.py
+# re-derives this table from the header and fails when they drift apart).  Declaring them lets ctypes convert plain Python
+# ints / floats / None itself — no `c_void_p` / `c_int64` object per argument on the launch path, which was 4.6 us of the
+# ~15 us a small `update()` costs — and makes a wrong argument count or kind a TypeError instead of a silent truncation.
+_C_TYPES = {"i": ctypes.c_int, "q": ctypes.c_int64, "Q": ctypes.c_uint64, "d": ctypes.c_double, "p": ctypes.c_void_p,
+            "s": ctypes.c_char_p}
+SIGNATURES = {
+    "mb200_abi_version": ("i", ""),
+    "mb200_last_error": ("s", ""),
+    "mb200_launch_count": ("Q", ""),
+    "mb200_multiclass_confmat_update": ("i", "piipiqqqiqppp"),
+    "mb200_multiclass_stat_scores_update": ("i", "piipiqqqiqippppppp"),
+    "mb200_multiclass_stat_scores_topk_update": ("i", "pipiqqqiqppppppp"),
+    "mb200_multiclass_stat_scores_samplewise": ("i", "piipiqqqiqpppp"),
+    "mb200_argmax_rows": ("i", "piqqqpp"),
+    "mb200_curve_sigmoid_if_logits": ("i", "piqppp"),
+    "mb200_curve_softmax_if_logits": ("i", "piqqppp"),
+    "mb200_curve_workspace_bytes": ("q", "qq"),
+    "mb200_curve_pack_keys": ("i", "piqqpp"),
+    "mb200_curve_evaluate_keys": ("i", "ppiqqqpqppppp"),
+    "mb200_curve_evaluate": ("i", "pipiqqqpqpppppppp"),
+    "mb200_curve_evaluate_multilabel": ("i", "pipiqqiqpqpppppppp"),
+    "mb200_coco_map_workspace_bytes": ("q", "qqq"),
+    "mb200_coco_map_evaluate": ("i", "pppppppppqqqqqpqipqpqpqpqppppp"),
+    "mb200_binary_stat_counts": ("i", "pipiqqqdiqipppp"),
+    "mb200_regression_num_sums": ("i", "i"),
+    "mb200_regression_scratch_doubles": ("q", "qqi"),
+    "mb200_regression_sums": ("i", "ppiqqiddppp"),
+    "mb200_binned_curve_scratch_words": ("q", "qq"),
+    "mb200_binned_curve_update": ("i", "pipiqqpqppp"),
+    "mb200_binned_curve_update_multilabel": ("i", "pipiqqpqppp"),
+}
+
+
+def declare_signatures(handle) -> None:
+    """Set ``restype`` / ``argtypes`` of every exported function on a loaded library handle."""
+    for name, (ret, args) in SIGNATURES.items():
+        fn = getattr(handle, name)
+        fn.restype = _C_TYPES[ret]
+        fn.argtypes = [_C_TYPES[a] for a in args]
 
 
 def launch_count() -> int:
@@ -109,27 +149,29 @@ def on_device(device: torch.device):
     return torch.cuda.device(device)
 
 
-def ptr(t: Optional[Tensor]) -> ctypes.c_void_p:
-    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+def ptr(t: Optional[Tensor]) -> Optional[int]:
+    """Device address for a ``void*`` parameter (``None`` -> NULL); ctypes converts it, see `declare_signatures`."""
+    return None if t is None else t.data_ptr()
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
-def stream_handle(device: torch.device) -> ctypes.c_void_p:
-    """``cudaStream_t`` of torch's current stream on ``device`` (raw-pointer query: no Stream object per launch)."""
+def stream_handle(device: torch.device) -> int:
+    """``cudaStream_t`` of torch's current stream on ``device`` as an integer (raw-pointer query: no Stream object per
+    launch; 0 is the legacy default stream)."""
     if _raw_stream is not None:
-        return ctypes.c_void_p(_raw_stream(device.index if device.index is not None else torch.cuda.current_device()))
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        return _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 _flag_words: dict = {}
 
 
-def _flag_scratch(device: torch.device, stream: ctypes.c_void_p) -> Tensor:
+def _flag_scratch(device: torch.device, stream: int) -> Tensor:
     """4-byte device word for the batch-global "are these logits?" vote, one per (device, stream): launches on one stream
     are ordered, so consecutive format calls can share it; different streams never do."""
-    key = (device.index, stream.value)
+    key = (device.index, stream)
     t = _flag_words.get(key)
     if t is None:
         t = torch.zeros(1, dtype=torch.int32, device=device)
@@ -137,8 +179,9 @@ def _flag_scratch(device: torch.device, stream: ctypes.c_void_p) -> Tensor:
     return t
 
 
-def i64(v: int) -> ctypes.c_int64:
-    return ctypes.c_int64(int(v))
+def i64(v: int) -> int:
+    """Value for an ``int64_t`` parameter."""
+    return int(v)
 
 
 def check(rc: int, what: str) -> None:
@@ -171,7 +214,8 @@ def multiclass_confmat_update_(
     ignore_index: Optional[int],
     err_flag: Optional[Tensor] = None,
 ) -> None:
-    """In-place ``confmat[t, argmax(preds)] += 1`` (``mb200_multiclass_confmat_update``)."""
+    """In-place ``confmat[t, argmax(preds)] += 1`` (``mb200_multiclass_confmat_update``).  Launch path of cfg1 / cfg2:
+    arguments are handed to ctypes as plain ints (see `declare_signatures`), no helper call per argument."""
     dev = require_cuda(confmat, preds, target)
     has_class_dim = preds.ndim == target.ndim + 1
     preds = preds.contiguous()
@@ -179,11 +223,12 @@ def multiclass_confmat_update_(
     n_outer, inner = _class_dim_geometry(preds, has_class_dim)
     with on_device(dev):
         rc = lib().mb200_multiclass_confmat_update(
-            ptr(preds), tag(preds), int(has_class_dim), ptr(target), tag(target), i64(n_outer), i64(num_classes),
-            i64(inner), int(ignore_index is not None), i64(ignore_index or 0), ptr(confmat), ptr(err_flag),
-            stream_handle(dev),
+            preds.data_ptr(), tag(preds), has_class_dim, target.data_ptr(), tag(target), n_outer, num_classes, inner,
+            ignore_index is not None, ignore_index or 0, confmat.data_ptr(),
+            None if err_flag is None else err_flag.data_ptr(), stream_handle(dev),
         )
-    check(rc, "multiclass_confmat_update")
+    if rc:
+        check(rc, "multiclass_confmat_update")
 
 
 def multiclass_stat_scores_update_(
@@ -199,19 +244,21 @@ def multiclass_stat_scores_update_(
     micro: bool,
     err_flag: Optional[Tensor] = None,
 ) -> None:
-    """In-place tp/fp/tn/fn accumulation (``mb200_multiclass_stat_scores_update``)."""
-    dev = require_cuda(tp, fp, tn, fn, workspace, preds, target)
+    """In-place tp/fp/tn/fn accumulation (``mb200_multiclass_stat_scores_update``).  The four states and the workspace
+    belong to one metric and move together (`Metric._apply`), so one of them stands for all in the device check."""
+    dev = require_cuda(tp, workspace, preds, target)
     has_class_dim = preds.ndim == target.ndim + 1
     preds = preds.contiguous()
     target = target.contiguous()
     n_outer, inner = _class_dim_geometry(preds, has_class_dim)
     with on_device(dev):
         rc = lib().mb200_multiclass_stat_scores_update(
-            ptr(preds), tag(preds), int(has_class_dim), ptr(target), tag(target), i64(n_outer), i64(num_classes),
-            i64(inner), int(ignore_index is not None), i64(ignore_index or 0), int(micro), ptr(tp), ptr(fp),
-            ptr(tn), ptr(fn), ptr(workspace), ptr(err_flag), stream_handle(dev),
+            preds.data_ptr(), tag(preds), has_class_dim, target.data_ptr(), tag(target), n_outer, num_classes, inner,
+            ignore_index is not None, ignore_index or 0, micro, tp.data_ptr(), fp.data_ptr(), tn.data_ptr(),
+            fn.data_ptr(), workspace.data_ptr(), None if err_flag is None else err_flag.data_ptr(), stream_handle(dev),
         )
-    check(rc, "multiclass_stat_scores_update")
+    if rc:
+        check(rc, "multiclass_stat_scores_update")
 
 
 def argmax_rows(preds: Tensor) -> Tensor:
@@ -278,7 +325,6 @@ def curve_evaluate(preds: Tensor, target: Tensor, num_classes: int = 1, pos_labe
     target = target.contiguous()
     n = target.numel()
     lib_ = lib()
-    lib_.mb200_curve_workspace_bytes.restype = ctypes.c_int64
     nbytes = int(lib_.mb200_curve_workspace_bytes(i64(num_classes), i64(n)))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     auroc = torch.empty(num_classes, dtype=torch.float32, device=dev)
@@ -325,7 +371,6 @@ def coco_map_evaluate(
     classes = classes.to(torch.int64).contiguous()
     rec_dev = torch.tensor(rec_thresholds, dtype=torch.float64).to(dev, non_blocking=True)
     lib_ = lib()
-    lib_.mb200_coco_map_workspace_bytes.restype = ctypes.c_int64
     nbytes = int(lib_.mb200_coco_map_workspace_bytes(i64(n_det), i64(max(1, classes.numel())), i64(M)))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     precision = torch.empty((T, R, K, 4, M), dtype=torch.float64, device=dev)
@@ -398,7 +443,6 @@ def regression_sums(preds: Tensor, target: Tensor, op: int, num_outputs: int = 1
     k = _REG_NUM_SUMS.get(op, 1)
     out = torch.empty((k, d), dtype=torch.float64, device=dev)
     lib_ = lib()
-    lib_.mb200_regression_scratch_doubles.restype = ctypes.c_int64
     scratch = torch.empty(int(lib_.mb200_regression_scratch_doubles(i64(n), i64(d), int(op))), dtype=torch.float64, device=dev)
     with on_device(dev):
         rc = lib_.mb200_regression_sums(
@@ -429,7 +473,6 @@ def binned_curve_update(preds: Tensor, target: Tensor, thresholds: Tensor, num_c
     t_count = thr.numel()
     confmat = torch.zeros((t_count, num_classes, 2, 2), dtype=torch.int64, device=dev)
     lib_ = lib()
-    lib_.mb200_binned_curve_scratch_words.restype = ctypes.c_int64
     scratch = torch.zeros(int(lib_.mb200_binned_curve_scratch_words(i64(num_classes), i64(t_count))), dtype=torch.int64, device=dev)
     with on_device(dev):
         fn = lib_.mb200_binned_curve_update_multilabel if multilabel else lib_.mb200_binned_curve_update
@@ -511,7 +554,6 @@ def curve_evaluate_keys(keys: Tensor, target: Tensor, first_class: int):
     target = target.contiguous()
     s, n = keys.shape
     lib_ = lib()
-    lib_.mb200_curve_workspace_bytes.restype = ctypes.c_int64
     nbytes = int(lib_.mb200_curve_workspace_bytes(i64(s), i64(n)))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     auroc = torch.empty(s, dtype=torch.float32, device=dev)
@@ -537,7 +579,6 @@ def curve_evaluate_multilabel(preds: Tensor, target: Tensor, num_labels: int, ig
     target = target.contiguous()
     n = preds.shape[0]
     lib_ = lib()
-    lib_.mb200_curve_workspace_bytes.restype = ctypes.c_int64
     nbytes = int(lib_.mb200_curve_workspace_bytes(i64(num_labels), i64(n)))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     auroc = torch.empty(num_labels, dtype=torch.float32, device=dev)
