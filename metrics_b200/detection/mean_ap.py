@@ -33,6 +33,68 @@ def _box_convert_to_xywh(boxes: Tensor, in_fmt: str) -> Tensor:
     return torch.stack((x1, y1, x2 - x1, y2 - y1), dim=-1)
 
 
+def _pairwise_ious(det_box: Tensor, det_score: Tensor, det_label: Tensor, det_counts: List[int], gt_box: Tensor,
+                   gt_label: Tensor, gt_crowd: Tensor, gt_counts: List[int], classes: List[int], micro: bool,
+                   max_det: int) -> Dict[Tuple[int, int], Any]:
+    """The ``ious`` entry of the extended summary (reference :552-555, i.e. pycocotools ``COCOeval.computeIoU`` for every
+    (image, category)): ``{(image, class): [D, G] float32}`` with the pair's detections in descending-score order (stable,
+    cut to the largest max-detection threshold) and its ground truths in input order; ``[]`` when either side is empty.
+
+    pycocotools fills the dict with one small host computation per (image, category).  Here ALL pairs of the whole state
+    are evaluated by one batch of device ops over a flat pair list (fp64, crowd ground truths use the detection's area as
+    the union, ``maskApi.c:bbIou``); the dict values are views into that one tensor."""
+    dev = det_box.device
+    n_img, n_cls = len(det_counts), (1 if micro else len(classes))
+    img_of_det = torch.repeat_interleave(torch.arange(n_img, device=dev), torch.tensor(det_counts, device=dev))
+    img_of_gt = torch.repeat_interleave(torch.arange(n_img, device=dev), torch.tensor(gt_counts, device=dev))
+    if micro:
+        det_key, gt_key = img_of_det, img_of_gt
+    else:
+        table = torch.tensor(classes, dtype=torch.int64, device=dev)
+        det_key = img_of_det * n_cls + torch.searchsorted(table, det_label)
+        gt_key = img_of_gt * n_cls + torch.searchsorted(table, gt_label)
+    # detections: by (pair, score descending, input order); ground truths: by (pair, input order)
+    by_score = torch.sort(det_score, descending=True, stable=True).indices
+    det_order = by_score[torch.sort(det_key[by_score], stable=True).indices]
+    gt_order = torch.sort(gt_key, stable=True).indices
+    n_pairs = n_img * n_cls
+    det_total = torch.bincount(det_key, minlength=n_pairs)
+    gt_cnt = torch.bincount(gt_key, minlength=n_pairs)
+    det_start = torch.cumsum(det_total, 0) - det_total
+    gt_start = torch.cumsum(gt_cnt, 0) - gt_cnt
+    sorted_key = det_key[det_order]
+    rank = torch.arange(det_order.numel(), device=dev) - det_start[sorted_key]
+    keep = rank < max_det
+    det_order, sorted_key = det_order[keep], sorted_key[keep]
+    det_cnt = torch.clamp(det_total, max=max_det)
+    # flat list of (detection row, ground-truth column) pairs, row-major inside every (image, class) block
+    cols_of_row = gt_cnt[sorted_key]
+    row = torch.repeat_interleave(torch.arange(det_order.numel(), device=dev), cols_of_row)
+    row_first = torch.cumsum(cols_of_row, 0) - cols_of_row
+    col = torch.arange(row.numel(), device=dev) - row_first[row]
+    d = det_box[det_order[row]].to(torch.float64)
+    g_index = gt_order[gt_start[sorted_key[row]] + col]
+    g = gt_box[g_index].to(torch.float64)
+    w = torch.minimum(d[:, 0] + d[:, 2], g[:, 0] + g[:, 2]) - torch.maximum(d[:, 0], g[:, 0])
+    h = torch.minimum(d[:, 1] + d[:, 3], g[:, 1] + g[:, 3]) - torch.maximum(d[:, 1], g[:, 1])
+    inter = torch.where((w > 0) & (h > 0), w * h, torch.zeros_like(w))
+    det_area = d[:, 2] * d[:, 3]
+    union = torch.where(gt_crowd[g_index] != 0, det_area, det_area + g[:, 2] * g[:, 3] - inter)
+    flat = (inter / union).to(torch.float32)
+    # one host read of the block shapes, then the dict is assembled from views
+    shapes = torch.stack((det_cnt, gt_cnt), 1).cpu().tolist()
+    out: Dict[Tuple[int, int], Any] = {}
+    offset = 0
+    for pair, (n_d, n_g) in enumerate(shapes):
+        key = (pair // n_cls, 0 if micro else classes[pair % n_cls])
+        if n_d == 0 or n_g == 0:
+            out[key] = []
+            continue
+        out[key] = flat[offset: offset + n_d * n_g].view(n_d, n_g)
+        offset += n_d * n_g
+    return out
+
+
 class MeanAveragePrecision(Metric):
     """mAP / mAR for bounding-box detection (reference :77-1063).
 
@@ -398,6 +460,9 @@ class MeanAveragePrecision(Metric):
             raise NotImplementedError("metrics_b200: more than 256 ground truths of one class in a single image")
         result.update(self._stats_dict(self._summarize(precision, recall)))
         if self.extended_summary:
+            micro = self.average == "micro"
+            result["ious"] = _pairwise_ious(det_box, det_score, det_label, det_counts, gt_box, gt_label, gt_crowd, gt_counts,
+                                            classes_list, micro, self.max_detection_thresholds[-1])
             result["precision"] = precision
             result["recall"] = recall
             result["scores"] = scores

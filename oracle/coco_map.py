@@ -71,6 +71,29 @@ def bb_iou(dt: np.ndarray, gt: np.ndarray, iscrowd: np.ndarray) -> np.ndarray:
     return out
 
 
+def compute_ious(det_boxes: Sequence[np.ndarray], det_scores: Sequence[np.ndarray], det_labels: Sequence[np.ndarray],
+                 gt_boxes: Sequence[np.ndarray], gt_labels: Sequence[np.ndarray], gt_crowds: Sequence[np.ndarray],
+                 classes: Sequence[int], max_det: int) -> dict:
+    """COCOeval.computeIoU for every (image, category), i.e. the `ious` entry of the reference's extended summary
+    (detection/mean_ap.py:552-555 reads `coco_eval.ious`): detections of the pair sorted by descending score (mergesort),
+    cut to the largest maxDets, ground truths in dataset order; `[]` when either side is empty (maskUtils.iou of an empty
+    list), else a float32 `[D, G]` array (the reference converts the double matrix with `torch.tensor(x, float32)`)."""
+    out = {}
+    for img in range(len(det_labels)):
+        for cat in classes:
+            d_sel = np.nonzero(np.asarray(det_labels[img]).reshape(-1) == cat)[0]
+            g_sel = np.nonzero(np.asarray(gt_labels[img]).reshape(-1) == cat)[0]
+            if len(d_sel) == 0 or len(g_sel) == 0:
+                out[(img, int(cat))] = []
+                continue
+            order = np.argsort(-np.asarray(det_scores[img], dtype=np.float64).reshape(-1)[d_sel], kind="mergesort")[:max_det]
+            d = np.asarray(det_boxes[img]).reshape(-1, 4)[d_sel][order]
+            g = np.asarray(gt_boxes[img]).reshape(-1, 4)[g_sel]
+            crowd = np.asarray(gt_crowds[img]).reshape(-1)[g_sel]
+            out[(img, int(cat))] = bb_iou(d, g, crowd).astype(np.float32)
+    return out
+
+
 def _evaluate_img(dt_boxes, dt_scores, gt_boxes, gt_crowd, gt_area, iou_thrs, area_rng, max_det):
     """COCOeval.computeIoU + evaluateImg for one (image, category, area range).  Returns None when both lists are empty."""
     if len(dt_scores) == 0 and len(gt_boxes) == 0:
