@@ -103,7 +103,7 @@ def test_binned_classes_and_large_threshold_counts(golden_binned):
         m.update(a, b)
     np.testing.assert_array_equal(m.confmat.cpu().numpy(), g["class/binary_auroc_50_confmat"])
     np.testing.assert_allclose(m.compute().cpu().numpy(), g["class/binary_auroc_50"], **TOL)
-    assert "confmat" in m.metric_state and m.thresholds.device.type == "cuda"
+    assert "confmat" in m.metric_state and m.thresholds.device.type == torch.device(DEV).type
     ml, mt = torch.from_numpy(g["m/logits"]).to(DEV), torch.from_numpy(g["m/target"]).to(DEV)
     m2 = MulticlassAveragePrecision(num_classes=6, thresholds=20).to(DEV)
     for a, b in zip(ml.chunk(3), mt.chunk(3)):

@@ -1,0 +1,24 @@
+"""CPU: the GPU parity suites replayed on CPU tensors with the kernel wrappers swapped for their torch stand-ins
+(tests/host_twin_plugin.py).  Everything above the C-ABI — validation, the format seams, states, reducers, compute groups,
+class / functional / task-wrapper plumbing — is thereby held to the reference's goldens on every CPU run; the kernels are
+held to the same goldens by the same files on the GPU box.  One child pytest process, so that the stand-ins never exist
+in this process."""
+import os
+import re
+import subprocess
+import sys
+
+from tests.conftest import ROOT
+
+SUITES = ["test_confmat_gpu", "test_topk_samplewise_gpu", "test_binary_gpu", "test_consumers_gpu", "test_curves_gpu",
+          "test_multilabel_gpu", "test_binned_gpu", "test_atfixed_gpu", "test_regression_gpu", "test_logauc"]
+
+
+def test_gpu_parity_suites_pass_on_kernel_standins():
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "tests.host_twin_plugin", "-p", "no:cacheprovider",
+           *[os.path.join("tests", f"{name}.py") for name in SUITES]]
+    run = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=1500)
+    tail = run.stdout.strip().splitlines()[-1] if run.stdout.strip() else run.stderr[-400:]
+    assert run.returncode == 0, run.stdout[-3000:] + run.stderr[-1000:]
+    passed = int(re.search(r"(\d+) passed", tail).group(1))
+    assert passed >= 290 and "failed" not in tail and "skipped" not in tail, tail

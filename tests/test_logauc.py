@@ -8,6 +8,8 @@ import torch
 from metrics_b200.functional.classification.logauc import _binary_logauc_compute
 from oracle import curves as oc
 
+DEV = "cuda:0"
+
 RANGES = ((0.001, 0.1), (0.01, 0.5), (0.0005, 1.0))
 
 
@@ -33,17 +35,17 @@ def test_functional_and_class_gpu(golden_logauc):
     import metrics_b200.functional.classification as F
 
     g = golden_logauc
-    p, t = torch.from_numpy(g["b/preds"]).cuda(), torch.from_numpy(g["b/target"]).cuda()
+    p, t = torch.from_numpy(g["b/preds"]).to(DEV), torch.from_numpy(g["b/target"]).to(DEV)
     for j, rng in enumerate(RANGES[:2]):
         np.testing.assert_allclose(F.binary_logauc(p, t, fpr_range=rng).cpu().numpy(), g[f"b/logauc{j}"], rtol=2e-6)
-    m = TC.BinaryLogAUC(fpr_range=RANGES[0]).cuda()
+    m = TC.BinaryLogAUC(fpr_range=RANGES[0]).to(DEV)
     for a, b in zip(p.chunk(3), t.chunk(3)):
         m.update(a, b)
     np.testing.assert_allclose(m.compute().cpu().numpy(), g["b/logauc0"], rtol=2e-6)
     # multiclass / multilabel: consistent with the per-class binary evaluation of the one-vs-rest problems
     gen = torch.Generator().manual_seed(9)
-    lg = torch.randn(2000, 4, generator=gen).cuda()
-    tg = torch.randint(0, 4, (2000,), generator=gen).cuda()
+    lg = torch.randn(2000, 4, generator=gen).to(DEV)
+    tg = torch.randint(0, 4, (2000,), generator=gen).to(DEV)
     per_class = F.multiclass_logauc(lg, tg, 4, average="none")
     probs = torch.softmax(lg, 1)
     for c in range(4):
