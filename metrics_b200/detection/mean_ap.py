@@ -407,8 +407,8 @@ class MeanAveragePrecision(Metric):
             return torch.empty(shape, dtype=dtype, device=device)
         try:  # common case: every entry already has the right trailing shape -> no per-image Python work
             flat = torch.cat(items)
-            if flat.ndim != len(shape):
-                raise RuntimeError("rank mismatch")
+            if flat.ndim != len(shape) or tuple(flat.shape[1:]) != tuple(shape[1:]):  # e.g. a lone `[1, 0]` "no boxes" entry
+                raise RuntimeError("layout mismatch")
         except RuntimeError:
             items = [t.reshape(-1, *shape[1:]) for t in items if t.numel() > 0]
             if not items:

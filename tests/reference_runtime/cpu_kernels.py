@@ -285,10 +285,35 @@ def binned_curve_update(preds, target, thresholds, num_classes=1, multilabel=Fal
     return out
 
 
+def coco_map_evaluate(det_box, det_score, det_label, det_counts, gt_box, gt_label, gt_crowd, gt_area, gt_counts, classes,
+                      micro, iou_thresholds, rec_thresholds, max_dets):
+    """Stand-in for the COCO mAP kernels: the numpy oracle (oracle/coco_map.py) on the flat, already-xywh state tensors.
+    The GPU tests compare the kernels with that same oracle, so a replay through this stand-in checks only what
+    `MeanAveragePrecision.compute` does around the kernel call (concatenation order, counts, defaults, summary table)."""
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from oracle.coco_map import coco_evaluate
+
+    def per_image(flat, counts):
+        return [piece.numpy() for piece in torch.split(flat, list(counts))]
+
+    res = coco_evaluate(
+        per_image(det_box, det_counts), per_image(det_score, det_counts), per_image(det_label, det_counts),
+        per_image(gt_box, gt_counts), per_image(gt_label, gt_counts), per_image(gt_crowd, gt_counts),
+        per_image(gt_area, gt_counts), box_format="xywh", iou_thresholds=list(iou_thresholds),
+        rec_thresholds=list(rec_thresholds), max_detection_thresholds=list(max_dets), average="micro" if micro else "macro")
+    as_f64 = lambda name: torch.from_numpy(res[name].astype("float64"))  # noqa: E731
+    return as_f64("precision"), as_f64("recall"), as_f64("scores"), torch.zeros(1, dtype=torch.int32)
+
+
 NAMES = ("launch_count", "multiclass_confmat_update_", "multiclass_stat_scores_update_",
          "multiclass_stat_scores_topk_update_", "multiclass_stat_scores_samplewise", "argmax_rows",
          "sigmoid_if_logits", "softmax_if_logits", "curve_evaluate", "curve_evaluate_multilabel",
-         "binary_stat_counts", "regression_sums", "binned_curve_update")
+         "binary_stat_counts", "regression_sums", "binned_curve_update", "coco_map_evaluate")
 
 
 def standins() -> dict:
