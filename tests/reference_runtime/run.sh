@@ -26,6 +26,6 @@ if [ $# -eq 0 ]; then
 else
     sub=$1; shift
     for f in "$@"; do
-        echo "=== $sub/$f: $(MB200_REF_CPU_KERNELS=1 run $sub/$f -k 'not plot and not nrmse and not _Absent')"
+        echo "=== $sub/$f: $(USE_PYTEST_POOL=1 MB200_REF_CPU_KERNELS=1 run $sub/$f -k 'not plot and not nrmse and not _Absent')"
     done
 fi
