@@ -1,7 +1,7 @@
 """Stat-scores metric classes (reference: classification/stat_scores.py)."""
 from __future__ import annotations
 
-from typing import Any, List, Optional, Union
+from typing import Any, Optional
 
 import torch
 from torch import Tensor

@@ -5,7 +5,7 @@ by ONE kernel pass instead of 2-5 elementwise/reduction launches; the `_x_comput
 """
 from __future__ import annotations
 
-from typing import Optional, Union
+from typing import Union
 
 import torch
 from torch import Tensor

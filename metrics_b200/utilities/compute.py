@@ -5,7 +5,7 @@ rounding of the final ratios (int64 -> float32, then divide), so they follow the
 """
 from __future__ import annotations
 
-from typing import Optional, Union
+from typing import Optional
 
 import torch
 from torch import Tensor
