@@ -60,6 +60,18 @@ def interp(x: Tensor, xp: Tensor, fp: Tensor) -> Tensor:
     return m[idx] * x + b[idx]
 
 
+def _safe_matmul(x: Tensor, y: Tensor) -> Tensor:
+    """``x @ y.T``; half inputs are multiplied in float32 and rounded back (reference compute.py:21-29)."""
+    if torch.float16 in (x.dtype, y.dtype):
+        return (x.float() @ y.float().T).half()
+    return x @ y.T
+
+
+def _safe_xlogy(x: Tensor, y: Tensor) -> Tensor:
+    """``x * log(y)`` with the convention ``0 * log(anything) = 0`` (reference compute.py:32-44)."""
+    return torch.where(x == 0, torch.zeros_like(x), x * torch.log(y))
+
+
 def _auc_format_inputs(x: Tensor, y: Tensor) -> tuple[Tensor, Tensor]:
     """Squeeze to 1-d and check the two lengths (reference compute.py:85-98)."""
     x = x.squeeze() if x.ndim > 1 else x

@@ -9,6 +9,9 @@
 #                                            reference's CPU-tensor tests reach our host layer: validation, formatting seams,
 #                                            state handling, reducers, task wrappers, error messages.
 #
+#   MB200_REF_CPU_KERNELS=1 PYTHONPATH=tests/reference_runtime python tests/reference_runtime/run_doctests.py
+#                                            the reference's docstring examples replayed against this package
+#
 # The stand-ins are TEST INFRASTRUCTURE (the product has no CPU path and raises on CPU tensors); they are only ever
 # installed by sitecustomize.py when MB200_REF_CPU_KERNELS=1.
 HERE="$(cd "$(dirname "$0")" && pwd)"
