@@ -239,12 +239,14 @@ MB200_API int mb200_binary_stat_counts(const void* preds, int preds_dtype, const
 /* ------------------------------------------------------------------------------------------------
  * K9 — regression running sums (one fused map-reduce per update).
  * Replaces the `_x_update` functions of functional/regression/{mse,mae,mape,symmetric_mape,wmape,log_mse,log_cosh,
- * minkowski,r2,explained_variance}.py (file:line list in csrc/regression.cu).
+ * minkowski,r2,explained_variance,tweedie_deviance}.py (file:line list in csrc/regression.cu).
  *  preds, target : [n, d] contiguous, same floating dtype (d = num_outputs; flatten to d = 1 for scalar metrics)
  *  op            : 0 MSE sum d^2 | 1 MAE sum|d| | 2 MAPE sum|d|/max(|t|,eps) | 3 SMAPE sum|d|/max(|t|+|p|,eps)
  *                  4 WMAPE {sum|d|, sum|t|} | 5 MSLE sum(log1p p - log1p t)^2 | 6 LogCosh sum log((e^d+e^-d)/2)
  *                  7 Minkowski sum|d|^param | 8 R2/RSE {sum t^2, sum t, sum (t-p)^2}
  *                  9 ExplainedVariance {sum (t-p), sum (t-p)^2, sum t, sum t^2}          (d = p - t)
+ *                  10 Tweedie deviance of power `param` (1 Poisson, 2 Gamma, else the general form; 0 is op 0) with the
+ *                     domain census the reference gets from extra passes: {sum dev, #(p <= 0), #(t < 0), #(t == 0)}
  *  out_sums      : float64 [num_sums(op)][d], overwritten
  *  scratch       : float64 [mb200_regression_scratch_doubles(n, d, op)]
  * Terms are evaluated in fp32 (fp64 for fp64 inputs), sums in fp64 with a fixed order (bitwise reproducible).

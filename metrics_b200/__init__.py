@@ -43,6 +43,7 @@ from metrics_b200.regression import (  # noqa: F401  (reference __init__.py:113-
     R2Score,
     RelativeSquaredError,
     SymmetricMeanAbsolutePercentageError,
+    TweedieDevianceScore,
     WeightedMeanAbsolutePercentageError,
 )
 from metrics_b200.wrappers import ClasswiseWrapper  # noqa: F401

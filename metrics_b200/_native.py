@@ -425,8 +425,8 @@ def binary_stat_counts(
 # ----------------------------------------------------------------------------------------------------------
 # K9 wrapper (regression running sums)
 # ----------------------------------------------------------------------------------------------------------
-REG_MSE, REG_MAE, REG_MAPE, REG_SMAPE, REG_WMAPE, REG_MSLE, REG_LOGCOSH, REG_MINKOWSKI, REG_R2, REG_EXPVAR = range(10)
-_REG_NUM_SUMS = {REG_WMAPE: 2, REG_R2: 3, REG_EXPVAR: 4}
+REG_MSE, REG_MAE, REG_MAPE, REG_SMAPE, REG_WMAPE, REG_MSLE, REG_LOGCOSH, REG_MINKOWSKI, REG_R2, REG_EXPVAR, REG_TWEEDIE = range(11)
+_REG_NUM_SUMS = {REG_WMAPE: 2, REG_R2: 3, REG_EXPVAR: 4, REG_TWEEDIE: 4}
 
 
 def regression_sums(preds: Tensor, target: Tensor, op: int, num_outputs: int = 1, param: float = 0.0, eps: float = 0.0) -> Tensor:

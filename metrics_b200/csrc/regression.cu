@@ -8,50 +8,11 @@
 // the per-CTA partials), so results are bitwise reproducible and at least as accurate as the reference's fp32 `torch.sum`.
 #include "common.cuh"
 
+#include "regression_terms.cuh"
+
 namespace mb200 {
 
 extern void count_launch();
-
-enum RegOp { REG_MSE = 0, REG_MAE, REG_MAPE, REG_SMAPE, REG_WMAPE, REG_MSLE, REG_LOGCOSH, REG_MINKOWSKI, REG_R2, REG_EXPVAR };
-constexpr int kRegMaxK = 4;
-
-__host__ __device__ inline int reg_num_sums(int op) {
-    switch (op) {
-        case REG_WMAPE: return 2;
-        case REG_R2: return 3;
-        case REG_EXPVAR: return 4;
-        default: return 1;
-    }
-}
-
-template <typename F>
-__device__ __forceinline__ void reg_terms(int op, F p, F t, F param, F eps, F (&out)[kRegMaxK]) {
-    const F d = p - t;
-    switch (op) {
-        case REG_MSE: out[0] = d * d; break;
-        case REG_MAE: out[0] = fabs(d); break;
-        case REG_MAPE: out[0] = fabs(d) / fmax(fabs(t), eps); break;
-        case REG_SMAPE: out[0] = fabs(d) / fmax(fabs(t) + fabs(p), eps); break;  // the factor 2 is applied to the sum
-        case REG_WMAPE: out[0] = fabs(d), out[1] = fabs(t); break;
-        case REG_MSLE: {
-            const F l = log1p(p) - log1p(t);
-            out[0] = l * l;
-            break;
-        }
-        case REG_LOGCOSH: out[0] = log((exp(d) + exp(-d)) / (F)2); break;
-        case REG_MINKOWSKI: out[0] = pow(fabs(d), param); break;
-        case REG_R2: {
-            const F r = t - p;
-            out[0] = t * t, out[1] = t, out[2] = r * r;
-            break;
-        }
-        case REG_EXPVAR: {
-            const F r = t - p;
-            out[0] = r, out[1] = r * r, out[2] = t, out[3] = t * t;
-            break;
-        }
-    }
-}
 
 template <typename T>
 __device__ __forceinline__ double load_as_double(const T* p, long long i);
@@ -65,7 +26,7 @@ template <>
 __device__ __forceinline__ double load_as_double<__nv_bfloat16>(const __nv_bfloat16* p, long long i) { return __bfloat162float(p[i]); }
 
 // grid.x CTAs of 256 threads laid out as rows x cols_per_block; grid.y tiles the columns.
-template <typename T, bool kDouble>
+template <typename T, bool kDouble, bool kTweedie = false>
 __global__ void __launch_bounds__(256) reg_partial_kernel(const T* __restrict__ preds, const T* __restrict__ target,
                                                           long long n, int d, int op, double param, double eps,
                                                           int cols_per_block, double* __restrict__ partial) {
@@ -81,12 +42,12 @@ __global__ void __launch_bounds__(256) reg_partial_kernel(const T* __restrict__ 
             const long long i = r * d + c;
             if (kDouble) {
                 double out[kRegMaxK];
-                reg_terms<double>(op, load_as_double<T>(preds, i), load_as_double<T>(target, i), param, eps, out);
+                reg_terms<double, kTweedie>(op, load_as_double<T>(preds, i), load_as_double<T>(target, i), param, eps, out);
                 for (int k = 0; k < K; ++k) acc[k] += out[k];
             } else {
                 float out[kRegMaxK];
-                reg_terms<float>(op, (float)load_as_double<T>(preds, i), (float)load_as_double<T>(target, i), (float)param,
-                                 (float)eps, out);
+                reg_terms<float, kTweedie>(op, (float)load_as_double<T>(preds, i), (float)load_as_double<T>(target, i),
+                                           (float)param, (float)eps, out);
                 for (int k = 0; k < K; ++k) acc[k] += (double)out[k];
             }
         }
@@ -109,7 +70,7 @@ __global__ void __launch_bounds__(256) reg_partial_kernel(const T* __restrict__ 
 // the CTA (deterministic order).  The generic kernel above walks one element per thread per iteration with 16 warps per SM
 // and measured 0.94 TB/s; this one is bound by HBM.
 constexpr int kRegFlatThreads = 512;
-template <typename T, bool kDouble>
+template <typename T, bool kDouble, bool kTweedie = false>
 __global__ void __launch_bounds__(kRegFlatThreads) reg_flat_kernel(const T* __restrict__ preds, const T* __restrict__ target,
                                                                    long long n, int op, double param, double eps,
                                                                    double* __restrict__ partial) {
@@ -124,11 +85,12 @@ __global__ void __launch_bounds__(kRegFlatThreads) reg_flat_kernel(const T* __re
     auto consume = [&](const T& pv, const T& tv) {
         if (kDouble) {
             double out[kRegMaxK];
-            reg_terms<double>(op, (double)pv, (double)tv, param, eps, out);
+            reg_terms<double, kTweedie>(op, (double)pv, (double)tv, param, eps, out);
             for (int k = 0; k < K; ++k) acc[k] += out[k];
         } else {
             float out[kRegMaxK];
-            reg_terms<float>(op, (float)load_as_double<T>(&pv, 0), (float)load_as_double<T>(&tv, 0), (float)param, (float)eps, out);
+            reg_terms<float, kTweedie>(op, (float)load_as_double<T>(&pv, 0), (float)load_as_double<T>(&tv, 0), (float)param,
+                                       (float)eps, out);
             for (int k = 0; k < K; ++k) acc[k] += (double)out[k];
         }
     };
@@ -185,17 +147,17 @@ __global__ void reg_final_kernel(const double* __restrict__ partial, int n_cta, 
 
 using namespace mb200;
 
-extern "C" int mb200_regression_num_sums(int op) { return (op >= 0 && op <= REG_EXPVAR) ? reg_num_sums(op) : -1; }
+extern "C" int mb200_regression_num_sums(int op) { return (op >= 0 && op <= REG_LAST) ? reg_num_sums(op) : -1; }
 
 extern "C" int64_t mb200_regression_scratch_doubles(int64_t n, int64_t d, int op) {
-    if (n < 0 || d < 1 || op < 0 || op > REG_EXPVAR) return -1;
+    if (n < 0 || d < 1 || op < 0 || op > REG_LAST) return -1;
     return (int64_t)296 * reg_num_sums(op) * d + 8;
 }
 
 extern "C" int mb200_regression_sums(const void* preds, const void* target, int dtype, int64_t n, int64_t d, int op,
                                      double param, double epsilon, double* out_sums, double* scratch, void* stream) {
     MB200_REQUIRE(n >= 0 && d >= 1 && d < (1 << 30), "bad sizes");
-    MB200_REQUIRE(op >= 0 && op <= REG_EXPVAR, "unknown regression op %d", op);
+    MB200_REQUIRE(op >= 0 && op <= REG_LAST, "unknown regression op %d", op);
     MB200_REQUIRE(out_sums && scratch, "NULL pointer");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int K = reg_num_sums(op);
@@ -213,34 +175,47 @@ extern "C" int mb200_regression_sums(const void* preds, const void* target, int 
         long long fg = (n + per_cta - 1) / per_cta;
         if (fg > 296) fg = 296;  // scratch holds 296 partial rows
         const int g1 = (int)(fg < 1 ? 1 : fg);
-        switch (dtype) {
-            case MB200_F32: reg_flat_kernel<float, false><<<g1, kRegFlatThreads, 0, st>>>((const float*)preds, (const float*)target, n, op, param, epsilon, scratch); break;
-            case MB200_F64: reg_flat_kernel<double, true><<<g1, kRegFlatThreads, 0, st>>>((const double*)preds, (const double*)target, n, op, param, epsilon, scratch); break;
-            case MB200_F16: reg_flat_kernel<__half, false><<<g1, kRegFlatThreads, 0, st>>>((const __half*)preds, (const __half*)target, n, op, param, epsilon, scratch); break;
-            case MB200_BF16: reg_flat_kernel<__nv_bfloat16, false><<<g1, kRegFlatThreads, 0, st>>>((const __nv_bfloat16*)preds, (const __nv_bfloat16*)target, n, op, param, epsilon, scratch); break;
-            default: set_error("regression inputs must be floating point (dtype tag %d)", dtype); return MB200_ERR_INVALID;
+#define MB200_REG_FLAT(T, DBL, TW) \
+    reg_flat_kernel<T, DBL, TW><<<g1, kRegFlatThreads, 0, st>>>((const T*)preds, (const T*)target, n, op, param, epsilon, scratch)
+#define MB200_REG_FLAT_BY_DTYPE(TW)                                                                                   \
+    switch (dtype) {                                                                                                  \
+        case MB200_F32: MB200_REG_FLAT(float, false, TW); break;                                                      \
+        case MB200_F64: MB200_REG_FLAT(double, true, TW); break;                                                      \
+        case MB200_F16: MB200_REG_FLAT(__half, false, TW); break;                                                     \
+        case MB200_BF16: MB200_REG_FLAT(__nv_bfloat16, false, TW); break;                                             \
+        default: set_error("regression inputs must be floating point (dtype tag %d)", dtype); return MB200_ERR_INVALID; \
+    }
+        if (op == REG_TWEEDIE) {
+            MB200_REG_FLAT_BY_DTYPE(true)
+        } else {
+            MB200_REG_FLAT_BY_DTYPE(false)
         }
+#undef MB200_REG_FLAT_BY_DTYPE
+#undef MB200_REG_FLAT
         reg_final_kernel<<<1, 256, 0, st>>>(scratch, g1, K, 1, out_sums);
         count_launch();
         count_launch();
         return check_cuda(cudaGetLastError(), "regression sums launch");
     }
     const dim3 grid((unsigned)gx, (unsigned)col_tiles);
-    switch (dtype) {
-        case MB200_F32:
-            reg_partial_kernel<float, false><<<grid, 256, 0, st>>>((const float*)preds, (const float*)target, n, (int)d, op, param, epsilon, cols_per_block, scratch);
-            break;
-        case MB200_F64:
-            reg_partial_kernel<double, true><<<grid, 256, 0, st>>>((const double*)preds, (const double*)target, n, (int)d, op, param, epsilon, cols_per_block, scratch);
-            break;
-        case MB200_F16:
-            reg_partial_kernel<__half, false><<<grid, 256, 0, st>>>((const __half*)preds, (const __half*)target, n, (int)d, op, param, epsilon, cols_per_block, scratch);
-            break;
-        case MB200_BF16:
-            reg_partial_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)preds, (const __nv_bfloat16*)target, n, (int)d, op, param, epsilon, cols_per_block, scratch);
-            break;
-        default: set_error("regression inputs must be floating point (dtype tag %d)", dtype); return MB200_ERR_INVALID;
+#define MB200_REG_PART(T, DBL, TW)                                                                                      \
+    reg_partial_kernel<T, DBL, TW><<<grid, 256, 0, st>>>((const T*)preds, (const T*)target, n, (int)d, op, param, epsilon, \
+                                                         cols_per_block, scratch)
+#define MB200_REG_PART_BY_DTYPE(TW)                                                                                   \
+    switch (dtype) {                                                                                                  \
+        case MB200_F32: MB200_REG_PART(float, false, TW); break;                                                      \
+        case MB200_F64: MB200_REG_PART(double, true, TW); break;                                                      \
+        case MB200_F16: MB200_REG_PART(__half, false, TW); break;                                                     \
+        case MB200_BF16: MB200_REG_PART(__nv_bfloat16, false, TW); break;                                             \
+        default: set_error("regression inputs must be floating point (dtype tag %d)", dtype); return MB200_ERR_INVALID; \
     }
+    if (op == REG_TWEEDIE) {
+        MB200_REG_PART_BY_DTYPE(true)
+    } else {
+        MB200_REG_PART_BY_DTYPE(false)
+    }
+#undef MB200_REG_PART_BY_DTYPE
+#undef MB200_REG_PART
     reg_final_kernel<<<(int)((K * d + 255) / 256), 256, 0, st>>>(scratch, gx, K, (int)d, out_sums);
     count_launch();
     count_launch();

@@ -10,6 +10,7 @@ from metrics_b200.functional.regression.metrics import (  # noqa: F401
     r2_score,
     relative_squared_error,
     symmetric_mean_absolute_percentage_error,
+    tweedie_deviance_score,
     weighted_mean_absolute_percentage_error,
 )
 

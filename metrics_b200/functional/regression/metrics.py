@@ -271,3 +271,48 @@ def explained_variance(preds: Tensor, target: Tensor, multioutput: str = "unifor
     if multioutput not in ("raw_values", "uniform_average", "variance_weighted"):
         raise ValueError(f"Invalid input to argument `multioutput`. Choose one of the following: ('raw_values', 'uniform_average', 'variance_weighted')")
     return _explained_variance_compute(*_explained_variance_update(preds, target), multioutput)
+
+
+# ---- Tweedie deviance (tweedie_deviance.py:22-143) -------------------------------------------------------------------
+def _tweedie_power_check(power: float) -> None:
+    if 0 < power < 1:
+        raise ValueError(f"Deviance Score is not defined for power={power}.")
+
+
+def _tweedie_deviance_score_update(preds: Tensor, targets: Tensor, power: float = 0.0) -> tuple[Tensor, Tensor]:
+    """Sum of the per-element deviances and their count.  ONE kernel pass produces the sum together with the census of
+    out-of-domain elements the reference collects with up to two extra `torch.any` passes (:51, :59, :65-75); the census is
+    read back (one sync per update, as in the reference, whose `if torch.any(...)` syncs too) and turned into the same
+    ValueErrors.  Power 0 needs no domain check and is the plain squared-error sum."""
+    _check_same_shape(preds, targets)
+    _tweedie_power_check(power)
+    num_observations = torch.tensor(preds.numel(), device=preds.device)
+    if power == 0:
+        return _sums(preds, targets, _native.REG_MSE)[0, 0], num_observations
+    sums = _native.regression_sums(preds, targets, _native.REG_TWEEDIE, 1, float(power))[:, 0]
+    deviance, bad_preds, neg_targets, zero_targets = sums.tolist()
+    if power == 1:
+        if bad_preds or neg_targets:
+            raise ValueError(f"For power={power}, 'preds' has to be strictly positive and 'targets' cannot be negative.")
+    elif power == 2:
+        if bad_preds or neg_targets or zero_targets:
+            raise ValueError(f"For power={power}, both 'preds' and 'targets' have to be strictly positive.")
+    elif power < 0:
+        if bad_preds:
+            raise ValueError(f"For power={power}, 'preds' has to be strictly positive.")
+    elif 1 < power < 2:
+        if bad_preds or neg_targets:
+            raise ValueError(f"For power={power}, 'targets' has to be strictly positive and 'preds' cannot be negative.")
+    elif bad_preds or neg_targets or zero_targets:
+        raise ValueError(f"For power={power}, both 'preds' and 'targets' have to be strictly positive.")
+    return sums[0].to(_out_dtype(preds)), num_observations
+
+
+def _tweedie_deviance_score_compute(sum_deviance_score: Tensor, num_observations: Tensor) -> Tensor:
+    return sum_deviance_score / num_observations
+
+
+def tweedie_deviance_score(preds: Tensor, targets: Tensor, power: float = 0.0) -> Tensor:
+    """Mean Tweedie deviance: power 0 normal, 1 Poisson, (1, 2) compound Poisson-Gamma, 2 Gamma, 3 inverse Gaussian, < 0
+    extreme stable (reference :101-143)."""
+    return _tweedie_deviance_score_compute(*_tweedie_deviance_score_update(preds, targets, power))

@@ -10,5 +10,6 @@ from metrics_b200.regression.metrics import (  # noqa: F401
     R2Score,
     RelativeSquaredError,
     SymmetricMeanAbsolutePercentageError,
+    TweedieDevianceScore,
     WeightedMeanAbsolutePercentageError,
 )

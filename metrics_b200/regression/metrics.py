@@ -281,3 +281,28 @@ class ExplainedVariance(Metric):
         return F._explained_variance_compute(
             self.num_obs, self.sum_error, self.sum_squared_error, self.sum_target, self.sum_squared_target, self.multioutput
         )
+
+
+class TweedieDevianceScore(Metric):
+    """Mean Tweedie deviance of the given ``power`` (reference regression/tweedie_deviance.py:30-111): two ``sum`` states,
+    filled by one K9 pass per update (which also carries the domain check)."""
+
+    is_differentiable: bool = False  # kernel launches carry no autograd graph (reference: True)
+    higher_is_better: Optional[bool] = None
+    full_state_update: bool = False
+    plot_lower_bound: float = 0.0
+
+    def __init__(self, power: float = 0.0, **kwargs: Any) -> None:
+        super().__init__(**kwargs)
+        F._tweedie_power_check(power)
+        self.power: float = power
+        self.add_state("sum_deviance_score", torch.tensor(0.0), dist_reduce_fx="sum")
+        self.add_state("num_observations", torch.tensor(0), dist_reduce_fx="sum")
+
+    def update(self, preds: Tensor, targets: Tensor) -> None:
+        sum_deviance_score, num_observations = F._tweedie_deviance_score_update(preds, targets, self.power)
+        self.sum_deviance_score += sum_deviance_score
+        self.num_observations += num_observations
+
+    def compute(self) -> Tensor:
+        return F._tweedie_deviance_score_compute(self.sum_deviance_score, self.num_observations)

@@ -127,3 +127,10 @@ def cpu_kernel_standins(monkeypatch):
     for name, fn in module.standins().items():
         monkeypatch.setattr(_native, name, fn)
     return module
+
+
+@pytest.fixture(scope="session")
+def golden_tweedie():
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN_DIR, "tweedie.npz"), allow_pickle=False)

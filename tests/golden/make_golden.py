@@ -1168,6 +1168,50 @@ def fairness_golden() -> dict:
     return out
 
 
+def tweedie_golden() -> dict:
+    """Tweedie deviance (reference functional/regression/tweedie_deviance.py + regression/tweedie_deviance.py): the mean
+    deviance, the `(sum, count)` of `_tweedie_deviance_score_update`, the class after two updates, and per-element
+    deviances of a small batch (for the host harness of the kernel's term function)."""
+    from torchmetrics.functional.regression.tweedie_deviance import _tweedie_deviance_score_update, tweedie_deviance_score
+    from torchmetrics.regression.tweedie_deviance import TweedieDevianceScore
+
+    g = torch.Generator().manual_seed(4242)
+    out = {}
+    powers = [-1.5, 0.0, 1.0, 1.5, 2.0, 3.0]
+    out["powers"] = np.array(powers)
+    case = 0
+    for dtype in (torch.float32, torch.float64):
+        for shape in ((257,), (64, 3)):
+            preds = (torch.rand(shape, generator=g, dtype=torch.float64) * 4 + 0.05).to(dtype)
+            targets = (torch.rand(shape, generator=g, dtype=torch.float64) * 4 + 0.05).to(dtype)
+            targets_with_zeros = targets.clone()
+            targets_with_zeros.view(-1)[::7] = 0  # legal for powers 1 and (1, 2) only
+            for power in powers:
+                tg = targets_with_zeros if power in (1.0, 1.5) else targets
+                key = f"case{case}"
+                out[f"{key}/preds"], out[f"{key}/targets"] = preds.numpy(), tg.numpy()
+                out[f"{key}/power"] = np.array(power)
+                out[f"{key}/value"] = tweedie_deviance_score(preds, tg, power).numpy()
+                total, count = _tweedie_deviance_score_update(preds, tg, power)
+                out[f"{key}/sum"], out[f"{key}/count"] = total.numpy(), count.numpy()
+                metric = TweedieDevianceScore(power=power)
+                half = shape[0] // 2
+                metric.update(preds[:half], tg[:half])
+                metric.update(preds[half:], tg[half:])
+                out[f"{key}/class_value"] = metric.compute().numpy()
+                case += 1
+    out["n_cases"] = np.array(case)
+    # per-element deviances (float64) for the term-function harness: x = preds, y = targets
+    x = torch.tensor([0.3, 1.0, 2.5, 4.0, 0.75, 3.25], dtype=torch.float64)
+    y = torch.tensor([2.0, 1.0, 0.5, 0.0, 3.5, 3.25], dtype=torch.float64)
+    out["elem/preds"], out["elem/targets"] = x.numpy(), y.numpy()
+    for power in powers:
+        tg = y if power in (1.0, 1.5) else y.clamp(min=0.125)
+        per = torch.stack([_tweedie_deviance_score_update(x[i:i + 1], tg[i:i + 1], power)[0] for i in range(len(x))])
+        out[f"elem/p{power}/targets"], out[f"elem/p{power}/deviance"] = tg.numpy(), per.numpy()
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["classification"]
     if "classification" in which:
@@ -1228,5 +1272,10 @@ if __name__ == "__main__":
     if "fairness" in which:
         data = fairness_golden()
         path = os.path.join(HERE, "fairness.npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
+    if "tweedie" in which:
+        data = tweedie_golden()
+        path = os.path.join(HERE, "tweedie.npz")
         np.savez_compressed(path, **data)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")

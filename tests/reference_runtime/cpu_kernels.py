@@ -255,9 +255,18 @@ def regression_sums(preds, target, op, num_outputs=1, param=0.0, eps=0.0) -> Ten
     elif op == 8:
         r = t - p
         terms = [t * t, t, r * r]
-    else:
+    elif op == 9:
         r = t - p
         terms = [r, r * r, t, t * t]
+    else:  # 10: Tweedie deviance of power `param` + the domain census
+        if param == 1:
+            dev = 2 * (torch.where(t == 0, torch.zeros_like(t), t * torch.log(t / p)) + p - t)
+        elif param == 2:
+            dev = 2 * (torch.log(p / t) + t / p - 1)
+        else:
+            a, b = 1 - param, 2 - param
+            dev = 2 * (t.clamp(min=0) ** b / (a * b) - t * p**a / a + p**b / b)
+        terms = [dev, (p <= 0).to(p.dtype), (t < 0).to(p.dtype), (t == 0).to(p.dtype)]
     return torch.stack([x.double().sum(0) for x in terms])
 
 
