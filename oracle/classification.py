@@ -159,3 +159,30 @@ def multilabel_stat_scores(preds, target, num_labels: int, threshold: float = 0.
 def confmat_from_counts(tp, fp, tn, fn) -> np.ndarray:
     """[[tn, fp], [fn, tp]] — what bincount(2*target + preds, 4).reshape(2, 2) yields (confusion_matrix.py:148-152, 511-516)."""
     return np.stack([np.stack([tn, fp], -1), np.stack([fn, tp], -1)], -2).astype(np.int64)
+
+
+def binary_groups_stat_scores(preds, target, groups, threshold: float = 0.5, ignore_index: Optional[int] = None) -> np.ndarray:
+    """_binary_groups_stat_scores (group_fairness.py:52-83): sort the samples by group id, split at the id changes, binary
+    stat scores per piece.  Returns ``[G, 4]`` (tp, fp, tn, fn) for the G ids present, ascending."""
+    if np.issubdtype(preds.dtype, np.floating):
+        preds = _sigmoid_if_logits(preds) > threshold  # the vote is taken over the WHOLE batch, before the split (:66)
+    preds = preds.reshape(preds.shape[0], -1)
+    target = target.reshape(target.shape[0], -1)
+    ids = groups.reshape(-1)
+    out = []
+    for gid in np.unique(ids):
+        sel = ids == gid
+        out.append(np.array([int(np.sum(x)) for x in binary_stat_scores(preds[sel].astype(np.int64), target[sel], threshold, ignore_index)]))
+    return np.stack(out)
+
+
+def fairness_ratios(counts: np.ndarray) -> dict:
+    """_compute_binary_demographic_parity / _equal_opportunity (group_fairness.py:164-174, :243-255) in float32 like the
+    reference's `_safe_divide`: lowest over highest positive rate / true-positive rate, keyed by the two group indices."""
+    tp, fp, tn, fn = (counts[:, i].astype(np.float32) for i in range(4))
+    out = {}
+    for tag, rates in (("DP", _safe_divide_f32(tp + fp, tp + fp + tn + fn)), ("EO", _safe_divide_f32(tp, tp + fn))):
+        lo, hi = int(np.argmin(rates)), int(np.argmax(rates))
+        out[f"{tag}_{lo}_{hi}"] = _safe_divide_f32(rates[lo], rates[hi])
+    return out
+

@@ -83,3 +83,20 @@ def explained_variance(p, t, multioutput="uniform_average"):  # explained_varian
     if multioutput == "uniform_average":
         return np.mean(s)
     return (den / den.sum() * s).sum()
+
+
+def tweedie_deviance_score(p, t, power=0.0):  # tweedie_deviance.py:22-143 (domain checks omitted: valid inputs only)
+    p, t = p.astype(np.float64).reshape(-1), t.astype(np.float64).reshape(-1)
+    if power == 0:
+        dev = (t - p) ** 2
+    elif power == 1:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            xlogy = np.where(t == 0, 0.0, t * np.log(t / p))  # _safe_xlogy, utilities/compute.py:32-44
+        dev = 2 * (xlogy + p - t)
+    elif power == 2:
+        dev = 2 * (np.log(p / t) + t / p - 1)
+    else:
+        dev = 2 * (np.maximum(t, 0) ** (2 - power) / ((1 - power) * (2 - power)) - t * p ** (1 - power) / (1 - power)
+                   + p ** (2 - power) / (2 - power))
+    return dev.sum() / dev.size
+

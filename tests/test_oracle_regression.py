@@ -27,3 +27,11 @@ def test_regression_functionals(golden_reg):
         np.testing.assert_allclose(orr.explained_variance(p2, t2, mo), g[f"reg/ev_{mo}"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(orr.relative_squared_error(p2, t2), g["reg/rse"], rtol=1e-5)
     np.testing.assert_allclose(orr.relative_squared_error(p2, t2, squared=False), g["reg/rrse"], rtol=1e-5)
+
+
+def test_tweedie_deviance(golden_tweedie):
+    g = golden_tweedie
+    for c in range(int(g["n_cases"])):
+        p, t, power = g[f"case{c}/preds"], g[f"case{c}/targets"], float(g[f"case{c}/power"])
+        tol = dict(rtol=3e-6) if p.dtype == np.float32 else dict(rtol=1e-12)
+        np.testing.assert_allclose(orr.tweedie_deviance_score(p, t, power), g[f"case{c}/value"], err_msg=f"case {c}", **tol)
