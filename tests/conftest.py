@@ -134,3 +134,10 @@ def golden_tweedie():
     import numpy as np
 
     return np.load(os.path.join(GOLDEN_DIR, "tweedie.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_fuzz2():
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN_DIR, "fuzz2.npz"), allow_pickle=False)

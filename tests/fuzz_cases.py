@@ -12,8 +12,8 @@ _DT = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfl
        "int64": torch.int64}
 
 
-def n_cases() -> int:
-    path = os.path.join(os.path.dirname(__file__), "golden", "fuzz.npz")
+def n_cases(name: str = "fuzz") -> int:
+    path = os.path.join(os.path.dirname(__file__), "golden", f"{name}.npz")
     return int(np.load(path)["n_cases"])
 
 

@@ -712,7 +712,7 @@ def consumers_golden() -> dict:
     return out
 
 
-def fuzz_golden() -> dict:
+def fuzz_golden(seed: int = 2026, mult: int = 1) -> dict:
     """Randomised differential cases: random shapes / dtypes / ignore_index / averages through the reference's
     functionals.  Each case k stores `k/spec` (JSON: functional name + kwargs), `k/preds`, `k/target` and `k/out*`."""
     import json
@@ -724,8 +724,8 @@ def fuzz_golden() -> dict:
     FR_holder = [_FR]
     warnings.simplefilter("ignore")
     out: dict = {}
-    rng = np.random.default_rng(2026)
-    g = torch.Generator().manual_seed(2026)
+    rng = np.random.default_rng(seed)
+    g = torch.Generator().manual_seed(seed)
     k = 0
 
     def emit(name, kwargs, preds, target):
@@ -754,7 +754,7 @@ def fuzz_golden() -> dict:
         return xs[int(rng.integers(len(xs)))]
 
     # ---- multiclass: confusion matrix / stat scores / accuracy / f1 / precision / jaccard -------------------------------
-    for _ in range(36):
+    for _ in range(36 * mult):
         C = int(pick(2, 3, 5, 9, 17))
         N = int(pick(1, 7, 64, 257))
         extra = pick((), (), (3,), (2, 2))
@@ -792,7 +792,7 @@ def fuzz_golden() -> dict:
                 kw["multidim_average"] = "samplewise"
         emit(fn, kw, preds, target)
     # ---- binary / multilabel counts ----------------------------------------------------------------------------------------
-    for _ in range(24):
+    for _ in range(24 * mult):
         ml = rng.random() < 0.5
         L = int(pick(2, 3, 6))
         N = int(pick(1, 9, 130))
@@ -827,7 +827,7 @@ def fuzz_golden() -> dict:
                 kw["multidim_average"] = "samplewise"
         emit(fn, kw, preds, target)
     # ---- curves ---------------------------------------------------------------------------------------------------------------
-    for _ in range(30):
+    for _ in range(30 * mult):
         task = pick("binary", "multiclass", "multilabel")
         N = int(pick(2, 33, 400, 1500))
         ig = pick(None, None, -1)
@@ -870,7 +870,7 @@ def fuzz_golden() -> dict:
         kw.update({"thresholds": thresholds, "ignore_index": ig})
         emit(fn, kw, preds, target)
     # ---- exact match (multiclass / multilabel, extra dims, samplewise, ignore_index) ---------------------------------------------
-    for _ in range(16):
+    for _ in range(16 * mult):
         N, P = int(pick(1, 5, 40)), int(pick(1, 3, 6))
         ig = pick(None, None, -1)
         mda = pick("global", "samplewise")
@@ -900,7 +900,7 @@ def fuzz_golden() -> dict:
     # ---- regression ------------------------------------------------------------------------------------------------------------
     import torchmetrics.functional.regression as FR
 
-    for _ in range(26):
+    for _ in range(26 * mult):
         fn = pick("mean_squared_error", "mean_absolute_error", "mean_absolute_percentage_error",
                   "symmetric_mean_absolute_percentage_error", "weighted_mean_absolute_percentage_error",
                   "mean_squared_log_error", "log_cosh_error", "minkowski_distance", "r2_score", "relative_squared_error",
@@ -1277,5 +1277,10 @@ if __name__ == "__main__":
     if "tweedie" in which:
         data = tweedie_golden()
         path = os.path.join(HERE, "tweedie.npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
+    if "fuzz2" in which:  # a second, larger draw (other seed): replayed by the CPU host twin and by the LAST GPU test file
+        data = fuzz_golden(seed=77077, mult=3)
+        path = os.path.join(HERE, "fuzz2.npz")
         np.savez_compressed(path, **data)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")

@@ -9,3 +9,9 @@ from tests.fuzz_cases import n_cases, run_case
 @pytest.mark.parametrize("k", range(n_cases()))
 def test_case(golden_fuzz, cpu_kernel_standins, k):
     run_case(golden_fuzz, k, "cpu")
+
+
+@pytest.mark.parametrize("k", range(n_cases("fuzz2")))
+def test_second_draw(golden_fuzz2, cpu_kernel_standins, k):
+    """A second, three times larger draw with another seed (make_golden.py fuzz2)."""
+    run_case(golden_fuzz2, k, "cpu")
