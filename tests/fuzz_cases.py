@@ -48,7 +48,7 @@ def run_case(g, k: int, DEV: str) -> None:
         exp = g[f"{k}/out{i}"]
         t = t.float() if t.dtype in (torch.float16, torch.bfloat16) else t
         arr = t.cpu().numpy()
-        assert arr.shape == exp.shape, (fn, kwargs, i, arr.shape, exp.shape)
+        assert arr.shape == exp.shape, f"shape mismatch {fn} {kwargs} out{i}: {arr.shape} vs {exp.shape}"
         if np.issubdtype(exp.dtype, np.integer) or exp.dtype == np.bool_:
             np.testing.assert_array_equal(arr, exp, err_msg=f"{fn} {kwargs} out{i}")
         else:
