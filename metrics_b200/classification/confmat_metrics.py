@@ -108,7 +108,7 @@ class JaccardIndex(_ClassificationTaskWrapper):
 class BinaryCohenKappa(_Score01, BinaryConfusionMatrix):
     """Reference cohen_kappa.py:36-158."""
 
-    plot_lower_bound: float = -1.0
+    plot_lower_bound: float = 0.0  # as declared by the reference (the score itself can be negative)
 
     def __init__(self, threshold: float = 0.5, ignore_index: Optional[int] = None,
                  weights: Optional[Literal["linear", "quadratic", "none"]] = None, validate_args: bool = True,
@@ -125,7 +125,7 @@ class BinaryCohenKappa(_Score01, BinaryConfusionMatrix):
 class MulticlassCohenKappa(_Score01, MulticlassConfusionMatrix):
     """Reference cohen_kappa.py:161-287."""
 
-    plot_lower_bound: float = -1.0
+    plot_lower_bound: float = 0.0  # as declared by the reference (the score itself can be negative)
     plot_legend_name: str = "Class"
 
     def __init__(self, num_classes: int, ignore_index: Optional[int] = None,
@@ -159,7 +159,7 @@ class CohenKappa(_ClassificationTaskWrapper):
 class BinaryMatthewsCorrCoef(_Score01, BinaryConfusionMatrix):
     """Reference matthews_corrcoef.py:40-145."""
 
-    plot_lower_bound: float = -1.0
+    plot_lower_bound: float = 0.0  # as declared by the reference (the score itself can be negative)
 
     def __init__(self, threshold: float = 0.5, ignore_index: Optional[int] = None, validate_args: bool = True,
                  **kwargs: Any) -> None:
@@ -172,7 +172,7 @@ class BinaryMatthewsCorrCoef(_Score01, BinaryConfusionMatrix):
 class MulticlassMatthewsCorrCoef(_Score01, MulticlassConfusionMatrix):
     """Reference matthews_corrcoef.py:148-257."""
 
-    plot_lower_bound: float = -1.0
+    plot_lower_bound: float = 0.0  # as declared by the reference (the score itself can be negative)
     plot_legend_name: str = "Class"
 
     def __init__(self, num_classes: int, ignore_index: Optional[int] = None, validate_args: bool = True,
@@ -186,7 +186,7 @@ class MulticlassMatthewsCorrCoef(_Score01, MulticlassConfusionMatrix):
 class MultilabelMatthewsCorrCoef(_Score01, MultilabelConfusionMatrix):
     """Reference matthews_corrcoef.py:260-368."""
 
-    plot_lower_bound: float = -1.0
+    plot_lower_bound: float = 0.0  # as declared by the reference (the score itself can be negative)
     plot_legend_name: str = "Label"
 
     def __init__(self, num_labels: int, threshold: float = 0.5, ignore_index: Optional[int] = None,

@@ -57,6 +57,8 @@ class _ExactMatchBase(Metric):
 class MulticlassExactMatch(_ExactMatchBase):
     """Reference :45-197."""
 
+    plot_legend_name: str = "Class"
+
     def __init__(self, num_classes: int, multidim_average: Literal["global", "samplewise"] = "global",
                  ignore_index: Optional[int] = None, validate_args: bool = True, **kwargs: Any) -> None:
         super().__init__(**kwargs)
@@ -80,6 +82,8 @@ class MulticlassExactMatch(_ExactMatchBase):
 
 class MultilabelExactMatch(_ExactMatchBase):
     """Reference :200-366."""
+
+    plot_legend_name: str = "Label"
 
     def __init__(self, num_labels: int, threshold: float = 0.5,
                  multidim_average: Literal["global", "samplewise"] = "global", ignore_index: Optional[int] = None,

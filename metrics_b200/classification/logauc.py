@@ -20,7 +20,7 @@ class BinaryLogAUC(BinaryROC):
     """Reference :35-159."""
 
     is_differentiable: bool = False
-    higher_is_better: Optional[bool] = None
+    higher_is_better: Optional[bool] = True
     full_state_update: bool = False
     plot_lower_bound: float = 0.0
     plot_upper_bound: float = 1.0
@@ -41,7 +41,7 @@ class MulticlassLogAUC(MulticlassROC):
     """Reference :162-309.  The per-class averaging mode is kept in ``average2`` (``average`` belongs to the ROC base)."""
 
     is_differentiable: bool = False
-    higher_is_better: Optional[bool] = None
+    higher_is_better: Optional[bool] = True
     full_state_update: bool = False
     plot_lower_bound: float = 0.0
     plot_upper_bound: float = 1.0
@@ -66,7 +66,7 @@ class MultilabelLogAUC(MultilabelROC):
     """Reference :312-459."""
 
     is_differentiable: bool = False
-    higher_is_better: Optional[bool] = None
+    higher_is_better: Optional[bool] = True
     full_state_update: bool = False
     plot_lower_bound: float = 0.0
     plot_upper_bound: float = 1.0

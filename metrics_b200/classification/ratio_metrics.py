@@ -28,7 +28,8 @@ _CLASS_ZERO_DIVISION = {"precision", "recall"}
 
 
 def _family(kind: str):
-    higher = kind != "hamming_distance"
+    # `higher_is_better` as the reference declares it (None for specificity / NPV: specificity.py:99, negative_predictive_value.py:99)
+    higher = {"hamming_distance": False, "specificity": None, "negative_predictive_value": None}.get(kind, True)
     stem = _CLASS_STEM[kind]
     attrs = {
         "is_differentiable": False,

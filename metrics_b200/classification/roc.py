@@ -14,6 +14,9 @@ from metrics_b200.functional.classification.roc import _binary_roc_compute, _mul
 class BinaryROC(BinaryPrecisionRecallCurve):
     """Reference :44-165."""
 
+    plot_lower_bound: float = 0.0
+    plot_upper_bound: float = 1.0
+
     def compute(self) -> tuple[Tensor, Tensor, Tensor]:
         return _binary_roc_compute(self._state(), self.thresholds)
 
@@ -21,12 +24,20 @@ class BinaryROC(BinaryPrecisionRecallCurve):
 class MulticlassROC(MulticlassPrecisionRecallCurve):
     """Reference :168-330."""
 
+    plot_lower_bound: float = 0.0
+    plot_upper_bound: float = 1.0
+    plot_legend_name: str = "Class"
+
     def compute(self):
         return _multiclass_roc_compute(self._state(), self.num_classes, self.thresholds, self.average)
 
 
 class MultilabelROC(MultilabelPrecisionRecallCurve):
     """Reference :333-497."""
+
+    plot_lower_bound: float = 0.0
+    plot_upper_bound: float = 1.0
+    plot_legend_name: str = "Label"
 
     def compute(self):
         return _multilabel_roc_compute(self._state(), self.num_labels, self.thresholds, self.ignore_index)

@@ -193,7 +193,6 @@ class R2Score(Metric):
     is_differentiable: bool = False  # kernel launches carry no autograd graph (reference: True)
     higher_is_better: bool = True
     full_state_update: bool = False
-    plot_lower_bound: float = 0.0
     plot_upper_bound: float = 1.0
 
     def __init__(self, adjusted: int = 0, multioutput: str = "uniform_average", **kwargs: Any) -> None:
