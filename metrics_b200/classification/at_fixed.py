@@ -15,6 +15,7 @@ from metrics_b200.classification.precision_recall_curve import (
     MultilabelPrecisionRecallCurve,
 )
 from metrics_b200.functional.classification.at_fixed import (
+    _publish_signature,
     _FAMILIES,
     _binary_at_fixed_compute,
     _floor_validation,
@@ -84,6 +85,8 @@ def _family(kind: str):
                                             getattr(self, fam.arg))
 
     doc = f"{kind.replace('_', ' ')} (reference classification/{fam.reference}); first positional argument after the task size is `{fam.arg}`."
+    for init in (b_init, mc_init, ml_init):
+        _publish_signature(init, fam.arg)
     b = type(f"Binary{stem}", (BinaryPrecisionRecallCurve,), {**attrs, "__init__": b_init, "compute": b_compute, "__doc__": "Binary " + doc})
     mc = type(f"Multiclass{stem}", (MulticlassPrecisionRecallCurve,),
               {**attrs, "plot_legend_name": "Class", "__init__": mc_init, "compute": mc_compute, "__doc__": "Multiclass " + doc})
@@ -107,6 +110,7 @@ def _family(kind: str):
             raise ValueError(f"`num_labels` is expected to be `int` but `{type(num_labels)} was passed.`")
         return ml(num_labels, floor, **kwargs)
 
+    _publish_signature(__new__, fam.arg)
     wrapper = type(stem, (_ClassificationTaskWrapper,), {"__new__": __new__, "__module__": __name__,
                                                          "__doc__": f"Task wrapper for {kind.replace('_', ' ')}."})
     return b, mc, ml, wrapper

@@ -91,18 +91,18 @@ class LogAUC(_ClassificationTaskWrapper):
     """Task wrapper (reference :462-528)."""
 
     def __new__(cls, task: Literal["binary", "multiclass", "multilabel"], thresholds: _Thr = None,  # type: ignore[misc]
-                num_classes: Optional[int] = None, num_labels: Optional[int] = None,
-                fpr_range: Tuple[float, float] = (0.001, 0.1), average: Optional[Literal["macro", "none"]] = None,
-                ignore_index: Optional[int] = None, validate_args: bool = True, **kwargs: Any) -> Metric:
+                fpr_range: Tuple[float, float] = (0.001, 0.1), num_classes: Optional[int] = None,
+                num_labels: Optional[int] = None, ignore_index: Optional[int] = None, validate_args: bool = True,
+                **kwargs: Any) -> Metric:
         task = ClassificationTask.from_str(task)
-        kwargs.update({"fpr_range": fpr_range, "thresholds": thresholds, "ignore_index": ignore_index,
+        kwargs.update({"thresholds": thresholds, "fpr_range": fpr_range, "ignore_index": ignore_index,
                        "validate_args": validate_args})
         if task == ClassificationTask.BINARY:
             return BinaryLogAUC(**kwargs)
         if task == ClassificationTask.MULTICLASS:
             if not isinstance(num_classes, int):
                 raise ValueError(f"`num_classes` is expected to be `int` but `{type(num_classes)} was passed.`")
-            return MulticlassLogAUC(num_classes, average=average, **kwargs)
+            return MulticlassLogAUC(num_classes, **kwargs)  # `average`, if any, travels in kwargs like in the reference
         if not isinstance(num_labels, int):
             raise ValueError(f"`num_labels` is expected to be `int` but `{type(num_labels)} was passed.`")
-        return MultilabelLogAUC(num_labels, average=average, **kwargs)
+        return MultilabelLogAUC(num_labels, **kwargs)

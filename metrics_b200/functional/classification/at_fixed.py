@@ -159,6 +159,23 @@ def _multilabel_at_fixed_compute(kind: str, state, num_labels: int, thresholds: 
     return _per_curve(fam, a, b, t, floor, isinstance(state, Tensor))
 
 
+def _publish_signature(fn: Callable, arg: str) -> Callable:
+    """Introspection parity: present the shared `floor` parameter under the family's own name (`min_precision`, ...), as a
+    required argument and without the catch-all that implements it, so `inspect.signature` shows the reference's signature."""
+    import inspect
+
+    params = []
+    for prm in inspect.signature(fn).parameters.values():
+        if prm.name == "floor":
+            params.append(prm.replace(name=arg, default=inspect.Parameter.empty, annotation=float))
+        elif prm.kind is inspect.Parameter.VAR_KEYWORD and prm.name == "named":
+            continue
+        else:
+            params.append(prm)
+    fn.__signature__ = inspect.Signature(params)
+    return fn
+
+
 def _make_binary(kind: str) -> Callable:
     fam = _FAMILIES[kind]
 
@@ -176,7 +193,7 @@ def _make_binary(kind: str) -> Callable:
 
     fn_.__name__ = fn_.__qualname__ = f"binary_{kind}"
     fn_.__doc__ = f"Binary {kind.replace('_', ' ')} (reference functional/classification/{fam.reference}); `floor` = `{fam.arg}`."
-    return fn_
+    return _publish_signature(fn_, fam.arg)
 
 
 def _make_multiclass(kind: str) -> Callable:
@@ -196,7 +213,7 @@ def _make_multiclass(kind: str) -> Callable:
 
     fn_.__name__ = fn_.__qualname__ = f"multiclass_{kind}"
     fn_.__doc__ = f"Multiclass one-vs-rest {kind.replace('_', ' ')} (reference {fam.reference}); `floor` = `{fam.arg}`."
-    return fn_
+    return _publish_signature(fn_, fam.arg)
 
 
 def _make_multilabel(kind: str) -> Callable:
@@ -216,7 +233,7 @@ def _make_multilabel(kind: str) -> Callable:
 
     fn_.__name__ = fn_.__qualname__ = f"multilabel_{kind}"
     fn_.__doc__ = f"Multilabel per-label {kind.replace('_', ' ')} (reference {fam.reference}); `floor` = `{fam.arg}`."
-    return fn_
+    return _publish_signature(fn_, fam.arg)
 
 
 binary_recall_at_fixed_precision = _make_binary("recall_at_fixed_precision")
@@ -250,7 +267,7 @@ def _make_task(kind: str, b: Callable, mc: Callable, ml: Callable) -> Callable:
 
     fn_.__name__ = fn_.__qualname__ = kind
     fn_.__doc__ = f"Task wrapper for {kind.replace('_', ' ')} (reference {fam.reference}); `floor` = `{fam.arg}`."
-    return fn_
+    return _publish_signature(fn_, fam.arg)
 
 
 recall_at_fixed_precision = _make_task("recall_at_fixed_precision", binary_recall_at_fixed_precision,

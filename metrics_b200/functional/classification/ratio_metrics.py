@@ -87,6 +87,17 @@ def _ratio_reduce(
     return _adjust_weights_safe_divide(score, average, multilabel, tp, fp, fn)
 
 
+def _publish(fn: Callable, spec: _Ratio) -> Callable:
+    """Introspection parity: the families without a `zero_division` argument in the reference (specificity, Hamming
+    distance) do not list the shared implementation's one in `inspect.signature`."""
+    if not spec.uses_zero_division:
+        import inspect
+
+        sig = inspect.signature(fn)
+        fn.__signature__ = sig.replace(parameters=[p for p in sig.parameters.values() if p.name != "zero_division"])
+    return fn
+
+
 def _make_binary(kind: str) -> Callable:
     spec = _RATIOS[kind]
 
@@ -101,7 +112,7 @@ def _make_binary(kind: str) -> Callable:
 
     fn_.__name__ = fn_.__qualname__ = f"binary_{kind}"
     fn_.__doc__ = f"Binary {kind.replace('_', ' ')} from ONE counting kernel (reference functional/classification/{spec.reference})."
-    return fn_
+    return _publish(fn_, spec)
 
 
 def _make_multiclass(kind: str) -> Callable:
@@ -120,7 +131,7 @@ def _make_multiclass(kind: str) -> Callable:
 
     fn_.__name__ = fn_.__qualname__ = f"multiclass_{kind}"
     fn_.__doc__ = f"Multiclass {kind.replace('_', ' ')} from the fused argmax + counters kernel (reference {spec.reference})."
-    return fn_
+    return _publish(fn_, spec)
 
 
 def _make_multilabel(kind: str) -> Callable:
@@ -139,7 +150,7 @@ def _make_multilabel(kind: str) -> Callable:
 
     fn_.__name__ = fn_.__qualname__ = f"multilabel_{kind}"
     fn_.__doc__ = f"Multilabel {kind.replace('_', ' ')} from ONE counting kernel (reference {spec.reference})."
-    return fn_
+    return _publish(fn_, spec)
 
 
 def _make_task(kind: str, b: Callable, mc: Callable, ml: Callable) -> Callable:
@@ -165,7 +176,7 @@ def _make_task(kind: str, b: Callable, mc: Callable, ml: Callable) -> Callable:
 
     fn_.__name__ = fn_.__qualname__ = kind
     fn_.__doc__ = f"Task wrapper for {kind.replace('_', ' ')}."
-    return fn_
+    return _publish(fn_, _RATIOS[kind])
 
 
 binary_precision, multiclass_precision, multilabel_precision = (

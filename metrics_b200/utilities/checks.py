@@ -58,7 +58,7 @@ def is_overridden(method_name: str, instance: object, parent: object) -> bool:
     return own.__code__ is not inherited.__code__
 
 
-def check_forward_full_state_property(metric_class, init_args=None, input_args=None, num_update_to_compare=(10, 100, 1000),
+def check_forward_full_state_property(metric_class, init_args=None, input_args=None, num_update_to_compare=[10, 100, 1000],  # noqa: B006 (read only; the reference's default)
                                       reps: int = 5) -> None:
     """Tell whether ``full_state_update = False`` is safe for ``metric_class`` and whether it is faster
     (reference checks.py:635-737): run ``forward`` both ways on the same inputs, compare every batch value and the final

@@ -1,0 +1,56 @@
+"""Dump the public call signatures and class metadata of the REFERENCE (build container only) to tests/golden/api_surface.json:
+for every class / function of the in-scope sub-packages the parameter names + defaults of `__init__` / `__new__`, `update`,
+`compute`, and `higher_is_better` / `is_differentiable` / `full_state_update` / plot bounds.  tests/test_api_surface.py holds
+this package to it.  Usage: python tests/golden/make_signatures.py"""
+import importlib
+import inspect
+import json
+import os
+import sys
+import warnings
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SUBPACKAGES = ("classification", "regression", "detection", "wrappers", "functional.classification", "functional.regression",
+               "utilities.data", "utilities.compute", "utilities.distributed", "utilities.checks")
+ATTRS = ("higher_is_better", "is_differentiable", "full_state_update", "plot_lower_bound", "plot_upper_bound", "plot_legend_name")
+
+
+def signature(fn):
+    try:
+        sig = inspect.signature(fn)
+    except (TypeError, ValueError):
+        return None
+    return [[n, "<required>" if p.default is inspect.Parameter.empty else repr(p.default)] for n, p in sig.parameters.items()
+            if n != "self"]
+
+
+def surface(pkg: str) -> dict:
+    out = {}
+    for sub in SUBPACKAGES:
+        try:
+            module = importlib.import_module(f"{pkg}.{sub}")
+        except ImportError:
+            continue
+        for name in dir(module):
+            obj = getattr(module, name)
+            if name.startswith("__") or not getattr(obj, "__module__", "").startswith(pkg):
+                continue
+            key = f"{sub}.{name}"
+            if isinstance(obj, type):
+                out[key] = {"init": signature(obj.__new__ if "__new__" in obj.__dict__ else obj.__init__),
+                            "update": signature(obj.update) if hasattr(obj, "update") else None,
+                            "compute": signature(obj.compute) if hasattr(obj, "compute") else None,
+                            "attrs": {a: repr(getattr(obj, a, None)) for a in ATTRS}}
+            elif inspect.isfunction(obj):
+                out[key] = {"call": signature(obj)}
+    return out
+
+
+if __name__ == "__main__":
+    warnings.simplefilter("ignore")
+    sys.path.insert(0, os.path.join(HERE, "_standins"))
+    sys.path.insert(0, "/root/reference/src")
+    data = surface("torchmetrics")
+    with open(os.path.join(HERE, "api_surface.json"), "w") as fh:
+        json.dump(data, fh, indent=0, sort_keys=True)
+    print("wrote api_surface.json:", len(data), "entries")
