@@ -230,21 +230,24 @@ class RelativeSquaredError(Metric):
     def __init__(self, num_outputs: int = 1, squared: bool = True, **kwargs: Any) -> None:
         super().__init__(**kwargs)
         self.num_outputs = num_outputs
-        self.add_state("sum_squared_obs", default=torch.zeros(num_outputs), dist_reduce_fx="sum")
-        self.add_state("sum_obs", default=torch.zeros(num_outputs), dist_reduce_fx="sum")
+        # state names as in the reference (rse.py:84-87), whose checkpoints must load: `sum_squared_error` holds the sum of
+        # squared TARGETS and `sum_error` the sum of targets (they receive `_r2_score_update`'s first two outputs, :93-96);
+        # the residual sum of squares is `residual`
         self.add_state("sum_squared_error", default=torch.zeros(num_outputs), dist_reduce_fx="sum")
+        self.add_state("sum_error", default=torch.zeros(num_outputs), dist_reduce_fx="sum")
+        self.add_state("residual", default=torch.zeros(num_outputs), dist_reduce_fx="sum")
         self.add_state("total", default=tensor(0), dist_reduce_fx="sum")
         self.squared = squared
 
     def update(self, preds: Tensor, target: Tensor) -> None:
-        sso, so, rss, n = F._r2_score_update(preds, target)
-        self.sum_squared_obs += sso
-        self.sum_obs += so
-        self.sum_squared_error += rss
+        sum_squared_obs, sum_obs, rss, n = F._r2_score_update(preds, target)
+        self.sum_squared_error += sum_squared_obs
+        self.sum_error += sum_obs
+        self.residual += rss
         self.total += n
 
     def compute(self) -> Tensor:
-        return F._relative_squared_error_compute(self.sum_squared_obs, self.sum_obs, self.sum_squared_error, self.total, self.squared)
+        return F._relative_squared_error_compute(self.sum_squared_error, self.sum_error, self.residual, self.total, self.squared)
 
 
 class ExplainedVariance(Metric):

@@ -46,6 +46,48 @@ def surface(pkg: str) -> dict:
     return out
 
 
+def state_registry(pkg: str) -> dict:
+    """{"Class[variant]": {state: {default shape/dtype or "list", reduce fn name, persistent}}} for every in-scope metric class
+    that can be built from a small table of constructor arguments — what `state_dict()` keys and cross-rank reductions are."""
+    import torch
+
+    def describe(metric) -> dict:
+        return {k: {"default": "list" if isinstance(v, list) else [list(v.shape), str(v.dtype)],
+                    "reduce": getattr(metric._reductions[k], "__name__", None) if metric._reductions[k] is not None else None,
+                    "persistent": metric._persistent[k]} for k, v in metric._defaults.items()}
+
+    out = {}
+    cls_pkg, reg_pkg = importlib.import_module(f"{pkg}.classification"), importlib.import_module(f"{pkg}.regression")
+    floors = ("AtFixed", "SensitivityAt", "SpecificityAt")
+    for name in sorted(dir(cls_pkg)):
+        cls = getattr(cls_pkg, name)
+        prefix = next((p for p in ("Binary", "Multiclass", "Multilabel") if name.startswith(p)), None)
+        if not isinstance(cls, type) or prefix is None:
+            continue
+        for variant, extra in (("default", {}), ("thresholds", {"thresholds": 7}), ("samplewise", {"multidim_average": "samplewise"}),
+                               ("micro", {"average": "micro"})):
+            args = () if prefix == "Binary" else (3,)
+            if "FBeta" in name:
+                args = (2.0, *args)
+            if any(f in name for f in floors):
+                args = (*args, 0.5)
+            if name in ("BinaryFairness", "BinaryGroupStatRates"):
+                args = (2,)
+            try:
+                out[f"{name}[{variant}]"] = describe(cls(*args, **extra))
+            except Exception:  # this variant's keyword does not exist for this class
+                continue
+    for name in sorted(dir(reg_pkg)):
+        cls = getattr(reg_pkg, name)
+        if isinstance(cls, type) and issubclass(cls, torch.nn.Module):
+            for variant, extra in (("default", {}), ("multi", {"num_outputs": 3})):
+                try:
+                    out[f"{name}[{variant}]"] = describe(cls(p=2.0, **extra) if name == "MinkowskiDistance" else cls(**extra))
+                except Exception:
+                    continue
+    return out
+
+
 if __name__ == "__main__":
     warnings.simplefilter("ignore")
     sys.path.insert(0, os.path.join(HERE, "_standins"))
@@ -54,3 +96,7 @@ if __name__ == "__main__":
     with open(os.path.join(HERE, "api_surface.json"), "w") as fh:
         json.dump(data, fh, indent=0, sort_keys=True)
     print("wrote api_surface.json:", len(data), "entries")
+    states = state_registry("torchmetrics")
+    with open(os.path.join(HERE, "state_registry.json"), "w") as fh:
+        json.dump(states, fh, indent=0, sort_keys=True)
+    print("wrote state_registry.json:", len(states), "metric configurations")

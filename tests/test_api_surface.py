@@ -60,3 +60,21 @@ def test_every_in_scope_name_of_the_reference_exists_here():
     )
     missing = sorted(k for k in ref if k not in mine and not any(tok in k for tok in out_of_scope))
     assert not missing, missing
+
+
+def test_state_registries_match_the_reference():
+    """State names, default shapes / dtypes, `dist_reduce_fx` and persistence of every shared metric configuration: a
+    `state_dict()` written by the reference must load here and the cross-rank reductions must be the same."""
+    import warnings
+
+    spec = importlib.util.spec_from_file_location("make_signatures", os.path.join(GOLDEN_DIR, "make_signatures.py"))
+    module = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(module)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mine = module.state_registry("metrics_b200")
+    ref = json.load(open(os.path.join(GOLDEN_DIR, "state_registry.json")))
+    shared = sorted(set(ref) & set(mine))
+    assert len(shared) >= 165, len(shared)
+    different = {k: (ref[k], mine[k]) for k in shared if ref[k] != mine[k]}
+    assert not different, different
