@@ -26,7 +26,7 @@ IN_SCOPE = {
     "regression": ["explained_variance", "log_cosh", "log_mse", "mae", "mape", "minkowski", "mse", "r2", "rse",
                    "symmetric_mape", "tweedie_deviance", "wmape"],
     "wrappers": ["classwise"],
-    "utilities": ["data", "compute", "distributed"],
+    "utilities": ["data", "compute", "distributed", "enums"],
     "detection": ["mean_ap"],
 }
 IN_SCOPE["functional/classification"] = IN_SCOPE["classification"]
