@@ -110,21 +110,12 @@ class MulticlassStatScores(_AbstractStatScores):
         )
 
     def _update_unknown_class_count(self, preds: Tensor, target: Tensor) -> None:
-        """``num_classes=None`` (only legal with ``average="micro"``, reference :238-241): the micro counters do not need
-        the class count except for ``tn``, for which the reference substitutes 1 (:343, :434), i.e. ``tn = -fp``.  The
-        kernel's range check needs a bound, so it is read from the batch — one device sync, on this corner only."""
+        """``num_classes=None`` with ``average="micro"`` (functional/classification/stat_scores.py::_class_count_bound)."""
         if self.multidim_average == "samplewise" or self.top_k != 1:
             raise NotImplementedError("`num_classes=None` is supported for global top-1 micro statistics only")
-        if preds.is_floating_point():
-            bound = preds.shape[1]
-        else:
-            bound = int(torch.maximum(preds.max(), target.max()).item()) + 1 if preds.numel() else 2
-        bound = max(bound, 2)
-        _multiclass_stat_scores_update_(
-            self.tp, self.fp, self.tn, self.fn, self._workspace(bound, self.tp.device), preds, target, bound, 1,
-            "micro", "global", self.ignore_index, False,
-        )
-        self.tn = -self.fp
+        from metrics_b200.functional.classification.stat_scores import _multiclass_micro_update_unknown_classes_
+
+        _multiclass_micro_update_unknown_classes_(self.tp, self.fp, self.tn, self.fn, preds, target, self.ignore_index)
 
     def compute(self) -> Tensor:
         tp, fp, tn, fn = self._final_state()

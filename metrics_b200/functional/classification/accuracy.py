@@ -53,7 +53,16 @@ def multiclass_accuracy(
     if validate_args:
         _multiclass_stat_scores_arg_validation(num_classes, top_k, average, multidim_average, ignore_index)
         _multiclass_stat_scores_tensor_validation(preds, target, num_classes, multidim_average, ignore_index)
-    states = _multiclass_stat_scores_states(preds, target, num_classes, top_k, average, multidim_average, ignore_index, validate_args)
+    if num_classes is None:  # micro only (validated above; reference :265-270 passes `num_classes or 1` on)
+        if average != "micro" or multidim_average != "global" or top_k != 1:
+            raise NotImplementedError("`num_classes=None` is supported for global top-1 micro accuracy only")
+        from metrics_b200.functional.classification.stat_scores import _multiclass_micro_update_unknown_classes_
+
+        states = [torch.zeros(1, dtype=torch.int64, device=preds.device) for _ in range(4)]
+        _multiclass_micro_update_unknown_classes_(*states, preds, target, ignore_index)
+        states = [s_.reshape(()) for s_ in states]
+    else:
+        states = _multiclass_stat_scores_states(preds, target, num_classes, top_k, average, multidim_average, ignore_index, validate_args)
     return _accuracy_reduce(*states, average=average, multidim_average=multidim_average, top_k=top_k)
 
 

@@ -113,6 +113,27 @@ def _multiclass_stat_scores_update_(
         raise_if_flagged(flag, num_classes, ignore_index)
 
 
+def _class_count_bound(preds: Tensor, target: Tensor) -> int:
+    """``num_classes=None`` (legal with ``average="micro"`` only, reference :238-241): the micro counters need no class count
+    — except ``tn``, where the reference substitutes 1 (:343, :434; accuracy.py:269), i.e. ``tn = -fp`` — but the kernel's
+    range check needs a bound.  It is read from the batch: one device sync, on this corner only."""
+    if preds.is_floating_point() and preds.ndim == target.ndim + 1:
+        return max(int(preds.shape[1]), 2)
+    if preds.numel() == 0:
+        return 2
+    return max(int(torch.maximum(preds.max(), target.max()).item()) + 1, 2)
+
+
+def _multiclass_micro_update_unknown_classes_(tp: Tensor, fp: Tensor, tn: Tensor, fn: Tensor, preds: Tensor, target: Tensor,
+                                             ignore_index: Optional[int], workspace: Optional[Tensor] = None) -> None:
+    """Global top-1 micro counters for inputs whose class count was not given; `tn` is rewritten to the reference's `-fp`."""
+    bound = _class_count_bound(preds, target)
+    if workspace is None or workspace.numel() != 3 * bound + 2:
+        workspace = stat_scores_workspace(bound, tp.device)
+    _multiclass_stat_scores_update_(tp, fp, tn, fn, workspace, preds, target, bound, 1, "micro", "global", ignore_index, False)
+    tn.copy_(-fp)
+
+
 def stat_scores_workspace(num_classes: int, device: torch.device) -> Tensor:
     """Zeroed, self-cleaning scratch required by the stat-scores kernel (see include/metrics_b200.h)."""
     return torch.zeros(3 * num_classes + 2, dtype=torch.int64, device=device)
