@@ -31,6 +31,7 @@ _DTYPE_TAG = {
     torch.bool: BOOL,
 }
 
+ABI_VERSION = 1  # MB200_ABI_VERSION of include/metrics_b200.h
 FLAG_TARGET_RANGE = 1
 FLAG_PREDS_RANGE = 2
 FLAG_SPIN_TIMEOUT = 4
@@ -56,6 +57,11 @@ def lib() -> ctypes.CDLL:
             )
         handle = ctypes.CDLL(_LIB_PATH)
         declare_signatures(handle)
+        if handle.mb200_abi_version() != ABI_VERSION:
+            raise NativeLibraryError(
+                f"metrics_b200: {_LIB_PATH} implements C-ABI version {handle.mb200_abi_version()}, this package binds version "
+                f"{ABI_VERSION} (include/metrics_b200.h): rebuild it with `python -c 'import __graft_entry__ as g; g.build()'`."
+            )
         _lib = handle
     return _lib
 

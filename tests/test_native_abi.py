@@ -174,3 +174,11 @@ def test_every_kernel_wrapper_calls_the_abi_as_declared(monkeypatch):
     assert with_flag[8] == 1 and with_flag[9] == 1 and without_flag[8] == 0
     counts_call = fake.calls["mb200_binary_stat_counts"][0]
     assert counts_call[7] == 0.5 and isinstance(counts_call[7], float)
+
+
+def test_binding_and_header_agree_on_the_abi_version():
+    from metrics_b200 import _native
+
+    text = open(os.path.join(ROOT, "include", "metrics_b200.h")).read()
+    assert int(re.search(r"#define\s+MB200_ABI_VERSION\s+(\d+)", text).group(1)) == _native.ABI_VERSION
+    assert _native.lib().mb200_abi_version() == _native.ABI_VERSION
