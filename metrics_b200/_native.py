@@ -229,8 +229,8 @@ def multiclass_confmat_update_(
     n_outer, inner = _class_dim_geometry(preds, has_class_dim)
     with on_device(dev):
         rc = lib().mb200_multiclass_confmat_update(
-            preds.data_ptr(), tag(preds), has_class_dim, target.data_ptr(), tag(target), n_outer, num_classes, inner,
-            ignore_index is not None, ignore_index or 0, confmat.data_ptr(),
+            preds.data_ptr(), tag(preds), has_class_dim, target.data_ptr(), tag(target), n_outer, int(num_classes), inner,
+            ignore_index is not None, int(ignore_index or 0), confmat.data_ptr(),
             None if err_flag is None else err_flag.data_ptr(), stream_handle(dev),
         )
     if rc:
@@ -259,8 +259,8 @@ def multiclass_stat_scores_update_(
     n_outer, inner = _class_dim_geometry(preds, has_class_dim)
     with on_device(dev):
         rc = lib().mb200_multiclass_stat_scores_update(
-            preds.data_ptr(), tag(preds), has_class_dim, target.data_ptr(), tag(target), n_outer, num_classes, inner,
-            ignore_index is not None, ignore_index or 0, micro, tp.data_ptr(), fp.data_ptr(), tn.data_ptr(),
+            preds.data_ptr(), tag(preds), has_class_dim, target.data_ptr(), tag(target), n_outer, int(num_classes), inner,
+            ignore_index is not None, int(ignore_index or 0), bool(micro), tp.data_ptr(), fp.data_ptr(), tn.data_ptr(),
             fn.data_ptr(), workspace.data_ptr(), None if err_flag is None else err_flag.data_ptr(), stream_handle(dev),
         )
     if rc:
