@@ -182,3 +182,52 @@ def test_binding_and_header_agree_on_the_abi_version():
     text = open(os.path.join(ROOT, "include", "metrics_b200.h")).read()
     assert int(re.search(r"#define\s+MB200_ABI_VERSION\s+(\d+)", text).group(1)) == _native.ABI_VERSION
     assert _native.lib().mb200_abi_version() == _native.ABI_VERSION
+
+
+def test_real_library_accepts_every_wrappers_arguments_up_to_the_first_cuda_call(monkeypatch):
+    """GPU-less boxes only.  Each wrapper is called against the REAL `.so` with host tensors (device checks patched out):
+    ctypes conversion, the library's own argument validation (`MB200_REQUIRE`) and its host-side set-up must all pass, so the
+    first failure has to be a CUDA runtime error (code -2, no driver) — never an argument error (-1 / ValueError / TypeError)."""
+    import pytest
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present: host pointers must not reach the kernels")
+    from metrics_b200 import _native
+
+    cpu = torch.device("cpu")
+    monkeypatch.setattr(_native, "require_cuda", lambda *t: cpu)
+    monkeypatch.setattr(_native, "on_device", lambda d: _native._NOOP)
+    monkeypatch.setattr(_native, "stream_handle", lambda d: 0)
+    monkeypatch.setattr(_native, "_flag_words", {})
+    n, c = 16, 3
+    scores, labels = torch.rand(n, c), torch.randint(c, (n,))
+    i64 = lambda *shape: torch.zeros(*shape, dtype=torch.int64)  # noqa: E731
+    flag = torch.zeros(1, dtype=torch.int32)
+    boxes = torch.rand(4, 4)
+    calls = {
+        "confmat": lambda: _native.multiclass_confmat_update_(i64(c, c), scores, labels, c, 1, flag),
+        "stat_scores": lambda: _native.multiclass_stat_scores_update_(i64(c), i64(c), i64(c), i64(c), i64(3 * c + 2), scores, labels, c, None, True, None),
+        "topk": lambda: _native.multiclass_stat_scores_topk_update_(i64(c), i64(c), i64(c), i64(c), i64(3 * c + 2), scores, labels, c, 2, None, None),
+        "samplewise": lambda: _native.multiclass_stat_scores_samplewise(scores.reshape(4, c, 4), labels.reshape(4, 4), c, None, flag),
+        "argmax": lambda: _native.argmax_rows(scores),
+        "sigmoid": lambda: _native.sigmoid_if_logits(scores[:, 0]),
+        "softmax": lambda: _native.softmax_if_logits(scores),
+        "curve": lambda: _native.curve_evaluate(scores[:, 0], labels.clamp(max=1), 1, 1, want_curve=True),
+        "curve_ovr": lambda: _native.curve_evaluate(scores, labels, c),
+        "pack_keys": lambda: _native.curve_pack_keys(scores, c),
+        "curve_multilabel": lambda: _native.curve_evaluate_multilabel(scores, torch.randint(2, (n, c)), c, ignore_index=-1),
+        "binary_counts": lambda: _native.binary_stat_counts(scores, torch.randint(2, (n, c)), c, 0.5, None, False, None, flag),
+        "regression": lambda: _native.regression_sums(scores[:, 0], scores[:, 1], _native.REG_MSE),
+        "regression_columns": lambda: _native.regression_sums(scores, scores, _native.REG_R2, c),
+        "tweedie": lambda: _native.regression_sums(scores[:, 0] + 0.1, scores[:, 1] + 0.1, _native.REG_TWEEDIE, 1, 1.5),
+        "binned": lambda: _native.binned_curve_update(scores[:, 0], labels.clamp(max=1), torch.linspace(0, 1, 5), 1),
+        "binned_multilabel": lambda: _native.binned_curve_update(scores, torch.randint(2, (n, c)), torch.linspace(0, 1, 5), c, multilabel=True),
+        "coco": lambda: _native.coco_map_evaluate(boxes, torch.rand(4), torch.zeros(4, dtype=torch.long), [2, 2], boxes,
+                                                  torch.zeros(4, dtype=torch.long), torch.zeros(4, dtype=torch.uint8), torch.ones(4), [2, 2],
+                                                  torch.zeros(1, dtype=torch.long), False, [0.5, 0.75], [0.0, 0.5, 1.0], [1, 10, 100]),
+    }
+    for name, call in calls.items():
+        with pytest.raises(_native.NativeLibraryError, match=r"\(code -2\): CUDA error") as info:
+            call()
+        assert "CUDA" in str(info.value), name
