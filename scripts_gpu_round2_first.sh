@@ -5,6 +5,10 @@
 set -x
 mkdir -p gpurun_out
 O=gpurun_out
+# 0. native binaries (seconds): the C-ABI without Python, and the round-2 K2 prototype with its built-in check + timing
+make -C metrics_b200/csrc tools > $O/r2_tools_build.log 2>&1
+timeout 60 metrics_b200/csrc/build/abi_smoke > $O/r2_abi_smoke.txt 2>&1; tail -3 $O/r2_abi_smoke.txt
+timeout 120 metrics_b200/csrc/build/k2_single_pass_proto > $O/r2_k2_proto.txt 2>&1; cat $O/r2_k2_proto.txt
 # 1. the launch path with declared ctypes signatures: smoke + the oldest parity suite
 timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE_OK')" > $O/r2_smoke.log 2>&1; tail -2 $O/r2_smoke.log
 timeout 300 python -m pytest tests/test_confmat_gpu.py tests/test_regression_gpu.py tests/test_map_gpu.py -q -x > $O/r2_core.log 2>&1; tail -3 $O/r2_core.log
