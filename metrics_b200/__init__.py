@@ -33,6 +33,7 @@ from metrics_b200.classification import (  # noqa: F401  (reference __init__.py:
     StatScores,
 )
 from metrics_b200.regression import (  # noqa: F401  (reference __init__.py:113-134)
+    CriticalSuccessIndex,
     ExplainedVariance,
     LogCoshError,
     MeanAbsoluteError,

@@ -1,5 +1,6 @@
 """Functional regression metrics (reference: src/torchmetrics/functional/regression/)."""
 from metrics_b200.functional.regression.metrics import (  # noqa: F401
+    critical_success_index,
     explained_variance,
     log_cosh_error,
     mean_absolute_error,

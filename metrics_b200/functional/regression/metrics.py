@@ -5,7 +5,7 @@ by ONE kernel pass instead of 2-5 elementwise/reduction launches; the `_x_comput
 """
 from __future__ import annotations
 
-from typing import Union
+from typing import Optional, Union
 
 import torch
 from torch import Tensor
@@ -316,3 +316,39 @@ def tweedie_deviance_score(preds: Tensor, targets: Tensor, power: float = 0.0) -
     """Mean Tweedie deviance: power 0 normal, 1 Poisson, (1, 2) compound Poisson-Gamma, 2 Gamma, 3 inverse Gaussian, < 0
     extreme stable (reference :101-143)."""
     return _tweedie_deviance_score_compute(*_tweedie_deviance_score_update(preds, targets, power))
+
+
+# ---- Critical success index (csi.py:22-107) --------------------------------------------------------------------------
+def _critical_success_index_update(preds: Tensor, target: Tensor, threshold: float,
+                                   keep_sequence_dim: Optional[int] = None) -> tuple[Tensor, Tensor, Tensor]:
+    """hits / misses / false alarms of the two fields binarised at ``threshold`` (``>=``), over everything or — with
+    ``keep_sequence_dim`` — separately per index of that dimension.  After the binarisation these are the tp / fn / fp of the
+    binary counting kernel (K2): ONE launch, with the kept dimension presented as its label dimension, instead of the
+    reference's three masked reductions (:44-51)."""
+    from metrics_b200.functional.classification import _binary_counts as _bc
+
+    _check_same_shape(preds, target)
+    if keep_sequence_dim is not None and not 0 <= keep_sequence_dim < preds.ndim:
+        raise ValueError(f"Expected keep_sequence dim to be in range [0, {preds.ndim}] but got {keep_sequence_dim}")
+    above_p, above_t = (preds >= threshold).long(), (target >= threshold).long()
+    if preds.ndim == 1:
+        keep_sequence_dim = None  # nothing left to sum over: `torch.sum(x, dim=())` reduces everything (reference :47-50)
+    if keep_sequence_dim is None:
+        counts = _bc.counts(above_p.reshape(-1), above_t.reshape(-1), 1, 0.5, None, False, False)[0]
+    else:  # [outer, S, inner]: the kernel's `[n_outer, num_labels, inner]` layout
+        kept = preds.shape[keep_sequence_dim]
+        as_labels = [x.movedim(keep_sequence_dim, 0).reshape(1, kept, -1) for x in (above_p, above_t)]
+        counts = _bc.counts(as_labels[0], as_labels[1], kept, 0.5, None, False, False)
+    tp, fp, fn = counts[..., 0], counts[..., 1], counts[..., 3]
+    return tp.int(), fn.int(), fp.int()
+
+
+def _critical_success_index_compute(hits: Tensor, misses: Tensor, false_alarms: Tensor) -> Tensor:
+    from metrics_b200.utilities.compute import _safe_divide
+
+    return _safe_divide(hits, hits + misses + false_alarms)
+
+
+def critical_success_index(preds: Tensor, target: Tensor, threshold: float, keep_sequence_dim: Optional[int] = None) -> Tensor:
+    """hits / (hits + misses + false alarms), also known as the threat score (reference :71-107)."""
+    return _critical_success_index_compute(*_critical_success_index_update(preds, target, threshold, keep_sequence_dim))

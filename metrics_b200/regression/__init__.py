@@ -1,5 +1,6 @@
 """Modular regression metrics (reference: src/torchmetrics/regression/)."""
 from metrics_b200.regression.metrics import (  # noqa: F401
+    CriticalSuccessIndex,
     ExplainedVariance,
     LogCoshError,
     MeanAbsoluteError,

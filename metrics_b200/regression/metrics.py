@@ -308,3 +308,42 @@ class TweedieDevianceScore(Metric):
 
     def compute(self) -> Tensor:
         return F._tweedie_deviance_score_compute(self.sum_deviance_score, self.num_observations)
+
+
+class CriticalSuccessIndex(Metric):
+    """Reference regression/csi.py:27-110: three ``sum`` states, or three ``cat`` list states (one ``[S]`` entry per update)
+    when a sequence dimension is kept."""
+
+    is_differentiable: bool = False
+    higher_is_better: bool = True
+
+    def __init__(self, threshold: float, keep_sequence_dim: Optional[int] = None, **kwargs: Any) -> None:
+        super().__init__(**kwargs)
+        self.threshold = float(threshold)
+        if keep_sequence_dim and (not isinstance(keep_sequence_dim, int) or keep_sequence_dim < 0):
+            raise ValueError(f"Expected keep_sequence_dim to be a non-negative integer but got {keep_sequence_dim}")
+        self.keep_sequence_dim = keep_sequence_dim
+        for name in ("hits", "misses", "false_alarms"):
+            if keep_sequence_dim is None:
+                self.add_state(name, default=torch.tensor(0), dist_reduce_fx="sum")
+            else:
+                self.add_state(name + "_list", default=[], dist_reduce_fx="cat")
+
+    def update(self, preds: Tensor, target: Tensor) -> None:
+        hits, misses, false_alarms = F._critical_success_index_update(preds, target, self.threshold, self.keep_sequence_dim)
+        if self.keep_sequence_dim is None:
+            self.hits += hits
+            self.misses += misses
+            self.false_alarms += false_alarms
+        else:
+            self.hits_list.append(hits)
+            self.misses_list.append(misses)
+            self.false_alarms_list.append(false_alarms)
+
+    def compute(self) -> Tensor:
+        if self.keep_sequence_dim is None:
+            return F._critical_success_index_compute(self.hits, self.misses, self.false_alarms)
+        from metrics_b200.utilities.data import dim_zero_cat
+
+        return F._critical_success_index_compute(dim_zero_cat(self.hits_list), dim_zero_cat(self.misses_list),
+                                                 dim_zero_cat(self.false_alarms_list))

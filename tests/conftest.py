@@ -141,3 +141,10 @@ def golden_fuzz2():
     import numpy as np
 
     return np.load(os.path.join(GOLDEN_DIR, "fuzz2.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_csi():
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN_DIR, "csi.npz"), allow_pickle=False)

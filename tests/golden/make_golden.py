@@ -1212,6 +1212,38 @@ def tweedie_golden() -> dict:
     return out
 
 
+def csi_golden() -> dict:
+    """Critical success index (reference functional/regression/csi.py + regression/csi.py): counts, scores, kept sequence
+    dimensions, the class after two updates."""
+    from torchmetrics.functional.regression.csi import _critical_success_index_update, critical_success_index
+    from torchmetrics.regression.csi import CriticalSuccessIndex
+
+    g = torch.Generator().manual_seed(31337)
+    out = {}
+    case = 0
+    for shape in ((513,), (40, 9), (6, 5, 4, 3), (2, 3, 8, 8, 2)):
+        for dtype in (torch.float32, torch.float64, torch.float16):
+            preds = torch.rand(shape, generator=g).to(dtype)
+            target = torch.rand(shape, generator=g).to(dtype)
+            target.view(-1)[::5] = preds.view(-1)[::5]  # ties with each other and (below) with the threshold
+            preds.view(-1)[::11] = 0.5
+            for threshold in (0.5, 0.25):
+                for keep in (None, *range(len(shape))):
+                    key = f"case{case}"
+                    out[f"{key}/preds"], out[f"{key}/target"] = np_of(preds), np_of(target)
+                    out[f"{key}/meta"] = np.array([threshold, -1 if keep is None else keep, {torch.float32: 0, torch.float64: 1, torch.float16: 2}[dtype]])
+                    hits, misses, fa = _critical_success_index_update(preds, target, threshold, keep)
+                    out[f"{key}/counts"] = np.stack([hits.numpy(), misses.numpy(), fa.numpy()])
+                    out[f"{key}/value"] = critical_success_index(preds, target, threshold, keep).numpy()
+                    metric = CriticalSuccessIndex(threshold, keep_sequence_dim=keep)
+                    metric.update(preds, target)
+                    metric.update(target, preds)
+                    out[f"{key}/class_value"] = metric.compute().numpy()
+                    case += 1
+    out["n_cases"] = np.array(case)
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["classification"]
     if "classification" in which:
@@ -1282,5 +1314,10 @@ if __name__ == "__main__":
     if "fuzz2" in which:  # a second, larger draw (other seed): replayed by the CPU host twin and by the LAST GPU test file
         data = fuzz_golden(seed=77077, mult=3)
         path = os.path.join(HERE, "fuzz2.npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
+    if "csi" in which:
+        data = csi_golden()
+        path = os.path.join(HERE, "csi.npz")
         np.savez_compressed(path, **data)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")

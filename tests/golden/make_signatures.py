@@ -82,9 +82,12 @@ def state_registry(pkg: str) -> dict:
         if isinstance(cls, type) and issubclass(cls, torch.nn.Module):
             for variant, extra in (("default", {}), ("multi", {"num_outputs": 3})):
                 try:
-                    out[f"{name}[{variant}]"] = describe(cls(p=2.0, **extra) if name == "MinkowskiDistance" else cls(**extra))
+                    special = {"MinkowskiDistance": {"p": 2.0}, "CriticalSuccessIndex": {"threshold": 0.5}}.get(name, {})
+                    out[f"{name}[{variant}]"] = describe(cls(**special, **extra))
                 except Exception:
                     continue
+            if name == "CriticalSuccessIndex":
+                out[f"{name}[sequence]"] = describe(cls(0.5, keep_sequence_dim=0))
     return out
 
 

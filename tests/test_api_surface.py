@@ -47,7 +47,7 @@ def test_every_in_scope_name_of_the_reference_exists_here():
         # other arithmetic than the three state kinds of the path
         "Calibration", "calibration", "Hinge", "hinge", "Ranking", "ranking", "Coverage", "coverage", "IntersectionOverUnion",
         "Panoptic", "panoptic", "Pearson", "pearson", "Spearman", "spearman", "Kendall", "kendall", "Cosine", "cosine",
-        "Concordance", "concordance", "KLDivergence", "kl_divergence", "CriticalSuccess", "critical_success", "NormalizedRoot",
+        "Concordance", "concordance", "KLDivergence", "kl_divergence", "NormalizedRoot",
         "normalized_root",
         # deprecated upstream (removed in 1.7) and built on the legacy input-format machinery
         "Dice", "dice", "_input_format_classification", "_check_classification_inputs", "_check_num_classes",
