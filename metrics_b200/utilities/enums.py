@@ -11,12 +11,18 @@ from typing import List
 from typing_extensions import Literal
 
 
+# what `from_str` calls each enum in its error message (the reference overrides a `_name()` staticmethod per class)
+_KIND_OF = {"DataType": "Data type", "AverageMethod": "Average method", "MDMCAverageMethod": "MDMC Average method",
+            "ClassificationTask": "Classification", "ClassificationTaskNoBinary": "Classification",
+            "ClassificationTaskNoMultilabel": "Classification"}
+
+
 class EnumStr(str, Enum):
     """Case-insensitive string enum (reference :20-52)."""
 
-    @staticmethod
-    def _name() -> str:
-        return "Task"
+    @classmethod
+    def _name(cls) -> str:
+        return _KIND_OF.get(cls.__name__, "Task")
 
     @classmethod
     def _allowed_matches(cls, source: str) -> List[str]:
@@ -48,10 +54,6 @@ class EnumStr(str, Enum):
 class DataType(EnumStr):
     """Kinds of classification input of the legacy API (reference :55-69)."""
 
-    @staticmethod
-    def _name() -> str:
-        return "Data type"
-
     BINARY = "binary"
     MULTILABEL = "multi-label"
     MULTICLASS = "multi-class"
@@ -60,10 +62,6 @@ class DataType(EnumStr):
 
 class AverageMethod(EnumStr):
     """Averaging over classes; ``AverageMethod.NONE == None`` and ``== "none"`` (reference :72-93)."""
-
-    @staticmethod
-    def _name() -> str:
-        return "Average method"
 
     MICRO = "micro"
     MACRO = "macro"
@@ -75,20 +73,12 @@ class AverageMethod(EnumStr):
 class MDMCAverageMethod(EnumStr):
     """Averaging over the extra dimensions of multi-dim multi-class input (reference :96-105)."""
 
-    @staticmethod
-    def _name() -> str:
-        return "MDMC Average method"
-
     GLOBAL = "global"
     SAMPLEWISE = "samplewise"
 
 
 class ClassificationTask(EnumStr):
     """Tasks of the task-dispatching wrappers (reference :108-122)."""
-
-    @staticmethod
-    def _name() -> str:
-        return "Classification"
 
     BINARY = "binary"
     MULTICLASS = "multiclass"
@@ -98,20 +88,12 @@ class ClassificationTask(EnumStr):
 class ClassificationTaskNoBinary(EnumStr):
     """Reference :125-138."""
 
-    @staticmethod
-    def _name() -> str:
-        return "Classification"
-
     MULTILABEL = "multilabel"
     MULTICLASS = "multiclass"
 
 
 class ClassificationTaskNoMultilabel(EnumStr):
     """Reference :141-154."""
-
-    @staticmethod
-    def _name() -> str:
-        return "Classification"
 
     BINARY = "binary"
     MULTICLASS = "multiclass"
