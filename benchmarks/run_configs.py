@@ -152,20 +152,37 @@ def cfg4(dev):
 
 
 def cfg5(dev, rank, world):
-    from metrics_b200 import MetricCollection
-    from metrics_b200.classification import MulticlassAUROC, MulticlassF1Score
-    from tests.helpers import cfg5_rank_batches
+    import bench
 
-    batches = [(lg.to(dev), tg.to(dev)) for lg, tg in cfg5_rank_batches(rank, 4)]
-    mc = MetricCollection([MulticlassF1Score(num_classes=1000, validate_args=False),
-                           MulticlassAUROC(num_classes=1000, validate_args=False)]).to(dev)
+    return bench.leg_cfg5(dev, rank, world)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# bench.py --config cfg3|cfg4|cfg5: the same line format as the cfg2 headline
+# --------------------------------------------------------------------------------------------------------------
+_LINES = {
+    "cfg3": ("samples/sec (BinaryAUROC + BinaryAveragePrecision: 1000 update() calls of 10,000 samples, then compute())", "samples/s", 10_000_000),
+    "cfg4": ("detections/sec (MeanAveragePrecision bbox: 50 update() calls of 100 images x 100 detections, then compute())", "detections/s", 500_000),
+    "cfg5": ("metric-updates/sec (MetricCollection([MulticlassF1Score, MulticlassAUROC], C=1000): 4 update() calls of [4096,1000] per rank, then compute())", "updates/s", 4 * 4096 * 1000),
+}
+
+
+def leg_cfg3(dev, steps: int = 3):
+    """cfg3 through the public API, `steps` full passes; device time of updates and compute separately, and end to end from
+    pinned host batches (H2D per update, scalar results read back)."""
+    from metrics_b200 import MetricCollection, _native
+    from metrics_b200.classification import BinaryAUROC, BinaryAveragePrecision
+
+    g = torch.Generator().manual_seed(0)
+    preds = torch.rand(1000, 10000, generator=g)
+    target = torch.randint(0, 2, (1000, 10000), generator=g)
+    dp, dt = preds.to(dev), target.to(dev)
+    mc = MetricCollection([BinaryAUROC(validate_args=False), BinaryAveragePrecision(validate_args=False)]).to(dev)
 
     def updates():
         mc.reset()
-        for lg, tg in batches:
-            mc.update(lg, tg)
-
-    upd_min, _ = ev_time(updates, reps=5, warm=2)
+        for i in range(1000):
+            mc.update(dp[i], dt[i])
 
     def compute():
         for m in mc.values(copy_state=False):
@@ -174,49 +191,146 @@ def cfg5(dev, rank, world):
                 m._group_cache.clear()
         return mc.compute()
 
-    comp_min, comp_med = ev_time(compute, reps=5, warm=2)
-    comp_gather_min = None
-    if world > 1:  # A/B: the reference's gather-everything sync followed by an all-class evaluation on every rank
-        os.environ["MB200_SHARDED_CURVES"] = "0"
-        comp_gather_min, _ = ev_time(compute, reps=5, warm=2)
-        os.environ["MB200_SHARDED_CURVES"] = "1"
-    # sync only
-    def sync_only():
-        for m in mc.values(copy_state=False):
-            m.sync()
-            m.unsync()
-
-    sync_min = None
-    if world > 1:
-        sync_min, _ = ev_time(sync_only, reps=5, warm=2)
+    upd_min, upd_med = ev_time(updates, reps=steps, warm=1)
+    cmp_min, cmp_med = ev_time(compute, reps=max(steps, 3), warm=1)
+    flat_p, flat_t = dp.reshape(-1), dt.reshape(-1)
+    k_min, _ = ev_time(lambda: _native.curve_evaluate(flat_p, flat_t), reps=10, warm=3)
     res = compute()
-    cpu = None
-    if rank == 0 and world == 1:  # the reference's CPU chain for one rank's share, timed beside it
+    # end to end: pinned host batches -> device, per update; two scalars back
+    pp, pt = preds.pin_memory(), target.pin_memory()
+
+    def e2e():
+        mc.reset()
+        for i in range(1000):
+            mc.update(pp[i].to(dev, non_blocking=True), pt[i].to(dev, non_blocking=True))
+        r = compute()
+        return float(r["BinaryAUROC"]), float(r["BinaryAveragePrecision"])
+
+    e2e()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e()
+    e2e_s = time.perf_counter() - t0
+    return {"update_phase_ms": upd_min, "update_phase_ms_median": upd_med, "us_per_update": upd_min, "compute_ms": cmp_min,
+            "compute_ms_median": cmp_med, "curve_evaluate_1e7_ms": k_min, "auroc": float(res["BinaryAUROC"]),
+            "ap": float(res["BinaryAveragePrecision"]), "samples_per_s_device_resident": 1e7 / ((upd_min + cmp_min) * 1e-3),
+            "e2e_samples_per_s": 1e7 / e2e_s, "e2e_h2d_bytes": 1e7 * 12, "e2e_d2h_bytes": 8,
+            "roofline_compute_only": {"algorithmic_bytes": 150e6, "achieved_gbs": 150e6 / (k_min * 1e-3) / 1e9}}
+
+
+def aten_cfg3(dev):
+    """The reference's compute chain for cfg3 on CUDA tensors (two `_binary_clf_curve` sorts, roc.py:53 and
+    precision_recall_curve.py:275), via baseline/_ref when present, else the device-agnostic restatement."""
+    import bench
+
+    g = torch.Generator().manual_seed(0)
+    p = torch.rand(10_000_000, generator=g).to(dev)
+    t = torch.randint(0, 2, (10_000_000,), generator=g).to(dev)
+    if bench.have_reference():
+        tm = bench.import_reference()
+        import torchmetrics.functional.classification as RF
+
+        fn = lambda: (RF.binary_auroc(p, t, validate_args=False), RF.binary_average_precision(p, t, validate_args=False))  # noqa: E731
+        kind = f"the unmodified reference (baseline/_ref, TorchMetrics {tm.__version__}) binary_auroc + binary_average_precision on CUDA tensors"
+    else:
+        from oracle.torch_cpu_chain import binary_auroc_ap_compute_cpu
+
+        fn = lambda: binary_auroc_ap_compute_cpu(p, t)  # noqa: E731
+        kind = "reference op chain (oracle/torch_cpu_chain.py) on CUDA tensors"
+    mn, med = ev_time(fn, reps=5, warm=2)
+    srt, _ = ev_time(lambda: torch.sort(p, descending=True), reps=10, warm=3)
+    a, b = fn()
+    return {"compute_ms": mn, "compute_ms_median": med, "torch_sort_1e7_ms": srt, "auroc": float(a), "ap": float(b), "kind": kind}
+
+
+def leg_cfg4(dev):
+    r = cfg4(dev)
+    r["detections_per_s"] = r["detections_per_s_end_to_end"]
+    return r
+
+
+def bench_line(args, dev, rank, world, sampler):
+    """One JSON line for --config cfg3|cfg4|cfg5 (bench.py prints it)."""
+    metric, unit, units = _LINES[args.config]
+    sampler.wait_ready()
+    w0 = time.time()
+    if args.config == "cfg3":
+        leg = leg_cfg3(dev, steps=max(1, min(args.steps, 5)))
+        step_ms = leg["update_phase_ms"] + leg["compute_ms"]
+        value, e2e = units / (step_ms * 1e-3), {"value": leg["e2e_samples_per_s"], "unit": unit,
+                                                "h2d_bytes_per_step": leg["e2e_h2d_bytes"], "d2h_bytes_per_step": leg["e2e_d2h_bytes"]}
+        leg["aten_gpu_baseline"] = aten_cfg3(dev)
+    elif args.config == "cfg4":
+        leg = leg_cfg4(dev)
+        step_ms = (leg["update_phase_s_wall"] + leg["compute_s_wall_min"]) * 1e3
+        value = units / (step_ms * 1e-3)
+        e2e = {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 12 * 4,
+               "note": "wall clock of the public API with device-resident per-image dicts (the reference's input format)"}
+    else:
+        import bench
+
+        leg = bench.leg_cfg5(dev, rank, world)
+        step_ms = leg["update_ms_4_batches"] + leg["compute_ms"]
+        value = world * units / (step_ms * 1e-3)
+        e2e = {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8}
+    sampler.window("value", w0, time.time())
+    return {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": f"BASELINE.json {args.config}", **leg},
+            "e2e": e2e, "clocks": sampler.stop()}
+
+
+def reference_line(args):
+    """--impl reference for cfg3/cfg5: the reference's CPU implementation (baseline/_ref when present, else the op-chain
+    port) on the host cores; cfg4 has no runnable reference (pycocotools absent)."""
+    import bench
+
+    metric, unit, units = _LINES[args.config]
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
+    kind = "reference" if bench.have_reference() else "port"
+    if args.config == "cfg3":
+        g = torch.Generator().manual_seed(0)
+        preds = torch.rand(1000, 10000, generator=g)
+        target = torch.randint(0, 2, (1000, 10000), generator=g)
+        if kind == "reference":
+            tm = bench.import_reference()
+            mc = tm.MetricCollection([tm.classification.BinaryAUROC(validate_args=False),
+                                      tm.classification.BinaryAveragePrecision(validate_args=False)])
+            t0 = time.perf_counter()
+            for i in range(1000):
+                mc.update(preds[i], target[i])
+            mc.compute()
+            dt = time.perf_counter() - t0
+        else:
+            from oracle.torch_cpu_chain import binary_auroc_ap_compute_cpu
+
+            t0 = time.perf_counter()
+            binary_auroc_ap_compute_cpu(preds.reshape(-1), target.reshape(-1))
+            dt = time.perf_counter() - t0
+        sample = "one full pass: 1000 updates of 10,000 samples + compute()"
+    elif args.config == "cfg5":
         from oracle.torch_cpu_chain import multiclass_auroc_compute_cpu, multiclass_stat_scores_update_cpu
 
-        torch.set_num_threads(min(os.cpu_count() or 1, 32))
-        cb = [(lg.cpu(), tg.cpu()) for lg, tg in batches]
+        torch.manual_seed(0)
+        cb = [(torch.randn(4096, 1000), torch.randint(0, 1000, (4096,))) for _ in range(4)]
+        kind = "port"
         t0 = time.perf_counter()
         st = [torch.zeros(1000, dtype=torch.long) for _ in range(4)]
         probs = []
         for lg, tg in cb:
             multiclass_stat_scores_update_cpu(*st, lg, tg, 1000)
-            probs.append(torch.softmax(lg, 1))  # normalize_logits_if_needed on logits
-        t_upd = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        auc = multiclass_auroc_compute_cpu(torch.cat(probs), torch.cat([tg for _, tg in cb]), 1000)
-        t_cmp = time.perf_counter() - t0
-        cpu = {"update_ms_4_batches": t_upd * 1e3, "compute_ms": t_cmp * 1e3, "auroc": float(auc),
-               "threads": torch.get_num_threads()}
-    t = torch.tensor([upd_min, comp_min, sync_min or 0.0, comp_gather_min or 0.0], device=dev, dtype=torch.float64)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    return {"world": world, "update_ms_4_batches": float(t[0]), "update_units_per_s_per_gpu": 4 * 4096 * 1000 / (float(t[0]) * 1e-3),
-            "compute_ms": float(t[1]), "sync_only_ms": float(t[2]) if world > 1 else None,
-            "compute_ms_gather_everything": float(t[3]) if world > 1 else None,
-            "compute_path": "class-sharded all_to_all (metrics_b200/parallel_curves.py)" if world > 1 else "local",
-            "f1": float(res["MulticlassF1Score"]), "auroc": float(res["MulticlassAUROC"]), "cpu_chain_one_rank": cpu,
-            "sync_bytes_per_rank": 16384 * 1000 * 4 + 16384 * 8 + 4 * 1000 * 8}
+            probs.append(torch.softmax(lg, 1))
+        multiclass_auroc_compute_cpu(torch.cat(probs), torch.cat([tg for _, tg in cb]), 1000)
+        dt = time.perf_counter() - t0
+        sample = "one rank's share: 4 updates of [4096,1000] + compute() (1000 one-vs-rest sorts)"
+    else:
+        return {"impl": "reference", "unavailable": "cfg4: the reference needs pycocotools / faster-coco-eval (absent, no network)"}
+    value = units / dt
+    return {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": 1,
+            "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": f"BASELINE.json {args.config}", "device": "cpu"},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
 
 
 def main():

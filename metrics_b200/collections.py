@@ -18,6 +18,7 @@ from torch import Tensor
 from torch.nn import ModuleDict
 
 from metrics_b200.metric import Metric
+from metrics_b200.utilities.data import allclose
 from metrics_b200.utilities.prints import rank_zero_warn
 
 
@@ -49,13 +50,13 @@ def _states_match(a: Metric, b: Metric) -> bool:
         if type(sa) != type(sb):  # noqa: E721
             return False
         if isinstance(sa, Tensor):
-            if sa.shape != sb.shape or not torch.allclose(sa, sb):
+            if sa.shape != sb.shape or not allclose(sa, sb):
                 return False
         elif isinstance(sa, list):
             if len(sa) != len(sb):
                 return False
             for xa, xb in zip(sa, sb):
-                if xa.shape != xb.shape or not torch.allclose(xa, xb):
+                if xa.shape != xb.shape or not allclose(xa, xb):
                     return False
     return True
 

@@ -184,29 +184,52 @@ class Metric(Module, ABC):
                 )
             if self._computed is not None:
                 return self._computed
-            # metrics whose consumer shards naturally (one-vs-rest curves: by class) may replace "gather everything,
-            # then compute" by their own exchange; explicit sync()/unsync() keep the full-gather semantics
-            sharded = getattr(self, "_compute_distributed", None)
-            if sharded is not None and self._to_sync and not self._is_synced:
-                value = sharded()
-                if value is not NotImplemented:
-                    value = apply_to_collection(_squeeze_if_scalar(value), Tensor, lambda t: t.clone())
-                    if self.compute_with_cache:
-                        self._computed = value
-                    return value
-            with self.sync_context(
-                dist_sync_fn=self.dist_sync_fn,
-                should_sync=self._to_sync,
-                should_unsync=self._should_unsync,
-            ):
-                value = _squeeze_if_scalar(compute(*args, **kwargs))
-                # results must not alias the states: later in-place updates would silently change them
-                value = apply_to_collection(value, Tensor, lambda t: t.clone())
-            if self.compute_with_cache:
-                self._computed = value
-            return value
+            if self.compute_on_cpu and self._device.type != "cpu":
+                # `compute_on_cpu` parks list states in host memory between updates (reference metric.py:478-479 computes
+                # there).  There is no CPU arithmetic in this package: the parked lists are staged back on the metric's
+                # device for this evaluation only and stay parked afterwards.
+                parked = self._stage_parked_lists()
+                try:
+                    return self._compute_impl(compute, args, kwargs)
+                finally:
+                    if not self._is_synced:  # a sync left in place (should_unsync=False) owns the states now
+                        for name, value in parked.items():
+                            setattr(self, name, value)
+            return self._compute_impl(compute, args, kwargs)
 
         return wrapped_func
+
+    def _stage_parked_lists(self) -> Dict[str, List[Tensor]]:
+        parked: Dict[str, List[Tensor]] = {}
+        for name in self._defaults:
+            value = getattr(self, name)
+            if isinstance(value, list) and any(isinstance(v, Tensor) and v.device != self._device for v in value):
+                parked[name] = value
+                setattr(self, name, [v.to(self._device, non_blocking=True) if isinstance(v, Tensor) else v for v in value])
+        return parked
+
+    def _compute_impl(self, compute: Callable, args: Any, kwargs: Any) -> Any:
+        # metrics whose consumer shards naturally (one-vs-rest curves: by class) may replace "gather everything,
+        # then compute" by their own exchange; explicit sync()/unsync() keep the full-gather semantics
+        sharded = getattr(self, "_compute_distributed", None)
+        if sharded is not None and self._to_sync and not self._is_synced:
+            value = sharded()
+            if value is not NotImplemented:
+                value = apply_to_collection(_squeeze_if_scalar(value), Tensor, lambda t: t.clone())
+                if self.compute_with_cache:
+                    self._computed = value
+                return value
+        with self.sync_context(
+            dist_sync_fn=self.dist_sync_fn,
+            should_sync=self._to_sync,
+            should_unsync=self._should_unsync,
+        ):
+            value = _squeeze_if_scalar(compute(*args, **kwargs))
+            # results must not alias the states: later in-place updates would silently change them
+            value = apply_to_collection(value, Tensor, lambda t: t.clone())
+        if self.compute_with_cache:
+            self._computed = value
+        return value
 
     @abstractmethod
     def update(self, *_: Any, **__: Any) -> None:

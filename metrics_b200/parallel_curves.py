@@ -32,6 +32,9 @@ def sharded_applicable(metric: Any) -> bool:
         return False
     if metric.dist_sync_fn is not None or not metric._to_sync or metric.thresholds is not None:
         return False
+    available = getattr(metric, "distributed_available_fn", None)
+    if available is not None and not available():  # the user switched syncing off for this metric (metric.py sync())
+        return False
     group = metric.process_group or torch.distributed.group.WORLD
     if torch.distributed.get_world_size(group) < 2:
         return False
