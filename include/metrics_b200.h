@@ -278,6 +278,33 @@ MB200_API int mb200_binned_curve_update_multilabel(const void* preds, int preds_
                                                    const float* thresholds_sorted, int64_t num_thresholds,
                                                    int64_t* confmat, uint64_t* scratch, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K10 — cross-rank state exchange over NVLink peer memory (csrc/peer.cu).  One process per GPU; `peer_bases` is a DEVICE
+ * array of `world` base pointers of one symmetric allocation (entry r = rank r's base, peer-mapped into this process).
+ * Replaces the per-state `barrier + all_gather(shape) + all_gather(data)` of Metric._sync_dist / gather_all_tensors
+ * (metric.py:501-540, utilities/distributed.py:100-153) for the states that shard naturally.  The entry points enqueue
+ * stores / loads only: cross-rank ordering is the caller's (a signal-pad barrier on the same stream before the data is
+ * consumed and before a region is reused).
+ *
+ * mb200_peer_pack_keys_put: the class-sharded exchange of one-vs-rest curve scores fused with key packing.  preds is this
+ *   rank's [n_local, num_classes] score matrix; class c is owned by rank c / classes_per_rank, whose key matrix
+ *   uint32 [classes_per_rank][n_total] starts `keys_offset_bytes` into its allocation; this rank's samples occupy columns
+ *   [col_offset, col_offset + n_local).  Keys are the ones mb200_curve_pack_keys produces (ready for
+ *   mb200_curve_evaluate_keys).
+ * mb200_peer_put_all: copies `nbytes` from `src` to offset `dst_offset_bytes` of EVERY rank's allocation (all-gather by
+ *   peer stores when every rank uses its own offset).
+ * mb200_peer_reduce_put_i64: all-reduce of an int64 [n] state held at `in_offset_bytes` of every rank's allocation: this
+ *   rank reduces its slice of every rank's input (op: 0 sum, 1 max, 2 min; bit-exact) and stores the result at
+ *   `out_offset_bytes` of every rank's allocation.  Offsets must be 16-byte aligned; world <= 16.
+ * ------------------------------------------------------------------------------------------------ */
+MB200_API int mb200_peer_pack_keys_put(const void* preds, int preds_dtype, int64_t n_local, int64_t num_classes,
+                                       int64_t classes_per_rank, int world, int64_t n_total, int64_t col_offset,
+                                       void* const* peer_bases, int64_t keys_offset_bytes, void* stream);
+MB200_API int mb200_peer_put_all(const void* src, int64_t nbytes, void* const* peer_bases, int64_t dst_offset_bytes,
+                                 int world, void* stream);
+MB200_API int mb200_peer_reduce_put_i64(void* const* peer_bases, int64_t in_offset_bytes, int64_t out_offset_bytes,
+                                        int64_t n, int rank, int world, int op, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

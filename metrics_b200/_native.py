@@ -97,6 +97,9 @@ SIGNATURES = {
     "mb200_binned_curve_scratch_words": ("q", "qq"),
     "mb200_binned_curve_update": ("i", "pipiqqpqppp"),
     "mb200_binned_curve_update_multilabel": ("i", "pipiqqpqppp"),
+    "mb200_peer_pack_keys_put": ("i", "piqqqiqqpqp"),
+    "mb200_peer_put_all": ("i", "pqpqip"),
+    "mb200_peer_reduce_put_i64": ("i", "pqqqiiip"),
 }
 
 

@@ -362,12 +362,27 @@ static cudaError_t launch_overlapped(Kernel kern, int grid, int threads, size_t 
     return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
+// One-wave grid size of a kernel: resident CTAs per SM x SMs.  The occupancy query takes a driver lock and costs 1-2 us —
+// a tenth of a small update's host time — so its answer is kept per (kernel, block size, dynamic smem, device).
 template <typename Kernel>
 static int resident_blocks(Kernel k, int threads, size_t smem) {
+    struct Entry { const void* fn; int threads; size_t smem; int dev; int blocks; };
+    static thread_local Entry cache[8] = {};
+    static thread_local int next = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+    const void* fn = reinterpret_cast<const void*>(k);
+    for (const Entry& e : cache)
+        if (e.fn == fn && e.threads == threads && e.smem == smem && e.dev == dev && e.blocks > 0) return e.blocks;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem) != cudaSuccess || per_sm < 1)
         per_sm = 1;
-    return per_sm * sm_count();
+    const int blocks = per_sm * sm_count();
+    if (dev >= 0) {
+        cache[next] = Entry{fn, threads, smem, dev, blocks};
+        next = (next + 1) & 7;
+    }
+    return blocks;
 }
 
 template <typename T, typename Sink, bool kI64, int kRows>

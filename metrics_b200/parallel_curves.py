@@ -79,6 +79,12 @@ def ovr_curve_scalars_sharded(preds: Optional[Tensor], target: Optional[Tensor],
     if n_total == 0:
         raise IndexError("metrics_b200: cannot evaluate a curve metric without samples")
 
+    packed_rows = world * cpr
+    ws = _peer_workspace(group, device, cpr, n_total, packed_rows)
+    if ws is not None:
+        return _exchange_over_peer_memory(ws, preds, target, num_classes, cpr, n_all, rank, world)
+
+    # ---- NCCL path (no peer memory: other backends' groups never get here, see sharded_applicable) -------------------------
     # targets of all ranks, in rank order (ragged ranks: pad to the longest, gather, compact)
     n_max = max(n_all)
     if n_max == n_local and len(set(n_all)) == 1:
@@ -108,4 +114,46 @@ def ovr_curve_scalars_sharded(preds: Optional[Tensor], target: Optional[Tensor],
     # per-class results of every rank
     packed = torch.cat([auroc.double().unsqueeze(1), ap.double().unsqueeze(1), counts.double()], dim=1).contiguous()  # [cpr, 5]
     gathered = _gather_equal(packed, group, world).reshape(world * cpr, 5)[:num_classes]
+    return gathered[:, 0].float(), gathered[:, 1].float(), gathered[:, 2:].round().to(torch.int64)
+
+
+def _layout(cpr: int, n_total: int, packed_rows: int) -> Tuple[int, int, int, int]:
+    """Byte offsets of (keys u32 [cpr][n_total], targets i64 [n_total], results f64 [packed_rows][5]) and the total."""
+    a = 256
+    keys_off = 0
+    tgt_off = (keys_off + cpr * n_total * 4 + a - 1) // a * a
+    res_off = (tgt_off + n_total * 8 + a - 1) // a * a
+    total = (res_off + packed_rows * 5 * 8 + a - 1) // a * a
+    return keys_off, tgt_off, res_off, total
+
+
+def _peer_workspace(group: Any, device: torch.device, cpr: int, n_total: int, packed_rows: int):
+    from metrics_b200 import peer
+
+    return peer.get(group, device, _layout(cpr, n_total, packed_rows)[3])
+
+
+def _exchange_over_peer_memory(ws: Any, preds: Tensor, target: Tensor, num_classes: int, cpr: int, n_all: list, rank: int,
+                               world: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """The exchange as stores into the owners' memory (csrc/peer.cu): ONE fused pack + put kernel for the scores, one put
+    for the targets, a barrier; the owner sorts its key matrix where it landed; one put + barrier for the per-class scalars.
+    No staging buffers, no all-to-all, no reorder pass, no host synchronisation beyond the sample-count read above.
+
+    The leading barrier makes region reuse safe whatever used the workspace before (a rank may still be reading the result
+    region of the previous exchange, or the output of a peer all-reduce, when a faster rank starts storing the next keys)."""
+    n_total = sum(n_all)
+    col_off = sum(n_all[:rank])
+    keys_off, tgt_off, res_off, _ = _layout(cpr, n_total, world * cpr)
+    ws.barrier()
+    ws.pack_keys_put(preds, cpr, n_total, col_off, keys_off)
+    if preds.shape[0]:
+        ws.put_all(target, tgt_off + col_off * 8)
+    ws.barrier()
+    keys_mine = ws.view(keys_off, (cpr, n_total), torch.int32)
+    tgt_all = ws.view(tgt_off, (n_total,), torch.int64)
+    auroc, ap, counts = _native.curve_evaluate_keys(keys_mine, tgt_all, first_class=rank * cpr)
+    packed = torch.cat([auroc.double().unsqueeze(1), ap.double().unsqueeze(1), counts.double()], dim=1).contiguous()  # [cpr, 5]
+    ws.put_all(packed, res_off + rank * cpr * 5 * 8)
+    ws.barrier()
+    gathered = ws.view(res_off, (world * cpr, 5), torch.float64)[:num_classes]
     return gathered[:, 0].float(), gathered[:, 1].float(), gathered[:, 2:].round().to(torch.int64)

@@ -48,6 +48,42 @@ def _gather_equal(t: Tensor, group: Any, world: int) -> Tensor:
     return out.reshape(world, *t.shape)
 
 
+_PEER_MIN_BYTES = 256 * 1024  # below this NCCL's small-message latency (~30 us) is as good as two signal barriers
+
+
+def _peer_all_reduce(parts: List[Tensor], dtype: torch.dtype, op: Any, group: Any) -> Optional[Tensor]:
+    """int64 bucket all-reduce over NVLink peer memory (csrc/peer.cu `mb200_peer_reduce_put_i64`): every rank stores its
+    bucket in the group's symmetric workspace, reduces ITS slice of all ranks' buckets with peer loads and stores the
+    reduced slice into every rank with peer stores — bit-exact like the NCCL all-reduce it replaces.  None = not applicable
+    (small bucket, other dtype, CPU / non-NCCL group, peer memory unavailable): the caller uses NCCL."""
+    if dtype != torch.int64 or not parts[0].is_cuda:
+        return None
+    n = sum(p.numel() for p in parts)
+    if n * 8 < _PEER_MIN_BYTES:
+        return None
+    from metrics_b200 import peer
+
+    ops = torch.distributed.ReduceOp
+    code = {ops.SUM: 0, ops.MAX: 1, ops.MIN: 2}.get(op)
+    if code is None:
+        return None
+    region = (n * 8 + 255) // 256 * 256
+    ws = peer.get(group, parts[0].device, 2 * region)
+    if ws is None:
+        return None
+    src = ws.view(0, (n,), torch.int64)
+    # No leading barrier: the copy-in only writes THIS rank's block, and remote stores into other ranks' blocks are issued
+    # after the first barrier below, which a rank enters behind everything it enqueued earlier on this stream.
+    offset = 0
+    for p in parts:
+        src[offset: offset + p.numel()].copy_(p.reshape(-1))
+        offset += p.numel()
+    ws.barrier()  # every rank's input is in place
+    ws.reduce_put_i64(0, region, n, code)
+    ws.barrier()  # every slice of the result has landed here
+    return ws.view(region, (n,), torch.int64).clone()
+
+
 def sync_states_bucketed(metric: Any, group: Optional[Any]) -> bool:
     """Synchronise all states of ``metric`` in place.  Returns False if the fast path does not apply."""
     if group is None:
@@ -77,8 +113,10 @@ def sync_states_bucketed(metric: Any, group: Optional[Any]) -> bool:
     # ---- integer reductions: one collective per (dtype, op) -------------------------------------------------
     for (dtype, op), names in int_buckets.items():
         parts = [getattr(metric, n).reshape(-1) for n in names]
-        bucket = torch.cat(parts) if len(parts) > 1 else parts[0].clone()
-        torch.distributed.all_reduce(bucket, op=op, group=group)
+        bucket = _peer_all_reduce(parts, dtype, op, group)
+        if bucket is None:
+            bucket = torch.cat(parts) if len(parts) > 1 else parts[0].clone()
+            torch.distributed.all_reduce(bucket, op=op, group=group)
         offset = 0
         for n in names:
             ref = getattr(metric, n)
