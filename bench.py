@@ -192,15 +192,20 @@ def run_reference(args) -> dict:
     while rows > 1024 and (args.steps + args.warmup) * est_full * rows / N_ROWS > budget_s:
         rows //= 2
     r = time_cpu_chain(logits, target, rows, args.steps, args.warmup)
-    ups = rows * N_CLASSES * args.steps / r["total_s"]
-    sample = f"{args.steps} update() calls on the first {rows} rows of the seed-0 [65536,1000] bf16 batch"
+    # `value` from the MEDIAN step: a 128-core shared host throws 100 ms outliers into a 5 ms step, and the mean over 20
+    # steps then swings 5x between runs.  The median is the reference at its steady best — the conservative denominator for
+    # every speed-up quoted against it; the total-time figure is kept beside it.
+    ups = rows * N_CLASSES / r["median_s"]
+    sample = (f"{args.steps} update() calls on the first {rows} rows of the seed-0 [65536,1000] bf16 batch; value = units / "
+              f"median step ({r['median_s'] * 1e3:.2f} ms; mean {r['total_s'] / args.steps * 1e3:.2f} ms)")
     return {
         "impl": "reference",
         "metric": METRIC, "value": ups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": r["total_s"] / args.steps * 1e3, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": r["median_s"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "MulticlassConfusionMatrix(num_classes=1000).update, [65536,1000] bf16 logits + int64 target",
                    "rows_per_step": rows, "device": "cpu", "what": r["what"],
+                   "value_from_total_time": rows * N_CLASSES * args.steps / r["total_s"],
                    "ms_per_step_min": r["min_s"] * 1e3, "ms_per_step_median": r["median_s"] * 1e3,
                    "thread_calibration_ms": r["calibration_ms"]},
         "cpu_baseline": {"value": ups, "unit": UNIT, "cores": r["threads"], "kind": r["kind"], "sample": sample},
@@ -566,7 +571,7 @@ def run_ours(args) -> dict:
         n_cpu = 60
         r = time_cpu_chain(logits0, target0, N_ROWS, n_cpu, 3)
         line["cpu_baseline"] = {
-            "value": UNITS_PER_STEP * n_cpu / r["total_s"], "unit": UNIT, "cores": r["threads"], "kind": r["kind"],
+            "value": UNITS_PER_STEP / r["median_s"], "unit": UNIT, "cores": r["threads"], "kind": r["kind"],
             "sample": f"{n_cpu} update() calls of the full seed-0 [65536,1000] bf16 batch: {r['what']}, {r['total_s']:.1f} s "
                       f"(per step min {r['min_s'] * 1e3:.2f} ms, median {r['median_s'] * 1e3:.2f} ms)",
         }

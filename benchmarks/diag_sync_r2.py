@@ -96,20 +96,26 @@ def main():
         dst = torch.empty_like(t)
         out["symm"]["peer_read_8MB"] = ev(lambda: dst.copy_(pt))
         out["symm"]["peer_write_8MB"] = ev(lambda: pt.copy_(dst))
-        from metrics_b200 import _native
+        from metrics_b200 import parallel_sync
 
-        if hasattr(_native, "peer_allreduce_i64"):
-            work = symm.empty(2 * 1000 * 1000, dtype=torch.int64, device=dev)
-            wh = symm.rendezvous(work, dist.group.WORLD)
-            src = torch.full((1000 * 1000,), rank + 1, dtype=torch.int64, device=dev)
+        src = torch.full((1000 * 1000,), rank + 1, dtype=torch.int64, device=dev)
+        res = parallel_sync._peer_all_reduce([src], torch.int64, dist.ReduceOp.SUM, dist.group.WORLD)
+        torch.cuda.synchronize()
+        out["symm"]["own_allreduce_ok"] = bool(res is not None and (res == world * (world + 1) // 2).all())
+        out["symm"]["own_allreduce_8MB"] = ev(lambda: parallel_sync._peer_all_reduce([src], torch.int64, dist.ReduceOp.SUM, dist.group.WORLD))
+        out["confmat_compute_peer"] = ev(compute)
+        os.environ["MB200_PEER_EXCHANGE"] = "0"
+        out["confmat_compute_nccl"] = ev(compute)
+        os.environ["MB200_PEER_EXCHANGE"] = "1"
+        # cfg5 compute: peer-memory exchange vs NCCL all_to_all exchange vs gather-everything
+        import bench
 
-            def mine():
-                return _native.peer_allreduce_i64(src, work, wh)
-
-            res = mine()
-            torch.cuda.synchronize()
-            out["symm"]["own_allreduce_ok"] = bool((res == world * (world + 1) // 2).all())
-            out["symm"]["own_allreduce_8MB"] = ev(mine)
+        leg = {}
+        for name, env in (("peer", {"MB200_PEER_EXCHANGE": "1"}), ("nccl_all_to_all", {"MB200_PEER_EXCHANGE": "0"})):
+            os.environ.update(env)
+            leg[name] = bench.leg_cfg5(dev, rank, world)
+        os.environ["MB200_PEER_EXCHANGE"] = "1"
+        out["cfg5"] = {k: {kk: v[kk] for kk in ("update_ms_4_batches", "compute_ms", "compute_ms_median", "compute_ms_gather_everything", "auroc", "parity")} for k, v in leg.items()}
     except Exception as err:  # pragma: no cover
         import traceback
 

@@ -166,6 +166,11 @@ MB200_API int mb200_curve_softmax_if_logits(const void* preds, int dtype, int64_
  * AP accumulated in fp64 in a fixed order (bitwise reproducible run to run).
  * ------------------------------------------------------------------------------------------------ */
 MB200_API int64_t mb200_curve_workspace_bytes(int64_t num_classes, int64_t n);
+/* float64 scores are sorted as 64-bit keys (the reference sorts them as doubles: functional/classification/
+ * precision_recall_curve.py:60 `argsort`), 8 radix passes and a larger workspace: size it with the score dtype.  For f64
+ * scores `thr_out` of the evaluate calls is double [num_classes][n]; for every other score type float [num_classes][n]
+ * (half / bfloat16 scores are compared as float32, like ATen). fps / tps stay float32 (the reference's `target * 1.0`). */
+MB200_API int64_t mb200_curve_workspace_bytes_for(int64_t num_classes, int64_t n, int preds_dtype);
 /* the packing step alone: class-major keys [num_classes][n] of [n, num_classes] scores, and sort+scan on packed keys
  * (positives of curve s: target == first_class + s; `keys` is sorted in place).  Used by the class-sharded multi-GPU
  * evaluation, which exchanges key rows between ranks (all-to-all) between the two calls. */
@@ -178,7 +183,16 @@ MB200_API int mb200_curve_evaluate_keys(uint32_t* keys, const void* target, int 
 MB200_API int mb200_curve_evaluate(const void* preds, int preds_dtype, const void* target, int target_dtype,
                                    int64_t n, int64_t num_classes, int64_t pos_label, void* workspace,
                                    int64_t workspace_bytes, float* out_auroc, float* out_ap, int64_t* out_counts,
-                                   float* fps_out, float* tps_out, float* thr_out, uint32_t* err_flag, void* stream);
+                                   float* fps_out, float* tps_out, void* thr_out, uint32_t* err_flag, void* stream);
+/* `_binary_clf_curve` with `sample_weights` (functional/classification/precision_recall_curve.py:64, 73-78): at every
+ * distinct score (descending) tps = cumsum(w * [target == pos_label]), fps = cumsum(w * [target != pos_label]), accumulated
+ * in fp64 in a fixed order.  weights: double [n].  fps_out / tps_out: double [n]; thr_out: double [n] for f64 scores, float
+ * [n] otherwise; count_out: device int64, number of distinct thresholds (valid prefix of the three outputs). */
+MB200_API int64_t mb200_curve_weighted_workspace_bytes(int64_t n, int preds_dtype);
+MB200_API int mb200_curve_weighted_clf_curve(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                             const double* weights, int64_t n, int64_t pos_label, void* workspace,
+                                             int64_t workspace_bytes, double* fps_out, double* tps_out, void* thr_out,
+                                             int64_t* count_out, uint32_t* err_flag, void* stream);
 /* Multilabel task: `num_labels` independent binary curves in one batched sort + scan.  preds / target are
  * [n, num_labels] row-major, positives are target == 1.  With has_ignore, entries with target == ignore_index are
  * removed from their own label's curve only (they are given the largest sort key and the scan stops before them).
@@ -188,7 +202,7 @@ MB200_API int mb200_curve_evaluate(const void* preds, int preds_dtype, const voi
 MB200_API int mb200_curve_evaluate_multilabel(const void* preds, int preds_dtype, const void* target, int target_dtype,
                                               int64_t n, int64_t num_labels, int has_ignore, int64_t ignore_index,
                                               void* workspace, int64_t workspace_bytes, float* out_auroc, float* out_ap,
-                                              int64_t* out_counts, float* fps_out, float* tps_out, float* thr_out,
+                                              int64_t* out_counts, float* fps_out, float* tps_out, void* thr_out,
                                               uint32_t* err_flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -84,6 +84,9 @@ SIGNATURES = {
     "mb200_curve_sigmoid_if_logits": ("i", "piqppp"),
     "mb200_curve_softmax_if_logits": ("i", "piqqppp"),
     "mb200_curve_workspace_bytes": ("q", "qq"),
+    "mb200_curve_workspace_bytes_for": ("q", "qqi"),
+    "mb200_curve_weighted_workspace_bytes": ("q", "qi"),
+    "mb200_curve_weighted_clf_curve": ("i", "pipipqqpqpppppp"),
     "mb200_curve_pack_keys": ("i", "piqqpp"),
     "mb200_curve_evaluate_keys": ("i", "ppiqqqpqppppp"),
     "mb200_curve_evaluate": ("i", "pipiqqqpqpppppppp"),
@@ -310,8 +313,6 @@ def softmax_if_logits(preds: Tensor) -> Tensor:
     out = torch.empty_like(preds)
     if preds.numel() == 0:
         return out
-    if preds.dtype == torch.float64:
-        raise NotImplementedError("metrics_b200: float64 scores are not supported by the multiclass curve kernels")
     st = stream_handle(dev)
     with on_device(dev):
         rc = lib().mb200_curve_softmax_if_logits(
@@ -325,23 +326,23 @@ def curve_evaluate(preds: Tensor, target: Tensor, num_classes: int = 1, pos_labe
     """Sort + TP/FP scan for ``num_classes`` one-vs-rest curves (``mb200_curve_evaluate``).
 
     Returns ``(auroc[C] f32, ap[C] f32, counts[C, 3] i64, curve)`` where ``curve`` is ``None`` or the tuple
-    ``(fps, tps, thresholds)`` of ``[C, N]`` float32 buffers whose first ``counts[c, 2]`` entries per row are valid.
+    ``(fps, tps, thresholds)`` of ``[C, N]`` buffers whose first ``counts[c, 2]`` entries per row are valid; fps / tps are
+    float32, thresholds float64 for float64 scores (sorted as 64-bit keys) and float32 otherwise.
     """
     dev = require_cuda(preds, target)
-    if preds.dtype == torch.float64:
-        raise NotImplementedError("metrics_b200: float64 scores are not supported by the exact curve kernels; cast to float32")
     preds = preds.contiguous()
     target = target.contiguous()
     n = target.numel()
     lib_ = lib()
-    nbytes = int(lib_.mb200_curve_workspace_bytes(i64(num_classes), i64(n)))
+    nbytes = int(lib_.mb200_curve_workspace_bytes_for(i64(num_classes), i64(n), tag(preds)))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     auroc = torch.empty(num_classes, dtype=torch.float32, device=dev)
     ap = torch.empty(num_classes, dtype=torch.float32, device=dev)
     counts = torch.empty((num_classes, 3), dtype=torch.int64, device=dev)
     curve = None
     if want_curve:
-        curve = tuple(torch.empty((num_classes, n), dtype=torch.float32, device=dev) for _ in range(3))
+        thr_dtype = torch.float64 if preds.dtype == torch.float64 else torch.float32
+        curve = tuple(torch.empty((num_classes, n), dtype=dt, device=dev) for dt in (torch.float32, torch.float32, thr_dtype))
     with on_device(dev):
         rc = lib_.mb200_curve_evaluate(
             ptr(preds), tag(preds), ptr(target), tag(target), i64(n), i64(num_classes), i64(pos_label), ptr(ws),
@@ -350,6 +351,29 @@ def curve_evaluate(preds: Tensor, target: Tensor, num_classes: int = 1, pos_labe
         )
     check(rc, "curve_evaluate")
     return auroc, ap, counts, curve
+
+
+def curve_weighted_clf_curve(preds: Tensor, target: Tensor, weights: Tensor, pos_label: int = 1):
+    """``(fps f64 [U], tps f64 [U], thresholds [U])`` of the weighted binary curve (``mb200_curve_weighted_clf_curve``); U is
+    read back from the device (data-dependent output size, like the reference's ``torch.where``)."""
+    dev = require_cuda(preds, target, weights)
+    preds, target = preds.contiguous(), target.contiguous()
+    weights = weights.to(torch.float64).contiguous()
+    n = preds.numel()
+    lib_ = lib()
+    nbytes = int(lib_.mb200_curve_weighted_workspace_bytes(n, tag(preds)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    fps = torch.empty(n, dtype=torch.float64, device=dev)
+    tps = torch.empty(n, dtype=torch.float64, device=dev)
+    thr = torch.empty(n, dtype=torch.float64 if preds.dtype == torch.float64 else torch.float32, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    with on_device(dev):
+        rc = lib_.mb200_curve_weighted_clf_curve(ptr(preds), tag(preds), ptr(target), tag(target), ptr(weights), n,
+                                                 int(pos_label), ptr(ws), nbytes, ptr(fps), ptr(tps), ptr(thr), ptr(count),
+                                                 None, stream_handle(dev))
+    check(rc, "curve_weighted_clf_curve")
+    u = int(count.item())
+    return fps[:u], tps[:u], thr[:u]
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -582,20 +606,19 @@ def curve_evaluate_multilabel(preds: Tensor, target: Tensor, num_labels: int, ig
     """``num_labels`` independent binary curves from ``[N, L]`` scores / targets in one batched sort + scan
     (``mb200_curve_evaluate_multilabel``).  Same return layout as :func:`curve_evaluate`."""
     dev = require_cuda(preds, target)
-    if preds.dtype == torch.float64:
-        raise NotImplementedError("metrics_b200: float64 scores are not supported by the exact curve kernels; cast to float32")
     preds = preds.contiguous()
     target = target.contiguous()
     n = preds.shape[0]
     lib_ = lib()
-    nbytes = int(lib_.mb200_curve_workspace_bytes(i64(num_labels), i64(n)))
+    nbytes = int(lib_.mb200_curve_workspace_bytes_for(i64(num_labels), i64(n), tag(preds)))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     auroc = torch.empty(num_labels, dtype=torch.float32, device=dev)
     ap = torch.empty(num_labels, dtype=torch.float32, device=dev)
     counts = torch.empty((num_labels, 3), dtype=torch.int64, device=dev)
     curve = None
     if want_curve:
-        curve = tuple(torch.empty((num_labels, n), dtype=torch.float32, device=dev) for _ in range(3))
+        thr_dtype = torch.float64 if preds.dtype == torch.float64 else torch.float32
+        curve = tuple(torch.empty((num_labels, n), dtype=dt, device=dev) for dt in (torch.float32, torch.float32, thr_dtype))
     with on_device(dev):
         rc = lib_.mb200_curve_evaluate_multilabel(
             ptr(preds), tag(preds), ptr(target), tag(target), i64(n), i64(num_labels),

@@ -52,6 +52,28 @@ __device__ __forceinline__ float score_of_key(unsigned k) {
     if (ok == 0xffffffffu) return __int_as_float(0x7fc00000);
     return f32_from_order_key(ok);
 }
+__device__ __forceinline__ double score_of_key(unsigned long long k) {
+    const unsigned long long ok = ~k;
+    if (ok == ~0ull) return __longlong_as_double(0x7ff8000000000000ll);
+    const unsigned long long b = (ok & 0x8000000000000000ull) ? (ok & 0x7fffffffffffffffull) : ~ok;
+    return __longlong_as_double((long long)b);
+}
+// Key type of a score type: float64 scores keep all 64 bits (the reference sorts them as doubles); everything else is
+// compared as float32, like ATen compares half / bfloat16 values.
+template <typename T>
+struct KeyOf {
+    using type = unsigned;
+    static __device__ __forceinline__ unsigned make(T v) { return desc_key(to_float<T>(v)); }
+};
+template <>
+struct KeyOf<double> {
+    using type = unsigned long long;
+    static __device__ __forceinline__ unsigned long long make(double v) { return ~f64_order_key(v); }
+};
+template <typename KeyT>
+struct ThrOf { using type = float; };
+template <>
+struct ThrOf<unsigned long long> { using type = double; };
 
 // =====================================================================================================
 // K6: batch-global "are these logits?" test and conditional sigmoid  (utilities/compute.py:223-229, device branch:
@@ -182,6 +204,32 @@ __global__ void __launch_bounds__(256) softmax_if_kernel(const T* __restrict__ x
     }
 }
 
+// float64 rows: the same warp layout in double arithmetic (ATen's CUDA softmax accumulates doubles in double)
+template <>
+__global__ void __launch_bounds__(256) softmax_if_kernel<double>(const double* __restrict__ x, double* __restrict__ out, int n,
+                                                                 int C, const unsigned* __restrict__ flag) {
+    const bool apply = (*flag) != 0u;
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n; r += gridDim.x * wpb) {
+        const double* __restrict__ row = x + (size_t)r * C;
+        double* __restrict__ orow = out + (size_t)r * C;
+        if (!apply) {
+            for (int c = lane; c < C; c += 32) orow[c] = row[c];
+            continue;
+        }
+        double m = -INFINITY;
+        for (int c = lane; c < C; c += 32) m = fmax(m, row[c]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(kFull, m, o));
+        double s = 0.0;
+        for (int c = lane; c < C; c += 32) s += exp(row[c] - m);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+        for (int c = lane; c < C; c += 32) orow[c] = exp(row[c] - m) / s;
+    }
+}
+
 // =====================================================================================================
 // key packing
 // =====================================================================================================
@@ -189,9 +237,10 @@ __global__ void __launch_bounds__(256) softmax_if_kernel(const T* __restrict__ x
 template <typename T>
 __global__ void __launch_bounds__(256) pack_binary_kernel(const T* __restrict__ preds, const void* __restrict__ target,
                                                           int tdtype, long long n, long long pos_label,
-                                                          unsigned* __restrict__ keys, unsigned char* __restrict__ labels) {
+                                                          typename KeyOf<T>::type* __restrict__ keys,
+                                                          unsigned char* __restrict__ labels) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        keys[i] = desc_key(to_float<T>(preds[i]));
+        keys[i] = KeyOf<T>::make(preds[i]);
         labels[i] = (unsigned char)(load_label(target, tdtype, i) == pos_label);
     }
 }
@@ -200,9 +249,10 @@ __global__ void __launch_bounds__(256) pack_binary_kernel(const T* __restrict__ 
 // 32x32 shared-memory tile transpose so that both the read and the write are coalesced.
 template <typename T>
 __global__ void __launch_bounds__(256) pack_ovr_kernel(const T* __restrict__ preds, const void* __restrict__ target,
-                                                       int tdtype, int n, int C, unsigned* __restrict__ keys,
+                                                       int tdtype, int n, int C,
+                                                       typename KeyOf<T>::type* __restrict__ keys,
                                                        unsigned char* __restrict__ labels) {
-    __shared__ unsigned tile[32][33];
+    __shared__ typename KeyOf<T>::type tile[32][33];
     __shared__ int tgt[32];
     const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of 32 threads
@@ -212,7 +262,7 @@ __global__ void __launch_bounds__(256) pack_ovr_kernel(const T* __restrict__ pre
     }
     for (int j = ty; j < 32; j += 8) {
         const int nn = n0 + j, cc = c0 + tx;
-        if (nn < n && cc < C) tile[j][tx] = desc_key(to_float<T>(preds[(size_t)nn * C + cc]));
+        if (nn < n && cc < C) tile[j][tx] = KeyOf<T>::make(preds[(size_t)nn * C + cc]);
     }
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
@@ -228,13 +278,15 @@ __global__ void __launch_bounds__(256) pack_ovr_kernel(const T* __restrict__ pre
 // Entries whose target equals `ignore` get the largest key (they sort behind every real score) and are counted per
 // label in seg_ignored[L]: the scan then works on the first n - seg_ignored[l] elements of segment l only — the
 // reference filters them per label before its sort (functional/classification/precision_recall_curve.py:826-830).
-constexpr unsigned kIgnoredKey = 0xFFFFFFFFu;
 template <typename T>
 __global__ void __launch_bounds__(256) pack_multilabel_kernel(const T* __restrict__ preds, const void* __restrict__ target,
                                                               int tdtype, int n, int L, int has_ignore, long long ignore,
-                                                              unsigned* __restrict__ keys, unsigned char* __restrict__ labels,
+                                                              typename KeyOf<T>::type* __restrict__ keys,
+                                                              unsigned char* __restrict__ labels,
                                                               int* __restrict__ seg_ignored) {
-    __shared__ unsigned tile[32][33];
+    using KeyT = typename KeyOf<T>::type;
+    constexpr KeyT kIgnoredKey = ~(KeyT)0;
+    __shared__ KeyT tile[32][33];
     __shared__ unsigned char ltile[32][33];
     const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -243,7 +295,7 @@ __global__ void __launch_bounds__(256) pack_multilabel_kernel(const T* __restric
         if (nn < n && cc < L) {
             const long long t = load_label(target, tdtype, (long long)nn * L + cc);
             const bool ign = has_ignore && t == ignore;
-            tile[j][tx] = ign ? kIgnoredKey : desc_key(to_float<T>(preds[(size_t)nn * L + cc]));
+            tile[j][tx] = ign ? kIgnoredKey : KeyOf<T>::make(preds[(size_t)nn * L + cc]);
             ltile[j][tx] = (unsigned char)(t == 1 && !ign);
         }
     }
@@ -251,7 +303,7 @@ __global__ void __launch_bounds__(256) pack_multilabel_kernel(const T* __restric
     for (int j = ty; j < 32; j += 8) {
         const int cc = c0 + j, nn = n0 + tx;
         const bool ok = nn < n && cc < L;
-        const unsigned k = ok ? tile[tx][j] : 0u;
+        const KeyT k = ok ? tile[tx][j] : (KeyT)0;
         if (ok) {
             keys[(size_t)cc * n + nn] = k;
             labels[(size_t)cc * n + nn] = ltile[tx][j];
@@ -352,23 +404,33 @@ __device__ __forceinline__ unsigned block_excl_max(unsigned v, unsigned* smem8) 
 }
 
 // Blocked arrangement: thread t owns elements [t*8, t*8+8) of the tile.
+template <typename KeyT>
 struct ScanThreadData {
-    unsigned key[kScanItems];
-    unsigned key_next;  // key following the thread's last element (or ~own for "end of segment")
+    KeyT key[kScanItems];
+    KeyT key_next;  // key following the thread's last element (or ~own for "end of segment")
     unsigned char lab[kScanItems];
     int count;  // valid elements
 };
 
-__device__ __forceinline__ void scan_load(ScanThreadData& d, const unsigned* __restrict__ k,
+template <typename KeyT>
+__device__ __forceinline__ void scan_load(ScanThreadData<KeyT>& d, const KeyT* __restrict__ k,
                                           const unsigned char* __restrict__ l, int n, int tile) {
     const int base = tile * kScanTile + threadIdx.x * kScanItems;
     d.count = max(0, min(kScanItems, n - base));
     const bool aligned = ((reinterpret_cast<uintptr_t>(k + base) & 15) == 0) && ((reinterpret_cast<uintptr_t>(l + base) & 7) == 0);
     if (d.count == kScanItems && aligned) {
-        const uint4 a = *reinterpret_cast<const uint4*>(k + base);
-        const uint4 b = *reinterpret_cast<const uint4*>(k + base + 4);
-        d.key[0] = a.x, d.key[1] = a.y, d.key[2] = a.z, d.key[3] = a.w;
-        d.key[4] = b.x, d.key[5] = b.y, d.key[6] = b.z, d.key[7] = b.w;
+        if constexpr (sizeof(KeyT) == 4) {
+            const uint4 a = *reinterpret_cast<const uint4*>(k + base);
+            const uint4 b = *reinterpret_cast<const uint4*>(k + base + 4);
+            d.key[0] = a.x, d.key[1] = a.y, d.key[2] = a.z, d.key[3] = a.w;
+            d.key[4] = b.x, d.key[5] = b.y, d.key[6] = b.z, d.key[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < kScanItems; i += 2) {
+                const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(k + base + i);
+                d.key[i] = a.x, d.key[i + 1] = a.y;
+            }
+        }
         const uint2 lb = *reinterpret_cast<const uint2*>(l + base);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -378,31 +440,33 @@ __device__ __forceinline__ void scan_load(ScanThreadData& d, const unsigned* __r
     } else {
 #pragma unroll
         for (int i = 0; i < kScanItems; ++i) {
-            d.key[i] = i < d.count ? k[base + i] : 0u;
+            d.key[i] = i < d.count ? k[base + i] : (KeyT)0;
             d.lab[i] = i < d.count ? l[base + i] : (unsigned char)0;
         }
     }
     const int nxt = base + kScanItems;
-    d.key_next = (d.count == kScanItems && nxt < n) ? k[nxt] : 0u;
+    d.key_next = (d.count == kScanItems && nxt < n) ? k[nxt] : (KeyT)0;
 }
 // is element i of this thread the last of its tie group?
-__device__ __forceinline__ bool is_group_end(const ScanThreadData& d, int i, int n, int tile) {
+template <typename KeyT>
+__device__ __forceinline__ bool is_group_end(const ScanThreadData<KeyT>& d, int i, int n, int tile) {
     if (i >= d.count) return false;
     const int g = tile * kScanTile + threadIdx.x * kScanItems + i;
     if (g == n - 1) return true;
-    const unsigned nk = (i + 1 < kScanItems) ? d.key[i + 1] : d.key_next;
+    const KeyT nk = (i + 1 < kScanItems) ? d.key[i + 1] : d.key_next;
     return d.key[i] != nk;
 }
 
 // phase 1: per-tile aggregates
-__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const unsigned* __restrict__ keys,
+template <typename KeyT>
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const KeyT* __restrict__ keys,
                                                                    const unsigned char* __restrict__ labels, int n_stride,
                                                                    const int* __restrict__ seg_ignored,
                                                                    int tiles, TileInfo* __restrict__ info) {
     __shared__ unsigned sm[8];
     const int seg = blockIdx.y, tile = blockIdx.x;
     const int n = seg_ignored ? n_stride - seg_ignored[seg] : n_stride;  // ignored entries sit behind the valid ones
-    ScanThreadData d;
+    ScanThreadData<KeyT> d;
     scan_load(d, keys + (size_t)seg * n_stride, labels + (size_t)seg * n_stride, n, tile);
     unsigned npos = 0, nb = 0, cum_at_last = 0;
     int last_local = -1;
@@ -493,21 +557,22 @@ __global__ void __launch_bounds__(kCarryThreads) scan_carry_kernel(TileInfo* __r
 
 // phase 3: per-tile scan with carries; accumulates the AUROC integer and the AP partial sum; optionally writes the
 // compacted curve (fps, tps, thresholds) at distinct thresholds.
-template <bool kWriteCurve>
-__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const unsigned* __restrict__ keys,
+template <bool kWriteCurve, typename KeyT>
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const KeyT* __restrict__ keys,
                                                                   const unsigned char* __restrict__ labels, int n_stride,
                                                                   const int* __restrict__ seg_ignored,
                                                                   int tiles, const TileInfo* __restrict__ info,
                                                                   unsigned long long* __restrict__ auroc_acc /*[seg]*/,
                                                                   double* __restrict__ ap_partial /*[seg][tiles]*/,
                                                                   float* __restrict__ fps_out, float* __restrict__ tps_out,
-                                                                  float* __restrict__ thr_out, long long curve_stride) {
+                                                                  typename ThrOf<KeyT>::type* __restrict__ thr_out,
+                                                                  long long curve_stride) {
     __shared__ unsigned sm[8];
     __shared__ double dsum[8];
     __shared__ unsigned long long usum[8];
     const int seg = blockIdx.y, tile = blockIdx.x;
     const int n = seg_ignored ? n_stride - seg_ignored[seg] : n_stride;
-    ScanThreadData d;
+    ScanThreadData<KeyT> d;
     scan_load(d, keys + (size_t)seg * n_stride, labels + (size_t)seg * n_stride, n, tile);
     const TileInfo carry = info[(size_t)seg * tiles + tile];
 
@@ -646,6 +711,81 @@ __global__ void __launch_bounds__(256) scan_finalize_wide_kernel(const unsigned 
     }
 }
 
+// =====================================================================================================
+// weighted `_binary_clf_curve` (sample_weights; functional/classification/precision_recall_curve.py:64, 73-78):
+// keys sorted with the sample INDEX as payload, then one CTA walks the sorted order in chunks and emits, at every
+// distinct score, tps = cumsum(w * [t == pos]) and fps = cumsum(w * [t != pos]) accumulated in fp64 in a fixed order.
+// A private-API path of the reference (no public functional passes weights): built for exactness, not for speed.
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) pack_indexed_kernel(const T* __restrict__ preds, long long n,
+                                                           typename KeyOf<T>::type* __restrict__ keys,
+                                                           unsigned* __restrict__ idx) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        keys[i] = KeyOf<T>::make(preds[i]);
+        idx[i] = (unsigned)i;
+    }
+}
+
+constexpr int kWThreads = 1024;
+template <typename KeyT>
+__global__ void __launch_bounds__(kWThreads) weighted_curve_kernel(const KeyT* __restrict__ keys,
+                                                                   const unsigned* __restrict__ idx,
+                                                                   const void* __restrict__ target, int tdtype,
+                                                                   const double* __restrict__ weights, long long pos_label,
+                                                                   int n, double* __restrict__ fps_out,
+                                                                   double* __restrict__ tps_out,
+                                                                   typename ThrOf<KeyT>::type* __restrict__ thr_out,
+                                                                   long long* __restrict__ count_out) {
+    __shared__ double wsum[2][kWThreads / 32];
+    __shared__ unsigned wcnt[kWThreads / 32];
+    __shared__ double carry_p, carry_n;
+    __shared__ unsigned carry_b;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_p = 0.0, carry_n = 0.0, carry_b = 0u;
+    __syncthreads();
+    for (int base = 0; base < n; base += kWThreads) {
+        const int i = base + threadIdx.x;
+        double wp = 0.0, wn = 0.0;
+        unsigned end = 0u;
+        KeyT k = 0;
+        if (i < n) {
+            k = keys[i];
+            const unsigned src = idx[i];
+            const double w = weights[src];
+            const bool pos = load_label(target, tdtype, src) == pos_label;
+            wp = pos ? w : 0.0;
+            wn = pos ? 0.0 : w;
+            end = (i == n - 1 || keys[i + 1] != k) ? 1u : 0u;
+        }
+        // inclusive block scans of (wp, wn, end) in a fixed order
+        double ip = wp, in_ = wn;
+        unsigned ib = end;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double tp = __shfl_up_sync(kFull, ip, o), tn = __shfl_up_sync(kFull, in_, o);
+            const unsigned tb = __shfl_up_sync(kFull, ib, o);
+            if (lane >= o) ip += tp, in_ += tn, ib += tb;
+        }
+        if (lane == 31) wsum[0][warp] = ip, wsum[1][warp] = in_, wcnt[warp] = ib;
+        __syncthreads();
+        double op = carry_p, on = carry_n;
+        unsigned ob = carry_b;
+        for (int w = 0; w < warp; ++w) op += wsum[0][w], on += wsum[1][w], ob += wcnt[w];
+        ip += op, in_ += on, ib += ob;
+        if (end) {
+            const unsigned o = ib - 1u;
+            tps_out[o] = ip;
+            fps_out[o] = in_;
+            thr_out[o] = score_of_key(k);
+        }
+        __syncthreads();
+        if (threadIdx.x == kWThreads - 1) carry_p = ip, carry_n = in_, carry_b = ib;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count_out = (long long)carry_b;
+}
+
 __global__ void zero_u64_kernel(unsigned long long* p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 0ull;
@@ -720,7 +860,8 @@ extern "C" int mb200_curve_softmax_if_logits(const void* preds, int dtype, int64
         case MB200_F32: MB200_FMT(float) break;
         case MB200_F16: MB200_FMT(__half) break;
         case MB200_BF16: MB200_FMT(__nv_bfloat16) break;
-        default: set_error("softmax scores must be f32/f16/bf16 (dtype tag %d)", dtype); return MB200_ERR_INVALID;
+        case MB200_F64: MB200_FMT(double) break;
+        default: set_error("softmax scores must be f32/f16/bf16/f64 (dtype tag %d)", dtype); return MB200_ERR_INVALID;
     }
 #undef MB200_FMT
     count_launch();
@@ -728,17 +869,15 @@ extern "C" int mb200_curve_softmax_if_logits(const void* preds, int dtype, int64
     return check_cuda(cudaGetLastError(), "curve softmax launch");
 }
 
-extern "C" int64_t mb200_curve_workspace_bytes(int64_t segments, int64_t n) {
+static int64_t curve_workspace_bytes(int64_t segments, int64_t n, int key_bytes) {
     if (segments < 1 || n < 0) return -1;
-    const int64_t sort_tiles = (n + kSortTile - 1) / kSortTile;
     const int64_t scan_tiles = (n + kScanTile - 1) / kScanTile;
     int64_t b = 0;
-    b += segments * n * 4;                          // keys ping
-    b += segments * n * 4;                          // keys pong
+    b += segments * n * key_bytes + 256;            // keys ping
+    b += segments * n * key_bytes + 256;            // keys pong
     b += segments * n * 1 + 16;                     // labels ping
     b += segments * n * 1 + 16;                     // labels pong
-    b += (int64_t)radix_sort_scratch_words(n, segments, 4) * 4 + 256;  // digit histograms, look-back status, tickets
-    (void)sort_tiles;
+    b += (int64_t)radix_sort_scratch_words(n, segments, key_bytes) * 4 + 256;  // digit histograms, look-back status, tickets
     b += segments * (scan_tiles + 1) * (int64_t)sizeof(TileInfo);
     b += segments * 2 * 4;                          // seg_totals
     b += segments * 4 + 256;                        // seg_ignored (multilabel + ignore_index)
@@ -746,10 +885,15 @@ extern "C" int64_t mb200_curve_workspace_bytes(int64_t segments, int64_t n) {
     b += segments * (scan_tiles + 1) * 8;           // ap_partial
     return b + 16 * 256;                            // alignment slack
 }
+extern "C" int64_t mb200_curve_workspace_bytes(int64_t segments, int64_t n) { return curve_workspace_bytes(segments, n, 4); }
+extern "C" int64_t mb200_curve_workspace_bytes_for(int64_t segments, int64_t n, int preds_dtype) {
+    return curve_workspace_bytes(segments, n, preds_dtype == MB200_F64 ? 8 : 4);
+}
 
 namespace {
+template <typename KeyT>
 struct CurveWs {
-    unsigned *keys_a, *keys_b;
+    KeyT *keys_a, *keys_b;
     unsigned char *lab_a, *lab_b;
     unsigned *sort_scratch, *seg_totals;
     int* seg_ignored;
@@ -762,17 +906,16 @@ inline unsigned char* bump(unsigned char*& p, int64_t bytes) {
     p += (bytes + 255) / 256 * 256;
     return r;
 }
-CurveWs carve(void* workspace, int64_t segments, int64_t n) {
-    const int64_t sort_tiles = (n + kSortTile - 1) / kSortTile;
+template <typename KeyT>
+CurveWs<KeyT> carve(void* workspace, int64_t segments, int64_t n) {
     const int64_t scan_tiles = (n + kScanTile - 1) / kScanTile;
     unsigned char* p = reinterpret_cast<unsigned char*>(workspace);
-    CurveWs w;
-    w.keys_a = (unsigned*)bump(p, segments * n * 4);
-    w.keys_b = (unsigned*)bump(p, segments * n * 4);
+    CurveWs<KeyT> w;
+    w.keys_a = (KeyT*)bump(p, segments * n * (int64_t)sizeof(KeyT));
+    w.keys_b = (KeyT*)bump(p, segments * n * (int64_t)sizeof(KeyT));
     w.lab_a = bump(p, segments * n + 16);
     w.lab_b = bump(p, segments * n + 16);
-    w.sort_scratch = (unsigned*)bump(p, (int64_t)radix_sort_scratch_words(n, segments, 4) * 4);
-    (void)sort_tiles;
+    w.sort_scratch = (unsigned*)bump(p, (int64_t)radix_sort_scratch_words(n, segments, (int)sizeof(KeyT)) * 4);
     w.info = (TileInfo*)bump(p, segments * (scan_tiles + 1) * (int64_t)sizeof(TileInfo));
     w.seg_totals = (unsigned*)bump(p, segments * 2 * 4);
     w.seg_ignored = (int*)bump(p, segments * 4);
@@ -780,35 +923,35 @@ CurveWs carve(void* workspace, int64_t segments, int64_t n) {
     w.ap_partial = (double*)bump(p, segments * (scan_tiles + 1) * 8);
     return w;
 }
-}  // namespace
 
-namespace {
 // sort (keys_a/lab_a are clobbered; the sorted result lands back in them) + tie-collapsing scan + finalize
-int sort_and_scan(unsigned* keys_a, unsigned char* lab_a, const CurveWs& w, int ni, int64_t segments, int64_t n,
-                  const int* seg_ignored, float* out_auroc, float* out_ap, int64_t* out_counts, float* fps_out, float* tps_out, float* thr_out,
-                  uint32_t* err_flag, cudaStream_t st) {
+template <typename KeyT>
+int sort_and_scan(KeyT* keys_a, unsigned char* lab_a, const CurveWs<KeyT>& w, int ni, int64_t segments, int64_t n,
+                  const int* seg_ignored, float* out_auroc, float* out_ap, int64_t* out_counts, float* fps_out, float* tps_out,
+                  void* thr_out_v, uint32_t* err_flag, cudaStream_t st) {
+    using ThrT = typename ThrOf<KeyT>::type;
+    ThrT* thr_out = reinterpret_cast<ThrT*>(thr_out_v);
     const int scan_tiles = (ni + kScanTile - 1) / kScanTile;
-    // ---- 4 one-sweep radix passes (ping-pong; an even number of passes leaves the result in the *_a buffers) ----
+    // ---- one-sweep radix passes, one per key byte (ping-pong; an even number of passes leaves the result in *_a) ----
     {
-        const int where = radix_sort_passes<unsigned, unsigned char>(keys_a, lab_a, w.keys_b, w.lab_b, ni,
-                                                                     (int)segments, 4, w.sort_scratch, err_flag, st,
-                                                                     &count_launch);
+        const int where = radix_sort_passes<KeyT, unsigned char>(keys_a, lab_a, w.keys_b, w.lab_b, ni, (int)segments,
+                                                                 (int)sizeof(KeyT), w.sort_scratch, err_flag, st, &count_launch);
         if (where < 0) return check_cuda(cudaGetLastError(), "radix sort");
     }
-    unsigned* kin = keys_a;
+    KeyT* kin = keys_a;
     unsigned char* lin = lab_a;
 
     // ---- scan ----
     const dim3 sgrid((unsigned)scan_tiles, (unsigned)segments);
     zero_u64_kernel<<<(int)((segments + 255) / 256), 256, 0, st>>>(w.auroc_acc, (int)segments);
-    scan_reduce_kernel<<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, seg_ignored, scan_tiles, w.info);
+    scan_reduce_kernel<KeyT><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, seg_ignored, scan_tiles, w.info);
     scan_carry_kernel<<<(unsigned)segments, kCarryThreads, 0, st>>>(w.info, scan_tiles, ni, w.seg_totals);
     if (fps_out)
-        scan_apply_kernel<true><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, seg_ignored, scan_tiles, w.info, w.auroc_acc,
-                                                                w.ap_partial, fps_out, tps_out, thr_out, n);
+        scan_apply_kernel<true, KeyT><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, seg_ignored, scan_tiles, w.info, w.auroc_acc,
+                                                                      w.ap_partial, fps_out, tps_out, thr_out, n);
     else
-        scan_apply_kernel<false><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, seg_ignored, scan_tiles, w.info, w.auroc_acc,
-                                                                 w.ap_partial, nullptr, nullptr, nullptr, n);
+        scan_apply_kernel<false, KeyT><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, seg_ignored, scan_tiles, w.info, w.auroc_acc,
+                                                                       w.ap_partial, nullptr, nullptr, nullptr, n);
     if (scan_tiles > 256)
         scan_finalize_wide_kernel<<<(unsigned)segments, 256, 0, st>>>(w.auroc_acc, w.ap_partial, w.seg_totals, scan_tiles, ni,
                                                                       seg_ignored, out_auroc, out_ap,
@@ -818,6 +961,44 @@ int sort_and_scan(unsigned* keys_a, unsigned char* lab_a, const CurveWs& w, int 
                                                                         ni, seg_ignored, (int)segments, out_auroc, out_ap, reinterpret_cast<long long*>(out_counts));
     for (int i = 0; i < 5; ++i) count_launch();
     return check_cuda(cudaGetLastError(), "curve evaluate launch");
+}
+
+template <typename T>
+int evaluate_typed(const void* preds, const void* target, int target_dtype, int64_t n, int64_t segments, int64_t pos_label,
+                   void* workspace, float* out_auroc, float* out_ap, int64_t* out_counts, float* fps_out, float* tps_out,
+                   void* thr_out, uint32_t* err_flag, cudaStream_t st) {
+    using KeyT = typename KeyOf<T>::type;
+    CurveWs<KeyT> w = carve<KeyT>(workspace, segments, n);
+    const int ni = (int)n;
+    if (segments == 1) {
+        const int grid = blocks_for(n, 256 * 4, sm_count() * 8);
+        pack_binary_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, n, pos_label,
+                                                    w.keys_a, w.lab_a);
+    } else {
+        const dim3 grid((unsigned)((ni + 31) / 32), (unsigned)((segments + 31) / 32));
+        pack_ovr_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, ni, (int)segments,
+                                                 w.keys_a, w.lab_a);
+    }
+    count_launch();
+    return sort_and_scan<KeyT>(w.keys_a, w.lab_a, w, ni, segments, n, nullptr, out_auroc, out_ap, out_counts, fps_out, tps_out,
+                               thr_out, err_flag, st);
+}
+
+template <typename T>
+int evaluate_multilabel_typed(const void* preds, const void* target, int target_dtype, int64_t n, int64_t num_labels,
+                              int has_ignore, int64_t ignore_index, void* workspace, float* out_auroc, float* out_ap,
+                              int64_t* out_counts, float* fps_out, float* tps_out, void* thr_out, uint32_t* err_flag,
+                              cudaStream_t st) {
+    using KeyT = typename KeyOf<T>::type;
+    CurveWs<KeyT> w = carve<KeyT>(workspace, num_labels, n);
+    const int ni = (int)n;
+    if (has_ignore) MB200_CUDA_OK(cudaMemsetAsync(w.seg_ignored, 0, (size_t)num_labels * sizeof(int), st));
+    const dim3 grid((unsigned)((ni + 31) / 32), (unsigned)((num_labels + 31) / 32));
+    pack_multilabel_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, ni, (int)num_labels,
+                                                    has_ignore, (long long)ignore_index, w.keys_a, w.lab_a, w.seg_ignored);
+    count_launch();
+    return sort_and_scan<KeyT>(w.keys_a, w.lab_a, w, ni, num_labels, n, has_ignore ? w.seg_ignored : nullptr, out_auroc, out_ap,
+                               out_counts, fps_out, tps_out, thr_out, err_flag, st);
 }
 }  // namespace
 
@@ -829,49 +1010,28 @@ int sort_and_scan(unsigned* keys_a, unsigned char* lab_a, const CurveWs& w, int 
 extern "C" int mb200_curve_evaluate(const void* preds, int preds_dtype, const void* target, int target_dtype,
                                     int64_t n, int64_t num_classes, int64_t pos_label, void* workspace,
                                     int64_t workspace_bytes, float* out_auroc, float* out_ap, int64_t* out_counts,
-                                    float* fps_out, float* tps_out, float* thr_out, uint32_t* err_flag, void* stream) {
+                                    float* fps_out, float* tps_out, void* thr_out, uint32_t* err_flag, void* stream) {
     MB200_REQUIRE(n >= 1, "curve evaluation needs at least one sample (got %lld)", (long long)n);
     MB200_REQUIRE(n < (1ll << 30), "more than 2^30-1 samples per curve are not supported");
     MB200_REQUIRE(num_classes >= 1, "bad num_classes");
-    MB200_REQUIRE(n < (1ll << 31), "more than 2^31-1 samples per curve are not supported");
     MB200_REQUIRE(preds && target && workspace && out_auroc && out_ap && out_counts, "NULL pointer");
     const int64_t segments = num_classes;
-    MB200_REQUIRE(workspace_bytes >= mb200_curve_workspace_bytes(segments, n), "workspace too small");
+    MB200_REQUIRE(workspace_bytes >= mb200_curve_workspace_bytes_for(segments, n, preds_dtype), "workspace too small");
     MB200_REQUIRE((fps_out == nullptr) == (tps_out == nullptr) && (fps_out == nullptr) == (thr_out == nullptr),
                   "curve outputs must be given all together or not at all");
     MB200_REQUIRE(segments <= 65535, "at most 65535 curves per call");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CurveWs w = carve(workspace, segments, n);
-    const int ni = (int)n;
-    const int sort_tiles = (ni + kSortTile - 1) / kSortTile;
-    // ---- pack ----
-    if (segments == 1) {
-        const int grid = blocks_for(n, 256 * 4, sm_count() * 8);
-#define MB200_PACK(T) \
-    pack_binary_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, n, pos_label, w.keys_a, w.lab_a);
-        switch (preds_dtype) {
-            case MB200_F32: MB200_PACK(float) break;
-            case MB200_F16: MB200_PACK(__half) break;
-            case MB200_BF16: MB200_PACK(__nv_bfloat16) break;
-            default: set_error("scores must be f32/f16/bf16 (dtype tag %d)", preds_dtype); return MB200_ERR_UNSUPPORTED;
-        }
-#undef MB200_PACK
-    } else {
-        const dim3 grid((unsigned)((ni + 31) / 32), (unsigned)((segments + 31) / 32));
-#define MB200_PACK(T) \
-    pack_ovr_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, ni, (int)segments, w.keys_a, w.lab_a);
-        switch (preds_dtype) {
-            case MB200_F32: MB200_PACK(float) break;
-            case MB200_F16: MB200_PACK(__half) break;
-            case MB200_BF16: MB200_PACK(__nv_bfloat16) break;
-            default: set_error("scores must be f32/f16/bf16 (dtype tag %d)", preds_dtype); return MB200_ERR_UNSUPPORTED;
-        }
-#undef MB200_PACK
+#define MB200_EVAL(T)                                                                                                  \
+    return evaluate_typed<T>(preds, target, target_dtype, n, segments, pos_label, workspace, out_auroc, out_ap, out_counts, \
+                             fps_out, tps_out, thr_out, err_flag, st)
+    switch (preds_dtype) {
+        case MB200_F32: MB200_EVAL(float);
+        case MB200_F16: MB200_EVAL(__half);
+        case MB200_BF16: MB200_EVAL(__nv_bfloat16);
+        case MB200_F64: MB200_EVAL(double);
+        default: set_error("scores must be f32/f16/bf16/f64 (dtype tag %d)", preds_dtype); return MB200_ERR_UNSUPPORTED;
     }
-    count_launch();
-
-    return sort_and_scan(w.keys_a, w.lab_a, w, ni, segments, n, nullptr, out_auroc, out_ap, out_counts, fps_out, tps_out, thr_out,
-                         err_flag, st);
+#undef MB200_EVAL
 }
 
 // Exact-mode evaluation of `num_labels` independent binary curves (multilabel task).
@@ -881,33 +1041,26 @@ extern "C" int mb200_curve_evaluate(const void* preds, int preds_dtype, const vo
 extern "C" int mb200_curve_evaluate_multilabel(const void* preds, int preds_dtype, const void* target, int target_dtype,
                                                int64_t n, int64_t num_labels, int has_ignore, int64_t ignore_index,
                                                void* workspace, int64_t workspace_bytes, float* out_auroc, float* out_ap,
-                                               int64_t* out_counts, float* fps_out, float* tps_out, float* thr_out,
+                                               int64_t* out_counts, float* fps_out, float* tps_out, void* thr_out,
                                                uint32_t* err_flag, void* stream) {
     MB200_REQUIRE(n >= 1 && n < (1ll << 30), "curve evaluation needs 1 <= n < 2^30 samples (got %lld)", (long long)n);
     MB200_REQUIRE(num_labels >= 1 && num_labels <= 65535, "bad num_labels");
     MB200_REQUIRE(preds && target && workspace && out_auroc && out_ap && out_counts, "NULL pointer");
-    MB200_REQUIRE(workspace_bytes >= mb200_curve_workspace_bytes(num_labels, n), "workspace too small");
+    MB200_REQUIRE(workspace_bytes >= mb200_curve_workspace_bytes_for(num_labels, n, preds_dtype), "workspace too small");
     MB200_REQUIRE((fps_out == nullptr) == (tps_out == nullptr) && (fps_out == nullptr) == (thr_out == nullptr),
                   "curve outputs must be given all together or not at all");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CurveWs w = carve(workspace, num_labels, n);
-    const int ni = (int)n;
-    if (has_ignore) MB200_CUDA_OK(cudaMemsetAsync(w.seg_ignored, 0, (size_t)num_labels * sizeof(int), st));
-    const dim3 grid((unsigned)((ni + 31) / 32), (unsigned)((num_labels + 31) / 32));
-#define MB200_PACK(T)                                                                                              \
-    pack_multilabel_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, ni,   \
-                                                    (int)num_labels, has_ignore, (long long)ignore_index, w.keys_a, \
-                                                    w.lab_a, w.seg_ignored);
+#define MB200_EVAL(T)                                                                                                   \
+    return evaluate_multilabel_typed<T>(preds, target, target_dtype, n, num_labels, has_ignore, ignore_index, workspace, \
+                                        out_auroc, out_ap, out_counts, fps_out, tps_out, thr_out, err_flag, st)
     switch (preds_dtype) {
-        case MB200_F32: MB200_PACK(float) break;
-        case MB200_F16: MB200_PACK(__half) break;
-        case MB200_BF16: MB200_PACK(__nv_bfloat16) break;
-        default: set_error("scores must be f32/f16/bf16 (dtype tag %d)", preds_dtype); return MB200_ERR_UNSUPPORTED;
+        case MB200_F32: MB200_EVAL(float);
+        case MB200_F16: MB200_EVAL(__half);
+        case MB200_BF16: MB200_EVAL(__nv_bfloat16);
+        case MB200_F64: MB200_EVAL(double);
+        default: set_error("scores must be f32/f16/bf16/f64 (dtype tag %d)", preds_dtype); return MB200_ERR_UNSUPPORTED;
     }
-#undef MB200_PACK
-    count_launch();
-    return sort_and_scan(w.keys_a, w.lab_a, w, ni, num_labels, n, has_ignore ? w.seg_ignored : nullptr, out_auroc, out_ap,
-                         out_counts, fps_out, tps_out, thr_out, err_flag, st);
+#undef MB200_EVAL
 }
 
 // Class-major keys of [n, num_classes] scores: keys_out [num_classes][n] (the packing step of mb200_curve_evaluate on
@@ -939,11 +1092,65 @@ extern "C" int mb200_curve_evaluate_keys(uint32_t* keys, const void* target, int
     MB200_REQUIRE(keys && target && workspace && out_auroc && out_ap && out_counts, "NULL pointer");
     MB200_REQUIRE(workspace_bytes >= mb200_curve_workspace_bytes(segments, n), "workspace too small");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CurveWs w = carve(workspace, segments, n);
+    CurveWs<unsigned> w = carve<unsigned>(workspace, segments, n);
     const long long total = n * segments;
     labels_from_target_kernel<<<blocks_for(total, 256 * 8, sm_count() * 8), 256, 0, st>>>(target, target_dtype, (int)n,
                                                                                           (int)segments, first_class, w.lab_a);
     count_launch();
-    return sort_and_scan(keys, w.lab_a, w, (int)n, segments, n, nullptr, out_auroc, out_ap, out_counts, nullptr, nullptr, nullptr,
-                         err_flag, st);
+    return sort_and_scan<unsigned>(keys, w.lab_a, w, (int)n, segments, n, nullptr, out_auroc, out_ap, out_counts, nullptr, nullptr,
+                                   nullptr, err_flag, st);
+}
+
+namespace {
+template <typename T>
+int weighted_typed(const void* preds, const void* target, int target_dtype, const double* weights, int64_t n,
+                   int64_t pos_label, void* workspace, double* fps_out, double* tps_out, void* thr_out, int64_t* count_out,
+                   uint32_t* err_flag, cudaStream_t st) {
+    using KeyT = typename KeyOf<T>::type;
+    unsigned char* p = reinterpret_cast<unsigned char*>(workspace);
+    KeyT* keys_a = (KeyT*)bump(p, n * (int64_t)sizeof(KeyT));
+    KeyT* keys_b = (KeyT*)bump(p, n * (int64_t)sizeof(KeyT));
+    unsigned* idx_a = (unsigned*)bump(p, n * 4);
+    unsigned* idx_b = (unsigned*)bump(p, n * 4);
+    unsigned* scratch = (unsigned*)bump(p, (int64_t)radix_sort_scratch_words(n, 1, (int)sizeof(KeyT)) * 4);
+    pack_indexed_kernel<T><<<blocks_for(n, 256 * 4, sm_count() * 8), 256, 0, st>>>(reinterpret_cast<const T*>(preds), n, keys_a,
+                                                                                  idx_a);
+    count_launch();
+    const int where = radix_sort_passes<KeyT, unsigned>(keys_a, idx_a, keys_b, idx_b, (int)n, 1, (int)sizeof(KeyT), scratch,
+                                                        err_flag, st, &count_launch);
+    if (where < 0) return check_cuda(cudaGetLastError(), "radix sort");
+    weighted_curve_kernel<KeyT><<<1, kWThreads, 0, st>>>(keys_a, idx_a, target, target_dtype, weights, (long long)pos_label,
+                                                         (int)n, fps_out, tps_out,
+                                                         reinterpret_cast<typename ThrOf<KeyT>::type*>(thr_out),
+                                                         reinterpret_cast<long long*>(count_out));
+    count_launch();
+    return check_cuda(cudaGetLastError(), "weighted curve launch");
+}
+}  // namespace
+
+extern "C" int64_t mb200_curve_weighted_workspace_bytes(int64_t n, int preds_dtype) {
+    if (n < 0) return -1;
+    const int kb = preds_dtype == MB200_F64 ? 8 : 4;
+    return 2 * (n * kb + 256) + 2 * (n * 4 + 256) + (int64_t)radix_sort_scratch_words(n, 1, kb) * 4 + 8 * 256;
+}
+
+extern "C" int mb200_curve_weighted_clf_curve(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                              const double* weights, int64_t n, int64_t pos_label, void* workspace,
+                                              int64_t workspace_bytes, double* fps_out, double* tps_out, void* thr_out,
+                                              int64_t* count_out, uint32_t* err_flag, void* stream) {
+    MB200_REQUIRE(n >= 1 && n < (1ll << 30), "curve evaluation needs 1 <= n < 2^30 samples (got %lld)", (long long)n);
+    MB200_REQUIRE(preds && target && weights && workspace && fps_out && tps_out && thr_out && count_out, "NULL pointer");
+    MB200_REQUIRE(workspace_bytes >= mb200_curve_weighted_workspace_bytes(n, preds_dtype), "workspace too small");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define MB200_W(T)                                                                                                       \
+    return weighted_typed<T>(preds, target, target_dtype, weights, n, pos_label, workspace, fps_out, tps_out, thr_out,  \
+                             count_out, err_flag, st)
+    switch (preds_dtype) {
+        case MB200_F32: MB200_W(float);
+        case MB200_F16: MB200_W(__half);
+        case MB200_BF16: MB200_W(__nv_bfloat16);
+        case MB200_F64: MB200_W(double);
+        default: set_error("scores must be f32/f16/bf16/f64 (dtype tag %d)", preds_dtype); return MB200_ERR_UNSUPPORTED;
+    }
+#undef MB200_W
 }

@@ -43,12 +43,18 @@ def _binary_clf_curve(
 ) -> tuple[Tensor, Tensor, Tensor]:
     """``fps, tps, thresholds`` at every distinct score, descending (reference :30-82).  All three are float32 with
     integer-valued counts, exactly like the reference's ``cumsum(target * 1.0)``."""
-    if sample_weights is not None:
-        raise NotImplementedError("metrics_b200: `sample_weights` is not supported by the curve kernels")
     if preds.ndim > target.ndim:
         preds = preds[:, 0]
     if preds.numel() == 0:
         raise IndexError("metrics_b200: cannot compute a curve from zero samples")
+    if sample_weights is not None:  # reference :45-46, :64, :73-78
+        if not isinstance(sample_weights, Tensor):
+            sample_weights = torch.tensor(sample_weights, device=preds.device, dtype=torch.float)
+        fps, tps, thr = _native.curve_weighted_clf_curve(preds, target, sample_weights.to(preds.device), pos_label)
+        out_dtype = torch.result_type(torch.zeros((), dtype=torch.long), sample_weights)  # `target * weight`
+        if preds.dtype not in (torch.float32, torch.float64):
+            thr = thr.to(preds.dtype)
+        return fps.to(out_dtype), tps.to(out_dtype), thr
     _, _, counts, (fps, tps, thr) = _native.curve_evaluate(preds, target, 1, pos_label, want_curve=True)
     n_thr = int(counts[0, 2])  # data-dependent output size -> one host sync (the reference syncs in `torch.where`)
     thr = thr[0, :n_thr]

@@ -13,6 +13,7 @@ Replaces the per-state ``barrier + all_gather(shape) + all_gather(data)`` of the
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Dict, List, Optional
 
 import torch
@@ -56,7 +57,10 @@ def _peer_all_reduce(parts: List[Tensor], dtype: torch.dtype, op: Any, group: An
     bucket in the group's symmetric workspace, reduces ITS slice of all ranks' buckets with peer loads and stores the
     reduced slice into every rank with peer stores — bit-exact like the NCCL all-reduce it replaces.  None = not applicable
     (small bucket, other dtype, CPU / non-NCCL group, peer memory unavailable): the caller uses NCCL."""
-    if dtype != torch.int64 or not parts[0].is_cuda:
+    if dtype != torch.int64 or not parts[0].is_cuda or os.environ.get("MB200_PEER_ALLREDUCE", "0") != "1":
+        # opt-in: measured on 2 x B200 (profiles/r02_sync_2gpu.json) the 8 MB bucket takes 80 us this way (three launches,
+        # two signal barriers, 63 us of host time) against 58 us for NCCL's all-reduce — a plain reduction has no compute to
+        # fuse with, so NCCL stays the default; the fused pack + put of the curve exchange is where peer stores pay.
         return None
     n = sum(p.numel() for p in parts)
     if n * 8 < _PEER_MIN_BYTES:

@@ -34,14 +34,18 @@ def softmax_if_logits(preds: np.ndarray) -> np.ndarray:
     return (e / e.sum(axis=1, keepdims=True, dtype=np.float32)).astype(preds.dtype)
 
 
-def binary_clf_curve(preds: np.ndarray, target: np.ndarray, pos_label: int = 1):
+def binary_clf_curve(preds: np.ndarray, target: np.ndarray, pos_label: int = 1, sample_weights: Optional[np.ndarray] = None):
     """_binary_clf_curve (functional/classification/precision_recall_curve.py:30-82).
-    Returns integer fps, tps (int64) and thresholds (preds dtype), thresholds descending."""
+    Returns integer fps, tps (int64) and thresholds (preds dtype), thresholds descending; with `sample_weights` (:64, :73-78)
+    fps / tps are float64 weighted cumulative sums.  float64 scores are compared as float64 (no down-cast anywhere)."""
     order = np.argsort(-preds.astype(np.float64), kind="stable")  # :60 argsort(descending=True)
     p = preds[order]
     t = (target[order] == pos_label).astype(np.int64)  # :72
     distinct = np.nonzero(p[1:] - p[:-1])[0]  # :70
     idx = np.concatenate([distinct, [t.size - 1]])  # :71
+    if sample_weights is not None:
+        w = np.asarray(sample_weights, dtype=np.float64)[order]  # :64
+        return np.cumsum((1 - t) * w)[idx], np.cumsum(t * w)[idx], p[idx]  # :73, :78
     tps = np.cumsum(t)[idx]  # :73
     fps = 1 + idx - tps  # :80
     return fps.astype(np.int64), tps.astype(np.int64), p[idx]

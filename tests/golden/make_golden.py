@@ -1244,11 +1244,102 @@ def csi_golden() -> dict:
     return out
 
 
+def curves64_golden() -> dict:
+    """float64 scores through the exact curve functionals (the reference sorts them as doubles) and `_binary_clf_curve`
+    with `sample_weights` (functional/classification/precision_recall_curve.py:30-82).  Scores are built so that pairs differ
+    ONLY below float32 resolution: a float32 sort would merge their thresholds."""
+    import torchmetrics.functional.classification as RF
+    from torchmetrics.functional.classification.precision_recall_curve import _binary_clf_curve
+
+    g = torch.Generator().manual_seed(6464)
+    out = {}
+
+    def flat(res):
+        parts = []
+        for part in (res if isinstance(res, (tuple, list)) else [res]):
+            parts.extend(part if isinstance(part, (tuple, list)) else [part])
+        return parts
+
+    def put(key, preds, target, res, **meta):
+        out[f"{key}/preds"], out[f"{key}/target"] = preds.numpy(), target.numpy()
+        parts = flat(res)
+        out[f"{key}/n_out"] = np.array(len(parts))
+        for i, t in enumerate(parts):
+            out[f"{key}/out{i}"] = t.numpy()
+        for k, v in meta.items():
+            out[f"{key}/{k}"] = np.array(v)
+
+    case = 0
+    # binary, probabilities and logits, with sub-float32 perturbations and exact ties
+    for n, logits in ((257, False), (4099, True), (20000, False)):
+        base = torch.rand(n, generator=g, dtype=torch.float64)
+        base[::3] = base[::3].float().double()                      # exactly representable in float32
+        base[1::3] = base[::3][: base[1::3].numel()] + 1e-12        # differs from its neighbour below float32 resolution
+        base[5::7] = base[4::7][: base[5::7].numel()]               # exact ties
+        preds = (base * 8 - 4) if logits else base.clamp(0, 1)
+        target = torch.randint(0, 2, (n,), generator=g)
+        for fn in ("binary_roc", "binary_precision_recall_curve", "binary_auroc", "binary_average_precision"):
+            put(f"case{case}", preds, target, getattr(RF, fn)(preds, target, thresholds=None), fn=fn, num_classes=0)
+            case += 1
+    # multiclass one-vs-rest
+    for n, c in ((300, 5), (1500, 37)):
+        lg = torch.randn(n, c, generator=g, dtype=torch.float64)
+        lg[1::2] = lg[::2][: lg[1::2].shape[0]] + 1e-13
+        target = torch.randint(0, c, (n,), generator=g)
+        for fn in ("multiclass_roc", "multiclass_precision_recall_curve", "multiclass_auroc", "multiclass_average_precision"):
+            kw = dict(num_classes=c, thresholds=None)
+            if "auroc" in fn or "average_precision" in fn:
+                kw["average"] = None
+            put(f"case{case}", lg, target, getattr(RF, fn)(lg, target, **kw), fn=fn, num_classes=c)
+            case += 1
+    # multilabel
+    for n, l in ((400, 4),):
+        pr = torch.rand(n, l, generator=g, dtype=torch.float64)
+        pr[1::2] = (pr[::2][: pr[1::2].shape[0]] + 1e-13).clamp(0, 1)
+        target = torch.randint(0, 2, (n, l), generator=g)
+        for fn in ("multilabel_roc", "multilabel_precision_recall_curve", "multilabel_auroc", "multilabel_average_precision"):
+            kw = dict(num_labels=l, thresholds=None)
+            if "auroc" in fn or "average_precision" in fn:
+                kw["average"] = None
+            put(f"case{case}", pr, target, getattr(RF, fn)(pr, target, **kw), fn=fn, num_classes=l)
+            case += 1
+    out["n_cases"] = np.array(case)
+    # sample weights through the private helper (no public functional forwards them)
+    wcase = 0
+    for n, pdt, wdt in ((64, torch.float32, torch.float32), (1000, torch.float32, torch.float64), (5000, torch.float64, torch.float32),
+                        (333, torch.float16, torch.float32)):
+        preds = (torch.rand(n, generator=g, dtype=torch.float64) * 16).round() / 16 if n < 2000 else torch.rand(n, generator=g, dtype=torch.float64)
+        preds = preds.to(pdt)
+        target = torch.randint(0, 3, (n,), generator=g)
+        weights = (torch.rand(n, generator=g, dtype=torch.float64) * 3).to(wdt)
+        for pos in (1, 2):
+            fps, tps, thr = _binary_clf_curve(preds, target, sample_weights=weights, pos_label=pos)
+            key = f"w{wcase}"
+            out[f"{key}/preds"] = preds.float().numpy() if pdt == torch.float16 else preds.numpy()
+            out[f"{key}/half"] = np.array(pdt == torch.float16)
+            out[f"{key}/target"], out[f"{key}/weights"], out[f"{key}/pos"] = target.numpy(), weights.numpy(), np.array(pos)
+            out[f"{key}/fps"], out[f"{key}/tps"] = fps.numpy(), tps.numpy()
+            out[f"{key}/thr"] = thr.float().numpy() if pdt == torch.float16 else thr.numpy()
+            wcase += 1
+    # weights given as a python list (reference :45-46 converts to float32)
+    preds = torch.tensor([0.1, 0.4, 0.35, 0.8, 0.4])
+    target = torch.tensor([0, 0, 1, 1, 1])
+    fps, tps, thr = _binary_clf_curve(preds, target, sample_weights=[1.0, 2.0, 0.5, 1.5, 1.0])
+    out["wlist/fps"], out["wlist/tps"], out["wlist/thr"] = fps.numpy(), tps.numpy(), thr.numpy()
+    out["n_weighted"] = np.array(wcase)
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["classification"]
     if "classification" in which:
         data = classification_golden()
         path = os.path.join(HERE, "classification.npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
+    if "curves64" in which:
+        data = curves64_golden()
+        path = os.path.join(HERE, "curves64.npz")
         np.savez_compressed(path, **data)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
     if "binned" in which:

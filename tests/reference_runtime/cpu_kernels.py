@@ -133,8 +133,9 @@ def softmax_if_logits(preds: Tensor) -> Tensor:
 def _one_curve(scores: Tensor, positive: Tensor, n_pad: int):
     """Tie-collapsed descending curve of one binary problem: auroc, ap, counts row, padded (fps, tps, thr)."""
     n = scores.numel()
-    order = torch.argsort(scores.float(), descending=True, stable=True)
-    s, y = scores[order].float(), positive[order].long()
+    cmp = scores if scores.dtype == torch.float64 else scores.float()  # float64 scores keep all their bits (64-bit keys)
+    order = torch.argsort(cmp, descending=True, stable=True)
+    s, y = cmp[order], positive[order].long()
     is_end = torch.ones(n, dtype=torch.bool)
     if n > 1:
         is_end[:-1] = s[1:] != s[:-1]
@@ -150,14 +151,22 @@ def _one_curve(scores: Tensor, positive: Tensor, n_pad: int):
     else:
         ap = -0.0
     pad = torch.zeros(n_pad)
-    f, t, h = pad.clone(), pad.clone(), pad.clone()
+    f, t, h = pad.clone(), pad.clone(), torch.zeros(n_pad, dtype=s.dtype)
     f[: idx.numel()], t[: idx.numel()], h[: idx.numel()] = fps.float(), tps.float(), s[idx]
     return auroc, ap, [P, N, int(idx.numel())], f, t, h
 
 
+def curve_weighted_clf_curve(preds: Tensor, target: Tensor, weights: Tensor, pos_label: int = 1):
+    cmp = preds if preds.dtype == torch.float64 else preds.float()
+    order = torch.argsort(cmp, descending=True, stable=True)
+    s, y, w = cmp[order], (target[order] == pos_label).double(), weights.double()[order]
+    is_end = torch.ones(s.numel(), dtype=torch.bool)
+    is_end[:-1] = s[1:] != s[:-1]
+    idx = torch.nonzero(is_end).flatten()
+    return torch.cumsum((1 - y) * w, 0)[idx], torch.cumsum(y * w, 0)[idx], s[idx]
+
+
 def curve_evaluate(preds: Tensor, target: Tensor, num_classes: int = 1, pos_label: int = 1, want_curve: bool = False):
-    if preds.dtype == torch.float64:
-        raise NotImplementedError("metrics_b200: float64 scores are not supported by the exact curve kernels; cast to float32")
     n = target.numel()
     rows = []
     for c in range(num_classes):
@@ -174,8 +183,6 @@ def curve_evaluate(preds: Tensor, target: Tensor, num_classes: int = 1, pos_labe
 
 def curve_evaluate_multilabel(preds: Tensor, target: Tensor, num_labels: int, ignore_index: Optional[int] = None,
                               want_curve: bool = False):
-    if preds.dtype == torch.float64:
-        raise NotImplementedError("metrics_b200: float64 scores are not supported by the exact curve kernels; cast to float32")
     n = preds.shape[0]
     rows = []
     for l in range(num_labels):
@@ -322,7 +329,7 @@ def coco_map_evaluate(det_box, det_score, det_label, det_counts, gt_box, gt_labe
 NAMES = ("launch_count", "multiclass_confmat_update_", "multiclass_stat_scores_update_",
          "multiclass_stat_scores_topk_update_", "multiclass_stat_scores_samplewise", "argmax_rows",
          "sigmoid_if_logits", "softmax_if_logits", "curve_evaluate", "curve_evaluate_multilabel",
-         "binary_stat_counts", "regression_sums", "binned_curve_update", "coco_map_evaluate")
+         "binary_stat_counts", "regression_sums", "binned_curve_update", "coco_map_evaluate", "curve_weighted_clf_curve")
 
 
 def standins() -> dict:

@@ -155,10 +155,20 @@ def test_every_kernel_wrapper_calls_the_abi_as_declared(monkeypatch):
     _native.coco_map_evaluate(boxes, torch.rand(4), torch.zeros(4, dtype=torch.long), [2, 2], boxes, torch.zeros(4, dtype=torch.long),
                               torch.zeros(4, dtype=torch.uint8), torch.ones(4), [2, 2], torch.zeros(1, dtype=torch.long), False,
                               [0.5, 0.75], [0.0, 0.5, 1.0], [1, 10, 100])
+    _native.curve_weighted_clf_curve(scores[:, 0].double(), labels.clamp(max=1), torch.rand(n), 1)
+    # K10: the peer-memory exchange wrappers live on the workspace object (metrics_b200/peer.py); drive them on a bare one
+    from metrics_b200 import peer
+
+    ws = peer.PeerWorkspace.__new__(peer.PeerWorkspace)
+    ws.device, ws.nbytes, ws.world, ws.rank, ws.table = cpu, 1 << 20, 2, 0, 0x1000
+    ws.put_all(labels, 256)
+    ws.pack_keys_put(scores, 2, 2 * n, n, 0)
+    ws.reduce_put_i64(0, 4096, 100, 0)
     assert _native.launch_count() == 0
 
     # (`mb200_regression_num_sums` is a query for C callers; the Python mirror knows the layout of each op's sums)
-    kernels = {k for k in _native.SIGNATURES if k not in ("mb200_abi_version", "mb200_last_error", "mb200_regression_num_sums")}
+    kernels = {k for k in _native.SIGNATURES if k not in ("mb200_abi_version", "mb200_last_error", "mb200_regression_num_sums",
+                                                          "mb200_curve_workspace_bytes")}
     never_called = sorted(kernels - set(fake.calls))
     assert not never_called, f"no wrapper exercised: {never_called}"
     for name, calls in fake.calls.items():

@@ -1,31 +1,69 @@
 """GPU: the second, larger randomised differential draw (tests/golden/fuzz2.npz, 394 cases from the unmodified reference,
-make_golden.py fuzz2) through the kernels.  The very last file on purpose: it was generated after the round's GPU budget was
-spent and has so far only been replayed on the kernel stand-ins (tests/test_fuzz_host.py::test_second_draw).
+make_golden.py fuzz2) through the kernels.
 
-float32 / float64 / integer inputs must meet the same bars as the first draw.  Half-precision inputs (whose tolerances in
-tests/fuzz_cases.py were tuned on the first draw only) are reported as `xfail` instead of failing when they miss them, so that
-an untriaged rounding corner shows up in the report without masking the rest of the run."""
+Every case must meet the golden outputs, which the reference produced ON CPU.  One class of cases cannot: exact curves list
+one point per DISTINCT score, and the reference itself yields a different number of distinct scores on CPU and on CUDA when two
+logits' float32 sigmoids / softmaxes differ by one ulp on one device and coincide on the other (ATen's vectorised CPU `exp`
+and CUDA's `expf` round differently).  For those — and only for a curve case whose LENGTH differs from the golden — the
+arbiter is the reference executed on the SAME B200: the unmodified reference from baseline/_ref when it travelled with the
+repo, else its op chain restated in oracle/torch_cpu_chain.py (checked bit-exactly against the reference on CPU by
+tests/test_cpu_chain.py).  Lengths must then agree exactly and values within the case's tolerance: no xfail is left."""
 import json
+import os
+import sys
+import warnings
 
+import numpy as np
 import pytest
+import torch
 
-from tests.fuzz_cases import n_cases, run_case
+from tests.fuzz_cases import _DT, _flatten, n_cases, run_case
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CURVES = ("binary_roc", "binary_precision_recall_curve", "multiclass_roc", "multiclass_precision_recall_curve")
+
+
+def reference_on_device(fn: str, preds: torch.Tensor, target: torch.Tensor, kwargs: dict):
+    """The reference's result for a curve functional on the tensors' own device."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref_dir, "torchmetrics")):
+        for p in (os.path.join(ROOT, "tests", "golden", "_standins"), ref_dir):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        import torchmetrics.functional.classification as RF
+
+        return _flatten(getattr(RF, fn)(preds, target, **kwargs)), "baseline/_ref"
+    from oracle.torch_cpu_chain import exact_curve_functional_chain
+
+    assert kwargs.get("thresholds") is None and kwargs.get("average") is None
+    return _flatten(exact_curve_functional_chain(fn, preds, target, num_classes=kwargs.get("num_classes"),
+                                                 ignore_index=kwargs.get("ignore_index"))), "op-chain port"
 
 
 @pytest.mark.parametrize("k", range(n_cases("fuzz2")))
 def test_case(golden_fuzz2, k):
     spec = json.loads(str(golden_fuzz2[f"{k}/spec"]))
-    half = spec["preds_dtype"] in ("float16", "bfloat16")
-    # exact curves list one point per DISTINCT score: two logits whose float32 sigmoids differ by one ulp on one device and
-    # coincide on the other change the number of points (the reference's own CPU and CUDA results differ the same way)
-    curve = any(token in spec["fn"] for token in ("roc", "curve"))
     try:
         run_case(golden_fuzz2, k, "cuda:0")
+        return
     except AssertionError as err:
-        if half:
-            pytest.xfail(f"half-precision case outside the first draw's tolerances, to triage: {str(err)[:300]}")
-        if curve and "shape" in str(err).lower():
-            pytest.xfail(f"different number of distinct thresholds (1-ulp sigmoid / softmax ties), to triage: {str(err)[:300]}")
-        raise
+        if not (spec["fn"] in _CURVES and "shape mismatch" in str(err)):
+            raise
+    # a curve whose number of distinct thresholds differs from the CPU golden: the reference on this device decides
+    import metrics_b200.functional.classification as F_cls
+
+    pdt = _DT[spec["preds_dtype"]]
+    preds = torch.from_numpy(golden_fuzz2[f"{k}/preds"]).to("cuda:0").to(pdt)
+    target = torch.from_numpy(golden_fuzz2[f"{k}/target"]).to("cuda:0")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = _flatten(getattr(F_cls, spec["fn"])(preds, target, **spec["kwargs"]))
+        want, source = reference_on_device(spec["fn"], preds, target, spec["kwargs"])
+    assert len(got) == len(want)
+    half = pdt in (torch.float16, torch.bfloat16)
+    rtol, atol = (4e-3, 1e-3) if half else (1e-6, 1e-7)
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert a.shape == b.shape, f"{spec['fn']} out{i}: {tuple(a.shape)} vs the reference on CUDA ({source}) {tuple(b.shape)}"
+        np.testing.assert_allclose(a.float().cpu().numpy(), b.float().cpu().numpy(), rtol=rtol, atol=atol, equal_nan=True,
+                                   err_msg=f"{spec['fn']} out{i} vs the reference on CUDA ({source})")
