@@ -293,6 +293,20 @@ MB200_API int mb200_binned_curve_update_multilabel(const void* preds, int preds_
                                                    int64_t* confmat, uint64_t* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K11 — collection-level fusion (csrc/fused.cu): one pass over a shared [n, num_classes] batch for a multiclass stat-scores
+ * metric AND an exact-mode multiclass curve metric of the same MetricCollection (collections.py:231-262 hands the batch to
+ * every member; stat_scores.py:328-448 then runs argmax -> bincount and utilities/compute.py:190-229 the range vote + softmax).
+ * tp/fp/tn/fn/workspace: as mb200_multiclass_stat_scores_update (top-1, global, no ignore_index).  probs_out [n, num_classes]
+ * (same dtype as preds) receives what `normalize_logits_if_needed(preds, "softmax")` returns: the softmax when any score of
+ * the batch lies outside [0, 1], else the scores themselves; logits_flag (device word, overwritten) holds that vote.
+ * num_classes <= 1024 (a warp keeps a row in registers).
+ * ------------------------------------------------------------------------------------------------ */
+MB200_API int mb200_multiclass_stats_softmax_update(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                                    int64_t n, int64_t num_classes, int micro, int64_t* tp, int64_t* fp,
+                                                    int64_t* tn, int64_t* fn, int64_t* workspace, void* probs_out,
+                                                    uint32_t* logits_flag, uint32_t* err_flag, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K10 — cross-rank state exchange over NVLink peer memory (csrc/peer.cu).  One process per GPU; `peer_bases` is a DEVICE
  * array of `world` base pointers of one symmetric allocation (entry r = rank r's base, peer-mapped into this process).
  * Replaces the per-state `barrier + all_gather(shape) + all_gather(data)` of Metric._sync_dist / gather_all_tensors

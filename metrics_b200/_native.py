@@ -100,6 +100,7 @@ SIGNATURES = {
     "mb200_binned_curve_scratch_words": ("q", "qq"),
     "mb200_binned_curve_update": ("i", "pipiqqpqppp"),
     "mb200_binned_curve_update_multilabel": ("i", "pipiqqpqppp"),
+    "mb200_multiclass_stats_softmax_update": ("i", "pipiqqippppppppp"),
     "mb200_peer_pack_keys_put": ("i", "piqqqiqqpqp"),
     "mb200_peer_put_all": ("i", "pqpqip"),
     "mb200_peer_reduce_put_i64": ("i", "pqqqiiip"),
@@ -271,6 +272,26 @@ def multiclass_stat_scores_update_(
         )
     if rc:
         check(rc, "multiclass_stat_scores_update")
+
+
+def multiclass_stats_softmax_update_(tp: Tensor, fp: Tensor, tn: Tensor, fn: Tensor, workspace: Tensor, preds: Tensor,
+                                     target: Tensor, num_classes: int, micro: bool, err_flag: Optional[Tensor] = None) -> Tensor:
+    """K11 (``mb200_multiclass_stats_softmax_update``): in-place tp/fp/tn/fn accumulation AND the batch's
+    ``normalize_logits_if_needed(preds, "softmax")`` from one read of ``preds [N, C]``; returns the probabilities."""
+    dev = require_cuda(tp, workspace, preds, target)
+    preds = preds.contiguous()
+    target = target.contiguous()
+    probs = torch.empty_like(preds)
+    st = stream_handle(dev)
+    with on_device(dev):
+        rc = lib().mb200_multiclass_stats_softmax_update(
+            preds.data_ptr(), tag(preds), target.data_ptr(), tag(target), preds.shape[0], int(num_classes), bool(micro),
+            tp.data_ptr(), fp.data_ptr(), tn.data_ptr(), fn.data_ptr(), workspace.data_ptr(), probs.data_ptr(),
+            _flag_scratch(dev, st).data_ptr(), None if err_flag is None else err_flag.data_ptr(), st,
+        )
+    if rc:
+        check(rc, "multiclass_stats_softmax_update")
+    return probs
 
 
 def argmax_rows(preds: Tensor) -> Tensor:

@@ -8,6 +8,7 @@ returns after the first state it looks at); groups are therefore never coarser t
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 from collections.abc import Hashable, Iterable, Iterator, Mapping, Sequence
 from copy import deepcopy
@@ -99,7 +100,10 @@ class MetricCollection(ModuleDict):
         if self._groups_checked:
             for name in self.keys(keep_base=True):
                 self._modules[str(name)]._computed = None  # invalidate every member's cached result
+            fused = self._fused_update(args, kwargs)
             for members in self._groups.values():
+                if members[0] in fused:
+                    continue
                 leader = self._modules[members[0]]
                 leader.update(*args, **leader._filter_kwargs(**kwargs))
             if self._state_is_copy:
@@ -113,6 +117,64 @@ class MetricCollection(ModuleDict):
             self._merge_compute_groups()
             self._compute_groups_create_state_ref()
             self._groups_checked = True
+
+    def _fused_update(self, args: tuple, kwargs: dict) -> tuple:
+        """Collection-level fusion (csrc/fused.cu, K11): when one group leader is a multiclass stat-scores metric and another
+        an exact-mode multiclass curve metric over the same classes, ONE kernel reads the shared batch once and feeds both —
+        the argmax counts of the first and the `normalize_logits_if_needed` probabilities the second keeps as its list state
+        (the reference hands the batch to every member: collections.py:231-262).  Returns the names of the leaders served."""
+        if len(args) != 2 or kwargs or os.environ.get("MB200_COLLECTION_FUSION", "1") == "0":
+            return ()
+        preds, target = args
+        if not (isinstance(preds, Tensor) and isinstance(target, Tensor) and preds.is_cuda and preds.ndim == 2
+                and target.ndim == 1 and preds.dtype in (torch.float32, torch.float16, torch.bfloat16)
+                and not target.is_floating_point() and target.shape[0] == preds.shape[0] and preds.shape[0] > 0):
+            return ()
+        plan = self._fusion_plan()
+        if plan is None or preds.shape[1] != plan[2]:
+            return ()
+        from metrics_b200 import _native
+
+        stats, curve = self._modules[plan[0]], self._modules[plan[1]]
+        for member in (stats, curve):  # what Metric._wrap_update does around a member's own update()
+            member._computed = None
+            member._update_count += 1
+        curve._group_cache.clear()
+        probs = _native.multiclass_stats_softmax_update_(
+            stats.tp, stats.fp, stats.tn, stats.fn, stats._workspace(plan[2], stats.tp.device), preds, target, plan[2],
+            stats.average == "micro")
+        curve.preds.append(probs)
+        curve.target.append(target)
+        if curve.compute_on_cpu:
+            curve._move_list_states_to_cpu()
+        return plan[:2]
+
+    def _fusion_plan(self) -> Optional[tuple]:
+        """(stat-scores leader, curve leader, num_classes) or None; decided once per grouping."""
+        cached = self.__dict__.get("_fusion_plan_cache")
+        if cached is not None and cached[0] == id(self._groups):
+            return cached[1]
+        from metrics_b200.classification.precision_recall_curve import MulticlassPrecisionRecallCurve
+        from metrics_b200.classification.stat_scores import MulticlassStatScores
+
+        stats = curve = None
+        for members in self._groups.values():
+            leader = self._modules[members[0]]
+            if getattr(leader, "validate_args", True) or getattr(leader, "ignore_index", 0) is not None:
+                continue
+            if (stats is None and isinstance(leader, MulticlassStatScores) and leader.top_k == 1 and leader.num_classes
+                    and leader.multidim_average == "global" and leader.num_classes <= 1024):
+                stats = members[0]
+            elif (curve is None and isinstance(leader, MulticlassPrecisionRecallCurve) and leader.thresholds is None
+                  and leader.average != "micro"):
+                curve = members[0]
+        plan = None
+        if stats is not None and curve is not None:
+            c = self._modules[stats].num_classes
+            if self._modules[curve].num_classes == c:
+                plan = (stats, curve, c)
+        self.__dict__["_fusion_plan_cache"] = (id(self._groups), plan)
+        return plan
 
     def _merge_compute_groups(self) -> None:
         """Partition members by equal states after the first update (first member of a group is its leader)."""

@@ -78,6 +78,11 @@ def multiclass_stat_scores_update_(tp, fp, tn, fn, workspace, preds, target, num
     fn += d
 
 
+def multiclass_stats_softmax_update_(tp, fp, tn, fn, workspace, preds, target, num_classes, micro, err_flag=None) -> Tensor:
+    multiclass_stat_scores_update_(tp, fp, tn, fn, workspace, preds, target, num_classes, None, micro, err_flag)
+    return softmax_if_logits(preds)
+
+
 def multiclass_stat_scores_topk_update_(tp, fp, tn, fn, workspace, preds, target, num_classes, top_k, ignore_index, err_flag=None) -> None:
     if preds.ndim != 2 or target.ndim != 1:
         raise NotImplementedError("metrics_b200: top_k > 1 supports `preds` of shape (N, C) with `target` of shape (N,)")
@@ -329,7 +334,8 @@ def coco_map_evaluate(det_box, det_score, det_label, det_counts, gt_box, gt_labe
 NAMES = ("launch_count", "multiclass_confmat_update_", "multiclass_stat_scores_update_",
          "multiclass_stat_scores_topk_update_", "multiclass_stat_scores_samplewise", "argmax_rows",
          "sigmoid_if_logits", "softmax_if_logits", "curve_evaluate", "curve_evaluate_multilabel",
-         "binary_stat_counts", "regression_sums", "binned_curve_update", "coco_map_evaluate", "curve_weighted_clf_curve")
+         "binary_stat_counts", "regression_sums", "binned_curve_update", "coco_map_evaluate", "curve_weighted_clf_curve",
+         "multiclass_stats_softmax_update_")
 
 
 def standins() -> dict:

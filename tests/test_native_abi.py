@@ -136,6 +136,7 @@ def test_every_kernel_wrapper_calls_the_abi_as_declared(monkeypatch):
     _native.multiclass_confmat_update_(i64(c, c), scores, labels, c, 1, flag)
     _native.multiclass_confmat_update_(i64(c, c), labels, labels, c, None, None)
     _native.multiclass_stat_scores_update_(i64(c), i64(c), i64(c), i64(c), i64(3 * c + 2), scores, labels, c, None, False, flag)
+    _native.multiclass_stats_softmax_update_(i64(c), i64(c), i64(c), i64(c), i64(3 * c + 2), scores, labels, c, False, flag)
     _native.multiclass_stat_scores_topk_update_(i64(c), i64(c), i64(c), i64(c), i64(3 * c + 2), scores, labels, c, 2, None, None)
     _native.multiclass_stat_scores_samplewise(scores.reshape(4, c, 4), labels.reshape(4, 4), c, None, flag)
     _native.argmax_rows(scores)
