@@ -32,6 +32,14 @@ _DTYPE_TAG = {
 }
 
 ABI_VERSION = 1  # MB200_ABI_VERSION of include/metrics_b200.h
+# second binding of the same C-ABI: the registered PyTorch operators (metrics_b200/torch_ops.py) instead of ctypes
+_TORCH_BINDING = os.environ.get("MB200_BINDING", "ctypes") == "torch"
+
+
+def _ops():
+    from metrics_b200 import torch_ops
+
+    return torch_ops.ops()
 FLAG_TARGET_RANGE = 1
 FLAG_PREDS_RANGE = 2
 FLAG_SPIN_TIMEOUT = 4
@@ -229,6 +237,9 @@ def multiclass_confmat_update_(
 ) -> None:
     """In-place ``confmat[t, argmax(preds)] += 1`` (``mb200_multiclass_confmat_update``).  Launch path of cfg1 / cfg2:
     arguments are handed to ctypes as plain ints (see `declare_signatures`), no helper call per argument."""
+    if _TORCH_BINDING:
+        _ops().confmat_update_(confmat, preds, target, int(num_classes), ignore_index, err_flag)
+        return
     dev = require_cuda(confmat, preds, target)
     has_class_dim = preds.ndim == target.ndim + 1
     preds = preds.contiguous()
@@ -259,6 +270,9 @@ def multiclass_stat_scores_update_(
 ) -> None:
     """In-place tp/fp/tn/fn accumulation (``mb200_multiclass_stat_scores_update``).  The four states and the workspace
     belong to one metric and move together (`Metric._apply`), so one of them stands for all in the device check."""
+    if _TORCH_BINDING:
+        _ops().stat_scores_update_(tp, fp, tn, fn, workspace, preds, target, int(num_classes), ignore_index, bool(micro), err_flag)
+        return
     dev = require_cuda(tp, workspace, preds, target)
     has_class_dim = preds.ndim == target.ndim + 1
     preds = preds.contiguous()
@@ -278,6 +292,8 @@ def multiclass_stats_softmax_update_(tp: Tensor, fp: Tensor, tn: Tensor, fn: Ten
                                      target: Tensor, num_classes: int, micro: bool, err_flag: Optional[Tensor] = None) -> Tensor:
     """K11 (``mb200_multiclass_stats_softmax_update``): in-place tp/fp/tn/fn accumulation AND the batch's
     ``normalize_logits_if_needed(preds, "softmax")`` from one read of ``preds [N, C]``; returns the probabilities."""
+    if _TORCH_BINDING:
+        return _ops().stats_softmax_update_(tp, fp, tn, fn, workspace, preds, target, int(num_classes), bool(micro), err_flag)
     dev = require_cuda(tp, workspace, preds, target)
     preds = preds.contiguous()
     target = target.contiguous()
@@ -313,6 +329,8 @@ def argmax_rows(preds: Tensor) -> Tensor:
 # ----------------------------------------------------------------------------------------------------------
 def sigmoid_if_logits(preds: Tensor) -> Tensor:
     """``normalize_logits_if_needed(preds, "sigmoid")``: per-call global range test + conditional sigmoid, no host sync."""
+    if _TORCH_BINDING:
+        return _ops().normalize_logits_if_needed(preds, "sigmoid")
     dev = require_cuda(preds)
     preds = preds.contiguous()
     out = torch.empty_like(preds)
@@ -329,6 +347,8 @@ def sigmoid_if_logits(preds: Tensor) -> Tensor:
 
 def softmax_if_logits(preds: Tensor) -> Tensor:
     """``normalize_logits_if_needed(preds, "softmax")`` for a contiguous ``[N, C]`` tensor."""
+    if _TORCH_BINDING:
+        return _ops().normalize_logits_if_needed(preds, "softmax")
     dev = require_cuda(preds)
     preds = preds.contiguous()
     out = torch.empty_like(preds)
@@ -350,6 +370,9 @@ def curve_evaluate(preds: Tensor, target: Tensor, num_classes: int = 1, pos_labe
     ``(fps, tps, thresholds)`` of ``[C, N]`` buffers whose first ``counts[c, 2]`` entries per row are valid; fps / tps are
     float32, thresholds float64 for float64 scores (sorted as 64-bit keys) and float32 otherwise.
     """
+    if _TORCH_BINDING:
+        auroc, ap, counts, fps, tps, thr = _ops().curve_evaluate(preds, target, int(num_classes), int(pos_label), bool(want_curve))
+        return auroc, ap, counts, ((fps, tps, thr) if want_curve else None)
     dev = require_cuda(preds, target)
     preds = preds.contiguous()
     target = target.contiguous()
@@ -490,6 +513,8 @@ def regression_sums(preds: Tensor, target: Tensor, op: int, num_outputs: int = 1
         preds = preds.float()
     if target.dtype != preds.dtype:
         target = target.to(preds.dtype)
+    if _TORCH_BINDING:
+        return _ops().regression_sums(preds, target, int(op), int(num_outputs), float(param), float(eps))
     preds = preds.contiguous()
     target = target.contiguous()
     d = int(num_outputs)
