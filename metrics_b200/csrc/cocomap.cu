@@ -27,7 +27,8 @@ extern void count_launch();
 
 constexpr int kMapAreas = 4;
 constexpr int kMapMaxThr = 16;  // T <= 16 so that area*T + thr fits a 64-bit word
-constexpr int kGtmWords = 4;    // <= 256 ground truths of one class in one image
+constexpr int kGtmWords = 4;    // "matched" bit mask kept in registers: <= 256 ground truths of one class in one image;
+                                // busier images switch to a per-thread mask in shared memory (kSmemMask)
 
 struct MapEvalArgs {
     const float4* det_box;  // xywh
@@ -94,6 +95,7 @@ __host__ __device__ inline size_t map_eval_smem_bytes(int max_d, int max_g) {
     return b + 64;
 }
 
+template <bool kSmemMask>
 __global__ void __launch_bounds__(256) map_evaluate_kernel(MapEvalArgs p, int max_d, int max_g) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __shared__ int ncats;
@@ -115,7 +117,10 @@ __global__ void __launch_bounds__(256) map_evaluate_kernel(MapEvalArgs p, int ma
     int* gcrowd = reinterpret_cast<int*>(ptr); ptr += (size_t)max_g * 4;
     int* cats = reinterpret_cast<int*>(ptr); ptr += (size_t)(max_d + max_g) * 4;
     int* cat_start = reinterpret_cast<int*>(ptr); ptr += (size_t)(max_d + max_g) * 4;
-    int* cat_cnt = reinterpret_cast<int*>(ptr);
+    int* cat_cnt = reinterpret_cast<int*>(ptr); ptr += (size_t)(max_d + max_g) * 4;
+    // kSmemMask: one "ground truth already matched" bit per ground truth of the image, per thread
+    const int mask_words = kSmemMask ? (max_g + 63) / 64 : kGtmWords;
+    unsigned long long* smem_mask = reinterpret_cast<unsigned long long*>(sm_raw + (((size_t)(ptr - sm_raw) + 7) & ~(size_t)7));
 
     const int tid = threadIdx.x, nth = blockDim.x;
     if (tid == 0) ncats = 0;
@@ -186,9 +191,15 @@ __global__ void __launch_bounds__(256) map_evaluate_kernel(MapEvalArgs p, int ma
         const int bit = a * T + t;
         const int nd = min(cat_cnt[ci], p.max_det_last);
         const double thr0 = fmin(p.iou_thr[t], 1.0 - 1e-10);
-        unsigned long long gtm[kGtmWords];
+        unsigned long long gtm_regs[kGtmWords];
+        unsigned long long* gtm = kSmemMask ? smem_mask + (size_t)tid * mask_words : gtm_regs;
+        if (kSmemMask) {
+            for (int q = 0; q < mask_words; ++q) gtm[q] = 0ull;
+        } else {
 #pragma unroll
-        for (int q = 0; q < kGtmWords; ++q) gtm[q] = 0ull;
+            for (int q = 0; q < kGtmWords; ++q) gtm_regs[q] = 0ull;
+        }
+        const int mask_bits = 64 * mask_words;
 
         if (t == 0) {  // one thread per (class, area) counts the non-ignored ground truths
             int n_valid = 0, n_c = 0;
@@ -198,7 +209,7 @@ __global__ void __launch_bounds__(256) map_evaluate_kernel(MapEvalArgs p, int ma
                 n_valid += !(gcrowd[g] || area_outside(garea[g], a));
             }
             if (n_valid) atomicAdd(&p.npig[c * kMapAreas + a], n_valid);
-            if (n_c > 64 * kGtmWords && p.err) atomicOr(p.err, MB200_FLAG_CAPACITY);
+            if (n_c > mask_bits && p.err) atomicOr(p.err, MB200_FLAG_CAPACITY);
         }
         for (int r = 0; r < nd; ++r) {
             const int d = by_pos[cat_start[ci] + r];
@@ -215,7 +226,7 @@ __global__ void __launch_bounds__(256) map_evaluate_kernel(MapEvalArgs p, int ma
                     const bool crowd = gcrowd[g] != 0;
                     const bool ig = crowd || area_outside(garea[g], a);
                     if ((int)ig != phase) continue;
-                    if (ord < 64 * kGtmWords && ((gtm[ord >> 6] >> (ord & 63)) & 1ull) && !crowd) continue;
+                    if (ord < mask_bits && ((gtm[ord >> 6] >> (ord & 63)) & 1ull) && !crowd) continue;
                     const double iou = bb_iou(db, gbox[g], crowd);
                     if (iou < best) continue;
                     best = iou;
@@ -228,7 +239,7 @@ __global__ void __launch_bounds__(256) map_evaluate_kernel(MapEvalArgs p, int ma
             } else {
                 atomicOr(&dmatch[d], 1ull << bit);
                 if (m_ig) atomicOr(&dign[d], 1ull << bit);
-                if (m < 64 * kGtmWords) gtm[m >> 6] |= 1ull << (m & 63);
+                if (m < mask_bits) gtm[m >> 6] |= 1ull << (m & 63);
             }
         }
     }
@@ -506,7 +517,11 @@ extern "C" int mb200_coco_map_evaluate(
     MB200_REQUIRE(workspace_bytes >= mb200_coco_map_workspace_bytes(n_det, num_classes, n_max_dets),
                   "workspace too small");
     const int K = micro ? 1 : (int)num_classes;
-    const size_t smem = map_eval_smem_bytes((int)max_det_per_img, (int)max_gt_per_img);
+    // More than 256 ground truths in one image MAY put more than 256 of one class there: then the per-thread "matched" masks
+    // move from registers to shared memory, one bit per ground truth of the image per thread.
+    const bool smem_mask = max_gt_per_img > 64 * kGtmWords;
+    const size_t smem = map_eval_smem_bytes((int)max_det_per_img, (int)max_gt_per_img) +
+                        (smem_mask ? (size_t)256 * ((max_gt_per_img + 63) / 64) * 8 + 8 : 0);
     if (smem > 200 * 1024) {
         set_error("an image holds %lld detections / %lld ground truths: more than the evaluate kernel can stage in "
                   "shared memory", (long long)max_det_per_img, (long long)max_gt_per_img);
@@ -546,8 +561,13 @@ extern "C" int mb200_coco_map_evaluate(
     ea.det_ignore = w.det_ignore;
     ea.npig = w.npig;
     ea.err = err_flag;
-    MB200_CUDA_OK(ensure_dynamic_smem(map_evaluate_kernel, 200 * 1024));
-    map_evaluate_kernel<<<(unsigned)n_img, 256, smem, st>>>(ea, (int)max_det_per_img, (int)max_gt_per_img);
+    if (smem_mask) {
+        MB200_CUDA_OK(ensure_dynamic_smem(map_evaluate_kernel<true>, 200 * 1024));
+        map_evaluate_kernel<true><<<(unsigned)n_img, 256, smem, st>>>(ea, (int)max_det_per_img, (int)max_gt_per_img);
+    } else {
+        MB200_CUDA_OK(ensure_dynamic_smem(map_evaluate_kernel<false>, 200 * 1024));
+        map_evaluate_kernel<false><<<(unsigned)n_img, 256, smem, st>>>(ea, (int)max_det_per_img, (int)max_gt_per_img);
+    }
     count_launch();
 
     // ---- sort detections by (class, score desc), stable w.r.t. (image, original index) ----

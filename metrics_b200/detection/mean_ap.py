@@ -457,7 +457,7 @@ class MeanAveragePrecision(Metric):
 
         precision, recall, scores, err = run(self.average == "micro")
         if int(err.item()) != 0:
-            raise NotImplementedError("metrics_b200: more than 256 ground truths of one class in a single image")
+            raise NotImplementedError("metrics_b200: an image holds more ground truths of one class than the matcher can track")
         result.update(self._stats_dict(self._summarize(precision, recall)))
         if self.extended_summary:
             micro = self.average == "micro"

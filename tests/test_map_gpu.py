@@ -149,3 +149,13 @@ def test_cfg4_shape_invariances_at_full_size():
     assert 0.0 < float(res["map"]) < 1.0 and res["precision"].shape == (10, 101, 80, 4, 3)
     sub_p, sub_t = preds[:150], target[:150]
     _check(_run(sub_p, sub_t, batch=50), coco_evaluate(**det_to_numpy(sub_p, sub_t)))
+
+
+def test_more_than_256_ground_truths_of_one_class_in_an_image():
+    """Past 256 ground truths per image the matcher's "already matched" masks move from registers to shared memory
+    (csrc/cocomap.cu kSmemMask): a crowded image of ONE class (300 and 700 boxes) must still follow the oracle."""
+    preds, target = synth_detection(seed=5, n_img=3, n_gt=300, n_det=100, n_cls=1, crowd_frac=0.05, dup_scores=True)
+    big_p, big_t = synth_detection(seed=6, n_img=1, n_gt=700, n_det=100, n_cls=2, crowd_frac=0.0)
+    big_t[0]["labels"][:] = 0  # 700 ground truths of one class
+    preds, target = preds + big_p, target + big_t
+    _check(_run(preds, target, batch=2), coco_evaluate(**det_to_numpy(preds, target)))
