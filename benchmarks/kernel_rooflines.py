@@ -90,6 +90,35 @@ n7 = 10_000_000
 p7, t7 = p[:n7].contiguous(), t[:n7].contiguous()
 record("K3/K5 curve_evaluate 1e7 f32 (pack + 4-pass sort + scan)", timed(lambda: _native.curve_evaluate(p7, t7, 1), reps=10), 150e6,
        "SURVEY 8(d) figure: each 5-byte record read once, written once, scanned once; the working set (50 MB) is L2-resident")
+# K11: fused stat scores + softmax store, cfg5-shaped batches scaled up: [65536, 1000] f32, 4 rotating batches (1 GB)
+lg32 = [torch.randn(N, C, generator=g, device=dev) for _ in range(4)]
+tg32 = [torch.randint(0, C, (N,), generator=g, device=dev) for _ in range(4)]
+kk = [0]
+
+
+def k11():
+    i = kk[0] = (kk[0] + 1) % 4
+    _native.multiclass_stats_softmax_update_(*st, ws, lg32[i], tg32[i], C, False)
+
+
+record("K11 stats+softmax fused update [65536,1000] f32", timed(k11, inner=16), N * C * 4 * 2 + N * 8,
+       "one read + one write of the batch (the unfused members read it three times and write it once)")
+
+
+def unfused():
+    i = kk[0] = (kk[0] + 1) % 4
+    _native.multiclass_stat_scores_update_(*st, ws, lg32[i], tg32[i], C, None, False, None)
+    _native.softmax_if_logits(lg32[i])
+
+
+record("K1b + K6 unfused on the same batches [65536,1000] f32", timed(unfused, inner=16), N * C * 4 * 2 + N * 8,
+       "same algorithmic bytes; three reads + one write of traffic")
+del lg32
+# K3 multiclass: 1000 one-vs-rest curves over 16384 samples (cfg5, one rank's share)
+pm5 = torch.softmax(torch.randn(16384, 1000, generator=g, device=dev), 1)
+tm5 = torch.randint(0, 1000, (16384,), generator=g, device=dev)
+record("K3/K5 curve_evaluate [16384,1000] f32, 1000 segments", timed(lambda: _native.curve_evaluate(pm5, tm5, 1000), reps=10),
+       16384 * 1000 * 15, "same per-record figure as the binary case (5-byte record read, written, scanned)")
 print(json.dumps(out, indent=1))
 if len(sys.argv) > 1:
     open(sys.argv[1], "w").write(json.dumps(out, indent=1))

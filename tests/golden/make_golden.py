@@ -1284,7 +1284,11 @@ def curves64_golden() -> dict:
     # multiclass one-vs-rest
     for n, c in ((300, 5), (1500, 37)):
         lg = torch.randn(n, c, generator=g, dtype=torch.float64)
-        lg[1::2] = lg[::2][: lg[1::2].shape[0]] + 1e-13
+        # odd rows repeat the even ones with ONE logit moved by 1e-10: every probability of the pair then differs by ~1e-11
+        # relative — far above float64 rounding of the softmax (so the order is well defined), far below float32 resolution
+        # (shifting the whole row would leave the softmax unchanged up to rounding noise)
+        lg[1::2] = lg[::2][: lg[1::2].shape[0]]
+        lg[1::2, 0] += 1e-10
         target = torch.randint(0, c, (n,), generator=g)
         for fn in ("multiclass_roc", "multiclass_precision_recall_curve", "multiclass_auroc", "multiclass_average_precision"):
             kw = dict(num_classes=c, thresholds=None)
