@@ -153,24 +153,37 @@ class Metric(Module, ABC):
         def wrapped_func(*args: Any, **kwargs: Any) -> None:
             self._computed = None
             self._update_count += 1
+            if torch.is_grad_enabled() == self._enable_grad:
+                # already in the grad mode `update` must run under (the usual `torch.no_grad()` evaluation loop): skip the
+                # context-manager object — a fifth of the host time of a small update
+                try:
+                    update(*args, **kwargs)
+                except RuntimeError as err:
+                    self._reraise_device_mismatch(err)
+                if self.compute_on_cpu:
+                    self._move_list_states_to_cpu()
+                return
             with torch.set_grad_enabled(self._enable_grad):
                 try:
                     update(*args, **kwargs)
                 except RuntimeError as err:
-                    if "Expected all tensors to be on" in str(err):
-                        name = self.__class__.__name__
-                        raise RuntimeError(
-                            "Encountered different devices in metric calculation (see stacktrace for details)."
-                            " This could be due to the metric class not being on the same device as input."
-                            f" Instead of `metric={name}(...)` try to do"
-                            f" `metric={name}(...).to(device)` where"
-                            " device corresponds to the device of the input."
-                        ) from err
-                    raise err
+                    self._reraise_device_mismatch(err)
             if self.compute_on_cpu:
                 self._move_list_states_to_cpu()
 
         return wrapped_func
+
+    def _reraise_device_mismatch(self, err: RuntimeError) -> None:
+        if "Expected all tensors to be on" in str(err):
+            name = self.__class__.__name__
+            raise RuntimeError(
+                "Encountered different devices in metric calculation (see stacktrace for details)."
+                " This could be due to the metric class not being on the same device as input."
+                f" Instead of `metric={name}(...)` try to do"
+                f" `metric={name}(...).to(device)` where"
+                " device corresponds to the device of the input."
+            ) from err
+        raise err
 
     def _wrap_compute(self, compute: Callable) -> Callable:
         @functools.wraps(compute)
