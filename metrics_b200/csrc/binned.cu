@@ -155,6 +155,118 @@ __global__ void __launch_bounds__(256) binned_bucket_kernel(const T* __restrict_
     if (threadIdx.x == 0) scratch[ncnt] = 0ull;
 }
 
+// ---- binary fast path ------------------------------------------------------------------------------------------------
+// The generic kernel above spends ~160 instructions per element (profiles/r02_binned_ncu.txt: issue-active 68 %, not a
+// memory stall in sight): runtime label dtype switch, 64-bit indexing, class division, loop-shaped bucket search.  The binary
+// task (C == 1, the shape of cfg3's binned variant) gets its own kernel: f32 scores, int64 / int32 / uint8-family labels
+// resolved at compile time, 16-byte vector loads of four scores (+ their four labels), 32-bit indices, thresholds in shared
+// memory, and a branch-free bucket search — uniform-grid hint, two corrective steps up and two down, verified against the
+// real thresholds (the hint can only cost time: an unsettled bucket falls back to the binary search).
+template <typename LabelT>
+__device__ __forceinline__ void load4_labels(const LabelT* __restrict__ t, unsigned q, long long (&out)[4]) {
+    if constexpr (sizeof(LabelT) == 8) {
+        const longlong2 a = reinterpret_cast<const longlong2*>(t)[2 * (size_t)q];
+        const longlong2 b = reinterpret_cast<const longlong2*>(t)[2 * (size_t)q + 1];
+        out[0] = a.x, out[1] = a.y, out[2] = b.x, out[3] = b.y;
+    } else if constexpr (sizeof(LabelT) == 4) {
+        const int4 a = reinterpret_cast<const int4*>(t)[q];
+        out[0] = a.x, out[1] = a.y, out[2] = a.z, out[3] = a.w;
+    } else {
+        const uchar4 a = reinterpret_cast<const uchar4*>(t)[q];
+        out[0] = a.x, out[1] = a.y, out[2] = a.z, out[3] = a.w;
+    }
+}
+
+template <typename LabelT>
+__global__ void __launch_bounds__(256) binned_binary_fast_kernel(const float* __restrict__ preds, const LabelT* __restrict__ target,
+                                                                 unsigned n, const float* __restrict__ thr, int nthr,
+                                                                 unsigned long long* __restrict__ scratch,
+                                                                 long long* __restrict__ confmat) {
+    extern __shared__ unsigned sh_fast[];  // [2 * (nthr + 1)] counters, then nthr thresholds
+    const int stride = nthr + 1;
+    const int ncnt = 2 * stride;
+    float* sh_thr = reinterpret_cast<float*>(sh_fast + ncnt);
+    for (int i = threadIdx.x; i < nthr; i += blockDim.x) sh_thr[i] = thr[i];
+    for (int i = threadIdx.x; i < ncnt; i += blockDim.x) sh_fast[i] = 0;
+    __syncthreads();
+    const float t_first = sh_thr[0], t_last = sh_thr[nthr - 1];
+    const float scale = (nthr > 1 && t_last > t_first) ? (float)(nthr - 1) / (t_last - t_first) : 0.f;
+    auto bucket_of = [&](float p) -> int {  // k = #{thr_j <= p}; NaN -> 0 (every comparison is false)
+        const float h = (p - t_first) * scale;
+        int k = h >= (float)nthr ? nthr : (h > 0.f ? (int)h : 0);
+        k += (k < nthr && sh_thr[min(k, nthr - 1)] <= p);
+        k += (k < nthr && sh_thr[min(k, nthr - 1)] <= p);
+        k -= (k > 0 && !(sh_thr[max(k - 1, 0)] <= p));
+        k -= (k > 0 && !(sh_thr[max(k - 1, 0)] <= p));
+        const bool settled = (k == nthr || !(sh_thr[min(k, nthr - 1)] <= p)) && (k == 0 || sh_thr[max(k - 1, 0)] <= p);
+        if (!settled) {
+            int lo = 0, hi = nthr;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (sh_thr[mid] <= p) lo = mid + 1;
+                else hi = mid;
+            }
+            k = lo;
+        }
+        return k;
+    };
+    auto commit = [&](long long t, float p) {
+        if ((unsigned long long)t > 1ull) return;  // only {0, 1} targets take part
+        atomicAdd(&sh_fast[(int)t * stride + bucket_of(p)], 1u);
+    };
+    const unsigned quads = n >> 2;
+    const unsigned gstride = gridDim.x * blockDim.x;
+    unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; q + gstride < quads; q += 2 * gstride) {  // two independent quads in flight
+        const float4 p0 = reinterpret_cast<const float4*>(preds)[q], p1 = reinterpret_cast<const float4*>(preds)[q + gstride];
+        long long t0[4], t1[4];
+        load4_labels<LabelT>(target, q, t0);
+        load4_labels<LabelT>(target, q + gstride, t1);
+        commit(t0[0], p0.x), commit(t0[1], p0.y), commit(t0[2], p0.z), commit(t0[3], p0.w);
+        commit(t1[0], p1.x), commit(t1[1], p1.y), commit(t1[2], p1.z), commit(t1[3], p1.w);
+    }
+    for (; q < quads; q += gstride) {
+        const float4 p0 = reinterpret_cast<const float4*>(preds)[q];
+        long long t0[4];
+        load4_labels<LabelT>(target, q, t0);
+        commit(t0[0], p0.x), commit(t0[1], p0.y), commit(t0[2], p0.z), commit(t0[3], p0.w);
+    }
+    for (unsigned i = (quads << 2) + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride)
+        commit((long long)target[i], preds[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ncnt; i += blockDim.x) {
+        const unsigned v = sh_fast[i];
+        if (v) atomicAdd(&scratch[i], (unsigned long long)v);
+    }
+    // ---- last CTA folds the bucket counts into the [T, 2, 2] state and cleans the scratch (as in the generic kernel) ----
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long ticket = atomicAdd(&scratch[ncnt], 1ull);
+        is_last = ticket == (unsigned long long)gridDim.x - 1ull;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < 2) {
+        const int y = threadIdx.x;
+        unsigned long long* row = scratch + (size_t)y * stride;
+        unsigned long long tot = 0;
+        for (int k = 0; k <= nthr; ++k) tot += __ldcg(row + k);
+        unsigned long long ge = tot;
+        for (int i = 0; i < nthr; ++i) {
+            ge -= __ldcg(row + i);
+            unsigned long long* cell = reinterpret_cast<unsigned long long*>(confmat + ((size_t)i * 2 + y) * 2);
+            if (ge) atomicAdd(cell + 1, ge);
+            if (tot - ge) atomicAdd(cell + 0, tot - ge);
+        }
+        for (int k = 0; k <= nthr; ++k) row[k] = 0ull;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) scratch[ncnt] = 0ull;
+}
+
 }  // namespace mb200
 
 using namespace mb200;
@@ -183,6 +295,32 @@ static int binned_update_impl(int multilabel, const void* preds, int preds_dtype
     if (blocks < 1) blocks = 1;
     unsigned long long* sc = reinterpret_cast<unsigned long long*>(scratch);
     long long* cm = reinterpret_cast<long long*>(confmat);
+    // binary fast path: f32 scores, 16-byte aligned inputs, the usual label dtypes, counters + thresholds in shared memory
+    const bool label_ok = target_dtype == MB200_I64 || target_dtype == MB200_I32 || target_dtype == MB200_U8 ||
+                          target_dtype == MB200_BOOL || target_dtype == MB200_I8;
+    if (!multilabel && num_classes == 1 && preds_dtype == MB200_F32 && label_ok && num_thresholds <= 4096 && n < (1ll << 31) &&
+        n >= 4096 && ((reinterpret_cast<uintptr_t>(preds) | reinterpret_cast<uintptr_t>(target)) & 15) == 0) {
+        const size_t smem_fast = (size_t)(2 * (num_thresholds + 1)) * sizeof(unsigned) + (size_t)num_thresholds * sizeof(float);
+        long long fb = (n / 4 + 256 * 4 - 1) / (256 * 4);
+        const long long fcap = (long long)sm_count() * 6;
+        if (fb > fcap) fb = fcap;
+        if (fb < 1) fb = 1;
+        const float* pf = reinterpret_cast<const float*>(preds);
+        if (target_dtype == MB200_I64)
+            binned_binary_fast_kernel<long long><<<(int)fb, 256, smem_fast, st>>>(pf, (const long long*)target, (unsigned)n,
+                                                                                 thresholds_sorted, (int)num_thresholds, sc, cm);
+        else if (target_dtype == MB200_I32)
+            binned_binary_fast_kernel<int><<<(int)fb, 256, smem_fast, st>>>(pf, (const int*)target, (unsigned)n, thresholds_sorted,
+                                                                           (int)num_thresholds, sc, cm);
+        else if (target_dtype == MB200_I8)
+            binned_binary_fast_kernel<signed char><<<(int)fb, 256, smem_fast, st>>>(pf, (const signed char*)target, (unsigned)n,
+                                                                                   thresholds_sorted, (int)num_thresholds, sc, cm);
+        else
+            binned_binary_fast_kernel<unsigned char><<<(int)fb, 256, smem_fast, st>>>(pf, (const unsigned char*)target, (unsigned)n,
+                                                                                     thresholds_sorted, (int)num_thresholds, sc, cm);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "binned curve launch");
+    }
 #define MB200_BINNED(T)                                                                                              \
     binned_bucket_kernel<T><<<(int)blocks, 256, smem_total, st>>>(                                                  \
         reinterpret_cast<const T*>(preds), target, target_dtype, n, (int)num_classes, thresholds_sorted,            \

@@ -125,3 +125,35 @@ def test_binned_classes_and_large_threshold_counts(golden_binned):
     thr = torch.linspace(0, 1, 33)
     np.testing.assert_array_equal(_native.binned_curve_update(p.to(DEV), t.to(DEV), thr.to(DEV), 40).cpu().numpy(),
                                   oc.binned_confmat(p.numpy(), t.numpy(), thr.numpy(), 40))
+
+
+@pytest.mark.parametrize("label_dtype", [torch.int64, torch.int32, torch.uint8, torch.bool, torch.int8])
+@pytest.mark.parametrize("thr_kind", ["linspace200", "linspace3", "irregular", "single", "dense"])
+def test_binary_fast_path_equals_generic_kernel_and_oracle(label_dtype, thr_kind):
+    """The binary fast path of K4 (float32 scores, 16-byte aligned, n >= 4096: vector loads, branch-free bucket search) against
+    the generic kernel (same data, forced by a 4-byte misaligned view) and the numpy oracle: integer confusion matrices,
+    bit-exact — including scores sitting exactly on thresholds, NaN, +-inf, and targets outside {0, 1}."""
+    from metrics_b200 import _native
+    from oracle import curves as oc
+
+    n = 100_003
+    g = torch.Generator().manual_seed(17)
+    thr = {"linspace200": torch.linspace(0, 1, 200), "linspace3": torch.linspace(0, 1, 3),
+           "irregular": torch.tensor([0.01, 0.011, 0.2, 0.5, 0.50001, 0.9, 0.97, 0.99]), "single": torch.tensor([0.5]),
+           "dense": torch.linspace(0.4, 0.6, 3000)}[thr_kind]
+    p = torch.rand(n + 1, generator=g)
+    p[1:4001] = thr[torch.randint(0, thr.numel(), (4000,), generator=g)]  # exactly on a threshold
+    p[5000:5004] = torch.tensor([float("nan"), float("inf"), float("-inf"), -0.0])
+    t = torch.randint(0, 2, (n + 1,), generator=g)
+    if label_dtype in (torch.int64, torch.int32, torch.int8):
+        t[6000:6010] = -1  # ignored entries
+    if label_dtype != torch.bool:
+        t[6010:6020] = 2 if label_dtype != torch.int8 else 2
+    pd, td, thr_d = p.to(DEV), t.to(label_dtype).to(DEV), thr.to(DEV)
+    fast = _native.binned_curve_update(pd[1:].clone(), td[1:].clone(), thr_d, 1)   # fresh allocations: aligned
+    slow = _native.binned_curve_update(pd[1:], td[1:].clone() if label_dtype != torch.int64 else td[1:], thr_d, 1)  # misaligned view
+    assert torch.equal(fast, slow)
+    tn = t[1:].to(label_dtype).to(torch.int64).numpy()
+    keep = (tn == 0) | (tn == 1)
+    want = oc.binned_confmat(p[1:].numpy()[keep], tn[keep], thr.numpy(), 1)
+    np.testing.assert_array_equal(fast.cpu().numpy(), want.reshape(fast.shape))
