@@ -249,6 +249,15 @@ MB200_API int mb200_binary_stat_counts(const void* preds, int preds_dtype, const
                                        int64_t n_outer, int64_t num_labels, int64_t inner, double threshold,
                                        int has_ignore_index, int64_t ignore_index, int samplewise, int64_t* counts,
                                        uint32_t* flag_scratch, uint32_t* err_flag, void* stream);
+/* Same contract with a larger caller-owned scratch (>= MB200_BINARY_SCRATCH_BYTES, 8-byte aligned, contents irrelevant): the
+ * binary task (num_labels == 1, global counts, int64 targets, 16-byte aligned f32/f16/bf16 scores) then reads the scores ONCE,
+ * counting under both outcomes of the batch-global logits vote and adding the selected set in a one-warp epilogue — 12 instead
+ * of 16 bytes of traffic per element; every other shape takes the kernels of mb200_binary_stat_counts. */
+#define MB200_BINARY_SCRATCH_BYTES 128
+MB200_API int mb200_binary_stat_counts_scratch(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                               int64_t n_outer, int64_t num_labels, int64_t inner, double threshold,
+                                               int has_ignore_index, int64_t ignore_index, int samplewise, int64_t* counts,
+                                               uint32_t* scratch, int64_t scratch_bytes, uint32_t* err_flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K9 — regression running sums (one fused map-reduce per update).

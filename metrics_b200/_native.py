@@ -102,6 +102,7 @@ SIGNATURES = {
     "mb200_coco_map_workspace_bytes": ("q", "qqq"),
     "mb200_coco_map_evaluate": ("i", "pppppppppqqqqqpqipqpqpqpqppppp"),
     "mb200_binary_stat_counts": ("i", "pipiqqqdiqipppp"),
+    "mb200_binary_stat_counts_scratch": ("i", "pipiqqqdiqippqpp"),
     "mb200_regression_num_sums": ("i", "i"),
     "mb200_regression_scratch_doubles": ("q", "qqi"),
     "mb200_regression_sums": ("i", "ppiqqiddppp"),
@@ -488,12 +489,13 @@ def binary_stat_counts(
     groups = n_outer * num_labels if samplewise else num_labels
     if counts is None:
         counts = torch.zeros((groups, 4), dtype=torch.int64, device=dev)
-    flag = torch.empty(1, dtype=torch.int32, device=dev) if preds.is_floating_point() else None
+    # scratch for the logits vote; large enough (MB200_BINARY_SCRATCH_BYTES) for the single-pass binary kernel's two count sets
+    scratch = torch.empty(32, dtype=torch.int32, device=dev) if preds.is_floating_point() else None
     with on_device(dev):
-        rc = lib().mb200_binary_stat_counts(
+        rc = lib().mb200_binary_stat_counts_scratch(
             ptr(preds), tag(preds), ptr(target), tag(target), i64(n_outer), i64(num_labels), i64(max(1, inner)),
             ctypes.c_double(float(threshold)), int(ignore_index is not None), i64(ignore_index or 0), int(samplewise),
-            ptr(counts), ptr(flag), ptr(err_flag), stream_handle(dev),
+            ptr(counts), ptr(scratch), 128, ptr(err_flag), stream_handle(dev),
         )
     check(rc, "binary_stat_counts")
     return counts

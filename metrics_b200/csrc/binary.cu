@@ -9,6 +9,7 @@
 // floating scores) and ONE counting kernel.  Counters are privatised per thread (runs of equal group), then per CTA in
 // shared memory, then added to the int64 outputs with 64-bit REDs.
 #include <algorithm>
+#include <cmath>
 
 #include "common.cuh"
 
@@ -255,6 +256,86 @@ __global__ void __launch_bounds__(256) bin_count_flat_kernel(BinArgs a) {
     }
 }
 
+// Single-pass variant of the flat path (f32 / f16 / bf16 scores): the batch-global "are these logits?" vote needs the whole
+// batch before the first threshold decision, which is why the kernels above read the scores twice (16 B / element of traffic
+// for 12 algorithmic).  Here every element is counted under BOTH outcomes of the vote in one read — four counters assuming
+// probabilities, four assuming logits — while the vote itself is taken on the way; a one-warp epilogue kernel adds the set the
+// vote selected to the states.  Counting under "logits" does not evaluate a sigmoid per element: sigmoid(x) > thr is decided
+// by comparing x with a bracket [x_lo, x_hi] around logit(thr) computed on the host in double precision, wide enough to cover
+// the rounding of the float32 sigmoid and of its store in T; only scores INSIDE the bracket (a ~2^-7 .. 2^-20 relative band
+// around the threshold) run the exact arithmetic of `pred_from_value`, so the result is bit-identical to the two-pass kernels.
+struct BothArgs {
+    float x_lo, x_hi;            // outside (x_lo, x_hi): sigmoid(x) > thr is decided by the side; NaN bracket = always exact
+    unsigned long long* both;    // [8] zeroed scratch: tp fp tn fn under "probabilities", then under "logits"
+    unsigned* vote;              // zeroed word, set when any score lies outside [0, 1]
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) bin_count_flat_both_kernel(BinArgs a, BothArgs b) {
+    const long long total = a.n_outer * a.num_labels * a.inner;
+    constexpr int kVec = 16 / (int)sizeof(T);
+    const long long nvec = total / kVec;
+    const uint4* __restrict__ pv = reinterpret_cast<const uint4*>(a.preds);
+    const uint4* __restrict__ tv = reinterpret_cast<const uint4*>(a.target);
+    const T* __restrict__ ps = reinterpret_cast<const T*>(a.preds);
+    const long long* __restrict__ ts = reinterpret_cast<const long long*>(a.target);
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    unsigned cp[4] = {0, 0, 0, 0}, cl[4] = {0, 0, 0, 0};
+    bool bad_target = false, outside = false;
+    const bool bracket = b.x_lo == b.x_lo;  // NaN bracket: no shortcut for this threshold
+    auto count = [&](T x, long long t) {
+        const float v = score_to_float<T>(x);
+        outside |= (v < 0.f) | (v > 1.f);  // the vote runs over EVERY score, ignored targets included, like the reference's
+                                           // `torch.all((preds >= 0) * (preds <= 1))` (stat_scores.py:118-121)
+        if (a.has_ignore && t == a.ignore_index) return;
+        if ((unsigned long long)t > 1ull) {
+            bad_target = true;
+            return;
+        }
+        const int pp = v > a.threshold ? 1 : 0;
+        int pl;
+        if (bracket && v > b.x_hi) pl = 1;
+        else if (bracket && v < b.x_lo) pl = 0;
+        else pl = pred_from_value<T>(a, x, true);
+        const int ti = (int)t;
+        cp[0] += (pp == 1 && ti == 1), cp[1] += (pp == 1 && ti == 0), cp[2] += (pp == 0 && ti == 0), cp[3] += (pp == 0 && ti == 1);
+        cl[0] += (pl == 1 && ti == 1), cl[1] += (pl == 1 && ti == 0), cl[2] += (pl == 0 && ti == 0), cl[3] += (pl == 0 && ti == 1);
+    };
+    for (long long v = gtid; v < nvec; v += stride) {
+        const uint4 q = ld_stream16(pv + v);
+        const T* e = reinterpret_cast<const T*>(&q);
+        uint4 lab[kVec / 2];
+#pragma unroll
+        for (int k = 0; k < kVec / 2; ++k) lab[k] = ld_stream16(tv + v * (kVec / 2) + k);
+        const long long* l = reinterpret_cast<const long long*>(lab);
+#pragma unroll
+        for (int k = 0; k < kVec; ++k) count(e[k], l[k]);
+    }
+    for (long long i = nvec * kVec + gtid; i < total; i += stride) count(ps[i], ts[i]);
+    if (__any_sync(kFull, bad_target) && (threadIdx.x & 31) == 0 && a.err) atomicOr(a.err, MB200_FLAG_TARGET_RANGE);
+    if (__any_sync(kFull, outside) && (threadIdx.x & 31) == 0) atomicOr(b.vote, 1u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        cp[k] = __reduce_add_sync(kFull, cp[k]);
+        cl[k] = __reduce_add_sync(kFull, cl[k]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (cp[k]) atomicAdd(b.both + k, (unsigned long long)cp[k]);
+            if (cl[k]) atomicAdd(b.both + 4 + k, (unsigned long long)cl[k]);
+        }
+    }
+}
+
+__global__ void bin_select_kernel(const unsigned long long* __restrict__ both, const unsigned* __restrict__ vote,
+                                  long long* __restrict__ counts) {
+    if (threadIdx.x < 4) {
+        const unsigned long long v = both[(*vote != 0u ? 4 : 0) + threadIdx.x];
+        if (v) red_add_u64(counts + threadIdx.x, v);
+    }
+}
+
 // Multilabel fast path (global counts, `[N, L]` layout with inner == 1, L <= 256): every thread OWNS one label column
 // (column = threadIdx % L, rows strided over the grid), so its four counters live in registers for the whole kernel and
 // consecutive threads still read consecutive addresses.  The generic kernel flushes its register counters to shared
@@ -315,10 +396,10 @@ __global__ void __launch_bounds__(256) bin_count_cols_kernel(BinArgs a) {
 
 using namespace mb200;
 
-extern "C" int mb200_binary_stat_counts(const void* preds, int preds_dtype, const void* target, int target_dtype,
-                                        int64_t n_outer, int64_t num_labels, int64_t inner, double threshold,
-                                        int has_ignore_index, int64_t ignore_index, int samplewise, int64_t* counts,
-                                        uint32_t* flag_scratch, uint32_t* err_flag, void* stream) {
+static int binary_stat_counts_impl(const void* preds, int preds_dtype, const void* target, int target_dtype, int64_t n_outer,
+                                   int64_t num_labels, int64_t inner, double threshold, int has_ignore_index,
+                                   int64_t ignore_index, int samplewise, int64_t* counts, uint32_t* flag_scratch,
+                                   int64_t flag_scratch_bytes, uint32_t* err_flag, void* stream) {
     MB200_REQUIRE(n_outer >= 0 && num_labels >= 1 && inner >= 1, "bad sizes");
     const long long total = n_outer * num_labels * inner;
     if (total == 0) return 0;
@@ -343,6 +424,36 @@ extern "C" int mb200_binary_stat_counts(const void* preds, int preds_dtype, cons
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     const int grid = (int)blocks;
+    const bool flat = float_preds && !samplewise && num_labels == 1 && target_dtype == MB200_I64 &&
+                      ((reinterpret_cast<uintptr_t>(preds) | reinterpret_cast<uintptr_t>(target)) & 15) == 0;
+    // single pass (see bin_count_flat_both_kernel): flag_scratch then holds the vote word and, 8 bytes in, the 8 counters
+    const bool single_pass = flat && preds_dtype != MB200_F64 && flag_scratch_bytes >= 72 &&
+                             (reinterpret_cast<uintptr_t>(flag_scratch) & 7) == 0;
+    if (single_pass) {
+        MB200_CUDA_OK(cudaMemsetAsync(flag_scratch, 0, 72, st));
+        BothArgs b;
+        b.vote = flag_scratch;
+        b.both = reinterpret_cast<unsigned long long*>(flag_scratch + 2);
+        // bracket around logit(threshold): rel. band eps covers the float32 sigmoid's error and its rounding to T
+        const double eps = preds_dtype == MB200_F32 ? 0x1p-20 : (preds_dtype == MB200_F16 ? 0x1p-9 : 0x1p-6);
+        const double lo_p = threshold * (1.0 - eps) - 1e-300, hi_p = threshold * (1.0 + eps) + 1e-300;
+        if (threshold > 1e-6 && hi_p < 1.0 - 1e-6) {
+            const double xl = std::log(lo_p / (1.0 - lo_p)), xh = std::log(hi_p / (1.0 - hi_p));
+            b.x_lo = (float)(xl - 1e-5 * (1.0 + std::fabs(xl)));
+            b.x_hi = (float)(xh + 1e-5 * (1.0 + std::fabs(xh)));
+        } else {
+            b.x_lo = b.x_hi = std::nanf("");
+        }
+        switch (preds_dtype) {
+            case MB200_F32: bin_count_flat_both_kernel<float><<<grid, 256, 0, st>>>(a, b); break;
+            case MB200_F16: bin_count_flat_both_kernel<__half><<<grid, 256, 0, st>>>(a, b); break;
+            default: bin_count_flat_both_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, b); break;
+        }
+        bin_select_kernel<<<1, 32, 0, st>>>(b.both, b.vote, a.counts);
+        count_launch();
+        count_launch();
+        return check_cuda(cudaGetLastError(), "binary stat counts launch");
+    }
     if (float_preds) {
         MB200_CUDA_OK(cudaMemsetAsync(flag_scratch, 0, sizeof(uint32_t), st));
         const int fgrid = (int)std::min<long long>(cap, (total + 2047) / 2048);
@@ -354,8 +465,6 @@ extern "C" int mb200_binary_stat_counts(const void* preds, int preds_dtype, cons
         }
         count_launch();
     }
-    const bool flat = float_preds && !samplewise && num_labels == 1 && target_dtype == MB200_I64 &&
-                      ((reinterpret_cast<uintptr_t>(preds) | reinterpret_cast<uintptr_t>(target)) & 15) == 0;
     if (flat) {
         switch (preds_dtype) {
             case MB200_F32: bin_count_flat_kernel<float><<<grid, 256, 0, st>>>(a); break;
@@ -385,4 +494,22 @@ extern "C" int mb200_binary_stat_counts(const void* preds, int preds_dtype, cons
     }
     count_launch();
     return check_cuda(cudaGetLastError(), "binary stat counts launch");
+}
+
+extern "C" int mb200_binary_stat_counts(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                        int64_t n_outer, int64_t num_labels, int64_t inner, double threshold,
+                                        int has_ignore_index, int64_t ignore_index, int samplewise, int64_t* counts,
+                                        uint32_t* flag_scratch, uint32_t* err_flag, void* stream) {
+    return binary_stat_counts_impl(preds, preds_dtype, target, target_dtype, n_outer, num_labels, inner, threshold,
+                                   has_ignore_index, ignore_index, samplewise, counts, flag_scratch, 4, err_flag, stream);
+}
+
+// Same contract with a larger caller-owned scratch (>= MB200_BINARY_SCRATCH_BYTES, 8-byte aligned): lets the binary task count
+// in ONE pass over the scores (both outcomes of the logits vote at once, see bin_count_flat_both_kernel).
+extern "C" int mb200_binary_stat_counts_scratch(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                                int64_t n_outer, int64_t num_labels, int64_t inner, double threshold,
+                                                int has_ignore_index, int64_t ignore_index, int samplewise, int64_t* counts,
+                                                uint32_t* scratch, int64_t scratch_bytes, uint32_t* err_flag, void* stream) {
+    return binary_stat_counts_impl(preds, preds_dtype, target, target_dtype, n_outer, num_labels, inner, threshold,
+                                   has_ignore_index, ignore_index, samplewise, counts, scratch, scratch_bytes, err_flag, stream);
 }
