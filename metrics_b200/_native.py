@@ -91,6 +91,8 @@ SIGNATURES = {
     "mb200_argmax_rows": ("i", "piqqqpp"),
     "mb200_curve_sigmoid_if_logits": ("i", "piqppp"),
     "mb200_curve_softmax_if_logits": ("i", "piqqppp"),
+    "mb200_curve_normalize_scratch_bytes": ("q", "q"),
+    "mb200_curve_sigmoid_if_logits_scratch": ("i", "piqppqp"),
     "mb200_curve_workspace_bytes": ("q", "qq"),
     "mb200_curve_workspace_bytes_for": ("q", "qqi"),
     "mb200_curve_weighted_workspace_bytes": ("q", "qi"),
@@ -338,9 +340,16 @@ def sigmoid_if_logits(preds: Tensor) -> Tensor:
     if preds.numel() == 0:
         return out
     st = stream_handle(dev)
+    n = preds.numel()
     with on_device(dev):
-        rc = lib().mb200_curve_sigmoid_if_logits(ptr(preds), tag(preds), i64(preds.numel()), ptr(out),
-                                                 ptr(_flag_scratch(dev, st)), st)
+        if n <= 32768:  # one-CTA kernel: the shared per-stream vote word is all it needs
+            rc = lib().mb200_curve_sigmoid_if_logits(preds.data_ptr(), tag(preds), n, out.data_ptr(),
+                                                     _flag_scratch(dev, st).data_ptr(), st)
+        else:  # large batches: speculative single pass, needs one byte of scratch per 16 KB tile
+            nbytes = int(lib().mb200_curve_normalize_scratch_bytes(n))
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            rc = lib().mb200_curve_sigmoid_if_logits_scratch(preds.data_ptr(), tag(preds), n, out.data_ptr(),
+                                                             scratch.data_ptr(), nbytes, st)
     if rc != 0:
         check(rc, "curve_sigmoid_if_logits")
     return out

@@ -160,8 +160,7 @@ __global__ void __launch_bounds__(256) binned_bucket_kernel(const T* __restrict_
 // memory stall in sight): runtime label dtype switch, 64-bit indexing, class division, loop-shaped bucket search.  The binary
 // task (C == 1, the shape of cfg3's binned variant) gets its own kernel: f32 scores, int64 / int32 / uint8-family labels
 // resolved at compile time, 16-byte vector loads of four scores (+ their four labels), 32-bit indices, thresholds in shared
-// memory, and a branch-free bucket search — uniform-grid hint, two corrective steps up and two down, verified against the
-// real thresholds (the hint can only cost time: an unsettled bucket falls back to the binary search).
+// memory, and a table-driven bucket search (one shared-memory lookup for most scores, see `bucket_of` below).
 template <typename LabelT>
 __device__ __forceinline__ void load4_labels(const LabelT* __restrict__ t, unsigned q, long long (&out)[4]) {
     if constexpr (sizeof(LabelT) == 8) {
@@ -177,37 +176,63 @@ __device__ __forceinline__ void load4_labels(const LabelT* __restrict__ t, unsig
     }
 }
 
+constexpr int kBinCells = 4096;
 template <typename LabelT>
 __global__ void __launch_bounds__(256) binned_binary_fast_kernel(const float* __restrict__ preds, const LabelT* __restrict__ target,
                                                                  unsigned n, const float* __restrict__ thr, int nthr,
                                                                  unsigned long long* __restrict__ scratch,
                                                                  long long* __restrict__ confmat) {
-    extern __shared__ unsigned sh_fast[];  // [2 * (nthr + 1)] counters, then nthr thresholds
+    extern __shared__ unsigned sh_fast[];  // [2 * (nthr + 1)] counters | nthr thresholds | kBinCells cell table
     const int stride = nthr + 1;
     const int ncnt = 2 * stride;
     float* sh_thr = reinterpret_cast<float*>(sh_fast + ncnt);
+    unsigned* cell = sh_fast + ncnt + nthr;  // per cell: low 16 bits = #thresholds in lower cells, high 16 = #thresholds inside
     for (int i = threadIdx.x; i < nthr; i += blockDim.x) sh_thr[i] = thr[i];
     for (int i = threadIdx.x; i < ncnt; i += blockDim.x) sh_fast[i] = 0;
+    for (int i = threadIdx.x; i < kBinCells; i += blockDim.x) cell[i] = 0;
     __syncthreads();
+    // Bucket of a score = k = #{thr_j <= p}.  A MONOTONE cell function f(p) = clamp(int((p - thr_0) * scale)) splits the score
+    // axis into kBinCells cells; thresholds in lower cells are certainly <= p, thresholds in higher cells certainly > p
+    // (monotonicity — whatever the rounding of f), so only the thresholds that fall into p's own cell are compared with p
+    // itself: none for ~95 % of the cells of a 200-point grid.  Exact for any threshold list; NaN lands in cell 0, passes no
+    // comparison and gets k = 0, like the reference's `preds >= thr`.
     const float t_first = sh_thr[0], t_last = sh_thr[nthr - 1];
-    const float scale = (nthr > 1 && t_last > t_first) ? (float)(nthr - 1) / (t_last - t_first) : 0.f;
-    auto bucket_of = [&](float p) -> int {  // k = #{thr_j <= p}; NaN -> 0 (every comparison is false)
+    const float scale = (nthr > 1 && t_last > t_first) ? (float)(kBinCells - 2) / (t_last - t_first) : 0.f;
+    auto cell_of = [&](float p) -> int {
         const float h = (p - t_first) * scale;
-        int k = h >= (float)nthr ? nthr : (h > 0.f ? (int)h : 0);
-        k += (k < nthr && sh_thr[min(k, nthr - 1)] <= p);
-        k += (k < nthr && sh_thr[min(k, nthr - 1)] <= p);
-        k -= (k > 0 && !(sh_thr[max(k - 1, 0)] <= p));
-        k -= (k > 0 && !(sh_thr[max(k - 1, 0)] <= p));
-        const bool settled = (k == nthr || !(sh_thr[min(k, nthr - 1)] <= p)) && (k == 0 || sh_thr[max(k - 1, 0)] <= p);
-        if (!settled) {
-            int lo = 0, hi = nthr;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (sh_thr[mid] <= p) lo = mid + 1;
-                else hi = mid;
-            }
-            k = lo;
+        return h >= (float)(kBinCells - 1) ? kBinCells - 1 : (h > 0.f ? (int)h : 0);
+    };
+    for (int j = threadIdx.x; j < nthr; j += blockDim.x) atomicAdd(&cell[cell_of(sh_thr[j])], 1u << 16);
+    __syncthreads();
+    {  // exclusive prefix of the per-cell counts -> low half (kBinCells / 256 consecutive cells per thread + block scan)
+        constexpr int kPer = kBinCells / 256;
+        __shared__ unsigned wsum[8];
+        unsigned local = 0;
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) local += cell[threadIdx.x * kPer + i] >> 16;
+        unsigned incl = local;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += v;
         }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned run = incl - local;
+        for (int w = 0; w < warp; ++w) run += wsum[w];
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            const unsigned e = cell[threadIdx.x * kPer + i];
+            cell[threadIdx.x * kPer + i] = e | run;
+            run += e >> 16;
+        }
+    }
+    __syncthreads();
+    auto bucket_of = [&](float p) -> int {
+        const unsigned e = cell[cell_of(p)];
+        int k = (int)(e & 0xffffu);
+        for (unsigned j = e >> 16; j > 0; --j) k += (sh_thr[(e & 0xffffu) + j - 1] <= p);  // thresholds sharing p's cell
         return k;
     };
     auto commit = [&](long long t, float p) {
@@ -298,9 +323,10 @@ static int binned_update_impl(int multilabel, const void* preds, int preds_dtype
     // binary fast path: f32 scores, 16-byte aligned inputs, the usual label dtypes, counters + thresholds in shared memory
     const bool label_ok = target_dtype == MB200_I64 || target_dtype == MB200_I32 || target_dtype == MB200_U8 ||
                           target_dtype == MB200_BOOL || target_dtype == MB200_I8;
-    if (!multilabel && num_classes == 1 && preds_dtype == MB200_F32 && label_ok && num_thresholds <= 4096 && n < (1ll << 31) &&
+    if (!multilabel && num_classes == 1 && preds_dtype == MB200_F32 && label_ok && num_thresholds <= 2048 && n < (1ll << 31) &&
         n >= 4096 && ((reinterpret_cast<uintptr_t>(preds) | reinterpret_cast<uintptr_t>(target)) & 15) == 0) {
-        const size_t smem_fast = (size_t)(2 * (num_thresholds + 1)) * sizeof(unsigned) + (size_t)num_thresholds * sizeof(float);
+        const size_t smem_fast = (size_t)(2 * (num_thresholds + 1)) * sizeof(unsigned) + (size_t)num_thresholds * sizeof(float) +
+                                 (size_t)kBinCells * sizeof(unsigned);
         long long fb = (n / 4 + 256 * 4 - 1) / (256 * 4);
         const long long fcap = (long long)sm_count() * 6;
         if (fb > fcap) fb = fcap;

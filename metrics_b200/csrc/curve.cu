@@ -137,6 +137,75 @@ __global__ void __launch_bounds__(256) sigmoid_if_kernel<double>(const double* _
         out[i] = apply ? 1.0 / (1.0 + exp(-x[i])) : x[i];
 }
 
+// Speculative single pass for large batches (f32 / f16 / bf16, 16-byte aligned): the vote is batch-global, but a TILE that
+// itself holds a score outside [0, 1] already knows the outcome — it writes sigmoids; a tile with all scores inside [0, 1]
+// writes them through and marks itself pending.  Real logits leave no pending tile (the chance that 4096 logits all fall in
+// [0, 1] is nil), real probabilities leave every tile pending AND the vote at "not logits": in both cases the batch was read
+// once and written once (8 B / element for f32 instead of 12) and the fix-up launch below finds nothing to do; only a batch
+// of logits with in-range stretches makes it revisit the pending tiles.
+constexpr int kSpecVecPerThread = 4;
+constexpr int kSpecTileVecs = 256 * kSpecVecPerThread;  // 16 KB of scores per tile
+template <typename T, bool kFix>
+__global__ void __launch_bounds__(256) sigmoid_spec_kernel(const T* __restrict__ x, T* __restrict__ out, long long n,
+                                                           unsigned* __restrict__ vote, unsigned char* __restrict__ pending,
+                                                           long long ntiles) {
+    constexpr int kVec = 16 / (int)sizeof(T);
+    const long long nvec = n / kVec;
+    const uint4* __restrict__ xv = reinterpret_cast<const uint4*>(x);
+    uint4* __restrict__ ov = reinterpret_cast<uint4*>(out);
+    if (kFix && *vote == 0u) return;
+    bool cta_voted = false;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (kFix && pending[tile] == 0) continue;
+        const long long v0 = tile * kSpecTileVecs + threadIdx.x;
+        uint4 q[kSpecVecPerThread];
+        bool outside = false;
+#pragma unroll
+        for (int k = 0; k < kSpecVecPerThread; ++k) {
+            const long long v = v0 + (long long)k * 256;
+            if (v < nvec) {
+                q[k] = ld_stream16(xv + v);
+                const T* e = reinterpret_cast<const T*>(&q[k]);
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) {
+                    const float f = to_float<T>(e[j]);
+                    outside |= (f < 0.f) | (f > 1.f);
+                }
+            }
+        }
+        const bool last = tile == ntiles - 1;
+        if (last)  // the (< one vector) scalar tail belongs to the last tile
+            for (long long i = nvec * kVec + threadIdx.x; i < n; i += 256) {
+                const float f = to_float<T>(x[i]);
+                outside |= (f < 0.f) | (f > 1.f);
+            }
+        const bool apply = kFix ? true : (__syncthreads_or(outside) != 0);
+        if (!kFix && threadIdx.x == 0) {
+            if (apply) {
+                if (!cta_voted) atomicOr(vote, 1u);
+                cta_voted = true;
+            } else {
+                pending[tile] = 1;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kSpecVecPerThread; ++k) {
+            const long long v = v0 + (long long)k * 256;
+            if (v < nvec) {
+                if (apply) {
+                    T* e = reinterpret_cast<T*>(&q[k]);
+#pragma unroll
+                    for (int j = 0; j < kVec; ++j) e[j] = from_float<T>(1.0f / (1.0f + expf(-to_float<T>(e[j]))));
+                }
+                ov[v] = q[k];
+            }
+        }
+        if (last)
+            for (long long i = nvec * kVec + threadIdx.x; i < n; i += 256)
+                out[i] = apply ? from_float<T>(1.0f / (1.0f + expf(-to_float<T>(x[i])))) : x[i];
+    }
+}
+
 // Small batches (n <= 1024 * kSmallItems): ONE CTA holds the whole batch in registers, votes with __syncthreads_or and
 // writes the result — one launch instead of memset + flag kernel + apply kernel (cfg3: 10 000 scores per update; the
 // launch sequence, not the 40 KB of traffic, is what an update costs).
@@ -1153,4 +1222,49 @@ extern "C" int mb200_curve_weighted_clf_curve(const void* preds, int preds_dtype
         default: set_error("scores must be f32/f16/bf16/f64 (dtype tag %d)", preds_dtype); return MB200_ERR_UNSUPPORTED;
     }
 #undef MB200_W
+}
+
+extern "C" int64_t mb200_curve_normalize_scratch_bytes(int64_t n) {
+    if (n < 0) return -1;
+    return 8 + (n / 1024 + 2);  // vote word + one byte per 16 KB tile (tiles hold >= 1024 elements)
+}
+
+// mb200_curve_sigmoid_if_logits with a caller-owned scratch of mb200_curve_normalize_scratch_bytes(n): large aligned
+// f32 / f16 / bf16 batches then take the speculative single pass (one read + one write); everything else the original path.
+extern "C" int mb200_curve_sigmoid_if_logits_scratch(const void* preds, int dtype, int64_t n, void* out, void* scratch,
+                                                     int64_t scratch_bytes, void* stream) {
+    MB200_REQUIRE(n >= 0, "negative n");
+    if (n == 0) return 0;
+    MB200_REQUIRE(preds && out && scratch, "NULL pointer");
+    MB200_REQUIRE(scratch_bytes >= mb200_curve_normalize_scratch_bytes(n), "scratch too small");
+    const bool spec = dtype != MB200_F64 && n > 1024 * kSmallItems &&
+                      ((reinterpret_cast<uintptr_t>(preds) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(scratch) & 3) == 0;
+    if (!spec) return mb200_curve_sigmoid_if_logits(preds, dtype, n, out, reinterpret_cast<uint32_t*>(scratch), stream);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int esize = dtype == MB200_F32 ? 4 : 2;
+    const long long kvec = 16 / esize;
+    const long long nvec = n / kvec;
+    const long long ntiles = (nvec + kSpecTileVecs - 1) / kSpecTileVecs + (nvec % kSpecTileVecs == 0 && n % kvec ? 1 : 0);
+    MB200_CUDA_OK(cudaMemsetAsync(scratch, 0, (size_t)(8 + ntiles), st));
+    unsigned* vote = reinterpret_cast<unsigned*>(scratch);
+    unsigned char* pending = reinterpret_cast<unsigned char*>(scratch) + 8;
+    long long grid = ntiles;
+    const long long cap = (long long)sm_count() * 8;
+    if (grid > cap) grid = cap;
+#define MB200_SPEC(T)                                                                                                         \
+    sigmoid_spec_kernel<T, false><<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), reinterpret_cast<T*>(out), n, \
+                                                                 vote, pending, ntiles);                                      \
+    sigmoid_spec_kernel<T, true><<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), reinterpret_cast<T*>(out), n,  \
+                                                                vote, pending, ntiles);
+    switch (dtype) {
+        case MB200_F32: MB200_SPEC(float) break;
+        case MB200_F16: MB200_SPEC(__half) break;
+        case MB200_BF16: MB200_SPEC(__nv_bfloat16) break;
+        default: set_error("scores must be floating point (dtype tag %d)", dtype); return MB200_ERR_INVALID;
+    }
+#undef MB200_SPEC
+    count_launch();
+    count_launch();
+    return check_cuda(cudaGetLastError(), "curve format launch");
 }

@@ -128,7 +128,7 @@ def test_binned_classes_and_large_threshold_counts(golden_binned):
 
 
 @pytest.mark.parametrize("label_dtype", [torch.int64, torch.int32, torch.uint8, torch.bool, torch.int8])
-@pytest.mark.parametrize("thr_kind", ["linspace200", "linspace3", "irregular", "single", "dense"])
+@pytest.mark.parametrize("thr_kind", ["linspace200", "linspace3", "irregular", "single", "dense", "equal"])
 def test_binary_fast_path_equals_generic_kernel_and_oracle(label_dtype, thr_kind):
     """The binary fast path of K4 (float32 scores, 16-byte aligned, n >= 4096: vector loads, branch-free bucket search) against
     the generic kernel (same data, forced by a 4-byte misaligned view) and the numpy oracle: integer confusion matrices,
@@ -140,7 +140,7 @@ def test_binary_fast_path_equals_generic_kernel_and_oracle(label_dtype, thr_kind
     g = torch.Generator().manual_seed(17)
     thr = {"linspace200": torch.linspace(0, 1, 200), "linspace3": torch.linspace(0, 1, 3),
            "irregular": torch.tensor([0.01, 0.011, 0.2, 0.5, 0.50001, 0.9, 0.97, 0.99]), "single": torch.tensor([0.5]),
-           "dense": torch.linspace(0.4, 0.6, 3000)}[thr_kind]
+           "dense": torch.linspace(0.4, 0.6, 2000), "equal": torch.full((5,), 0.25)}[thr_kind]
     p = torch.rand(n + 1, generator=g)
     p[1:4001] = thr[torch.randint(0, thr.numel(), (4000,), generator=g)]  # exactly on a threshold
     p[5000:5004] = torch.tensor([float("nan"), float("inf"), float("-inf"), -0.0])

@@ -141,6 +141,7 @@ def test_every_kernel_wrapper_calls_the_abi_as_declared(monkeypatch):
     _native.multiclass_stat_scores_samplewise(scores.reshape(4, c, 4), labels.reshape(4, 4), c, None, flag)
     _native.argmax_rows(scores)
     _native.sigmoid_if_logits(scores[:, 0])
+    _native.sigmoid_if_logits(torch.rand(40000))
     _native.softmax_if_logits(scores)
     _native.curve_evaluate(scores[:, 0], labels.clamp(max=1), 1, 1, want_curve=True)
     _native.curve_evaluate(scores, labels, c)

@@ -49,3 +49,23 @@ def test_probabilities_pass_through_untouched():
     assert torch.equal(_native.sigmoid_if_logits(p), p)
     q = torch.softmax(torch.randn(50, 9, device=DEV), 1)
     assert torch.equal(_native.softmax_if_logits(q), q)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n", [32769, 1 << 20, (1 << 22) + 3, 4096 * 257 + 1])
+def test_speculative_single_pass_sigmoid(dtype, n):
+    """Large batches take the speculative single pass (tile-local vote, pending tiles, fix-up launch): logits, probabilities,
+    and the adversarial mix — in-range stretches of tiles with ONE out-of-range score at the very end (or the very start)."""
+    g = torch.Generator().manual_seed(n)
+    logits = (torch.randn(n, generator=g) * 5).to(dtype).to(DEV)
+    assert torch.equal(_native.sigmoid_if_logits(logits), torch.sigmoid(logits))
+    probs = torch.rand(n, generator=g).to(dtype).to(DEV)
+    assert torch.equal(_native.sigmoid_if_logits(probs), probs)
+    for where in (n - 1, 0, n // 2):
+        mixed = probs.clone()
+        mixed[where] = -0.25  # a single logit: every other tile is pending and must be revisited
+        assert torch.equal(_native.sigmoid_if_logits(mixed), torch.sigmoid(mixed))
+    nan = probs.clone()
+    nan[17] = float("nan")  # NaN compares false: still probabilities
+    got = _native.sigmoid_if_logits(nan)
+    assert torch.equal(got.nan_to_num(7.0), nan.nan_to_num(7.0))
