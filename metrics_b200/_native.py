@@ -546,6 +546,22 @@ def regression_sums(preds: Tensor, target: Tensor, op: int, num_outputs: int = 1
 # ----------------------------------------------------------------------------------------------------------
 # K4 wrapper (binned curve update)
 # ----------------------------------------------------------------------------------------------------------
+_sorted_cache: dict = {}
+
+
+def _is_sorted(thr: Tensor) -> bool:
+    """Is the threshold tensor ascending?  Reading the answer is a host sync, and a metric hands the SAME buffer to every
+    update: remember it per (storage address, version counter, length)."""
+    key = (thr.data_ptr(), thr._version, thr.numel(), thr.device.index)
+    hit = _sorted_cache.get(key)
+    if hit is None:
+        hit = bool((thr[1:] >= thr[:-1]).all())
+        if len(_sorted_cache) > 256:
+            _sorted_cache.clear()
+        _sorted_cache[key] = hit
+    return hit
+
+
 def binned_curve_update(preds: Tensor, target: Tensor, thresholds: Tensor, num_classes: int = 1,
                         multilabel: bool = False) -> Tensor:
     """Multi-threshold confusion matrix of one batch: int64 ``[T, 2, 2]`` (``num_classes == 1``) or ``[T, C, 2, 2]``.
@@ -556,7 +572,7 @@ def binned_curve_update(preds: Tensor, target: Tensor, thresholds: Tensor, num_c
     target = target.contiguous()
     thr = thresholds.to(torch.float32)
     order = None
-    if thr.numel() > 1 and not bool((thr[1:] >= thr[:-1]).all()):
+    if thr.numel() > 1 and not _is_sorted(thr):
         thr, order = torch.sort(thr)
     thr = thr.contiguous()
     n = preds.shape[0] if multilabel else target.numel()

@@ -231,8 +231,11 @@ __global__ void __launch_bounds__(256) binned_binary_fast_kernel(const float* __
     __syncthreads();
     auto bucket_of = [&](float p) -> int {
         const unsigned e = cell[cell_of(p)];
-        int k = (int)(e & 0xffffu);
-        for (unsigned j = e >> 16; j > 0; --j) k += (sh_thr[(e & 0xffffu) + j - 1] <= p);  // thresholds sharing p's cell
+        const int k_lo = (int)(e & 0xffffu);
+        const unsigned inside = e >> 16;  // thresholds sharing p's cell: 0 for most cells, 1 for the rest of a regular grid
+        int k = k_lo + (int)((inside != 0u) & (sh_thr[min(k_lo, nthr - 1)] <= p));  // branch-free for inside <= 1
+        if (inside > 1u)
+            for (unsigned j = 1; j < inside; ++j) k += (sh_thr[k_lo + j] <= p);
         return k;
     };
     auto commit = [&](long long t, float p) {
