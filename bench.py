@@ -325,12 +325,14 @@ def leg_cfg5(dev, rank: int, world: int, reps: int = 5) -> dict:
         for r in range(world):
             gg = torch.Generator().manual_seed(4242 + r)
             n_r = 300 + 17 * r
-            lg = (torch.randn(n_r, c_small, generator=gg) * 4).round() / 4  # many exact ties, also across ranks
-            data.append((lg, torch.randint(0, c_small, (n_r,), generator=gg)))
+            # scores already in [0, 1] (no normalisation on either side: the oracle and the kernels see the SAME numbers),
+            # quantised to 1/64 so that exact ties abound within and across ranks
+            pr = (torch.softmax(torch.randn(n_r, c_small, generator=gg) * 2, 1) * 64).round() / 64
+            data.append((pr, torch.randint(0, c_small, (n_r,), generator=gg)))
         small = MulticlassAUROC(num_classes=c_small, average=None, validate_args=False).to(dev)
         small.update(data[rank][0].to(dev), data[rank][1].to(dev))
         got = small.compute().cpu().numpy()
-        probs = torch.softmax(torch.cat([d[0] for d in data]), 1).numpy()
+        probs = torch.cat([d[0] for d in data]).numpy()
         want = oc.multiclass_auroc_exact(probs, torch.cat([d[1] for d in data]).numpy(), c_small)
         import numpy as np
 
@@ -445,6 +447,11 @@ def run_ours(args) -> dict:
     assert int(result.sum()) == N_ROWS * args.steps * world, "confusion matrix lost samples"
     assert torch.equal(result, expect), "timed + synced confusion matrix differs from the sum of isolated per-batch updates"
 
+    per_rank_ms = [ms_updates / args.steps]
+    if distributed:  # every rank's own window, for the record (the value uses the maximum)
+        slab = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(slab, torch.tensor([ms_updates / args.steps], dtype=torch.float64, device=dev))
+        per_rank_ms = [round(float(x), 6) for x in slab.tolist()]
     times = torch.tensor([ms_updates] + sync_ms, dtype=torch.float64, device=dev)
     if distributed:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -539,6 +546,7 @@ def run_ours(args) -> dict:
         "l2": f"inputs larger than L2: rotating {N_ROT} distinct 131 MB device batches ({N_ROT * 131} MB >> 126 MB L2)",
         "parallelism": f"dp{world} (independent shards, no data-path collective; one int64 all-reduce of the [C,C] state at compute())",
         "pre_warm": "0.25 s untimed spin-up after the W warm-up steps",
+        "ms_per_step_per_rank": per_rank_ms,
         "sync": {"what": "metric.compute(): all-reduce of the 8 MB int64 [C,C] state + result clone; 7 repetitions, each entered "
                          "from a barrier, device time, max over ranks" if distributed else "metric.compute() on one GPU (no collective)",
                  "compute_ms_min": min(sync_ms), "compute_ms_median": statistics.median(sync_ms), "state_bytes": N_CLASSES * N_CLASSES * 8,
