@@ -388,15 +388,23 @@ def run_ours(args) -> dict:
     pre = max(args.warmup, 3)
     for i in range(pre):
         metric.update(*dev_batches[i % N_ROT])
-    torch.cuda.synchronize(dev)
-    t_spin = time.perf_counter()  # extra untimed spin-up so clocks are at their loaded state
-    while time.perf_counter() - t_spin < 0.25:
-        for i in range(64):
-            metric.update(*dev_batches[i % N_ROT])
-        torch.cuda.synchronize(dev)
     metric.compute()  # untimed: brings up the NCCL communicator / first exchange so that it is not billed to the steps
-    metric.reset()
+    if distributed:
+        dist.barrier()  # ... and the barrier's own first collective
     sampler.wait_ready()
+    metric.reset()
+    # Untimed spin-up LAST: communicator bring-up and the sampler hand-shake leave the GPU idle for up to a second, and the
+    # first 20-step window after such a pause measures 27 us/step on 8 GPUs against 21.9 us for every later one
+    # (profiles/r02_diag_scale_8gpu.json).  The spin-up updates stay in the state: they are part of the expectation below.
+    uses = [0] * N_ROT  # how often each resident batch has been folded into the state since the reset
+    torch.cuda.synchronize(dev)
+    t_spin = time.perf_counter()
+    with torch.no_grad():
+        while time.perf_counter() - t_spin < 0.25:
+            for i in range(64):
+                metric.update(*dev_batches[i % N_ROT])
+                uses[i % N_ROT] += 1
+            torch.cuda.synchronize(dev)
 
     order = [dev_batches[i % N_ROT] for i in range(args.steps)]
     update = metric.update
@@ -435,16 +443,22 @@ def run_ours(args) -> dict:
     # update, weighted by how often the batch was cycled through; the expectations are combined over ranks by a DIFFERENT path
     # than the one under test (all_gather + local sum instead of the metric's all-reduce)
     expect = torch.zeros(N_CLASSES, N_CLASSES, dtype=torch.long, device=dev)
-    for b in range(min(N_ROT, args.steps)):
+    for b in range(N_ROT):
+        times_used = uses[b] + len(range(b, args.steps, N_ROT))  # spin-up + the K timed steps
+        if times_used == 0:
+            continue
         single = MulticlassConfusionMatrix(num_classes=N_CLASSES, validate_args=False, sync_on_compute=False).to(dev)
         single.update(*dev_batches[b])
         torch.cuda.synchronize(dev)
-        expect += single.confmat * len(range(b, args.steps, N_ROT))
+        expect += single.confmat * times_used
     if distributed:
         slab = torch.empty((world, N_CLASSES, N_CLASSES), dtype=torch.long, device=dev)
         dist.all_gather_into_tensor(slab, expect)
         expect = slab.sum(0)
-    assert int(result.sum()) == N_ROWS * args.steps * world, "confusion matrix lost samples"
+    n_updates = torch.tensor([sum(uses) + args.steps], dtype=torch.long, device=dev)
+    if distributed:
+        dist.all_reduce(n_updates)  # ranks spin for the same wall time, not the same number of updates
+    assert int(result.sum()) == N_ROWS * int(n_updates), "confusion matrix lost samples"
     assert torch.equal(result, expect), "timed + synced confusion matrix differs from the sum of isolated per-batch updates"
 
     per_rank_ms = [ms_updates / args.steps]
@@ -545,7 +559,7 @@ def run_ours(args) -> dict:
         "units_per_step_per_gpu": UNITS_PER_STEP, "validate_args": False,
         "l2": f"inputs larger than L2: rotating {N_ROT} distinct 131 MB device batches ({N_ROT * 131} MB >> 126 MB L2)",
         "parallelism": f"dp{world} (independent shards, no data-path collective; one int64 all-reduce of the [C,C] state at compute())",
-        "pre_warm": "0.25 s untimed spin-up after the W warm-up steps",
+        "pre_warm": "W warm-up steps, NCCL bring-up, then 0.25 s of untimed updates immediately before the timed window",
         "ms_per_step_per_rank": per_rank_ms,
         "sync": {"what": "metric.compute(): all-reduce of the 8 MB int64 [C,C] state + result clone; 7 repetitions, each entered "
                          "from a barrier, device time, max over ranks" if distributed else "metric.compute() on one GPU (no collective)",

@@ -145,7 +145,11 @@ def sync_states_bucketed(metric: Any, group: Optional[Any]) -> bool:
         desc = torch.zeros((len(cat_states), 2 + _MAX_DIMS), dtype=torch.int64)
         for i, t in enumerate(locals_):
             if t.ndim > _MAX_DIMS or t.dtype not in _DTYPE_CODES:
-                return False
+                # not expressible in the descriptor: say so IN the descriptor, so that every rank — also one that holds an
+                # empty placeholder of another dtype — routes this state through the generic gather together (returning False
+                # here would be a rank-local decision taken after the integer buckets above were already reduced)
+                desc[i, 0] = -1
+                continue
             desc[i, 0] = t.ndim
             desc[i, 1] = _DTYPE_CODES.index(t.dtype)
             for d, s in enumerate(t.shape):
@@ -154,6 +158,10 @@ def sync_states_bucketed(metric: Any, group: Optional[Any]) -> bool:
         all_desc = _gather_equal(desc, group, world).cpu()  # [world, n_states, 2 + MAX_DIMS]; the one host sync
         for i, n in enumerate(cat_states):
             t = locals_[i]
+            if any(int(all_desc[r, i, 0]) < 0 for r in range(world)):
+                pieces = gather_all_tensors(t, group=group)
+                setattr(metric, n, dim_zero_cat([p for p in pieces if p.numel() > 0] or [t]))
+                continue
             shapes = [tuple(int(x) for x in all_desc[r, i, 2: 2 + int(all_desc[r, i, 0])]) for r in range(world)]
             numels = [int(torch.Size(s).numel()) for s in shapes]
             nonempty = [r for r in range(world) if numels[r] > 0]
