@@ -499,12 +499,14 @@ def binary_stat_counts(
     if counts is None:
         counts = torch.zeros((groups, 4), dtype=torch.int64, device=dev)
     # scratch for the logits vote; large enough (MB200_BINARY_SCRATCH_BYTES) for the single-pass binary kernel's two count sets
-    scratch = torch.empty(32, dtype=torch.int32, device=dev) if preds.is_floating_point() else None
+    # (multilabel, L <= 256: two [L, 4] count sets = 64 L bytes behind the vote word)
+    words = 32 if num_labels == 1 or num_labels > 256 or samplewise else 4 + 16 * num_labels
+    scratch = torch.empty(words, dtype=torch.int32, device=dev) if preds.is_floating_point() else None
     with on_device(dev):
         rc = lib().mb200_binary_stat_counts_scratch(
             ptr(preds), tag(preds), ptr(target), tag(target), i64(n_outer), i64(num_labels), i64(max(1, inner)),
             ctypes.c_double(float(threshold)), int(ignore_index is not None), i64(ignore_index or 0), int(samplewise),
-            ptr(counts), ptr(scratch), 128, ptr(err_flag), stream_handle(dev),
+            ptr(counts), ptr(scratch), 4 * words, ptr(err_flag), stream_handle(dev),
         )
     check(rc, "binary_stat_counts")
     return counts
