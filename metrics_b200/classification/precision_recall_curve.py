@@ -53,9 +53,9 @@ class BinaryPrecisionRecallCurve(Metric):
             _binary_precision_recall_curve_arg_validation(thresholds, ignore_index)
         self.ignore_index = ignore_index
         self.validate_args = validate_args
-        self._install_curve_states(thresholds, lambda n_thr: (n_thr, 2, 2))
+        self._install_curve_states(thresholds, lambda n_thr: (n_thr, 2, 2), arena=True)
 
-    def _install_curve_states(self, thresholds, binned_shape) -> None:
+    def _install_curve_states(self, thresholds, binned_shape, arena: bool = False) -> None:
         """Exact mode (``thresholds=None``): list states ``preds`` / ``target`` (``cat``).  Binned mode: a non-persistent
         ``thresholds`` buffer and ONE constant-size int64 ``confmat`` state of shape ``binned_shape(T)`` (``sum``)."""
         grid = _adjust_threshold_arg(thresholds)
@@ -63,6 +63,11 @@ class BinaryPrecisionRecallCurve(Metric):
             self.thresholds = None
             for name in ("preds", "target"):
                 self.add_state(name, default=[], dist_reduce_fx="cat")
+            if arena:  # binary task: the two lists are views of growing buffers from the start (utilities/arena.py)
+                from metrics_b200.utilities.arena import ArenaList
+
+                for name in ("preds", "target"):
+                    setattr(self, name, ArenaList())
         else:
             self.register_buffer("thresholds", grid, persistent=False)
             self.add_state("confmat", default=torch.zeros(*binned_shape(len(grid)), dtype=torch.long), dist_reduce_fx="sum")
@@ -117,13 +122,44 @@ class BinaryPrecisionRecallCurve(Metric):
         self._group_cache.clear()
         if self.validate_args:
             _binary_precision_recall_curve_tensor_validation(preds, target, self.ignore_index)
+        if self.thresholds is None and self.ignore_index is None and self._append_to_arena(preds, target):
+            return
         preds, target, _ = _binary_precision_recall_curve_format(preds, target, self.thresholds, self.ignore_index)
         state = _binary_precision_recall_curve_update(preds, target, self.thresholds)
         self._accumulate(state)
 
+    def _append_to_arena(self, preds: Tensor, target: Tensor) -> bool:
+        """Exact mode without ``ignore_index``: format + append in ONE launch, straight into the growing buffers behind the
+        two list states (`utilities/arena.py`), so that ``compute()`` need not concatenate.  False = use the generic path."""
+        from metrics_b200 import _native
+        from metrics_b200.utilities.arena import ArenaList
+
+        if not (preds.is_floating_point() and not target.is_floating_point() and preds.device == target.device
+                and target.numel() == preds.numel() and preds.numel() > 0 and not self.compute_on_cpu):
+            return False
+        lists = []
+        for name, t in (("preds", preds), ("target", target)):
+            current = getattr(self, name)  # arena-backed since construction (`_install_curve_states`); a plain list means
+            # something rebuilt the state (device move with data, unsync, load_state_dict, forward's restore): generic path
+            if not (isinstance(current, ArenaList) and current.accepts(t.numel(), t.dtype, t.device)):
+                return False
+            lists.append(current)
+        p_flat, t_flat = preds.reshape(-1).contiguous(), target.reshape(-1).contiguous()
+        out_p = lists[0].reserve(p_flat.numel(), p_flat.dtype, p_flat.device)
+        out_t = lists[1].reserve(t_flat.numel(), t_flat.dtype, t_flat.device)
+        _native.sigmoid_if_logits_append(p_flat, t_flat, out_p, out_t)
+        lists[0].commit(out_p)
+        lists[1].commit(out_t)
+        return True
+
     def _state(self):
         if self.thresholds is not None:
             return self.confmat
+        from metrics_b200.utilities.arena import ArenaList
+
+        packed = [s.packed() if isinstance(s, ArenaList) else None for s in (self.preds, self.target)]
+        if packed[0] is not None and packed[1] is not None:
+            return packed[0], packed[1]
         return dim_zero_cat(self.preds), dim_zero_cat(self.target)
 
     def compute(self) -> tuple[Tensor, Tensor, Tensor]:
