@@ -358,11 +358,16 @@ def sigmoid_if_logits(preds: Tensor) -> Tensor:
 
 def sigmoid_if_logits_append(preds: Tensor, target: Tensor, out_preds: Tensor, out_target: Tensor) -> None:
     """``normalize_logits_if_needed(preds, "sigmoid")`` written into ``out_preds`` and ``target`` copied into ``out_target``
-    (``mb200_curve_sigmoid_append``): the per-batch step of an arena-backed exact curve state — one launch for small batches."""
-    dev = require_cuda(preds, target, out_preds, out_target)
+    (``mb200_curve_sigmoid_append``): the per-batch step of an arena-backed exact curve state — one launch for small batches.
+    The outputs are slices of buffers the caller allocated on the inputs' device; only the inputs are checked."""
+    if not preds.is_cuda or not target.is_cuda:
+        require_cuda(preds, target)
+    dev = preds.device
     n = preds.numel()
-    if n == 0:
-        return
+    if not preds.is_contiguous():
+        preds = preds.contiguous()
+    if not target.is_contiguous():
+        target = target.contiguous()
     st = stream_handle(dev)
     with on_device(dev):
         if n <= 32768:
@@ -371,8 +376,7 @@ def sigmoid_if_logits_append(preds: Tensor, target: Tensor, out_preds: Tensor, o
             nbytes = int(lib().mb200_curve_normalize_scratch_bytes(n))
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         rc = lib().mb200_curve_sigmoid_append(preds.data_ptr(), tag(preds), n, out_preds.data_ptr(), target.data_ptr(),
-                                              target.numel() * target.element_size(), out_target.data_ptr(),
-                                              scratch.data_ptr(), nbytes, st)
+                                              n * target.element_size(), out_target.data_ptr(), scratch.data_ptr(), nbytes, st)
     if rc != 0:
         check(rc, "curve_sigmoid_append")
 

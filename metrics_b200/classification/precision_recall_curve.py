@@ -30,7 +30,9 @@ from metrics_b200.functional.classification.precision_recall_curve import (
     _multilabel_precision_recall_curve_tensor_validation,
     _multilabel_precision_recall_curve_update,
 )
+from metrics_b200 import _native
 from metrics_b200.metric import Metric
+from metrics_b200.utilities.arena import ArenaList
 from metrics_b200.utilities.data import dim_zero_cat
 
 
@@ -64,8 +66,6 @@ class BinaryPrecisionRecallCurve(Metric):
             for name in ("preds", "target"):
                 self.add_state(name, default=[], dist_reduce_fx="cat")
             if arena:  # binary task: the two lists are views of growing buffers from the start (utilities/arena.py)
-                from metrics_b200.utilities.arena import ArenaList
-
                 for name in ("preds", "target"):
                     setattr(self, name, ArenaList())
         else:
@@ -130,33 +130,42 @@ class BinaryPrecisionRecallCurve(Metric):
 
     def _append_to_arena(self, preds: Tensor, target: Tensor) -> bool:
         """Exact mode without ``ignore_index``: format + append in ONE launch, straight into the growing buffers behind the
-        two list states (`utilities/arena.py`), so that ``compute()`` need not concatenate.  False = use the generic path."""
-        from metrics_b200 import _native
-        from metrics_b200.utilities.arena import ArenaList
-
-        if not (preds.is_floating_point() and not target.is_floating_point() and preds.device == target.device
-                and target.numel() == preds.numel() and preds.numel() > 0 and not self.compute_on_cpu):
+        two list states (`utilities/arena.py`), so that ``compute()`` need not concatenate.  False = use the generic path.
+        (Written flat on purpose: this runs once per ``update`` and a small update is all host time.)"""
+        pl, tl = self.preds, self.target
+        if type(pl) is not ArenaList or type(tl) is not ArenaList or self.compute_on_cpu:
+            return False  # a plain list: something rebuilt the state (device move with data, unsync, load_state_dict, forward)
+        n = preds.numel()
+        sizes = pl.sizes
+        if n == 0 or target.numel() != n or len(pl) != len(sizes) or len(tl) != len(sizes):
             return False
-        lists = []
-        for name, t in (("preds", preds), ("target", target)):
-            current = getattr(self, name)  # arena-backed since construction (`_install_curve_states`); a plain list means
-            # something rebuilt the state (device move with data, unsync, load_state_dict, forward's restore): generic path
-            if not (isinstance(current, ArenaList) and current.accepts(t.numel(), t.dtype, t.device)):
+        pb, tb = pl.buffer, tl.buffer
+        used = pl.used
+        need = used + n
+        if pb is None or need > pb.numel():
+            if pb is None:
+                if not preds.is_floating_point() or target.is_floating_point() or preds.device != target.device:
+                    return False
+            elif pb.dtype != preds.dtype or tb.dtype != target.dtype or pb.device != preds.device:
                 return False
-            lists.append(current)
-        p_flat, t_flat = preds.reshape(-1).contiguous(), target.reshape(-1).contiguous()
-        out_p = lists[0].reserve(p_flat.numel(), p_flat.dtype, p_flat.device)
-        out_t = lists[1].reserve(t_flat.numel(), t_flat.dtype, t_flat.device)
-        _native.sigmoid_if_logits_append(p_flat, t_flat, out_p, out_t)
-        lists[0].commit(out_p)
-        lists[1].commit(out_t)
+            pl.grow(need, preds.dtype, preds.device)
+            tl.grow(need, target.dtype, target.device)
+            pb, tb = pl.buffer, tl.buffer
+        elif pb.dtype != preds.dtype or tb.dtype != target.dtype or pb.device != preds.device:
+            return False
+        out_p, out_t = pb[used:need], tb[used:need]
+        _native.sigmoid_if_logits_append(preds if preds.ndim == 1 else preds.reshape(-1),
+                                         target if target.ndim == 1 else target.reshape(-1), out_p, out_t)
+        list.append(pl, out_p)
+        list.append(tl, out_t)
+        pl.used = tl.used = need
+        sizes.append(n)
+        tl.sizes.append(n)
         return True
 
     def _state(self):
         if self.thresholds is not None:
             return self.confmat
-        from metrics_b200.utilities.arena import ArenaList
-
         packed = [s.packed() if isinstance(s, ArenaList) else None for s in (self.preds, self.target)]
         if packed[0] is not None and packed[1] is not None:
             return packed[0], packed[1]

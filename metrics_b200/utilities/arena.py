@@ -41,30 +41,16 @@ class ArenaList(list):
         return (self.buffer is not None and isinstance(last, Tensor) and last.dtype == self.buffer.dtype
                 and last.data_ptr() == self.buffer.data_ptr() + (self.used - self.sizes[-1]) * self.buffer.element_size())
 
-    def accepts(self, n: int, dtype: torch.dtype, device: torch.device) -> bool:
-        """Can the next batch (``n`` elements of ``dtype`` on ``device``) be placed behind the ones already here?"""
-        if not self.consistent():
-            return False
-        return self.buffer is None or (self.buffer.dtype == dtype and self.buffer.device == device)
-
-    def reserve(self, n: int, dtype: torch.dtype, device: torch.device) -> Tensor:
-        """The next ``n`` elements of the buffer (grown by doubling; existing entries are re-pointed at the new buffer)."""
-        need = self.used + n
-        if self.buffer is None or self.buffer.numel() < need:
-            cap = max(need, 2 * (self.buffer.numel() if self.buffer is not None else 0), 1 << 16)
-            grown = torch.empty(cap, dtype=dtype, device=device)
-            if self.used:
-                grown[: self.used].copy_(self.buffer[: self.used])
-                super().clear()
-                super().extend(torch.split(grown[: self.used], self.sizes))
-            self.buffer = grown
-        return self.buffer[self.used: need]
-
-    def commit(self, view: Tensor) -> None:
-        """The view handed out by `reserve` now holds a batch: make it the next list entry."""
-        super().append(view)
-        self.used += view.numel()
-        self.sizes.append(view.numel())
+    def grow(self, need: int, dtype: torch.dtype, device: torch.device) -> None:
+        """Make room for ``need`` elements in total (doubling); existing entries are re-pointed at the new buffer."""
+        old = self.buffer
+        cap = max(need, 2 * (old.numel() if old is not None else 0), 1 << 16)
+        grown = torch.empty(cap, dtype=dtype, device=device)
+        if self.used:
+            grown[: self.used].copy_(old[: self.used])
+            super().clear()
+            super().extend(torch.split(grown[: self.used], self.sizes))
+        self.buffer = grown
 
     def packed(self) -> Optional[Tensor]:
         """All entries as ONE tensor without a copy, or ``None`` when the list was changed behind the arena's back."""
