@@ -150,11 +150,6 @@ MB200_API int mb200_curve_sigmoid_if_logits(const void* preds, int dtype, int64_
 MB200_API int64_t mb200_curve_normalize_scratch_bytes(int64_t n);
 MB200_API int mb200_curve_sigmoid_if_logits_scratch(const void* preds, int dtype, int64_t n, void* out, void* scratch,
                                                     int64_t scratch_bytes, void* stream);
-/* Format + append for arena-backed list states: mb200_curve_sigmoid_if_logits[_scratch] into `out` plus a copy of the batch's
- * `target_bytes` bytes of targets into `target_out` (small batches: one launch for both). */
-MB200_API int mb200_curve_sigmoid_append(const void* preds, int dtype, int64_t n, void* out, const void* target,
-                                         int64_t target_bytes, void* target_out, void* scratch, int64_t scratch_bytes,
-                                         void* stream);
 MB200_API int mb200_curve_softmax_if_logits(const void* preds, int dtype, int64_t n, int64_t num_classes, void* out,
                                             uint32_t* flag_scratch, void* stream);
 

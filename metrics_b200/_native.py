@@ -93,7 +93,6 @@ SIGNATURES = {
     "mb200_curve_softmax_if_logits": ("i", "piqqppp"),
     "mb200_curve_normalize_scratch_bytes": ("q", "q"),
     "mb200_curve_sigmoid_if_logits_scratch": ("i", "piqppqp"),
-    "mb200_curve_sigmoid_append": ("i", "piqppqppqp"),
     "mb200_curve_workspace_bytes": ("q", "qq"),
     "mb200_curve_workspace_bytes_for": ("q", "qqi"),
     "mb200_curve_weighted_workspace_bytes": ("q", "qi"),
@@ -354,31 +353,6 @@ def sigmoid_if_logits(preds: Tensor) -> Tensor:
     if rc != 0:
         check(rc, "curve_sigmoid_if_logits")
     return out
-
-
-def sigmoid_if_logits_append(preds: Tensor, target: Tensor, out_preds: Tensor, out_target: Tensor) -> None:
-    """``normalize_logits_if_needed(preds, "sigmoid")`` written into ``out_preds`` and ``target`` copied into ``out_target``
-    (``mb200_curve_sigmoid_append``): the per-batch step of an arena-backed exact curve state — one launch for small batches.
-    The outputs are slices of buffers the caller allocated on the inputs' device; only the inputs are checked."""
-    if not preds.is_cuda or not target.is_cuda:
-        require_cuda(preds, target)
-    dev = preds.device
-    n = preds.numel()
-    if not preds.is_contiguous():
-        preds = preds.contiguous()
-    if not target.is_contiguous():
-        target = target.contiguous()
-    st = stream_handle(dev)
-    with on_device(dev):
-        if n <= 32768:
-            scratch, nbytes = _flag_scratch(dev, st), 4
-        else:
-            nbytes = int(lib().mb200_curve_normalize_scratch_bytes(n))
-            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        rc = lib().mb200_curve_sigmoid_append(preds.data_ptr(), tag(preds), n, out_preds.data_ptr(), target.data_ptr(),
-                                              n * target.element_size(), out_target.data_ptr(), scratch.data_ptr(), nbytes, st)
-    if rc != 0:
-        check(rc, "curve_sigmoid_append")
 
 
 def softmax_if_logits(preds: Tensor) -> Tensor:

@@ -30,9 +30,7 @@ from metrics_b200.functional.classification.precision_recall_curve import (
     _multilabel_precision_recall_curve_tensor_validation,
     _multilabel_precision_recall_curve_update,
 )
-from metrics_b200 import _native
 from metrics_b200.metric import Metric
-from metrics_b200.utilities.arena import ArenaList
 from metrics_b200.utilities.data import dim_zero_cat
 
 
@@ -55,9 +53,9 @@ class BinaryPrecisionRecallCurve(Metric):
             _binary_precision_recall_curve_arg_validation(thresholds, ignore_index)
         self.ignore_index = ignore_index
         self.validate_args = validate_args
-        self._install_curve_states(thresholds, lambda n_thr: (n_thr, 2, 2), arena=True)
+        self._install_curve_states(thresholds, lambda n_thr: (n_thr, 2, 2))
 
-    def _install_curve_states(self, thresholds, binned_shape, arena: bool = False) -> None:
+    def _install_curve_states(self, thresholds, binned_shape) -> None:
         """Exact mode (``thresholds=None``): list states ``preds`` / ``target`` (``cat``).  Binned mode: a non-persistent
         ``thresholds`` buffer and ONE constant-size int64 ``confmat`` state of shape ``binned_shape(T)`` (``sum``)."""
         grid = _adjust_threshold_arg(thresholds)
@@ -65,9 +63,6 @@ class BinaryPrecisionRecallCurve(Metric):
             self.thresholds = None
             for name in ("preds", "target"):
                 self.add_state(name, default=[], dist_reduce_fx="cat")
-            if arena:  # binary task: the two lists are views of growing buffers from the start (utilities/arena.py)
-                for name in ("preds", "target"):
-                    setattr(self, name, ArenaList())
         else:
             self.register_buffer("thresholds", grid, persistent=False)
             self.add_state("confmat", default=torch.zeros(*binned_shape(len(grid)), dtype=torch.long), dist_reduce_fx="sum")
@@ -122,53 +117,13 @@ class BinaryPrecisionRecallCurve(Metric):
         self._group_cache.clear()
         if self.validate_args:
             _binary_precision_recall_curve_tensor_validation(preds, target, self.ignore_index)
-        if self.thresholds is None and self.ignore_index is None and self._append_to_arena(preds, target):
-            return
         preds, target, _ = _binary_precision_recall_curve_format(preds, target, self.thresholds, self.ignore_index)
         state = _binary_precision_recall_curve_update(preds, target, self.thresholds)
         self._accumulate(state)
 
-    def _append_to_arena(self, preds: Tensor, target: Tensor) -> bool:
-        """Exact mode without ``ignore_index``: format + append in ONE launch, straight into the growing buffers behind the
-        two list states (`utilities/arena.py`), so that ``compute()`` need not concatenate.  False = use the generic path.
-        (Written flat on purpose: this runs once per ``update`` and a small update is all host time.)"""
-        pl, tl = self.preds, self.target
-        if type(pl) is not ArenaList or type(tl) is not ArenaList or self.compute_on_cpu:
-            return False  # a plain list: something rebuilt the state (device move with data, unsync, load_state_dict, forward)
-        n = preds.numel()
-        sizes = pl.sizes
-        if n == 0 or target.numel() != n or len(pl) != len(sizes) or len(tl) != len(sizes):
-            return False
-        pb, tb = pl.buffer, tl.buffer
-        used = pl.used
-        need = used + n
-        if pb is None or need > pb.numel():
-            if pb is None:
-                if not preds.is_floating_point() or target.is_floating_point() or preds.device != target.device:
-                    return False
-            elif pb.dtype != preds.dtype or tb.dtype != target.dtype or pb.device != preds.device:
-                return False
-            pl.grow(need, preds.dtype, preds.device)
-            tl.grow(need, target.dtype, target.device)
-            pb, tb = pl.buffer, tl.buffer
-        elif pb.dtype != preds.dtype or tb.dtype != target.dtype or pb.device != preds.device:
-            return False
-        out_p, out_t = pb[used:need], tb[used:need]
-        _native.sigmoid_if_logits_append(preds if preds.ndim == 1 else preds.reshape(-1),
-                                         target if target.ndim == 1 else target.reshape(-1), out_p, out_t)
-        list.append(pl, out_p)
-        list.append(tl, out_t)
-        pl.used = tl.used = need
-        sizes.append(n)
-        tl.sizes.append(n)
-        return True
-
     def _state(self):
         if self.thresholds is not None:
             return self.confmat
-        packed = [s.packed() if isinstance(s, ArenaList) else None for s in (self.preds, self.target)]
-        if packed[0] is not None and packed[1] is not None:
-            return packed[0], packed[1]
         return dim_zero_cat(self.preds), dim_zero_cat(self.target)
 
     def compute(self) -> tuple[Tensor, Tensor, Tensor]:

@@ -212,21 +212,8 @@ __global__ void __launch_bounds__(256) sigmoid_spec_kernel(const T* __restrict__
 constexpr int kSmallItems = 32;
 constexpr int kSmallItemsF64 = 12;
 template <typename T, int kItems>
-__global__ void __launch_bounds__(1024) sigmoid_if_small_kernel(const T* __restrict__ x, T* __restrict__ out, int n,
-                                                                const unsigned char* __restrict__ tsrc = nullptr,
-                                                                unsigned char* __restrict__ tdst = nullptr, long long tbytes = 0) {
+__global__ void __launch_bounds__(1024) sigmoid_if_small_kernel(const T* __restrict__ x, T* __restrict__ out, int n) {
     constexpr int kSmallItems = kItems;
-    // optional rider: append the batch's targets next to its scores (arena-backed list states: one launch per update)
-    if (tsrc != nullptr) {
-        if (((reinterpret_cast<uintptr_t>(tsrc) | reinterpret_cast<uintptr_t>(tdst)) & 15) == 0) {
-            const long long nv = tbytes >> 4;
-            for (long long i = threadIdx.x; i < nv; i += 1024)
-                reinterpret_cast<uint4*>(tdst)[i] = reinterpret_cast<const uint4*>(tsrc)[i];
-            for (long long i = (nv << 4) + threadIdx.x; i < tbytes; i += 1024) tdst[i] = tsrc[i];
-        } else {
-            for (long long i = threadIdx.x; i < tbytes; i += 1024) tdst[i] = tsrc[i];
-        }
-    }
     T v[kSmallItems];
     bool bad = false;
 #pragma unroll
@@ -1280,31 +1267,4 @@ extern "C" int mb200_curve_sigmoid_if_logits_scratch(const void* preds, int dtyp
     count_launch();
     count_launch();
     return check_cuda(cudaGetLastError(), "curve format launch");
-}
-
-// `normalize_logits_if_needed(preds, "sigmoid")` written to `out` AND the batch's targets copied to `target_out` — the
-// "format + append" step of an exact binary curve metric whose list states are views of one growing buffer
-// (classification/precision_recall_curve.py:161-170 keeps both per batch).  Small batches: ONE launch for both.
-extern "C" int mb200_curve_sigmoid_append(const void* preds, int dtype, int64_t n, void* out, const void* target,
-                                          int64_t target_bytes, void* target_out, void* scratch, int64_t scratch_bytes,
-                                          void* stream) {
-    MB200_REQUIRE(n >= 0 && target_bytes >= 0, "negative size");
-    if (n == 0) return 0;
-    MB200_REQUIRE(preds && out && target && target_out && scratch, "NULL pointer");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (n <= 1024 * (dtype == MB200_F64 ? kSmallItemsF64 : kSmallItems)) {
-        const unsigned char* ts = static_cast<const unsigned char*>(target);
-        unsigned char* td = static_cast<unsigned char*>(target_out);
-        switch (dtype) {
-            case MB200_F32: sigmoid_if_small_kernel<float, kSmallItems><<<1, 1024, 0, st>>>((const float*)preds, (float*)out, (int)n, ts, td, target_bytes); break;
-            case MB200_F16: sigmoid_if_small_kernel<__half, kSmallItems><<<1, 1024, 0, st>>>((const __half*)preds, (__half*)out, (int)n, ts, td, target_bytes); break;
-            case MB200_BF16: sigmoid_if_small_kernel<__nv_bfloat16, kSmallItems><<<1, 1024, 0, st>>>((const __nv_bfloat16*)preds, (__nv_bfloat16*)out, (int)n, ts, td, target_bytes); break;
-            case MB200_F64: sigmoid_if_small_kernel<double, kSmallItemsF64><<<1, 1024, 0, st>>>((const double*)preds, (double*)out, (int)n, ts, td, target_bytes); break;
-            default: set_error("scores must be floating point (dtype tag %d)", dtype); return MB200_ERR_INVALID;
-        }
-        count_launch();
-        return check_cuda(cudaGetLastError(), "curve format+append launch");
-    }
-    MB200_CUDA_OK(cudaMemcpyAsync(target_out, target, (size_t)target_bytes, cudaMemcpyDeviceToDevice, st));
-    return mb200_curve_sigmoid_if_logits_scratch(preds, dtype, n, out, scratch, scratch_bytes, stream);
 }

@@ -644,10 +644,7 @@ class Metric(Module, ABC):
             if isinstance(current, Tensor):
                 setattr(this, name, fn(current))
             elif isinstance(current, Sequence):
-                if len(current) > 0 or type(current) is list:
-                    setattr(this, name, [fn(v) for v in current])
-                # (an EMPTY list of a list subclass — an arena-backed state, utilities/arena.py — has nothing to move: keep
-                # the object, so that `.to(device)` right after construction does not turn it into a plain list)
+                setattr(this, name, [fn(v) for v in current])
             else:
                 raise TypeError(
                     f"Expected metric state to be either a Tensor or a list of Tensor, but encountered {current}"

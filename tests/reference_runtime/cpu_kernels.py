@@ -131,11 +131,6 @@ def sigmoid_if_logits(preds: Tensor) -> Tensor:
     return preds.sigmoid() if preds.numel() and _is_logits(preds) else preds.clone()
 
 
-def sigmoid_if_logits_append(preds: Tensor, target: Tensor, out_preds: Tensor, out_target: Tensor) -> None:
-    out_preds.copy_(sigmoid_if_logits(preds))
-    out_target.copy_(target)
-
-
 def softmax_if_logits(preds: Tensor) -> Tensor:
     return preds.softmax(1) if preds.numel() and _is_logits(preds) else preds.clone()
 
@@ -340,7 +335,7 @@ NAMES = ("launch_count", "multiclass_confmat_update_", "multiclass_stat_scores_u
          "multiclass_stat_scores_topk_update_", "multiclass_stat_scores_samplewise", "argmax_rows",
          "sigmoid_if_logits", "softmax_if_logits", "curve_evaluate", "curve_evaluate_multilabel",
          "binary_stat_counts", "regression_sums", "binned_curve_update", "coco_map_evaluate", "curve_weighted_clf_curve",
-         "multiclass_stats_softmax_update_", "sigmoid_if_logits_append")
+         "multiclass_stats_softmax_update_")
 
 
 def standins() -> dict:

@@ -12,7 +12,7 @@ from tests.conftest import ROOT
 
 SUITES = ["test_confmat_gpu", "test_topk_samplewise_gpu", "test_binary_gpu", "test_consumers_gpu", "test_curves_gpu",
           "test_multilabel_gpu", "test_binned_gpu", "test_atfixed_gpu", "test_regression_gpu", "test_logauc", "test_curves64_gpu",
-          "test_fusion_gpu", "test_arena_gpu"]
+          "test_fusion_gpu"]
 
 
 def _replay(files, *extra) -> int:

@@ -142,9 +142,6 @@ def test_every_kernel_wrapper_calls_the_abi_as_declared(monkeypatch):
     _native.argmax_rows(scores)
     _native.sigmoid_if_logits(scores[:, 0])
     _native.sigmoid_if_logits(torch.rand(40000))
-    _native.sigmoid_if_logits_append(scores[:, 0].contiguous(), labels, torch.empty(n), torch.empty(n, dtype=torch.long))
-    _native.sigmoid_if_logits_append(torch.rand(40000), torch.zeros(40000, dtype=torch.long), torch.empty(40000),
-                                     torch.empty(40000, dtype=torch.long))
     _native.softmax_if_logits(scores)
     _native.curve_evaluate(scores[:, 0], labels.clamp(max=1), 1, 1, want_curve=True)
     _native.curve_evaluate(scores, labels, c)
