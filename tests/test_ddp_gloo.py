@@ -82,6 +82,29 @@ def _scenarios(rank: int) -> None:
     vals, _ = c4.compute()
     assert tuple(vals.shape) == (5, 3) and vals[:2].sum() == 0 and vals[2:].sum() == 9
 
+    # ---- a cat state the descriptor cannot express (9 dims) next to integer sum states: it goes through the generic gather —
+    # a decision carried IN the descriptor exchange, so all ranks take it together — and the integer buckets reduced before it
+    # must not be reduced twice ---------------------------------------------------------------------------------------------
+    class Mixed(DummyIntStates):
+        def __init__(self, **kw):
+            super().__init__(n=2, **kw)
+            self.add_state("z", [], dist_reduce_fx="cat")
+
+        def update(self, v):
+            super().update(v)
+            self.z.append(torch.full((1 + rank, 1, 1, 1, 1, 1, 1, 1, 2), float(rank)))
+
+        def compute(self):
+            from metrics_b200.utilities.data import dim_zero_cat
+
+            return self.tp, dim_zero_cat(self.z)
+
+    mx = Mixed()
+    mx.update([1 + rank, 5])
+    tp, z = mx.compute()
+    assert tp.tolist() == [3, 10], tp  # 1 + 2 and 5 + 5: reduced exactly once
+    assert tuple(z.shape) == (3, 1, 1, 1, 1, 1, 1, 1, 2) and z.flatten().tolist() == [0.0, 0.0, 1.0, 1.0, 1.0, 1.0]
+
     # ---- dist_reduce_fx=None: stacked tensor / flattened list -------------------------------------------------------------
     n = DummyNone()
     n.update([1.0 * rank, 2.0])

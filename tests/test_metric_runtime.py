@@ -377,3 +377,72 @@ def test_classwise_wrapper_names_results_and_is_transparent_to_compute_groups():
     auto.update(torch.tensor([1, 2, 3]))
     assert auto.compute_groups == {0: ["a", "b"]}
     assert int(auto(torch.tensor([1, 1, 1]))["b2"]) == 2
+
+
+def test_compute_groups_compare_states_across_dtypes():
+    """Two members whose same-named states differ in dtype (long vs float32) must not raise when the collection looks for
+    compute groups: the comparison casts like the reference's `allclose` helper (utilities/data.py:242-246)."""
+    import torch
+
+    from metrics_b200 import Metric, MetricCollection
+
+    class CountLong(Metric):
+        full_state_update = False
+
+        def __init__(self, **kw):
+            super().__init__(**kw)
+            self.add_state("total", torch.tensor(0), dist_reduce_fx="sum")
+
+        def update(self, x):
+            self.total += int(x.numel())
+
+        def compute(self):
+            return self.total
+
+    class CountFloat(CountLong):
+        def __init__(self, **kw):
+            Metric.__init__(self, **kw)
+            self.add_state("total", torch.tensor(0.0), dist_reduce_fx="sum")
+
+    mc = MetricCollection({"a": CountLong(), "b": CountFloat()})
+    mc.update(torch.zeros(5))
+    mc.update(torch.zeros(3))
+    out = mc.compute()
+    assert int(out["a"]) == 8 and float(out["b"]) == 8.0
+
+
+def test_compute_on_cpu_parks_lists_and_stages_them_for_compute():
+    """`compute_on_cpu=True`: list states live in host memory between updates; `compute` sees them on the metric's device
+    (here a fake "device" = the meta of the metric's own device attribute: the staging logic is device-agnostic) and leaves
+    them parked afterwards."""
+    import torch
+
+    from metrics_b200 import Metric
+
+    seen = {}
+
+    class Cat(Metric):
+        full_state_update = False
+
+        def __init__(self, **kw):
+            super().__init__(**kw)
+            self.add_state("xs", [], dist_reduce_fx="cat")
+
+        def update(self, x):
+            self.xs.append(x)
+
+        def compute(self):
+            seen["devices"] = {v.device.type for v in self.xs}
+            return torch.cat(self.xs).sum()
+
+    m = Cat(compute_on_cpu=True)
+    m.update(torch.ones(3))
+    m.update(torch.ones(2))
+    assert all(v.device.type == "cpu" for v in m.xs)
+    m._device = torch.device("meta")  # pretend the metric lives elsewhere: compute must stage the parked lists there
+    try:
+        m.compute()
+    except (RuntimeError, NotImplementedError):
+        pass  # meta tensors cannot be summed to a value; what matters is where compute saw them
+    assert seen["devices"] == {"meta"}
+    assert all(v.device.type == "cpu" for v in m.xs)  # parked again
