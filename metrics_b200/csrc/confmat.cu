@@ -421,7 +421,7 @@ static int launch_rows(const RowArgs& a, Sink sink, size_t smem, cudaStream_t st
                     if constexpr (Sink::kOverlapSafe) {
                         if (rows_overlap_enabled()) {
                             RowArgs ao = a;
-                            ao.pdl_wait = rows_overlap_mode() == 1;
+                            ao.pdl_wait = rows_overlap_mode() == 1 || Sink::kMustWait;  // see sinks.cuh
                             MB200_CUDA_OK(launch_overlapped(kern, grid, kRowThreads, smem, st, ao, sink));
                         } else {
                             kern<<<grid, kRowThreads, smem, st>>>(a, sink);
@@ -546,6 +546,17 @@ extern "C" int mb200_multiclass_stat_scores_update(const void* preds, int preds_
                           (long long*)workspace, (int)num_classes, micro};
         return dispatch_rows(preds_dtype, preds_has_class_dim, a, s, (size_t)(3 * num_classes) * sizeof(unsigned),
                              st);
+    }
+    // Large launches: rows only RED into the workspace, the fold follows as its own one-CTA kernel (see sinks.cuh kDeferFold);
+    // small ones keep the single launch (an extra launch costs more host time than the fold tail costs device time).
+    if (preds_has_class_dim && inner == 1 && n_outer * num_classes >= (1ll << 24) && rows_overlap_enabled()) {
+        StatsSink<false, true> s{(long long*)tp, (long long*)fp, (long long*)tn, (long long*)fn, (long long*)workspace,
+                                 (int)num_classes, micro};
+        if (int rc = dispatch_rows(preds_dtype, preds_has_class_dim, a, s, 0, st)) return rc;
+        MB200_CUDA_OK(launch_overlapped(stats_fold_kernel, 1, 1024, 0, st, (long long*)tp, (long long*)fp, (long long*)tn,
+                                        (long long*)fn, (long long*)workspace, (int)num_classes, micro));
+        count_launch();
+        return check_cuda(cudaGetLastError(), "stat-scores fold launch");
     }
     StatsSink<false> s{(long long*)tp, (long long*)fp, (long long*)tn, (long long*)fn, (long long*)workspace,
                        (int)num_classes, micro};

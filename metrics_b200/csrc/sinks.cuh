@@ -16,6 +16,7 @@ struct ArgmaxOutSink {
     __device__ __forceinline__ void finish(Local&) {}
     static constexpr bool kNeedsTarget = false;
     static constexpr bool kOverlapSafe = false;
+    static constexpr bool kMustWait = true;
 };
 
 // confmat[t, p] += 1 straight into the (L2-resident) state; optional shared-memory privatisation for tiny C.
@@ -28,6 +29,7 @@ struct ConfmatSink {
     // Two consecutive launches may overlap (programmatic dependent launch): all they share is the state, and they only
     // ever touch it with commutative 64-bit REDs.
     static constexpr bool kOverlapSafe = true;
+    static constexpr bool kMustWait = false;  // the opt-in no-wait overlap (MB200_ROWS_OVERLAP=2) is allowed
     __device__ __forceinline__ void block_init() {
         if (kSmem) {
             extern __shared__ unsigned sh_bins[];
@@ -59,7 +61,11 @@ struct ConfmatSink {
 // tp/fp/fn deltas go to a zeroed workspace; the last block to finish folds them (and tn) into the states and
 // re-zeroes the workspace.  ws layout: [0,C) dtp | [C,2C) dfp | [2C,3C) dfn | [3C] n_valid | [3C+1] ticket.
 // micro: ws[0] = #match, ws[1] = #mismatch.
-template <bool kSmem>
+// kDeferFold (large launches): the row kernel only REDs into the workspace and exits — no fence, no ticket — and the fold runs
+// as its own one-CTA kernel behind it (stats_fold_kernel, launched with programmatic stream serialization, waiting for this
+// grid with griddepcontrol.wait).  The fence + ticket round trip that every CTA pays otherwise, and the last CTA's fold while
+// the rest of the GPU idles, were 7 of the 31 us of a cfg2-shaped update (profiles/r02_k1b_ncu.txt: membar 1.8, barrier 1.4).
+template <bool kSmem, bool kDeferFold = false>
 struct StatsSink {
     long long *tp, *fp, *tn, *fn, *ws;
     int C;
@@ -68,7 +74,10 @@ struct StatsSink {
         unsigned n_valid, n_match;
     };
     static constexpr bool kNeedsTarget = true;
-    static constexpr bool kOverlapSafe = false;  // self-cleaning workspace + last-CTA ticket: launches must not overlap
+    // self-cleaning workspace + last-CTA ticket: launches must not overlap — unless the fold is deferred: then this grid only
+    // issues commutative REDs, and its successor in the stream (the fold kernel) waits for it explicitly
+    static constexpr bool kOverlapSafe = kDeferFold;
+    static constexpr bool kMustWait = true;  // the previous update's fold kernel zeroes the workspace these REDs go to
     __device__ __forceinline__ void block_init() {
         if (kSmem) {
             extern __shared__ unsigned sh_bins[];
@@ -119,6 +128,7 @@ struct StatsSink {
                 if (v) red_add_u64(ws + i, v);
             }
         }
+        if (kDeferFold) return;  // stats_fold_kernel takes it from here
         // ---- last-block fold -------------------------------------------------------------------
         __shared__ int is_last;
         __threadfence();
@@ -164,6 +174,35 @@ struct StatsSink {
 };
 
 
+// The deferred fold of StatsSink<false, true>: ONE CTA, launched behind the row kernel with programmatic stream serialization.
+static __global__ void __launch_bounds__(1024) stats_fold_kernel(long long* tp, long long* fp, long long* tn, long long* fn,
+                                                                 long long* ws, int C, int micro) {
+    asm volatile("griddepcontrol.launch_dependents;");  // the next update's row kernel may queue up; it waits for this grid
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // all REDs of the row kernel have landed
+    const long long n_valid = __ldcg(ws + 3 * C);
+    if (micro) {
+        if (threadIdx.x == 0) {
+            const long long m = __ldcg(ws + 0), mm = __ldcg(ws + 1);
+            red_add_u64(tp, (unsigned long long)m);
+            red_add_u64(fp, (unsigned long long)mm);
+            red_add_u64(fn, (unsigned long long)mm);
+            red_add_u64(tn, (unsigned long long)((long long)C * n_valid - (m + 2 * mm)));
+            ws[0] = 0;
+            ws[1] = 0;
+        }
+    } else {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const long long a = __ldcg(ws + c), b = __ldcg(ws + C + c), d = __ldcg(ws + 2 * C + c);
+            if (a) red_add_u64(tp + c, (unsigned long long)a), ws[c] = 0;
+            if (b) red_add_u64(fp + c, (unsigned long long)b), ws[C + c] = 0;
+            if (d) red_add_u64(fn + c, (unsigned long long)d), ws[2 * C + c] = 0;
+            red_add_u64(tn + c, (unsigned long long)(n_valid - (a + b + d)));
+        }
+    }
+    __syncthreads();  // every thread has read n_valid
+    if (threadIdx.x == 0) ws[3 * C] = 0;
+}
+
 // Samplewise stat scores: per (sample, class) tp / fp / fn deltas in a zeroed [3][n_samples][C] int64 scratch plus the
 // number of admitted positions per sample; `idx / inner` is the sample.  tn is derived by the caller.
 struct SamplewiseSink {
@@ -175,6 +214,7 @@ struct SamplewiseSink {
     struct Local {};
     static constexpr bool kNeedsTarget = true;
     static constexpr bool kOverlapSafe = false;
+    static constexpr bool kMustWait = true;
     __device__ __forceinline__ void block_init() {}
     __device__ __forceinline__ void init(Local&) {}
     __device__ __forceinline__ void row(Local&, long long idx, long long t, int p) {

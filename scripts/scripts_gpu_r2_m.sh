@@ -4,7 +4,7 @@ set -x
 O=gpurun_out
 mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/r2m_all.log 2>&1; tail -4 $O/r2m_all.log
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_fusion_gpu.py tests/test_arena_gpu.py tests/test_binary_single_pass_gpu.py tests/test_curves64_gpu.py tests/test_normalize_aten_gpu.py tests/test_binned_gpu.py -q -x -k "not 1048576 and not 4194307 and not dense" > $O/r02_memcheck.log 2>&1; tail -6 $O/r02_memcheck.log
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_fusion_gpu.py tests/test_binary_single_pass_gpu.py tests/test_curves64_gpu.py tests/test_normalize_aten_gpu.py tests/test_binned_gpu.py -q -x -k "not 1048576 and not 4194307 and not dense" > $O/r02_memcheck.log 2>&1; tail -6 $O/r02_memcheck.log
 timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_fusion_gpu.py tests/test_binary_single_pass_gpu.py tests/test_binned_gpu.py -q -x -k "float32 and not dense and not 1024" > $O/r02_racecheck.log 2>&1; tail -6 $O/r02_racecheck.log
 timeout 600 python benchmarks/kernel_rooflines.py $O/r02_kernel_rooflines.json > $O/r2m_rooflines.log 2>&1; python - <<'PY'
 import json

@@ -220,3 +220,24 @@ def test_stat_scores_privatised_and_label_paths_vs_oracle():
             got = multiclass_stat_scores(labels.to(DEV), target.to(DEV), C, average=avg, ignore_index=-1, validate_args=False)
             tp, fp, tn, fn = oc.multiclass_stat_scores(labels.numpy(), target.numpy(), C, avg, -1)
             np.testing.assert_array_equal(got.cpu().numpy(), np.stack([tp, fp, tn, fn, tp + fn], axis=-1))
+
+
+@pytest.mark.parametrize("average", ["macro", "micro"])
+def test_large_stat_score_updates_with_deferred_fold_equal_chunked_updates(average):
+    """Updates of >= 2^24 scores run the row kernel without the last-CTA fold and a one-CTA fold kernel behind it
+    (csrc/sinks.cuh kDeferFold): several back-to-back large updates must leave exactly the states that the same rows leave when
+    fed in small chunks (single-launch path), and the workspace must come back clean."""
+    from metrics_b200.classification import MulticlassStatScores
+
+    g = torch.Generator().manual_seed(99)
+    big = MulticlassStatScores(num_classes=1000, average=average, validate_args=False).to(DEV)
+    small = MulticlassStatScores(num_classes=1000, average=average, validate_args=False).to(DEV)
+    for _ in range(4):
+        lg = torch.randn(20000, 1000, generator=g).bfloat16().to(DEV)
+        tg = torch.randint(0, 1000, (20000,), generator=g).to(DEV)
+        big.update(lg, tg)  # 2e7 scores: deferred fold
+        for lo in range(0, 20000, 4000):
+            small.update(lg[lo:lo + 4000], tg[lo:lo + 4000])  # 4e6 scores: fold inside the row kernel
+    for name in ("tp", "fp", "tn", "fn"):
+        assert torch.equal(getattr(big, name), getattr(small, name)), name
+    assert int(big._workspace(1000, torch.device(DEV)).abs().sum()) == 0
