@@ -259,9 +259,8 @@ MB200_API int mb200_binary_stat_counts(const void* preds, int preds_dtype, const
 /* Same contract with a larger caller-owned scratch (>= MB200_BINARY_SCRATCH_BYTES, 8-byte aligned, contents irrelevant): the
  * binary task (num_labels == 1, global counts, int64 targets, 16-byte aligned f32/f16/bf16 scores) then reads the scores ONCE,
  * counting under both outcomes of the batch-global logits vote and adding the selected set in a one-warp epilogue — 12 instead
- * of 16 bytes of traffic per element.  With scratch_bytes >= 8 + 64 * num_labels the multilabel `[n, num_labels]` layout
- * (inner == 1, 2 <= num_labels <= 256) does the same with both count sets of a label column in registers.  Every other shape
- * takes the kernels of mb200_binary_stat_counts. */
+ * of 16 bytes of traffic per element; every other shape takes the kernels of mb200_binary_stat_counts (a single-pass variant of
+ * the multilabel column kernel was measured slower than its two passes — 250 vs 218 us at [2^20, 64] — and removed). */
 #define MB200_BINARY_SCRATCH_BYTES 128
 MB200_API int mb200_binary_stat_counts_scratch(const void* preds, int preds_dtype, const void* target, int target_dtype,
                                                int64_t n_outer, int64_t num_labels, int64_t inner, double threshold,

@@ -499,8 +499,7 @@ def binary_stat_counts(
     if counts is None:
         counts = torch.zeros((groups, 4), dtype=torch.int64, device=dev)
     # scratch for the logits vote; large enough (MB200_BINARY_SCRATCH_BYTES) for the single-pass binary kernel's two count sets
-    # (multilabel, L <= 256: two [L, 4] count sets = 64 L bytes behind the vote word)
-    words = 32 if num_labels == 1 or num_labels > 256 or samplewise else 4 + 16 * num_labels
+    words = 32
     scratch = torch.empty(words, dtype=torch.int32, device=dev) if preds.is_floating_point() else None
     with on_device(dev):
         rc = lib().mb200_binary_stat_counts_scratch(

@@ -392,76 +392,6 @@ __global__ void __launch_bounds__(256) bin_count_cols_kernel(BinArgs a) {
     }
 }
 
-// Single-pass variant of the column-owner kernel (multilabel `[N, L]`, L <= 256, f32 / f16 / bf16): every thread keeps BOTH
-// count sets of its label column in registers; `both` is [2][L][4] zeroed scratch, selected by bin_select_cols_kernel.
-template <typename T>
-__global__ void __launch_bounds__(256) bin_count_cols_both_kernel(BinArgs a, BothArgs b) {
-    __shared__ unsigned sh[2 * 256 * 4];
-    const int L = (int)a.num_labels;
-    for (int i = threadIdx.x; i < 2 * L * 4; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-    const int rows_per_block = 256 / L;
-    const int col = threadIdx.x % L;
-    const int rloc = threadIdx.x / L;
-    unsigned cp[4] = {0, 0, 0, 0}, cl[4] = {0, 0, 0, 0};
-    bool bad_target = false, outside = false;
-    const bool bracket = b.x_lo == b.x_lo;
-    if (rloc < rows_per_block) {
-        const T* __restrict__ ps = reinterpret_cast<const T*>(a.preds);
-        const long long rstride = (long long)gridDim.x * rows_per_block;
-        long long r = (long long)blockIdx.x * rows_per_block + rloc;
-        auto count = [&](T x, long long t) {
-            const float v = score_to_float<T>(x);
-            outside |= (v < 0.f) | (v > 1.f);
-            if (a.has_ignore && t == a.ignore_index) return;
-            if ((unsigned long long)t > 1ull) {
-                bad_target = true;
-                return;
-            }
-            const int pp = v > a.threshold ? 1 : 0;
-            int pl;
-            if (bracket && v > b.x_hi) pl = 1;
-            else if (bracket && v < b.x_lo) pl = 0;
-            else pl = pred_from_value<T>(a, x, true);
-            const int ti = (int)t;
-            cp[0] += (pp == 1 && ti == 1), cp[1] += (pp == 1 && ti == 0), cp[2] += (pp == 0 && ti == 0), cp[3] += (pp == 0 && ti == 1);
-            cl[0] += (pl == 1 && ti == 1), cl[1] += (pl == 1 && ti == 0), cl[2] += (pl == 0 && ti == 0), cl[3] += (pl == 0 && ti == 1);
-        };
-        for (; r + rstride < a.n_outer; r += 2 * rstride) {
-            const long long i0 = r * L + col, i1 = (r + rstride) * L + col;
-            const T x0 = ps[i0], x1 = ps[i1];
-            const long long t0 = load_label(a.target, a.target_dtype, i0), t1 = load_label(a.target, a.target_dtype, i1);
-            count(x0, t0);
-            count(x1, t1);
-        }
-        for (; r < a.n_outer; r += rstride) {
-            const long long i0 = r * L + col;
-            count(ps[i0], load_label(a.target, a.target_dtype, i0));
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (cp[k]) atomicAdd(&sh[col * 4 + k], cp[k]);
-            if (cl[k]) atomicAdd(&sh[(L + col) * 4 + k], cl[k]);
-        }
-    }
-    if (__any_sync(kFull, bad_target) && (threadIdx.x & 31) == 0 && a.err) atomicOr(a.err, MB200_FLAG_TARGET_RANGE);
-    if (__any_sync(kFull, outside) && (threadIdx.x & 31) == 0) atomicOr(b.vote, 1u);
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * L * 4; i += blockDim.x) {
-        const unsigned v = sh[i];
-        if (v) atomicAdd(b.both + i, (unsigned long long)v);
-    }
-}
-
-__global__ void bin_select_cols_kernel(const unsigned long long* __restrict__ both, const unsigned* __restrict__ vote,
-                                       long long* __restrict__ counts, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const unsigned long long v = both[(*vote != 0u ? n : 0) + i];
-        if (v) red_add_u64(counts + i, v);
-    }
-}
-
 }  // namespace mb200
 
 using namespace mb200;
@@ -520,33 +450,6 @@ static int binary_stat_counts_impl(const void* preds, int preds_dtype, const voi
             default: bin_count_flat_both_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, b); break;
         }
         bin_select_kernel<<<1, 32, 0, st>>>(b.both, b.vote, a.counts);
-        count_launch();
-        count_launch();
-        return check_cuda(cudaGetLastError(), "binary stat counts launch");
-    }
-    const bool cols = float_preds && !samplewise && inner == 1 && num_labels >= 2 && num_labels <= 256;
-    if (cols && preds_dtype != MB200_F64 && flag_scratch_bytes >= 8 + 64 * num_labels &&
-        (reinterpret_cast<uintptr_t>(flag_scratch) & 7) == 0) {
-        MB200_CUDA_OK(cudaMemsetAsync(flag_scratch, 0, (size_t)(8 + 64 * num_labels), st));
-        BothArgs b;
-        b.vote = flag_scratch;
-        b.both = reinterpret_cast<unsigned long long*>(flag_scratch + 2);
-        const double eps = preds_dtype == MB200_F32 ? 0x1p-20 : (preds_dtype == MB200_F16 ? 0x1p-9 : 0x1p-6);
-        const double lo_p = threshold * (1.0 - eps) - 1e-300, hi_p = threshold * (1.0 + eps) + 1e-300;
-        if (threshold > 1e-6 && hi_p < 1.0 - 1e-6) {
-            const double xl = std::log(lo_p / (1.0 - lo_p)), xh = std::log(hi_p / (1.0 - hi_p));
-            b.x_lo = (float)(xl - 1e-5 * (1.0 + std::fabs(xl)));
-            b.x_hi = (float)(xh + 1e-5 * (1.0 + std::fabs(xh)));
-        } else {
-            b.x_lo = b.x_hi = std::nanf("");
-        }
-        switch (preds_dtype) {
-            case MB200_F32: bin_count_cols_both_kernel<float><<<grid, 256, 0, st>>>(a, b); break;
-            case MB200_F16: bin_count_cols_both_kernel<__half><<<grid, 256, 0, st>>>(a, b); break;
-            default: bin_count_cols_both_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, b); break;
-        }
-        const int nsel = (int)num_labels * 4;
-        bin_select_cols_kernel<<<(nsel + 255) / 256, 256, 0, st>>>(b.both, b.vote, a.counts, nsel);
         count_launch();
         count_launch();
         return check_cuda(cudaGetLastError(), "binary stat counts launch");

@@ -66,37 +66,3 @@ def test_nan_and_infinite_scores():
     x = torch.tensor([float("nan"), float("inf"), float("-inf"), 0.3, -0.0, 2.0] * 1000, device=DEV)
     t = torch.tensor([1, 1, 0, 0, 1, 0] * 1000, device=DEV)
     assert torch.equal(_native.binary_stat_counts(x, t, 1, 0.5, None, False), _two_pass(x, t, 0.5, None))
-
-
-def _two_pass_multilabel(preds, target, num_labels, threshold, ignore_index):
-    counts = torch.zeros((num_labels, 4), dtype=torch.int64, device=DEV)
-    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
-    rc = _native.lib().mb200_binary_stat_counts(
-        preds.data_ptr(), _native.tag(preds), target.data_ptr(), _native.tag(target), preds.shape[0], num_labels, 1,
-        ctypes.c_double(float(threshold)), int(ignore_index is not None), int(ignore_index or 0), 0, counts.data_ptr(),
-        flag.data_ptr(), None, _native.stream_handle(torch.device(DEV)))
-    _native.check(rc, "binary_stat_counts")
-    return counts
-
-
-@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("num_labels", [2, 7, 64, 256])
-@pytest.mark.parametrize("kind", ["logits", "probs"])
-def test_multilabel_single_pass_equals_two_pass(dtype, num_labels, kind):
-    n = 20_000
-    g = torch.Generator().manual_seed(num_labels)
-    for threshold in (0.5, 0.25, 0.97):
-        c = math.log(threshold / (1 - threshold))
-        if kind == "logits":
-            x = torch.randn(n, num_labels, generator=g) * 3
-            x[: n // 3] = c + (torch.rand(n // 3, num_labels, generator=g) - 0.5) * 0.1  # crowd the crossing
-        else:
-            x = torch.rand(n, num_labels, generator=g)
-            x[:100] = threshold
-        x = x.to(dtype).to(DEV)
-        t = torch.randint(0, 2, (n, num_labels), generator=g).to(DEV)
-        t[5, :] = -1
-        for ignore in (None, -1):
-            got = _native.binary_stat_counts(x, t, num_labels, threshold, ignore, False)
-            want = _two_pass_multilabel(x, t, num_labels, threshold, ignore)
-            assert torch.equal(got, want)
