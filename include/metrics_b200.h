@@ -239,6 +239,27 @@ MB200_API int mb200_coco_map_evaluate(
     const int64_t* classes, int64_t num_classes, int micro, const double* iou_thr_host, int64_t n_iou_thr,
     const double* rec_thr_dev, int64_t n_rec_thr, const int64_t* max_dets_host, int64_t n_max_dets, void* workspace,
     int64_t workspace_bytes, double* precision, double* recall, double* scores, uint32_t* err_flag, void* stream);
+/* The two phases of mb200_coco_map_evaluate on their own, for an evaluation sharded over ranks (detection/mean_ap.py
+ * `_compute_distributed`; the reference gathers every image to every rank, mean_ap.py:1032-1063, and every rank evaluates
+ * everything).  mb200_coco_map_match = COCOeval.evaluateImg for THIS rank's images: per detection (image order) the class
+ * index in `classes` (int32), its rank inside its (image, class) (int32), and 64-bit match / ignore words (bit = area * T +
+ * threshold); `npig` int32 [num_classes][4] is ADDED to (zero it first).  mb200_coco_map_accumulate = COCOeval.accumulate for
+ * the classes [class_lo, class_hi) over records from ALL ranks (ties in score keep the order the records are given in):
+ * precision / recall / scores are full-size [.., num_classes, ..] arrays, filled with -1 here, owned classes written. */
+MB200_API int mb200_coco_map_match(const float* det_box_xywh, const float* det_score, const int64_t* det_label,
+                                   const int32_t* det_off, const float* gt_box_xywh, const int64_t* gt_label,
+                                   const uint8_t* gt_crowd, const double* gt_area, const int32_t* gt_off, int64_t n_img,
+                                   int64_t max_det_per_img, int64_t max_gt_per_img, const int64_t* classes,
+                                   int64_t num_classes, const double* iou_thr_host, int64_t n_iou_thr, int64_t max_det_last,
+                                   int32_t* det_cat, int32_t* det_rank, uint64_t* det_match, uint64_t* det_ignore,
+                                   int32_t* npig, uint32_t* err_flag, void* stream);
+MB200_API int mb200_coco_map_accumulate(const int32_t* det_cat, const float* det_score, const int32_t* det_rank,
+                                        const uint64_t* det_match, const uint64_t* det_ignore, int64_t n_det,
+                                        const int32_t* npig, int64_t num_classes, int64_t class_lo, int64_t class_hi,
+                                        int64_t n_iou_thr, const double* rec_thr_dev, int64_t n_rec_thr,
+                                        const int64_t* max_dets_host, int64_t n_max_dets, void* workspace,
+                                        int64_t workspace_bytes, double* precision, double* recall, double* scores,
+                                        uint32_t* err_flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K2 — binary / multilabel stat scores and confusion-matrix counts.

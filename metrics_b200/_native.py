@@ -103,6 +103,8 @@ SIGNATURES = {
     "mb200_curve_evaluate_multilabel": ("i", "pipiqqiqpqpppppppp"),
     "mb200_coco_map_workspace_bytes": ("q", "qqq"),
     "mb200_coco_map_evaluate": ("i", "pppppppppqqqqqpqipqpqpqpqppppp"),
+    "mb200_coco_map_match": ("i", "pppppppppqqqpqpqqppppppp"),
+    "mb200_coco_map_accumulate": ("i", "pppppqpqqqqpqpqpqppppp"),
     "mb200_binary_stat_counts": ("i", "pipiqqqdiqipppp"),
     "mb200_binary_stat_counts_scratch": ("i", "pipiqqqdiqippqpp"),
     "mb200_regression_num_sums": ("i", "i"),
@@ -477,6 +479,73 @@ def coco_map_evaluate(
     if rc == -3:
         raise NotImplementedError("metrics_b200: " + lib_.mb200_last_error().decode("utf-8", "replace"))
     check(rc, "coco_map_evaluate")
+    return precision, recall, scores, err
+
+
+def coco_map_match(det_box: Tensor, det_score: Tensor, det_label: Tensor, det_counts: list, gt_box: Tensor, gt_label: Tensor,
+                   gt_crowd: Tensor, gt_area: Tensor, gt_counts: list, classes: Tensor, iou_thresholds: list, max_det_last: int):
+    """``mb200_coco_map_match``: COCOeval.evaluateImg for the given images only.  Returns the per-detection records
+    ``(det_cat i32 [n], det_rank i32 [n], det_match i64 [n], det_ignore i64 [n])``, ``npig`` i32 ``[K, 4]`` and the error word."""
+    import numpy as np
+
+    dev = require_cuda(det_box, det_score, det_label, gt_box, gt_label, gt_crowd, gt_area, classes)
+    n_img = len(det_counts)
+    det_off = torch.from_numpy(np.concatenate([[0], np.cumsum(det_counts)]).astype(np.int32)).to(dev, non_blocking=True)
+    gt_off = torch.from_numpy(np.concatenate([[0], np.cumsum(gt_counts)]).astype(np.int32)).to(dev, non_blocking=True)
+    n_det = int(sum(det_counts))
+    det_box = det_box.to(torch.float32).contiguous()
+    det_score = det_score.to(torch.float32).contiguous()
+    det_label = det_label.to(torch.int64).contiguous()
+    gt_box = gt_box.to(torch.float32).contiguous()
+    gt_label = gt_label.to(torch.int64).contiguous()
+    gt_crowd = gt_crowd.to(torch.uint8).contiguous()
+    gt_area = gt_area.to(torch.float64).contiguous()
+    classes = classes.to(torch.int64).contiguous()
+    k, t = int(classes.numel()), len(iou_thresholds)
+    det_cat = torch.empty(max(n_det, 1), dtype=torch.int32, device=dev)
+    det_rank = torch.empty(max(n_det, 1), dtype=torch.int32, device=dev)
+    det_match = torch.empty(max(n_det, 1), dtype=torch.int64, device=dev)
+    det_ignore = torch.empty(max(n_det, 1), dtype=torch.int64, device=dev)
+    npig = torch.zeros((k, 4), dtype=torch.int32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    iou_host = (ctypes.c_double * t)(*[float(x) for x in iou_thresholds])
+    with on_device(dev):
+        rc = lib().mb200_coco_map_match(
+            ptr(det_box), ptr(det_score), ptr(det_label), ptr(det_off), ptr(gt_box), ptr(gt_label), ptr(gt_crowd), ptr(gt_area),
+            ptr(gt_off), n_img, max(det_counts) if det_counts else 0, max(gt_counts) if gt_counts else 0, ptr(classes), k,
+            iou_host, t, int(max_det_last), ptr(det_cat), ptr(det_rank), ptr(det_match), ptr(det_ignore), ptr(npig), ptr(err),
+            stream_handle(dev))
+    if rc == -3:
+        raise NotImplementedError("metrics_b200: " + lib().mb200_last_error().decode("utf-8", "replace"))
+    check(rc, "coco_map_match")
+    return (det_cat[:n_det], det_rank[:n_det], det_match[:n_det], det_ignore[:n_det]), npig, err
+
+
+def coco_map_accumulate(det_cat: Tensor, det_score: Tensor, det_rank: Tensor, det_match: Tensor, det_ignore: Tensor, npig: Tensor,
+                        num_classes: int, class_lo: int, class_hi: int, n_iou_thr: int, rec_thresholds: list, max_dets: list):
+    """``mb200_coco_map_accumulate``: COCOeval.accumulate for classes ``[class_lo, class_hi)`` over the given records (ties in
+    score keep the given order).  Returns full-size ``precision [T,R,K,A,M]``, ``recall [T,K,A,M]``, ``scores`` (-1 outside)."""
+    dev = require_cuda(det_cat, det_score, det_rank, det_match, det_ignore, npig)
+    n_det = int(det_cat.numel())
+    k, t, r, m = int(num_classes), int(n_iou_thr), len(rec_thresholds), len(max_dets)
+    rec_dev = torch.tensor(rec_thresholds, dtype=torch.float64).to(dev, non_blocking=True)
+    lib_ = lib()
+    nbytes = int(lib_.mb200_coco_map_workspace_bytes(n_det, max(1, k), m))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    precision = torch.empty((t, r, k, 4, m), dtype=torch.float64, device=dev)
+    recall = torch.empty((t, k, 4, m), dtype=torch.float64, device=dev)
+    scores = torch.empty((t, r, k, 4, m), dtype=torch.float64, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    md_host = (ctypes.c_int64 * m)(*[int(x) for x in max_dets])
+    args = [x.contiguous() for x in (det_cat.to(torch.int32), det_score.to(torch.float32), det_rank.to(torch.int32),
+                                     det_match.to(torch.int64), det_ignore.to(torch.int64), npig.to(torch.int32))]
+    with on_device(dev):
+        rc = lib_.mb200_coco_map_accumulate(
+            ptr(args[0]) if n_det else None, ptr(args[1]) if n_det else None, ptr(args[2]) if n_det else None,
+            ptr(args[3]) if n_det else None, ptr(args[4]) if n_det else None, n_det, ptr(args[5]), k, int(class_lo), int(class_hi),
+            t, ptr(rec_dev), r, md_host, m, ptr(ws), nbytes, ptr(precision), ptr(recall), ptr(scores), ptr(err),
+            stream_handle(dev))
+    check(rc, "coco_map_accumulate")
     return precision, recall, scores, err
 
 

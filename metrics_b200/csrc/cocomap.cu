@@ -288,6 +288,7 @@ struct MapAccArgs {
     const int* npig;
     const double* rec_thr;  // [R]
     int K, T, R, M;
+    int class_lo;  // blockIdx.x counts from here (class-sharded accumulation)
     int max_dets[8];
     int n_det;
     // scratch planes [A*M][n_det]
@@ -325,7 +326,7 @@ __device__ __forceinline__ unsigned block_scan_excl_u32(unsigned v, unsigned* sm
 __global__ void __launch_bounds__(256) map_accumulate_kernel(MapAccArgs p) {
     __shared__ unsigned sm8[8];
     __shared__ double smd[8];
-    const int k = blockIdx.x;
+    const int k = blockIdx.x + p.class_lo;
     const int a = blockIdx.y / p.M, m = blockIdx.y % p.M;
     const int np_ig = p.npig[k * kMapAreas + a];
     if (np_ig == 0) return;  // COCOeval.accumulate: `if npig == 0: continue` -> stays -1
@@ -498,25 +499,17 @@ extern "C" int64_t mb200_coco_map_workspace_bytes(int64_t n_det, int64_t num_cla
     return total;
 }
 
-extern "C" int mb200_coco_map_evaluate(
-    const float* det_box_xywh, const float* det_score, const int64_t* det_label, const int32_t* det_off,
-    const float* gt_box_xywh, const int64_t* gt_label, const uint8_t* gt_crowd, const double* gt_area,
-    const int32_t* gt_off, int64_t n_img, int64_t n_det, int64_t n_gt, int64_t max_det_per_img, int64_t max_gt_per_img,
-    const int64_t* classes, int64_t num_classes, int micro, const double* iou_thr_host, int64_t n_iou_thr,
-    const double* rec_thr_dev, int64_t n_rec_thr, const int64_t* max_dets_host, int64_t n_max_dets, void* workspace,
-    int64_t workspace_bytes, double* precision, double* recall, double* scores, uint32_t* err_flag, void* stream) {
-    MB200_REQUIRE(n_img >= 1 && n_det >= 0 && n_gt >= 0, "bad sizes");
-    MB200_REQUIRE(num_classes >= 1, "need at least one class");
-    MB200_REQUIRE(n_iou_thr >= 1 && n_iou_thr <= kMapMaxThr, "between 1 and %d IoU thresholds are supported (got %lld)",
-                  kMapMaxThr, (long long)n_iou_thr);
-    MB200_REQUIRE(n_max_dets >= 1 && n_max_dets <= 8, "between 1 and 8 max-detection thresholds are supported");
-    MB200_REQUIRE(n_rec_thr >= 1, "need recall thresholds");
-    MB200_REQUIRE(n_det < (1ll << 31) && n_gt < (1ll << 31), "too many boxes");
-    MB200_REQUIRE(workspace && precision && recall && scores && det_off && gt_off && classes && rec_thr_dev,
-                  "NULL pointer");
-    MB200_REQUIRE(workspace_bytes >= mb200_coco_map_workspace_bytes(n_det, num_classes, n_max_dets),
-                  "workspace too small");
-    const int K = micro ? 1 : (int)num_classes;
+namespace {
+
+// Phase 1 — per-image greedy matching (COCOeval.evaluateImg): one CTA per image of THIS call.  Outputs per detection (image
+// order): class index, rank inside its (image, class), match / ignore bit words; `npig` [K][4] is ADDED to (caller zeroes it).
+int map_match_impl(const float* det_box_xywh, const float* det_score, const int64_t* det_label, const int32_t* det_off,
+                   const float* gt_box_xywh, const int64_t* gt_label, const uint8_t* gt_crowd, const double* gt_area,
+                   const int32_t* gt_off, int64_t n_img, int64_t max_det_per_img, int64_t max_gt_per_img,
+                   const int64_t* classes, int64_t num_classes, int micro, const double* iou_thr_host, int T, int max_det_last,
+                   int* det_cat, int* det_rank, unsigned long long* det_match, unsigned long long* det_ignore, int* npig,
+                   uint32_t* err_flag, cudaStream_t st) {
+    if (n_img == 0) return 0;
     // More than 256 ground truths in one image MAY put more than 256 of one class there: then the per-thread "matched" masks
     // move from registers to shared memory, one bit per ground truth of the image per thread.
     const bool smem_mask = max_gt_per_img > 64 * kGtmWords;
@@ -527,18 +520,6 @@ extern "C" int mb200_coco_map_evaluate(
                   "shared memory", (long long)max_det_per_img, (long long)max_gt_per_img);
         return MB200_ERR_UNSUPPORTED;
     }
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    MapWs w = carve(workspace, n_det, num_classes, n_max_dets, nullptr);
-    const int M = (int)n_max_dets, T = (int)n_iou_thr, R = (int)n_rec_thr;
-
-    const long long n_prec = (long long)T * R * K * kMapAreas * M;
-    const long long n_rec = (long long)T * K * kMapAreas * M;
-    fill_double_kernel<<<256, 256, 0, st>>>(precision, n_prec, -1.0);
-    fill_double_kernel<<<256, 256, 0, st>>>(scores, n_prec, -1.0);
-    fill_double_kernel<<<64, 256, 0, st>>>(recall, n_rec, -1.0);
-    zero_int_kernel<<<(K * kMapAreas + 255) / 256, 256, 0, st>>>(w.npig, K * kMapAreas);
-    for (int i = 0; i < 4; ++i) count_launch();
-
     MapEvalArgs ea;
     ea.det_box = reinterpret_cast<const float4*>(det_box_xywh);
     ea.det_score = det_score;
@@ -553,13 +534,13 @@ extern "C" int mb200_coco_map_evaluate(
     ea.K = (int)num_classes;
     ea.micro = micro;
     ea.T = T;
-    ea.max_det_last = (int)max_dets_host[n_max_dets - 1];
+    ea.max_det_last = max_det_last;
     for (int t = 0; t < T; ++t) ea.iou_thr[t] = iou_thr_host[t];
-    ea.det_cat = w.det_cat;
-    ea.det_rank = w.det_rank;
-    ea.det_match = w.det_match;
-    ea.det_ignore = w.det_ignore;
-    ea.npig = w.npig;
+    ea.det_cat = det_cat;
+    ea.det_rank = det_rank;
+    ea.det_match = det_match;
+    ea.det_ignore = det_ignore;
+    ea.npig = npig;
     ea.err = err_flag;
     if (smem_mask) {
         MB200_CUDA_OK(ensure_dynamic_smem(map_evaluate_kernel<true>, 200 * 1024));
@@ -569,13 +550,26 @@ extern "C" int mb200_coco_map_evaluate(
         map_evaluate_kernel<false><<<(unsigned)n_img, 256, smem, st>>>(ea, (int)max_det_per_img, (int)max_gt_per_img);
     }
     count_launch();
+    return check_cuda(cudaGetLastError(), "coco map match launch");
+}
 
-    // ---- sort detections by (class, score desc), stable w.r.t. (image, original index) ----
-    const int nd = (int)n_det;
+// Phase 2 — COCOeval.accumulate for classes [class_lo, class_hi): stable sort of the records by (class, score desc) — ties keep
+// the order the records are GIVEN in —, integer TP / FP prefix sums, fp64 precision envelope, recall-threshold sampling.
+// precision / recall / scores are full-size [.., K, ..] arrays, pre-filled with -1 here; only the owned classes are written.
+int map_accumulate_impl(const int* det_cat, const float* det_score, const int* det_rank, const unsigned long long* det_match,
+                        const unsigned long long* det_ignore, int nd, const int* npig, int K, int class_lo, int class_hi, int T,
+                        const double* rec_thr_dev, int R, const int64_t* max_dets_host, int M, const MapWs& w, double* precision,
+                        double* recall, double* scores, uint32_t* err_flag, cudaStream_t st) {
+    const long long n_prec = (long long)T * R * K * kMapAreas * M;
+    const long long n_rec = (long long)T * K * kMapAreas * M;
+    fill_double_kernel<<<256, 256, 0, st>>>(precision, n_prec, -1.0);
+    fill_double_kernel<<<256, 256, 0, st>>>(scores, n_prec, -1.0);
+    fill_double_kernel<<<64, 256, 0, st>>>(recall, n_rec, -1.0);
+    for (int i = 0; i < 3; ++i) count_launch();
     const unsigned long long* skeys = w.keys_a;
     const unsigned* sidx = w.vals_a;
     if (nd > 0) {
-        map_pack_keys_kernel<<<(nd + 255) / 256, 256, 0, st>>>(w.det_cat, det_score, nd, w.keys_a, w.vals_a);
+        map_pack_keys_kernel<<<(nd + 255) / 256, 256, 0, st>>>(det_cat, det_score, nd, w.keys_a, w.vals_a);
         count_launch();
         int key_bytes = 4;  // score
         for (long long kk = K - 1; kk > 0; kk >>= 8) key_bytes++;
@@ -588,17 +582,19 @@ extern "C" int mb200_coco_map_evaluate(
     }
     map_class_ranges_kernel<<<(K + 1 + 255) / 256, 256, 0, st>>>(skeys, nd, K, w.range_start);
     count_launch();
+    if (class_hi <= class_lo) return check_cuda(cudaGetLastError(), "coco map launch");
 
     MapAccArgs aa;
     aa.sorted_idx = sidx;
     aa.range_start = w.range_start;
-    aa.det_rank = w.det_rank;
-    aa.det_match = w.det_match;
-    aa.det_ignore = w.det_ignore;
+    aa.det_rank = det_rank;
+    aa.det_match = det_match;
+    aa.det_ignore = det_ignore;
     aa.det_score = det_score;
-    aa.npig = w.npig;
+    aa.npig = npig;
     aa.rec_thr = rec_thr_dev;
     aa.K = K, aa.T = T, aa.R = R, aa.M = M;
+    aa.class_lo = class_lo;
     for (int i = 0; i < M; ++i) aa.max_dets[i] = (int)max_dets_host[i];
     aa.n_det = nd;
     aa.tp_cum = w.tp_cum;
@@ -607,7 +603,86 @@ extern "C" int mb200_coco_map_evaluate(
     aa.precision = precision;
     aa.recall = recall;
     aa.scores = scores;
-    map_accumulate_kernel<<<dim3((unsigned)K, (unsigned)(kMapAreas * M)), 256, 0, st>>>(aa);
+    map_accumulate_kernel<<<dim3((unsigned)(class_hi - class_lo), (unsigned)(kMapAreas * M)), 256, 0, st>>>(aa);
     count_launch();
     return check_cuda(cudaGetLastError(), "coco map launch");
+}
+
+int check_map_sizes(int64_t n_iou_thr, int64_t n_max_dets, int64_t n_rec_thr) {
+    MB200_REQUIRE(n_iou_thr >= 1 && n_iou_thr <= kMapMaxThr, "between 1 and %d IoU thresholds are supported (got %lld)",
+                  kMapMaxThr, (long long)n_iou_thr);
+    MB200_REQUIRE(n_max_dets >= 1 && n_max_dets <= 8, "between 1 and 8 max-detection thresholds are supported");
+    MB200_REQUIRE(n_rec_thr >= 1, "need recall thresholds");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int mb200_coco_map_evaluate(
+    const float* det_box_xywh, const float* det_score, const int64_t* det_label, const int32_t* det_off,
+    const float* gt_box_xywh, const int64_t* gt_label, const uint8_t* gt_crowd, const double* gt_area,
+    const int32_t* gt_off, int64_t n_img, int64_t n_det, int64_t n_gt, int64_t max_det_per_img, int64_t max_gt_per_img,
+    const int64_t* classes, int64_t num_classes, int micro, const double* iou_thr_host, int64_t n_iou_thr,
+    const double* rec_thr_dev, int64_t n_rec_thr, const int64_t* max_dets_host, int64_t n_max_dets, void* workspace,
+    int64_t workspace_bytes, double* precision, double* recall, double* scores, uint32_t* err_flag, void* stream) {
+    MB200_REQUIRE(n_img >= 1 && n_det >= 0 && n_gt >= 0, "bad sizes");
+    MB200_REQUIRE(num_classes >= 1, "need at least one class");
+    if (int rc = check_map_sizes(n_iou_thr, n_max_dets, n_rec_thr)) return rc;
+    MB200_REQUIRE(n_det < (1ll << 31) && n_gt < (1ll << 31), "too many boxes");
+    MB200_REQUIRE(workspace && precision && recall && scores && det_off && gt_off && classes && rec_thr_dev,
+                  "NULL pointer");
+    MB200_REQUIRE(workspace_bytes >= mb200_coco_map_workspace_bytes(n_det, num_classes, n_max_dets),
+                  "workspace too small");
+    const int K = micro ? 1 : (int)num_classes;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    MapWs w = carve(workspace, n_det, num_classes, n_max_dets, nullptr);
+    const int M = (int)n_max_dets, T = (int)n_iou_thr, R = (int)n_rec_thr;
+    zero_int_kernel<<<(K * kMapAreas + 255) / 256, 256, 0, st>>>(w.npig, K * kMapAreas);
+    count_launch();
+    if (int rc = map_match_impl(det_box_xywh, det_score, det_label, det_off, gt_box_xywh, gt_label, gt_crowd, gt_area, gt_off,
+                                n_img, max_det_per_img, max_gt_per_img, classes, num_classes, micro, iou_thr_host, T,
+                                (int)max_dets_host[n_max_dets - 1], w.det_cat, w.det_rank, w.det_match, w.det_ignore, w.npig,
+                                err_flag, st))
+        return rc;
+    return map_accumulate_impl(w.det_cat, det_score, w.det_rank, w.det_match, w.det_ignore, (int)n_det, w.npig, K, 0, K, T,
+                               rec_thr_dev, R, max_dets_host, M, w, precision, recall, scores, err_flag, st);
+}
+
+// The two phases on their own, for evaluation sharded over ranks (detection/mean_ap.py `_compute_distributed`): every rank
+// MATCHES its own images, the per-detection records are exchanged, and every rank ACCUMULATES its own classes.
+extern "C" int mb200_coco_map_match(
+    const float* det_box_xywh, const float* det_score, const int64_t* det_label, const int32_t* det_off,
+    const float* gt_box_xywh, const int64_t* gt_label, const uint8_t* gt_crowd, const double* gt_area,
+    const int32_t* gt_off, int64_t n_img, int64_t max_det_per_img, int64_t max_gt_per_img, const int64_t* classes,
+    int64_t num_classes, const double* iou_thr_host, int64_t n_iou_thr, int64_t max_det_last, int32_t* det_cat,
+    int32_t* det_rank, uint64_t* det_match, uint64_t* det_ignore, int32_t* npig, uint32_t* err_flag, void* stream) {
+    MB200_REQUIRE(n_img >= 0 && num_classes >= 1, "bad sizes");
+    MB200_REQUIRE(n_iou_thr >= 1 && n_iou_thr <= kMapMaxThr, "between 1 and %d IoU thresholds are supported (got %lld)",
+                  kMapMaxThr, (long long)n_iou_thr);
+    MB200_REQUIRE(npig && classes && (n_img == 0 || (det_off && gt_off)), "NULL pointer");
+    return map_match_impl(det_box_xywh, det_score, det_label, det_off, gt_box_xywh, gt_label, gt_crowd, gt_area, gt_off, n_img,
+                          max_det_per_img, max_gt_per_img, classes, num_classes, 0, iou_thr_host, (int)n_iou_thr,
+                          (int)max_det_last, det_cat, det_rank, reinterpret_cast<unsigned long long*>(det_match),
+                          reinterpret_cast<unsigned long long*>(det_ignore), npig, err_flag,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mb200_coco_map_accumulate(
+    const int32_t* det_cat, const float* det_score, const int32_t* det_rank, const uint64_t* det_match,
+    const uint64_t* det_ignore, int64_t n_det, const int32_t* npig, int64_t num_classes, int64_t class_lo, int64_t class_hi,
+    int64_t n_iou_thr, const double* rec_thr_dev, int64_t n_rec_thr, const int64_t* max_dets_host, int64_t n_max_dets,
+    void* workspace, int64_t workspace_bytes, double* precision, double* recall, double* scores, uint32_t* err_flag,
+    void* stream) {
+    MB200_REQUIRE(n_det >= 0 && n_det < (1ll << 31) && num_classes >= 1, "bad sizes");
+    MB200_REQUIRE(class_lo >= 0 && class_lo <= class_hi && class_hi <= num_classes, "bad class range [%lld, %lld)",
+                  (long long)class_lo, (long long)class_hi);
+    if (int rc = check_map_sizes(n_iou_thr, n_max_dets, n_rec_thr)) return rc;
+    MB200_REQUIRE(workspace && precision && recall && scores && npig && rec_thr_dev, "NULL pointer");
+    MB200_REQUIRE(workspace_bytes >= mb200_coco_map_workspace_bytes(n_det, num_classes, n_max_dets), "workspace too small");
+    MapWs w = carve(workspace, n_det, num_classes, n_max_dets, nullptr);
+    return map_accumulate_impl(det_cat, det_score, det_rank, reinterpret_cast<const unsigned long long*>(det_match),
+                               reinterpret_cast<const unsigned long long*>(det_ignore), (int)n_det, npig, (int)num_classes,
+                               (int)class_lo, (int)class_hi, (int)n_iou_thr, rec_thr_dev, (int)n_rec_thr, max_dets_host,
+                               (int)n_max_dets, w, precision, recall, scores, err_flag,
+                               reinterpret_cast<cudaStream_t>(stream));
 }

@@ -8,6 +8,8 @@ area, maxDet) accumulation.  Only ``iou_type="bbox"`` is in scope.
 """
 from __future__ import annotations
 
+import os
+
 import json
 from typing import Any, Dict, List, Optional, Tuple, Union
 
@@ -458,26 +460,128 @@ class MeanAveragePrecision(Metric):
         precision, recall, scores, err = run(self.average == "micro")
         if int(err.item()) != 0:
             raise NotImplementedError("metrics_b200: an image holds more ground truths of one class than the matcher can track")
-        result.update(self._stats_dict(self._summarize(precision, recall)))
+        extras: Dict[str, Tensor] = {}
         if self.extended_summary:
             micro = self.average == "micro"
-            result["ious"] = _pairwise_ious(det_box, det_score, det_label, det_counts, gt_box, gt_label, gt_crowd, gt_counts,
+            extras["ious"] = _pairwise_ious(det_box, det_score, det_label, det_counts, gt_box, gt_label, gt_crowd, gt_counts,
                                             classes_list, micro, self.max_detection_thresholds[-1])
-            result["precision"] = precision
-            result["recall"] = recall
-            result["scores"] = scores
-        last = self.max_detection_thresholds[-1]
+            extras["precision"] = precision
+            extras["recall"] = recall
+            extras["scores"] = scores
+        per_class = None
         if self.class_metrics:
+            per_class = (precision, recall)
             if self.average == "micro":  # the reference re-evaluates per class with the true labels (:566-569)
-                precision, recall, _, _ = run(False)
+                per_class = run(False)[:2]
+        return self._results(precision, recall, classes_list, extras, per_class)
+
+    def _results(self, precision: Tensor, recall: Tensor, classes_list: List[int], extras: Dict[str, Tensor],
+                 per_class: Optional[Tuple[Tensor, Tensor]]) -> Dict[str, Tensor]:
+        """The result dict from the accumulated ``precision [T,R,K,A,M]`` / ``recall [T,K,A,M]`` (reference :571-598)."""
+        dev = precision.device
+        result: Dict[str, Tensor] = {}
+        result.update(self._stats_dict(self._summarize(precision, recall)))
+        result.update(extras)
+        last = self.max_detection_thresholds[-1]
+        if per_class is not None:
             m_last = len(self.max_detection_thresholds) - 1
-            result["map_per_class"] = self._masked_mean(precision[:, :, :, 0, m_last], dims=(0, 1)).to(torch.float32)
-            result[f"mar_{last}_per_class"] = self._masked_mean(recall[:, :, 0, m_last], dims=(0,)).to(torch.float32)
+            result["map_per_class"] = self._masked_mean(per_class[0][:, :, :, 0, m_last], dims=(0, 1)).to(torch.float32)
+            result[f"mar_{last}_per_class"] = self._masked_mean(per_class[1][:, :, 0, m_last], dims=(0,)).to(torch.float32)
         else:
             result["map_per_class"] = torch.tensor([-1.0], dtype=torch.float32, device=dev)
             result[f"mar_{last}_per_class"] = torch.tensor([-1.0], dtype=torch.float32, device=dev)
         result["classes"] = torch.tensor(classes_list, dtype=torch.int32, device=dev)
         return result
+
+    # ------------------------------------------------------------------------------------------------
+    # evaluation sharded over ranks
+    # ------------------------------------------------------------------------------------------------
+    def _compute_distributed(self) -> Any:
+        """``compute()`` under an NCCL group without gathering a single box.
+
+        The reference gathers every rank's per-image lists to every rank and lets every rank evaluate everything
+        (mean_ap.py:1032-1063 ``_sync_dist`` + :521-598).  Here the two phases of COCOeval are sharded along their natural axes:
+        every rank MATCHES only its own images (`mb200_coco_map_match`, one CTA per image), the per-detection records
+        (class, score, rank, match / ignore words: 32 B) are all-gathered and put into the reference's interleaved image order
+        (so ties in score break exactly as in the gathered evaluation), every rank ACCUMULATES only its own K / W classes
+        (`mb200_coco_map_accumulate`), and the per-class slices of precision / recall are exchanged.  Bit-identical to the
+        gather path (`MB200_SHARDED_MAP=0`) and to one GPU fed the interleaved images.  `average="micro"` (one class) and
+        `extended_summary` (needs every box everywhere) keep the gather path."""
+        dist = torch.distributed
+        if not (dist.is_available() and dist.is_initialized()) or os.environ.get("MB200_SHARDED_MAP", "1") == "0":
+            return NotImplemented
+        if self.dist_sync_fn is not None or self.average == "micro" or self.extended_summary or self.device.type != "cuda":
+            return NotImplemented
+        if self.distributed_available_fn is not None and not self.distributed_available_fn():
+            return NotImplemented
+        group = self.process_group or dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        try:
+            if world < 2 or dist.get_backend(group) != "nccl":
+                return NotImplemented
+        except Exception:
+            return NotImplemented
+        import numpy as np
+
+        from metrics_b200.parallel_sync import _gather_equal
+        from metrics_b200.utilities.distributed import gather_all_tensors
+
+        dev = self.device
+        det_counts = [int(t.shape[0]) for t in self.detection_labels]
+        gt_counts = [int(t.shape[0]) for t in self.groundtruth_labels]
+        # ---- the class list and the image layout of every rank (two small ragged gathers) -------------------------------------
+        labels = self.detection_labels + self.groundtruth_labels
+        local_labels = torch.cat(labels).to(torch.int64).unique() if labels else torch.zeros(0, dtype=torch.int64, device=dev)
+        classes = torch.cat(gather_all_tensors(local_labels, group)).unique()
+        classes_list = classes.cpu().tolist()
+        counts_all = [c.cpu().tolist() for c in gather_all_tensors(torch.tensor(det_counts, dtype=torch.int64, device=dev), group)]
+        if sum(len(c) for c in counts_all) == 0:
+            return NotImplemented  # no image anywhere: the generic path produces the reference's "-1 everywhere" result
+        if classes.numel() == 0:
+            classes = torch.zeros(1, dtype=torch.int64, device=dev)
+        k = int(classes.numel())
+        # ---- phase 1 on this rank's images --------------------------------------------------------------------------------------
+        det_score = self._cat_or_empty(self.detection_scores, (0,), torch.float32, dev)
+        records, npig, err = _native.coco_map_match(
+            self._cat_or_empty(self.detection_box, (0, 4), torch.float32, dev), det_score,
+            self._cat_or_empty(self.detection_labels, (0,), torch.int64, dev), det_counts,
+            self._cat_or_empty(self.groundtruth_box, (0, 4), torch.float32, dev),
+            self._cat_or_empty(self.groundtruth_labels, (0,), torch.int64, dev),
+            self._cat_or_empty(self.groundtruth_crowds, (0,), torch.uint8, dev),
+            self._cat_or_empty(self.groundtruth_area, (0,), torch.float64, dev), gt_counts, classes, self.iou_thresholds,
+            self.max_detection_thresholds[-1])
+        dist.all_reduce(npig, group=group)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX, group=group)
+        if int(err.item()) != 0:
+            raise NotImplementedError("metrics_b200: an image holds more ground truths of one class than the matcher can track")
+        # ---- records of all ranks, in the interleaved image order of the gathered evaluation -------------------------------------
+        cat, rnk, match, ignore = records
+        packed = torch.stack([(cat.to(torch.int64) << 32) | rnk.to(torch.int64), det_score.contiguous().view(torch.int32).to(torch.int64),
+                              match, ignore], dim=1)  # [n_local, 4] int64
+        allrec = torch.cat(gather_all_tensors(packed, group))
+        bases = np.concatenate([[0], np.cumsum([sum(c) for c in counts_all])])
+        offs = [np.concatenate([[0], np.cumsum(c)]) for c in counts_all]
+        pieces = [np.arange(bases[r] + offs[r][i], bases[r] + offs[r][i + 1]) for i in range(max(len(c) for c in counts_all))
+                  for r in range(world) if i < len(counts_all[r])]
+        perm = torch.from_numpy(np.concatenate(pieces).astype(np.int64) if pieces else np.zeros(0, np.int64)).to(dev)
+        allrec = allrec[perm]
+        # ---- phase 2 on this rank's classes ----------------------------------------------------------------------------------------
+        cpr = (k + world - 1) // world
+        lo = min(rank * cpr, k)
+        hi = min(lo + cpr, k)
+        precision, recall, scores, _ = _native.coco_map_accumulate(
+            (allrec[:, 0] >> 32).to(torch.int32), allrec[:, 1].to(torch.int32).view(torch.float32),
+            (allrec[:, 0] & 0xFFFFFFFF).to(torch.int32), allrec[:, 2], allrec[:, 3], npig, k, lo, hi, len(self.iou_thresholds),
+            self.rec_thresholds, self.max_detection_thresholds)
+        # ---- the class slices of every rank ---------------------------------------------------------------------------------------
+        t, r_, m = precision.shape[0], precision.shape[1], precision.shape[4]
+        slab_p = torch.full((t, r_, cpr, 4, m), -1.0, dtype=torch.float64, device=dev)
+        slab_r = torch.full((t, cpr, 4, m), -1.0, dtype=torch.float64, device=dev)
+        slab_p[:, :, : hi - lo] = precision[:, :, lo:hi]
+        slab_r[:, : hi - lo] = recall[:, lo:hi]
+        precision = _gather_equal(slab_p, group, world).permute(1, 2, 0, 3, 4, 5).reshape(t, r_, world * cpr, 4, m)[:, :, :k].contiguous()
+        recall = _gather_equal(slab_r, group, world).permute(1, 0, 2, 3, 4).reshape(t, world * cpr, 4, m)[:, :k].contiguous()
+        return self._results(precision, recall, classes_list, {}, (precision, recall) if self.class_metrics else None)
 
     @staticmethod
     def _masked_mean(x: Tensor, dims: Optional[Tuple[int, ...]] = None) -> Tensor:

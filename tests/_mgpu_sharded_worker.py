@@ -84,6 +84,26 @@ def main():
     for k in truth:
         assert torch.equal(got[k].cpu(), truth[k].cpu()), (k, got[k], truth[k])
     assert len(m.detection_box) == n_imgs[rank]  # unsynced again
+    # the default path above is the evaluation SHARDED over ranks (own images matched, own classes accumulated); the
+    # reference-shaped "gather every image everywhere" sync must give the very same numbers, and so must an empty rank
+    os.environ["MB200_SHARDED_MAP"] = "0"
+    m._computed = None
+    gathered = m.compute()
+    os.environ["MB200_SHARDED_MAP"] = "1"
+    for k in truth:
+        assert torch.equal(gathered[k].cpu(), truth[k].cpu()), (k, gathered[k], truth[k])
+    lonely = MeanAveragePrecision(class_metrics=True).to(dev)
+    if rank != 0:  # rank 0 holds no image at all
+        lonely.update(to_dev(shards[rank][0]), to_dev(shards[rank][1]))
+    got2 = lonely.compute()
+    one2 = MeanAveragePrecision(class_metrics=True, sync_on_compute=False).to(dev)
+    for i in range(max(n_imgs)):
+        for r in range(1, world):
+            if i < n_imgs[r]:
+                one2.update(to_dev(shards[r][0][i:i + 1]), to_dev(shards[r][1][i:i + 1]))
+    truth2 = one2.compute()
+    for k in truth2:
+        assert torch.equal(got2[k].cpu(), truth2[k].cpu()), (k, got2[k], truth2[k])
     torch.distributed.barrier()
     if rank == 0:
         print("SHARDED_OK")

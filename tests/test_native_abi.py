@@ -166,6 +166,10 @@ def test_every_kernel_wrapper_calls_the_abi_as_declared(monkeypatch):
     ws.put_all(labels, 256)
     ws.pack_keys_put(scores, 2, 2 * n, n, 0)
     ws.reduce_put_i64(0, 4096, 100, 0)
+    recs, npig, _ = _native.coco_map_match(boxes, torch.rand(4), torch.zeros(4, dtype=torch.long), [2, 2], boxes,
+                                           torch.zeros(4, dtype=torch.long), torch.zeros(4, dtype=torch.uint8), torch.ones(4), [2, 2],
+                                           torch.zeros(1, dtype=torch.long), [0.5, 0.75], 100)
+    _native.coco_map_accumulate(recs[0], torch.rand(4), recs[1], recs[2], recs[3], npig, 1, 0, 1, 2, [0.0, 0.5, 1.0], [1, 10, 100])
     assert _native.launch_count() == 0
 
     # (`mb200_regression_num_sums` is a query for C callers; the Python mirror knows the layout of each op's sums)
