@@ -69,11 +69,19 @@ def _multiclass_confusion_matrix_update_(
     ignore_index: Optional[int] = None,
     validate_args: bool = False,
 ) -> None:
-    """FUSED format+update: ``confmat[target, argmax(preds)] += 1`` in place, one pass over ``preds``."""
-    flag = new_flag(confmat.device) if validate_args else None
-    _native.multiclass_confmat_update_(confmat, labels_as_int(preds, target), target, num_classes, ignore_index, flag)
-    if flag is not None:
-        raise_if_flagged(flag, num_classes, ignore_index)
+    """FUSED format+update: ``confmat[target, argmax(preds)] += 1`` in place, one pass over ``preds``.
+
+    ``validate_args=True``: the label range check runs INSIDE the kernel, so the batch is first counted into a scratch matrix
+    and folded into the state only after the error word came back clean — a caller that catches the error finds the state
+    untouched, like the reference, which validates before it counts (confusion_matrix.py:287-294)."""
+    if not validate_args:
+        _native.multiclass_confmat_update_(confmat, labels_as_int(preds, target), target, num_classes, ignore_index, None)
+        return
+    flag = new_flag(confmat.device)
+    scratch = torch.zeros_like(confmat)
+    _native.multiclass_confmat_update_(scratch, labels_as_int(preds, target), target, num_classes, ignore_index, flag)
+    raise_if_flagged(flag, num_classes, ignore_index)
+    confmat += scratch
 
 
 def _multiclass_confusion_matrix_format(

@@ -103,14 +103,19 @@ def _multiclass_stat_scores_update_(
     if multidim_average != "global":
         raise ValueError("use `_multiclass_stat_scores_update` for samplewise statistics")
     flag = new_flag(tp.device) if validate_args else None
+    # validate_args: count into scratch states first and fold them in only after the kernel's error word came back clean, so
+    # that a caught validation error leaves the states untouched (the reference validates before it counts, :287-326)
+    states = (tp, fp, tn, fn) if flag is None else tuple(torch.zeros_like(s) for s in (tp, fp, tn, fn))
     if top_k > 1:
-        _native.multiclass_stat_scores_topk_update_(tp, fp, tn, fn, workspace, preds, target, num_classes, top_k, ignore_index, flag)
+        _native.multiclass_stat_scores_topk_update_(*states, workspace, preds, target, num_classes, top_k, ignore_index, flag)
     else:
         _native.multiclass_stat_scores_update_(
-            tp, fp, tn, fn, workspace, labels_as_int(preds, target), target, num_classes, ignore_index, average == "micro", flag
+            *states, workspace, labels_as_int(preds, target), target, num_classes, ignore_index, average == "micro", flag
         )
     if flag is not None:
         raise_if_flagged(flag, num_classes, ignore_index)
+        for state, delta in zip((tp, fp, tn, fn), states):
+            state += delta
 
 
 def _class_count_bound(preds: Tensor, target: Tensor) -> int:

@@ -241,3 +241,27 @@ def test_large_stat_score_updates_with_deferred_fold_equal_chunked_updates(avera
     for name in ("tp", "fp", "tn", "fn"):
         assert torch.equal(getattr(big, name), getattr(small, name)), name
     assert int(big._workspace(1000, torch.device(DEV)).abs().sum()) == 0
+
+
+def test_failed_validation_leaves_the_state_untouched():
+    """`validate_args=True`: the range check runs inside the counting kernel, but a batch with an out-of-range label must not
+    leave its in-range rows in the state (the reference validates before it counts): a caller that catches the error and goes
+    on sees exactly the state from before the bad batch."""
+    from metrics_b200.classification import MulticlassConfusionMatrix, MulticlassStatScores
+
+    g = torch.Generator().manual_seed(21)
+    lg = torch.randn(500, 7, generator=g).to(DEV)
+    good = torch.randint(0, 7, (500,), generator=g).to(DEV)
+    bad = good.clone()
+    bad[123] = 9
+    for metric in (MulticlassConfusionMatrix(num_classes=7), MulticlassStatScores(num_classes=7, average=None)):
+        metric = metric.to(DEV)
+        metric.update(lg, good)
+        before = {k: v.clone() for k, v in metric.metric_state.items()}
+        with pytest.raises(RuntimeError, match="Detected more unique values"):
+            metric.update(lg, bad)
+        for k, v in metric.metric_state.items():
+            assert torch.equal(v, before[k]), k
+        metric.update(lg, good)  # and the metric keeps working
+        for k, v in metric.metric_state.items():
+            assert torch.equal(v, 2 * before[k]), k
