@@ -203,9 +203,8 @@ class MeanAveragePrecision(Metric):
                 pieces = iter(converted.split([c for c in counts if c > 0]))
             for b, c in zip(boxes_list, counts):
                 store.append(next(pieces) if c > 0 else b)
-        for item in preds:
-            self.detection_labels.append(item["labels"])
-            self.detection_scores.append(item["scores"])
+        self.detection_labels.extend([item["labels"] for item in preds])
+        self.detection_scores.extend([item["scores"] for item in preds])
         # defaults for missing `iscrowd` / `area` (reference :518: zeros_like(labels) per image): ONE zero buffer per call,
         # handed out as per-image views — a launch per image would dominate the whole update otherwise
         zero_views = None
