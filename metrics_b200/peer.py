@@ -100,6 +100,11 @@ class PeerWorkspace:
         _native.check(rc, "peer_reduce_put_i64")
 
 
+def _group_key(group: Any) -> Any:
+    """c10d's unique name of the group (an `id()` could be handed to a later group after this one is destroyed)."""
+    return getattr(group, "group_name", None) or id(group)
+
+
 def enabled() -> bool:
     return os.environ.get("MB200_PEER_EXCHANGE", "1") != "0"
 
@@ -110,10 +115,13 @@ def get(group: Any, device: torch.device, nbytes: int) -> Optional[PeerWorkspace
     if not enabled() or device.type != "cuda":
         return None
     group = group or torch.distributed.group.WORLD
-    key = (id(group), device.index if device.index is not None else torch.cuda.current_device())
+    key = (_group_key(group), device.index if device.index is not None else torch.cuda.current_device())
     if key[0] in _disabled:
         return None
     ws = _workspaces.get(key)
+    if ws is not None and ws.group is not group:  # a re-initialised process group reusing the name: never talk to the old one
+        _workspaces.pop(key)
+        ws = None
     if ws is not None and ws.nbytes >= nbytes:
         return ws
     want = _round_up(max(nbytes + nbytes // 4, 1 << 20), 1 << 20)  # headroom: growing is a collective re-allocation
@@ -138,4 +146,4 @@ def get(group: Any, device: torch.device, nbytes: int) -> Optional[PeerWorkspace
 
 def why_disabled(group: Any = None) -> Optional[str]:
     group = group or torch.distributed.group.WORLD
-    return _disabled.get(id(group))
+    return _disabled.get(_group_key(group))
