@@ -93,6 +93,7 @@ SIGNATURES = {
     "mb200_curve_softmax_if_logits": ("i", "piqqppp"),
     "mb200_curve_normalize_scratch_bytes": ("q", "q"),
     "mb200_curve_sigmoid_if_logits_scratch": ("i", "piqppqp"),
+    "mb200_curve_softmax_if_logits_scratch": ("i", "piqqppqp"),
     "mb200_curve_workspace_bytes": ("q", "qq"),
     "mb200_curve_workspace_bytes_for": ("q", "qqi"),
     "mb200_curve_weighted_workspace_bytes": ("q", "qi"),
@@ -367,10 +368,14 @@ def softmax_if_logits(preds: Tensor) -> Tensor:
     if preds.numel() == 0:
         return out
     st = stream_handle(dev)
+    n, c = preds.shape[0], preds.shape[1]
     with on_device(dev):
-        rc = lib().mb200_curve_softmax_if_logits(
-            ptr(preds), tag(preds), i64(preds.shape[0]), i64(preds.shape[1]), ptr(out), ptr(_flag_scratch(dev, st)), st
-        )
+        if c <= 1024 and preds.dtype != torch.float64:  # speculative single pass: one pending byte per row behind the vote word
+            scratch = torch.empty(8 + n, dtype=torch.uint8, device=dev)
+            rc = lib().mb200_curve_softmax_if_logits_scratch(preds.data_ptr(), tag(preds), n, c, out.data_ptr(),
+                                                             scratch.data_ptr(), 8 + n, st)
+        else:
+            rc = lib().mb200_curve_softmax_if_logits(ptr(preds), tag(preds), i64(n), i64(c), ptr(out), ptr(_flag_scratch(dev, st)), st)
     check(rc, "curve_softmax_if_logits")
     return out
 

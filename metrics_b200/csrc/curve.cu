@@ -273,6 +273,73 @@ __global__ void __launch_bounds__(256) softmax_if_kernel(const T* __restrict__ x
     }
 }
 
+// Speculative single pass over [N, C <= 1024] rows (f32 / f16 / bf16): a warp keeps its row in registers, so the maximum, the
+// sum and the quotient need ONE read and ONE `expf` per score (the kernel above reads the row three times and exponentiates
+// twice), and the batch-global vote is handled like in `sigmoid_spec_kernel`: a row that itself holds a score outside [0, 1]
+// knows the outcome and writes its softmax; an in-range row is written through and marked pending, to be revisited by the
+// fix-up launch only if the batch turns out to be logits.  Same summation order as above (lane-strided partial sums,
+// butterfly), hence the same bits as ATen's warp softmax.
+template <typename T, int kIter, bool kFix>
+__global__ void __launch_bounds__(256) softmax_spec_kernel(const T* __restrict__ x, T* __restrict__ out, int n, int C,
+                                                           unsigned* __restrict__ vote, unsigned char* __restrict__ pending) {
+    if (kFix && *vote == 0u) return;
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    bool warp_voted = false;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n; r += gridDim.x * wpb) {
+        if (kFix && pending[r] == 0) continue;
+        const T* __restrict__ row = x + (size_t)r * C;
+        T* __restrict__ orow = out + (size_t)r * C;
+        float v[kIter];
+        bool outside = false;
+        float m = -INFINITY;
+#pragma unroll
+        for (int it = 0; it < kIter; ++it) {
+            const int c = lane + 32 * it;
+            if (c < C) {
+                v[it] = to_float<T>(row[c]);
+                outside |= (v[it] < 0.f) | (v[it] > 1.f);
+                m = fmaxf(m, v[it]);
+            }
+        }
+        const bool apply = kFix ? true : (__any_sync(kFull, outside) != 0);
+        if (!kFix && lane == 0) {
+            if (apply) {
+                if (!warp_voted) atomicOr(vote, 1u);
+            } else {
+                pending[r] = 1;
+            }
+        }
+        warp_voted |= apply;
+        if (!apply) {
+#pragma unroll
+            for (int it = 0; it < kIter; ++it) {
+                const int c = lane + 32 * it;
+                if (c < C) orow[c] = row[c];
+            }
+            continue;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+        float s = 0.f;
+#pragma unroll
+        for (int it = 0; it < kIter; ++it) {
+            const int c = lane + 32 * it;
+            if (c < C) {
+                v[it] = expf(v[it] - m);
+                s += v[it];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+#pragma unroll
+        for (int it = 0; it < kIter; ++it) {
+            const int c = lane + 32 * it;
+            if (c < C) orow[c] = from_float<T>(v[it] / s);
+        }
+    }
+}
+
 // float64 rows: the same warp layout in double arithmetic (ATen's CUDA softmax accumulates doubles in double)
 template <>
 __global__ void __launch_bounds__(256) softmax_if_kernel<double>(const double* __restrict__ x, double* __restrict__ out, int n,
@@ -1267,4 +1334,46 @@ extern "C" int mb200_curve_sigmoid_if_logits_scratch(const void* preds, int dtyp
     count_launch();
     count_launch();
     return check_cuda(cudaGetLastError(), "curve format launch");
+}
+
+// mb200_curve_softmax_if_logits with a caller-owned scratch of 8 + n bytes (vote word + one pending byte per row): rows of at
+// most 1024 f32 / f16 / bf16 scores take the speculative single pass above; everything else the original kernels.
+extern "C" int mb200_curve_softmax_if_logits_scratch(const void* preds, int dtype, int64_t n, int64_t num_classes, void* out,
+                                                     void* scratch, int64_t scratch_bytes, void* stream) {
+    MB200_REQUIRE(n >= 0 && num_classes >= 1, "bad sizes");
+    if (n == 0) return 0;
+    MB200_REQUIRE(preds && out && scratch, "NULL pointer");
+    MB200_REQUIRE(n < (1ll << 31) && num_classes < (1ll << 31), "sizes exceed int32");
+    const bool spec = dtype != MB200_F64 && num_classes <= 1024 && scratch_bytes >= 8 + n &&
+                      (reinterpret_cast<uintptr_t>(scratch) & 3) == 0;
+    if (!spec) return mb200_curve_softmax_if_logits(preds, dtype, n, num_classes, out, reinterpret_cast<uint32_t*>(scratch), stream);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    MB200_CUDA_OK(cudaMemsetAsync(scratch, 0, (size_t)(8 + n), st));
+    unsigned* vote = reinterpret_cast<unsigned*>(scratch);
+    unsigned char* pending = reinterpret_cast<unsigned char*>(scratch) + 8;
+    const int grid = blocks_for(n, 8, sm_count() * 6);
+    const int C = (int)num_classes;
+#define MB200_SMX2(T, ITER)                                                                                                  \
+    softmax_spec_kernel<T, ITER, false><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), reinterpret_cast<T*>(out),   \
+                                                              (int)n, C, vote, pending);                                     \
+    softmax_spec_kernel<T, ITER, true><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), reinterpret_cast<T*>(out),    \
+                                                             (int)n, C, vote, pending);
+#define MB200_SMX(T)                       \
+    if (C <= 32) { MB200_SMX2(T, 1) }       \
+    else if (C <= 64) { MB200_SMX2(T, 2) }  \
+    else if (C <= 128) { MB200_SMX2(T, 4) } \
+    else if (C <= 256) { MB200_SMX2(T, 8) } \
+    else if (C <= 512) { MB200_SMX2(T, 16) } \
+    else { MB200_SMX2(T, 32) }
+    switch (dtype) {
+        case MB200_F32: MB200_SMX(float) break;
+        case MB200_F16: MB200_SMX(__half) break;
+        case MB200_BF16: MB200_SMX(__nv_bfloat16) break;
+        default: set_error("softmax scores must be f32/f16/bf16/f64 (dtype tag %d)", dtype); return MB200_ERR_INVALID;
+    }
+#undef MB200_SMX
+#undef MB200_SMX2
+    count_launch();
+    count_launch();
+    return check_cuda(cudaGetLastError(), "curve softmax launch");
 }

@@ -143,6 +143,7 @@ def test_every_kernel_wrapper_calls_the_abi_as_declared(monkeypatch):
     _native.sigmoid_if_logits(scores[:, 0])
     _native.sigmoid_if_logits(torch.rand(40000))
     _native.softmax_if_logits(scores)
+    _native.softmax_if_logits(scores.double())
     _native.curve_evaluate(scores[:, 0], labels.clamp(max=1), 1, 1, want_curve=True)
     _native.curve_evaluate(scores, labels, c)
     keys = _native.curve_pack_keys(scores, c)

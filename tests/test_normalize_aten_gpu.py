@@ -69,3 +69,19 @@ def test_speculative_single_pass_sigmoid(dtype, n):
     nan[17] = float("nan")  # NaN compares false: still probabilities
     got = _native.sigmoid_if_logits(nan)
     assert torch.equal(got.nan_to_num(7.0), nan.nan_to_num(7.0))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_speculative_single_pass_softmax_mixed_batches(dtype):
+    """Rows entirely inside [0, 1] are written through speculatively and must be revisited when ANOTHER row makes the batch
+    logits (the reference applies softmax to the whole tensor, utilities/compute.py:223-229); a batch of probabilities stays as
+    it is; wide rows (C > 1024) keep the original kernels."""
+    g = torch.Generator().manual_seed(12)
+    probs = torch.softmax(torch.randn(3000, 37, generator=g), 1).to(dtype).to(DEV)
+    assert torch.equal(_native.softmax_if_logits(probs), probs)
+    for where in (0, 1499, 2999):
+        mixed = probs.clone()
+        mixed[where, 5] = -2.0  # one logit row: every other row was pending
+        assert torch.equal(_native.softmax_if_logits(mixed), torch.softmax(mixed, dim=1))
+    logits = (torch.randn(2048, 1000, generator=g) * 3).to(dtype).to(DEV)
+    assert torch.equal(_native.softmax_if_logits(logits), torch.softmax(logits, dim=1))
