@@ -70,12 +70,15 @@ __global__ void __launch_bounds__(256) reg_partial_kernel(const T* __restrict__ 
 // the CTA (deterministic order).  The generic kernel above walks one element per thread per iteration with 16 warps per SM
 // and measured 0.94 TB/s; this one is bound by HBM.
 constexpr int kRegFlatThreads = 512;
-template <typename T, bool kDouble, bool kTweedie = false>
+// kOp >= 0 fixes the op at compile time (the switch over ops and the loops over the op's sums fold away: MSE / MAE, the
+// hottest ops, get their own instantiations); kOp < 0 reads it from the argument.
+template <typename T, bool kDouble, bool kTweedie = false, int kOp = -1>
 __global__ void __launch_bounds__(kRegFlatThreads) reg_flat_kernel(const T* __restrict__ preds, const T* __restrict__ target,
-                                                                   long long n, int op, double param, double eps,
+                                                                   long long n, int op_arg, double param, double eps,
                                                                    double* __restrict__ partial) {
     __shared__ double sm[kRegFlatThreads / 32];
-    const int K = reg_num_sums(op);
+    const int op = kOp >= 0 ? kOp : op_arg;
+    const int K = kOp >= 0 ? reg_num_sums(kOp) : reg_num_sums(op);
     constexpr int kVec = 16 / (int)sizeof(T);
     double acc[kRegMaxK] = {0.0, 0.0, 0.0, 0.0};
     const long long gtid = (long long)blockIdx.x * kRegFlatThreads + threadIdx.x;
@@ -175,8 +178,13 @@ extern "C" int mb200_regression_sums(const void* preds, const void* target, int 
         long long fg = (n + per_cta - 1) / per_cta;
         if (fg > 296) fg = 296;  // scratch holds 296 partial rows
         const int g1 = (int)(fg < 1 ? 1 : fg);
-#define MB200_REG_FLAT(T, DBL, TW) \
-    reg_flat_kernel<T, DBL, TW><<<g1, kRegFlatThreads, 0, st>>>((const T*)preds, (const T*)target, n, op, param, epsilon, scratch)
+#define MB200_REG_FLAT(T, DBL, TW)                                                                                          \
+    if (!TW && op == REG_MSE)                                                                                              \
+        reg_flat_kernel<T, DBL, false, REG_MSE><<<g1, kRegFlatThreads, 0, st>>>((const T*)preds, (const T*)target, n, op, param, epsilon, scratch); \
+    else if (!TW && op == REG_MAE)                                                                                         \
+        reg_flat_kernel<T, DBL, false, REG_MAE><<<g1, kRegFlatThreads, 0, st>>>((const T*)preds, (const T*)target, n, op, param, epsilon, scratch); \
+    else                                                                                                                   \
+        reg_flat_kernel<T, DBL, TW><<<g1, kRegFlatThreads, 0, st>>>((const T*)preds, (const T*)target, n, op, param, epsilon, scratch)
 #define MB200_REG_FLAT_BY_DTYPE(TW)                                                                                   \
     switch (dtype) {                                                                                                  \
         case MB200_F32: MB200_REG_FLAT(float, false, TW); break;                                                      \
