@@ -111,6 +111,13 @@ def unfused():
     _native.softmax_if_logits(lg32[i])
 
 
+def k6s():
+    i = kk[0] = (kk[0] + 1) % 4
+    _native.softmax_if_logits(lg32[i])
+
+
+record("K6 softmax_if_logits [65536,1000] f32", timed(k6s, inner=16), N * C * 4 * 2,
+       "speculative single pass: row in registers, one read + one write")
 record("K1b + K6 unfused on the same batches [65536,1000] f32", timed(unfused, inner=16), N * C * 4 * 2 + N * 8,
        "same algorithmic bytes; three reads + one write of traffic")
 del lg32

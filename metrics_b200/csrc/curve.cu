@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(256) softmax_if_kernel(const T* __restrict__ x
 // fix-up launch only if the batch turns out to be logits.  Same summation order as above (lane-strided partial sums,
 // butterfly), hence the same bits as ATen's warp softmax.
 template <typename T, int kIter, bool kFix>
-__global__ void __launch_bounds__(256) softmax_spec_kernel(const T* __restrict__ x, T* __restrict__ out, int n, int C,
+__global__ void __launch_bounds__(256, 3) softmax_spec_kernel(const T* __restrict__ x, T* __restrict__ out, int n, int C,
                                                            unsigned* __restrict__ vote, unsigned char* __restrict__ pending) {
     if (kFix && *vote == 0u) return;
     const int lane = threadIdx.x & 31;
@@ -311,11 +311,11 @@ __global__ void __launch_bounds__(256) softmax_spec_kernel(const T* __restrict__
             }
         }
         warp_voted |= apply;
-        if (!apply) {
+        if (!apply) {  // write-through from the registers: T -> float -> T is exact
 #pragma unroll
             for (int it = 0; it < kIter; ++it) {
                 const int c = lane + 32 * it;
-                if (c < C) orow[c] = row[c];
+                if (c < C) orow[c] = from_float<T>(v[it]);
             }
             continue;
         }
@@ -1351,7 +1351,7 @@ extern "C" int mb200_curve_softmax_if_logits_scratch(const void* preds, int dtyp
     MB200_CUDA_OK(cudaMemsetAsync(scratch, 0, (size_t)(8 + n), st));
     unsigned* vote = reinterpret_cast<unsigned*>(scratch);
     unsigned char* pending = reinterpret_cast<unsigned char*>(scratch) + 8;
-    const int grid = blocks_for(n, 8, sm_count() * 6);
+    const int grid = blocks_for(n, 8, sm_count() * 3);  // 3 resident CTAs per SM (<= 85 registers): one wave
     const int C = (int)num_classes;
 #define MB200_SMX2(T, ITER)                                                                                                  \
     softmax_spec_kernel<T, ITER, false><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), reinterpret_cast<T*>(out),   \
