@@ -17,9 +17,9 @@ else:
     p = torch.rand(n, c, generator=g).cuda()
     t = torch.randint(0, c, (n,), generator=g).cuda()
 for _ in range(2):
-    _native.curve_evaluate(p, t, c)
+    _native.curve_evaluate(p, t, c, unit_range=True)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-_native.curve_evaluate(p, t, c)
+_native.curve_evaluate(p, t, c, unit_range=True)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()

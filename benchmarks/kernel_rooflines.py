@@ -88,8 +88,12 @@ del q
 # K3/K5: exact binary curve evaluation, 10^7 samples
 n7 = 10_000_000
 p7, t7 = p[:n7].contiguous(), t[:n7].contiguous()
-record("K3/K5 curve_evaluate 1e7 f32 (pack + 4-pass sort + scan)", timed(lambda: _native.curve_evaluate(p7, t7, 1), reps=10), 150e6,
+record("K3/K5 curve_evaluate 1e7 f32 (pack + 4-pass sort + scan), (key, label) pairs",
+       timed(lambda: _native.curve_evaluate(p7, t7, 1, unit_range=False), reps=10), 150e6,
        "SURVEY 8(d) figure: each 5-byte record read once, written once, scanned once; the working set (50 MB) is L2-resident")
+record("K3/K5 curve_evaluate 1e7 f32, label in bit 0 of the key (metric states: non-negative scores)",
+       timed(lambda: _native.curve_evaluate(p7, t7, 1, unit_range=True), reps=10), 150e6,
+       "same algorithmic figure; the passes move 4-byte keys, the last one splits (key, label)")
 # K11: fused stat scores + softmax store, cfg5-shaped batches scaled up: [65536, 1000] f32, 4 rotating batches (1 GB)
 lg32 = [torch.randn(N, C, generator=g, device=dev) for _ in range(4)]
 tg32 = [torch.randint(0, C, (N,), generator=g, device=dev) for _ in range(4)]
@@ -124,7 +128,7 @@ del lg32
 # K3 multiclass: 1000 one-vs-rest curves over 16384 samples (cfg5, one rank's share)
 pm5 = torch.softmax(torch.randn(16384, 1000, generator=g, device=dev), 1)
 tm5 = torch.randint(0, 1000, (16384,), generator=g, device=dev)
-record("K3/K5 curve_evaluate [16384,1000] f32, 1000 segments", timed(lambda: _native.curve_evaluate(pm5, tm5, 1000), reps=10),
+record("K3/K5 curve_evaluate [16384,1000] f32, 1000 segments", timed(lambda: _native.curve_evaluate(pm5, tm5, 1000, unit_range=True), reps=10),
        16384 * 1000 * 15, "same per-record figure as the binary case (5-byte record read, written, scanned)")
 print(json.dumps(out, indent=1))
 if len(sys.argv) > 1:

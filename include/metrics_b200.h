@@ -206,6 +206,14 @@ MB200_API int mb200_curve_weighted_clf_curve(const void* preds, int preds_dtype,
                                              const double* weights, int64_t n, int64_t pos_label, void* workspace,
                                              int64_t workspace_bytes, double* fps_out, double* tps_out, void* thr_out,
                                              int64_t* count_out, uint32_t* err_flag, void* stream);
+/* mb200_curve_evaluate for scores PROMISED to be non-negative or NaN (in particular the output of normalize_logits_if_needed
+ * — every state of the curve metric classes): 31-bit keys, the label rides in bit 0, the radix passes move 4-byte keys only.
+ * A negative score (-0 is fine) raises MB200_FLAG_PREDS_RANGE in err_flag (results invalid).  float64 scores take the general
+ * path. */
+MB200_API int mb200_curve_evaluate_nonneg(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                        int64_t n, int64_t num_classes, int64_t pos_label, void* workspace,
+                                        int64_t workspace_bytes, float* out_auroc, float* out_ap, int64_t* out_counts,
+                                        float* fps_out, float* tps_out, void* thr_out, uint32_t* err_flag, void* stream);
 /* Multilabel task: `num_labels` independent binary curves in one batched sort + scan.  preds / target are
  * [n, num_labels] row-major, positives are target == 1.  With has_ignore, entries with target == ignore_index are
  * removed from their own label's curve only (they are given the largest sort key and the scan stops before them).
@@ -259,6 +267,23 @@ MB200_API int mb200_coco_map_match(const float* det_box_xywh, const float* det_s
                                    int64_t num_classes, const double* iou_thr_host, int64_t n_iou_thr, int64_t max_det_last,
                                    int32_t* det_cat, int32_t* det_rank, uint64_t* det_match, uint64_t* det_ignore,
                                    int32_t* npig, uint32_t* err_flag, void* stream);
+/* mb200_coco_map_match with what `iou_type="segm"` needs (reference detection/mean_ap.py:527-547 evaluation per IoU type,
+ * :848-853 masks, :917-944 annotation areas):
+ *   pair_inter     NULL = boxes.  Else instance masks: per image the [detections x ground truths] table of intersection pixel
+ *                  counts (mb200_mask_pair_intersections), `pair_off` [n_img] its offsets, `det_mask_area` / `gt_mask_area`
+ *                  the masks' pixel counts; IoU = inter / union as maskApi.c:rleIou (0 when inter is 0; crowd: union = the
+ *                  detection's area), detections' area ranges from `det_mask_area`; the boxes are not read.
+ *   gt_area_exact  `gt_area` is the annotation's final "area" (no w*h fallback for values <= 0).
+ *   micro          every label is class 0 (npig then has one row). */
+MB200_API int mb200_coco_map_match_ex(const float* det_box_xywh, const float* det_score, const int64_t* det_label,
+                                      const int32_t* det_off, const float* gt_box_xywh, const int64_t* gt_label,
+                                      const uint8_t* gt_crowd, const double* gt_area, const int32_t* gt_off, int64_t n_img,
+                                      int64_t max_det_per_img, int64_t max_gt_per_img, const int64_t* classes,
+                                      int64_t num_classes, int micro, const double* iou_thr_host, int64_t n_iou_thr,
+                                      int64_t max_det_last, const double* pair_inter, const int64_t* pair_off,
+                                      const double* det_mask_area, const double* gt_mask_area, int gt_area_exact,
+                                      int32_t* det_cat, int32_t* det_rank, uint64_t* det_match, uint64_t* det_ignore,
+                                      int32_t* npig, uint32_t* err_flag, void* stream);
 MB200_API int mb200_coco_map_accumulate(const int32_t* det_cat, const float* det_score, const int32_t* det_rank,
                                         const uint64_t* det_match, const uint64_t* det_ignore, int64_t n_det,
                                         const int32_t* npig, int64_t num_classes, int64_t class_lo, int64_t class_hi,
@@ -376,6 +401,23 @@ MB200_API int mb200_peer_put_all(const void* src, int64_t nbytes, void* const* p
                                  int world, void* stream);
 MB200_API int mb200_peer_reduce_put_i64(void* const* peer_bases, int64_t in_offset_bytes, int64_t out_offset_bytes,
                                         int64_t n, int rank, int world, int op, void* stream);
+
+/* ---- K12: instance masks for MeanAveragePrecision(iou_type="segm") (csrc/maskiou.cu) --------------------------------------
+ * The reference run-length encodes every mask on the host (detection/mean_ap.py:848-853, pycocotools mask_utils.encode) and
+ * pycocotools intersects run-length codes pair by pair on the host (maskApi.c:rleIou).  Here:
+ * mb200_mask_pack_bits: `masks` uint8/bool [n_masks][pixels_per_mask] (non-zero = set) -> one bit per pixel, 32 pixels per
+ *   word in pixel order, row m at words_out + m * out_stride_words; area_out[m] = number of set pixels (int64).
+ * mb200_mask_pair_intersections: for image i with detections [det_off[i], det_off[i+1]) and ground truths [gt_off[i],
+ *   gt_off[i+1]), whose bit rows start at det_words + det_word_off[d] / gt_words + gt_word_off[g] and are img_words[i] words
+ *   long: inter_out[pair_off[i] + d_local * G_i + g_local] = popcount(det & gt) as a double; pairs of different labels
+ *   (unless micro) are written as 0 — the matcher never reads them.  max_pairs_per_img only sizes the grid. */
+MB200_API int mb200_mask_pack_bits(const uint8_t* masks, int64_t n_masks, int64_t pixels_per_mask, uint32_t* words_out,
+                                   int64_t out_stride_words, int64_t* area_out, void* stream);
+MB200_API int mb200_mask_pair_intersections(const uint32_t* det_words, const int64_t* det_word_off, const uint32_t* gt_words,
+                                            const int64_t* gt_word_off, const int32_t* det_off, const int32_t* gt_off,
+                                            const int32_t* img_words, const int64_t* det_label, const int64_t* gt_label,
+                                            int micro, const int64_t* pair_off, int64_t n_img, int64_t max_pairs_per_img,
+                                            double* inter_out, void* stream);
 
 #ifdef __cplusplus
 }

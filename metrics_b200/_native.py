@@ -101,6 +101,7 @@ SIGNATURES = {
     "mb200_curve_pack_keys": ("i", "piqqpp"),
     "mb200_curve_evaluate_keys": ("i", "ppiqqqpqppppp"),
     "mb200_curve_evaluate": ("i", "pipiqqqpqpppppppp"),
+    "mb200_curve_evaluate_nonneg": ("i", "pipiqqqpqpppppppp"),
     "mb200_curve_evaluate_multilabel": ("i", "pipiqqiqpqpppppppp"),
     "mb200_coco_map_workspace_bytes": ("q", "qqq"),
     "mb200_coco_map_evaluate": ("i", "pppppppppqqqqqpqipqpqpqpqppppp"),
@@ -380,12 +381,19 @@ def softmax_if_logits(preds: Tensor) -> Tensor:
     return out
 
 
-def curve_evaluate(preds: Tensor, target: Tensor, num_classes: int = 1, pos_label: int = 1, want_curve: bool = False):
-    """Sort + TP/FP scan for ``num_classes`` one-vs-rest curves (``mb200_curve_evaluate``).
+def curve_evaluate(preds: Tensor, target: Tensor, num_classes: int = 1, pos_label: int = 1, want_curve: bool = False,
+                   unit_range: Optional[bool] = None):
+    """Sort + TP/FP scan for ``num_classes`` one-vs-rest curves (``mb200_curve_evaluate`` / ``mb200_curve_evaluate_nonneg``).
 
     Returns ``(auroc[C] f32, ap[C] f32, counts[C, 3] i64, curve)`` where ``curve`` is ``None`` or the tuple
     ``(fps, tps, thresholds)`` of ``[C, N]`` buffers whose first ``counts[c, 2]`` entries per row are valid; fps / tps are
     float32, thresholds float64 for float64 scores (sorted as 64-bit keys) and float32 otherwise.
+
+    ``unit_range``: non-negative (or NaN) scores — anything in [0, 1] — sort as 4-byte keys with the label in bit 0 (the
+    ``_nonneg`` entry).  ``True`` is the
+    caller's promise (metric states: ``normalize_logits_if_needed`` ran on them) and is not checked here; ``None`` tries that
+    path, reads the kernel's range flag back (one host sync — every caller reads ``counts`` on the host next anyway) and
+    re-evaluates on the general path if a score was outside; ``False`` takes the general path.
     """
     if _TORCH_BINDING:
         auroc, ap, counts, fps, tps, thr = _ops().curve_evaluate(preds, target, int(num_classes), int(pos_label), bool(want_curve))
@@ -404,13 +412,19 @@ def curve_evaluate(preds: Tensor, target: Tensor, num_classes: int = 1, pos_labe
     if want_curve:
         thr_dtype = torch.float64 if preds.dtype == torch.float64 else torch.float32
         curve = tuple(torch.empty((num_classes, n), dtype=dt, device=dev) for dt in (torch.float32, torch.float32, thr_dtype))
+    unit = unit_range is not False and preds.dtype != torch.float64 and n > 0
+    flag = torch.zeros(1, dtype=torch.int32, device=dev) if unit and unit_range is None else None
     with on_device(dev):
-        rc = lib_.mb200_curve_evaluate(
-            ptr(preds), tag(preds), ptr(target), tag(target), i64(n), i64(num_classes), i64(pos_label), ptr(ws),
-            i64(nbytes), ptr(auroc), ptr(ap), ptr(counts), ptr(curve[0] if curve else None),
-            ptr(curve[1] if curve else None), ptr(curve[2] if curve else None), ptr(None), stream_handle(dev),
-        )
-    check(rc, "curve_evaluate")
+        for entry in ((lib_.mb200_curve_evaluate_nonneg, lib_.mb200_curve_evaluate) if unit else (lib_.mb200_curve_evaluate,)):
+            rc = entry(
+                ptr(preds), tag(preds), ptr(target), tag(target), i64(n), i64(num_classes), i64(pos_label), ptr(ws),
+                i64(nbytes), ptr(auroc), ptr(ap), ptr(counts), ptr(curve[0] if curve else None),
+                ptr(curve[1] if curve else None), ptr(curve[2] if curve else None), ptr(flag), stream_handle(dev),
+            )
+            check(rc, "curve_evaluate")
+            if flag is None or int(flag) == 0:
+                break
+            flag = None  # a negative score: once more on the general path
     return auroc, ap, counts, curve
 
 

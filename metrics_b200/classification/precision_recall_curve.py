@@ -108,7 +108,8 @@ class BinaryPrecisionRecallCurve(Metric):
             preds, target = self._state()
             if preds.numel() == 0:
                 raise IndexError("metrics_b200: cannot evaluate a curve metric without samples")
-            auroc, ap, counts, _ = _native.curve_evaluate(preds, target, num_classes, pos_label, want_curve=False)
+            auroc, ap, counts, _ = _native.curve_evaluate(preds, target, num_classes, pos_label, want_curve=False,
+                                                          unit_range=True)  # states are post-format
             hit = (auroc, ap, counts)
             self._cache_put(key, hit)
         return hit

@@ -38,8 +38,14 @@ struct MapEvalArgs {
     const float4* gt_box;
     const long long* gt_label;
     const unsigned char* gt_crowd;
-    const double* gt_area_given;  // <= 0: use w*h
+    const double* gt_area_given;  // <= 0: use w*h (unless gt_area_exact)
     const int* gt_off;
+    // instance masks (K12, maskiou.cu) instead of boxes: per image a [D][G] table of intersection pixel counts + mask areas
+    const double* pair_inter;     // NULL: box IoU
+    const long long* pair_off;    // [n_img] offset of the image's table
+    const double* det_mask_area;  // [n_det]
+    const double* gt_mask_area;   // [n_gt]   (union of the IoU; the area-range test uses gt_area_given)
+    int gt_area_exact;            // gt_area_given is final (the caller resolved "given or computed")
     const long long* classes;  // sorted unique labels, [K]
     int K;
     int micro;
@@ -85,8 +91,15 @@ __device__ __forceinline__ double bb_iou(const float4 d, const float4 g, bool cr
     return inter / uni;
 }
 
+// maskApi.c:rleIou: intersection / union from pixel counts; no intersection -> 0 (also for empty masks)
+__device__ __forceinline__ double mask_iou(double inter, double det_area, double gt_area, bool crowd) {
+    if (inter <= 0.0) return 0.0;
+    return inter / (crowd ? det_area : det_area + gt_area - inter);
+}
+
 __host__ __device__ inline size_t map_eval_smem_bytes(int max_d, int max_g) {
     size_t b = 0;
+    b += (size_t)(max_d + max_g) * 8;       // mask areas (mask mode; boxes leave them unused)
     b += (size_t)max_d * (16 + 8 + 8);      // box, match word, ignore word
     b += (size_t)max_g * (16 + 8);          // box, area
     b += (size_t)max_d * (4 + 4 + 4 + 4);   // score, cat, rank, by_pos
@@ -109,6 +122,10 @@ __global__ void __launch_bounds__(256) map_evaluate_kernel(MapEvalArgs p, int ma
     unsigned long long* dmatch = reinterpret_cast<unsigned long long*>(ptr); ptr += (size_t)max_d * 8;
     unsigned long long* dign = reinterpret_cast<unsigned long long*>(ptr); ptr += (size_t)max_d * 8;
     double* garea = reinterpret_cast<double*>(ptr); ptr += (size_t)max_g * 8;
+    double* dmarea = reinterpret_cast<double*>(ptr); ptr += (size_t)max_d * 8;  // mask mode: detection mask areas
+    double* gmarea = reinterpret_cast<double*>(ptr); ptr += (size_t)max_g * 8;  //            ground-truth mask areas
+    const bool masks = p.pair_inter != nullptr;
+    const double* __restrict__ inter_tab = masks ? p.pair_inter + p.pair_off[img] : nullptr;
     float* dscore = reinterpret_cast<float*>(ptr); ptr += (size_t)max_d * 4;
     int* dcat = reinterpret_cast<int*>(ptr); ptr += (size_t)max_d * 4;
     int* drank = reinterpret_cast<int*>(ptr); ptr += (size_t)max_d * 4;
@@ -130,6 +147,7 @@ __global__ void __launch_bounds__(256) map_evaluate_kernel(MapEvalArgs p, int ma
         dcat[i] = p.micro ? 0 : class_index(p.classes, p.K, p.det_label[d0 + i]);
         dmatch[i] = 0ull;
         dign[i] = 0ull;
+        if (masks) dmarea[i] = p.det_mask_area[d0 + i];
     }
     for (int i = tid; i < G; i += nth) {
         const float4 b = p.gt_box[g0 + i];
@@ -137,7 +155,8 @@ __global__ void __launch_bounds__(256) map_evaluate_kernel(MapEvalArgs p, int ma
         gcat[i] = p.micro ? 0 : class_index(p.classes, p.K, p.gt_label[g0 + i]);
         gcrowd[i] = p.gt_crowd[g0 + i] != 0;
         const double given = p.gt_area_given[g0 + i];
-        garea[i] = given > 0.0 ? given : (double)b.z * (double)b.w;  // detection/mean_ap.py:920-925
+        garea[i] = (p.gt_area_exact || given > 0.0) ? given : (double)b.z * (double)b.w;  // detection/mean_ap.py:920-925
+        if (masks) gmarea[i] = p.gt_mask_area[g0 + i];
     }
     __syncthreads();
 
@@ -227,7 +246,8 @@ __global__ void __launch_bounds__(256) map_evaluate_kernel(MapEvalArgs p, int ma
                     const bool ig = crowd || area_outside(garea[g], a);
                     if ((int)ig != phase) continue;
                     if (ord < mask_bits && ((gtm[ord >> 6] >> (ord & 63)) & 1ull) && !crowd) continue;
-                    const double iou = bb_iou(db, gbox[g], crowd);
+                    const double iou = masks ? mask_iou(inter_tab[(long long)d * G + g], dmarea[d], gmarea[g], crowd)
+                                             : bb_iou(db, gbox[g], crowd);
                     if (iou < best) continue;
                     best = iou;
                     m = ord;
@@ -235,7 +255,7 @@ __global__ void __launch_bounds__(256) map_evaluate_kernel(MapEvalArgs p, int ma
                 }
             }
             if (m == -1) {
-                if (area_outside((double)db.z * (double)db.w, a)) atomicOr(&dign[d], 1ull << bit);
+                if (area_outside(masks ? dmarea[d] : (double)db.z * (double)db.w, a)) atomicOr(&dign[d], 1ull << bit);
             } else {
                 atomicOr(&dmatch[d], 1ull << bit);
                 if (m_ig) atomicOr(&dign[d], 1ull << bit);
@@ -508,7 +528,8 @@ int map_match_impl(const float* det_box_xywh, const float* det_score, const int6
                    const int32_t* gt_off, int64_t n_img, int64_t max_det_per_img, int64_t max_gt_per_img,
                    const int64_t* classes, int64_t num_classes, int micro, const double* iou_thr_host, int T, int max_det_last,
                    int* det_cat, int* det_rank, unsigned long long* det_match, unsigned long long* det_ignore, int* npig,
-                   uint32_t* err_flag, cudaStream_t st) {
+                   uint32_t* err_flag, cudaStream_t st, const double* pair_inter = nullptr, const int64_t* pair_off = nullptr,
+                   const double* det_mask_area = nullptr, const double* gt_mask_area = nullptr, int gt_area_exact = 0) {
     if (n_img == 0) return 0;
     // More than 256 ground truths in one image MAY put more than 256 of one class there: then the per-thread "matched" masks
     // move from registers to shared memory, one bit per ground truth of the image per thread.
@@ -530,6 +551,11 @@ int map_match_impl(const float* det_box_xywh, const float* det_score, const int6
     ea.gt_crowd = gt_crowd;
     ea.gt_area_given = gt_area;
     ea.gt_off = gt_off;
+    ea.pair_inter = pair_inter;
+    ea.pair_off = reinterpret_cast<const long long*>(pair_off);
+    ea.det_mask_area = det_mask_area;
+    ea.gt_mask_area = gt_mask_area;
+    ea.gt_area_exact = gt_area_exact;
     ea.classes = reinterpret_cast<const long long*>(classes);
     ea.K = (int)num_classes;
     ea.micro = micro;
@@ -665,6 +691,33 @@ extern "C" int mb200_coco_map_match(
                           (int)max_det_last, det_cat, det_rank, reinterpret_cast<unsigned long long*>(det_match),
                           reinterpret_cast<unsigned long long*>(det_ignore), npig, err_flag,
                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+// mb200_coco_map_match with the two extensions `iou_type="segm"` needs (reference detection/mean_ap.py:527-547, 917-944):
+//  * instance masks: `pair_inter` (NULL = boxes) holds per image the [detections x ground truths] intersection pixel counts
+//    (mb200_mask_pair_intersections), `pair_off` the table offsets, `det_mask_area` / `gt_mask_area` the pixel counts of the
+//    masks; IoU and the detections' area ranges come from them (maskApi.c:rleIou), the boxes are ignored;
+//  * `gt_area_exact`: `gt_area` already is the annotation's final "area" (the reference resolves "given, else mask area, else
+//    w*h" on the host — with both IoU types it uses the MASK area for the box evaluation too), no w*h fallback here;
+//  * `micro`: every label is class 0.
+extern "C" int mb200_coco_map_match_ex(
+    const float* det_box_xywh, const float* det_score, const int64_t* det_label, const int32_t* det_off,
+    const float* gt_box_xywh, const int64_t* gt_label, const uint8_t* gt_crowd, const double* gt_area,
+    const int32_t* gt_off, int64_t n_img, int64_t max_det_per_img, int64_t max_gt_per_img, const int64_t* classes,
+    int64_t num_classes, int micro, const double* iou_thr_host, int64_t n_iou_thr, int64_t max_det_last,
+    const double* pair_inter, const int64_t* pair_off, const double* det_mask_area, const double* gt_mask_area,
+    int gt_area_exact, int32_t* det_cat, int32_t* det_rank, uint64_t* det_match, uint64_t* det_ignore, int32_t* npig,
+    uint32_t* err_flag, void* stream) {
+    MB200_REQUIRE(n_img >= 0 && num_classes >= 1, "bad sizes");
+    MB200_REQUIRE(n_iou_thr >= 1 && n_iou_thr <= kMapMaxThr, "between 1 and %d IoU thresholds are supported (got %lld)",
+                  kMapMaxThr, (long long)n_iou_thr);
+    MB200_REQUIRE(npig && classes && (n_img == 0 || (det_off && gt_off)), "NULL pointer");
+    MB200_REQUIRE(!pair_inter || (pair_off && det_mask_area && gt_mask_area), "mask mode needs table offsets and both areas");
+    return map_match_impl(det_box_xywh, det_score, det_label, det_off, gt_box_xywh, gt_label, gt_crowd, gt_area, gt_off, n_img,
+                          max_det_per_img, max_gt_per_img, classes, num_classes, micro, iou_thr_host, (int)n_iou_thr,
+                          (int)max_det_last, det_cat, det_rank, reinterpret_cast<unsigned long long*>(det_match),
+                          reinterpret_cast<unsigned long long*>(det_ignore), npig, err_flag,
+                          reinterpret_cast<cudaStream_t>(stream), pair_inter, pair_off, det_mask_area, gt_mask_area, gt_area_exact);
 }
 
 extern "C" int mb200_coco_map_accumulate(

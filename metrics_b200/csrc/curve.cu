@@ -370,24 +370,72 @@ __global__ void __launch_bounds__(256) softmax_if_kernel<double>(const double* _
 // key packing
 // =====================================================================================================
 // binary: keys[i] = desc_key(preds[i]), labels[i] = (target[i] == pos_label)
-template <typename T>
+// kBit0 (scores promised to be non-negative or NaN — in particular everything normalize_logits_if_needed returns): their
+// 32-bit keys use 31 bits (no sign; NaN -> 0), so the label rides in bit 0 of the key and the sort moves 4-byte keys only
+// (radix_sort_passes_bit0); a negative score (other than -0) raises MB200_FLAG_PREDS_RANGE.
+template <typename T, bool kBit0 = false, bool kI64 = false>
 __global__ void __launch_bounds__(256) pack_binary_kernel(const T* __restrict__ preds, const void* __restrict__ target,
                                                           int tdtype, long long n, long long pos_label,
                                                           typename KeyOf<T>::type* __restrict__ keys,
-                                                          unsigned char* __restrict__ labels) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        keys[i] = KeyOf<T>::make(preds[i]);
-        labels[i] = (unsigned char)(load_label(target, tdtype, i) == pos_label);
+                                                          unsigned char* __restrict__ labels, unsigned* __restrict__ err = nullptr,
+                                                          unsigned* __restrict__ hist = nullptr) {
+    // kBit0 also counts the four digit histograms of the sort (radix_sort.cuh, layout [pass][256]) while the key is in a
+    // register; the sort's own histogram read of the keys goes away.  The shared-memory atomics (4 per key, ~4.6 lanes per
+    // clock per SM measured) are the floor of this kernel, so the loads of kVec elements per thread are issued together
+    // (coalesced, kI64: no dtype switch in between) and hide behind them.
+    constexpr int kVec = 4;
+    __shared__ unsigned sh_hist[kBit0 ? 4 * 256 : 1];
+    if constexpr (kBit0) {
+        for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) sh_hist[i] = 0;
+        __syncthreads();
+    }
+    bool bad = false;
+    const long long step = (long long)gridDim.x * (256 * kVec);
+    for (long long base = (long long)blockIdx.x * (256 * kVec) + threadIdx.x; base < n; base += step) {
+        T v[kVec];
+        long long lab[kVec];
+#pragma unroll
+        for (int q = 0; q < kVec; ++q) {
+            const long long i = base + q * 256;
+            const bool ok = i < n;
+            v[q] = ok ? preds[i] : T(0);
+            lab[q] = !ok ? 0ll : kI64 ? reinterpret_cast<const long long*>(target)[i] : load_label(target, tdtype, i);
+        }
+#pragma unroll
+        for (int q = 0; q < kVec; ++q) {
+            const long long i = base + q * 256;
+            if (i >= n) continue;
+            const typename KeyOf<T>::type k = KeyOf<T>::make(v[q]);
+            const unsigned one = (unsigned)(lab[q] == pos_label);
+            if constexpr (kBit0) {
+                bad |= (k >> 31) != 0;
+                const unsigned ck = (unsigned)((k << 1) | one);
+                keys[i] = ck;
+#pragma unroll
+                for (int p = 0; p < 4; ++p) atomicAdd(&sh_hist[p * 256 + ((ck >> (8 * p)) & 255u)], 1u);
+            } else {
+                keys[i] = k;
+                labels[i] = (unsigned char)one;
+            }
+        }
+    }
+    if constexpr (kBit0) {
+        if (bad && err) atomicOr(err, MB200_FLAG_PREDS_RANGE);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) {
+            const unsigned v = sh_hist[i];
+            if (v) atomicAdd(&hist[i], v);
+        }
     }
 }
 
 // multiclass one-vs-rest: preds [N, C] row-major -> keys [C][N] (class-major), labels[c][n] = (target[n] == c).
 // 32x32 shared-memory tile transpose so that both the read and the write are coalesced.
-template <typename T>
+template <typename T, bool kBit0 = false>
 __global__ void __launch_bounds__(256) pack_ovr_kernel(const T* __restrict__ preds, const void* __restrict__ target,
                                                        int tdtype, int n, int C,
                                                        typename KeyOf<T>::type* __restrict__ keys,
-                                                       unsigned char* __restrict__ labels) {
+                                                       unsigned char* __restrict__ labels, unsigned* __restrict__ err = nullptr) {
     __shared__ typename KeyOf<T>::type tile[32][33];
     __shared__ int tgt[32];
     const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -404,6 +452,12 @@ __global__ void __launch_bounds__(256) pack_ovr_kernel(const T* __restrict__ pre
     for (int j = ty; j < 32; j += 8) {
         const int cc = c0 + j, nn = n0 + tx;
         if (nn < n && cc < C) {
+            if constexpr (kBit0) {
+                const typename KeyOf<T>::type k = tile[tx][j];
+                if ((k >> 31) != 0 && err) atomicOr(err, MB200_FLAG_PREDS_RANGE);
+                keys[(size_t)cc * n + nn] = (k << 1) | (typename KeyOf<T>::type)(tgt[tx] == cc);
+                continue;
+            }
             keys[(size_t)cc * n + nn] = tile[tx][j];
             labels[(size_t)cc * n + nn] = (unsigned char)(tgt[tx] == cc);
         }
@@ -482,306 +536,10 @@ __global__ void __launch_bounds__(256) labels_from_target_kernel(const void* __r
 }
 
 // =====================================================================================================
-// tie-collapsing TP/FP scan over sorted (key, label)     grid = (tiles, segments), tile = 256 threads x 8 items
+// tie-collapsing TP/FP scan over sorted (key, label): scan_chained_kernel below (tile states, look-back, apply) and the two
+// finalize kernels that fold the per-tile AP partials in tile order.
 // =====================================================================================================
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
-constexpr int kScanTile = kScanThreads * kScanItems;  // 2048
-
-struct TileInfo {        // produced by phase 1, turned into carries by phase 2
-    unsigned npos;       // positives in the tile           -> exclusive prefix of positives before the tile
-    unsigned nbound;     // distinct-threshold group ends   -> exclusive prefix of group ends before the tile
-    unsigned tp_last;    // local TP at the tile's last group end (or 0)   -> TP at the last group end before the tile
-    unsigned fp_last;    // local FP at the tile's last group end (or 0)   -> FP at the last group end before the tile
-    unsigned has_bound;  // tile contains a group end
-};
-
-template <int kWarps = 8>
-__device__ __forceinline__ unsigned block_excl_sum(unsigned v, unsigned* smem8, unsigned& total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned t = __shfl_up_sync(kFull, incl, o);
-        if (lane >= o) incl += t;
-    }
-    __syncthreads();
-    if (lane == 31) smem8[warp] = incl;
-    __syncthreads();
-    unsigned woff = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-        const unsigned s = smem8[w];
-        if (w < warp) woff += s;
-        tot += s;
-    }
-    total = tot;
-    return woff + incl - v;
-}
-template <int kWarps = 8>
-__device__ __forceinline__ unsigned block_excl_max(unsigned v, unsigned* smem8) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned t = __shfl_up_sync(kFull, incl, o);
-        if (lane >= o) incl = max(incl, t);
-    }
-    __syncthreads();
-    if (lane == 31) smem8[warp] = incl;
-    __syncthreads();
-    unsigned wmax = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w)
-        if (w < warp) wmax = max(wmax, smem8[w]);
-    unsigned excl = __shfl_up_sync(kFull, incl, 1);
-    if (lane == 0) excl = 0;
-    return max(wmax, excl);
-}
-
-// Blocked arrangement: thread t owns elements [t*8, t*8+8) of the tile.
-template <typename KeyT>
-struct ScanThreadData {
-    KeyT key[kScanItems];
-    KeyT key_next;  // key following the thread's last element (or ~own for "end of segment")
-    unsigned char lab[kScanItems];
-    int count;  // valid elements
-};
-
-template <typename KeyT>
-__device__ __forceinline__ void scan_load(ScanThreadData<KeyT>& d, const KeyT* __restrict__ k,
-                                          const unsigned char* __restrict__ l, int n, int tile) {
-    const int base = tile * kScanTile + threadIdx.x * kScanItems;
-    d.count = max(0, min(kScanItems, n - base));
-    const bool aligned = ((reinterpret_cast<uintptr_t>(k + base) & 15) == 0) && ((reinterpret_cast<uintptr_t>(l + base) & 7) == 0);
-    if (d.count == kScanItems && aligned) {
-        if constexpr (sizeof(KeyT) == 4) {
-            const uint4 a = *reinterpret_cast<const uint4*>(k + base);
-            const uint4 b = *reinterpret_cast<const uint4*>(k + base + 4);
-            d.key[0] = a.x, d.key[1] = a.y, d.key[2] = a.z, d.key[3] = a.w;
-            d.key[4] = b.x, d.key[5] = b.y, d.key[6] = b.z, d.key[7] = b.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < kScanItems; i += 2) {
-                const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(k + base + i);
-                d.key[i] = a.x, d.key[i + 1] = a.y;
-            }
-        }
-        const uint2 lb = *reinterpret_cast<const uint2*>(l + base);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            d.lab[i] = (unsigned char)((lb.x >> (8 * i)) & 0xff);
-            d.lab[4 + i] = (unsigned char)((lb.y >> (8 * i)) & 0xff);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < kScanItems; ++i) {
-            d.key[i] = i < d.count ? k[base + i] : (KeyT)0;
-            d.lab[i] = i < d.count ? l[base + i] : (unsigned char)0;
-        }
-    }
-    const int nxt = base + kScanItems;
-    d.key_next = (d.count == kScanItems && nxt < n) ? k[nxt] : (KeyT)0;
-}
-// is element i of this thread the last of its tie group?
-template <typename KeyT>
-__device__ __forceinline__ bool is_group_end(const ScanThreadData<KeyT>& d, int i, int n, int tile) {
-    if (i >= d.count) return false;
-    const int g = tile * kScanTile + threadIdx.x * kScanItems + i;
-    if (g == n - 1) return true;
-    const KeyT nk = (i + 1 < kScanItems) ? d.key[i + 1] : d.key_next;
-    return d.key[i] != nk;
-}
-
-// phase 1: per-tile aggregates
-template <typename KeyT>
-__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const KeyT* __restrict__ keys,
-                                                                   const unsigned char* __restrict__ labels, int n_stride,
-                                                                   const int* __restrict__ seg_ignored,
-                                                                   int tiles, TileInfo* __restrict__ info) {
-    __shared__ unsigned sm[8];
-    const int seg = blockIdx.y, tile = blockIdx.x;
-    const int n = seg_ignored ? n_stride - seg_ignored[seg] : n_stride;  // ignored entries sit behind the valid ones
-    ScanThreadData<KeyT> d;
-    scan_load(d, keys + (size_t)seg * n_stride, labels + (size_t)seg * n_stride, n, tile);
-    unsigned npos = 0, nb = 0, cum_at_last = 0;
-    int last_local = -1;
-#pragma unroll
-    for (int i = 0; i < kScanItems; ++i) {
-        npos += d.lab[i];
-        if (is_group_end(d, i, n, tile)) {
-            nb++;
-            last_local = threadIdx.x * kScanItems + i;
-            cum_at_last = npos;  // thread-local inclusive count at that element
-        }
-    }
-    unsigned tot_pos, tot_b;
-    const unsigned pos_excl = block_excl_sum(npos, sm, tot_pos);
-    (void)block_excl_sum(nb, sm, tot_b);
-    // the thread holding the tile's last group end: the max local index
-    const unsigned mine = last_local >= 0 ? (unsigned)(last_local + 1) : 0u;
-    unsigned best = mine;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(kFull, best, o));
-    __shared__ unsigned wbest[8];
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
-    __syncthreads();
-    unsigned tile_best = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) tile_best = max(tile_best, wbest[w]);
-    TileInfo* out = info + (size_t)seg * tiles + tile;
-    if (threadIdx.x == 0) {
-        out->npos = tot_pos;
-        out->nbound = tot_b;
-        out->has_bound = tile_best != 0u;
-        if (tile_best == 0u) {
-            out->tp_last = 0;
-            out->fp_last = 0;
-        }
-    }
-    if (mine != 0u && mine == tile_best) {
-        const unsigned tp = pos_excl + cum_at_last;
-        out->tp_last = tp;                          // local (within tile) counts; made global in phase 2
-        out->fp_last = (unsigned)last_local + 1u - tp;
-    }
-}
-
-// phase 2: one CTA per segment turns tile aggregates into exclusive carries (sequential over <= a few thousand tiles,
-// chunked 256 at a time with block scans).
-constexpr int kCarryThreads = 1024;
-__global__ void __launch_bounds__(kCarryThreads) scan_carry_kernel(TileInfo* __restrict__ info, int tiles, int n,
-                                                         unsigned* __restrict__ seg_totals /* [seg][2]: P, U */) {
-    __shared__ unsigned sm[kCarryThreads / 32];
-    __shared__ unsigned c_pos, c_b, c_tp, c_fp;
-    const int seg = blockIdx.x;
-    TileInfo* __restrict__ ti = info + (size_t)seg * tiles;
-    if (threadIdx.x == 0) c_pos = 0, c_b = 0, c_tp = 0, c_fp = 0;
-    __syncthreads();
-    for (int base = 0; base < tiles; base += kCarryThreads) {
-        const int t = base + threadIdx.x;
-        TileInfo v{0, 0, 0, 0, 0};
-        if (t < tiles) v = ti[t];
-        unsigned tot_pos, tot_b;
-        const unsigned pos_excl = c_pos + block_excl_sum<kCarryThreads / 32>(v.npos, sm, tot_pos);
-        const unsigned b_excl = c_b + block_excl_sum<kCarryThreads / 32>(v.nbound, sm, tot_b);
-        // global TP / FP at this tile's last group end (monotone non-decreasing along the segment -> max-scan = "last valid")
-        const unsigned tp_here = v.has_bound ? pos_excl + v.tp_last : 0u;
-        const unsigned fp_here = v.has_bound ? ((unsigned)t * (unsigned)kScanTile - pos_excl) + v.fp_last : 0u;
-        const unsigned tp_prev = max(c_tp, block_excl_max<kCarryThreads / 32>(tp_here, sm));
-        const unsigned fp_prev = max(c_fp, block_excl_max<kCarryThreads / 32>(fp_here, sm));
-        if (t < tiles) {
-            ti[t].npos = pos_excl;
-            ti[t].nbound = b_excl;
-            ti[t].tp_last = tp_prev;
-            ti[t].fp_last = fp_prev;
-        }
-        __syncthreads();
-        if (threadIdx.x == kCarryThreads - 1) {
-            c_pos = pos_excl + v.npos;
-            c_b = b_excl + v.nbound;
-            c_tp = max(tp_prev, tp_here);
-            c_fp = max(fp_prev, fp_here);
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        seg_totals[2 * seg + 0] = c_pos;
-        seg_totals[2 * seg + 1] = c_b;
-    }
-}
-
-// phase 3: per-tile scan with carries; accumulates the AUROC integer and the AP partial sum; optionally writes the
-// compacted curve (fps, tps, thresholds) at distinct thresholds.
-template <bool kWriteCurve, typename KeyT>
-__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const KeyT* __restrict__ keys,
-                                                                  const unsigned char* __restrict__ labels, int n_stride,
-                                                                  const int* __restrict__ seg_ignored,
-                                                                  int tiles, const TileInfo* __restrict__ info,
-                                                                  unsigned long long* __restrict__ auroc_acc /*[seg]*/,
-                                                                  double* __restrict__ ap_partial /*[seg][tiles]*/,
-                                                                  float* __restrict__ fps_out, float* __restrict__ tps_out,
-                                                                  typename ThrOf<KeyT>::type* __restrict__ thr_out,
-                                                                  long long curve_stride) {
-    __shared__ unsigned sm[8];
-    __shared__ double dsum[8];
-    __shared__ unsigned long long usum[8];
-    const int seg = blockIdx.y, tile = blockIdx.x;
-    const int n = seg_ignored ? n_stride - seg_ignored[seg] : n_stride;
-    ScanThreadData<KeyT> d;
-    scan_load(d, keys + (size_t)seg * n_stride, labels + (size_t)seg * n_stride, n, tile);
-    const TileInfo carry = info[(size_t)seg * tiles + tile];
-
-    unsigned npos = 0, nb = 0;
-    bool ends[kScanItems];
-#pragma unroll
-    for (int i = 0; i < kScanItems; ++i) {
-        npos += d.lab[i];
-        ends[i] = is_group_end(d, i, n, tile);
-        nb += ends[i];
-    }
-    unsigned tot;
-    const unsigned pos_excl = carry.npos + block_excl_sum(npos, sm, tot);
-    const unsigned b_excl = carry.nbound + block_excl_sum(nb, sm, tot);
-    // TP / FP at the thread's own last group end (0 if none) -> exclusive max-scan gives "previous group end" values
-    unsigned my_tp = 0, my_fp = 0;
-    {
-        unsigned run = pos_excl;
-#pragma unroll
-        for (int i = 0; i < kScanItems; ++i) {
-            run += d.lab[i];
-            if (ends[i]) {
-                my_tp = run;
-                my_fp = (unsigned)(tile * kScanTile + threadIdx.x * kScanItems + i) + 1u - run;
-            }
-        }
-    }
-    unsigned tp_prev = max(carry.tp_last, block_excl_max(my_tp, sm));
-    unsigned fp_prev = max(carry.fp_last, block_excl_max(my_fp, sm));
-
-    unsigned long long s_auc = 0;
-    double s_ap = 0.0;
-    unsigned run = pos_excl, bi = b_excl;
-#pragma unroll
-    for (int i = 0; i < kScanItems; ++i) {
-        run += d.lab[i];
-        if (ends[i]) {
-            const unsigned tp = run;
-            const unsigned fp = (unsigned)(tile * kScanTile + threadIdx.x * kScanItems + i) + 1u - tp;
-            s_auc += (unsigned long long)(fp - fp_prev) * (unsigned long long)(tp_prev + tp);
-            if (tp != tp_prev) s_ap += (double)(tp - tp_prev) * ((double)tp / (double)(tp + fp));
-            if (kWriteCurve) {
-                const long long o = (long long)seg * curve_stride + bi;
-                fps_out[o] = (float)fp;
-                tps_out[o] = (float)tp;
-                thr_out[o] = score_of_key(d.key[i]);
-            }
-            tp_prev = tp;
-            fp_prev = fp;
-            bi++;
-        }
-    }
-    // block reductions in a fixed order (deterministic fp64 result)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s_auc += __shfl_down_sync(kFull, s_auc, o);
-        s_ap += __shfl_down_sync(kFull, s_ap, o);
-    }
-    __syncthreads();
-    if (lane == 0) usum[warp] = s_auc, dsum[warp] = s_ap;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long a = 0;
-        double p = 0.0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) a += usum[w], p += dsum[w];
-        if (a) atomicAdd(auroc_acc + seg, a);  // integer: order-independent, exact
-        ap_partial[(size_t)seg * tiles + tile] = p;
-    }
-}
-
-// phase 4: one warp per segment folds the per-tile AP partials in tile order and emits the scalars.
+// finalize: one warp per segment folds the per-tile AP partials in tile order and emits the scalars.
 // out[seg] = {auroc, ap, n_pos, n_neg, n_thresholds} as fp32 (counts < 2^24 are exact; larger ones only inform weights)
 __global__ void __launch_bounds__(256) scan_finalize_kernel(const unsigned long long* __restrict__ auroc_acc,
                                                             const double* __restrict__ ap_partial,
@@ -844,6 +602,303 @@ __global__ void __launch_bounds__(256) scan_finalize_wide_kernel(const unsigned 
         out_counts[3 * seg + 0] = (long long)seg_totals[2 * seg + 0];
         out_counts[3 * seg + 1] = (long long)n - (long long)seg_totals[2 * seg + 0];
         out_counts[3 * seg + 2] = (long long)seg_totals[2 * seg + 1];
+    }
+}
+
+// =====================================================================================================
+// The scan as ONE chained kernel: tiles of 4096 take a ticket, compute their aggregates, publish them, resolve their carries
+// by decoupled look-back over the earlier tiles of the segment and go straight on to the apply phase.  (Round 1 ran it as
+// reduce / one-CTA carry / apply kernels: the sorted records were read twice and the carry kernel alone took 27 of the scan's
+// 92 us at 10^7 samples, profiles/r02_curve_launches.txt.)
+//
+// Tile state = two 64-bit words, each [flag:2 | hi:31 | lo:31]:
+//     sums  [npos | nbound]                           aggregate: of the tile          prefix: inclusive, from the segment start
+//     last  [pos1 | tp]   last group end so far       aggregate: tile-local pos1 =    prefix: segment-global pos1 and TP;
+//                          (pos1 = index + 1, 0 =      index+1 in the tile, TP local           pos1 = 0: no group end yet
+//                          none; FP = pos1 - TP)
+// A reader accepts a tile when both words carry the SAME non-zero flag: each word is written at most twice (aggregate, then
+// prefix), so equal flags mean the same generation.  Warp 0 looks back 32 tiles per round trip.  TP at the last group end before
+// the tile comes either from a prefix word (global already) or from the nearest aggregate that has one: then
+// TP = (positives before THAT tile) + its local TP = (positives before this tile) - (positives from that tile up to here) + ...
+// The spin is bounded (MB200_FLAG_SPIN_TIMEOUT instead of a hang).
+// =====================================================================================================
+constexpr int kChainThreads = 256;
+constexpr int kChainItems = 16;
+constexpr int kChainTile = kChainThreads * kChainItems;  // 4096
+constexpr unsigned long long kChainAgg = 1ull << 62;
+constexpr unsigned long long kChainPrefix = 2ull << 62;
+constexpr unsigned long long kChainField = 0x7fffffffull;
+
+__device__ __forceinline__ unsigned long long chain_word(unsigned long long flag, unsigned hi, unsigned lo) {
+    return flag | ((unsigned long long)hi << 31) | (unsigned long long)lo;
+}
+
+__device__ __forceinline__ unsigned long long block_excl_sum64(unsigned long long v, unsigned long long* sm8,
+                                                               unsigned long long& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();
+    if (lane == 31) sm8[warp] = incl;
+    __syncthreads();
+    unsigned long long woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kChainThreads / 32; ++w) {
+        const unsigned long long x = sm8[w];
+        if (w < warp) woff += x;
+        tot += x;
+    }
+    total = tot;
+    return woff + incl - v;
+}
+__device__ __forceinline__ unsigned long long block_excl_max64(unsigned long long v, unsigned long long* sm8,
+                                                               unsigned long long& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl = max(incl, t);
+    }
+    __syncthreads();
+    if (lane == 31) sm8[warp] = incl;
+    __syncthreads();
+    unsigned long long wmax = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kChainThreads / 32; ++w) {
+        const unsigned long long x = sm8[w];
+        if (w < warp) wmax = max(wmax, x);
+        tot = max(tot, x);
+    }
+    total = tot;
+    unsigned long long excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 0;
+    return max(wmax, excl);
+}
+
+// tp / (tp + fp) in fp64 without the ~40-instruction IEEE division (it was a third of the scan at one group end per element):
+// hardware reciprocal seed (2^-23) + two Newton steps -> relative error < 2^-50, the same instruction sequence everywhere
+// (bitwise reproducible); the results leave the kernel as float32.
+__device__ __forceinline__ double precision_at(unsigned tp, unsigned total) {
+    const double x = (double)total;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return (double)tp * r;
+}
+
+template <bool kWriteCurve, typename KeyT>
+__global__ void __launch_bounds__(kChainThreads) scan_chained_kernel(
+    const KeyT* __restrict__ keys, const unsigned char* __restrict__ labels, int n_stride, const int* __restrict__ seg_ignored,
+    int tiles, unsigned long long* status /*[segments*tiles][2], zeroed*/, unsigned* ticket /*zeroed*/,
+    unsigned long long* __restrict__ auroc_acc /*[seg], zeroed*/, double* __restrict__ ap_partial /*[seg][tiles]*/,
+    unsigned* __restrict__ seg_totals /*[seg][2]: P, U*/, float* __restrict__ fps_out, float* __restrict__ tps_out,
+    typename ThrOf<KeyT>::type* __restrict__ thr_out, long long curve_stride, unsigned* __restrict__ err) {
+    __shared__ unsigned long long sm8[kChainThreads / 32];
+    __shared__ double dsum[kChainThreads / 32];
+    __shared__ unsigned long long usum[kChainThreads / 32];
+    __shared__ unsigned s_ticket;
+    __shared__ unsigned s_carry[4];  // positives before the tile, group ends before it, TP / FP at the last group end before it
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned tg = s_ticket;
+    const int seg = (int)(tg / (unsigned)tiles), tile = (int)(tg % (unsigned)tiles);
+    const int n = seg_ignored ? n_stride - seg_ignored[seg] : n_stride;  // ignored entries sit behind the valid ones
+    const KeyT* __restrict__ k = keys + (size_t)seg * n_stride;
+    const unsigned char* __restrict__ l = labels + (size_t)seg * n_stride;
+
+    // ---- load: thread t owns elements [16 t, 16 t + 16) of the tile ----
+    const int base = tile * kChainTile + threadIdx.x * kChainItems;
+    const int count = max(0, min(kChainItems, n - base));
+    KeyT key[kChainItems];
+    unsigned labw[4];
+    const bool aligned = ((reinterpret_cast<uintptr_t>(k + base) & 15) == 0) && ((reinterpret_cast<uintptr_t>(l + base) & 15) == 0);
+    if (count == kChainItems && aligned) {
+        if constexpr (sizeof(KeyT) == 4) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint4 a = *reinterpret_cast<const uint4*>(k + base + 4 * q);
+                key[4 * q] = a.x, key[4 * q + 1] = a.y, key[4 * q + 2] = a.z, key[4 * q + 3] = a.w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(k + base + 2 * q);
+                key[2 * q] = a.x, key[2 * q + 1] = a.y;
+            }
+        }
+        const uint4 lb = *reinterpret_cast<const uint4*>(l + base);
+        labw[0] = lb.x, labw[1] = lb.y, labw[2] = lb.z, labw[3] = lb.w;
+    } else {
+        labw[0] = labw[1] = labw[2] = labw[3] = 0u;
+#pragma unroll
+        for (int i = 0; i < kChainItems; ++i) {
+            key[i] = i < count ? k[base + i] : (KeyT)0;
+            if (i < count) labw[i >> 2] |= (unsigned)l[base + i] << (8 * (i & 3));
+        }
+    }
+    const KeyT key_next = (count == kChainItems && base + kChainItems < n) ? k[base + kChainItems] : (KeyT)0;
+
+    // ---- thread-local: positives, group ends, the thread's last group end ----
+    unsigned npos = 0, nb = 0, ends = 0, cum_at_last = 0;
+    int last_i = -1;
+#pragma unroll
+    for (int i = 0; i < kChainItems; ++i) {
+        npos += (labw[i >> 2] >> (8 * (i & 3))) & 0xffu;
+        bool e = false;
+        if (i < count) {
+            const KeyT nk = (i + 1 < kChainItems) ? key[i + 1] : key_next;
+            e = (base + i == n - 1) || key[i] != nk;
+        }
+        if (e) {
+            ends |= 1u << i;
+            nb++;
+            last_i = i;
+            cum_at_last = npos;
+        }
+    }
+    unsigned long long tile_sums, tile_last;
+    const unsigned long long excl = block_excl_sum64(((unsigned long long)npos << 32) | nb, sm8, tile_sums);
+    const unsigned pos_excl_l = (unsigned)(excl >> 32), nb_excl_l = (unsigned)excl;
+    const unsigned long long my_last =
+        last_i >= 0 ? (((unsigned long long)(threadIdx.x * kChainItems + last_i + 1) << 32) | (pos_excl_l + cum_at_last)) : 0ull;
+    const unsigned long long prev_last_l = block_excl_max64(my_last, sm8, tile_last);  // ends with a __syncthreads-free read of sm8
+
+    // ---- publish, look back, publish the prefix (warp 0) ----
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const unsigned t_npos = (unsigned)(tile_sums >> 32), t_nb = (unsigned)tile_sums;
+        const unsigned t_pos1 = (unsigned)(tile_last >> 32), t_tp = (unsigned)tile_last;
+        volatile unsigned long long* st = status + 2 * (size_t)tg;
+        unsigned sp = 0, sb = 0, f_tp = 0, f_pos1 = 0;
+        if (tile > 0) {
+            if (lane == 0) {
+                st[0] = chain_word(kChainAgg, t_npos, t_nb);
+                st[1] = chain_word(kChainAgg, t_pos1, t_tp);
+            }
+            bool found = false, pending = false;
+            unsigned p_tp_l = 0, p_pos1_g = 0, p_acc = 0;
+            const long long seg_first = (long long)tg - tile;
+            long long j = (long long)tg - 1;
+            unsigned spins = 0;
+            while (true) {
+                const long long jj = j - lane;
+                unsigned long long a = kChainPrefix, b = kChainPrefix;  // in front of the segment: an empty prefix
+                if (jj >= seg_first) {
+                    a = *(volatile unsigned long long*)(status + 2 * (size_t)jj);
+                    b = *(volatile unsigned long long*)(status + 2 * (size_t)jj + 1);
+                }
+                const unsigned fa = (unsigned)(a >> 62), fb = (unsigned)(b >> 62);
+                const unsigned ready = __ballot_sync(kFull, fa != 0u && fa == fb);
+                const int first_not = __ffs(~ready) - 1;  // -1: all 32 ready
+                const unsigned usable = first_not < 0 ? kFull : ((1u << first_not) - 1u);
+                const unsigned pm = __ballot_sync(kFull, fa == 2u) & ready & usable;
+                const int stop = __ffs(pm) - 1;  // nearest tile that holds a prefix (-1: none in the window)
+                const unsigned consumed = stop >= 0 ? (stop == 31 ? kFull : ((1u << (stop + 1)) - 1u)) : usable;
+                const bool in_c = (consumed >> lane) & 1u;
+                const unsigned my_np = in_c ? (unsigned)((a >> 31) & kChainField) : 0u;
+                const unsigned my_nb = in_c ? (unsigned)(a & kChainField) : 0u;
+                unsigned incl_np = my_np;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned t = __shfl_up_sync(kFull, incl_np, o);
+                    if (lane >= o) incl_np += t;
+                }
+                const unsigned tot_np = __shfl_sync(kFull, incl_np, 31);
+                const unsigned tot_nb = __reduce_add_sync(kFull, my_nb);
+                if (!found && !pending) {
+                    const unsigned pos1 = (unsigned)((b >> 31) & kChainField), tpw = (unsigned)(b & kChainField);
+                    const unsigned hb = __ballot_sync(kFull, in_c && pos1 != 0u);
+                    if (hb) {
+                        const int ls = __ffs(hb) - 1;  // the nearest tile with a group end
+                        const bool is_prefix = __shfl_sync(kFull, fa, ls) == 2u;
+                        const unsigned tp_s = __shfl_sync(kFull, tpw, ls), pos_s = __shfl_sync(kFull, pos1, ls);
+                        const unsigned acc_s = __shfl_sync(kFull, incl_np, ls);
+                        if (is_prefix) {
+                            found = true, f_tp = tp_s, f_pos1 = pos_s;
+                        } else {
+                            pending = true, p_tp_l = tp_s;
+                            p_pos1_g = (unsigned)(j - ls - seg_first) * (unsigned)kChainTile + pos_s;
+                            p_acc = sp + acc_s;  // positives from that tile (inclusive) up to this one (exclusive)
+                        }
+                    }
+                }
+                sp += tot_np;
+                sb += tot_nb;
+                if (stop >= 0) break;
+                const int adv = __popc(consumed);
+                j -= adv;
+                if (adv < 32) {  // ran into a tile that has not published yet
+                    if (++spins > (1u << 22)) {
+                        if (lane == 0 && err) atomicOr(err, MB200_FLAG_SPIN_TIMEOUT);
+                        break;
+                    }
+                    __nanosleep(20);
+                }
+            }
+            if (pending) f_tp = sp - p_acc + p_tp_l, f_pos1 = p_pos1_g;
+        }
+        if (lane == 0) {
+            const unsigned g_pos1 = t_pos1 ? (unsigned)tile * (unsigned)kChainTile + t_pos1 : f_pos1;
+            const unsigned g_tp = t_pos1 ? sp + t_tp : f_tp;
+            st[0] = chain_word(kChainPrefix, sp + t_npos, sb + t_nb);
+            st[1] = chain_word(kChainPrefix, g_pos1, g_tp);
+            s_carry[0] = sp, s_carry[1] = sb, s_carry[2] = f_tp, s_carry[3] = f_pos1 - f_tp;
+            if (tile == tiles - 1) seg_totals[2 * seg + 0] = sp + t_npos, seg_totals[2 * seg + 1] = sb + t_nb;
+        }
+    }
+    __syncthreads();
+
+    // ---- apply ----
+    const unsigned c_pos = s_carry[0], c_nb = s_carry[1];
+    unsigned tp_prev = s_carry[2], fp_prev = s_carry[3];
+    if (prev_last_l) {  // a group end earlier in this tile
+        tp_prev = c_pos + (unsigned)prev_last_l;
+        fp_prev = (unsigned)tile * (unsigned)kChainTile + (unsigned)(prev_last_l >> 32) - tp_prev;
+    }
+    unsigned long long s_auc = 0;
+    double s_ap = 0.0;
+    unsigned run = c_pos + pos_excl_l, bi = c_nb + nb_excl_l;
+#pragma unroll
+    for (int i = 0; i < kChainItems; ++i) {
+        run += (labw[i >> 2] >> (8 * (i & 3))) & 0xffu;
+        if ((ends >> i) & 1u) {
+            const unsigned tp = run;
+            const unsigned fp = (unsigned)(base + i) + 1u - tp;
+            s_auc += (unsigned long long)(fp - fp_prev) * (unsigned long long)(tp_prev + tp);
+            if (tp != tp_prev) s_ap += (double)(tp - tp_prev) * precision_at(tp, tp + fp);
+            if (kWriteCurve) {
+                const long long o = (long long)seg * curve_stride + bi;
+                fps_out[o] = (float)fp;
+                tps_out[o] = (float)tp;
+                thr_out[o] = score_of_key(key[i]);
+            }
+            tp_prev = tp;
+            fp_prev = fp;
+            bi++;
+        }
+    }
+    // block reductions in a fixed order (deterministic fp64 result)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s_auc += __shfl_down_sync(kFull, s_auc, o);
+        s_ap += __shfl_down_sync(kFull, s_ap, o);
+    }
+    if (lane == 0) usum[warp] = s_auc, dsum[warp] = s_ap;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long a = 0;
+        double p = 0.0;
+#pragma unroll
+        for (int w = 0; w < kChainThreads / 32; ++w) a += usum[w], p += dsum[w];
+        if (a) atomicAdd(auroc_acc + seg, a);  // integer: order-independent, exact
+        ap_partial[(size_t)seg * tiles + tile] = p;
     }
 }
 
@@ -920,11 +975,6 @@ __global__ void __launch_bounds__(kWThreads) weighted_curve_kernel(const KeyT* _
         __syncthreads();
     }
     if (threadIdx.x == 0) *count_out = (long long)carry_b;
-}
-
-__global__ void zero_u64_kernel(unsigned long long* p, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = 0ull;
 }
 
 static inline int blocks_for(long long n, int per_block, int cap) {
@@ -1007,14 +1057,14 @@ extern "C" int mb200_curve_softmax_if_logits(const void* preds, int dtype, int64
 
 static int64_t curve_workspace_bytes(int64_t segments, int64_t n, int key_bytes) {
     if (segments < 1 || n < 0) return -1;
-    const int64_t scan_tiles = (n + kScanTile - 1) / kScanTile;
+    const int64_t scan_tiles = (n + kChainTile - 1) / kChainTile;
     int64_t b = 0;
     b += segments * n * key_bytes + 256;            // keys ping
     b += segments * n * key_bytes + 256;            // keys pong
     b += segments * n * 1 + 16;                     // labels ping
     b += segments * n * 1 + 16;                     // labels pong
     b += (int64_t)radix_sort_scratch_words(n, segments, key_bytes) * 4 + 256;  // digit histograms, look-back status, tickets
-    b += segments * (scan_tiles + 1) * (int64_t)sizeof(TileInfo);
+    b += segments * (scan_tiles + 1) * 16 + 256;    // chained-scan tile states + ticket
     b += segments * 2 * 4;                          // seg_totals
     b += segments * 4 + 256;                        // seg_ignored (multilabel + ignore_index)
     b += segments * 8;                              // auroc_acc
@@ -1033,7 +1083,7 @@ struct CurveWs {
     unsigned char *lab_a, *lab_b;
     unsigned *sort_scratch, *seg_totals;
     int* seg_ignored;
-    TileInfo* info;
+    unsigned long long* chain;  // chained-scan tile states [segments * tiles][2], then the ticket
     unsigned long long* auroc_acc;
     double* ap_partial;
 };
@@ -1044,7 +1094,7 @@ inline unsigned char* bump(unsigned char*& p, int64_t bytes) {
 }
 template <typename KeyT>
 CurveWs<KeyT> carve(void* workspace, int64_t segments, int64_t n) {
-    const int64_t scan_tiles = (n + kScanTile - 1) / kScanTile;
+    const int64_t scan_tiles = (n + kChainTile - 1) / kChainTile;
     unsigned char* p = reinterpret_cast<unsigned char*>(workspace);
     CurveWs<KeyT> w;
     w.keys_a = (KeyT*)bump(p, segments * n * (int64_t)sizeof(KeyT));
@@ -1052,7 +1102,7 @@ CurveWs<KeyT> carve(void* workspace, int64_t segments, int64_t n) {
     w.lab_a = bump(p, segments * n + 16);
     w.lab_b = bump(p, segments * n + 16);
     w.sort_scratch = (unsigned*)bump(p, (int64_t)radix_sort_scratch_words(n, segments, (int)sizeof(KeyT)) * 4);
-    w.info = (TileInfo*)bump(p, segments * (scan_tiles + 1) * (int64_t)sizeof(TileInfo));
+    w.chain = (unsigned long long*)bump(p, segments * (scan_tiles + 1) * 16 + 256);
     w.seg_totals = (unsigned*)bump(p, segments * 2 * 4);
     w.seg_ignored = (int*)bump(p, segments * 4);
     w.auroc_acc = (unsigned long long*)bump(p, segments * 8);
@@ -1064,60 +1114,96 @@ CurveWs<KeyT> carve(void* workspace, int64_t segments, int64_t n) {
 template <typename KeyT>
 int sort_and_scan(KeyT* keys_a, unsigned char* lab_a, const CurveWs<KeyT>& w, int ni, int64_t segments, int64_t n,
                   const int* seg_ignored, float* out_auroc, float* out_ap, int64_t* out_counts, float* fps_out, float* tps_out,
-                  void* thr_out_v, uint32_t* err_flag, cudaStream_t st) {
+                  void* thr_out_v, uint32_t* err_flag, cudaStream_t st, bool bit0 = false, bool hist_done = false) {
     using ThrT = typename ThrOf<KeyT>::type;
     ThrT* thr_out = reinterpret_cast<ThrT*>(thr_out_v);
-    const int scan_tiles = (ni + kScanTile - 1) / kScanTile;
     // ---- one-sweep radix passes, one per key byte (ping-pong; an even number of passes leaves the result in *_a) ----
+    // bit0: the keys carry the label in bit 0 — 4-byte records until the last pass, which splits them into (key, label)
     {
-        const int where = radix_sort_passes<KeyT, unsigned char>(keys_a, lab_a, w.keys_b, w.lab_b, ni, (int)segments,
-                                                                 (int)sizeof(KeyT), w.sort_scratch, err_flag, st, &count_launch);
+        const int where = bit0 ? radix_sort_passes_bit0<KeyT, unsigned char>(keys_a, lab_a, w.keys_b, w.lab_b, ni, (int)segments,
+                                                                             (int)sizeof(KeyT), w.sort_scratch, err_flag, st, &count_launch,
+                                                                             hist_done)
+                               : radix_sort_passes<KeyT, unsigned char>(keys_a, lab_a, w.keys_b, w.lab_b, ni, (int)segments,
+                                                                        (int)sizeof(KeyT), w.sort_scratch, err_flag, st, &count_launch);
         if (where < 0) return check_cuda(cudaGetLastError(), "radix sort");
     }
     KeyT* kin = keys_a;
     unsigned char* lin = lab_a;
 
-    // ---- scan ----
-    const dim3 sgrid((unsigned)scan_tiles, (unsigned)segments);
-    zero_u64_kernel<<<(int)((segments + 255) / 256), 256, 0, st>>>(w.auroc_acc, (int)segments);
-    scan_reduce_kernel<KeyT><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, seg_ignored, scan_tiles, w.info);
-    scan_carry_kernel<<<(unsigned)segments, kCarryThreads, 0, st>>>(w.info, scan_tiles, ni, w.seg_totals);
+    // ---- scan: one chained kernel (tile states + ticket live in the tile-info region), then the finalize ----
+    const int chain_tiles = (ni + kChainTile - 1) / kChainTile;
+    unsigned long long* status = w.chain;
+    const size_t status_bytes = (size_t)segments * chain_tiles * 16;
+    unsigned* ticket = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(w.chain) + status_bytes);
+    if (cudaMemsetAsync(w.chain, 0, status_bytes + 16, st) != cudaSuccess ||
+        cudaMemsetAsync(w.auroc_acc, 0, (size_t)segments * 8, st) != cudaSuccess)
+        return check_cuda(cudaGetLastError(), "curve scan memset");
+    const unsigned sgrid = (unsigned)(segments * chain_tiles);
     if (fps_out)
-        scan_apply_kernel<true, KeyT><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, seg_ignored, scan_tiles, w.info, w.auroc_acc,
-                                                                      w.ap_partial, fps_out, tps_out, thr_out, n);
+        scan_chained_kernel<true, KeyT><<<sgrid, kChainThreads, 0, st>>>(kin, lin, ni, seg_ignored, chain_tiles, status, ticket,
+                                                                         w.auroc_acc, w.ap_partial, w.seg_totals, fps_out, tps_out,
+                                                                         thr_out, n, err_flag);
     else
-        scan_apply_kernel<false, KeyT><<<sgrid, kScanThreads, 0, st>>>(kin, lin, ni, seg_ignored, scan_tiles, w.info, w.auroc_acc,
-                                                                       w.ap_partial, nullptr, nullptr, nullptr, n);
-    if (scan_tiles > 256)
-        scan_finalize_wide_kernel<<<(unsigned)segments, 256, 0, st>>>(w.auroc_acc, w.ap_partial, w.seg_totals, scan_tiles, ni,
+        scan_chained_kernel<false, KeyT><<<sgrid, kChainThreads, 0, st>>>(kin, lin, ni, seg_ignored, chain_tiles, status, ticket,
+                                                                          w.auroc_acc, w.ap_partial, w.seg_totals, nullptr, nullptr,
+                                                                          nullptr, n, err_flag);
+    if (chain_tiles > 256)
+        scan_finalize_wide_kernel<<<(unsigned)segments, 256, 0, st>>>(w.auroc_acc, w.ap_partial, w.seg_totals, chain_tiles, ni,
                                                                       seg_ignored, out_auroc, out_ap,
                                                                       reinterpret_cast<long long*>(out_counts));
     else
-        scan_finalize_kernel<<<(int)((segments + 7) / 8), 256, 0, st>>>(w.auroc_acc, w.ap_partial, w.seg_totals, scan_tiles,
+        scan_finalize_kernel<<<(int)((segments + 7) / 8), 256, 0, st>>>(w.auroc_acc, w.ap_partial, w.seg_totals, chain_tiles,
                                                                         ni, seg_ignored, (int)segments, out_auroc, out_ap, reinterpret_cast<long long*>(out_counts));
-    for (int i = 0; i < 5; ++i) count_launch();
+    for (int i = 0; i < 2; ++i) count_launch();
     return check_cuda(cudaGetLastError(), "curve evaluate launch");
 }
 
 template <typename T>
 int evaluate_typed(const void* preds, const void* target, int target_dtype, int64_t n, int64_t segments, int64_t pos_label,
                    void* workspace, float* out_auroc, float* out_ap, int64_t* out_counts, float* fps_out, float* tps_out,
-                   void* thr_out, uint32_t* err_flag, cudaStream_t st) {
+                   void* thr_out, uint32_t* err_flag, cudaStream_t st, bool unit_range = false) {
     using KeyT = typename KeyOf<T>::type;
     CurveWs<KeyT> w = carve<KeyT>(workspace, segments, n);
     const int ni = (int)n;
+    constexpr bool kCanBit0 = sizeof(KeyT) == 4;
+    const bool bit0 = kCanBit0 && unit_range;
+    bool hist_done = false;  // the pack kernel already counted the sort's digit histograms
     if (segments == 1) {
         const int grid = blocks_for(n, 256 * 4, sm_count() * 8);
-        pack_binary_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, n, pos_label,
-                                                    w.keys_a, w.lab_a);
+        if constexpr (kCanBit0) {
+            if (bit0) {
+                if (radix_sort_zero_scratch(w.sort_scratch, ni, 1, 4, st)) return check_cuda(cudaGetLastError(), "sort scratch");
+                if (target_dtype == MB200_I64)
+                    pack_binary_kernel<T, true, true><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype,
+                                                                            n, pos_label, w.keys_a, w.lab_a, err_flag, w.sort_scratch);
+                else
+                    pack_binary_kernel<T, true, false><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype,
+                                                                             n, pos_label, w.keys_a, w.lab_a, err_flag, w.sort_scratch);
+                hist_done = true;
+            }
+        }
+        if (!bit0) {
+            if (target_dtype == MB200_I64)
+                pack_binary_kernel<T, false, true><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, n,
+                                                                         pos_label, w.keys_a, w.lab_a);
+            else
+                pack_binary_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, n, pos_label,
+                                                            w.keys_a, w.lab_a);
+        }
     } else {
         const dim3 grid((unsigned)((ni + 31) / 32), (unsigned)((segments + 31) / 32));
-        pack_ovr_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, ni, (int)segments,
-                                                 w.keys_a, w.lab_a);
+        if constexpr (kCanBit0) {
+            if (bit0)
+                pack_ovr_kernel<T, true><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, ni,
+                                                               (int)segments, w.keys_a, w.lab_a, err_flag);
+        }
+        if (!bit0)
+            pack_ovr_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(preds), target, target_dtype, ni, (int)segments,
+                                                     w.keys_a, w.lab_a);
     }
     count_launch();
     return sort_and_scan<KeyT>(w.keys_a, w.lab_a, w, ni, segments, n, nullptr, out_auroc, out_ap, out_counts, fps_out, tps_out,
-                               thr_out, err_flag, st);
+                               thr_out, err_flag, st, bit0, hist_done);
 }
 
 template <typename T>
@@ -1143,10 +1229,10 @@ int evaluate_multilabel_typed(const void* preds, const void* target, int target_
 //   target : [n] integer labels; positive for segment c is (target == c) (binary: target == pos_label).
 //   out_auroc / out_ap : float32 [segments];  out_counts : int64 [segments][3] = {n_pos, n_neg, n_distinct_thresholds}
 //   curve outputs (optional, all three or none): float32 [segments][n] each, valid prefix = n_distinct_thresholds.
-extern "C" int mb200_curve_evaluate(const void* preds, int preds_dtype, const void* target, int target_dtype,
-                                    int64_t n, int64_t num_classes, int64_t pos_label, void* workspace,
-                                    int64_t workspace_bytes, float* out_auroc, float* out_ap, int64_t* out_counts,
-                                    float* fps_out, float* tps_out, void* thr_out, uint32_t* err_flag, void* stream) {
+static int curve_evaluate_impl(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                               int64_t n, int64_t num_classes, int64_t pos_label, void* workspace,
+                               int64_t workspace_bytes, float* out_auroc, float* out_ap, int64_t* out_counts,
+                               float* fps_out, float* tps_out, void* thr_out, uint32_t* err_flag, void* stream, bool unit_range) {
     MB200_REQUIRE(n >= 1, "curve evaluation needs at least one sample (got %lld)", (long long)n);
     MB200_REQUIRE(n < (1ll << 30), "more than 2^30-1 samples per curve are not supported");
     MB200_REQUIRE(num_classes >= 1, "bad num_classes");
@@ -1159,7 +1245,7 @@ extern "C" int mb200_curve_evaluate(const void* preds, int preds_dtype, const vo
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define MB200_EVAL(T)                                                                                                  \
     return evaluate_typed<T>(preds, target, target_dtype, n, segments, pos_label, workspace, out_auroc, out_ap, out_counts, \
-                             fps_out, tps_out, thr_out, err_flag, st)
+                             fps_out, tps_out, thr_out, err_flag, st, unit_range)
     switch (preds_dtype) {
         case MB200_F32: MB200_EVAL(float);
         case MB200_F16: MB200_EVAL(__half);
@@ -1168,6 +1254,25 @@ extern "C" int mb200_curve_evaluate(const void* preds, int preds_dtype, const vo
         default: set_error("scores must be f32/f16/bf16/f64 (dtype tag %d)", preds_dtype); return MB200_ERR_UNSUPPORTED;
     }
 #undef MB200_EVAL
+}
+
+extern "C" int mb200_curve_evaluate(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                    int64_t n, int64_t num_classes, int64_t pos_label, void* workspace,
+                                    int64_t workspace_bytes, float* out_auroc, float* out_ap, int64_t* out_counts,
+                                    float* fps_out, float* tps_out, void* thr_out, uint32_t* err_flag, void* stream) {
+    return curve_evaluate_impl(preds, preds_dtype, target, target_dtype, n, num_classes, pos_label, workspace, workspace_bytes,
+                               out_auroc, out_ap, out_counts, fps_out, tps_out, thr_out, err_flag, stream, false);
+}
+
+// The same evaluation for scores PROMISED to be non-negative or NaN — in particular what normalize_logits_if_needed returns,
+// i.e. every state of the curve metric classes.  Their sort keys need 31 bits, so the label rides in bit 0 and the radix
+// passes move 4-byte keys only.  A negative score (-0 is fine) raises MB200_FLAG_PREDS_RANGE in err_flag (results invalid).
+extern "C" int mb200_curve_evaluate_nonneg(const void* preds, int preds_dtype, const void* target, int target_dtype,
+                                         int64_t n, int64_t num_classes, int64_t pos_label, void* workspace,
+                                         int64_t workspace_bytes, float* out_auroc, float* out_ap, int64_t* out_counts,
+                                         float* fps_out, float* tps_out, void* thr_out, uint32_t* err_flag, void* stream) {
+    return curve_evaluate_impl(preds, preds_dtype, target, target_dtype, n, num_classes, pos_label, workspace, workspace_bytes,
+                               out_auroc, out_ap, out_counts, fps_out, tps_out, thr_out, err_flag, stream, true);
 }
 
 // Exact-mode evaluation of `num_labels` independent binary curves (multilabel task).

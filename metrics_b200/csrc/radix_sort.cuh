@@ -67,10 +67,12 @@ static __global__ void __launch_bounds__(256) radix_digit_scan_kernel(unsigned* 
 }
 
 // ---- one radix pass ------------------------------------------------------------------------------------------------------
-template <typename KeyT, typename ValT>
+// kMode: 0 = (key, value) pairs; 1 = keys only; 2 = keys only in, and the pass SPLITS every key on the way out into
+// (key >> 1, key & 1) — the last pass of a sort whose keys carry a one-bit payload in bit 0 (curve.cu: the label).
+template <typename KeyT, typename ValT, int kMode = 0>
 struct SortSmem {
     KeyT keys[kSortTile];
-    ValT vals[kSortTile];
+    ValT vals[kMode == 0 ? kSortTile : 1];
     unsigned warp_hist[kSortWarps][256];
     unsigned digit_base[256];  // global position of the tile's first key of each digit
     unsigned tile_off[256];    // position of the digit's run inside the tile
@@ -78,14 +80,14 @@ struct SortSmem {
     unsigned tile_index;
 };
 
-template <typename KeyT, typename ValT>
+template <typename KeyT, typename ValT, int kMode = 0>
 __global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 2 : 1) radix_onesweep_kernel(
     const KeyT* __restrict__ keys_in, const ValT* __restrict__ vals_in, KeyT* __restrict__ keys_out,
     ValT* __restrict__ vals_out, int n, int tiles_per_seg, int shift, int pass, int key_bytes,
     const unsigned* __restrict__ digit_offsets /*[seg][pass][256] exclusive*/, unsigned* __restrict__ status /*[tiles][256]*/,
     unsigned* __restrict__ ticket, unsigned* __restrict__ err) {
     extern __shared__ __align__(16) unsigned char sort_smem_raw[];
-    SortSmem<KeyT, ValT>& sm = *reinterpret_cast<SortSmem<KeyT, ValT>*>(sort_smem_raw);
+    SortSmem<KeyT, ValT, kMode>& sm = *reinterpret_cast<SortSmem<KeyT, ValT, kMode>*>(sort_smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) sm.tile_index = atomicAdd(ticket, 1u);
     for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&sm.warp_hist[0][0])[i] = 0;
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 2 : 1) radix
         const int idx = wbase + i * 32 + lane;
         const bool valid = idx < n;
         key[i] = valid ? kin[idx] : (KeyT)0;
-        val[i] = valid ? vin[idx] : (ValT)0;
+        if (kMode == 0) val[i] = valid ? vin[idx] : (ValT)0;
     }
     const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 2 : 1) radix
             const unsigned digit = (unsigned)(key[i] >> shift) & 255u;
             const unsigned pos = sm.tile_off[digit] + sm.warp_hist[warp][digit] + rank[i];
             sm.keys[pos] = key[i];
-            sm.vals[pos] = val[i];
+            if (kMode == 0) sm.vals[pos] = val[i];
         }
     }
     __syncthreads();
@@ -234,8 +236,13 @@ __global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 2 : 1) radix
         const KeyT k = sm.keys[i];
         const unsigned digit = (unsigned)(k >> shift) & 255u;
         const unsigned dst = sm.digit_base[digit] + (unsigned)i;
-        kout[dst] = k;
-        vout[dst] = sm.vals[i];
+        if (kMode == 2) {
+            kout[dst] = k >> 1;
+            vout[dst] = (ValT)(k & (KeyT)1);
+        } else {
+            kout[dst] = k;
+            if (kMode == 0) vout[dst] = sm.vals[i];
+        }
     }
 }
 
@@ -284,6 +291,55 @@ static inline int radix_sort_passes(KeyT* keys_a, ValT* vals_a, KeyT* keys_b, Va
         ValT* tv = vin;
         vin = vout;
         vout = tv;
+    }
+    return (key_bytes & 1);
+}
+
+// Keys with a one-bit payload in bit 0 (the curve label): every pass moves 4-byte keys only, the LAST pass writes the split
+// (key >> 1, key & 1) pair.  Pass p sorts by byte p of the composite key; the result lands in (keys_b, vals_b) for an odd
+// number of passes, (keys_a, vals_a) for an even one — returned like radix_sort_passes.
+// hist_done: the caller zeroed the scratch (radix_sort_zero_scratch) and its key-producing kernel already counted every digit
+// into the histograms at the front of it (layout [segment][pass][256]) — the separate histogram read of the keys is skipped.
+static inline int radix_sort_zero_scratch(unsigned* scratch, int n, int segments, int key_bytes, cudaStream_t st) {
+    const size_t words = radix_sort_scratch_words(n, segments, key_bytes);
+    return cudaMemsetAsync(scratch, 0, words * sizeof(unsigned), st) == cudaSuccess ? 0 : MB200_ERR_CUDA;
+}
+template <typename KeyT, typename ValT>
+static inline int radix_sort_passes_bit0(KeyT* keys_a, ValT* vals_a, KeyT* keys_b, ValT* vals_b, int n, int segments,
+                                         int key_bytes, unsigned* scratch, unsigned* err_flag, cudaStream_t st,
+                                         void (*on_launch)(), bool hist_done = false) {
+    const int tiles = (n + kSortTile - 1) / kSortTile;
+    unsigned* hist = scratch;
+    unsigned* status = hist + (size_t)segments * key_bytes * 256;
+    unsigned* tickets = status + (size_t)key_bytes * segments * tiles * 256;
+    if (!hist_done) {
+        if (radix_sort_zero_scratch(scratch, n, segments, key_bytes, st)) return MB200_ERR_CUDA;
+        int hgrid = (n + 256 * 16 - 1) / (256 * 16);
+        const int hcap = std::max(1, (sm_count() * 8) / std::max(1, segments));
+        if (hgrid > hcap) hgrid = hcap;
+        if (hgrid < 1) hgrid = 1;
+        radix_digit_hist_kernel<KeyT><<<dim3((unsigned)hgrid, (unsigned)segments), 256, (size_t)key_bytes * 256 * 4, st>>>(
+            keys_a, n, key_bytes, hist);
+        if (on_launch) on_launch();
+    }
+    radix_digit_scan_kernel<<<(unsigned)(segments * key_bytes), 256, 0, st>>>(hist);
+    if (on_launch) on_launch();
+    auto mid = radix_onesweep_kernel<KeyT, ValT, 1>;
+    auto last = radix_onesweep_kernel<KeyT, ValT, 2>;
+    const size_t smem = sizeof(SortSmem<KeyT, ValT, 1>);
+    if (ensure_dynamic_smem(mid, (int)smem) != cudaSuccess || ensure_dynamic_smem(last, (int)smem) != cudaSuccess)
+        return MB200_ERR_CUDA;
+    KeyT *kin = keys_a, *kout = keys_b;
+    ValT* vout = (key_bytes & 1) ? vals_b : vals_a;
+    for (int pass = 0; pass < key_bytes; ++pass) {
+        auto kern = pass == key_bytes - 1 ? last : mid;
+        kern<<<(unsigned)(segments * tiles), kSortThreads, smem, st>>>(
+            kin, nullptr, kout, vout, n, tiles, 8 * pass, pass, key_bytes, hist,
+            status + (size_t)pass * segments * tiles * 256, tickets + pass, err_flag);
+        if (on_launch) on_launch();
+        KeyT* tk = kin;
+        kin = kout;
+        kout = tk;
     }
     return (key_bytes & 1);
 }

@@ -171,7 +171,8 @@ def curve_weighted_clf_curve(preds: Tensor, target: Tensor, weights: Tensor, pos
     return torch.cumsum((1 - y) * w, 0)[idx], torch.cumsum(y * w, 0)[idx], s[idx]
 
 
-def curve_evaluate(preds: Tensor, target: Tensor, num_classes: int = 1, pos_label: int = 1, want_curve: bool = False):
+def curve_evaluate(preds: Tensor, target: Tensor, num_classes: int = 1, pos_label: int = 1, want_curve: bool = False,
+                   unit_range=None):
     n = target.numel()
     rows = []
     for c in range(num_classes):

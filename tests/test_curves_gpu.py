@@ -191,3 +191,110 @@ def test_cfg5_single_rank_modular_vs_golden(golden_curves):
         warnings.simplefilter("ignore")
         np.testing.assert_allclose(m_auc.compute().cpu().numpy(), golden_curves["mc/cfg5_rank0_2batches/auroc"], rtol=2e-6)
         np.testing.assert_allclose(m_ap.compute().cpu().numpy(), golden_curves["mc/cfg5_rank0_2batches/ap"], rtol=2e-6)
+
+
+def _same_evaluation(a, b):
+    assert torch.equal(a[2], b[2])
+    assert torch.equal(a[0].view(torch.int32), b[0].view(torch.int32)) and torch.equal(a[1].view(torch.int32), b[1].view(torch.int32))
+    for c in range(a[2].shape[0]):
+        u = int(a[2][c, 2])
+        for x, y in zip(a[3], b[3]):
+            assert torch.equal(x[c, :u].view(torch.int32), y[c, :u].view(torch.int32))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_label_in_key_path_is_bit_identical_to_the_pair_path(dtype):
+    """`mb200_curve_evaluate_nonneg` (non-negative or NaN scores: 31-bit keys, label in bit 0, 4-byte records) against the general
+    (key, label) pair sort: every output bit-identical — binary and one-vs-rest, ties, NaN, +-0, exact 0 and 1, ragged sizes."""
+    from metrics_b200 import _native
+
+    g = torch.Generator().manual_seed(7)
+    for n in (1, 2, 33, 2049, 12289, 300001):
+        p = (torch.rand(n, generator=g) * 64).floor() / 64 if n % 2 else torch.rand(n, generator=g)
+        p[::7] = 0.0
+        p[3::11] = 1.0
+        p[5::13] = float("nan")
+        p[6::17] = -0.0
+        t = torch.randint(0, 2, (n,), generator=g)
+        pd, td = p.to(DEV).to(dtype), t.to(DEV)
+        _same_evaluation(_native.curve_evaluate(pd, td, 1, 1, want_curve=True, unit_range=True),
+                         _native.curve_evaluate(pd, td, 1, 1, want_curve=True, unit_range=False))
+    for n, c in ((5, 3), (1000, 7), (4099, 33), (20000, 100)):
+        p = torch.softmax(torch.randn(n, c, generator=g) * 3, 1)
+        p[::5, 0] = float("nan")
+        p[1::9] = 0.0
+        t = torch.randint(0, c, (n,), generator=g)
+        pd, td = p.to(DEV).to(dtype), t.to(DEV)
+        _same_evaluation(_native.curve_evaluate(pd, td, c, want_curve=True, unit_range=True),
+                         _native.curve_evaluate(pd, td, c, want_curve=True, unit_range=False))
+
+
+def test_label_in_key_path_refuses_negative_scores():
+    """Default mode (unit_range=None) speculates, sees MB200_FLAG_PREDS_RANGE and re-evaluates on the general path; the raw
+    `_nonneg` entry raises the flag for a caller that broke its promise (and only then: 1.5 and +inf have 31-bit keys)."""
+    from metrics_b200 import _native
+
+    g = torch.Generator().manual_seed(8)
+    n = 5000
+    for bad in (-1e-30, -1e-42, 1.5, float("-inf"), float("inf")):
+        p = torch.rand(n, generator=g)
+        p[n // 2] = bad
+        t = torch.randint(0, 2, (n,), generator=g)
+        pd, td = p.to(DEV), t.to(DEV)
+        _same_evaluation(_native.curve_evaluate(pd, td, 1, 1, want_curve=True),
+                         _native.curve_evaluate(pd, td, 1, 1, want_curve=True, unit_range=False))
+        lib = _native.lib()
+        nbytes = int(lib.mb200_curve_workspace_bytes_for(1, n, _native.tag(pd)))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+        out = [torch.empty(1, dtype=torch.float32, device=DEV), torch.empty(1, dtype=torch.float32, device=DEV),
+               torch.empty((1, 3), dtype=torch.int64, device=DEV)]
+        flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+        with _native.on_device(pd.device):
+            rc = lib.mb200_curve_evaluate_nonneg(pd.data_ptr(), _native.tag(pd), td.data_ptr(), _native.tag(td), n, 1, 1, ws.data_ptr(),
+                                               nbytes, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), None, None, None,
+                                               flag.data_ptr(), _native.stream_handle(pd.device))
+        assert rc == 0 and bool(int(flag) & _native.FLAG_PREDS_RANGE) == (bad < 0)
+
+
+@pytest.mark.parametrize("unit", [True, False])
+def test_chained_scan_long_tie_runs(unit):
+    """Tie groups longer than a scan tile (4096): tiles without any group end must hand the previous TP/FP through — constant
+    scores, two-valued scores with runs of 10^4, a single odd score in the middle, and the same per class."""
+    from metrics_b200 import _native
+
+    g = torch.Generator().manual_seed(21)
+    cases = []
+    for n in (4096, 4097, 20000, 70001):
+        cases.append(torch.full((n,), 0.25))
+        p = torch.full((n,), 0.5)
+        p[n // 2:] = 0.125
+        cases.append(p)
+        p = torch.full((n,), 0.75)
+        p[n // 3] = 0.5
+        cases.append(p)
+        p = (torch.rand(n, generator=g) * 3).floor() / 4
+        cases.append(p)
+    for p in cases:
+        n = p.numel()
+        t = torch.randint(0, 2, (n,), generator=g)
+        auroc, ap, counts, (fps, tps, thr) = _native.curve_evaluate(p.to(DEV), t.to(DEV), 1, 1, want_curve=True, unit_range=unit)
+        rf, rt, rth = oc.binary_clf_curve(p.numpy(), t.numpy())
+        u = int(counts[0, 2])
+        assert u == rf.size
+        np.testing.assert_array_equal(fps[0, :u].cpu().numpy().astype(np.int64), rf)
+        np.testing.assert_array_equal(tps[0, :u].cpu().numpy().astype(np.int64), rt)
+        np.testing.assert_array_equal(thr[0, :u].cpu().numpy(), rth)
+        np.testing.assert_allclose(float(auroc[0]), oc.binary_auroc_exact(p.numpy(), t.numpy()), rtol=2e-7, atol=1e-7)
+        np.testing.assert_allclose(float(ap[0]), oc.binary_average_precision_exact(p.numpy(), t.numpy()), rtol=2e-7, atol=1e-7)
+    # per class: [n, 3] with a constant column, a two-valued column and a random one
+    n = 30011
+    p = torch.stack([torch.full((n,), 0.3), (torch.arange(n) < n // 2).float() * 0.5, torch.rand(n, generator=g)], 1)
+    t = torch.randint(0, 3, (n,), generator=g)
+    auroc, ap, counts, (fps, tps, thr) = _native.curve_evaluate(p.to(DEV), t.to(DEV), 3, want_curve=True, unit_range=unit)
+    for c in range(3):
+        rf, rt, rth = oc.binary_clf_curve(p[:, c].numpy(), (t == c).long().numpy())
+        u = int(counts[c, 2])
+        assert u == rf.size
+        np.testing.assert_array_equal(fps[c, :u].cpu().numpy().astype(np.int64), rf)
+        np.testing.assert_array_equal(tps[c, :u].cpu().numpy().astype(np.int64), rt)
+        np.testing.assert_allclose(float(auroc[c]), oc.binary_auroc_exact(p[:, c].numpy(), (t == c).long().numpy()), rtol=2e-7, atol=1e-7)

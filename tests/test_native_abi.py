@@ -145,7 +145,7 @@ def test_every_kernel_wrapper_calls_the_abi_as_declared(monkeypatch):
     _native.softmax_if_logits(scores)
     _native.softmax_if_logits(scores.double())
     _native.curve_evaluate(scores[:, 0], labels.clamp(max=1), 1, 1, want_curve=True)
-    _native.curve_evaluate(scores, labels, c)
+    _native.curve_evaluate(scores, labels, c, unit_range=False)
     keys = _native.curve_pack_keys(scores, c)
     _native.curve_evaluate_keys(keys, labels, 0)
     _native.curve_evaluate_multilabel(scores, torch.randint(2, (n, c)), c, ignore_index=-1, want_curve=True)
