@@ -106,6 +106,9 @@ SIGNATURES = {
     "mb200_coco_map_workspace_bytes": ("q", "qqq"),
     "mb200_coco_map_evaluate": ("i", "pppppppppqqqqqpqipqpqpqpqppppp"),
     "mb200_coco_map_match": ("i", "pppppppppqqqpqpqqppppppp"),
+    "mb200_coco_map_match_ex": ("i", "pppppppppqqqpqipqqppppippppppp"),
+    "mb200_mask_pack_bits": ("i", "pqqpqpp"),
+    "mb200_mask_pair_intersections": ("i", "pppppppppipqqpp"),
     "mb200_coco_map_accumulate": ("i", "pppppqpqqqqpqpqpqppppp"),
     "mb200_binary_stat_counts": ("i", "pipiqqqdiqipppp"),
     "mb200_binary_stat_counts_scratch": ("i", "pipiqqqdiqippqpp"),
@@ -501,10 +504,49 @@ def coco_map_evaluate(
     return precision, recall, scores, err
 
 
+def mask_pack_bits(masks: Tensor):
+    """``mb200_mask_pack_bits``: boolean / uint8 masks ``[n, H, W]`` -> ``(words int32 [n, ceil(H*W/32)], area int64 [n])``."""
+    dev = require_cuda(masks)
+    if masks.dtype not in (torch.bool, torch.uint8):
+        masks = masks != 0
+    masks = masks.contiguous()
+    n = int(masks.shape[0])
+    hw = int(masks[0].numel()) if n else 0
+    words = (hw + 31) // 32
+    out = torch.empty((n, words), dtype=torch.int32, device=dev)
+    area = torch.empty(n, dtype=torch.int64, device=dev)
+    if n:
+        with on_device(dev):
+            rc = lib().mb200_mask_pack_bits(masks.view(torch.uint8).data_ptr(), n, hw, out.data_ptr() if words else None, words,
+                                            area.data_ptr(), stream_handle(dev))
+        check(rc, "mask_pack_bits")
+    return out, area
+
+
+def mask_pair_intersections(det_words: Tensor, det_word_off: Tensor, gt_words: Tensor, gt_word_off: Tensor, det_off: Tensor,
+                            gt_off: Tensor, img_words: Tensor, det_label: Tensor, gt_label: Tensor, micro: bool,
+                            pair_off: Tensor, n_pairs: int, max_pairs_per_img: int) -> Tensor:
+    """``mb200_mask_pair_intersections``: the flat per-image ``[D_i, G_i]`` tables of intersection pixel counts (float64)."""
+    dev = require_cuda(det_words, gt_words, det_word_off, gt_word_off, det_off, gt_off, img_words, det_label, gt_label, pair_off)
+    out = torch.empty(max(1, n_pairs), dtype=torch.float64, device=dev)
+    n_img = int(img_words.numel())
+    if n_img and n_pairs:
+        with on_device(dev):
+            rc = lib().mb200_mask_pair_intersections(
+                ptr(det_words), ptr(det_word_off), ptr(gt_words), ptr(gt_word_off), ptr(det_off), ptr(gt_off), ptr(img_words),
+                ptr(det_label), ptr(gt_label), 1 if micro else 0, ptr(pair_off), n_img, int(max_pairs_per_img), ptr(out),
+                stream_handle(dev))
+        check(rc, "mask_pair_intersections")
+    return out
+
+
 def coco_map_match(det_box: Tensor, det_score: Tensor, det_label: Tensor, det_counts: list, gt_box: Tensor, gt_label: Tensor,
-                   gt_crowd: Tensor, gt_area: Tensor, gt_counts: list, classes: Tensor, iou_thresholds: list, max_det_last: int):
-    """``mb200_coco_map_match``: COCOeval.evaluateImg for the given images only.  Returns the per-detection records
-    ``(det_cat i32 [n], det_rank i32 [n], det_match i64 [n], det_ignore i64 [n])``, ``npig`` i32 ``[K, 4]`` and the error word."""
+                   gt_crowd: Tensor, gt_area: Tensor, gt_counts: list, classes: Tensor, iou_thresholds: list, max_det_last: int,
+                   micro: bool = False, masks: Optional[dict] = None, gt_area_exact: bool = False):
+    """``mb200_coco_map_match`` (``_ex`` with any of the last three arguments): COCOeval.evaluateImg for the given images only.
+    Returns the per-detection records ``(det_cat i32 [n], det_rank i32 [n], det_match i64 [n], det_ignore i64 [n])``, ``npig``
+    i32 ``[K, 4]`` and the error word.  ``masks``: ``{"pair_inter", "pair_off", "det_area", "gt_area"}`` (float64 / int64 /
+    float64 / float64 device tensors) switches the IoU from boxes to instance masks."""
     import numpy as np
 
     dev = require_cuda(det_box, det_score, det_label, gt_box, gt_label, gt_crowd, gt_area, classes)
@@ -525,15 +567,24 @@ def coco_map_match(det_box: Tensor, det_score: Tensor, det_label: Tensor, det_co
     det_rank = torch.empty(max(n_det, 1), dtype=torch.int32, device=dev)
     det_match = torch.empty(max(n_det, 1), dtype=torch.int64, device=dev)
     det_ignore = torch.empty(max(n_det, 1), dtype=torch.int64, device=dev)
-    npig = torch.zeros((k, 4), dtype=torch.int32, device=dev)
+    npig = torch.zeros((1 if micro else k, 4), dtype=torch.int32, device=dev)
     err = torch.zeros(1, dtype=torch.int32, device=dev)
     iou_host = (ctypes.c_double * t)(*[float(x) for x in iou_thresholds])
+    max_d, max_g = (max(det_counts) if det_counts else 0), (max(gt_counts) if gt_counts else 0)
     with on_device(dev):
-        rc = lib().mb200_coco_map_match(
-            ptr(det_box), ptr(det_score), ptr(det_label), ptr(det_off), ptr(gt_box), ptr(gt_label), ptr(gt_crowd), ptr(gt_area),
-            ptr(gt_off), n_img, max(det_counts) if det_counts else 0, max(gt_counts) if gt_counts else 0, ptr(classes), k,
-            iou_host, t, int(max_det_last), ptr(det_cat), ptr(det_rank), ptr(det_match), ptr(det_ignore), ptr(npig), ptr(err),
-            stream_handle(dev))
+        if micro or masks is not None or gt_area_exact:
+            m = masks or {}
+            keep = [m[name].contiguous() for name in ("pair_inter", "pair_off", "det_area", "gt_area")] if masks else [None] * 4
+            rc = lib().mb200_coco_map_match_ex(
+                ptr(det_box), ptr(det_score), ptr(det_label), ptr(det_off), ptr(gt_box), ptr(gt_label), ptr(gt_crowd),
+                ptr(gt_area), ptr(gt_off), n_img, max_d, max_g, ptr(classes), k, 1 if micro else 0, iou_host, t,
+                int(max_det_last), ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), 1 if gt_area_exact else 0,
+                ptr(det_cat), ptr(det_rank), ptr(det_match), ptr(det_ignore), ptr(npig), ptr(err), stream_handle(dev))
+        else:
+            rc = lib().mb200_coco_map_match(
+                ptr(det_box), ptr(det_score), ptr(det_label), ptr(det_off), ptr(gt_box), ptr(gt_label), ptr(gt_crowd),
+                ptr(gt_area), ptr(gt_off), n_img, max_d, max_g, ptr(classes), k, iou_host, t, int(max_det_last), ptr(det_cat),
+                ptr(det_rank), ptr(det_match), ptr(det_ignore), ptr(npig), ptr(err), stream_handle(dev))
     if rc == -3:
         raise NotImplementedError("metrics_b200: " + lib().mb200_last_error().decode("utf-8", "replace"))
     check(rc, "coco_map_match")

@@ -693,7 +693,7 @@ __device__ __forceinline__ double precision_at(unsigned tp, unsigned total) {
 }
 
 template <bool kWriteCurve, typename KeyT>
-__global__ void __launch_bounds__(kChainThreads) scan_chained_kernel(
+__global__ void __launch_bounds__(kChainThreads, sizeof(KeyT) == 4 ? 4 : 2) scan_chained_kernel(
     const KeyT* __restrict__ keys, const unsigned char* __restrict__ labels, int n_stride, const int* __restrict__ seg_ignored,
     int tiles, unsigned long long* status /*[segments*tiles][2], zeroed*/, unsigned* ticket /*zeroed*/,
     unsigned long long* __restrict__ auroc_acc /*[seg], zeroed*/, double* __restrict__ ap_partial /*[seg][tiles]*/,

@@ -4,7 +4,14 @@ The reference stores per-image tensors, then at ``compute`` copies every number 
 ``pycocotools`` do all the arithmetic on the CPU.  Here the nine list states and their per-image layout are kept (same
 names, ``dist_reduce_fx=None``), but ``compute`` concatenates them once on the device and runs three kernels
 (`mb200_coco_map_evaluate`, csrc/cocomap.cu): per-image matching, a stable radix sort by (class, score), per-(class,
-area, maxDet) accumulation.  Only ``iou_type="bbox"`` is in scope.
+area, maxDet) accumulation.
+
+``iou_type="segm"`` (reference :848-853, :897-944): the reference run-length encodes every mask on the host at ``update`` and
+pycocotools intersects the codes pair by pair on the host at ``compute``.  Here ``update`` packs the masks to one bit per pixel
+on the device (`mb200_mask_pack_bits`; the state entry of an image is ONE int32 tensor ``[n, H, W, areas.., bit words..]``),
+``compute`` builds every image's [detections x ground truths] table of intersection pixel counts with one launch
+(`mb200_mask_pair_intersections`) and the matching kernel reads IoUs from it (`mb200_coco_map_match_ex`).  COCO json of masks
+(``coco_to_tm`` / ``tm_to_coco`` with segm) is not implemented.
 """
 from __future__ import annotations
 
@@ -37,7 +44,7 @@ def _box_convert_to_xywh(boxes: Tensor, in_fmt: str) -> Tensor:
 
 def _pairwise_ious(det_box: Tensor, det_score: Tensor, det_label: Tensor, det_counts: List[int], gt_box: Tensor,
                    gt_label: Tensor, gt_crowd: Tensor, gt_counts: List[int], classes: List[int], micro: bool,
-                   max_det: int) -> Dict[Tuple[int, int], Any]:
+                   max_det: int, masks: Optional[Dict[str, Tensor]] = None) -> Dict[Tuple[int, int], Any]:
     """The ``ious`` entry of the extended summary (reference :552-555, i.e. pycocotools ``COCOeval.computeIoU`` for every
     (image, category)): ``{(image, class): [D, G] float32}`` with the pair's detections in descending-score order (stable,
     cut to the largest max-detection threshold) and its ground truths in input order; ``[]`` when either side is empty.
@@ -74,15 +81,26 @@ def _pairwise_ious(det_box: Tensor, det_score: Tensor, det_label: Tensor, det_co
     row = torch.repeat_interleave(torch.arange(det_order.numel(), device=dev), cols_of_row)
     row_first = torch.cumsum(cols_of_row, 0) - cols_of_row
     col = torch.arange(row.numel(), device=dev) - row_first[row]
-    d = det_box[det_order[row]].to(torch.float64)
+    d_index = det_order[row]
     g_index = gt_order[gt_start[sorted_key[row]] + col]
-    g = gt_box[g_index].to(torch.float64)
-    w = torch.minimum(d[:, 0] + d[:, 2], g[:, 0] + g[:, 2]) - torch.maximum(d[:, 0], g[:, 0])
-    h = torch.minimum(d[:, 1] + d[:, 3], g[:, 1] + g[:, 3]) - torch.maximum(d[:, 1], g[:, 1])
-    inter = torch.where((w > 0) & (h > 0), w * h, torch.zeros_like(w))
-    det_area = d[:, 2] * d[:, 3]
-    union = torch.where(gt_crowd[g_index] != 0, det_area, det_area + g[:, 2] * g[:, 3] - inter)
-    flat = (inter / union).to(torch.float32)
+    if masks is None:
+        d = det_box[d_index].to(torch.float64)
+        g = gt_box[g_index].to(torch.float64)
+        w = torch.minimum(d[:, 0] + d[:, 2], g[:, 0] + g[:, 2]) - torch.maximum(d[:, 0], g[:, 0])
+        h = torch.minimum(d[:, 1] + d[:, 3], g[:, 1] + g[:, 3]) - torch.maximum(d[:, 1], g[:, 1])
+        inter = torch.where((w > 0) & (h > 0), w * h, torch.zeros_like(w))
+        det_area = d[:, 2] * d[:, 3]
+        union = torch.where(gt_crowd[g_index] != 0, det_area, det_area + g[:, 2] * g[:, 3] - inter)
+        flat = (inter / union).to(torch.float32)
+    else:  # instance masks: the per-image [D, G] tables of intersection pixel counts (maskApi.c:rleIou semantics)
+        det_counts_t, gt_counts_t = torch.tensor(det_counts, device=dev), torch.tensor(gt_counts, device=dev)
+        det_first = torch.cumsum(det_counts_t, 0) - det_counts_t
+        gt_first = torch.cumsum(gt_counts_t, 0) - gt_counts_t
+        img = img_of_det[d_index]
+        inter = masks["pair_inter"][masks["pair_off"][img] + (d_index - det_first[img]) * gt_counts_t[img] + (g_index - gt_first[img])]
+        det_area = masks["det_area"][d_index]
+        union = torch.where(gt_crowd[g_index] != 0, det_area, det_area + masks["gt_area"][g_index] - inter)
+        flat = torch.where(inter > 0, inter / union, torch.zeros_like(inter)).to(torch.float32)
     # one host read of the block shapes, then the dict is assembled from views
     shapes = torch.stack((det_cnt, gt_cnt), 1).cpu().tolist()
     out: Dict[Tuple[int, int], Any] = {}
@@ -98,10 +116,11 @@ def _pairwise_ious(det_box: Tensor, det_score: Tensor, det_label: Tensor, det_co
 
 
 class MeanAveragePrecision(Metric):
-    """mAP / mAR for bounding-box detection (reference :77-1063).
+    """mAP / mAR for object detection and instance segmentation (reference :77-1063).
 
-    ``update(preds, target)``: lists (one entry per image) of dicts with ``boxes [n,4]``, ``scores [n]``, ``labels [n]``
-    (preds) and ``boxes``, ``labels`` and optional ``iscrowd``, ``area`` (target).  ``compute()`` returns the
+    ``update(preds, target)``: lists (one entry per image) of dicts with ``boxes [n,4]`` (``iou_type`` bbox) and / or ``masks
+    [n,H,W]`` bool (segm), ``scores [n]``, ``labels [n]`` (preds) and the same geometry keys, ``labels`` and optional
+    ``iscrowd``, ``area`` (target).  With both IoU types the result keys carry a ``bbox_`` / ``segm_`` prefix.  ``compute()`` returns the
     reference's dict: ``map, map_50, map_75, map_small/medium/large, mar_{d1,d2,d3}, mar_small/medium/large,
     map_per_class, mar_{d3}_per_class, classes`` (+ ``precision / recall / scores`` with ``extended_summary``).
     """
@@ -136,8 +155,6 @@ class MeanAveragePrecision(Metric):
             iou_type = (iou_type,)
         if any(tp not in ("bbox", "segm") for tp in iou_type):
             raise ValueError(f"Expected argument `iou_type` to be one of ('bbox', 'segm') or a tuple of, but got {iou_type}")
-        if tuple(iou_type) != ("bbox",):
-            raise NotImplementedError("metrics_b200: only `iou_type='bbox'` is implemented (mask IoU is out of scope)")
         self.iou_type = tuple(iou_type)
 
         if iou_thresholds is not None and not isinstance(iou_thresholds, list):
@@ -184,7 +201,7 @@ class MeanAveragePrecision(Metric):
     def update(self, preds: List[Dict[str, Tensor]], target: List[Dict[str, Tensor]]) -> None:
         """Append one entry per image to the list states (reference :478-519).  Box conversion to xywh runs as ONE
         batched op per call; the per-image states are views into it."""
-        _input_validator(preds, target)
+        _input_validator(preds, target, iou_type=self.iou_type)
         limit = self.max_detection_thresholds[-1]
         if self.warn_on_many_detections and any(len(p["labels"]) > limit for p in preds):
             rank_zero_warn(
@@ -194,8 +211,13 @@ class MeanAveragePrecision(Metric):
                 "class `warn_on_many_detections=False`, after initializing the metric.",
                 UserWarning,
             )
-        for boxes_list, store in (([_fix_empty_tensors(p["boxes"]) for p in preds], self.detection_box),
-                                  ([_fix_empty_tensors(t["boxes"]) for t in target], self.groundtruth_box)):
+        if "segm" in self.iou_type:  # reference :848-853 (host RLE per mask); here: bit-packed on the device, one entry per image
+            self.detection_mask.extend(self._mask_state(p["masks"]) for p in preds)
+            self.groundtruth_mask.extend(self._mask_state(t["masks"]) for t in target)
+        box_sources = () if "bbox" not in self.iou_type else (
+            ([_fix_empty_tensors(p["boxes"]) for p in preds], self.detection_box),
+            ([_fix_empty_tensors(t["boxes"]) for t in target], self.groundtruth_box))
+        for boxes_list, store in box_sources:
             counts = [b.shape[0] if b.numel() > 0 else 0 for b in boxes_list]
             nonempty = [b if b.ndim == 2 else b.reshape(-1, 4) for b in boxes_list if b.numel() > 0]
             if nonempty:
@@ -222,6 +244,61 @@ class MeanAveragePrecision(Metric):
             self.groundtruth_area.append(item["area"] if "area" in item else default)
 
     # ------------------------------------------------------------------------------------------------
+    # instance masks (iou_type "segm")
+    # ------------------------------------------------------------------------------------------------
+    def _mask_state(self, masks: Tensor) -> Tensor:
+        """``[n, H, W]`` boolean masks -> the image's state entry: int32 ``[n, H, W, area_0..area_{n-1}, bit words (n rows of
+        ceil(H*W/32), pixel order)]`` on the metric's device (`mb200_mask_pack_bits`)."""
+        if masks.ndim != 3:
+            raise ValueError(f"Expected `masks` of shape (num_masks, height, width) but got {tuple(masks.shape)}")
+        n, h, w = (int(x) for x in masks.shape)
+        words, area = _native.mask_pack_bits(masks.to(self.device))
+        head = torch.tensor([n, h, w], dtype=torch.int32).to(words.device, non_blocking=True)
+        return torch.cat([head, area.to(torch.int32), words.reshape(-1)])
+
+    def _mask_tables(self, det_label: Tensor, gt_label: Tensor, det_counts: List[int], gt_counts: List[int],
+                     micro: bool) -> Dict[str, Tensor]:
+        """Everything the matcher needs instead of boxes, for the images this process holds: the flat per-image [D, G] tables
+        of intersection pixel counts (`mb200_mask_pair_intersections`: ONE launch for all images), their offsets and the
+        masks' pixel counts."""
+        import numpy as np
+
+        dev = self.device
+        if len(self.detection_mask) != len(det_counts) or len(self.groundtruth_mask) != len(gt_counts):
+            raise ValueError("every image needs a `masks` entry when `iou_type` contains 'segm'")
+        first = lambda c: np.concatenate([[0], np.cumsum(c)])[:-1].astype(np.int64)  # noqa: E731
+
+        def side(entries: List[Tensor], counts: List[int]):
+            n = np.asarray(counts, dtype=np.int64)
+            length = np.asarray([int(e.numel()) for e in entries], dtype=np.int64)
+            words = np.where(n > 0, (length - 3 - n) // np.maximum(n, 1), 0)
+            if np.any(length != 3 + n + n * words):
+                raise ValueError("a mask state entry does not match the number of labels of its image")
+            base = first(length)
+            img = np.repeat(np.arange(len(counts)), n)
+            k = np.arange(int(n.sum())) - np.repeat(first(n), n)
+            flat = torch.cat(entries) if entries else torch.zeros(0, dtype=torch.int32, device=dev)
+            area_index = torch.from_numpy(base[img] + 3 + k).to(dev)
+            word_off = torch.from_numpy(base[img] + 3 + n[img] + k * words[img]).to(dev)
+            return n, words, flat, flat[area_index].to(torch.float64), word_off, base
+
+        dn, dwords, dflat, det_area, det_word_off, dbase = side(self.detection_mask, det_counts)
+        gn, gwords, gflat, gt_area, gt_word_off, gbase = side(self.groundtruth_mask, gt_counts)
+        both = np.nonzero((dn > 0) & (gn > 0))[0]
+        if both.size:  # (H, W) of the two sides of an image, from the entries' headers: one device comparison
+            hw = lambda flat, base: flat[torch.from_numpy(np.stack([base[both] + 1, base[both] + 2], 1)).to(dev)]  # noqa: E731
+            if np.any(dwords[both] != gwords[both]) or not bool(torch.equal(hw(dflat, dbase), hw(gflat, gbase))):
+                raise ValueError("the masks of the predictions and of the target of one image must have the same height and width")
+        pairs = dn * gn
+        to_dev = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a).astype(dt)).to(dev)  # noqa: E731
+        pair_off = to_dev(first(pairs), np.int64)
+        inter = _native.mask_pair_intersections(
+            dflat, det_word_off, gflat, gt_word_off, to_dev(np.concatenate([[0], np.cumsum(dn)]), np.int32),
+            to_dev(np.concatenate([[0], np.cumsum(gn)]), np.int32), to_dev(np.where(dn > 0, dwords, gwords), np.int32),
+            det_label, gt_label, micro, pair_off, int(pairs.sum()), int(pairs.max()) if len(pairs) else 0)
+        return {"pair_inter": inter, "pair_off": pair_off, "det_area": det_area, "gt_area": gt_area}
+
+    # ------------------------------------------------------------------------------------------------
     # cross-rank sync of the per-image list states
     # ------------------------------------------------------------------------------------------------
     def _sync_states_fast(self, group: Optional[Any]) -> bool:
@@ -230,8 +307,9 @@ class MeanAveragePrecision(Metric):
         The reference gathers the ``dist_reduce_fx=None`` list states one per-image tensor at a time — 7 collectives
         (+ barrier + shape gather each) per image, and it dead-locks unless every rank holds the same number of images
         (metric.py:501-540 as reached from detection/mean_ap.py:1031-1043).  Here every rank packs its seven flat arrays
-        and the per-image counts into ONE byte buffer: two collectives in total (sizes, payload), ragged image counts
-        allowed.  Afterwards the states are per-image lists again, images interleaved rank by rank exactly like the
+        (plus the bit-packed masks with ``iou_type`` "segm" — the reference ships pickled run-length tuples through
+        ``all_gather_object``, :1041-1063) and the per-image counts into ONE byte buffer: two collectives in total (sizes,
+        payload), ragged image counts allowed.  Afterwards the states are per-image lists again, images interleaved rank by rank exactly like the
         reference's ``_flatten`` of per-image gathers (image i of rank 0, image i of rank 1, ...).
         """
         from metrics_b200.parallel_sync import _gather_equal
@@ -240,24 +318,37 @@ class MeanAveragePrecision(Metric):
         group = group or dist.group.WORLD
         world = dist.get_world_size(group)
         dev = self.device
+        boxes, masks = "bbox" in self.iou_type, "segm" in self.iou_type
         n_img = len(self.detection_labels)
         det_counts = [int(t.shape[0]) for t in self.detection_labels]
         gt_counts = [int(t.shape[0]) for t in self.groundtruth_labels]
         n_det, n_gt = sum(det_counts), sum(gt_counts)
+        # mask entries are ragged int32 rows (one per image): their lengths travel with the per-image counts
+        dm_len = [int(t.numel()) for t in self.detection_mask] if masks else []
+        gm_len = [int(t.numel()) for t in self.groundtruth_mask] if masks else []
+        if masks and (len(dm_len) != n_img or len(gm_len) != n_img):
+            raise ValueError("every image needs a `masks` entry when `iou_type` contains 'segm'")
         # 8-byte fields first so that every field starts 8-byte aligned inside the row
         fields = [
             self._cat_or_empty(self.detection_labels, (0,), torch.int64, dev),
             self._cat_or_empty(self.groundtruth_labels, (0,), torch.int64, dev),
             self._cat_or_empty(self.groundtruth_crowds, (0,), torch.int64, dev),
             self._cat_or_empty(self.groundtruth_area, (0,), torch.float64, dev),
-            torch.tensor(det_counts + gt_counts, dtype=torch.int64, device=dev),
-            self._cat_or_empty(self.detection_box, (0, 4), torch.float32, dev),
-            self._cat_or_empty(self.groundtruth_box, (0, 4), torch.float32, dev),
+            torch.tensor(det_counts + gt_counts + dm_len + gm_len, dtype=torch.int64, device=dev),
             self._cat_or_empty(self.detection_scores, (0,), torch.float32, dev),
         ]
+        if boxes:
+            fields += [self._cat_or_empty(self.detection_box, (0, 4), torch.float32, dev),
+                       self._cat_or_empty(self.groundtruth_box, (0, 4), torch.float32, dev)]
+        if masks:
+            fields += [self._cat_or_empty(self.detection_mask, (0,), torch.int32, dev),
+                       self._cat_or_empty(self.groundtruth_mask, (0,), torch.int32, dev)]
         payload = torch.cat([f.contiguous().reshape(-1).view(torch.uint8) for f in fields])
-        sizes = _gather_equal(torch.tensor([n_img, n_det, n_gt], dtype=torch.int64, device=dev), group, world).tolist()
-        row_bytes = max(8 * (nd + 3 * ng + 2 * ni) + 16 * (nd + ng) + 4 * nd for ni, nd, ng in sizes)
+        sizes = _gather_equal(torch.tensor([n_img, n_det, n_gt, sum(dm_len), sum(gm_len)], dtype=torch.int64, device=dev),
+                              group, world).tolist()
+        per_img = 4 if masks else 2
+        row_bytes = max(8 * (nd + 3 * ng + per_img * ni) + 4 * nd + (16 * (nd + ng) if boxes else 0) + 4 * (ndm + ngm)
+                        for ni, nd, ng, ndm, ngm in sizes)
         row_bytes = (row_bytes + 15) // 16 * 16
         if row_bytes == 0:
             return True
@@ -266,7 +357,7 @@ class MeanAveragePrecision(Metric):
         rows = _gather_equal(row, group, world)
 
         per_rank = []
-        for r, (ni, nd, ng) in enumerate(sizes):
+        for r, (ni, nd, ng, ndm, ngm) in enumerate(sizes):
             buf, off = rows[r], 0
 
             def take(count: int, dtype: torch.dtype, width: int = 1) -> Tensor:
@@ -277,17 +368,23 @@ class MeanAveragePrecision(Metric):
                 return out.reshape(count, width) if width > 1 else out
 
             det_label, gt_label, gt_crowd, gt_area = take(nd, torch.int64), take(ng, torch.int64), take(ng, torch.int64), take(ng, torch.float64)
-            counts = take(2 * ni, torch.int64).tolist()
-            det_box, gt_box, det_score = take(nd, torch.float32, 4), take(ng, torch.float32, 4), take(nd, torch.float32)
-            dc, gc = counts[:ni], counts[ni:]
-            per_rank.append({
-                "detection_box": det_box.split(dc), "detection_scores": det_score.split(dc), "detection_labels": det_label.split(dc),
-                "groundtruth_box": gt_box.split(gc), "groundtruth_labels": gt_label.split(gc),
-                "groundtruth_crowds": gt_crowd.split(gc), "groundtruth_area": gt_area.split(gc),
-            })
-        max_img = max(ni for ni, _, _ in sizes)
-        for name in ("detection_box", "detection_scores", "detection_labels", "groundtruth_box", "groundtruth_labels",
-                     "groundtruth_crowds", "groundtruth_area"):
+            counts = take(per_img * ni, torch.int64).tolist()
+            det_score = take(nd, torch.float32)
+            dc, gc = counts[:ni], counts[ni:2 * ni]
+            entry = {
+                "detection_scores": det_score.split(dc), "detection_labels": det_label.split(dc),
+                "groundtruth_labels": gt_label.split(gc), "groundtruth_crowds": gt_crowd.split(gc),
+                "groundtruth_area": gt_area.split(gc),
+            }
+            if boxes:
+                entry["detection_box"] = take(nd, torch.float32, 4).split(dc)
+                entry["groundtruth_box"] = take(ng, torch.float32, 4).split(gc)
+            if masks:
+                entry["detection_mask"] = take(ndm, torch.int32).split(counts[2 * ni:3 * ni])
+                entry["groundtruth_mask"] = take(ngm, torch.int32).split(counts[3 * ni:])
+            per_rank.append(entry)
+        max_img = max(s[0] for s in sizes)
+        for name in per_rank[0]:
             setattr(self, name, [per_rank[r][name][i] for i in range(max_img) for r in range(world) if i < sizes[r][0]])
         return True
 
@@ -388,6 +485,8 @@ class MeanAveragePrecision(Metric):
     def tm_to_coco(self, name: str = "tm_map_input") -> None:
         """Write everything ``update`` has cached as ``{name}_preds.json`` (the COCO results list) and
         ``{name}_target.json`` (the COCO ground-truth dataset), reference :762-825."""
+        if "segm" in self.iou_type:
+            raise NotImplementedError("metrics_b200: COCO json export of instance masks (run-length codes) is not implemented")
         target = self._coco_dataset(self.groundtruth_labels, self.groundtruth_box, crowds=self.groundtruth_crowds,
                                     area=self.groundtruth_area)
         preds = self._coco_dataset(self.detection_labels, self.detection_box, scores=self.detection_scores)
@@ -417,78 +516,126 @@ class MeanAveragePrecision(Metric):
             flat = torch.cat(items)
         return flat.to(dtype)
 
-    def _stats_dict(self, stats: List[Tensor]) -> Dict[str, Tensor]:
+    def _stats_dict(self, stats: List[Tensor], prefix: str = "") -> Dict[str, Tensor]:
         mdt = self.max_detection_thresholds
         names = ["map", "map_50", "map_75", "map_small", "map_medium", "map_large", f"mar_{mdt[0]}", f"mar_{mdt[1]}",
                  f"mar_{mdt[2]}", "mar_small", "mar_medium", "mar_large"]
-        return {n: s.to(torch.float32).reshape(1) for n, s in zip(names, stats)}
+        return {prefix + n: s.to(torch.float32).reshape(1) for n, s in zip(names, stats)}
+
+    def _local_states(self) -> Dict[str, Any]:
+        """The per-image list states of this process as flat device tensors (+ per-image counts)."""
+        dev = self.device
+        out: Dict[str, Any] = {
+            "det_counts": [int(t.shape[0]) for t in self.detection_labels],
+            "gt_counts": [int(t.shape[0]) for t in self.groundtruth_labels],
+            "det_score": self._cat_or_empty(self.detection_scores, (0,), torch.float32, dev),
+            "det_label": self._cat_or_empty(self.detection_labels, (0,), torch.int64, dev),
+            "gt_label": self._cat_or_empty(self.groundtruth_labels, (0,), torch.int64, dev),
+            "gt_crowd": self._cat_or_empty(self.groundtruth_crowds, (0,), torch.uint8, dev),
+            "gt_area": self._cat_or_empty(self.groundtruth_area, (0,), torch.float64, dev),
+        }
+        if "bbox" in self.iou_type:
+            out["det_box"] = self._cat_or_empty(self.detection_box, (0, 4), torch.float32, dev)
+            out["gt_box"] = self._cat_or_empty(self.groundtruth_box, (0, 4), torch.float32, dev)
+        else:  # masks only: the matcher never reads the boxes
+            out["det_box"] = torch.zeros((out["det_label"].numel(), 4), dtype=torch.float32, device=dev)
+            out["gt_box"] = torch.zeros((out["gt_label"].numel(), 4), dtype=torch.float32, device=dev)
+        return out
+
+    def _match(self, st: Dict[str, Any], i_type: str, classes: Tensor, micro: bool, tables: Optional[Dict[str, Tensor]]):
+        """COCOeval.evaluateImg over this process' images for one IoU type whenever masks are involved (reference :527-547):
+        ``tables`` (`_mask_tables`) provides the mask IoUs for "segm" and — reference :917-933 — the annotation area of a
+        ground truth without a positive ``area`` is its MASK area for every IoU type as soon as "segm" is among them."""
+        gt_area = st["gt_area"]
+        if tables is not None:
+            gt_area = torch.where(gt_area > 0, gt_area, tables["gt_area"])
+        return _native.coco_map_match(
+            st["det_box"], st["det_score"], st["det_label"], st["det_counts"], st["gt_box"], st["gt_label"], st["gt_crowd"],
+            gt_area, st["gt_counts"], classes, self.iou_thresholds, self.max_detection_thresholds[-1], micro=micro,
+            masks=tables if i_type == "segm" else None, gt_area_exact=tables is not None)
 
     def compute(self) -> Dict[str, Tensor]:
-        """Reference :521-598 (bbox)."""
+        """Reference :521-598: one evaluation per IoU type (keys prefixed ``bbox_`` / ``segm_`` when there are two)."""
         dev = self.device
         n_img = len(self.detection_labels)
         minus_one = torch.tensor(-1.0, dtype=torch.float64, device=dev)
         classes_list = self._get_classes()
+        multi = len(self.iou_type) > 1
+        last = self.max_detection_thresholds[-1]
         result: Dict[str, Tensor] = {}
         if n_img == 0:
-            result.update(self._stats_dict([minus_one] * 12))
-            result["map_per_class"] = torch.tensor([-1.0], dtype=torch.float32, device=dev)
-            result[f"mar_{self.max_detection_thresholds[-1]}_per_class"] = torch.tensor([-1.0], dtype=torch.float32, device=dev)
+            for i_type in self.iou_type:
+                prefix = f"{i_type}_" if multi else ""
+                result.update(self._stats_dict([minus_one] * 12, prefix))
+                result[f"{prefix}map_per_class"] = torch.tensor([-1.0], dtype=torch.float32, device=dev)
+                result[f"{prefix}mar_{last}_per_class"] = torch.tensor([-1.0], dtype=torch.float32, device=dev)
             result["classes"] = torch.tensor(classes_list, dtype=torch.int32, device=dev)
             return result
 
-        det_counts = [int(t.shape[0]) for t in self.detection_labels]
-        gt_counts = [int(t.shape[0]) for t in self.groundtruth_labels]
-        det_box = self._cat_or_empty(self.detection_box, (0, 4), torch.float32, dev)
-        det_score = self._cat_or_empty(self.detection_scores, (0,), torch.float32, dev)
-        det_label = self._cat_or_empty(self.detection_labels, (0,), torch.int64, dev)
-        gt_box = self._cat_or_empty(self.groundtruth_box, (0, 4), torch.float32, dev)
-        gt_label = self._cat_or_empty(self.groundtruth_labels, (0,), torch.int64, dev)
-        gt_crowd = self._cat_or_empty(self.groundtruth_crowds, (0,), torch.uint8, dev)
-        gt_area = self._cat_or_empty(self.groundtruth_area, (0,), torch.float64, dev)
+        st = self._local_states()
         classes = torch.tensor(classes_list, dtype=torch.int64, device=dev)
         if classes.numel() == 0:  # images without any box at all
             classes = torch.zeros(1, dtype=torch.int64, device=dev)
+        micro = self.average == "micro"
+        with_masks = "segm" in self.iou_type
+        tables: Dict[bool, Dict[str, Tensor]] = {}
 
-        def run(micro: bool):
-            return _native.coco_map_evaluate(
-                det_box, det_score, det_label, det_counts, gt_box, gt_label, gt_crowd, gt_area, gt_counts, classes,
-                micro, self.iou_thresholds, self.rec_thresholds, self.max_detection_thresholds,
-            )
+        def tables_for(as_micro: bool) -> Optional[Dict[str, Tensor]]:
+            if not with_masks:
+                return None
+            if as_micro not in tables:
+                tables[as_micro] = self._mask_tables(st["det_label"], st["gt_label"], st["det_counts"], st["gt_counts"], as_micro)
+            return tables[as_micro]
 
-        precision, recall, scores, err = run(self.average == "micro")
-        if int(err.item()) != 0:
-            raise NotImplementedError("metrics_b200: an image holds more ground truths of one class than the matcher can track")
-        extras: Dict[str, Tensor] = {}
-        if self.extended_summary:
-            micro = self.average == "micro"
-            extras["ious"] = _pairwise_ious(det_box, det_score, det_label, det_counts, gt_box, gt_label, gt_crowd, gt_counts,
-                                            classes_list, micro, self.max_detection_thresholds[-1])
-            extras["precision"] = precision
-            extras["recall"] = recall
-            extras["scores"] = scores
-        per_class = None
-        if self.class_metrics:
-            per_class = (precision, recall)
-            if self.average == "micro":  # the reference re-evaluates per class with the true labels (:566-569)
-                per_class = run(False)[:2]
-        return self._results(precision, recall, classes_list, extras, per_class)
+        def run(i_type: str, as_micro: bool):
+            if not with_masks:  # boxes only: matching + accumulation behind one call
+                return _native.coco_map_evaluate(
+                    st["det_box"], st["det_score"], st["det_label"], st["det_counts"], st["gt_box"], st["gt_label"], st["gt_crowd"],
+                    st["gt_area"], st["gt_counts"], classes, as_micro, self.iou_thresholds, self.rec_thresholds,
+                    self.max_detection_thresholds)
+            (cat, rnk, match, ignore), npig, err = self._match(st, i_type, classes, as_micro, tables_for(as_micro))
+            k = 1 if as_micro else int(classes.numel())
+            precision, recall, scores, _ = _native.coco_map_accumulate(
+                cat, st["det_score"], rnk, match, ignore, npig, k, 0, k, len(self.iou_thresholds), self.rec_thresholds,
+                self.max_detection_thresholds)
+            return precision, recall, scores, err
+
+        for i_type in self.iou_type:
+            prefix = f"{i_type}_" if multi else ""
+            precision, recall, scores, err = run(i_type, micro)
+            if int(err.item()) != 0:
+                raise NotImplementedError("metrics_b200: an image holds more ground truths of one class than the matcher can track")
+            extras: Dict[str, Tensor] = {}
+            if self.extended_summary:
+                extras["ious"] = _pairwise_ious(st["det_box"], st["det_score"], st["det_label"], st["det_counts"], st["gt_box"],
+                                                st["gt_label"], st["gt_crowd"], st["gt_counts"], classes_list, micro, last,
+                                                masks=tables_for(micro) if i_type == "segm" else None)
+                extras["precision"] = precision
+                extras["recall"] = recall
+                extras["scores"] = scores
+            per_class = None
+            if self.class_metrics:
+                per_class = (precision, recall)
+                if micro:  # the reference re-evaluates per class with the true labels (:566-569)
+                    per_class = run(i_type, False)[:2]
+            result.update(self._results(precision, recall, classes_list, extras, per_class, prefix))
+        return result
 
     def _results(self, precision: Tensor, recall: Tensor, classes_list: List[int], extras: Dict[str, Tensor],
-                 per_class: Optional[Tuple[Tensor, Tensor]]) -> Dict[str, Tensor]:
+                 per_class: Optional[Tuple[Tensor, Tensor]], prefix: str = "") -> Dict[str, Tensor]:
         """The result dict from the accumulated ``precision [T,R,K,A,M]`` / ``recall [T,K,A,M]`` (reference :571-598)."""
         dev = precision.device
         result: Dict[str, Tensor] = {}
-        result.update(self._stats_dict(self._summarize(precision, recall)))
-        result.update(extras)
+        result.update(self._stats_dict(self._summarize(precision, recall), prefix))
+        result.update({prefix + k: v for k, v in extras.items()})
         last = self.max_detection_thresholds[-1]
         if per_class is not None:
             m_last = len(self.max_detection_thresholds) - 1
-            result["map_per_class"] = self._masked_mean(per_class[0][:, :, :, 0, m_last], dims=(0, 1)).to(torch.float32)
-            result[f"mar_{last}_per_class"] = self._masked_mean(per_class[1][:, :, 0, m_last], dims=(0,)).to(torch.float32)
+            result[f"{prefix}map_per_class"] = self._masked_mean(per_class[0][:, :, :, 0, m_last], dims=(0, 1)).to(torch.float32)
+            result[f"{prefix}mar_{last}_per_class"] = self._masked_mean(per_class[1][:, :, 0, m_last], dims=(0,)).to(torch.float32)
         else:
-            result["map_per_class"] = torch.tensor([-1.0], dtype=torch.float32, device=dev)
-            result[f"mar_{last}_per_class"] = torch.tensor([-1.0], dtype=torch.float32, device=dev)
+            result[f"{prefix}map_per_class"] = torch.tensor([-1.0], dtype=torch.float32, device=dev)
+            result[f"{prefix}mar_{last}_per_class"] = torch.tensor([-1.0], dtype=torch.float32, device=dev)
         result["classes"] = torch.tensor(classes_list, dtype=torch.int32, device=dev)
         return result
 
@@ -526,8 +673,8 @@ class MeanAveragePrecision(Metric):
         from metrics_b200.utilities.distributed import gather_all_tensors
 
         dev = self.device
-        det_counts = [int(t.shape[0]) for t in self.detection_labels]
-        gt_counts = [int(t.shape[0]) for t in self.groundtruth_labels]
+        st = self._local_states()
+        det_counts, det_score = st["det_counts"], st["det_score"]
         # ---- the class list and the image layout of every rank (two small ragged gathers) -------------------------------------
         labels = self.detection_labels + self.groundtruth_labels
         local_labels = torch.cat(labels).to(torch.int64).unique() if labels else torch.zeros(0, dtype=torch.int64, device=dev)
@@ -539,48 +686,47 @@ class MeanAveragePrecision(Metric):
         if classes.numel() == 0:
             classes = torch.zeros(1, dtype=torch.int64, device=dev)
         k = int(classes.numel())
-        # ---- phase 1 on this rank's images --------------------------------------------------------------------------------------
-        det_score = self._cat_or_empty(self.detection_scores, (0,), torch.float32, dev)
-        records, npig, err = _native.coco_map_match(
-            self._cat_or_empty(self.detection_box, (0, 4), torch.float32, dev), det_score,
-            self._cat_or_empty(self.detection_labels, (0,), torch.int64, dev), det_counts,
-            self._cat_or_empty(self.groundtruth_box, (0, 4), torch.float32, dev),
-            self._cat_or_empty(self.groundtruth_labels, (0,), torch.int64, dev),
-            self._cat_or_empty(self.groundtruth_crowds, (0,), torch.uint8, dev),
-            self._cat_or_empty(self.groundtruth_area, (0,), torch.float64, dev), gt_counts, classes, self.iou_thresholds,
-            self.max_detection_thresholds[-1])
-        dist.all_reduce(npig, group=group)
-        dist.all_reduce(err, op=dist.ReduceOp.MAX, group=group)
-        if int(err.item()) != 0:
-            raise NotImplementedError("metrics_b200: an image holds more ground truths of one class than the matcher can track")
-        # ---- records of all ranks, in the interleaved image order of the gathered evaluation -------------------------------------
-        cat, rnk, match, ignore = records
-        packed = torch.stack([(cat.to(torch.int64) << 32) | rnk.to(torch.int64), det_score.contiguous().view(torch.int32).to(torch.int64),
-                              match, ignore], dim=1)  # [n_local, 4] int64
-        allrec = torch.cat(gather_all_tensors(packed, group))
         bases = np.concatenate([[0], np.cumsum([sum(c) for c in counts_all])])
         offs = [np.concatenate([[0], np.cumsum(c)]) for c in counts_all]
         pieces = [np.arange(bases[r] + offs[r][i], bases[r] + offs[r][i + 1]) for i in range(max(len(c) for c in counts_all))
                   for r in range(world) if i < len(counts_all[r])]
         perm = torch.from_numpy(np.concatenate(pieces).astype(np.int64) if pieces else np.zeros(0, np.int64)).to(dev)
-        allrec = allrec[perm]
-        # ---- phase 2 on this rank's classes ----------------------------------------------------------------------------------------
         cpr = (k + world - 1) // world
         lo = min(rank * cpr, k)
         hi = min(lo + cpr, k)
-        precision, recall, scores, _ = _native.coco_map_accumulate(
-            (allrec[:, 0] >> 32).to(torch.int32), allrec[:, 1].to(torch.int32).view(torch.float32),
-            (allrec[:, 0] & 0xFFFFFFFF).to(torch.int32), allrec[:, 2], allrec[:, 3], npig, k, lo, hi, len(self.iou_thresholds),
-            self.rec_thresholds, self.max_detection_thresholds)
-        # ---- the class slices of every rank ---------------------------------------------------------------------------------------
-        t, r_, m = precision.shape[0], precision.shape[1], precision.shape[4]
-        slab_p = torch.full((t, r_, cpr, 4, m), -1.0, dtype=torch.float64, device=dev)
-        slab_r = torch.full((t, cpr, 4, m), -1.0, dtype=torch.float64, device=dev)
-        slab_p[:, :, : hi - lo] = precision[:, :, lo:hi]
-        slab_r[:, : hi - lo] = recall[:, lo:hi]
-        precision = _gather_equal(slab_p, group, world).permute(1, 2, 0, 3, 4, 5).reshape(t, r_, world * cpr, 4, m)[:, :, :k].contiguous()
-        recall = _gather_equal(slab_r, group, world).permute(1, 0, 2, 3, 4).reshape(t, world * cpr, 4, m)[:, :k].contiguous()
-        return self._results(precision, recall, classes_list, {}, (precision, recall) if self.class_metrics else None)
+        # masks stay where they are: every rank intersects the masks of its own images only
+        tables = (self._mask_tables(st["det_label"], st["gt_label"], det_counts, st["gt_counts"], False)
+                  if "segm" in self.iou_type else None)
+        multi = len(self.iou_type) > 1
+        result: Dict[str, Tensor] = {}
+        for i_type in self.iou_type:
+            # ---- phase 1 on this rank's images ----------------------------------------------------------------------------------
+            records, npig, err = self._match(st, i_type, classes, False, tables)
+            dist.all_reduce(npig, group=group)
+            dist.all_reduce(err, op=dist.ReduceOp.MAX, group=group)
+            if int(err.item()) != 0:
+                raise NotImplementedError("metrics_b200: an image holds more ground truths of one class than the matcher can track")
+            # ---- records of all ranks, in the interleaved image order of the gathered evaluation ---------------------------------
+            cat, rnk, match, ignore = records
+            packed = torch.stack([(cat.to(torch.int64) << 32) | rnk.to(torch.int64),
+                                  det_score.contiguous().view(torch.int32).to(torch.int64), match, ignore], dim=1)  # [n_local, 4] int64
+            allrec = torch.cat(gather_all_tensors(packed, group))[perm]
+            # ---- phase 2 on this rank's classes ------------------------------------------------------------------------------------
+            precision, recall, scores, _ = _native.coco_map_accumulate(
+                (allrec[:, 0] >> 32).to(torch.int32), allrec[:, 1].to(torch.int32).view(torch.float32),
+                (allrec[:, 0] & 0xFFFFFFFF).to(torch.int32), allrec[:, 2], allrec[:, 3], npig, k, lo, hi, len(self.iou_thresholds),
+                self.rec_thresholds, self.max_detection_thresholds)
+            # ---- the class slices of every rank -----------------------------------------------------------------------------------
+            t, r_, m = precision.shape[0], precision.shape[1], precision.shape[4]
+            slab_p = torch.full((t, r_, cpr, 4, m), -1.0, dtype=torch.float64, device=dev)
+            slab_r = torch.full((t, cpr, 4, m), -1.0, dtype=torch.float64, device=dev)
+            slab_p[:, :, : hi - lo] = precision[:, :, lo:hi]
+            slab_r[:, : hi - lo] = recall[:, lo:hi]
+            precision = _gather_equal(slab_p, group, world).permute(1, 2, 0, 3, 4, 5).reshape(t, r_, world * cpr, 4, m)[:, :, :k].contiguous()
+            recall = _gather_equal(slab_r, group, world).permute(1, 0, 2, 3, 4).reshape(t, world * cpr, 4, m)[:, :k].contiguous()
+            result.update(self._results(precision, recall, classes_list, {}, (precision, recall) if self.class_metrics else None,
+                                        f"{i_type}_" if multi else ""))
+        return result
 
     @staticmethod
     def _masked_mean(x: Tensor, dims: Optional[Tuple[int, ...]] = None) -> Tensor:

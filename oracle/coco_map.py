@@ -1,4 +1,4 @@
-"""Oracle for detection.MeanAveragePrecision (bbox), numpy/fp64.  TEST INFRASTRUCTURE ONLY — see oracle/__init__.py.
+"""Oracle for detection.MeanAveragePrecision (bbox, and segm on decoded masks), numpy/fp64.  TEST INFRASTRUCTURE ONLY — see oracle/__init__.py.
 
 PARITY STATUS: **partially pinned**.  In the reference all mAP arithmetic happens inside the third-party package
 `pycocotools >2.0.0,<2.1.0` (`cocoeval.py` COCOeval.evaluate/accumulate/summarize and `maskApi.c:bbIou`; call sites
@@ -94,8 +94,25 @@ def compute_ious(det_boxes: Sequence[np.ndarray], det_scores: Sequence[np.ndarra
     return out
 
 
-def _evaluate_img(dt_boxes, dt_scores, gt_boxes, gt_crowd, gt_area, iou_thrs, area_rng, max_det):
-    """COCOeval.computeIoU + evaluateImg for one (image, category, area range).  Returns None when both lists are empty."""
+def mask_iou(dt: np.ndarray, gt: np.ndarray, iscrowd: np.ndarray) -> np.ndarray:
+    """maskApi.c:rleIou on decoded masks (bool [n, H, W]): intersection / union of pixel counts in double; no intersection
+    -> 0 (`if(i==0) u=1`); for a crowd gt the union is the detection's area.  (pycocotools walks run-length codes; the counts
+    it arrives at are these.)"""
+    out = np.zeros((dt.shape[0], gt.shape[0]), dtype=np.float64)
+    for gi in range(gt.shape[0]):
+        ga = int(gt[gi].sum())
+        for di in range(dt.shape[0]):
+            inter = int(np.logical_and(dt[di], gt[gi]).sum())
+            if inter == 0:
+                continue
+            da = int(dt[di].sum())
+            out[di, gi] = inter / (da if iscrowd[gi] else da + ga - inter)
+    return out
+
+
+def _evaluate_img(dt_boxes, dt_scores, gt_boxes, gt_crowd, gt_area, iou_thrs, area_rng, max_det, masks=False):
+    """COCOeval.computeIoU + evaluateImg for one (image, category, area range).  Returns None when both lists are empty.
+    `masks`: dt_boxes / gt_boxes are boolean instance masks [n, H, W] (iouType "segm")."""
     if len(dt_scores) == 0 and len(gt_boxes) == 0:
         return None
     dt_order = np.argsort(-dt_scores, kind="mergesort")[:max_det]
@@ -104,7 +121,7 @@ def _evaluate_img(dt_boxes, dt_scores, gt_boxes, gt_crowd, gt_area, iou_thrs, ar
     gt_order = np.argsort(gt_ig, kind="mergesort")
     gt_boxes, gt_crowd, gt_ig = gt_boxes[gt_order], gt_crowd[gt_order], gt_ig[gt_order]
     T, G, D = len(iou_thrs), len(gt_boxes), len(dt_scores)
-    ious = bb_iou(dt_boxes, gt_boxes, gt_crowd) if D and G else np.zeros((D, G))
+    ious = (mask_iou if masks else bb_iou)(dt_boxes, gt_boxes, gt_crowd) if D and G else np.zeros((D, G))
     gtm = np.zeros((T, G), dtype=np.int64)
     dtm = np.zeros((T, D), dtype=np.int64)
     dt_ig = np.zeros((T, D), dtype=bool)
@@ -127,7 +144,10 @@ def _evaluate_img(dt_boxes, dt_scores, gt_boxes, gt_crowd, gt_area, iou_thrs, ar
                 dt_ig[ti, di] = gt_ig[m]
                 dtm[ti, di] = m + 1
                 gtm[ti, m] = di + 1
-    dt_area = dt_boxes[:, 2].astype(np.float64) * dt_boxes[:, 3].astype(np.float64) if D else np.zeros(0)
+    if masks:  # detection/mean_ap.py:923-924: the detection's "area" is its mask area
+        dt_area = dt_boxes.sum(axis=(1, 2)).astype(np.float64) if D else np.zeros(0)
+    else:
+        dt_area = dt_boxes[:, 2].astype(np.float64) * dt_boxes[:, 3].astype(np.float64) if D else np.zeros(0)
     out_of_range = (dt_area < area_rng[0]) | (dt_area > area_rng[1])
     dt_ig = dt_ig | ((dtm == 0) & out_of_range[None, :])
     return {"dtm": dtm, "dt_ig": dt_ig, "scores": dt_scores, "gt_ig": gt_ig}
@@ -146,8 +166,15 @@ def coco_evaluate(
     rec_thresholds: Optional[List[float]] = None,
     max_detection_thresholds: Optional[List[int]] = None,
     average: str = "macro",
+    det_masks: Optional[Sequence[np.ndarray]] = None,
+    gt_masks: Optional[Sequence[np.ndarray]] = None,
+    iou_type: str = "bbox",
 ) -> Dict[str, np.ndarray]:
-    """MeanAveragePrecision.compute for iou_type="bbox" (detection/mean_ap.py:521-598) with COCOeval restated inline.
+    """MeanAveragePrecision.compute for ONE IoU type (detection/mean_ap.py:521-598) with COCOeval restated inline.
+
+    `det_masks` / `gt_masks` (per image bool [n, H, W]) = the metric was built with "segm" among its IoU types: a ground truth
+    without a positive `area` then gets its MASK area (detection/mean_ap.py:920-925 — for the "bbox" evaluation of a
+    ("bbox", "segm") metric as well), and `iou_type="segm"` evaluates mask IoUs (boxes may then be None).
 
     Inputs are per-image arrays (list position = image id, detection/mean_ap.py:886).  Returns the reference's result
     dict (numpy scalars/arrays) plus the raw `precision [T,R,K,A,M]`, `recall [T,K,A,M]`, `scores` tensors.
@@ -156,8 +183,15 @@ def coco_evaluate(
     rec_thrs = np.array(rec_thresholds or default_rec_thresholds(), dtype=np.float64)
     max_dets = sorted(max_detection_thresholds or [1, 10, 100])
     n_img = len(det_labels)
+    if det_boxes is None:
+        det_boxes = [np.zeros((len(np.asarray(x).reshape(-1)), 4), np.float32) for x in det_labels]
+        gt_boxes = [np.zeros((len(np.asarray(x).reshape(-1)), 4), np.float32) for x in gt_labels]
     dboxes = [box_convert_to_xywh(np.asarray(b), box_format) for b in det_boxes]
     gboxes = [box_convert_to_xywh(np.asarray(b), box_format) for b in gt_boxes]
+    segm = iou_type == "segm"
+    if gt_masks is not None:
+        det_masks = [np.asarray(m).astype(bool) for m in det_masks]
+        gt_masks = [np.asarray(m).astype(bool) for m in gt_masks]
     dlab = [np.asarray(x).astype(np.int64).reshape(-1) for x in det_labels]
     glab = [np.asarray(x).astype(np.int64).reshape(-1) for x in gt_labels]
     dsc = [np.asarray(x).astype(np.float32).astype(np.float64).reshape(-1) for x in det_scores]
@@ -166,6 +200,8 @@ def coco_evaluate(
     garea = []
     for i in range(n_img):
         wh = gboxes[i][:, 2].astype(np.float64) * gboxes[i][:, 3].astype(np.float64)
+        if gt_masks is not None:
+            wh = gt_masks[i].sum(axis=(1, 2)).astype(np.float64)
         if gt_areas is not None:
             given = np.asarray(gt_areas[i]).astype(np.float64).reshape(-1)
             wh = np.where(given > 0, given, wh)  # detection/mean_ap.py:920-925
@@ -191,8 +227,9 @@ def coco_evaluate(
             for a, rng in enumerate(AREA_RANGES):
                 for i in range(n_img):
                     dm, gm = dlab[i] == cat, glab[i] == cat
-                    evals[k, a, i] = _evaluate_img(dboxes[i][dm], dsc[i][dm], gboxes[i][gm], gcr[i][gm], garea[i][gm],
-                                                   iou_thrs, rng, max_dets[-1])
+                    evals[k, a, i] = _evaluate_img((det_masks if segm else dboxes)[i][dm], dsc[i][dm],
+                                                   (gt_masks if segm else gboxes)[i][gm], gcr[i][gm], garea[i][gm],
+                                                   iou_thrs, rng, max_dets[-1], masks=segm)
         # ---- accumulate (COCOeval.accumulate) ----
         for k in range(K):
             for a in range(A):

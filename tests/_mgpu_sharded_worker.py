@@ -104,6 +104,31 @@ def main():
     truth2 = one2.compute()
     for k in truth2:
         assert torch.equal(got2[k].cpu(), truth2[k].cpu()), (k, got2[k], truth2[k])
+    # ---- the same three-way agreement with instance masks (("bbox", "segm")): sharded (no mask leaves its rank), gathered
+    # (bit-packed masks in the packed exchange), one GPU fed the interleaved images -------------------------------------------
+    from tests.test_map_segm_gpu import synth_masks
+
+    seg = [synth_masks(seed=90 + r, n_img=4 + 3 * r, n_gt=4, n_det=9, n_cls=4, crowd_frac=0.2, dup_scores=True, with_boxes=True)
+           for r in range(world)]
+    n_seg = [4 + 3 * r for r in range(world)]
+    ms = MeanAveragePrecision(iou_type=("bbox", "segm"), class_metrics=True).to(dev)
+    ms.update(to_dev(seg[rank][0]), to_dev(seg[rank][1]))
+    got_s = ms.compute()
+    one_s = MeanAveragePrecision(iou_type=("bbox", "segm"), class_metrics=True, sync_on_compute=False).to(dev)
+    for i in range(max(n_seg)):
+        for r in range(world):
+            if i < n_seg[r]:
+                one_s.update(to_dev(seg[r][0][i:i + 1]), to_dev(seg[r][1][i:i + 1]))
+    truth_s = one_s.compute()
+    os.environ["MB200_SHARDED_MAP"] = "0"
+    ms._computed = None
+    gathered_s = ms.compute()
+    os.environ["MB200_SHARDED_MAP"] = "1"
+    assert "segm_map" in truth_s and "bbox_map_per_class" in truth_s
+    for k in truth_s:
+        assert torch.equal(got_s[k].cpu(), truth_s[k].cpu()), (k, got_s[k], truth_s[k])
+        assert torch.equal(gathered_s[k].cpu(), truth_s[k].cpu()), (k, gathered_s[k], truth_s[k])
+    assert len(ms.detection_mask) == n_seg[rank]
     torch.distributed.barrier()
     if rank == 0:
         print("SHARDED_OK")

@@ -336,7 +336,20 @@ NAMES = ("launch_count", "multiclass_confmat_update_", "multiclass_stat_scores_u
          "multiclass_stat_scores_topk_update_", "multiclass_stat_scores_samplewise", "argmax_rows",
          "sigmoid_if_logits", "softmax_if_logits", "curve_evaluate", "curve_evaluate_multilabel",
          "binary_stat_counts", "regression_sums", "binned_curve_update", "coco_map_evaluate", "curve_weighted_clf_curve",
-         "multiclass_stats_softmax_update_")
+         "multiclass_stats_softmax_update_", "mask_pack_bits")
+
+
+def mask_pack_bits(masks: Tensor):
+    """Stand-in for `mb200_mask_pack_bits`: 32 pixels per int32 word in pixel order (bit k of word w = pixel 32 w + k), areas."""
+    n = int(masks.shape[0])
+    hw = int(masks[0].numel()) if n else 0
+    flat = masks.reshape(n, hw) != 0
+    words = (hw + 31) // 32
+    pad = torch.zeros((n, words * 32), dtype=torch.int64)
+    pad[:, :hw] = flat.to(torch.int64)
+    packed = (pad.reshape(n, words, 32) << torch.arange(32, dtype=torch.int64)).sum(2)
+    packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32)
+    return packed, flat.sum(1).to(torch.int64)
 
 
 def standins() -> dict:

@@ -177,6 +177,38 @@ def _scenarios(rank: int) -> None:
     assert mp_.groundtruth_area[2].tolist() == [0.0, 0.0, 0.0]
     mp_.unsync()
     assert len(mp_.detection_box) == n_mine and all(torch.equal(a, b) for a, b in zip(mp_.detection_box, local_boxes))
+    # ---- mAP with instance masks: the bit-packed per-image mask entries ride in the same packed exchange ---------------------
+    import metrics_b200._native as native
+    from tests.reference_runtime import cpu_kernels
+
+    real_pack = native.mask_pack_bits
+    native.mask_pack_bits = cpu_kernels.mask_pack_bits  # the kernel's stand-in: this scenario is about the exchange
+    try:
+        g = torch.Generator().manual_seed(70 + rank)
+        sizes = [(9, 11), (33, 40), (5, 5)][: n_mine]
+        seg_p = [dict(masks=torch.rand(2 + i, h, w, generator=g) > 0.5, scores=torch.rand(2 + i, generator=g),
+                      labels=torch.randint(0, 3, (2 + i,), generator=g)) for i, (h, w) in enumerate(sizes)]
+        seg_t = [dict(masks=torch.rand(i, h, w, generator=g) > 0.5, labels=torch.randint(0, 3, (i,), generator=g))
+                 for i, (h, w) in enumerate(sizes)]  # image 0 has no ground truth at all
+        ms = MeanAveragePrecision(iou_type="segm")
+        ms.update(seg_p, seg_t)
+        mine = [m.clone() for m in ms.detection_mask]
+        assert [m[:3].tolist() for m in mine] == [[2 + i, h, w] for i, (h, w) in enumerate(sizes)]
+        assert [int(m.numel()) for m in ms.groundtruth_mask] == [3 + i + i * ((h * w + 31) // 32) for i, (h, w) in enumerate(sizes)]
+        for m, p_ in zip(mine, seg_p):  # areas follow the header
+            assert m[3:3 + p_["masks"].shape[0]].tolist() == p_["masks"].reshape(p_["masks"].shape[0], -1).sum(1).tolist()
+        ms.sync()
+        assert len(ms.detection_mask) == 5 == len(ms.groundtruth_mask) == len(ms.detection_scores) and len(ms.detection_box) == 0
+        heads = [m[:3].tolist() for m in ms.detection_mask]
+        assert heads == [[2, 9, 11], [2, 9, 11], [3, 33, 40], [3, 33, 40], [4, 5, 5]]  # images interleaved rank by rank
+        for pos, (r, i) in enumerate(order):
+            if r == rank:
+                assert torch.equal(ms.detection_mask[pos], mine[i]) and torch.equal(ms.detection_scores[pos], seg_p[i]["scores"])
+            assert ms.detection_mask[pos].dtype == torch.int32 and ms.groundtruth_mask[pos][0] == i
+        ms.unsync()
+        assert len(ms.detection_mask) == n_mine and all(torch.equal(a, b) for a, b in zip(ms.detection_mask, mine))
+    finally:
+        native.mask_pack_bits = real_pack
     dist.barrier()
     _sharded_curve_choreography(rank)
     dist.barrier()

@@ -171,6 +171,17 @@ def test_every_kernel_wrapper_calls_the_abi_as_declared(monkeypatch):
                                            torch.zeros(4, dtype=torch.long), torch.zeros(4, dtype=torch.uint8), torch.ones(4), [2, 2],
                                            torch.zeros(1, dtype=torch.long), [0.5, 0.75], 100)
     _native.coco_map_accumulate(recs[0], torch.rand(4), recs[1], recs[2], recs[3], npig, 1, 0, 1, 2, [0.0, 0.5, 1.0], [1, 10, 100])
+    # K12: instance masks
+    words, area = _native.mask_pack_bits(torch.rand(4, 5, 7) > 0.5)
+    off = torch.arange(4, dtype=torch.int64) * words.shape[1]
+    img_off = torch.tensor([0, 2, 4], dtype=torch.int32)
+    inter = _native.mask_pair_intersections(words.reshape(-1), off, words.reshape(-1), off, img_off, img_off,
+                                            torch.tensor([2, 2], dtype=torch.int32), torch.zeros(4, dtype=torch.long),
+                                            torch.zeros(4, dtype=torch.long), False, torch.tensor([0, 4]), 8, 4)
+    _native.coco_map_match(boxes, torch.rand(4), torch.zeros(4, dtype=torch.long), [2, 2], boxes, torch.zeros(4, dtype=torch.long),
+                           torch.zeros(4, dtype=torch.uint8), torch.ones(4), [2, 2], torch.zeros(1, dtype=torch.long), [0.5, 0.75], 100,
+                           micro=True, masks={"pair_inter": inter, "pair_off": torch.tensor([0, 4]), "det_area": area.double(),
+                                              "gt_area": area.double()}, gt_area_exact=True)
     assert _native.launch_count() == 0
 
     # (`mb200_regression_num_sums` is a query for C callers; the Python mirror knows the layout of each op's sums)

@@ -57,3 +57,24 @@ def test_against_legacy_in_tree_evaluator(golden_det, name):
     # unstable sort, so ties in scores ("dup") or recall levels sitting on a threshold move a few samples
     for k in ("map", "map_50", "map_75"):
         np.testing.assert_allclose(r[k], golden_det[f"legacy/{name}/{k}"], rtol=2e-2 if name == "dup" else 3e-4)
+
+
+def test_segm_docstring_known_answer():
+    """detection/mean_ap.py:285-340 — the reference's only pinned `iou_type="segm"` value: a 4-pixel prediction and a 4-pixel
+    ground truth sharing 3 pixels (IoU 3/5) match at the IoU thresholds 0.5 and 0.55 -> map = mar = 0.2, map_50 1, map_75 0,
+    everything "small"."""
+    import numpy as np
+
+    from oracle.coco_map import mask_iou
+
+    mask_pred = np.array([[[0, 0, 0, 0, 0], [0, 0, 1, 1, 0], [0, 0, 1, 1, 0], [0, 0, 0, 0, 0], [0, 0, 0, 0, 0]]], bool)
+    mask_tgt = np.array([[[0, 0, 0, 0, 0], [0, 0, 1, 0, 0], [0, 0, 1, 1, 0], [0, 0, 1, 0, 0], [0, 0, 0, 0, 0]]], bool)
+    assert mask_iou(mask_pred, mask_tgt, np.zeros(1)).tolist() == [[0.6]]
+    assert mask_iou(mask_pred, mask_tgt, np.ones(1)).tolist() == [[0.75]]  # crowd: union = the detection's area
+    assert mask_iou(mask_pred, np.zeros_like(mask_tgt), np.zeros(1)).tolist() == [[0.0]]
+    r = coco_evaluate(None, [np.array([0.536])], [np.array([0])], None, [np.array([0])], det_masks=[mask_pred],
+                      gt_masks=[mask_tgt], iou_type="segm")
+    want = dict(map=0.2, map_50=1.0, map_75=0.0, map_large=-1.0, map_medium=-1.0, map_small=0.2, mar_1=0.2, mar_10=0.2,
+                mar_100=0.2, mar_large=-1.0, mar_medium=-1.0, mar_small=0.2)
+    for k, v in want.items():
+        assert abs(float(r[k]) - v) < 1e-6, k
