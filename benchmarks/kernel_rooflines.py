@@ -130,6 +130,43 @@ pm5 = torch.softmax(torch.randn(16384, 1000, generator=g, device=dev), 1)
 tm5 = torch.randint(0, 1000, (16384,), generator=g, device=dev)
 record("K3/K5 curve_evaluate [16384,1000] f32, 1000 segments", timed(lambda: _native.curve_evaluate(pm5, tm5, 1000, unit_range=True), reps=10),
        16384 * 1000 * 15, "same per-record figure as the binary case (5-byte record read, written, scanned)")
+del pm5
+# K12: instance masks, 64 images of 480 x 640 with 100 detections x 20 ground truths each, one class (every pair intersected)
+n_img12, d12, g12, hw12 = 64, 100, 20, 480 * 640
+dm12 = torch.rand(n_img12 * d12, hw12, generator=g, device=dev) > 0.7
+gm12 = torch.rand(n_img12 * g12, hw12, generator=g, device=dev) > 0.7
+record("K12 mask_pack_bits 6400 masks of 480x640 (bool -> 1 bit/pixel + areas)", timed(lambda: _native.mask_pack_bits(dm12), reps=5),
+       dm12.numel() * (1 + 1 / 8), "one read of the byte masks, one write of the bit rows")
+dw12, _ = _native.mask_pack_bits(dm12)
+gw12, _ = _native.mask_pack_bits(gm12)
+del dm12, gm12
+w12 = dw12.shape[1]
+i64 = lambda x: torch.tensor(x, dtype=torch.int64, device=dev)  # noqa: E731
+args12 = (dw12.reshape(-1), torch.arange(n_img12 * d12, device=dev) * w12, gw12.reshape(-1), torch.arange(n_img12 * g12, device=dev) * w12,
+          (torch.arange(n_img12 + 1, device=dev) * d12).int(), (torch.arange(n_img12 + 1, device=dev) * g12).int(),
+          torch.full((n_img12,), w12, dtype=torch.int32, device=dev), torch.zeros(n_img12 * d12, dtype=torch.int64, device=dev),
+          torch.zeros(n_img12 * g12, dtype=torch.int64, device=dev), True, torch.arange(n_img12, device=dev) * (d12 * g12),
+          n_img12 * d12 * g12, d12 * g12)
+record("K12 mask_pair_intersections 64 img x (100 x 20) pairs of 480x640 masks",
+       timed(lambda: _native.mask_pair_intersections(*args12), reps=5), (dw12.numel() + gw12.numel()) * 4,
+       "algorithmic: every bit row read once (the pairs re-read them from L2: 128 000 pairs x 2 x 38.4 KB = 9.8 GB of L2 reads)")
+del dw12, gw12, args12
+# K13: per-row KL divergence, [65536, 1000] f32 probabilities (and the reference's own op chain on the same tensors)
+p13 = torch.rand(65536, 1000, generator=g, device=dev) + 1e-3
+q13 = torch.rand(65536, 1000, generator=g, device=dev) + 1e-3
+record("K13 kl_divergence_rows [65536,1000] f32", timed(lambda: _native.kl_divergence_rows(p13, q13, False), reps=10),
+       2 * p13.numel() * 4, "one read of p and q (the second pass over a row hits L1/L2)")
+
+
+def kld_aten():
+    a = p13 / p13.sum(-1, keepdim=True)
+    b = q13 / q13.sum(-1, keepdim=True)
+    r = a * torch.log(a / b)
+    r[a == 0] = 0.0
+    return r.sum(-1)
+
+
+record("K13 reference op chain in ATen on the same tensors", timed(kld_aten, reps=10), 2 * p13.numel() * 4, "eight passes with [N, d] temporaries")
 print(json.dumps(out, indent=1))
 if len(sys.argv) > 1:
     open(sys.argv[1], "w").write(json.dumps(out, indent=1))

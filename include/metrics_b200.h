@@ -419,6 +419,14 @@ MB200_API int mb200_mask_pair_intersections(const uint32_t* det_words, const int
                                             int micro, const int64_t* pair_off, int64_t n_img, int64_t max_pairs_per_img,
                                             double* inter_out, void* stream);
 
+/* ---- K13: per-row KL divergence (csrc/kldiv.cu) ------------------------------------------------------------------------------
+ * Replaces `_kld_update` (functional/regression/kl_divergence.py:25-46): measures_out[i] = KL(p_i || q_i) for the rows of the
+ * [n, d] distributions `p`, `q` (dtype tag f32/f16/bf16/f64, row-major, same dtype), in the inputs' dtype.  log_prob = 0: both
+ * rows are normalised to sum 1 first and terms with p = 0 count 0 (`_safe_xlogy`, utilities/compute.py:32-44); log_prob = 1:
+ * sum exp(p) * (p - q).  One read of p and q from HBM (the reference chain makes eight passes with [n, d] temporaries). */
+MB200_API int mb200_kl_divergence_rows(const void* p, const void* q, int dtype, int64_t n, int64_t d, int log_prob,
+                                       void* measures_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

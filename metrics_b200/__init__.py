@@ -35,6 +35,7 @@ from metrics_b200.classification import (  # noqa: F401  (reference __init__.py:
 from metrics_b200.regression import (  # noqa: F401  (reference __init__.py:113-134)
     CriticalSuccessIndex,
     ExplainedVariance,
+    KLDivergence,
     LogCoshError,
     MeanAbsoluteError,
     MeanAbsolutePercentageError,

@@ -108,6 +108,7 @@ SIGNATURES = {
     "mb200_coco_map_match": ("i", "pppppppppqqqpqpqqppppppp"),
     "mb200_coco_map_match_ex": ("i", "pppppppppqqqpqipqqppppippppppp"),
     "mb200_mask_pack_bits": ("i", "pqqpqpp"),
+    "mb200_kl_divergence_rows": ("i", "ppiqqipp"),
     "mb200_mask_pair_intersections": ("i", "pppppppppipqqpp"),
     "mb200_coco_map_accumulate": ("i", "pppppqpqqqqpqpqpqppppp"),
     "mb200_binary_stat_counts": ("i", "pipiqqqdiqipppp"),
@@ -680,6 +681,24 @@ def regression_sums(preds: Tensor, target: Tensor, op: int, num_outputs: int = 1
             ctypes.c_double(float(eps)), ptr(out), ptr(scratch), stream_handle(dev),
         )
     check(rc, "regression_sums")
+    return out
+
+
+def kl_divergence_rows(p: Tensor, q: Tensor, log_prob: bool) -> Tensor:
+    """``measures [N]`` = KL(p_i || q_i) per row of the ``[N, d]`` distributions (``mb200_kl_divergence_rows``), in p's dtype."""
+    dev = require_cuda(p, q)
+    if not p.is_floating_point():
+        p = p.float()
+    if q.dtype != p.dtype:
+        q = q.to(p.dtype)
+    p, q = p.contiguous(), q.contiguous()
+    n, d = int(p.shape[0]), int(p.shape[1])
+    out = torch.empty(n, dtype=p.dtype, device=dev)
+    if n:
+        with on_device(dev):
+            rc = lib().mb200_kl_divergence_rows(ptr(p) if d else None, ptr(q) if d else None, tag(p), i64(n), i64(d),
+                                                1 if log_prob else 0, ptr(out), stream_handle(dev))
+        check(rc, "kl_divergence_rows")
     return out
 
 

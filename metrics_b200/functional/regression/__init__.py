@@ -15,12 +15,14 @@ from metrics_b200.functional.regression.metrics import (  # noqa: F401
     weighted_mean_absolute_percentage_error,
 )
 
+from metrics_b200.functional.regression.kl_divergence import kl_divergence  # noqa: F401,E402
+
 # The reference's import paths `<package>.{explained_variance}` are alias submodules that share a name with a function exported
 # above.  Loading a submodule binds it as a package attribute, so load them now and re-bind the functions afterwards: a
 # later `import` of an already-loaded submodule does not touch the attribute again.
 import importlib as _importlib  # noqa: E402
 
-for _name in ("explained_variance",):
+for _name in ("explained_variance", "kl_divergence"):
     _fn = globals()[_name]
     _importlib.import_module(f"{__name__}.{_name}")
     globals()[_name] = _fn

@@ -14,3 +14,4 @@ from metrics_b200.regression.metrics import (  # noqa: F401
     TweedieDevianceScore,
     WeightedMeanAbsolutePercentageError,
 )
+from metrics_b200.regression.kl_divergence import KLDivergence  # noqa: F401,E402

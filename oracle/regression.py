@@ -100,3 +100,27 @@ def tweedie_deviance_score(p, t, power=0.0):  # tweedie_deviance.py:22-143 (doma
                    + p ** (2 - power) / (2 - power))
     return dev.sum() / dev.size
 
+
+
+def kl_divergence_rows(p, q, log_prob=False):  # kl_divergence.py:25-46 (`_kld_update`), fp64 throughout
+    """Per-row KL(p || q).  Probabilities: both rows normalised to sum 1, terms with p = 0 count 0 (`_safe_xlogy`,
+    utilities/compute.py:32-44); log-probabilities: sum exp(p) * (p - q)."""
+    p = np.asarray(p, dtype=np.float64)
+    q = np.asarray(q, dtype=np.float64)
+    if log_prob:
+        return (np.exp(p) * (p - q)).sum(-1)
+    p = p / p.sum(-1, keepdims=True)
+    q = q / q.sum(-1, keepdims=True)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        terms = p * np.log(p / q)
+    terms[p == 0] = 0.0
+    return terms.sum(-1)
+
+
+def kl_divergence(p, q, log_prob=False, reduction="mean"):  # kl_divergence.py:49-78
+    m = kl_divergence_rows(p, q, log_prob)
+    if reduction == "sum":
+        return m.sum()
+    if reduction == "mean":
+        return m.sum() / m.shape[0]
+    return m

@@ -12,6 +12,7 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "raw_abi: drives libmetrics_b200.so directly (deselected when the kernel stand-ins replace the wrappers)")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -148,3 +149,10 @@ def golden_csi():
     import numpy as np
 
     return np.load(os.path.join(GOLDEN_DIR, "csi.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_kld():
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN_DIR, "kld.npz"), allow_pickle=False)

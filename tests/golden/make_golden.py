@@ -1244,6 +1244,43 @@ def csi_golden() -> dict:
     return out
 
 
+def kld_golden() -> dict:
+    """KL divergence (reference functional/regression/kl_divergence.py + regression/kl_divergence.py): per-row measures, the
+    three reductions, probabilities (normalised by the reference) and log-probabilities, zeros in p (xlogy convention), the
+    class after two updates."""
+    from torchmetrics.functional.regression.kl_divergence import _kld_update, kl_divergence
+    from torchmetrics.regression.kl_divergence import KLDivergence
+
+    g = torch.Generator().manual_seed(4711)
+    out = {}
+    case = 0
+    for n, d in ((1, 3), (7, 1), (33, 10), (24, 257), (5, 1000), (120, 40)):
+        for dtype in (torch.float32, torch.float64):
+            for log_prob in (False, True):
+                p = torch.rand(n, d, generator=g, dtype=torch.float64) * 3
+                q = torch.rand(n, d, generator=g, dtype=torch.float64) * 3 + 1e-3
+                if log_prob:
+                    p, q = torch.log_softmax(p, 1), torch.log_softmax(q, 1)
+                else:
+                    p.view(-1)[::7] = 0.0  # xlogy(0, .) = 0
+                p, q = p.to(dtype), q.to(dtype)
+                key = f"case{case}"
+                out[f"{key}/p"], out[f"{key}/q"] = np_of(p), np_of(q)
+                out[f"{key}/meta"] = np.array([int(log_prob), {torch.float32: 0, torch.float64: 1}[dtype]])
+                out[f"{key}/measures"] = _kld_update(p, q, log_prob)[0].numpy()
+                for red in ("mean", "sum", "none"):
+                    out[f"{key}/{red}"] = kl_divergence(p, q, log_prob, red).numpy()
+                    metric = KLDivergence(log_prob=log_prob, reduction=red)
+                    metric.update(p, q)
+                    metric.update(q.abs() if not log_prob else q, p.abs() + 1e-3 if not log_prob else p)
+                    out[f"{key}/class_{red}"] = metric.compute().numpy()
+                case += 1
+    p, q = torch.tensor([[0.36, 0.48, 0.16]]), torch.tensor([[1 / 3, 1 / 3, 1 / 3]])
+    out["doc/value"] = kl_divergence(p, q).numpy()  # docstring: 0.0853
+    out["n_cases"] = np.array(case)
+    return out
+
+
 def curves64_golden() -> dict:
     """float64 scores through the exact curve functionals (the reference sorts them as doubles) and `_binary_clf_curve`
     with `sample_weights` (functional/classification/precision_recall_curve.py:30-82).  Scores are built so that pairs differ
@@ -1339,6 +1376,11 @@ if __name__ == "__main__":
     if "classification" in which:
         data = classification_golden()
         path = os.path.join(HERE, "classification.npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
+    if "kld" in which:
+        data = kld_golden()
+        path = os.path.join(HERE, "kld.npz")
         np.savez_compressed(path, **data)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(data), "arrays")
     if "curves64" in which:

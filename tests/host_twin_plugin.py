@@ -23,6 +23,11 @@ def pytest_collection_modifyitems(config, items):
         module = getattr(item, "module", None)
         if module is not None and isinstance(getattr(module, "DEV", None), str) and module.DEV.startswith("cuda"):
             module.DEV = "cpu"
+    # tests that drive the C-ABI library directly (not through a wrapper that has a stand-in) only make sense on the GPU box
+    raw = [item for item in items if item.get_closest_marker("raw_abi")]
+    if raw:
+        config.hook.pytest_deselected(items=raw)
+        items[:] = [item for item in items if item not in raw]
 
 
 @pytest.fixture(autouse=True)

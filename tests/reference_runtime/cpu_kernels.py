@@ -336,7 +336,7 @@ NAMES = ("launch_count", "multiclass_confmat_update_", "multiclass_stat_scores_u
          "multiclass_stat_scores_topk_update_", "multiclass_stat_scores_samplewise", "argmax_rows",
          "sigmoid_if_logits", "softmax_if_logits", "curve_evaluate", "curve_evaluate_multilabel",
          "binary_stat_counts", "regression_sums", "binned_curve_update", "coco_map_evaluate", "curve_weighted_clf_curve",
-         "multiclass_stats_softmax_update_", "mask_pack_bits")
+         "multiclass_stats_softmax_update_", "mask_pack_bits", "kl_divergence_rows")
 
 
 def mask_pack_bits(masks: Tensor):
@@ -350,6 +350,16 @@ def mask_pack_bits(masks: Tensor):
     packed = (pad.reshape(n, words, 32) << torch.arange(32, dtype=torch.int64)).sum(2)
     packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32)
     return packed, flat.sum(1).to(torch.int64)
+
+
+def kl_divergence_rows(p: Tensor, q: Tensor, log_prob: bool) -> Tensor:
+    """Stand-in for `mb200_kl_divergence_rows`: the op chain of functional/regression/kl_divergence.py:25-46 in torch."""
+    if log_prob:
+        return torch.sum(p.exp() * (p - q), dim=-1)
+    p = p / p.sum(dim=-1, keepdim=True)
+    q = q / q.sum(dim=-1, keepdim=True)
+    res = p * torch.log(p / q)
+    return torch.where(p == 0, torch.zeros_like(res), res).sum(dim=-1)
 
 
 def standins() -> dict:

@@ -229,6 +229,7 @@ def test_label_in_key_path_is_bit_identical_to_the_pair_path(dtype):
                          _native.curve_evaluate(pd, td, c, want_curve=True, unit_range=False))
 
 
+@pytest.mark.raw_abi
 def test_label_in_key_path_refuses_negative_scores():
     """Default mode (unit_range=None) speculates, sees MB200_FLAG_PREDS_RANGE and re-evaluates on the general path; the raw
     `_nonneg` entry raises the flag for a caller that broke its promise (and only then: 1.5 and +inf have 31-bit keys)."""

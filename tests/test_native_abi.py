@@ -171,6 +171,7 @@ def test_every_kernel_wrapper_calls_the_abi_as_declared(monkeypatch):
                                            torch.zeros(4, dtype=torch.long), torch.zeros(4, dtype=torch.uint8), torch.ones(4), [2, 2],
                                            torch.zeros(1, dtype=torch.long), [0.5, 0.75], 100)
     _native.coco_map_accumulate(recs[0], torch.rand(4), recs[1], recs[2], recs[3], npig, 1, 0, 1, 2, [0.0, 0.5, 1.0], [1, 10, 100])
+    _native.kl_divergence_rows(scores, scores + 1.0, False)  # K13
     # K12: instance masks
     words, area = _native.mask_pack_bits(torch.rand(4, 5, 7) > 0.5)
     off = torch.arange(4, dtype=torch.int64) * words.shape[1]
