@@ -1,7 +1,7 @@
 """Run ONE kernel family a few times at a large size, for an ncu capture:
 
     ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 2 -o gpurun_out/prof_<name> \
-        python benchmarks/prof_one.py <name>        # k4 | k1b | k3 | fused | k2 | k6 | cfg5_eval
+        python benchmarks/prof_one.py <name>        # k4 | k1b | k3 | fused | k2 | k6 | cfg5_eval | k12 | k13
 """
 import os
 import sys
@@ -43,11 +43,18 @@ elif name == "fused":
 elif name == "k3":
     p = torch.rand(10_000_000, generator=g, device=dev)
     t = torch.randint(0, 2, (10_000_000,), generator=g, device=dev)
-    fn = lambda: _native.curve_evaluate(p, t, 1)  # noqa: E731
+    fn = lambda: _native.curve_evaluate(p, t, 1, unit_range=True)  # noqa: E731
 elif name == "cfg5_eval":
     p = torch.softmax(torch.randn(16384, 1000, generator=g, device=dev), 1)
     t = torch.randint(0, 1000, (16384,), generator=g, device=dev)
-    fn = lambda: _native.curve_evaluate(p, t, 1000)  # noqa: E731
+    fn = lambda: _native.curve_evaluate(p, t, 1000, unit_range=True)  # noqa: E731
+elif name == "k12":
+    masks = torch.rand(1200, 480 * 640, generator=g, device=dev) > 0.7
+    fn = lambda: _native.mask_pack_bits(masks)  # noqa: E731
+elif name == "k13":
+    p = torch.rand(65536, 1000, generator=g, device=dev) + 1e-3
+    q = torch.rand(65536, 1000, generator=g, device=dev) + 1e-3
+    fn = lambda: _native.kl_divergence_rows(p, q, False)  # noqa: E731
 else:
     raise SystemExit(f"unknown kernel family {name}")
 for _ in range(3):

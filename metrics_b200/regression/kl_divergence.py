@@ -21,8 +21,6 @@ class KLDivergence(Metric):
     full_state_update: bool = False
     plot_lower_bound: float = 0.0
 
-    total: Tensor
-
     def __init__(self, log_prob: bool = False, reduction: Optional[Literal["mean", "sum", "none"]] = "mean", **kwargs: Any) -> None:
         super().__init__(**kwargs)
         if not isinstance(log_prob, bool):
