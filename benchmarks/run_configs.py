@@ -132,10 +132,15 @@ def cfg4(dev):
         for i in range(0, 5000, 100):
             m.update(preds[i:i + 100], target[i:i + 100])
 
-    t0 = time.perf_counter()
-    updates()
+    updates()  # untimed warm-up: the first pass pays one-off costs (first use of the cat / stack kernels, allocator growth)
     torch.cuda.synchronize()
-    upd_wall = time.perf_counter() - t0
+    upd_walls = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        updates()
+        torch.cuda.synchronize()
+        upd_walls.append(time.perf_counter() - t0)
+    upd_wall = min(upd_walls)
     vals = []
     walls = []
     for _ in range(3):
@@ -146,7 +151,7 @@ def cfg4(dev):
         torch.cuda.synchronize()
         walls.append(time.perf_counter() - t0)
         vals.append(float(r["map"]))
-    return {"update_phase_s_wall": upd_wall, "compute_s_wall_min": min(walls), "map": vals[-1],
+    return {"update_phase_s_wall": upd_wall, "update_phase_s_wall_all": upd_walls, "compute_s_wall_min": min(walls), "map": vals[-1],
             "detections_per_s_end_to_end": 500000 / (upd_wall + min(walls)), "images_per_s_end_to_end": 5000 / (upd_wall + min(walls)),
             "note": "reference CPU path not runnable anywhere (pycocotools absent); oracle is a Python restatement, far too slow to time at this size"}
 

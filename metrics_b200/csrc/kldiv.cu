@@ -51,14 +51,17 @@ __global__ void __launch_bounds__(256) kl_rows_kernel(const T* __restrict__ p, c
         const T* __restrict__ qr = q + r * d;
         double acc = 0.0;
         if (log_prob) {
+#pragma unroll 4
             for (int j = lane; j < d; j += 32) {
                 const float a = kl_load<T>(pr, j), b = kl_load<T>(qr, j);
                 acc += (double)(expf(a) * (a - b));
             }
         } else {
             double sp = 0.0, sq = 0.0;
+#pragma unroll 8
             for (int j = lane; j < d; j += 32) sp += (double)kl_load<T>(pr, j), sq += (double)kl_load<T>(qr, j);
             const float fp = (float)warp_sum(sp), fq = (float)warp_sum(sq);
+#pragma unroll 4
             for (int j = lane; j < d; j += 32) {
                 const float a = kl_load<T>(pr, j) / fp, b = kl_load<T>(qr, j) / fq;
                 if (a != 0.f) acc += (double)(a * logf(a / b));  // a NaN `a` takes this branch too, like `res[x == 0] = 0`
