@@ -193,6 +193,12 @@ MB200_API int mb200_curve_evaluate_keys(uint32_t* keys, const void* target, int 
                                         int64_t segments, int64_t first_class, void* workspace, int64_t workspace_bytes,
                                         float* out_auroc, float* out_ap, int64_t* out_counts, uint32_t* err_flag,
                                         void* stream);
+/* mb200_curve_evaluate_keys for keys of non-negative (or NaN) scores (metric states): the label is folded into bit 0 of the key
+ * in place, 4-byte sort records; a key of a negative score raises MB200_FLAG_PREDS_RANGE (see mb200_curve_evaluate_nonneg). */
+MB200_API int mb200_curve_evaluate_keys_nonneg(uint32_t* keys, const void* target, int target_dtype, int64_t n,
+                                        int64_t segments, int64_t first_class, void* workspace, int64_t workspace_bytes,
+                                        float* out_auroc, float* out_ap, int64_t* out_counts, uint32_t* err_flag,
+                                        void* stream);
 MB200_API int mb200_curve_evaluate(const void* preds, int preds_dtype, const void* target, int target_dtype,
                                    int64_t n, int64_t num_classes, int64_t pos_label, void* workspace,
                                    int64_t workspace_bytes, float* out_auroc, float* out_ap, int64_t* out_counts,

@@ -100,6 +100,7 @@ SIGNATURES = {
     "mb200_curve_weighted_clf_curve": ("i", "pipipqqpqpppppp"),
     "mb200_curve_pack_keys": ("i", "piqqpp"),
     "mb200_curve_evaluate_keys": ("i", "ppiqqqpqppppp"),
+    "mb200_curve_evaluate_keys_nonneg": ("i", "ppiqqqpqppppp"),
     "mb200_curve_evaluate": ("i", "pipiqqqpqpppppppp"),
     "mb200_curve_evaluate_nonneg": ("i", "pipiqqqpqpppppppp"),
     "mb200_curve_evaluate_multilabel": ("i", "pipiqqiqpqpppppppp"),
@@ -812,8 +813,10 @@ def curve_pack_keys(preds: Tensor, rows_out: Optional[int] = None) -> Tensor:
     return keys
 
 
-def curve_evaluate_keys(keys: Tensor, target: Tensor, first_class: int):
-    """Sort + scan of packed keys ``[S, n]`` (sorted in place); positives of row ``s`` are ``target == first_class + s``."""
+def curve_evaluate_keys(keys: Tensor, target: Tensor, first_class: int, nonneg: bool = False):
+    """Sort + scan of packed keys ``[S, n]`` (sorted in place); positives of row ``s`` are ``target == first_class + s``.
+    ``nonneg``: the keys come from non-negative (or NaN) scores — metric states — and sort as 4-byte records with the label in
+    bit 0 (``mb200_curve_evaluate_keys_nonneg``)."""
     dev = require_cuda(keys, target)
     assert keys.is_contiguous() and keys.dtype == torch.int32
     target = target.contiguous()
@@ -825,7 +828,7 @@ def curve_evaluate_keys(keys: Tensor, target: Tensor, first_class: int):
     ap = torch.empty(s, dtype=torch.float32, device=dev)
     counts = torch.empty((s, 3), dtype=torch.int64, device=dev)
     with on_device(dev):
-        rc = lib_.mb200_curve_evaluate_keys(
+        rc = (lib_.mb200_curve_evaluate_keys_nonneg if nonneg else lib_.mb200_curve_evaluate_keys)(
             ptr(keys), ptr(target), tag(target), i64(n), i64(s), i64(first_class), ptr(ws), i64(nbytes), ptr(auroc), ptr(ap),
             ptr(counts), ptr(None), stream_handle(dev),
         )

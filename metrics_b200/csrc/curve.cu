@@ -535,6 +535,22 @@ __global__ void __launch_bounds__(256) labels_from_target_kernel(const void* __r
     }
 }
 
+// keys[s][i] = (keys[s][i] << 1) | (target[i] == first_class + s)   — packed keys of non-negative scores (31 bits), in place
+__global__ void __launch_bounds__(256) fold_labels_into_keys_kernel(unsigned* __restrict__ keys, const void* __restrict__ target,
+                                                                    int tdtype, int n, int segments, long long first_class,
+                                                                    unsigned* __restrict__ err) {
+    const long long total = (long long)n * segments;
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(i / n);
+        const int k = (int)(i - (long long)s * n);
+        const unsigned key = keys[i];
+        bad |= (key >> 31) != 0;
+        keys[i] = (key << 1) | (unsigned)(load_label(target, tdtype, k) == first_class + s);
+    }
+    if (bad && err) atomicOr(err, MB200_FLAG_PREDS_RANGE);
+}
+
 // =====================================================================================================
 // tie-collapsing TP/FP scan over sorted (key, label): scan_chained_kernel below (tile states, look-back, apply) and the two
 // finalize kernels that fold the per-tile AP partials in tile order.
@@ -1340,6 +1356,25 @@ extern "C" int mb200_curve_evaluate_keys(uint32_t* keys, const void* target, int
     count_launch();
     return sort_and_scan<unsigned>(keys, w.lab_a, w, (int)n, segments, n, nullptr, out_auroc, out_ap, out_counts, nullptr, nullptr,
                                    nullptr, err_flag, st);
+}
+
+// mb200_curve_evaluate_keys for keys of non-negative (or NaN) scores — the class-sharded exchange of metric states: the label is
+// folded into bit 0 of the key in place and the sort moves 4-byte records (see mb200_curve_evaluate_nonneg).
+extern "C" int mb200_curve_evaluate_keys_nonneg(uint32_t* keys, const void* target, int target_dtype, int64_t n,
+                                                int64_t segments, int64_t first_class, void* workspace, int64_t workspace_bytes,
+                                                float* out_auroc, float* out_ap, int64_t* out_counts, uint32_t* err_flag,
+                                                void* stream) {
+    MB200_REQUIRE(n >= 1 && n < (1ll << 30) && segments >= 1 && segments <= 65535, "bad sizes");
+    MB200_REQUIRE(keys && target && workspace && out_auroc && out_ap && out_counts, "NULL pointer");
+    MB200_REQUIRE(workspace_bytes >= mb200_curve_workspace_bytes(segments, n), "workspace too small");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CurveWs<unsigned> w = carve<unsigned>(workspace, segments, n);
+    const long long total = n * segments;
+    fold_labels_into_keys_kernel<<<blocks_for(total, 256 * 8, sm_count() * 8), 256, 0, st>>>(keys, target, target_dtype, (int)n,
+                                                                                             (int)segments, first_class, err_flag);
+    count_launch();
+    return sort_and_scan<unsigned>(keys, w.lab_a, w, (int)n, segments, n, nullptr, out_auroc, out_ap, out_counts, nullptr, nullptr,
+                                   nullptr, err_flag, st, true);
 }
 
 namespace {

@@ -110,7 +110,7 @@ def ovr_curve_scalars_sharded(preds: Optional[Tensor], target: Optional[Tensor],
         off_e += cpr * n
         off_n += n
 
-    auroc, ap, counts = _native.curve_evaluate_keys(keys_mine, tgt_all, first_class=rank * cpr)
+    auroc, ap, counts = _native.curve_evaluate_keys(keys_mine, tgt_all, first_class=rank * cpr, nonneg=True)  # metric states: post-format scores
     # per-class results of every rank
     packed = torch.cat([auroc.double().unsqueeze(1), ap.double().unsqueeze(1), counts.double()], dim=1).contiguous()  # [cpr, 5]
     gathered = _gather_equal(packed, group, world).reshape(world * cpr, 5)[:num_classes]
@@ -151,7 +151,7 @@ def _exchange_over_peer_memory(ws: Any, preds: Tensor, target: Tensor, num_class
     ws.barrier()
     keys_mine = ws.view(keys_off, (cpr, n_total), torch.int32)
     tgt_all = ws.view(tgt_off, (n_total,), torch.int64)
-    auroc, ap, counts = _native.curve_evaluate_keys(keys_mine, tgt_all, first_class=rank * cpr)
+    auroc, ap, counts = _native.curve_evaluate_keys(keys_mine, tgt_all, first_class=rank * cpr, nonneg=True)  # metric states: post-format scores
     packed = torch.cat([auroc.double().unsqueeze(1), ap.double().unsqueeze(1), counts.double()], dim=1).contiguous()  # [cpr, 5]
     ws.put_all(packed, res_off + rank * cpr * 5 * 8)
     ws.barrier()

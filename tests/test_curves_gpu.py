@@ -299,3 +299,20 @@ def test_chained_scan_long_tie_runs(unit):
         np.testing.assert_array_equal(fps[c, :u].cpu().numpy().astype(np.int64), rf)
         np.testing.assert_array_equal(tps[c, :u].cpu().numpy().astype(np.int64), rt)
         np.testing.assert_allclose(float(auroc[c]), oc.binary_auroc_exact(p[:, c].numpy(), (t == c).long().numpy()), rtol=2e-7, atol=1e-7)
+
+
+@pytest.mark.raw_abi
+def test_evaluate_keys_label_in_key_path_matches_the_pair_path():
+    """`mb200_curve_evaluate_keys_nonneg` (the class-sharded exchange of metric states) against `mb200_curve_evaluate_keys`:
+    same packed keys, same targets -> bit-identical scalars and counts, for class offsets and ragged sizes."""
+    from metrics_b200 import _native
+
+    g = torch.Generator().manual_seed(77)
+    for n, c, first in ((1, 2, 0), (4097, 5, 0), (20000, 7, 3), (333, 40, 10)):
+        p = torch.softmax(torch.randn(n, c, generator=g) * 2, 1).to(DEV)
+        p[::9, 0] = float("nan")
+        t = torch.randint(0, c + first, (n,), generator=g).to(DEV)
+        a = _native.curve_evaluate_keys(_native.curve_pack_keys(p), t, first)
+        b = _native.curve_evaluate_keys(_native.curve_pack_keys(p), t, first, nonneg=True)
+        for x, y in zip(a, b):
+            assert torch.equal(x.view(torch.int32) if x.dtype == torch.float32 else x, y.view(torch.int32) if y.dtype == torch.float32 else y)

@@ -240,7 +240,7 @@ def _sharded_curve_choreography(rank: int) -> None:
         keys[:c] = to_key(preds.float().T.contiguous())
         return keys
 
-    def evaluate_keys(keys, target, first_class):
+    def evaluate_keys(keys, target, first_class, nonneg=False):
         s, n = keys.shape
         au, ap, cnt = np.zeros(s, np.float32), np.zeros(s, np.float32), np.zeros((s, 3), np.int64)
         for j in range(s):

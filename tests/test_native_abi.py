@@ -148,6 +148,7 @@ def test_every_kernel_wrapper_calls_the_abi_as_declared(monkeypatch):
     _native.curve_evaluate(scores, labels, c, unit_range=False)
     keys = _native.curve_pack_keys(scores, c)
     _native.curve_evaluate_keys(keys, labels, 0)
+    _native.curve_evaluate_keys(keys, labels, 0, nonneg=True)
     _native.curve_evaluate_multilabel(scores, torch.randint(2, (n, c)), c, ignore_index=-1, want_curve=True)
     _native.binary_stat_counts(scores, torch.randint(2, (n, c)), c, 0.5, None, False, None, flag)
     _native.binary_stat_counts(scores[:, 0], torch.randint(2, (n,)), 1, 0.5, 0, True)
