@@ -419,6 +419,10 @@ MB200_API int mb200_peer_reduce_put_i64(void* const* peer_bases, int64_t in_offs
  *   (unless micro) are written as 0 — the matcher never reads them.  max_pairs_per_img only sizes the grid. */
 MB200_API int mb200_mask_pack_bits(const uint8_t* masks, int64_t n_masks, int64_t pixels_per_mask, uint32_t* words_out,
                                    int64_t out_stride_words, int64_t* area_out, void* stream);
+/* The same packing straight into the per-image state entry of MeanAveragePrecision (one call per image and side at update()):
+ * entry_out int32 [3 + n + n * ceil(H*W/32)] = [n, H, W, area_0 .. area_{n-1}, bit rows of the n masks]. */
+MB200_API int mb200_mask_pack_entry(const uint8_t* masks, int64_t n_masks, int64_t height, int64_t width, int32_t* entry_out,
+                                    void* stream);
 MB200_API int mb200_mask_pair_intersections(const uint32_t* det_words, const int64_t* det_word_off, const uint32_t* gt_words,
                                             const int64_t* gt_word_off, const int32_t* det_off, const int32_t* gt_off,
                                             const int32_t* img_words, const int64_t* det_label, const int64_t* gt_label,

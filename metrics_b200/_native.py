@@ -109,6 +109,7 @@ SIGNATURES = {
     "mb200_coco_map_match": ("i", "pppppppppqqqpqpqqppppppp"),
     "mb200_coco_map_match_ex": ("i", "pppppppppqqqpqipqqppppippppppp"),
     "mb200_mask_pack_bits": ("i", "pqqpqpp"),
+    "mb200_mask_pack_entry": ("i", "pqqqpp"),
     "mb200_kl_divergence_rows": ("i", "ppiqqipp"),
     "mb200_mask_pair_intersections": ("i", "pppppppppipqqpp"),
     "mb200_coco_map_accumulate": ("i", "pppppqpqqqqpqpqpqppppp"),
@@ -523,6 +524,21 @@ def mask_pack_bits(masks: Tensor):
                                             area.data_ptr(), stream_handle(dev))
         check(rc, "mask_pack_bits")
     return out, area
+
+
+def mask_pack_entry(masks: Tensor) -> Tensor:
+    """``mb200_mask_pack_entry``: boolean / uint8 masks ``[n, H, W]`` -> the int32 state entry ``[n, H, W, areas.., bit rows..]``."""
+    dev = require_cuda(masks)
+    if masks.dtype not in (torch.bool, torch.uint8):
+        masks = masks != 0
+    masks = masks.contiguous()
+    n, h, w = (int(x) for x in masks.shape)
+    out = torch.empty(3 + n + n * ((h * w + 31) // 32), dtype=torch.int32, device=dev)
+    with on_device(dev):
+        rc = lib().mb200_mask_pack_entry(masks.view(torch.uint8).data_ptr() if masks.numel() else None, n, h, w, out.data_ptr(),
+                                         stream_handle(dev))
+    check(rc, "mask_pack_entry")
+    return out
 
 
 def mask_pair_intersections(det_words: Tensor, det_word_off: Tensor, gt_words: Tensor, gt_word_off: Tensor, det_off: Tensor,

@@ -28,10 +28,13 @@ __device__ __forceinline__ unsigned nibble_of(unsigned x) {
 // lanes join their halves, even lanes store.  (The first version read one byte per lane and balloted: 32 bytes per warp
 // instruction, 219 GB/s; one 512-pixel piece per step: 3.2 TB/s, latency-bound.)
 constexpr int kPackPieces = 4;
+template <typename AreaT>  // long long: area array of mb200_mask_pack_bits; int: the area slots of a state entry
 __global__ void __launch_bounds__(256) mask_pack_bits_kernel(const unsigned char* __restrict__ masks, long long n_masks,
                                                              long long hw, long long words, unsigned* __restrict__ out,
-                                                             long long out_stride, long long* __restrict__ area) {
+                                                             long long out_stride, AreaT* __restrict__ area, int* __restrict__ header,
+                                                             int h0, int h1, int h2) {
     const int lane = threadIdx.x & 31;
+    if (header && blockIdx.x == 0 && threadIdx.x == 0) header[0] = h0, header[1] = h1, header[2] = h2;
     const long long chunks = (hw + 512 * kPackPieces - 1) / (512 * kPackPieces);  // per mask
     const long long total = n_masks * chunks;
     const long long wstep = (long long)gridDim.x * (blockDim.x >> 5);
@@ -65,7 +68,10 @@ __global__ void __launch_bounds__(256) mask_pack_bits_kernel(const unsigned char
             cnt += (unsigned)__popc(bits[q]);
         }
         cnt = __reduce_add_sync(kFull, cnt);
-        if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long*>(area + m), (unsigned long long)cnt);
+        if (lane == 0 && cnt) {
+            if constexpr (sizeof(AreaT) == 8) atomicAdd(reinterpret_cast<unsigned long long*>(area + m), (unsigned long long)cnt);
+            else atomicAdd(reinterpret_cast<unsigned*>(area + m), cnt);
+        }
     }
 }
 
@@ -160,10 +166,33 @@ extern "C" int mb200_mask_pack_bits(const uint8_t* masks, int64_t n_masks, int64
     long long grid = (n_masks * ((pixels_per_mask + 512 * kPackPieces - 1) / (512 * kPackPieces)) + 7) / 8;
     const long long cap = (long long)sm_count() * 8;
     if (grid > cap) grid = cap;
-    mask_pack_bits_kernel<<<(unsigned)grid, 256, 0, st>>>(masks, n_masks, pixels_per_mask, words, words_out, out_stride_words,
-                                                         reinterpret_cast<long long*>(area_out));
+    mask_pack_bits_kernel<long long><<<(unsigned)grid, 256, 0, st>>>(masks, n_masks, pixels_per_mask, words, words_out,
+                                                                    out_stride_words, reinterpret_cast<long long*>(area_out),
+                                                                    nullptr, 0, 0, 0);
     count_launch();
     return check_cuda(cudaGetLastError(), "mask pack launch");
+}
+
+// The per-image state entry of MeanAveragePrecision (detection/mean_ap.py `_mask_state`) in one call:
+// entry_out int32 [3 + n + n * ceil(H*W/32)] = [n, H, W, area_0 .. area_{n-1}, bit rows].
+extern "C" int mb200_mask_pack_entry(const uint8_t* masks, int64_t n_masks, int64_t height, int64_t width, int32_t* entry_out,
+                                     void* stream) {
+    MB200_REQUIRE(n_masks >= 0 && n_masks < (1ll << 31) && height >= 0 && width >= 0 && height < (1ll << 31) && width < (1ll << 31) &&
+                      height * width < (1ll << 31),
+                  "bad sizes");
+    MB200_REQUIRE(entry_out && (n_masks == 0 || height * width == 0 || masks), "NULL pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t hw = height * width, words = (hw + 31) / 32;
+    MB200_CUDA_OK(cudaMemsetAsync(entry_out, 0, (size_t)(3 + n_masks) * 4, st));  // areas are accumulated with atomics
+    long long grid = (n_masks * ((hw + 512 * kPackPieces - 1) / (512 * kPackPieces)) + 7) / 8;
+    const long long cap = (long long)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;  // the header is written even for an image without masks
+    mask_pack_bits_kernel<int><<<(unsigned)grid, 256, 0, st>>>(masks, n_masks, hw, words,
+                                                              reinterpret_cast<unsigned*>(entry_out + 3 + n_masks), words,
+                                                              entry_out + 3, entry_out, (int)n_masks, (int)height, (int)width);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "mask entry launch");
 }
 
 extern "C" int mb200_mask_pair_intersections(const uint32_t* det_words, const int64_t* det_word_off, const uint32_t* gt_words,

@@ -248,13 +248,10 @@ class MeanAveragePrecision(Metric):
     # ------------------------------------------------------------------------------------------------
     def _mask_state(self, masks: Tensor) -> Tensor:
         """``[n, H, W]`` boolean masks -> the image's state entry: int32 ``[n, H, W, area_0..area_{n-1}, bit words (n rows of
-        ceil(H*W/32), pixel order)]`` on the metric's device (`mb200_mask_pack_bits`)."""
+        ceil(H*W/32), pixel order)]`` on the metric's device (`mb200_mask_pack_entry`)."""
         if masks.ndim != 3:
             raise ValueError(f"Expected `masks` of shape (num_masks, height, width) but got {tuple(masks.shape)}")
-        n, h, w = (int(x) for x in masks.shape)
-        words, area = _native.mask_pack_bits(masks.to(self.device))
-        head = torch.tensor([n, h, w], dtype=torch.int32).to(words.device, non_blocking=True)
-        return torch.cat([head, area.to(torch.int32), words.reshape(-1)])
+        return _native.mask_pack_entry(masks.to(self.device))  # one memset + one launch, no host -> device copy
 
     def _mask_tables(self, det_label: Tensor, gt_label: Tensor, det_counts: List[int], gt_counts: List[int],
                      micro: bool) -> Dict[str, Tensor]:

@@ -336,7 +336,7 @@ NAMES = ("launch_count", "multiclass_confmat_update_", "multiclass_stat_scores_u
          "multiclass_stat_scores_topk_update_", "multiclass_stat_scores_samplewise", "argmax_rows",
          "sigmoid_if_logits", "softmax_if_logits", "curve_evaluate", "curve_evaluate_multilabel",
          "binary_stat_counts", "regression_sums", "binned_curve_update", "coco_map_evaluate", "curve_weighted_clf_curve",
-         "multiclass_stats_softmax_update_", "mask_pack_bits", "kl_divergence_rows")
+         "multiclass_stats_softmax_update_", "mask_pack_bits", "mask_pack_entry", "kl_divergence_rows")
 
 
 def mask_pack_bits(masks: Tensor):
@@ -350,6 +350,13 @@ def mask_pack_bits(masks: Tensor):
     packed = (pad.reshape(n, words, 32) << torch.arange(32, dtype=torch.int64)).sum(2)
     packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32)
     return packed, flat.sum(1).to(torch.int64)
+
+
+def mask_pack_entry(masks: Tensor) -> Tensor:
+    """Stand-in for `mb200_mask_pack_entry`: int32 [n, H, W, areas.., bit rows..]."""
+    n, h, w = (int(x) for x in masks.shape)
+    words, area = mask_pack_bits(masks)
+    return torch.cat([torch.tensor([n, h, w], dtype=torch.int32), area.to(torch.int32), words.reshape(-1)])
 
 
 def kl_divergence_rows(p: Tensor, q: Tensor, log_prob: bool) -> Tensor:

@@ -181,8 +181,8 @@ def _scenarios(rank: int) -> None:
     import metrics_b200._native as native
     from tests.reference_runtime import cpu_kernels
 
-    real_pack = native.mask_pack_bits
-    native.mask_pack_bits = cpu_kernels.mask_pack_bits  # the kernel's stand-in: this scenario is about the exchange
+    real_pack = native.mask_pack_entry
+    native.mask_pack_entry = cpu_kernels.mask_pack_entry  # the kernel's stand-in: this scenario is about the exchange
     try:
         g = torch.Generator().manual_seed(70 + rank)
         sizes = [(9, 11), (33, 40), (5, 5)][: n_mine]
@@ -208,7 +208,7 @@ def _scenarios(rank: int) -> None:
         ms.unsync()
         assert len(ms.detection_mask) == n_mine and all(torch.equal(a, b) for a, b in zip(ms.detection_mask, mine))
     finally:
-        native.mask_pack_bits = real_pack
+        native.mask_pack_entry = real_pack
     dist.barrier()
     _sharded_curve_choreography(rank)
     dist.barrier()

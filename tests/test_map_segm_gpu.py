@@ -143,6 +143,12 @@ def test_pack_and_pair_kernels_vs_numpy():
         pad[:, : h * w] = flat
         want = (pad.reshape(6, nw, 32) * (1 << np.arange(32, dtype=np.uint64))).sum(2).astype(np.uint32)
         np.testing.assert_array_equal(words.cpu().numpy().view(np.uint32), want)
+        entry = _native.mask_pack_entry(m.to(DEV)).cpu()  # the metric's state entry: [n, H, W, areas, bit rows] in one call
+        assert entry.dtype == torch.int32 and entry[:3].tolist() == [6, h, w] and entry[3:9].tolist() == area.cpu().tolist()
+        np.testing.assert_array_equal(entry[9:].numpy().view(np.uint32).reshape(6, nw), want)
+        assert _native.mask_pack_entry(m[:0].to(DEV)).cpu().tolist() == [0, h, w]
+        as_bytes = (m.to(torch.uint8) * 7).to(DEV)  # any non-zero byte counts as set
+        assert torch.equal(_native.mask_pack_entry(as_bytes).cpu(), entry)
         # two "images": masks 0-2 vs 3-5 (all pairs) and 3-5 vs 0-2, labels filter half of the pairs
         off = (torch.arange(6, dtype=torch.int64) * nw).to(DEV)
         lab = torch.tensor([0, 1, 0, 0, 0, 1], device=DEV)

@@ -175,6 +175,7 @@ def test_every_kernel_wrapper_calls_the_abi_as_declared(monkeypatch):
     _native.kl_divergence_rows(scores, scores + 1.0, False)  # K13
     # K12: instance masks
     words, area = _native.mask_pack_bits(torch.rand(4, 5, 7) > 0.5)
+    _native.mask_pack_entry(torch.rand(4, 5, 7) > 0.5)
     off = torch.arange(4, dtype=torch.int64) * words.shape[1]
     img_off = torch.tensor([0, 2, 4], dtype=torch.int32)
     inter = _native.mask_pair_intersections(words.reshape(-1), off, words.reshape(-1), off, img_off, img_off,
