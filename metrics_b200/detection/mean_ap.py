@@ -11,7 +11,7 @@ pycocotools intersects the codes pair by pair on the host at ``compute``.  Here 
 on the device (`mb200_mask_pack_bits`; the state entry of an image is ONE int32 tensor ``[n, H, W, areas.., bit words..]``),
 ``compute`` builds every image's [detections x ground truths] table of intersection pixel counts with one launch
 (`mb200_mask_pair_intersections`) and the matching kernel reads IoUs from it (`mb200_coco_map_match_ex`).  COCO json of masks
-(``coco_to_tm`` / ``tm_to_coco`` with segm) is not implemented.
+(``coco_to_tm`` / ``tm_to_coco`` with segm): run-length codes, host side (detection/rle.py); polygons are not supported.
 """
 from __future__ import annotations
 
@@ -250,7 +250,9 @@ class MeanAveragePrecision(Metric):
         """``[n, H, W]`` boolean masks -> the image's state entry: int32 ``[n, H, W, area_0..area_{n-1}, bit words (n rows of
         ceil(H*W/32), pixel order)]`` on the metric's device (`mb200_mask_pack_entry`)."""
         if masks.ndim != 3:
-            raise ValueError(f"Expected `masks` of shape (num_masks, height, width) but got {tuple(masks.shape)}")
+            if masks.numel() != 0:
+                raise ValueError(f"Expected `masks` of shape (num_masks, height, width) but got {tuple(masks.shape)}")
+            masks = masks.reshape(0, 0, 0)  # e.g. `coco_to_tm` of an image without detections
         return _native.mask_pack_entry(masks.to(self.device))  # one memset + one launch, no host -> device copy
 
     def _mask_tables(self, det_label: Tensor, gt_label: Tensor, det_counts: List[int], gt_counts: List[int],
@@ -398,12 +400,13 @@ class MeanAveragePrecision(Metric):
         """COCO ground-truth json (``{"annotations": [...], ...}``) + COCO results json (a list of detections) -> the
         ``(preds, target)`` lists ``update`` takes (reference :651-760).  The files are read directly — the reference goes
         through ``pycocotools.COCO(...).loadRes`` only to get the same annotation lists back.  One entry per image that
-        has at least one ground-truth annotation, in order of first appearance; boxes stay in the files' xywh format."""
+        has at least one ground-truth annotation, in order of first appearance; boxes stay in the files' xywh format.
+        With "segm", run-length coded segmentations (compressed strings or count lists) become uint8 ``masks``
+        (metrics_b200/detection/rle.py); polygon segmentations need pycocotools' rasteriser and raise."""
         kinds = (iou_type,) if isinstance(iou_type, str) else tuple(iou_type)
         if any(k not in ("bbox", "segm") for k in kinds):
             raise ValueError(f"Expected argument `iou_type` to be one of ('bbox', 'segm') or a tuple of, but got {iou_type}")
-        if kinds != ("bbox",):
-            raise NotImplementedError("metrics_b200: only `iou_type='bbox'` is implemented (mask IoU is out of scope)")
+        boxes, masks = "bbox" in kinds, "segm" in kinds
         with open(coco_target) as fh:
             gt_file = json.load(fh)
         with open(coco_preds) as fh:
@@ -416,31 +419,53 @@ class MeanAveragePrecision(Metric):
         if any(d["image_id"] not in known_images for d in dt_file):
             raise ValueError("Results do not correspond to current coco set")
 
+        import numpy as np
+
+        from metrics_b200.detection.rle import segmentation_to_mask
+
+        sizes = {img["id"]: (int(img.get("height", 0)), int(img.get("width", 0))) for img in gt_file.get("images", [])}
+
+        def mask_of(ann: dict):  # pycocotools `annToMask` for run-length coded segmentations (reference :710, :726)
+            return segmentation_to_mask(ann["segmentation"], *sizes.get(ann["image_id"], (0, 0)))
+
         per_image: Dict[Any, Dict[str, list]] = {}
         for ann in gt_file["annotations"]:
-            slot = per_image.setdefault(ann["image_id"], {"g_boxes": [], "g_labels": [], "g_crowd": [], "g_area": [],
-                                                          "d_boxes": [], "d_labels": [], "d_scores": []})
-            slot["g_boxes"].append(ann["bbox"])
+            slot = per_image.setdefault(ann["image_id"], {"g_boxes": [], "g_masks": [], "g_labels": [], "g_crowd": [], "g_area": [],
+                                                          "d_boxes": [], "d_masks": [], "d_labels": [], "d_scores": []})
+            if boxes:
+                slot["g_boxes"].append(ann["bbox"])
+            if masks:
+                slot["g_masks"].append(mask_of(ann))
             slot["g_labels"].append(ann["category_id"])
             slot["g_crowd"].append(ann["iscrowd"])
             slot["g_area"].append(ann["area"])
         for det in dt_file:
             slot = per_image.get(det["image_id"])
             if slot is not None:  # detections on images without ground truth are not evaluated (reference :736)
-                slot["d_boxes"].append(det["bbox"])
+                if boxes:
+                    slot["d_boxes"].append(det["bbox"])
+                if masks:
+                    slot["d_masks"].append(mask_of(det))
                 slot["d_labels"].append(det["category_id"])
                 slot["d_scores"].append(det["score"])
-        preds = [{"scores": torch.tensor(s["d_scores"], dtype=torch.float32),
-                  "labels": torch.tensor(s["d_labels"], dtype=torch.int32),
-                  "boxes": torch.tensor(s["d_boxes"], dtype=torch.float32)} for s in per_image.values()]
-        target = [{"labels": torch.tensor(s["g_labels"], dtype=torch.int32),
-                   "iscrowd": torch.tensor(s["g_crowd"], dtype=torch.int32),
-                   "area": torch.tensor(s["g_area"], dtype=torch.float32),
-                   "boxes": torch.tensor(s["g_boxes"], dtype=torch.float32)} for s in per_image.values()]
+        preds, target = [], []
+        for s in per_image.values():
+            p = {"scores": torch.tensor(s["d_scores"], dtype=torch.float32), "labels": torch.tensor(s["d_labels"], dtype=torch.int32)}
+            t = {"labels": torch.tensor(s["g_labels"], dtype=torch.int32), "iscrowd": torch.tensor(s["g_crowd"], dtype=torch.int32),
+                 "area": torch.tensor(s["g_area"], dtype=torch.float32)}
+            if boxes:
+                p["boxes"] = torch.tensor(s["d_boxes"], dtype=torch.float32)
+                t["boxes"] = torch.tensor(s["g_boxes"], dtype=torch.float32)
+            if masks:  # uint8 [n, H, W] like the reference (:746, :757); an image without detections gets an empty tensor
+                p["masks"] = torch.tensor(np.array(s["d_masks"]), dtype=torch.uint8)
+                t["masks"] = torch.tensor(np.array(s["g_masks"]), dtype=torch.uint8)
+            preds.append(p)
+            target.append(t)
         return preds, target
 
-    def _coco_dataset(self, labels: List[Tensor], boxes: List[Tensor], scores: Optional[List[Tensor]] = None,
-                      crowds: Optional[List[Tensor]] = None, area: Optional[List[Tensor]] = None) -> Dict[str, list]:
+    def _coco_dataset(self, labels: List[Tensor], boxes: Optional[List[Tensor]], scores: Optional[List[Tensor]] = None,
+                      crowds: Optional[List[Tensor]] = None, area: Optional[List[Tensor]] = None,
+                      masks: Optional[List[Tensor]] = None) -> Dict[str, list]:
         """The cached per-image states as one COCO dataset dict (reference :867-958, bbox): annotation ids start at 1,
         image ids are the positions in the state lists, ``area`` falls back to ``w * h`` when missing or not positive.
         Every state kind is brought to the host with ONE copy (the reference does one per image and per annotation)."""
@@ -452,23 +477,44 @@ class MeanAveragePrecision(Metric):
             kept = [t.reshape(-1, width) if width > 1 else t.reshape(-1) for t in items if t.numel() > 0]
             return torch.cat(kept).cpu().tolist() if kept else []
 
-        for image_id, (lab, box) in enumerate(zip(labels, boxes)):
+        for image_id, (lab, box) in enumerate(zip(labels, boxes or [])):
             if box.numel() != 4 * lab.numel():
                 raise ValueError(f"Invalid input box of sample {image_id}, element 0 (expected 4 values, got"
                                  f" {box.numel() // max(1, lab.numel())})")
         flat_labels, flat_boxes = host(labels), host(boxes, 4)
         flat_scores, flat_crowds, flat_area = host(scores), host(crowds), host(area)
+        images = [{"id": i} for i in range(len(counts))]
+        codes: Optional[list] = None
+        if masks is not None:  # run-length codes of the bit-packed masks, on the host (reference :897-905, :943-944)
+            from metrics_b200.detection.rle import counts_to_string, entry_to_masks, mask_to_counts
+
+            codes = []
+            for image_id, entry in enumerate(masks):
+                decoded = entry_to_masks(entry.cpu().numpy())
+                if decoded.shape[0]:
+                    images[image_id]["height"], images[image_id]["width"] = int(decoded.shape[1]), int(decoded.shape[2])
+                for m in decoded:
+                    codes.append(({"size": [int(m.shape[0]), int(m.shape[1])], "counts": counts_to_string(mask_to_counts(m))},
+                                  int(m.sum())))
         annotations = []
         k = 0
         for image_id, count in enumerate(counts):
             for j in range(count):
-                label, box = flat_labels[k], flat_boxes[k]
+                label = flat_labels[k]
+                box = flat_boxes[k] if flat_boxes is not None else None
                 if not isinstance(label, int):
                     raise ValueError(f"Invalid input class of sample {image_id}, element {j}"
                                      f" (expected value of type integer, got type {type(label)})")
                 given = flat_area[k] if flat_area is not None else 0
-                ann = {"id": k + 1, "image_id": image_id, "area": given if given > 0 else box[2] * box[3],
-                       "category_id": label, "iscrowd": flat_crowds[k] if flat_crowds is not None else 0, "bbox": box}
+                computed = codes[k][1] if codes is not None else box[2] * box[3]  # mask area as soon as "segm" is in (:923-925)
+                ann = {"id": k + 1, "image_id": image_id, "area": given if given > 0 else computed,
+                       "category_id": label, "iscrowd": flat_crowds[k] if flat_crowds is not None else 0}
+                if box is not None:
+                    ann["bbox"] = box
+                if codes is not None:
+                    ann["segmentation"] = codes[k][0]
+                    if box is not None:  # both IoU types: the reference keeps both areas (:926-939)
+                        ann["area_bbox"], ann["area_segm"] = box[2] * box[3], codes[k][1]
                 if flat_scores is not None:
                     if not isinstance(flat_scores[k], float):
                         raise ValueError(f"Invalid input score of sample {image_id}, element {j}"
@@ -476,17 +522,19 @@ class MeanAveragePrecision(Metric):
                     ann["score"] = flat_scores[k]
                 annotations.append(ann)
                 k += 1
-        return {"images": [{"id": i} for i in range(len(counts))], "annotations": annotations,
+        return {"images": images, "annotations": annotations,
                 "categories": [{"id": c, "name": str(c)} for c in self._get_classes()]}
 
     def tm_to_coco(self, name: str = "tm_map_input") -> None:
         """Write everything ``update`` has cached as ``{name}_preds.json`` (the COCO results list) and
-        ``{name}_target.json`` (the COCO ground-truth dataset), reference :762-825."""
-        if "segm" in self.iou_type:
-            raise NotImplementedError("metrics_b200: COCO json export of instance masks (run-length codes) is not implemented")
-        target = self._coco_dataset(self.groundtruth_labels, self.groundtruth_box, crowds=self.groundtruth_crowds,
-                                    area=self.groundtruth_area)
-        preds = self._coco_dataset(self.detection_labels, self.detection_box, scores=self.detection_scores)
+        ``{name}_target.json`` (the COCO ground-truth dataset), reference :762-825.  Masks are written as compressed run-length
+        codes (metrics_b200/detection/rle.py) — this is an export path: the bit rows are decoded on the host."""
+        with_boxes, with_masks = "bbox" in self.iou_type, "segm" in self.iou_type
+        target = self._coco_dataset(self.groundtruth_labels, self.groundtruth_box if with_boxes else None,
+                                    crowds=self.groundtruth_crowds, area=self.groundtruth_area,
+                                    masks=self.groundtruth_mask if with_masks else None)
+        preds = self._coco_dataset(self.detection_labels, self.detection_box if with_boxes else None, scores=self.detection_scores,
+                                   masks=self.detection_mask if with_masks else None)
         with open(f"{name}_preds.json", "w") as fh:
             fh.write(json.dumps(preds["annotations"], indent=4))
         with open(f"{name}_target.json", "w") as fh:

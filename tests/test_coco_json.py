@@ -91,7 +91,7 @@ def test_coco_to_tm_reads_plain_coco_files(tmp_path):
     (tmp_path / "bad.json").write_text(json.dumps([{"image_id": 99, "category_id": 1, "bbox": [0, 0, 1, 1], "score": 0.1}]))
     with pytest.raises(ValueError, match="do not correspond"):
         MeanAveragePrecision.coco_to_tm(str(tmp_path / "bad.json"), str(tmp_path / "gt.json"))
-    with pytest.raises(NotImplementedError, match="bbox"):
+    with pytest.raises(KeyError, match="segmentation"):  # these annotations carry boxes only (segm json: tests/test_rle.py)
         MeanAveragePrecision.coco_to_tm(str(tmp_path / "dt.json"), str(tmp_path / "gt.json"), iou_type="segm")
     with pytest.raises(ValueError, match="iou_type"):
         MeanAveragePrecision.coco_to_tm(str(tmp_path / "dt.json"), str(tmp_path / "gt.json"), iou_type="boxes")

@@ -229,5 +229,39 @@ def test_input_checks():
     m.update([dict(ok, scores=torch.zeros(1, device=DEV))], [dict(masks=torch.zeros((1, 5, 4), dtype=torch.bool, device=DEV), labels=ok["labels"])])
     with pytest.raises(ValueError, match="same height and width"):
         m.compute()
-    with pytest.raises(NotImplementedError):
-        MeanAveragePrecision(iou_type="segm").tm_to_coco("x")
+
+
+@pytest.mark.parametrize("iou_type", ["segm", ("bbox", "segm")])
+def test_coco_json_round_trip(tmp_path, iou_type):
+    """`tm_to_coco` writes the cached masks as compressed run-length codes, `coco_to_tm` reads them back: a second metric fed
+    from the files computes the very same result; the files follow the reference's layout (:867-958)."""
+    import json
+
+    from metrics_b200.detection import MeanAveragePrecision
+    from metrics_b200.detection.rle import segmentation_to_mask
+
+    preds, target = synth_masks(seed=8, n_img=6, n_gt=3, n_det=5, n_cls=3, crowd_frac=0.3, with_boxes=True)
+    h2, w2 = preds[2]["masks"].shape[1:]  # one image without any detection (images without ground truth are not in the files)
+    preds[2] = dict(masks=torch.zeros((0, h2, w2), dtype=torch.bool), scores=torch.zeros(0), labels=torch.zeros(0, dtype=torch.long),
+                    boxes=torch.zeros((0, 4)))
+    m = MeanAveragePrecision(iou_type=iou_type, box_format="xywh").to(DEV)
+    m.update(_to_dev(preds), _to_dev(target))
+    want = m.compute()
+    name = str(tmp_path / "segm_io")
+    m.tm_to_coco(name)
+    gt_file, dt_file = json.load(open(name + "_target.json")), json.load(open(name + "_preds.json"))
+    ann = gt_file["annotations"][0]
+    assert set(ann) >= {"id", "image_id", "area", "category_id", "iscrowd", "segmentation"} and ann["id"] == 1
+    assert ("bbox" in ann) == (iou_type != "segm") and ("area_segm" in ann) == (iou_type != "segm")
+    assert isinstance(ann["segmentation"]["counts"], str) and ann["segmentation"]["size"] == list(target[0]["masks"].shape[1:])
+    first = 0
+    np.testing.assert_array_equal(segmentation_to_mask(ann["segmentation"]).astype(bool), target[first]["masks"][0].numpy())
+    assert ann["area"] == int(target[first]["masks"][0].sum())  # no `area` given: the mask area (reference :923-925)
+    assert gt_file["images"][first]["height"] == target[first]["masks"].shape[1] and "score" in dt_file[0]
+    p2, t2 = MeanAveragePrecision.coco_to_tm(name + "_preds.json", name + "_target.json", iou_type=iou_type)
+    assert p2[0]["masks"].dtype == torch.uint8 and len(p2) == 6 and p2[2]["masks"].numel() == 0
+    m2 = MeanAveragePrecision(iou_type=iou_type, box_format="xywh").to(DEV)
+    m2.update(_to_dev(p2), _to_dev(t2))
+    got = m2.compute()
+    for k in want:
+        np.testing.assert_allclose(got[k].cpu().numpy(), want[k].cpu().numpy(), rtol=1e-6, atol=1e-7, err_msg=k)
