@@ -110,18 +110,12 @@ def mask_iou(dt: np.ndarray, gt: np.ndarray, iscrowd: np.ndarray) -> np.ndarray:
     return out
 
 
-def _evaluate_img(dt_boxes, dt_scores, gt_boxes, gt_crowd, gt_area, iou_thrs, area_rng, max_det, masks=False):
-    """COCOeval.computeIoU + evaluateImg for one (image, category, area range).  Returns None when both lists are empty.
-    `masks`: dt_boxes / gt_boxes are boolean instance masks [n, H, W] (iouType "segm")."""
-    if len(dt_scores) == 0 and len(gt_boxes) == 0:
-        return None
-    dt_order = np.argsort(-dt_scores, kind="mergesort")[:max_det]
-    dt_boxes, dt_scores = dt_boxes[dt_order], dt_scores[dt_order]
-    gt_ig = np.array([bool(c) or (a < area_rng[0] or a > area_rng[1]) for c, a in zip(gt_crowd, gt_area)], dtype=bool)
-    gt_order = np.argsort(gt_ig, kind="mergesort")
-    gt_boxes, gt_crowd, gt_ig = gt_boxes[gt_order], gt_crowd[gt_order], gt_ig[gt_order]
-    T, G, D = len(iou_thrs), len(gt_boxes), len(dt_scores)
-    ious = (mask_iou if masks else bb_iou)(dt_boxes, gt_boxes, gt_crowd) if D and G else np.zeros((D, G))
+def match_detections(ious, gt_crowd, gt_ig, iou_thrs):
+    """The greedy matching loop of COCOeval.evaluateImg: `ious` [D, G] with the detections in descending-score order and the
+    ground truths with the ignored ones last.  Returns dtm [T, D] (index + 1 of the matched ground truth, 0 = none) and the
+    "matched to an ignored ground truth" flags [T, D]."""
+    D, G = ious.shape
+    T = len(iou_thrs)
     gtm = np.zeros((T, G), dtype=np.int64)
     dtm = np.zeros((T, D), dtype=np.int64)
     dt_ig = np.zeros((T, D), dtype=bool)
@@ -144,6 +138,22 @@ def _evaluate_img(dt_boxes, dt_scores, gt_boxes, gt_crowd, gt_area, iou_thrs, ar
                 dt_ig[ti, di] = gt_ig[m]
                 dtm[ti, di] = m + 1
                 gtm[ti, m] = di + 1
+    return dtm, dt_ig
+
+
+def _evaluate_img(dt_boxes, dt_scores, gt_boxes, gt_crowd, gt_area, iou_thrs, area_rng, max_det, masks=False):
+    """COCOeval.computeIoU + evaluateImg for one (image, category, area range).  Returns None when both lists are empty.
+    `masks`: dt_boxes / gt_boxes are boolean instance masks [n, H, W] (iouType "segm")."""
+    if len(dt_scores) == 0 and len(gt_boxes) == 0:
+        return None
+    dt_order = np.argsort(-dt_scores, kind="mergesort")[:max_det]
+    dt_boxes, dt_scores = dt_boxes[dt_order], dt_scores[dt_order]
+    gt_ig = np.array([bool(c) or (a < area_rng[0] or a > area_rng[1]) for c, a in zip(gt_crowd, gt_area)], dtype=bool)
+    gt_order = np.argsort(gt_ig, kind="mergesort")
+    gt_boxes, gt_crowd, gt_ig = gt_boxes[gt_order], gt_crowd[gt_order], gt_ig[gt_order]
+    T, G, D = len(iou_thrs), len(gt_boxes), len(dt_scores)
+    ious = (mask_iou if masks else bb_iou)(dt_boxes, gt_boxes, gt_crowd) if D and G else np.zeros((D, G))
+    dtm, dt_ig = match_detections(ious, gt_crowd, gt_ig, iou_thrs)
     if masks:  # detection/mean_ap.py:923-924: the detection's "area" is its mask area
         dt_area = dt_boxes.sum(axis=(1, 2)).astype(np.float64) if D else np.zeros(0)
     else:
@@ -151,6 +161,26 @@ def _evaluate_img(dt_boxes, dt_scores, gt_boxes, gt_crowd, gt_area, iou_thrs, ar
     out_of_range = (dt_area < area_rng[0]) | (dt_area > area_rng[1])
     dt_ig = dt_ig | ((dtm == 0) & out_of_range[None, :])
     return {"dtm": dtm, "dt_ig": dt_ig, "scores": dt_scores, "gt_ig": gt_ig}
+
+
+def sample_pr_curve(tp, fp, sorted_scores, npig, rec_thrs):
+    """The per-threshold tail of COCOeval.accumulate: cumulative TP / FP counts of the score-sorted detections -> (final
+    recall, precision envelope sampled at the recall thresholds, the scores at those samples)."""
+    R, nd = len(rec_thrs), len(tp)
+    rc = tp / npig
+    pr = tp / (fp + tp + EPS)
+    q = np.zeros(R)
+    ss = np.zeros(R)
+    for i in range(nd - 1, 0, -1):
+        if pr[i] > pr[i - 1]:
+            pr[i - 1] = pr[i]
+    idx = np.searchsorted(rc, rec_thrs, side="left")
+    for ri, pi in enumerate(idx):
+        if pi >= nd:
+            break
+        q[ri] = pr[pi]
+        ss[ri] = sorted_scores[pi]
+    return (rc[-1] if nd else 0), q, ss
 
 
 def coco_evaluate(
@@ -251,24 +281,8 @@ def coco_evaluate(
                     tp_sum = np.cumsum(tps, axis=1).astype(np.float64)
                     fp_sum = np.cumsum(fps, axis=1).astype(np.float64)
                     for t in range(T):
-                        tp, fp = tp_sum[t], fp_sum[t]
-                        nd = len(tp)
-                        rc = tp / npig
-                        pr = tp / (fp + tp + EPS)
-                        q = np.zeros(R)
-                        ss = np.zeros(R)
-                        recall[t, k, a, m] = rc[-1] if nd else 0
-                        for i in range(nd - 1, 0, -1):
-                            if pr[i] > pr[i - 1]:
-                                pr[i - 1] = pr[i]
-                        idx = np.searchsorted(rc, rec_thrs, side="left")
-                        for ri, pi in enumerate(idx):
-                            if pi >= nd:
-                                break
-                            q[ri] = pr[pi]
-                            ss[ri] = sorted_scores[pi]
-                        precision[t, :, k, a, m] = q
-                        scores[t, :, k, a, m] = ss
+                        recall[t, k, a, m], precision[t, :, k, a, m], scores[t, :, k, a, m] = sample_pr_curve(
+                            tp_sum[t], fp_sum[t], sorted_scores, npig, rec_thrs)
 
         # ---- summarize (COCOeval.summarize / _summarize) ----
         def summ(ap: bool, iou_thr=None, area=0, mdet=M - 1):

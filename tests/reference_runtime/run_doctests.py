@@ -24,7 +24,7 @@ IN_SCOPE = {
                        "precision_fixed_recall", "precision_recall", "precision_recall_curve", "recall_fixed_precision", "roc",
                        "sensitivity_specificity", "specificity", "specificity_sensitivity", "stat_scores"],
     "regression": ["explained_variance", "log_cosh", "log_mse", "mae", "mape", "minkowski", "mse", "r2", "rse",
-                   "symmetric_mape", "tweedie_deviance", "wmape", "csi"],
+                   "symmetric_mape", "tweedie_deviance", "wmape", "csi", "kl_divergence"],
     "wrappers": ["classwise"],
     "utilities": ["data", "compute", "distributed", "enums"],
     "detection": ["mean_ap"],

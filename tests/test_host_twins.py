@@ -35,3 +35,11 @@ def test_map_marshalling_around_the_kernel_call():
     per-image counts, iscrowd / area defaults, box formats, micro / class_metrics re-evaluation, the summary table, the
     extended summary — not the evaluation.  (The oracle-sized and full-size cases are left to the GPU run.)"""
     assert _replay(["test_map_gpu"], "-k", "not cfg4 and not synthetic") >= 5
+
+
+def test_segm_map_host_layer_on_kernel_standins():
+    """`MeanAveragePrecision` with instance masks replayed on CPU: mask state entries, the table marshalling of `_mask_tables`,
+    the match + accumulate call sequence, both IoU types with their prefixes, micro / class metrics, the extended-summary IoUs
+    and the run-length json round trip — with numpy stand-ins for K12 and the two mAP phases (built on the oracle's matching
+    loop and precision sampling, tests/reference_runtime/cpu_kernels.py)."""
+    assert _replay(["test_map_segm_gpu"]) >= 12
