@@ -541,16 +541,22 @@ def run_ours(args) -> dict:
 
     extras = {}
     if not args.no_extras:
-        extras["cfg5"] = leg_cfg5(dev, rank, world)
+        extras["cfg5"] = leg_cfg5(dev, rank, world)  # collective: every rank runs it (an error here must stay loud)
         extras["aten"] = aten_gpu_cfg2(dev, dev_batches, max(10, min(args.steps, 50)))
         if world == 1:  # the single-GPU BASELINE configs, so that the driver's N=1 line times them too
             from benchmarks import run_configs
 
             del dev_batches[2:]
             torch.cuda.empty_cache()
-            extras["cfg3"] = run_configs.leg_cfg3(dev)
-            extras["cfg3"]["aten_gpu_baseline"] = run_configs.aten_cfg3(dev)
-            extras["cfg4"] = run_configs.leg_cfg4(dev)
+
+            def secondary(name, fn):  # a failing side leg is reported in the line; it never takes the headline down
+                try:
+                    extras[name] = fn()
+                except Exception as err:  # noqa: BLE001
+                    extras[name] = {"error": f"{type(err).__name__}: {err}"}
+
+            secondary("cfg3", lambda: dict(run_configs.leg_cfg3(dev), aten_gpu_baseline=run_configs.aten_cfg3(dev)))
+            secondary("cfg4", lambda: run_configs.leg_cfg4(dev))
 
     cfg = {
         "workload": "MulticlassConfusionMatrix(num_classes=1000).update, [65536,1000] bf16 logits + int64 target"
